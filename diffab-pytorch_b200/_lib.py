@@ -1,0 +1,131 @@
+"""ctypes binding of ``csrc/libdiffab_b200.so`` (the C ABI declared in ``include/diffab_b200.h``).
+
+No fallback of any kind: ``lib()`` raises if the shared library has not been built, and every
+wrapper raises on CPU tensors, wrong dtypes or a non-zero return code (with ``dab_last_error``).
+PyTorch is used only for device memory and the current stream.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libdiffab_b200.so")
+_lib = None
+
+
+class DabSchedule(Structure):
+    _fields_ = [("T", c_int), ("alpha", c_void_p), ("alpha_bar", c_void_p), ("alpha_bar_sqrt", c_void_p),
+                ("one_minus_alpha_bar_sqrt", c_void_p), ("beta", c_void_p)]
+
+
+class DabIpaDims(Structure):
+    _fields_ = [(n, c_int) for n in ("B", "L", "D", "C", "H", "ds", "Pq", "Pv")]
+
+
+_W_FIELDS = ("w_q_scalar", "w_k_scalar", "w_v_scalar", "w_q_point", "w_k_point", "w_v_point",
+             "w_pair_bias", "gamma", "w_out", "b_out")
+
+
+class DabIpaWeights(Structure):
+    _fields_ = [(n, c_void_p) for n in _W_FIELDS]
+
+
+class DabIpaGrads(Structure):
+    _fields_ = [(n, c_void_p) for n in _W_FIELDS]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "dab_version": (c_int, []),
+    "dab_last_error": (c_char_p, []),
+    "dab_so3_exp": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "dab_so3_log": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "dab_so3_log_skew": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "dab_so3_exp_skew": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "dab_so3_scale_rot": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "dab_igso3_table": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dab_igso3_sample": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
+    "dab_forward_noise": (c_int, [POINTER(DabSchedule), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
+    "dab_seq_probs": (c_int, [POINTER(DabSchedule), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                              c_void_p, c_void_p]),
+    "dab_reverse_step": (c_int, [POINTER(DabSchedule)] + [c_void_p] * 8 + [c_int, c_int] + [c_void_p] * 8),
+    "dab_ipa_f32_workspace_bytes": (c_size_t, [POINTER(DabIpaDims), c_int]),
+    "dab_ipa_fwd_f32": (c_int, [POINTER(DabIpaDims), POINTER(DabIpaWeights), c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "dab_ipa_bwd_f32": (c_int, [POINTER(DabIpaDims), POINTER(DabIpaWeights), c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, POINTER(DabIpaGrads), c_void_p, c_size_t, c_void_p]),
+    "dab_ipa_packed_bytes": (c_size_t, [POINTER(DabIpaDims)]),
+    "dab_ipa_pack_weights": (c_int, [POINTER(DabIpaDims), POINTER(DabIpaWeights), c_void_p, c_void_p]),
+    "dab_ipa_sm100_workspace_bytes": (c_size_t, [POINTER(DabIpaDims)]),
+    "dab_ipa_fwd_sm100": (c_int, [POINTER(DabIpaDims), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_size_t, c_void_p]),
+    "dab_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+}
+
+
+def lib():
+    """Load the shared library once; fail loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C diffab-pytorch_b200/csrc`). There is no CPU or PyTorch fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().dab_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed with code {rc}: {msg}")
+
+
+def stream_ptr():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dev(t, dtype, name):
+    """Validate a tensor argument and return it contiguous (never copies to another device)."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor - diffab_pytorch_b200 has no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def mask_u8(mask, name="mask"):
+    if not mask.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor - diffab_pytorch_b200 has no CPU path")
+    return mask.to(torch.uint8).contiguous() if mask.dtype != torch.uint8 else mask.contiguous()
+
+
+class Schedule:
+    """Device copy of the five schedule tables plus the ctypes struct that points at them."""
+
+    def __init__(self, sched_cpu, device):
+        self.T = sched_cpu["beta"].numel() - 1
+        self.device = torch.device(device)
+        self.tensors = {k: v.to(device=self.device, dtype=torch.float32).contiguous() for k, v in sched_cpu.items()}
+        self.struct = DabSchedule(self.T, *(self.tensors[k].data_ptr() for k in
+                                            ("alpha", "alpha_bar", "alpha_bar_sqrt", "one_minus_alpha_bar_sqrt",
+                                             "beta")))
+
+    def ref(self):
+        return ctypes.byref(self.struct)

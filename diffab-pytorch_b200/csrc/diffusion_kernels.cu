@@ -1,0 +1,255 @@
+// Forward noising and reverse step of the three diffusers, fused per residue (sm_100a).
+//
+// Replaces /root/reference/diffab_pytorch/diffusion.py:38-294 and DiffAb._add_noise
+// (diffab_pytorch.py:778-806).  HBM-bound, ~0.3 KB per residue: one thread per residue; every
+// residue's frames/coordinates/sequence move through HBM exactly once per call.  Integer outputs
+// are bit-exact against the reference given the same injected noise: the probability expressions
+// use explicit round-to-nearest intrinsics so nvcc cannot contract them into FMAs.
+#include "common.cuh"
+
+namespace dab {
+
+struct Sched {
+  int T;
+  const float *alpha, *alpha_bar, *alpha_bar_sqrt, *one_minus_alpha_bar_sqrt, *beta;
+};
+
+__device__ __forceinline__ float kUniform() { return __fdiv_rn(1.0f, 21.0f); }  // fl32(1/21), diffusion.py:71
+
+// p_k = fl(fl(w_keep * onehot_k) + fl(w_noise * u));  diffusion.py:38-41,74-79 (mask off -> one-hot)
+__device__ __forceinline__ float mix_prob(bool hot, float w_keep, float w_noise, bool generated) {
+  float oh = hot ? 1.0f : 0.0f;
+  if (!generated) return oh;
+  return __fadd_rn(__fmul_rn(w_keep, oh), __fmul_rn(w_noise, kUniform()));
+}
+
+// argmax_k p_k / q_k with first-index tie-break == torch.multinomial(p, 1) given its Exp(1) draw q
+template <typename F>
+__device__ __forceinline__ int argmax_ratio(F prob, const float* __restrict__ q) {
+  int best = 0;
+  float best_key = -1.0f;
+#pragma unroll
+  for (int k = 0; k < DAB_VOCAB; ++k) {
+    float key = __fdiv_rn(prob(k), __ldg(q + k));
+    if (key > best_key) { best_key = key; best = k; }
+  }
+  return best;
+}
+
+__global__ void __launch_bounds__(128) forward_noise_kernel(
+    Sched sc, const int64_t* __restrict__ seq0, const float* __restrict__ x0, const float* __restrict__ O0,
+    const uint8_t* __restrict__ mask, const int64_t* __restrict__ t, int B, int L,
+    const float* __restrict__ seq_exp, const float* __restrict__ eps, const float* __restrict__ rotvec,
+    int64_t* __restrict__ seq_t, float* __restrict__ posterior, float* __restrict__ x_t, float* __restrict__ O_t) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= (int64_t)B * L) return;
+  int b = (int)(r / L);
+  int tt = (int)t[b];
+  bool gen = mask[r] != 0;
+  int s0 = (int)seq0[r];
+
+  // ---- sequence: s_t ~ Multinomial(abar_t onehot + (1-abar_t)/21)   diffusion.py:105-158
+  float ab = __ldg(sc.alpha_bar + tt);
+  float one_m_ab = __fsub_rn(1.0f, ab);
+  int st = argmax_ratio([&](int k) { return mix_prob(k == s0, ab, one_m_ab, gen); }, seq_exp + r * DAB_VOCAB);
+  seq_t[r] = st;
+  // ---- posterior q(s_{t-1} | s_t, s_0) ∝ p_single(s_t, t) * p_from_t0(s_0, t-1)   diffusion.py:168-192
+  float beta = __ldg(sc.beta + tt);
+  float one_m_beta = __fsub_rn(1.0f, beta);
+  int tm1 = tt - 1;
+  if (tm1 < 0) tm1 += sc.T + 1;  // python negative index wrap (reference is never called with t = 0)
+  float abm = __ldg(sc.alpha_bar + tm1);
+  float one_m_abm = __fsub_rn(1.0f, abm);
+  float p[DAB_VOCAB];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < DAB_VOCAB; ++k) {
+    p[k] = __fmul_rn(mix_prob(k == st, one_m_beta, beta, gen), mix_prob(k == s0, abm, one_m_abm, gen));
+    sum = __fadd_rn(sum, p[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < DAB_VOCAB; ++k) posterior[r * DAB_VOCAB + k] = __fdiv_rn(p[k], sum);
+
+  // ---- positions: x_t = sqrt(abar) x_0 + sqrt(1-abar) eps   diffusion.py:219-231
+  float a = __ldg(sc.alpha_bar_sqrt + tt), s = __ldg(sc.one_minus_alpha_bar_sqrt + tt);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v0 = __ldg(x0 + r * 3 + c);
+    float v = __fadd_rn(__fmul_rn(a, v0), __fmul_rn(s, __ldg(eps + r * 3 + c)));
+    x_t[r * 3 + c] = gen ? v : v0;
+  }
+  // ---- orientations: O_t = scale_rot(O_0, sqrt(abar)) @ exp(rotvec)   diffusion.py:280-292
+  float R0[9], Rm[9], Rn[9], Ro[9];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) R0[c] = __ldg(O0 + r * 9 + c);
+  if (gen) {
+    float lx, ly, lz;
+    so3_log(R0, lx, ly, lz);
+    so3_exp(a * lx, a * ly, a * lz, Rm);
+    so3_exp(__ldg(rotvec + r * 3), __ldg(rotvec + r * 3 + 1), __ldg(rotvec + r * 3 + 2), Rn);
+    mat3_mul(Rm, Rn, Ro);
+#pragma unroll
+    for (int c = 0; c < 9; ++c) O_t[r * 9 + c] = Ro[c];
+  } else {
+#pragma unroll
+    for (int c = 0; c < 9; ++c) O_t[r * 9 + c] = R0[c];
+  }
+}
+
+__global__ void __launch_bounds__(128) seq_probs_kernel(Sched sc, int kind, const int64_t* __restrict__ seq,
+                                                        const int64_t* __restrict__ seq0,
+                                                        const uint8_t* __restrict__ mask,
+                                                        const int64_t* __restrict__ t, int B, int L,
+                                                        float* __restrict__ out) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= (int64_t)B * L) return;
+  int b = (int)(r / L);
+  int tt = (int)t[b];
+  bool gen = mask[r] != 0;
+  int s = (int)seq[r];
+  if (kind == 0) {  // forward_prob_single_step
+    float beta = __ldg(sc.beta + tt);
+    for (int k = 0; k < DAB_VOCAB; ++k) out[r * DAB_VOCAB + k] = mix_prob(k == s, __fsub_rn(1.0f, beta), beta, gen);
+  } else if (kind == 1) {  // forward_prob_from_t0
+    float ab = __ldg(sc.alpha_bar + tt);
+    for (int k = 0; k < DAB_VOCAB; ++k) out[r * DAB_VOCAB + k] = mix_prob(k == s, ab, __fsub_rn(1.0f, ab), gen);
+  } else {  // posterior_single_step
+    int s0 = (int)seq0[r];
+    float beta = __ldg(sc.beta + tt);
+    int tm1 = tt - 1;
+    if (tm1 < 0) tm1 += sc.T + 1;
+    float abm = __ldg(sc.alpha_bar + tm1);
+    float p[DAB_VOCAB];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < DAB_VOCAB; ++k) {
+      p[k] = __fmul_rn(mix_prob(k == s, __fsub_rn(1.0f, beta), beta, gen),
+                       mix_prob(k == s0, abm, __fsub_rn(1.0f, abm), gen));
+      sum = __fadd_rn(sum, p[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < DAB_VOCAB; ++k) out[r * DAB_VOCAB + k] = __fdiv_rn(p[k], sum);
+  }
+}
+
+// Reverse step; composition fixed by oracle/sampler.py (the reference has none).
+__global__ void __launch_bounds__(128) reverse_step_kernel(
+    Sched sc, const int64_t* seq_t, const float* x_t, const float* O_t,  // may alias the outputs (in-place)
+    const float* __restrict__ eps_theta, const float* __restrict__ v_theta, const float* __restrict__ seq_post,
+    const uint8_t* __restrict__ mask, const int64_t* __restrict__ t, int B, int L,
+    const float* __restrict__ seq_exp, const float* __restrict__ z, const float* __restrict__ rotvec,
+    int64_t* seq_out, float* x_out, float* O_out, float* O0_out) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= (int64_t)B * L) return;
+  int b = (int)(r / L);
+  int tt = (int)t[b];
+  bool gen = mask[r] != 0;
+  bool noisy = tt > 1;
+
+  // sequence
+  int64_t s_old = seq_t[r];
+  if (gen) {
+    const float* p = seq_post + r * DAB_VOCAB;
+    seq_out[r] = argmax_ratio([&](int k) { return __ldg(p + k); }, seq_exp + r * DAB_VOCAB);
+  } else {
+    seq_out[r] = s_old;
+  }
+  // positions: (x_t - beta/sqrt(1-abar) eps_theta) * (1/sqrt(alpha)) + sqrt(beta) z
+  float beta = __ldg(sc.beta + tt);
+  float c_eps = __fdiv_rn(beta, __ldg(sc.one_minus_alpha_bar_sqrt + tt));
+  float inv_sa = __fdiv_rn(1.0f, __fsqrt_rn(__ldg(sc.alpha + tt)));
+  float sig = noisy ? __fsqrt_rn(beta) : 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float xo = x_t[r * 3 + c];
+    float v = __fadd_rn(__fmul_rn(__fsub_rn(xo, __fmul_rn(c_eps, __ldg(eps_theta + r * 3 + c))), inv_sa),
+                        __fmul_rn(sig, __ldg(z + r * 3 + c)));
+    x_out[r * 3 + c] = gen ? v : xo;
+  }
+  // orientations: O0 = O_t @ exp(v_theta)  (Denoiser tail, diffab_pytorch.py:594-596); O' = O0 @ exp(rotvec)
+  float Rt[9], Re[9], R0[9];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) Rt[c] = O_t[r * 9 + c];
+  so3_exp(__ldg(v_theta + r * 3), __ldg(v_theta + r * 3 + 1), __ldg(v_theta + r * 3 + 2), Re);
+  mat3_mul(Rt, Re, R0);
+  if (O0_out) {
+#pragma unroll
+    for (int c = 0; c < 9; ++c) O0_out[r * 9 + c] = R0[c];
+  }
+  if (gen) {
+    if (noisy) {
+      float Rn[9], Ro[9];
+      so3_exp(__ldg(rotvec + r * 3), __ldg(rotvec + r * 3 + 1), __ldg(rotvec + r * 3 + 2), Rn);
+      mat3_mul(R0, Rn, Ro);
+#pragma unroll
+      for (int c = 0; c < 9; ++c) O_out[r * 9 + c] = Ro[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) O_out[r * 9 + c] = R0[c];
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 9; ++c) O_out[r * 9 + c] = Rt[c];
+  }
+}
+
+static int check_sched(const DabSchedule* s, Sched& out, const char* name) {
+  DAB_REQUIRE(s && s->alpha && s->alpha_bar && s->alpha_bar_sqrt && s->one_minus_alpha_bar_sqrt && s->beta && s->T > 0,
+              DAB_EINVAL, "%s: incomplete schedule", name);
+  out = Sched{s->T, s->alpha, s->alpha_bar, s->alpha_bar_sqrt, s->one_minus_alpha_bar_sqrt, s->beta};
+  return DAB_OK;
+}
+
+}  // namespace dab
+
+using namespace dab;
+
+extern "C" {
+
+int dab_forward_noise(const DabSchedule* sched, const int64_t* seq0, const float* x0, const float* O0,
+                      const uint8_t* mask, const int64_t* t, int B, int L, const float* seq_exp, const float* eps,
+                      const float* rotvec, int64_t* seq_t, float* posterior, float* x_t, float* O_t, void* stream) {
+  Sched sc;
+  if (int rc = check_sched(sched, sc, "dab_forward_noise")) return rc;
+  DAB_REQUIRE(B >= 0 && L >= 0, DAB_EINVAL, "dab_forward_noise: negative size");
+  if ((int64_t)B * L == 0) return DAB_OK;
+  DAB_REQUIRE(seq0 && x0 && O0 && mask && t && seq_exp && eps && rotvec && seq_t && posterior && x_t && O_t,
+              DAB_EINVAL, "dab_forward_noise: null pointer");
+  int64_t n = (int64_t)B * L;
+  forward_noise_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      sc, seq0, x0, O0, mask, t, B, L, seq_exp, eps, rotvec, seq_t, posterior, x_t, O_t);
+  return check_launch("dab_forward_noise");
+}
+
+int dab_seq_probs(const DabSchedule* sched, int kind, const int64_t* seq, const int64_t* seq0, const uint8_t* mask,
+                  const int64_t* t, int B, int L, float* out, void* stream) {
+  Sched sc;
+  if (int rc = check_sched(sched, sc, "dab_seq_probs")) return rc;
+  DAB_REQUIRE(kind >= 0 && kind <= 2, DAB_EINVAL, "dab_seq_probs: kind must be 0, 1 or 2");
+  DAB_REQUIRE(B >= 0 && L >= 0, DAB_EINVAL, "dab_seq_probs: negative size");
+  if ((int64_t)B * L == 0) return DAB_OK;
+  DAB_REQUIRE(seq && mask && t && out && (kind != 2 || seq0), DAB_EINVAL, "dab_seq_probs: null pointer");
+  int64_t n = (int64_t)B * L;
+  seq_probs_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(sc, kind, seq, seq0, mask, t, B, L, out);
+  return check_launch("dab_seq_probs");
+}
+
+int dab_reverse_step(const DabSchedule* sched, const int64_t* seq_t, const float* x_t, const float* O_t,
+                     const float* eps_theta, const float* v_theta, const float* seq_post, const uint8_t* mask,
+                     const int64_t* t, int B, int L, const float* seq_exp, const float* z, const float* rotvec,
+                     int64_t* seq_out, float* x_out, float* O_out, float* O0_out, void* stream) {
+  Sched sc;
+  if (int rc = check_sched(sched, sc, "dab_reverse_step")) return rc;
+  DAB_REQUIRE(B >= 0 && L >= 0, DAB_EINVAL, "dab_reverse_step: negative size");
+  if ((int64_t)B * L == 0) return DAB_OK;
+  DAB_REQUIRE(seq_t && x_t && O_t && eps_theta && v_theta && seq_post && mask && t && seq_exp && z && rotvec &&
+                  seq_out && x_out && O_out,
+              DAB_EINVAL, "dab_reverse_step: null pointer");
+  int64_t n = (int64_t)B * L;
+  reverse_step_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      sc, seq_t, x_t, O_t, eps_theta, v_theta, seq_post, mask, t, B, L, seq_exp, z, rotvec, seq_out, x_out, O_out,
+      O0_out);
+  return check_launch("dab_reverse_step");
+}
+
+}  // extern "C"

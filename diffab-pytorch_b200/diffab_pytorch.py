@@ -1,0 +1,634 @@
+"""``DiffAb`` and its epsilon network on the GPU - mirror of ``diffab_pytorch/diffab_pytorch.py``.
+
+Drop-in boundary: same class names, constructor signatures, method names, return
+dict keys and the same 106 state-dict keys/shapes as the reference, so a reference checkpoint
+loads with ``load_state_dict``.  What runs where:
+
+* per-timestep hot path - IPA layers, SO(3) maps, forward noising, reverse step: hand-written
+  sm_100a kernels behind the C ABI (``csrc/``);
+* context encoders (``ResidueEmbedding``, ``PairEmbedding``; once per patch, out of scope per
+  SURVEY §2) and the small dense glue of ``Denoiser`` (embedding + MLP heads, "next" row N1): PyTorch
+  modules on the GPU (library GEMMs);
+* ``sample()`` - an empty stub in the reference (``diffab_pytorch.py:770-776``) - is implemented
+  here following oracle/sampler.py.
+
+Not a LightningModule: ``pytorch_lightning`` is not a dependency; ``training_step`` /
+``validation_step`` / ``configure_optimizers`` keep their names and return values.
+"""
+import ctypes
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from . import diffusion as _diffusion
+from . import so3 as _so3
+from ._lib import ptr
+from .diffusion import (CoordinateDiffuser, OrientationDiffuser, SequenceDiffuser,  # noqa: F401
+                        cosine_variance_schedule)
+from .so3 import vector_to_rotation_matrix
+
+CA_IDX = 1     # protstruc.general.ATOM.CA (diffab_pytorch.py:110,249,820)
+AA_UNK = 20    # protstruc.general.AA.UNK  (diffab_pytorch.py:115,273; assumed)
+
+
+# =============================================================================================
+# Context encoders (out of the hot path; forward-identical PyTorch restatements)
+# =============================================================================================
+class AngularEncoding(nn.Module):
+    """diffab_pytorch.py:20-54: [x, sin(f x), cos(f x)] for f in (1..n, 1/1..1/n)."""
+
+    def __init__(self, num_funcs=3):
+        super().__init__()
+        self.num_funcs = num_funcs
+        self.freq_bands = torch.tensor([float(i + 1) for i in range(num_funcs)] +
+                                       [1.0 / (i + 1) for i in range(num_funcs)])
+
+    def get_output_dimension(self, d_in):
+        return d_in * (4 * self.num_funcs + 1)
+
+    def forward(self, x):
+        f = self.freq_bands.to(x.device)
+        x = x.unsqueeze(-1)
+        return torch.cat([x, torch.sin(f * x), torch.cos(f * x)], dim=-1).flatten(-2)
+
+
+def _mlp(dims, final_relu=False):
+    layers = []
+    for i in range(len(dims) - 1):
+        layers.append(nn.Linear(dims[i], dims[i + 1]))
+        if i + 2 < len(dims) or final_relu:
+            layers.append(nn.ReLU())
+    return nn.Sequential(*layers)
+
+
+class ResidueEmbedding(nn.Module):
+    """diffab_pytorch.py:57-183."""
+
+    def __init__(self, max_n_atoms_per_residue, d_feat):
+        super().__init__()
+        self.max_n_aa_types = 21
+        self.max_n_atoms_per_residue = max_n_atoms_per_residue
+        self.amino_acid_type_embedding = nn.Embedding(self.max_n_aa_types, d_feat)
+        self.dihedral_embedding = AngularEncoding(num_funcs=3)
+        self.chain_embedding = nn.Embedding(10, d_feat, padding_idx=0)
+        d_coord = self.max_n_aa_types * max_n_atoms_per_residue * 3
+        d_dihedral = self.dihedral_embedding.get_output_dimension(3)
+        self.mlp = _mlp([d_feat + d_coord + d_dihedral + d_feat, d_feat * 2, d_feat, d_feat, d_feat])
+
+    def forward(self, seq_idx, xyz, orientation, dihedrals, chain_idx, atom_mask, structure_context_mask=None,
+                sequence_context_mask=None):
+        B, L = seq_idx.shape
+        A = self.max_n_atoms_per_residue
+        if sequence_context_mask is not None:
+            seq_idx = torch.where(sequence_context_mask.bool(), seq_idx, torch.full_like(seq_idx, AA_UNK))
+        aa = self.amino_acid_type_embedding(seq_idx)
+        rel = xyz - xyz[:, :, CA_IDX:CA_IDX + 1, :]
+        local = torch.einsum("blji,blaj->blai", orientation, rel) * atom_mask[..., None]   # O^T (x - x_CA)
+        # place the (A,3) local block in the slot of the residue's amino-acid type, zeros elsewhere
+        coord = torch.zeros(B, L, self.max_n_aa_types, A * 3, device=xyz.device, dtype=local.dtype)
+        coord.scatter_(2, seq_idx[:, :, None, None].expand(B, L, 1, A * 3), local.reshape(B, L, 1, A * 3))
+        coord = coord.reshape(B, L, -1)
+        dih = self.dihedral_embedding(dihedrals)
+        if structure_context_mask is not None:
+            sm = structure_context_mask
+            coord = coord * sm[:, :, None]
+            dih = dih * (sm & torch.roll(sm, shifts=-1, dims=1))[:, :, None]
+        chain = self.chain_embedding(chain_idx)
+        return self.mlp(torch.cat([aa, coord, dih, chain], dim=-1))
+
+
+class PairEmbedding(nn.Module):
+    """diffab_pytorch.py:186-312.  The two in-place ``distmat *= mask`` lines (:296,:301) do not
+    affect the forward result (``dist_feat`` is computed before them) and break autograd in the
+    reference; they are dropped, which is forward-identical."""
+
+    def __init__(self, max_n_atoms_per_residue, d_feat, max_dist_to_consider=32):
+        super().__init__()
+        self.d_feat = d_feat
+        self.max_dist_to_consider = max_dist_to_consider
+        self.max_n_aa_types = 21
+        self.aa_pair_type_embedding = nn.Embedding(self.max_n_aa_types**2, d_feat)
+        self.relpos_embedding = nn.Embedding(2 * max_dist_to_consider + 1, d_feat)
+        self.pair2distcoef = nn.Embedding(self.max_n_aa_types**2, max_n_atoms_per_residue**2)
+        nn.init.zeros_(self.pair2distcoef.weight)
+        self.distance_embedding = _mlp([max_n_atoms_per_residue**2, d_feat, d_feat], final_relu=True)
+        self.dihedral_embedding = AngularEncoding(2)
+        d_dihedral = self.dihedral_embedding.get_output_dimension(2)
+        self.mlp = _mlp([3 * d_feat + d_dihedral, d_feat, d_feat, d_feat])
+
+    def forward(self, seq_idx, distmat, dihedrals, residue_idx, chain_idx, atom_mask, structure_context_mask,
+                sequence_context_mask):
+        B, L = seq_idx.shape
+        am = atom_mask
+        atom_pair = (am[:, :, None, :, None] * am[:, None, :, None, :]).flatten(-2)
+        res_mask = am[:, :, CA_IDX]
+        res_pair = res_mask[:, :, None] * res_mask[:, None, :]
+        if sequence_context_mask is not None:
+            seq_idx = torch.where(sequence_context_mask.bool(), seq_idx, torch.full_like(seq_idx, AA_UNK))
+        pair_type = seq_idx[:, :, None] * self.max_n_aa_types + seq_idx[:, None, :]
+        f_type = self.aa_pair_type_embedding(pair_type)
+        # note: the reference multiplies by the PRODUCT of chain indices, not an equality mask (:279,285)
+        chain_prod = chain_idx[:, :, None] * chain_idx[:, None, :]
+        rel = (residue_idx[:, :, None] - residue_idx[:, None, :]).clamp(-self.max_dist_to_consider,
+                                                                         self.max_dist_to_consider)
+        f_rel = self.relpos_embedding(rel + self.max_dist_to_consider) * chain_prod[..., None]
+        coef = F.softplus(self.pair2distcoef(pair_type))
+        d = distmat.flatten(-2)
+        f_dist = self.distance_embedding(torch.exp(-1 * coef * d**2) * atom_pair)
+        f_dih = self.dihedral_embedding(dihedrals)
+        return self.mlp(torch.cat([f_type, f_rel, f_dist, f_dih], dim=-1)) * res_pair[..., None]
+
+
+# =============================================================================================
+# Invariant point attention
+# =============================================================================================
+def euclidean_transform(x, r, t):
+    """diffab_pytorch.py:315-324: (b,n,l,p,3) local points -> global, row vectors: x @ R + t."""
+    return torch.einsum("bnlpk,blkc->bnlpc", x, r) + t[:, None, :, None, :]
+
+
+def inverse_euclidean_transform(x, r, t):
+    """diffab_pytorch.py:327-336: (x - t) @ R^T."""
+    return torch.einsum("bnlpk,blck->bnlpc", x - t[:, None, :, None, :], r)
+
+
+def _ipa_structs(layer, B, L):
+    dims = _lib.DabIpaDims(B, L, layer.d_residue_emb, layer.d_pair_emb, layer.n_head, layer.d_scalar_per_head,
+                           layer.n_query_point_per_head, layer.n_value_point_per_head)
+    return dims
+
+
+def _weights_struct(tensors):
+    return _lib.DabIpaWeights(*(t.data_ptr() for t in tensors))
+
+
+class _IpaFunction(torch.autograd.Function):
+    """fp32 IPA layer: ``dab_ipa_fwd_f32`` / ``dab_ipa_bwd_f32``."""
+
+    @staticmethod
+    def forward(ctx, layer, x, e, r, t, *weights):
+        x = _lib.dev(x, torch.float32, "x")
+        e = _lib.dev(e, torch.float32, "e")
+        r = _lib.dev(r, torch.float32, "r")
+        t = _lib.dev(t, torch.float32, "t")
+        weights = tuple(_lib.dev(w.detach(), torch.float32, "weight") for w in weights)
+        B, L, D = x.shape
+        if e.shape != (B, L, L, layer.d_pair_emb) or r.shape != (B, L, 3, 3) or t.shape != (B, L, 3):
+            raise ValueError(f"IPA shape mismatch: x {tuple(x.shape)} e {tuple(e.shape)} r {tuple(r.shape)} t {tuple(t.shape)}")
+        dims = _ipa_structs(layer, B, L)
+        need_bwd = any(ctx.needs_input_grad)
+        lib = _lib.lib()
+        nbytes = lib.dab_ipa_f32_workspace_bytes(ctypes.byref(dims), 1 if need_bwd else 0)
+        ws = torch.empty(max(nbytes, 16) // 4, device=x.device, dtype=torch.float32)
+        y = torch.empty(B, L, D, device=x.device, dtype=torch.float32)
+        wstruct = _weights_struct(weights)
+        _lib.check(lib.dab_ipa_fwd_f32(ctypes.byref(dims), ctypes.byref(wstruct), ptr(x), ptr(e), ptr(r), ptr(t),
+                                       ptr(y), ptr(ws), ws.numel() * 4, int(need_bwd), _lib.stream_ptr()),
+                   "dab_ipa_fwd_f32")
+        if need_bwd:
+            ctx.save_for_backward(x, e, r, t, ws, *weights)
+            ctx.layer = layer
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, e, r, t, ws, *weights = ctx.saved_tensors
+        layer = ctx.layer
+        if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
+            raise NotImplementedError("gradients w.r.t. the frames (r, t) are not provided: in DiffAb they are the "
+                                      "noised frames and carry no gradient (diffab_pytorch.py:824-854)")
+        B, L, D = x.shape
+        dims = _ipa_structs(layer, B, L)
+        dy = _lib.dev(dy, torch.float32, "dy")
+        dx = torch.empty_like(x)
+        de = torch.empty_like(e)
+        grads = [torch.zeros_like(w) for w in weights]
+        wstruct = _weights_struct(weights)
+        gstruct = _lib.DabIpaGrads(*(g.data_ptr() for g in grads))
+        _lib.check(_lib.lib().dab_ipa_bwd_f32(ctypes.byref(dims), ctypes.byref(wstruct), ptr(x), ptr(e), ptr(r),
+                                              ptr(t), ptr(dy), ptr(dx), ptr(de), ctypes.byref(gstruct), ptr(ws),
+                                              ws.numel() * 4, _lib.stream_ptr()), "dab_ipa_bwd_f32")
+        return (None, dx, de, None, None, *grads)
+
+
+class InvariantPointAttentionLayer(nn.Module):
+    """diffab_pytorch.py:339-465.  Parameters keep the reference's names and shapes."""
+
+    def __init__(self, d_residue_emb, d_pair_emb, d_scalar_per_head=16, n_query_point_per_head=4,
+                 n_value_point_per_head=4, n_head=8, use_pair_bias=True):
+        super().__init__()
+        if not use_pair_bias:
+            raise NotImplementedError("use_pair_bias=False is never constructed by the reference model "
+                                      "(diffab_pytorch.py:482-489) and has no kernel here")
+        self.d_residue_emb, self.d_pair_emb = d_residue_emb, d_pair_emb
+        self.d_scalar_per_head = d_scalar_per_head
+        self.n_query_point_per_head, self.n_value_point_per_head = n_query_point_per_head, n_value_point_per_head
+        self.n_head = n_head
+        self.use_pair_bias = use_pair_bias
+        d_scalar = d_scalar_per_head * n_head
+        self.to_q_scalar = nn.Linear(d_residue_emb, d_scalar, bias=False)
+        self.to_k_scalar = nn.Linear(d_residue_emb, d_scalar, bias=False)
+        self.to_v_scalar = nn.Linear(d_residue_emb, d_scalar, bias=False)
+        self.scale_scalar = d_scalar_per_head**-0.5
+        self.to_pair_bias = nn.Linear(d_pair_emb, n_head, bias=False)
+        d_query_point = n_query_point_per_head * 3 * n_head
+        d_value_point = n_value_point_per_head * 3 * n_head
+        self.to_q_point = nn.Linear(d_residue_emb, d_query_point, bias=False)
+        self.to_k_point = nn.Linear(d_residue_emb, d_query_point, bias=False)
+        self.to_v_point = nn.Linear(d_residue_emb, d_value_point, bias=False)
+        self.scale_point = (4.5 * n_query_point_per_head) ** -0.5
+        self.gamma = nn.Parameter(torch.log(torch.exp(torch.ones(n_head)) - 1.0))  # used raw (:373,429)
+        self.to_out = nn.Linear(d_scalar + d_pair_emb * n_head + d_value_point + n_value_point_per_head * n_head,
+                                d_residue_emb)
+        self.num_independent_logits = 3
+        self.scale_total = self.num_independent_logits**-0.5
+        self._packed = None  # (version key, packed weights) for the sm_100a fast path
+
+    def _weights(self):
+        return (self.to_q_scalar.weight, self.to_k_scalar.weight, self.to_v_scalar.weight, self.to_q_point.weight,
+                self.to_k_point.weight, self.to_v_point.weight, self.to_pair_bias.weight, self.gamma,
+                self.to_out.weight, self.to_out.bias)
+
+    def forward(self, x, e, r, t):
+        if e.dtype == torch.bfloat16:
+            return self.forward_fast(x, e, r, t)
+        return _IpaFunction.apply(self, x, e, r, t, *self._weights())
+
+    # ---- sm_100a fast path (inference; train.py configuration only) ----
+    def fast_path_supported(self, L):
+        return (L == 128 and self.d_residue_emb == 128 and self.d_pair_emb == 64 and self.n_head == 8 and
+                self.d_scalar_per_head == 32 and self.n_query_point_per_head == 8 and
+                self.n_value_point_per_head == 8)
+
+    def _packed_weights(self, dims):
+        ws = self._weights()
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        if self._packed is None or self._packed[0] != key:
+            lib = _lib.lib()
+            nbytes = lib.dab_ipa_packed_bytes(ctypes.byref(dims))
+            buf = torch.empty(max(nbytes, 16), device=ws[0].device, dtype=torch.uint8)
+            wstruct = _weights_struct([_lib.dev(w.detach(), torch.float32, "weight") for w in ws])
+            _lib.check(lib.dab_ipa_pack_weights(ctypes.byref(dims), ctypes.byref(wstruct), ptr(buf), _lib.stream_ptr()),
+                       "dab_ipa_pack_weights")
+            self._packed = (key, buf)
+        return self._packed[1]
+
+    def forward_fast(self, x, e_bf16, r, t):
+        if torch.is_grad_enabled() and (x.requires_grad or any(w.requires_grad for w in self._weights())):
+            raise RuntimeError("the bf16 tensor-core IPA path is inference-only; run under torch.no_grad()")
+        x = _lib.dev(x, torch.float32, "x")
+        e = _lib.dev(e_bf16, torch.bfloat16, "e")
+        r = _lib.dev(r, torch.float32, "r")
+        t = _lib.dev(t, torch.float32, "t")
+        B, L, D = x.shape
+        if not self.fast_path_supported(L):
+            raise RuntimeError("bf16 pair tensor given but the sm_100a fast path only supports the train.py "
+                               "configuration (L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8)")
+        dims = _ipa_structs(self, B, L)
+        lib = _lib.lib()
+        packed = self._packed_weights(dims)
+        nbytes = lib.dab_ipa_sm100_workspace_bytes(ctypes.byref(dims))
+        ws = torch.empty(max(nbytes, 16), device=x.device, dtype=torch.uint8)
+        y = torch.empty(B, L, D, device=x.device, dtype=torch.float32)
+        _lib.check(lib.dab_ipa_fwd_sm100(ctypes.byref(dims), ptr(packed), ptr(x), ptr(e), ptr(r), ptr(t), ptr(y),
+                                         ptr(ws), ws.numel(), _lib.stream_ptr()), "dab_ipa_fwd_sm100")
+        return y
+
+
+class InvariantPointAttentionModule(nn.Module):
+    """diffab_pytorch.py:468-498: plain chain, same (pair_emb, R, t) for every layer."""
+
+    def __init__(self, n_layers, d_residue_emb, d_pair_emb, d_scalar_per_head, n_query_point_per_head,
+                 n_value_point_per_head, n_head):
+        super().__init__()
+        self.layers = nn.ModuleList([
+            InvariantPointAttentionLayer(d_residue_emb, d_pair_emb, d_scalar_per_head, n_query_point_per_head,
+                                         n_value_point_per_head, n_head) for _ in range(n_layers)])
+
+    def forward(self, res_emb, pair_emb, orientations, translations):
+        for layer in self.layers:
+            res_emb = layer(res_emb, pair_emb, orientations, translations)
+        return res_emb
+
+
+def cast_pair_to_bf16(pair_emb):
+    """fp32 (B,L,L,C) -> bf16 once per patch (the pair tensor is constant over layers and steps)."""
+    e = _lib.dev(pair_emb, torch.float32, "pair_emb")
+    out = torch.empty(e.shape, device=e.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().dab_cast_f32_to_bf16(ptr(e), ptr(out), e.numel(), _lib.stream_ptr()), "dab_cast_f32_to_bf16")
+    return out
+
+
+class Denoiser(nn.Module):
+    """diffab_pytorch.py:501-607."""
+
+    def __init__(self, d_residue_emb, d_pair_emb, n_ipa_layers, d_scalar_per_head, n_query_point_per_head,
+                 n_value_point_per_head, n_head, aa_vocab_size):
+        super().__init__()
+        D = d_residue_emb
+        self.sequence_embedding = nn.Embedding(25, D)
+        self.to_res_emb = _mlp([2 * D, D, D])
+        self.ipa = InvariantPointAttentionModule(n_ipa_layers, D, d_pair_emb, d_scalar_per_head,
+                                                 n_query_point_per_head, n_value_point_per_head, n_head)
+        self.coordinate_denoising = _mlp([D + 3, D, D, 3])
+        self.orientation_denoising = _mlp([D + 3, D, D, 3])
+        self.sequence_denoising = _mlp([D + 3, D, D, aa_vocab_size])
+        self.sequence_denoising.append(nn.Softmax(dim=-1))
+
+    def heads(self, seq_idx_t, translations_t, orientations_t, res_context_emb, pair_context_emb, beta):
+        """Everything up to the three head outputs; returns (eps, rotvec, seq_posterior)."""
+        n_residues = seq_idx_t.shape[1]
+        h = torch.cat([res_context_emb, self.sequence_embedding(seq_idx_t)], dim=-1)
+        h = self.to_res_emb(h)
+        h = self.ipa(h, pair_context_emb, orientations_t, translations_t)
+        t_emb = torch.stack([beta, torch.sin(beta), torch.cos(beta)], dim=-1)
+        h = torch.cat([h, t_emb[:, None, :].expand(-1, n_residues, -1)], dim=-1)
+        return self.coordinate_denoising(h), self.orientation_denoising(h), self.sequence_denoising(h)
+
+    def forward(self, seq_idx_t, translations_t, orientations_t, res_context_emb, pair_context_emb, beta,
+                generation_mask=None, residue_mask=None):
+        # the two masks are accepted and unused, as in the reference (:566-567)
+        eps, v_eps, post = self.heads(seq_idx_t, translations_t, orientations_t, res_context_emb, pair_context_emb,
+                                      beta)
+        o_denoised = orientations_t @ vector_to_rotation_matrix(v_eps)   # :594-596
+        return {"translations_eps": eps, "orientations_t0": o_denoised, "seq_posterior": post}
+
+
+class OrientationLoss(nn.Module):
+    """diffab_pytorch.py:610-625: MSE(R_pred^T R_true, I)."""
+
+    def __init__(self, reduction="mean"):
+        super().__init__()
+        self.reduction = reduction
+
+    def forward(self, pred_rotmat, target_rotmat):
+        d = torch.einsum("blij,blik->bljk", pred_rotmat, target_rotmat)
+        eye = torch.eye(3, device=d.device, dtype=d.dtype).expand_as(d)
+        return F.mse_loss(d, eye, reduction=self.reduction)
+
+
+# =============================================================================================
+# DiffAb
+# =============================================================================================
+class DiffAb(nn.Module):
+    """diffab_pytorch.py:628-931.  ``device`` is where the schedules / IGSO(3) tables are built; they
+    follow ``.to()`` / ``.cuda()`` and are not part of the state dict (106 keys, as in the reference)."""
+
+    def __init__(self, d_residue_emb, d_pair_emb, n_ipa_layers, d_scalar_per_head, n_query_point_per_head,
+                 n_value_point_per_head, n_head, T=100, s=0.01, beta_max=0.999, n_atoms=15, aa_vocab_size=21,
+                 max_dist_to_consider=32, lr=1e-4, weight_decay=0.0, betas=(0.9, 0.999), device="cuda"):
+        super().__init__()
+        self.sched = cosine_variance_schedule(T=T, s=s, beta_max=beta_max)
+        self.residue_context_embedding = ResidueEmbedding(n_atoms, d_residue_emb)
+        self.pair_context_embedding = PairEmbedding(n_atoms, d_pair_emb, max_dist_to_consider)
+        self.denoiser = Denoiser(d_residue_emb, d_pair_emb, n_ipa_layers, d_scalar_per_head,
+                                 n_query_point_per_head, n_value_point_per_head, n_head, aa_vocab_size)
+        self.seq_diffuser = SequenceDiffuser(T, s, beta_max, aa_vocab_size, device=device)
+        self.coordinate_diffuser = CoordinateDiffuser(T, s, beta_max, device=device)
+        self.orientation_diffuser = OrientationDiffuser(T, s, beta_max, device=device)
+        # reverse-step IGSO(3) table at sigma = sqrt(beta_t); built lazily by sample()
+        self._so3_reverse = None
+        self.aa_loss = nn.KLDivLoss(reduction="none")
+        self.coordinate_loss = nn.MSELoss(reduction="none")
+        self.orientation_loss = OrientationLoss(reduction="none")
+        self.T, self.lr, self.weight_decay, self.betas = T, lr, weight_decay, betas
+        self._device = torch.device(device)
+        self._dsched = None
+        if self._device.type == "cuda" and torch.cuda.is_available():
+            if self._device.index is None:
+                self._device = torch.device("cuda", torch.cuda.current_device())
+            self.to(self._device)
+        # without a GPU the module can still be constructed (state-dict inspection); every op raises
+
+    # ---- device plumbing: non-buffer tables follow the module ----
+    def _apply(self, fn, *args, **kwargs):
+        super()._apply(fn, *args, **kwargs)
+        probe = fn(torch.empty(0, device=self._device))
+        if probe.device != self._device:
+            if probe.device.type != "cuda":
+                raise RuntimeError("DiffAb lives on the GPU - diffab_pytorch_b200 has no CPU path")
+            self._device = probe.device
+            self._dsched = None
+            for d in (self.seq_diffuser, self.coordinate_diffuser, self.orientation_diffuser):
+                d.to(self._device)
+            if self._so3_reverse is not None:
+                self._so3_reverse.to(self._device)
+        return self
+
+    @property
+    def dsched(self):
+        if self._dsched is None:
+            self._dsched = _lib.Schedule(self.sched, self._device)
+        return self._dsched
+
+    @property
+    def so3_reverse(self):
+        if self._so3_reverse is None:
+            self._so3_reverse = _so3.SO3(self.sched["beta"].sqrt(), sigma_threshold=0.1, n_bins=8192, num_iters=1024,
+                                         device=self._device)
+        return self._so3_reverse
+
+    # ---- reference API ----
+    def encode_context(self, seq_idx_t0, xyz_t0, orientations_t0, backbone_dihedrals, distmat, pairwise_dihedrals,
+                       atom_mask, chain_idx, residue_idx, generation_mask, residue_mask, generate_structure=True,
+                       generate_sequence=True):
+        """diffab_pytorch.py:680-724."""
+        context_mask = residue_mask & (~generation_mask)
+        structure_context_mask = context_mask if generate_structure else None
+        sequence_context_mask = context_mask if generate_sequence else None
+        res = self.residue_context_embedding(seq_idx_t0, xyz_t0, orientations_t0, backbone_dihedrals, chain_idx,
+                                             atom_mask, structure_context_mask, sequence_context_mask)
+        pair = self.pair_context_embedding(seq_idx_t0, distmat, pairwise_dihedrals, residue_idx, chain_idx, atom_mask,
+                                           structure_context_mask, sequence_context_mask)
+        return res, pair
+
+    def denoise(self, seq_idx_t, translations_t, orientations_t, res_context_emb, pair_context_emb, beta,
+                generation_mask, residue_mask) -> Dict[str, torch.Tensor]:
+        """diffab_pytorch.py:726-768."""
+        return self.denoiser(seq_idx_t, translations_t, orientations_t, res_context_emb, pair_context_emb, beta,
+                             generation_mask, residue_mask)
+
+    def _add_noise(self, seq_idx_t0, translations_t0, orientations_t0, generation_mask, t, noise=None):
+        """diffab_pytorch.py:778-806, fused (two launches).  ``noise`` = the six draws of
+        ``diffusion.draw_add_noise_tensors``; drawn on the device in that order when omitted."""
+        B, L = seq_idx_t0.shape
+        if noise is None:
+            noise = _diffusion.draw_add_noise_tensors(B, L, device=seq_idx_t0.device)
+        return _diffusion.fused_add_noise(self.dsched, self.orientation_diffuser.so3, seq_idx_t0, translations_t0,
+                                          orientations_t0, generation_mask, t, noise)
+
+    def _losses(self, denoised, noised, orientations_t0, generation_mask, residue_mask):
+        """diffab_pytorch.py:856-880."""
+        seq_loss = self.aa_loss(denoised["seq_posterior"].log(), noised["seq_posterior"])
+        translations_loss = self.coordinate_loss(denoised["translations_eps"], noised["translations_eps"])
+        orientations_loss = self.orientation_loss(denoised["orientations_t0"], orientations_t0)
+        loss_mask = generation_mask & residue_mask
+        denom = loss_mask.sum()
+        return ((seq_loss * loss_mask[..., None]).sum() / denom,
+                (translations_loss * loss_mask[..., None]).sum() / denom,
+                (orientations_loss * loss_mask[..., None, None]).sum() / denom)
+
+    def _shared_step(self, batch, batch_idx, t=None, noise=None):
+        """diffab_pytorch.py:808-880.  ``t`` / ``noise`` may be injected (tests); otherwise drawn on the
+        device in the reference's order (#1 t, then the six noising draws)."""
+        device = batch["generation_mask"].device
+        bsz = batch["generation_mask"].size(0)
+        if t is None:
+            t = torch.randint(low=1, high=self.T + 1, size=(bsz,), device=device)
+        beta = self.dsched.tensors["beta"][t]
+        seq_idx_t0 = batch["seq_idx"]
+        xyz_t0 = batch["xyz"]
+        translations_t0 = xyz_t0[:, :, CA_IDX].contiguous()
+        orientations_t0 = batch["orientations"]
+        generation_mask = batch["generation_mask"]
+        noised = self._add_noise(seq_idx_t0, translations_t0, orientations_t0, generation_mask, t, noise=noise)
+        res_context_emb, pair_context_emb = self.encode_context(
+            seq_idx_t0, xyz_t0, orientations_t0, batch["backbone_dihedrals"], batch["distmat"],
+            batch["pairwise_dihedrals"], batch["atom_mask"], batch["chain_idx"], batch["residue_idx"],
+            batch["generation_mask"], batch["residue_mask"])
+        denoised = self.denoise(noised["seq_idx_t"], noised["translations_t"], noised["orientations_t"],
+                                res_context_emb, pair_context_emb, beta, batch["generation_mask"],
+                                batch["residue_mask"])
+        return self._losses(denoised, noised, batch["orientations"], batch["generation_mask"], batch["residue_mask"])
+
+    def training_step(self, batch, batch_idx):
+        seq_loss, translations_loss, orientations_loss = self._shared_step(batch, batch_idx)
+        loss = seq_loss + translations_loss + orientations_loss
+        self.log_dict({"train/seq_loss": seq_loss, "train/translations_loss": translations_loss,
+                       "train/orientations_loss": orientations_loss, "train/loss": loss})
+        return loss
+
+    def validation_step(self, batch, batch_idx):
+        seq_loss, translations_loss, orientations_loss = self._shared_step(batch, batch_idx)
+        loss = seq_loss + translations_loss + orientations_loss
+        self.log_dict({"val/seq_loss": seq_loss, "val/translations_loss": translations_loss,
+                       "val/orientations_loss": orientations_loss, "val/loss": loss})
+        return loss
+
+    def log_dict(self, metrics, *args, **kwargs):
+        """Lightning's logging hook; here the last metrics are kept on the module."""
+        self.last_metrics = {k: v.detach() for k, v in metrics.items()}
+
+    def configure_optimizers(self):
+        return torch.optim.Adam(self.parameters(), lr=self.lr, weight_decay=self.weight_decay, betas=self.betas)
+
+    # ---- sampling (a stub in the reference, diffab_pytorch.py:770-776) ----
+    @staticmethod
+    def draw_step_noise(B, L, device, n_bins=8192, generator=None):
+        """Per-step draws in the order fixed by oracle/sampler.py."""
+        g = generator
+        return {
+            "seq_exp": torch.empty(B * L, 21, device=device).exponential_(generator=g),
+            "z": torch.randn(B, L, 3, device=device, generator=g),
+            "axis": torch.randn(B, L, 3, device=device, generator=g),
+            "hist_exp": torch.empty(B, n_bins, device=device).exponential_(generator=g),
+            "jitter": torch.rand(B, L, device=device, generator=g),
+            "gauss": torch.randn(B, L, device=device, generator=g),
+        }
+
+    @torch.no_grad()
+    def reverse_step(self, seq_idx_t, translations_t, orientations_t, res_context_emb, pair_context_emb,
+                     generation_mask, t, noise, inplace=False):
+        """One reverse-diffusion step: epsilon network + fused update kernel.  ``t`` is (B,) int64."""
+        beta = self.dsched.tensors["beta"][t]
+        eps, v_eps, post = self.denoiser.heads(seq_idx_t, translations_t, orientations_t, res_context_emb,
+                                               pair_context_emb, beta)
+        return _diffusion.fused_reverse_step(self.dsched, self.so3_reverse, seq_idx_t, translations_t,
+                                             orientations_t, eps, v_eps, post, generation_mask, t, noise,
+                                             inplace=inplace)
+
+    @torch.no_grad()
+    def sample_from_context(self, seq_idx, translations, orientations, res_context_emb, pair_context_emb,
+                            generation_mask, noises=None, generator=None, t_start=None, t_stop=1,
+                            use_cuda_graph=False):
+        """The reverse loop t_start..t_stop on resident tensors (this is what bench.py's ``value`` times).
+        ``pair_context_emb`` may be fp32 (exact path) or bf16 (tensor-core path)."""
+        T = self.T
+        t_start = T if t_start is None else t_start
+        s, x, O = seq_idx.clone(), translations.clone().contiguous(), orientations.clone().contiguous()
+        B, L = s.shape
+        dev = s.device
+        _ = self.so3_reverse  # build the table outside any capture
+        if use_cuda_graph and noises is None:
+            return self._sample_graphed(s, x, O, res_context_emb, pair_context_emb, generation_mask, t_start, t_stop)
+        for step in range(t_start, t_stop - 1, -1):
+            t = torch.full((B,), step, device=dev, dtype=torch.int64)
+            noise = noises[step] if noises is not None else self.draw_step_noise(B, L, dev, generator=generator)
+            out = self.reverse_step(s, x, O, res_context_emb, pair_context_emb, generation_mask, t, noise, inplace=True)
+            s, x, O = out["seq_idx"], out["translations"], out["orientations"]
+        return {"seq_idx": s, "translations": x, "orientations": O}
+
+    def _sample_graphed(self, s, x, O, res_ctx, pair_ctx, generation_mask, t_start, t_stop):
+        """One reverse step captured in a CUDA graph and replayed; the step index lives in a device tensor."""
+        B, L = s.shape
+        dev = s.device
+        t_buf = torch.full((B,), t_start, device=dev, dtype=torch.int64)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm-up outside capture (allocator, lazy module init)
+                self.reverse_step(s.clone(), x.clone(), O.clone(), res_ctx, pair_ctx, generation_mask, t_buf,
+                                  self.draw_step_noise(B, L, dev))
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            noise = self.draw_step_noise(B, L, dev)
+            self.reverse_step(s, x, O, res_ctx, pair_ctx, generation_mask, t_buf, noise, inplace=True)
+            t_buf.sub_(1)
+        for _ in range(t_start, t_stop - 1, -1):
+            graph.replay()
+        return {"seq_idx": s, "translations": x, "orientations": O}
+
+    @torch.no_grad()
+    def sample(self, seq_idx, xyz, orientations, backbone_dihedrals=None, distmat=None, pairwise_dihedrals=None,
+               atom_mask=None, chain_idx=None, residue_idx=None, generation_mask=None, residue_mask=None,
+               generator=None, precision="bf16", use_cuda_graph=True, context_chunk=32, t_start=None, t_stop=1):
+        """Reverse-diffusion sampling of the masked residues (the reference's stub, made real).
+
+        Accepts host or device tensors (host tensors are copied to the model's device; pinned memory
+        makes that asynchronous).  Features not given are derived: ``distmat`` from ``xyz`` on the
+        device, masks default to "all residues valid / generation mask required".  Returns a dict
+        ``{seq_idx, translations, orientations}`` on the model's device."""
+        dev = self._device
+        mv = lambda v: None if v is None else v.to(dev, non_blocking=True)
+        seq_idx, xyz, orientations = mv(seq_idx), mv(xyz), mv(orientations)
+        B, L = seq_idx.shape
+        A = xyz.shape[2]
+        if generation_mask is None:
+            raise ValueError("sample() needs generation_mask: which residues to generate")
+        generation_mask = mv(generation_mask).bool()
+        residue_mask = torch.ones(B, L, dtype=torch.bool, device=dev) if residue_mask is None else mv(residue_mask).bool()
+        atom_mask = torch.ones(B, L, A, dtype=torch.bool, device=dev) if atom_mask is None else mv(atom_mask)
+        chain_idx = torch.ones(B, L, dtype=torch.long, device=dev) if chain_idx is None else mv(chain_idx)
+        residue_idx = torch.arange(L, device=dev)[None].expand(B, L) if residue_idx is None else mv(residue_idx)
+        backbone_dihedrals = torch.zeros(B, L, 3, device=dev) if backbone_dihedrals is None else mv(backbone_dihedrals)
+        pairwise_dihedrals = torch.zeros(B, L, L, 2, device=dev) if pairwise_dihedrals is None else mv(pairwise_dihedrals)
+        distmat = mv(distmat)
+        use_bf16 = precision == "bf16" and self.denoiser.ipa.layers[0].fast_path_supported(L)
+        res_parts, pair_parts = [], []
+        from .synth import pairwise_atom_distances
+        for lo in range(0, B, context_chunk):
+            sl = slice(lo, min(B, lo + context_chunk))
+            dm = distmat[sl] if distmat is not None else pairwise_atom_distances(xyz[sl])
+            r, p = self.encode_context(seq_idx[sl], xyz[sl], orientations[sl], backbone_dihedrals[sl], dm,
+                                       pairwise_dihedrals[sl], atom_mask[sl], chain_idx[sl], residue_idx[sl],
+                                       generation_mask[sl], residue_mask[sl])
+            res_parts.append(r)
+            pair_parts.append(cast_pair_to_bf16(p) if use_bf16 else p)
+        res_ctx, pair_ctx = torch.cat(res_parts), torch.cat(pair_parts)
+        # t = T prior on generated residues: s ~ U{0..20}, x ~ N(0, I), O ~ uniform SO(3)
+        from .synth import uniform_rotations
+        m = generation_mask
+        sT = torch.randint(0, 21, (B, L), device=dev, generator=generator)
+        xT = torch.randn(B, L, 3, device=dev, generator=generator)
+        OT = uniform_rotations(B, L, generator=generator, device=dev)
+        x0 = xyz[:, :, CA_IDX]
+        s = torch.where(m, sT, seq_idx)
+        x = torch.where(m[..., None], xT, x0)
+        O = torch.where(m[..., None, None], OT, orientations)
+        return self.sample_from_context(s, x, O, res_ctx, pair_ctx, m, generator=generator, t_start=t_start,
+                                        t_stop=t_stop, use_cuda_graph=use_cuda_graph and generator is None)

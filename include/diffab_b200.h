@@ -1,0 +1,165 @@
+/* diffab_b200.h - flat C ABI of libdiffab_b200.so (sm_100a only).
+ *
+ * The reference (dohlee/diffab-pytorch) is pure Python/PyTorch and has no FFI layer; its boundary
+ * for the denoising hot path is the Python class `DiffAb` and the free functions of `so3.py` /
+ * `diffusion.py`.  Each entry point below replaces the arithmetic of the reference function(s)
+ * cited next to it (paths relative to the reference root).  The Python mirror in
+ * `diffab-pytorch_b200/` binds these with ctypes; INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer owned by the caller; the library never allocates, frees or
+ *    retains memory.  Tensors are contiguous in the layouts given; float pointers must be 16-byte
+ *    aligned (bf16 pair tensors handed to the TMA path: 128-byte aligned).
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), does no host
+ *    synchronisation and no allocation, and is CUDA-graph capturable.
+ *  - Return value: 0 on success, negative DAB_E* code otherwise; dab_last_error() gives a
+ *    thread-local message.  Nothing aborts or throws across the ABI.  There is no CPU fallback.
+ *  - RNG never lives inside the library: noise tensors are inputs, drawn by the caller in the
+ *    reference's call order (SURVEY 3.1 draws #2-#7), which is what makes integer outputs
+ *    bit-exact against the reference.
+ */
+#ifndef DIFFAB_B200_H
+#define DIFFAB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAB_OK 0
+#define DAB_EINVAL (-1)      /* bad argument (null pointer, negative size, misalignment) */
+#define DAB_EUNSUPPORTED (-2) /* shape outside what the kernels support */
+#define DAB_ELAUNCH (-3)     /* CUDA launch / runtime error */
+#define DAB_EWORKSPACE (-4)  /* workspace too small */
+
+#define DAB_VOCAB 21 /* diffusion.py:47 (hard-coded there) */
+
+int dab_version(void);
+const char* dab_last_error(void);
+
+/* ------------------------------------------------------------------ SO(3) maps, so3.py:142-259 */
+/* vector_to_rotation_matrix (so3.py:207-237): v[n,3] -> R[n,3,3], Rodrigues, no epsilon guard. */
+int dab_so3_exp(const float* v, float* R, int64_t n, void* stream);
+/* rotation_matrix_to_vector (so3.py:173-182): R[n,3,3] -> v[n,3]. */
+int dab_so3_log(const float* R, float* v, int64_t n, void* stream);
+/* log_rotmat (so3.py:146-162): R[n,3,3] -> skew S[n,3,3]. */
+int dab_so3_log_skew(const float* R, float* S, int64_t n, void* stream);
+/* exp_skew_symmetric_mat (so3.py:219-237): S[n,3,3] -> R[n,3,3]. */
+int dab_so3_exp_skew(const float* S, float* R, int64_t n, void* stream);
+/* scale_rot (so3.py:240-259): out = exp(k * log R); rotation i uses k[i / group]. */
+int dab_so3_scale_rot(const float* R, const float* k, int64_t n, int64_t group, float* out, void* stream);
+
+/* ------------------------------------------------------------------ IGSO(3), so3.py:37-126 */
+/* SO3._precompute_histogram/_angular_pdf (so3.py:52-72): out[n_sigma, n_bins], unnormalised. */
+int dab_igso3_table(const float* sigma, int n_sigma, int n_bins, int n_terms, float* out, void* stream);
+/* SO3.sample_isotropic_gaussian (so3.py:98-126) with its four draws injected:
+ *   axis_noise[B,L,3] randn, exp_noise[B,n_bins] Exp(1) (the draw inside torch.multinomial),
+ *   jitter[B,L] U[0,1), gauss[B,L] randn.  sigma_idx[B] int64 indexes hist rows / sigmas.
+ *   rotvec[B,L,3] out; bins[B,L] int64 out (may be NULL; then the histogram top-L selection is
+ *   skipped for rows whose sigma >= threshold, whose result does not depend on it). */
+int dab_igso3_sample(const float* hist, const float* sigmas, int n_sigma, int n_bins,
+                     const int64_t* sigma_idx, int B, int L, const float* axis_noise,
+                     const float* exp_noise, const float* jitter, const float* gauss,
+                     float sigma_threshold, float* rotvec, int64_t* bins, void* stream);
+
+/* ------------------------------------------------------------------ diffusion.py */
+/* Schedule tables of cosine_variance_schedule (diffusion.py:11-35), each [T+1] floats on device. */
+typedef struct DabSchedule {
+  int T;
+  const float* alpha;
+  const float* alpha_bar;
+  const float* alpha_bar_sqrt;
+  const float* one_minus_alpha_bar_sqrt;
+  const float* beta;
+} DabSchedule;
+
+/* DiffAb._add_noise (diffab_pytorch.py:778-806) = SequenceDiffuser.diffuse_from_t0 +
+ * posterior_single_step (diffusion.py:137-192), CoordinateDiffuser.diffuse_from_t0 (:199-236),
+ * OrientationDiffuser.diffuse_from_t0 (:262-294; `rotvec` is dab_igso3_sample's output).
+ * mask[B,L] uint8 (bool); t[B] int64; seq_exp[B*L,21] Exp(1); eps[B,L,3] randn.
+ * Outputs: seq_t[B,L] int64, posterior[B,L,21], x_t[B,L,3], O_t[B,L,3,3]. */
+int dab_forward_noise(const DabSchedule* sched, const int64_t* seq0, const float* x0, const float* O0,
+                      const uint8_t* mask, const int64_t* t, int B, int L, const float* seq_exp,
+                      const float* eps, const float* rotvec, int64_t* seq_t, float* posterior,
+                      float* x_t, float* O_t, void* stream);
+
+/* SequenceDiffuser.forward_prob_single_step / forward_prob_from_t0 / posterior_single_step
+ * (diffusion.py:49-79,105-135,168-192).  kind: 0 single step, 1 from t0, 2 posterior
+ * (seq = s_t, seq0 = s_0).  out[B,L,21]. */
+int dab_seq_probs(const DabSchedule* sched, int kind, const int64_t* seq, const int64_t* seq0,
+                  const uint8_t* mask, const int64_t* t, int B, int L, float* out, void* stream);
+
+/* Reverse step (NOT in the reference: DiffAb.sample is a stub, diffab_pytorch.py:770-776; the
+ * composition is fixed by oracle/sampler.py).  Fuses the tail of Denoiser.forward
+ * (diffab_pytorch.py:594-596: O0 = O_t @ exp(v_theta)) with the three updates:
+ *   s' = argmax(seq_post / seq_exp); x' = (x - beta/sqrt(1-abar) eps_theta)/sqrt(alpha) + sqrt(beta) z;
+ *   O' = O0 @ exp(rotvec) (no noise at t = 1); each under where(mask, new, old).
+ * O0_out may be NULL.  In-place (seq_out == seq_t etc.) is allowed. */
+int dab_reverse_step(const DabSchedule* sched, const int64_t* seq_t, const float* x_t, const float* O_t,
+                     const float* eps_theta, const float* v_theta, const float* seq_post,
+                     const uint8_t* mask, const int64_t* t, int B, int L, const float* seq_exp,
+                     const float* z, const float* rotvec, int64_t* seq_out, float* x_out, float* O_out,
+                     float* O0_out, void* stream);
+
+/* ------------------------------------------------------------------ invariant point attention */
+/* One InvariantPointAttentionLayer (diffab_pytorch.py:339-465, use_pair_bias=True).
+ * Weights are the layer's own state-dict tensors, nn.Linear layout (out, in) row-major. */
+typedef struct DabIpaDims {
+  int B, L, D, C, H, ds, Pq, Pv;
+} DabIpaDims;
+
+typedef struct DabIpaWeights {
+  const float* w_q_scalar; /* (H*ds, D)    to_q_scalar.weight */
+  const float* w_k_scalar; /* (H*ds, D) */
+  const float* w_v_scalar; /* (H*ds, D) */
+  const float* w_q_point;  /* (H*Pq*3, D) */
+  const float* w_k_point;  /* (H*Pq*3, D) */
+  const float* w_v_point;  /* (H*Pv*3, D) */
+  const float* w_pair_bias; /* (H, C) */
+  const float* gamma;      /* (H)  used raw, no softplus (diffab_pytorch.py:373,429) */
+  const float* w_out;      /* (D, H*ds + H*C + H*Pv*3 + H*Pv) */
+  const float* b_out;      /* (D) */
+} DabIpaWeights;
+
+typedef struct DabIpaGrads { /* same shapes as DabIpaWeights; accumulated INTO (caller zeroes) */
+  float* w_q_scalar; float* w_k_scalar; float* w_v_scalar;
+  float* w_q_point; float* w_k_point; float* w_v_point;
+  float* w_pair_bias; float* gamma; float* w_out; float* b_out;
+} DabIpaGrads;
+
+/* Shape-generic fp32 path (the "<= 1e-4" path of north_star; any L, D, C, H, ds, Pq, Pv that fit
+ * shared memory).  x[B,L,D], e[B,L,L,C], R[B,L,3,3], t[B,L,3] -> y[B,L,D].
+ * Workspace (floats): dab_ipa_f32_workspace_bytes().  If save_for_bwd != 0 the workspace keeps what
+ * dab_ipa_bwd_f32 needs (projections, concat features) and must be handed to it untouched. */
+size_t dab_ipa_f32_workspace_bytes(const DabIpaDims* d, int for_backward);
+int dab_ipa_fwd_f32(const DabIpaDims* d, const DabIpaWeights* w, const float* x, const float* e,
+                    const float* R, const float* t, float* y, void* workspace, size_t workspace_bytes,
+                    int save_for_bwd, void* stream);
+/* Backward of the layer wrt x, e and all ten parameters (R and t are treated as constants: in the
+ * reference they are the noised frames, which carry no gradient, diffab_pytorch.py:824-854).
+ * dx[B,L,D] and de[B,L,L,C] are overwritten; parameter grads are accumulated into `g`. */
+int dab_ipa_bwd_f32(const DabIpaDims* d, const DabIpaWeights* w, const float* x, const float* e,
+                    const float* R, const float* t, const float* dy, float* dx, float* de,
+                    const DabIpaGrads* g, void* workspace, size_t workspace_bytes, void* stream);
+
+/* sm_100a fast path for the train.py configuration (L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8):
+ * bf16 pair tensor streamed by TMA, tcgen05 tensor-core contractions with TMEM accumulators,
+ * split-bf16 point-distance logits, fp32 softmax.  `packed` is produced once per layer by
+ * dab_ipa_pack_weights (weights are constant during sampling).  x[B,L,D] fp32 in, y[B,L,D] fp32
+ * out, e_bf16[B,L,L,C] bf16. */
+size_t dab_ipa_packed_bytes(const DabIpaDims* d);
+int dab_ipa_pack_weights(const DabIpaDims* d, const DabIpaWeights* w, void* packed, void* stream);
+size_t dab_ipa_sm100_workspace_bytes(const DabIpaDims* d);
+int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
+                      const float* R, const float* t, float* y, void* workspace, size_t workspace_bytes,
+                      void* stream);
+/* fp32 -> bf16 conversion of the pair tensor (once per patch; round-to-nearest-even). */
+int dab_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFAB_B200_H */

@@ -1,0 +1,155 @@
+"""GPU parity of the whole path: Denoiser / _shared_step vs reference goldens, sample() vs the
+oracle sampler (our composition), CUDA-graph replay vs eager."""
+import pytest
+import torch
+
+from conftest import load_golden
+from diffab_pytorch_b200 import synth
+from diffab_pytorch_b200.diffab_pytorch import DiffAb
+from oracle import diffusion as odiff
+from oracle import ipa as oipa
+from oracle import sampler as osamp
+from oracle import so3 as oso3
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TRAIN = (128, 64, 6, 32, 8, 8, 8)
+
+
+def _model(seed=0):
+    model = DiffAb(*TRAIN, device=DEV)
+    model.load_state_dict(synth.synthetic_state(load_golden("state_shapes.pt"), seed=seed))
+    return model.eval()
+
+
+def _to(batch):
+    return {k: v.to(DEV) for k, v in batch.items()}
+
+
+def _rel(a, b):
+    return float((a.double().cpu() - b.double()).abs().max() / b.double().abs().max())
+
+
+def test_denoiser_and_losses_vs_reference():
+    g = load_golden("denoiser.pt")
+    model = _model(g["seed_state"])
+    b = _to(synth.make_patches(2, 128, seed=g["seed_patches"]))
+    with torch.no_grad():
+        res, pair = model.encode_context(b["seq_idx"], b["xyz"], b["orientations"], b["backbone_dihedrals"],
+                                         b["distmat"], b["pairwise_dihedrals"], b["atom_mask"], b["chain_idx"],
+                                         b["residue_idx"], b["generation_mask"], b["residue_mask"])
+        assert _rel(res, g["res_ctx"]) < 1e-4
+        assert _rel(pair[:, ::8, ::8], g["pair_ctx"]["sub"]) < 1e-4
+        n = _to(g["noised"])
+        beta = model.dsched.tensors["beta"][g["t"].to(DEV)]
+        den = model.denoise(n["seq_idx_t"], n["translations_t"], n["orientations_t"], res, pair, beta,
+                            b["generation_mask"], b["residue_mask"])
+        for k, ref in g["denoised"].items():
+            assert _rel(den[k], ref) < 1e-4, k
+        losses = torch.stack(model._losses(den, n, b["orientations"], b["generation_mask"], b["residue_mask"]))
+    assert torch.allclose(losses.cpu(), g["losses"], rtol=1e-4)
+
+
+def test_shared_step_losses_vs_reference_under_injected_draws():
+    """The reference's _shared_step under torch.manual_seed(99) on CPU; here the same CPU draws
+    (#1 t, #2-#7 noise) are made in the same order and injected."""
+    g = load_golden("shared_step.pt")
+    model = _model(g["seed_state"])
+    batch = synth.make_patches(2, 128, seed=g["seed_patches"])
+    torch.manual_seed(g["seed_step"])
+    t = torch.randint(low=1, high=101, size=(2,))
+    noise = odiff.draw_add_noise_tensors(2, 128)
+    with torch.no_grad():
+        losses = torch.stack(model._shared_step(_to(batch), 0, t=t.to(DEV), noise=_to(noise)))
+    assert torch.allclose(losses.cpu(), g["losses"], rtol=1e-4), (losses.cpu(), g["losses"])
+
+
+def test_training_step_backward_runs_and_matches_oracle_grads():
+    model = DiffAb(32, 16, 2, 8, 4, 4, 4, device=DEV)
+    batch = synth.make_patches(2, 24, seed=5, cdr=(8, 16))
+    torch.manual_seed(3)
+    t = torch.randint(1, 101, (2,))
+    noise = odiff.draw_add_noise_tensors(2, 24)
+    model.zero_grad()
+    losses = model._shared_step(_to(batch), 0, t=t.to(DEV), noise=_to(noise))
+    sum(losses).backward()
+    # oracle: same forward in fp64 on CPU with autograd
+    state = {k: v.detach().cpu().double().requires_grad_(True) for k, v in model.state_dict().items()}
+    sched = odiff.cosine_schedule(100, s=0.01, beta_max=0.999)
+    hist = model.orientation_diffuser.so3.histograms.cpu()
+    noised = odiff.add_noise(sched, hist, batch["seq_idx"], batch["xyz"][:, :, 1], batch["orientations"],
+                             batch["generation_mask"], t, noise)
+    with torch.no_grad():
+        res, pair = model.encode_context(*[_to(batch)[k] for k in ("seq_idx", "xyz", "orientations",
+                                           "backbone_dihedrals", "distmat", "pairwise_dihedrals", "atom_mask",
+                                           "chain_idx", "residue_idx", "generation_mask", "residue_mask")])
+    den = oipa.denoiser_forward(state, noised["seq_idx_t"], noised["translations_t"].double(),
+                                noised["orientations_t"].double(), res.cpu().double(), pair.cpu().double(),
+                                sched["beta"][t].double(), 2, 4)
+    ol = oipa.losses(den, {k: (v.double() if v.dtype.is_floating_point else v) for k, v in noised.items()},
+                     batch["orientations"].double(), batch["generation_mask"], batch["residue_mask"])
+    sum(ol).backward()
+    assert torch.allclose(torch.stack(losses).detach().cpu().double(), torch.stack(ol).detach(), rtol=2e-4)
+    for name, p in model.denoiser.named_parameters():
+        ref = state["denoiser." + name].grad
+        if ref is None:
+            continue
+        err = (p.grad.cpu().double() - ref).abs().max() / ref.abs().max().clamp_min(1e-12)
+        assert err < 5e-3, (name, float(err))
+
+
+def _oracle_sample(model, batch, s, x, O, res, pair, noises, t_start, t_stop=1):
+    state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    sched = odiff.cosine_schedule(100, s=0.01, beta_max=0.999)
+    hist_rev = model.so3_reverse.histograms.cpu()
+    return osamp.sample_loop(state, sched, hist_rev, s, x, O, res.cpu(), pair.cpu(), batch["generation_mask"],
+                             len(model.denoiser.ipa.layers), model.denoiser.ipa.layers[0].n_head, noises,
+                             t_start=t_start, t_stop=t_stop)
+
+
+def test_reverse_steps_vs_oracle_sampler():
+    model = _model(0)
+    batch = synth.make_patches(2, 128, seed=9)
+    b = _to(batch)
+    with torch.no_grad():
+        res, pair = model.encode_context(b["seq_idx"], b["xyz"], b["orientations"], b["backbone_dihedrals"],
+                                         b["distmat"], b["pairwise_dihedrals"], b["atom_mask"], b["chain_idx"],
+                                         b["residue_idx"], b["generation_mask"], b["residue_mask"])
+    gen = torch.Generator().manual_seed(4)
+    s, x, O = osamp.draw_initial_state(batch["seq_idx"], batch["xyz"][:, :, 1], batch["orientations"],
+                                       batch["generation_mask"], generator=gen)
+    t_start, t_stop = 100, 96
+    noises = {t: osamp.draw_step_noise(2, 128, generator=gen) for t in range(t_start, t_stop - 1, -1)}
+    ref = _oracle_sample(model, batch, s, x, O, res, pair, noises, t_start, t_stop)
+    got = model.sample_from_context(s.to(DEV), x.to(DEV), O.to(DEV), res, pair, b["generation_mask"],
+                                    noises={t: _to(n) for t, n in noises.items()}, t_start=t_start, t_stop=t_stop)
+    m = batch["generation_mask"]
+    mism = (got["seq_idx"].cpu() != ref["seq_idx"])[m].float().mean()
+    assert mism <= 0.02, float(mism)           # identical up to near-ties of p/q after fp32 reordering
+    assert torch.equal(got["seq_idx"].cpu()[~m], batch["seq_idx"][~m])
+    same = (got["seq_idx"].cpu() == ref["seq_idx"]).all(dim=1)
+    dx = (got["translations"].cpu() - ref["translations"]).norm(dim=-1)[m]
+    assert dx.max() < 1e-2, float(dx.max())     # CA drift after 5 steps (Angstrom)
+    dO = (got["orientations"].cpu() - ref["orientations"]).abs().amax(dim=(-1, -2))[m]
+    assert dO.max() < 1e-2
+
+
+def test_sample_end_to_end_graph_and_eager():
+    model = DiffAb(32, 16, 2, 8, 4, 4, 4, device=DEV).eval()
+    batch = synth.make_patches(3, 32, seed=1, cdr=(10, 20))
+    args = (batch["seq_idx"], batch["xyz"], batch["orientations"], batch["backbone_dihedrals"], None,
+            batch["pairwise_dihedrals"], batch["atom_mask"], batch["chain_idx"], batch["residue_idx"],
+            batch["generation_mask"], batch["residue_mask"])
+    for graph in (False, True):
+        out = model.sample(*args, use_cuda_graph=graph, t_start=10)
+        m = batch["generation_mask"]
+        assert out["seq_idx"].shape == (3, 32) and out["seq_idx"].dtype == torch.int64
+        assert int(out["seq_idx"].min()) >= 0 and int(out["seq_idx"].max()) <= 20
+        assert torch.equal(out["seq_idx"].cpu()[~m], batch["seq_idx"][~m])
+        assert torch.equal(out["translations"].cpu()[~m], batch["xyz"][:, :, 1][~m])
+        assert torch.equal(out["orientations"].cpu()[~m], batch["orientations"][~m])
+        O = out["orientations"][m.to(DEV)]
+        assert torch.allclose(O.transpose(-1, -2) @ O, torch.eye(3, device=DEV).expand_as(O), atol=1e-4)
+        assert torch.isfinite(out["translations"]).all()
+    with pytest.raises(ValueError):
+        model.sample(batch["seq_idx"], batch["xyz"], batch["orientations"])
