@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Headline benchmark: reverse-diffusion patches/s (K=128 residues, T=100 steps) on N B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels)
+    python bench.py --impl reference --steps K --warmup W    # CPU baseline arm (oracle port)
+
+One "step" = one full reverse-diffusion pass (T=100 denoise + update steps) over the rank's batch of
+synthetic 128-residue CDR-H3 patches (BASELINE config 3: 256 patches per GPU; weak scaling: every
+rank owns 256 independent patches, results are all-gathered with NCCL inside the timed region).
+`value` times the loop with context embeddings and the t=T state resident in HBM; `e2e` times
+`DiffAb.sample()` from pinned host buffers to host results (H2D, context encoding, loop, D2H).
+Prints ONE JSON line (see DESIGN.md "Measurement" for every field).
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "reverse-diffusion patches/s (K=128, T=100)"
+TRAIN_CFG = (128, 64, 6, 32, 8, 8, 8)  # train.py:62-70 of the reference = "DiffAb default config"
+L, T = 128, 100
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--patches", type=int, default=256, help="patches per GPU")
+    ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="skip e2e / roofline / cpu_baseline passes")
+    ap.add_argument("--reverse-steps", type=int, default=T,
+                    help="PROFILING ONLY: run this many of the T reverse steps per pass (ncu launch lists); "
+                         "the JSON line is then marked profile_only and is not a bench value")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference's algorithm; the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_reverse_sample_rate(n_patches, n_timesteps, repeats, threads):
+    """Times `n_timesteps` reverse steps of `n_patches` patches with the oracle on host cores and
+    returns (patches/s extrapolated to T=100, seconds per call)."""
+    from diffab_pytorch_b200 import synth
+    from oracle import diffusion as odiff
+    from oracle import sampler as osamp
+
+    torch.set_num_threads(threads)
+    shapes = torch.load(os.path.join(ROOT, "tests", "golden", "state_shapes.pt"), weights_only=False)
+    state = synth.synthetic_state(shapes, seed=0)
+    sched = odiff.cosine_schedule(T, s=0.01, beta_max=0.999)
+    g = torch.Generator().manual_seed(0)
+    batch = synth.make_patches(n_patches, L, seed=0, with_distmat=False)
+    res_ctx = torch.randn(n_patches, L, 128, generator=g)
+    pair_ctx = torch.randn(n_patches, L, L, 64, generator=g)
+    s, x, O = osamp.draw_initial_state(batch["seq_idx"], batch["xyz"][:, :, 1], batch["orientations"],
+                                       batch["generation_mask"], generator=g)
+    # steps T..T-n+1 use sigma = sqrt(beta) >= 0.1 (gaussian branch): the histogram rows are not needed
+    hist_rev = torch.ones(T + 1, 8192)
+    noises = {t: osamp.draw_step_noise(n_patches, L, generator=g) for t in range(T, T - n_timesteps, -1)}
+    times = []
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            osamp.sample_loop(state, sched, hist_rev, s, x, O, res_ctx, pair_ctx, batch["generation_mask"], 6, 8,
+                              noises, t_start=T, t_stop=T - n_timesteps + 1)
+            times.append(time.perf_counter() - t0)
+    per_call = min(times)
+    return n_patches / (per_call * T / n_timesteps), per_call
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_patches, n_ts = 4, 2
+    for _ in range(args.warmup):
+        cpu_reverse_sample_rate(n_patches, n_ts, 1, threads)
+    t0 = time.perf_counter()
+    rates = [cpu_reverse_sample_rate(n_patches, n_ts, 1, threads)[0] for _ in range(args.steps)]
+    elapsed = time.perf_counter() - t0
+    value = statistics.mean(rates)
+    sample = (f"{n_patches} patches x {n_ts} of {T} reverse steps per timed step (oracle port of the reference's "
+              f"PyTorch CPU path, fp32), extrapolated x{T // n_ts} to T={T}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * elapsed / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"reverse sampling T={T}, L={L}, train.py config (D=128,C=64,6 IPA layers,H=8)",
+                   "patches_per_gpu": args.patches},
+        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import diffab_pytorch_b200  # noqa: F401
+    from diffab_pytorch_b200 import _lib, synth
+    from diffab_pytorch_b200.diffab_pytorch import DiffAb, cast_pair_to_bf16
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    lib = _lib.lib()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    # ---- model + resident inputs ------------------------------------------------------------
+    B = args.patches
+    shapes = torch.load(os.path.join(ROOT, "tests", "golden", "state_shapes.pt"), weights_only=False)
+    model = DiffAb(*TRAIN_CFG, device=dev).eval()
+    model.load_state_dict(synth.synthetic_state(shapes, seed=0))   # random-init stand-in weights
+    layer0 = model.denoiser.ipa.layers[0]
+    precision = args.precision
+    if precision == "auto":
+        d = _lib.DabIpaDims(1, L, *TRAIN_CFG[:2], 8, 32, 8, 8)
+        precision = "bf16" if lib.dab_ipa_packed_bytes(ctypes.byref(d)) > 0 else "fp32"
+    batch = synth.make_patches(B, L, seed=1000 + rank, with_distmat=False)
+    host = {k: v.pin_memory() for k, v in batch.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def sample_e2e():
+        out = model.sample(host["seq_idx"], host["xyz"], host["orientations"], host["backbone_dihedrals"], None,
+                           host["pairwise_dihedrals"], host["atom_mask"], host["chain_idx"], host["residue_idx"],
+                           host["generation_mask"], host["residue_mask"], precision=precision,
+                           use_cuda_graph=not args.no_graph)
+        return {k: v.to("cpu", non_blocking=False) for k, v in out.items()}
+
+    # resident context for the kernel-path number
+    with torch.no_grad():
+        b = {k: v.to(dev) for k, v in batch.items()}
+        res_parts, pair_parts = [], []
+        for lo in range(0, B, 32):
+            sl = slice(lo, min(B, lo + 32))
+            r, p = model.encode_context(b["seq_idx"][sl], b["xyz"][sl], b["orientations"][sl],
+                                        b["backbone_dihedrals"][sl], synth.pairwise_atom_distances(b["xyz"][sl]),
+                                        b["pairwise_dihedrals"][sl], b["atom_mask"][sl], b["chain_idx"][sl],
+                                        b["residue_idx"][sl], b["generation_mask"][sl], b["residue_mask"][sl])
+            res_parts.append(r)
+            pair_parts.append(cast_pair_to_bf16(p) if precision == "bf16" else p)
+        res_ctx, pair_ctx = torch.cat(res_parts), torch.cat(pair_parts)
+        del res_parts, pair_parts
+        m = b["generation_mask"]
+        s0 = torch.where(m, torch.randint(0, 21, (B, L), device=dev), b["seq_idx"])
+        x0 = torch.where(m[..., None], torch.randn(B, L, 3, device=dev), b["xyz"][:, :, 1])
+        O0 = torch.where(m[..., None, None], synth.uniform_rotations(B, L, device=dev), b["orientations"])
+
+    t_stop = T - args.reverse_steps + 1
+    n_warm = max(args.warmup, 3) if args.reverse_steps == T else args.warmup
+
+    def one_step():
+        out = model.sample_from_context(s0, x0, O0, res_ctx, pair_ctx, m, use_cuda_graph=not args.no_graph,
+                                        t_stop=t_stop)
+        if dist is not None:   # gather the sampled structures on every rank (7,168 B per patch)
+            for k in ("seq_idx", "translations", "orientations"):
+                buf = torch.empty((world,) + out[k].shape, device=dev, dtype=out[k].dtype)
+                dist.all_gather_into_tensor(buf, out[k].contiguous())
+        return out
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(n_warm):
+        one_step()
+    barrier()
+    # launches of OUR kernels per step, counted on one eager step (graph replays do not pass through the host)
+    c0 = lib.dab_launch_count()
+    model.sample_from_context(s0, x0, O0, res_ctx, pair_ctx, m, use_cuda_graph=False, t_start=T, t_stop=T)
+    launches_per_reverse_step = lib.dab_launch_count() - c0
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        one_step()
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    clock_info = clocks.stop()
+    if dist is not None:
+        tmax = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tmax)
+    value = B * n_gpus * args.steps / (elapsed_ms / 1000.0)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": n_warm, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32",
+        "data": "synthetic",
+        "config": {"workload": f"full reverse sampling T={T} over {B} synthetic 128-residue CDR-H3 patches per GPU "
+                               "(BASELINE config 3), train.py model config, random-init weights",
+                   "patches_per_gpu": B, "L": L, "T": T, "precision": precision,
+                   "cuda_graph": not args.no_graph,
+                   "l2": f"pair tensor {pair_ctx.numel() * pair_ctx.element_size() / 1e6:.0f} MB per GPU > 126 MB L2 "
+                         "(inputs larger than L2, no flush)",
+                   "gather": "nccl all_gather of results inside the timed region" if dist is not None else "none"},
+        "clocks": clock_info,
+        "gpu_launches": int(launches_per_reverse_step) * args.reverse_steps * args.steps,
+    }
+    if args.reverse_steps != T:
+        line["profile_only"] = True
+
+    if rank == 0 and not args.skip_extras:
+        # ---- e2e through DiffAb.sample() from pinned host memory -------------------------------
+        sample_e2e()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 2))
+        for _ in range(n_e2e):
+            res = sample_e2e()
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / n_e2e
+        d2h_bytes = sum(v.numel() * v.element_size() for v in res.values())
+        line["e2e"] = {"value": B / e2e_s, "unit": "patches/s", "h2d_bytes_per_step": h2d_bytes,
+                       "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1000 * e2e_s, "n_gpus_measured": 1}
+
+        # ---- roofline of the dominant kernel (IPA attention core), measured live ---------------
+        line["roofline"] = measure_roofline(model, layer0, res_ctx, pair_ctx, x0, O0, precision, hbm_peak, peak_src)
+        line["ipa_fwd_bwd"] = measure_ipa_fwd_bwd(dev)
+
+        # ---- CPU baseline on this box's host cores ----------------------------------------------
+        threads = os.cpu_count() or 1
+        rate, per_call = cpu_reverse_sample_rate(2, 2, 2, threads)
+        rate1, _ = cpu_reverse_sample_rate(1, 1, 1, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": "patches/s", "cores": threads, "kind": "port",
+                                "single_thread_value": rate1,
+                                "sample": f"2 patches x 2 of {T} reverse steps (oracle port of the reference's PyTorch "
+                                          f"CPU path, fp32, {per_call:.2f} s per call), extrapolated x50 to T={T}"}
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def measure_roofline(model, layer, res_ctx, pair_ctx, x0, O0, precision, hbm_peak, peak_src, iters=20):
+    """Average device time of the attention-core launch alone (phase mask 2), CUDA events on the
+    launching stream, input (pair tensor of all patches) larger than L2."""
+    from diffab_pytorch_b200 import _lib
+    lib = _lib.lib()
+    B = res_ctx.shape[0]
+    x = res_ctx.contiguous()
+    with torch.no_grad():
+        layer(x, pair_ctx, O0, x0)            # full call: fills the workspace the core kernel reads
+        torch.cuda.synchronize()
+        # inference calls reuse the layer's persistent workspace, which the phase-mask contract needs
+        lib.dab_debug_set_phase_mask(2)
+        try:
+            for _ in range(3):
+                layer(x, pair_ctx, O0, x0)
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+            for a, b_ in evs:
+                a.record()
+                layer(x, pair_ctx, O0, x0)
+                b_.record()
+            torch.cuda.synchronize()
+        finally:
+            lib.dab_debug_set_phase_mask(7)
+    us = statistics.mean(a.elapsed_time(b_) for a, b_ in evs) * 1000.0
+    sz = pair_ctx.element_size()
+    if precision == "bf16":
+        # core kernel: reads e (bf16), packed q/k/v operands, writes concat features
+        alg = B * (L * L * 64 * sz) + B * L * (1344 + 1024) * 4
+    else:
+        alg = B * (L * L * 64 * sz) + B * L * (1344 + 1024) * 4
+    achieved = alg / (us * 1e-6) / 1e9
+    return {"bound": "hbm", "kernel": "ipa attention core (" + precision + ")", "achieved": achieved,
+            "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "traffic": None, "us_per_launch": us, "algorithmic_bytes_per_launch": alg, "patches_per_launch": B}
+
+
+def measure_ipa_fwd_bwd(dev, B=32, iters=5):
+    """Secondary metric of BASELINE.json: one IPA layer fwd+bwd, B=32 patches x K=128 (config 2), fp32."""
+    from diffab_pytorch_b200 import synth
+    from diffab_pytorch_b200.diffab_pytorch import InvariantPointAttentionLayer
+    layer = InvariantPointAttentionLayer(128, 64, 32, 8, 8, 8).to(dev)
+    layer.load_state_dict(synth.synthetic_state(synth.ipa_layer_shapes(128, 64, 8, 32, 8, 8), seed=0))
+    bufs = []
+    for i in range(3):   # rotate 3 input sets (3 x 134 MB of e > L2)
+        x, e, R, t = (v.to(dev) for v in synth.make_ipa_inputs(B, L, 128, 64, seed=i))
+        bufs.append((x.requires_grad_(True), e.requires_grad_(True), R, t))
+    gy = torch.randn(B, L, 128, device=dev)
+
+    def run(i):
+        x, e, R, t = bufs[i % 3]
+        y = layer(x, e, R, t)
+        y.backward(gy)
+        x.grad = None; e.grad = None
+
+    for i in range(3):
+        run(i)
+    torch.cuda.synchronize()
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(iters):
+        run(i)
+    b_.record()
+    torch.cuda.synchronize()
+    us = a.elapsed_time(b_) * 1000 / iters
+    alg = 3 * B * L * L * 64 * 4 + 6 * B * L * 128 * 4
+    return {"metric": "IPA fwd+bwd us/layer (B=32, K=128, fp32)", "value": us, "unit": "us",
+            "algorithmic_bytes": alg, "hbm_roofline_us": alg / 6528.4e9 * 1e6}
+
+
+if __name__ == "__main__":
+    main()

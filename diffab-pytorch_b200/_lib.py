@@ -40,6 +40,8 @@ EXPORTS = {
     # name: (restype, argtypes)
     "dab_version": (c_int, []),
     "dab_last_error": (c_char_p, []),
+    "dab_launch_count": (ctypes.c_longlong, []),
+    "dab_debug_set_phase_mask": (c_int, [c_int]),
     "dab_so3_exp": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dab_so3_log": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dab_so3_log_skew": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),

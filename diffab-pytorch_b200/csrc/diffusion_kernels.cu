@@ -218,6 +218,7 @@ int dab_forward_noise(const DabSchedule* sched, const int64_t* seq0, const float
   int64_t n = (int64_t)B * L;
   forward_noise_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       sc, seq0, x0, O0, mask, t, B, L, seq_exp, eps, rotvec, seq_t, posterior, x_t, O_t);
+  count_launch();
   return check_launch("dab_forward_noise");
 }
 
@@ -231,6 +232,7 @@ int dab_seq_probs(const DabSchedule* sched, int kind, const int64_t* seq, const 
   DAB_REQUIRE(seq && mask && t && out && (kind != 2 || seq0), DAB_EINVAL, "dab_seq_probs: null pointer");
   int64_t n = (int64_t)B * L;
   seq_probs_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(sc, kind, seq, seq0, mask, t, B, L, out);
+  count_launch();
   return check_launch("dab_seq_probs");
 }
 
@@ -249,6 +251,7 @@ int dab_reverse_step(const DabSchedule* sched, const int64_t* seq_t, const float
   reverse_step_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       sc, seq_t, x_t, O_t, eps_theta, v_theta, seq_post, mask, t, B, L, seq_exp, z, rotvec, seq_out, x_out, O_out,
       O0_out);
+  count_launch();
   return check_launch("dab_reverse_step");
 }
 

@@ -117,6 +117,7 @@ static void sgemm(cudaStream_t s, const float* A, int64_t sam, int64_t sak, cons
   int nz = (K + kchunk - 1) / kchunk;
   dim3 grid((N + 63) / 64, (M + 63) / 64, nz);
   sgemm_kernel<<<grid, 256, 0, s>>>(A, sam, sak, Bp, sbk, sbn, Cp, ldc, bias, M, N, K, kchunk, nz > 1 ? 2 : mode);
+  count_launch();
 }
 
 // column sums: out[n] += sum_m A[m, n]   (d bias of to_out)
@@ -782,15 +783,22 @@ int dab_ipa_fwd_f32(const DabIpaDims* dims, const DabIpaWeights* w, const float*
   const float* Ws[6] = {w->w_q_scalar, w->w_k_scalar, w->w_v_scalar, w->w_q_point, w->w_k_point, w->w_v_point};
   int offs[6] = {d.o_qs, d.o_ks, d.o_vs, d.o_qp, d.o_kp, d.o_vp};
   int ns[6] = {d.NS, d.NS, d.NS, d.NQ, d.NQ, d.NV};
-  for (int k = 0; k < 6; ++k) sgemm(s, x, d.D, 1, Ws[k], 1, d.D, ws.proj + offs[k], d.NPROJ, nullptr, M, ns[k], d.D, 0);
-  int64_t npts = (int64_t)M * ((2 * d.NQ + d.NV) / 3);
-  frame_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, s>>>(ws.proj, R, t, d, 0);
-  size_t smem = fwd_smem_bytes(d);
-  allow_smem(ipa_attn_fwd_kernel, smem);
-  dim3 grid((d.L + IBF - 1) / IBF, d.B);
-  ipa_attn_fwd_kernel<<<grid, NT, smem, s>>>(d, ws.proj, e, R, t, w->w_pair_bias, w->gamma, ws.cat);
+  const int phases = phase_mask();
+  if (phases & 1) {
+    for (int k = 0; k < 6; ++k) sgemm(s, x, d.D, 1, Ws[k], 1, d.D, ws.proj + offs[k], d.NPROJ, nullptr, M, ns[k], d.D, 0);
+    int64_t npts = (int64_t)M * ((2 * d.NQ + d.NV) / 3);
+    frame_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, s>>>(ws.proj, R, t, d, 0);
+    count_launch();
+  }
+  if (phases & 2) {
+    size_t smem = fwd_smem_bytes(d);
+    allow_smem(ipa_attn_fwd_kernel, smem);
+    dim3 grid((d.L + IBF - 1) / IBF, d.B);
+    ipa_attn_fwd_kernel<<<grid, NT, smem, s>>>(d, ws.proj, e, R, t, w->w_pair_bias, w->gamma, ws.cat);
+    count_launch();
+  }
   // to_out, diffab_pytorch.py:464
-  sgemm(s, ws.cat, d.NCAT, 1, w->w_out, 1, d.NCAT, y, d.D, w->b_out, M, d.D, d.NCAT, 0);
+  if (phases & 4) sgemm(s, ws.cat, d.NCAT, 1, w->w_out, 1, d.NCAT, y, d.D, w->b_out, M, d.D, d.NCAT, 0);
   return check_launch("dab_ipa_fwd_f32");
 }
 
@@ -816,6 +824,7 @@ int dab_ipa_bwd_f32(const DabIpaDims* dims, const DabIpaWeights* w, const float*
   {
     dim3 grid((d.D + 127) / 128, M >= 1024 ? 32 : 1);
     colsum_kernel<<<grid, 128, 0, s>>>(dy, M, d.D, g->b_out);
+    count_launch();
   }
   // attention core
   size_t smq = bwdq_smem_bytes(d), smk = bwdk_smem_bytes(d);
@@ -826,6 +835,7 @@ int dab_ipa_bwd_f32(const DabIpaDims* dims, const DabIpaWeights* w, const float*
                                             ws.ds, de, ws.dproj, ws.dog, g->w_pair_bias, g->gamma);
   dim3 gk((d.L + JBB - 1) / JBB, d.B);
   ipa_attn_bwd_k_kernel<<<gk, NT, smk, s>>>(d, ws.proj, w->gamma, ws.dcat, ws.dog, ws.attn, ws.ds, ws.dproj);
+  count_launch(3);  // q-side, k-side, inverse frame
   // frames: d_local = d_global @ R^T
   int64_t npts = (int64_t)M * ((2 * d.NQ + d.NV) / 3);
   frame_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, s>>>(ws.dproj, R, t, d, 1);

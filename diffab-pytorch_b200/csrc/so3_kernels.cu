@@ -85,6 +85,7 @@ static int launch_map(const float* in, const float* k, float* out, int64_t n, in
   DAB_REQUIRE(aligned16(in) && aligned16(out), DAB_EINVAL, "%s: pointers must be 16-byte aligned", name);
   int64_t n_tiles = (n + kTile - 1) / kTile;
   so3_map_kernel<KIND><<<grid_for(n_tiles), kTile, 0, (cudaStream_t)stream>>>(in, k, out, n, group);
+  count_launch();
   return check_launch(name);
 }
 
@@ -222,6 +223,7 @@ int dab_igso3_table(const float* sigma, int n_sigma, int n_bins, int n_terms, fl
   dim3 grid((n_bins + 255) / 256, n_sigma);
   igso3_table_kernel<<<grid, 256, n_terms * sizeof(float), (cudaStream_t)stream>>>(
       sigma, n_bins, n_terms, 3.14159265358979323846 / (double)n_bins, out);
+  count_launch();
   return check_launch("dab_igso3_table");
 }
 
@@ -245,6 +247,7 @@ int dab_igso3_sample(const float* hist, const float* sigmas, int n_sigma, int n_
   igso3_sample_kernel<<<B, kSortThreads, smem, (cudaStream_t)stream>>>(
       hist, sigmas, n_bins, n_pow2, sigma_idx, L, axis_noise, exp_noise, jitter, gauss, sigma_threshold,
       3.14159265358979323846 / (double)n_bins, rotvec, bins);
+  count_launch();
   return check_launch("dab_igso3_sample");
 }
 

@@ -183,7 +183,10 @@ class _IpaFunction(torch.autograd.Function):
         need_bwd = any(ctx.needs_input_grad)
         lib = _lib.lib()
         nbytes = lib.dab_ipa_f32_workspace_bytes(ctypes.byref(dims), 1 if need_bwd else 0)
-        ws = torch.empty(max(nbytes, 16) // 4, device=x.device, dtype=torch.float32)
+        if need_bwd:   # kept for the backward pass: must be private to this call
+            ws = torch.empty(max(nbytes, 16) // 4, device=x.device, dtype=torch.float32)
+        else:          # inference: one persistent workspace per layer (stable address, graph friendly)
+            ws = layer._workspace(max(nbytes, 16), x.device).view(torch.float32)
         y = torch.empty(B, L, D, device=x.device, dtype=torch.float32)
         wstruct = _weights_struct(weights)
         _lib.check(lib.dab_ipa_fwd_f32(ctypes.byref(dims), ctypes.byref(wstruct), ptr(x), ptr(e), ptr(r), ptr(t),
@@ -248,6 +251,13 @@ class InvariantPointAttentionLayer(nn.Module):
         self.scale_total = self.num_independent_logits**-0.5
         self._packed = None  # (version key, packed weights) for the sm_100a fast path
 
+    def _workspace(self, nbytes, device):
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() < nbytes or ws.device != device:
+            ws = torch.empty((nbytes + 255) // 256 * 256, device=device, dtype=torch.uint8)
+            self._ws = ws
+        return ws[: (nbytes // 4) * 4]
+
     def _weights(self):
         return (self.to_q_scalar.weight, self.to_k_scalar.weight, self.to_v_scalar.weight, self.to_q_point.weight,
                 self.to_k_point.weight, self.to_v_point.weight, self.to_pair_bias.weight, self.gamma,
@@ -292,7 +302,7 @@ class InvariantPointAttentionLayer(nn.Module):
         lib = _lib.lib()
         packed = self._packed_weights(dims)
         nbytes = lib.dab_ipa_sm100_workspace_bytes(ctypes.byref(dims))
-        ws = torch.empty(max(nbytes, 16), device=x.device, dtype=torch.uint8)
+        ws = self._workspace(max(nbytes, 16), x.device)
         y = torch.empty(B, L, D, device=x.device, dtype=torch.float32)
         _lib.check(lib.dab_ipa_fwd_sm100(ctypes.byref(dims), ptr(packed), ptr(x), ptr(e), ptr(r), ptr(t), ptr(y),
                                          ptr(ws), ws.numel(), _lib.stream_ptr()), "dab_ipa_fwd_sm100")
@@ -563,25 +573,37 @@ class DiffAb(nn.Module):
         return {"seq_idx": s, "translations": x, "orientations": O}
 
     def _sample_graphed(self, s, x, O, res_ctx, pair_ctx, generation_mask, t_start, t_stop):
-        """One reverse step captured in a CUDA graph and replayed; the step index lives in a device tensor."""
+        """One reverse step captured in a CUDA graph and replayed; the step index lives in a device
+        tensor.  The graph is cached for as long as the context tensors stay the same objects."""
         B, L = s.shape
         dev = s.device
-        t_buf = torch.full((B,), t_start, device=dev, dtype=torch.int64)
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(2):  # warm-up outside capture (allocator, lazy module init)
-                self.reverse_step(s.clone(), x.clone(), O.clone(), res_ctx, pair_ctx, generation_mask, t_buf,
-                                  self.draw_step_noise(B, L, dev))
-        torch.cuda.current_stream(dev).wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            noise = self.draw_step_noise(B, L, dev)
-            self.reverse_step(s, x, O, res_ctx, pair_ctx, generation_mask, t_buf, noise, inplace=True)
-            t_buf.sub_(1)
+        key = (B, L, res_ctx.data_ptr(), pair_ctx.data_ptr(), generation_mask.data_ptr(), pair_ctx.dtype)
+        cache = getattr(self, "_graph_cache", None)
+        if cache is None or cache["key"] != key:
+            st = {"key": key, "s": torch.empty_like(s), "x": torch.empty_like(x), "O": torch.empty_like(O),
+                  "t": torch.full((B,), t_start, device=dev, dtype=torch.int64),
+                  "keep": (res_ctx, pair_ctx, generation_mask)}
+            st["s"].copy_(s); st["x"].copy_(x); st["O"].copy_(O)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up outside capture (allocator, lazy init, weight packing)
+                    self.reverse_step(st["s"].clone(), st["x"].clone(), st["O"].clone(), res_ctx, pair_ctx,
+                                      generation_mask, st["t"], self.draw_step_noise(B, L, dev))
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                noise = self.draw_step_noise(B, L, dev)
+                self.reverse_step(st["s"], st["x"], st["O"], res_ctx, pair_ctx, generation_mask, st["t"], noise,
+                                  inplace=True)
+                st["t"].sub_(1)
+            st["graph"] = graph
+            self._graph_cache = cache = st
+        cache["s"].copy_(s); cache["x"].copy_(x); cache["O"].copy_(O)
+        cache["t"].fill_(t_start)
         for _ in range(t_start, t_stop - 1, -1):
-            graph.replay()
-        return {"seq_idx": s, "translations": x, "orientations": O}
+            cache["graph"].replay()
+        return {"seq_idx": cache["s"].clone(), "translations": cache["x"].clone(), "orientations": cache["O"].clone()}
 
     @torch.no_grad()
     def sample(self, seq_idx, xyz, orientations, backbone_dihedrals=None, distmat=None, pairwise_dihedrals=None,

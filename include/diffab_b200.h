@@ -39,6 +39,12 @@ extern "C" {
 
 int dab_version(void);
 const char* dab_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's "gpu_launches" claim). */
+long long dab_launch_count(void);
+/* Measurement aid: restrict dab_ipa_fwd_* to a subset of its launches (bit0 projections + frame
+ * transform, bit1 attention core, bit2 to_out) so bench.py can bracket the dominant kernel alone with
+ * CUDA events; the workspace must hold the products of an earlier full call.  Default 7 (all). */
+int dab_debug_set_phase_mask(int mask);
 
 /* ------------------------------------------------------------------ SO(3) maps, so3.py:142-259 */
 /* vector_to_rotation_matrix (so3.py:207-237): v[n,3] -> R[n,3,3], Rodrigues, no epsilon guard. */
