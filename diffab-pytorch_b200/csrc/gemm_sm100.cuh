@@ -1,0 +1,147 @@
+// bf16 x bf16 -> fp32 GEMM on tcgen05 tensor cores with TMA-staged operands (sm_100a).
+//
+//   C[M, N] (fp32, row-major, ldc) = A[M, K] (bf16, K contiguous) * B[N, K]^T (bf16, K contiguous) + bias[N]
+//
+// Used for the IPA projections (K = 128) and to_out (K = 1024), i.e. the nn.Linear layers of
+// diffab_pytorch.py:391-403,464.  One CTA computes a 128 x BN tile: one thread issues the TMA loads
+// (128B-swizzled 64-wide K chunks, ring of kStages) and the tcgen05.mma chain (M = 128, N = BN, K = 16
+// per instruction, fp32 accumulator in TMEM); all four warps then read the accumulator with tcgen05.ld
+// (warp w owns TMEM lanes 32w..32w+31 = tile rows), add the bias and store.
+#pragma once
+#include "common.cuh"
+#include "sm100_prims.cuh"
+
+namespace dab {
+namespace sm100 {
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 64;   // bf16 elements per K chunk = one 128-byte swizzle atom row
+constexpr int kGemmStages = 3;
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = kGemmBM * kGemmBK * 2;  // 16 KB
+  static constexpr int kBBytes = BN * kGemmBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTotal = kGemmStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(128) gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                        const __grid_constant__ CUtensorMap map_b,
+                                                        float* __restrict__ C, int64_t ldc,
+                                                        const float* __restrict__ bias, int K) {
+  static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "BN");
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled operands need 1024-byte aligned tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using S = GemmSmem<BN>;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kGemmStages * S::kStageBytes);
+  uint64_t* empty = full + kGemmStages;
+  uint64_t* done = empty + kGemmStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kGemmBM, n0 = blockIdx.x * BN;
+  constexpr uint32_t kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGemmStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  tcgen05_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nk = K / kGemmBK;
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, BN, 0, 0);
+    auto issue_load = [&](int kc) {
+      int s = kc % kGemmStages;
+      uint8_t* a = smem + s * S::kStageBytes;
+      mbar_arrive_expect_tx(&full[s], S::kStageBytes);
+      tma_load_2d(a, &map_a, &full[s], kc * kGemmBK, m0);
+      tma_load_2d(a + S::kABytes, &map_b, &full[s], kc * kGemmBK, n0);
+    };
+    for (int kc = 0; kc < nk && kc < kGemmStages; ++kc) issue_load(kc);
+    for (int kc = 0; kc < nk; ++kc) {
+      int s = kc % kGemmStages;
+      mbar_wait(&full[s], (kc / kGemmStages) & 1);
+      tcgen05_fence_after_sync();
+      uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
+      uint32_t b_addr = a_addr + S::kABytes;
+#pragma unroll
+      for (int k = 0; k < kGemmBK / 16; ++k) {
+        // K-major, 128B swizzle: 8-row groups are 1024 B apart (SBO); a K step of 16 bf16 is +32 B
+        uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024, kSwizzle128B);
+        uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024, kSwizzle128B);
+        umma_bf16(tmem_base, da, db, idesc, (kc | k) != 0);
+      }
+      umma_commit(&empty[s]);  // slot reusable once these MMAs have read it
+      // refill the slot of the PREVIOUS chunk (its MMAs finish while this chunk's are queued)
+      if (kc >= 1 && kc - 1 + kGemmStages < nk) {
+        mbar_wait(&empty[(kc - 1) % kGemmStages], ((kc - 1) / kGemmStages) & 1);
+        issue_load(kc - 1 + kGemmStages);
+      }
+    }
+    umma_commit(done);
+  }
+  __syncwarp();
+  mbar_wait(done, 0);
+  tcgen05_fence_after_sync();
+
+  // epilogue: thread (warp, lane) owns tile row 32*warp + lane
+  const int row = m0 + warp * 32 + lane;
+  float* crow = C + (int64_t)row * ldc + n0;
+#pragma unroll
+  for (int c0 = 0; c0 < BN; c0 += 16) {
+    float v[16];
+    tmem_ld_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 o;
+      o.x = v[4 * q] + (bias ? __ldg(bias + n0 + c0 + 4 * q) : 0.f);
+      o.y = v[4 * q + 1] + (bias ? __ldg(bias + n0 + c0 + 4 * q + 1) : 0.f);
+      o.z = v[4 * q + 2] + (bias ? __ldg(bias + n0 + c0 + 4 * q + 2) : 0.f);
+      o.w = v[4 * q + 3] + (bias ? __ldg(bias + n0 + c0 + 4 * q + 3) : 0.f);
+      *reinterpret_cast<float4*>(crow + c0 + 4 * q) = o;
+    }
+  }
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_free(tmem_base, kTmemCols);
+}
+
+// Host launcher.  A: [M, K] bf16 row-major (lda elements), B: [N, K] bf16 row-major (ldb), M % 128 == 0,
+// N % BN == 0, K % 64 == 0.
+template <int BN>
+int launch_gemm_bf16(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* C, int64_t ldc, const float* bias,
+                     int M, int N, int K, cudaStream_t stream) {
+  DAB_REQUIRE(M % kGemmBM == 0 && N % BN == 0 && K % kGemmBK == 0 && K > 0, DAB_EUNSUPPORTED,
+              "gemm_bf16: M %% 128, N %% %d, K %% 64 required (M=%d N=%d K=%d)", BN, M, N, K);
+  CUtensorMap ma, mb;
+  uint64_t dims_a[2] = {(uint64_t)K, (uint64_t)M}, str_a[1] = {(uint64_t)lda * 2};
+  uint64_t dims_b[2] = {(uint64_t)K, (uint64_t)N}, str_b[1] = {(uint64_t)ldb * 2};
+  uint32_t box_a[2] = {kGemmBK, kGemmBM}, box_b[2] = {kGemmBK, (uint32_t)BN};
+  if (int rc = make_tensor_map_bf16(&ma, A, 2, dims_a, str_a, box_a, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  if (int rc = make_tensor_map_bf16(&mb, Bm, 2, dims_b, str_b, box_b, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal);
+    attr_done = true;
+  }
+  dim3 grid(N / BN, M / kGemmBM);
+  gemm_bf16_kernel<BN><<<grid, 128, GemmSmem<BN>::kTotal, stream>>>(ma, mb, C, ldc, bias, K);
+  count_launch();
+  return check_launch("gemm_bf16");
+}
+
+}  // namespace sm100
+}  // namespace dab

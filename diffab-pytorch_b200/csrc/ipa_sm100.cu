@@ -1,16 +1,703 @@
-// sm_100a tcgen05/TMA fast path of the IPA layer (placeholder until the kernel lands).
+// sm_100a fast path of one InvariantPointAttentionLayer (inference, train.py configuration:
+// L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8).  Replaces diffab_pytorch.py:389-465 of the reference.
+//
+// Launch sequence per layer (dab_ipa_fwd_sm100):
+//   1. cast x -> bf16
+//   2. projection GEMM on tcgen05 (gemm_sm100.cuh): proj[B*L,1344] = x Wcat^T
+//   3. pack: frame transform (x R + t, centred on the patch centroid), logit scales folded into q,
+//      split-bf16 (hi + lo) of the point coordinates, -0.5 c |k|^2 as extra K columns  -> Qp, Kp, Vp
+//   4. attention core (this file): per CTA = (patch, 16 query rows); TMA-staged tiles, tcgen05.mma with
+//      TMEM accumulators; j (keys) sits on the 128 TMEM lanes:
+//        S^T_h = K_h Q_h^T          (M=128 j, N=16 i, K=32+3*32)   scalar + expanded point-distance logits
+//        bias^T_i = e[i] Wpb^T      (M=128 j, N=16,   K=64)        pair bias, e tile read by TMA once
+//        softmax over j in fp32 (warp butterflies + one shared-memory exchange per row)
+//        pair_i^T = e[i]^T P_i^T    (M=64 c,  N=8 h,  K=128 j)     same shared-memory e tile, MN-major
+//        O^T_h = [Vs|Vp]_h^T P_h^T  (M=64,    N=16 i, K=128 j)       fp16 operands: point coordinates (|v| ~ 40 A)
+//                                                                   keep 11 mantissa bits instead of 8
+//      epilogue: normalise, inverse frame, norms -> concat features (bf16)
+//   5. to_out GEMM on tcgen05: y = concat Wout^T + b
+// Logits never leave the SM; the pair tensor is read from HBM exactly once per layer.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <mutex>
+
 #include "common.cuh"
+#include "gemm_sm100.cuh"
+#include "sm100_prims.cuh"
+
+namespace dab {
+
+// ------------------------------------------------------------------------------------------------
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  EncodeTiledFn enc = get_encode_tiled();
+  DAB_REQUIRE(enc != nullptr, DAB_ELAUNCH, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DAB_REQUIRE(r == CUDA_SUCCESS, DAB_EINVAL, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return DAB_OK;
+}
+
+namespace sm100 {
+
+// fixed configuration of the fast path
+constexpr int L = 128, D = 128, C = 64, H = 8, DS = 32, P = 8;
+constexpr int NS = H * DS;            // 256
+constexpr int NPT = H * P * 3;        // 192
+constexpr int NPROJ = 3 * NS + 3 * NPT;  // 1344
+constexpr int NCAT = NS + H * C + NPT + H * P;  // 1024
+constexpr int QK_W = 96;              // packed q/k row per head: [scalar 32 | point hi 24 + 3 + pad 5 | point lo 24 + pad 8]
+constexpr int V_W = 64;               // packed v row per head:   [scalar 32 | point 24 | pad 8]
+constexpr int IB = 16;                // query rows per CTA
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct PackedOffsets {
+  size_t wcat, wout, wpb, bout, gamma, total;
+};
+__host__ __device__ inline PackedOffsets packed_offsets() {
+  PackedOffsets o;
+  o.wcat = 0;
+  o.wout = o.wcat + (size_t)NPROJ * D * 2;          // 344,064
+  o.wpb = o.wout + (size_t)D * NCAT * 2;            // +262,144
+  o.bout = o.wpb + 2048;
+  o.gamma = o.bout + 512;
+  o.total = o.gamma + 64;
+  return o;
+}
+
+// ---- weight packing (once per layer) --------------------------------------------------------------
+__global__ void pack_weights_kernel(DabIpaWeights w, uint8_t* packed) {
+  const PackedOffsets o = packed_offsets();
+  __nv_bfloat16* wcat = reinterpret_cast<__nv_bfloat16*>(packed + o.wcat);
+  __nv_bfloat16* wout = reinterpret_cast<__nv_bfloat16*>(packed + o.wout);
+  const float* src[6] = {w.w_q_scalar, w.w_k_scalar, w.w_v_scalar, w.w_q_point, w.w_k_point, w.w_v_point};
+  const int rows[6] = {NS, NS, NS, NPT, NPT, NPT};
+  int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  int row0 = 0;
+  for (int s = 0; s < 6; ++s) {
+    for (int i = tid; i < rows[s] * D; i += nth) wcat[row0 * D + i] = __float2bfloat16_rn(src[s][i]);
+    row0 += rows[s];
+  }
+  for (int i = tid; i < D * NCAT; i += nth) wout[i] = __float2bfloat16_rn(w.w_out[i]);
+  // pair-bias operand: B matrix N=16 (8 heads + 8 zero rows) x K=64, K-major, 128B swizzle; scale_total and
+  // log2(e) folded in (diffab_pytorch.py:385-387,439)
+  uint8_t* wpb = packed + o.wpb;
+  const float st = rsqrtf(3.0f) * kLog2e;
+  for (int i = tid; i < 16 * C; i += nth) {
+    int n = i / C, c = i % C;
+    float v = n < H ? w.w_pair_bias[n * C + c] * st : 0.f;
+    uint32_t off = swz128_offset(n, c >> 3) + (c & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(wpb + off) = __float2bfloat16_rn(v);
+  }
+  float* bout = reinterpret_cast<float*>(packed + o.bout);
+  float* gam = reinterpret_cast<float*>(packed + o.gamma);
+  for (int i = tid; i < D; i += nth) bout[i] = w.b_out[i];
+  for (int i = tid; i < H; i += nth) gam[i] = w.gamma[i];
+}
+
+// ---- operand packing (per call) --------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 p = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// grid (L/16, B), 128 threads; warp w handles rows i0 + 4w .. 4w+3, lanes spread over features.
+__global__ void __launch_bounds__(128) ipa_pack_kernel(const float* __restrict__ proj, const float* __restrict__ R,
+                                                       const float* __restrict__ t, const float* __restrict__ gamma,
+                                                       __nv_bfloat16* __restrict__ Qp, __nv_bfloat16* __restrict__ Kp,
+                                                       __nv_bfloat16* __restrict__ Vp, float* __restrict__ tc) {
+  __shared__ float s_part[4][3];
+  __shared__ float s_cen[3];
+  const int b = blockIdx.y, i0 = blockIdx.x * 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // patch centroid of the translations (distances are translation invariant; centring keeps the
+  // expanded |q|^2 + |k|^2 - 2 q.k form well conditioned for patches far from the origin)
+  {
+    const float* tp = t + ((int64_t)b * L + threadIdx.x) * 3;
+    float x = tp[0], y = tp[1], z = tp[2];
+    x = warp_sum(x); y = warp_sum(y); z = warp_sum(z);
+    if (lane == 0) { s_part[warp][0] = x; s_part[warp][1] = y; s_part[warp][2] = z; }
+    __syncthreads();
+    if (threadIdx.x < 3)
+      s_cen[threadIdx.x] = (s_part[0][threadIdx.x] + s_part[1][threadIdx.x] + s_part[2][threadIdx.x] +
+                            s_part[3][threadIdx.x]) * (1.0f / L);
+    __syncthreads();
+  }
+  const float ss = rsqrtf((float)DS), sp = rsqrtf(4.5f * P), st = rsqrtf(3.0f);
+  const int h = lane >> 2, sub = lane & 3;
+  const float ch = st * sp * __ldg(gamma + h) * kLog2e;
+  for (int k = 0; k < 4; ++k) {
+    const int64_t row = (int64_t)b * L + i0 + warp * 4 + k;
+    const float* prow = proj + row * NPROJ;
+    const float* Rr = R + row * 9;
+    float Rm[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) Rm[c] = __ldg(Rr + c);
+    float tcx = __ldg(t + row * 3) - s_cen[0], tcy = __ldg(t + row * 3 + 1) - s_cen[1], tcz = __ldg(t + row * 3 + 2) - s_cen[2];
+    if (lane == 0) { tc[row * 3] = tcx; tc[row * 3 + 1] = tcy; tc[row * 3 + 2] = tcz; }
+    // scalars: lane covers features 8*lane .. 8*lane+7 -> head lane/4, offset (lane%4)*8
+#pragma unroll
+    for (int seg = 0; seg < 3; ++seg) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(prow + seg * NS + lane * 8));
+      const float4 c = __ldg(reinterpret_cast<const float4*>(prow + seg * NS + lane * 8 + 4));
+      const float sc = seg == 0 ? st * ss * kLog2e : 1.0f;   // scale_total * scale_scalar folded into q
+      uint4 o;
+      if (seg == 2) {   // values travel as fp16
+        o.x = pack_h2(a.x, a.y); o.y = pack_h2(a.z, a.w); o.z = pack_h2(c.x, c.y); o.w = pack_h2(c.z, c.w);
+      } else {
+        o.x = pack_bf162(a.x * sc, a.y * sc); o.y = pack_bf162(a.z * sc, a.w * sc);
+        o.z = pack_bf162(c.x * sc, c.y * sc); o.w = pack_bf162(c.z * sc, c.w * sc);
+      }
+      __nv_bfloat16* dst = seg == 0 ? Qp + row * (H * QK_W) + h * QK_W + sub * 8
+                         : seg == 1 ? Kp + row * (H * QK_W) + h * QK_W + sub * 8
+                                    : Vp + row * (H * V_W) + h * V_W + sub * 8;
+      *reinterpret_cast<uint4*>(dst) = o;
+    }
+    // points: lane covers points 2*lane, 2*lane+1 (6 consecutive floats) of head lane/4
+#pragma unroll
+    for (int seg = 0; seg < 3; ++seg) {
+      const float* pp = prow + 3 * NS + seg * NPT + lane * 6;
+      float loc[6];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float2 v = __ldg(reinterpret_cast<const float2*>(pp + 2 * c));
+        loc[2 * c] = v.x; loc[2 * c + 1] = v.y;
+      }
+      float g[6];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {   // euclidean_transform, diffab_pytorch.py:315-324 (row vector @ R + t)
+        float x = loc[3 * q], y = loc[3 * q + 1], z = loc[3 * q + 2];
+        g[3 * q] = x * Rm[0] + y * Rm[3] + z * Rm[6] + tcx;
+        g[3 * q + 1] = x * Rm[1] + y * Rm[4] + z * Rm[7] + tcy;
+        g[3 * q + 2] = x * Rm[2] + y * Rm[5] + z * Rm[8] + tcz;
+      }
+      if (seg == 2) {
+        __nv_bfloat16* dst = Vp + row * (H * V_W) + h * V_W + 32 + sub * 6;
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+        d32[0] = pack_h2(g[0], g[1]); d32[1] = pack_h2(g[2], g[3]); d32[2] = pack_h2(g[4], g[5]);
+        if (sub == 3) *reinterpret_cast<uint4*>(Vp + row * (H * V_W) + h * V_W + 56) = make_uint4(0, 0, 0, 0);
+      } else {
+        const float sc = seg == 0 ? ch : 1.0f;
+        float hi[6], lo[6], n2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          float v = g[c] * sc;
+          hi[c] = __bfloat162float(__float2bfloat16_rn(v));
+          lo[c] = v - hi[c];
+          n2 = fmaf(g[c], g[c], n2);
+        }
+        __nv_bfloat16* base = (seg == 0 ? Qp : Kp) + row * (H * QK_W) + h * QK_W;
+        uint32_t* dh = reinterpret_cast<uint32_t*>(base + 32 + sub * 6);
+        uint32_t* dl = reinterpret_cast<uint32_t*>(base + 64 + sub * 6);
+        dh[0] = pack_bf162(hi[0], hi[1]); dh[1] = pack_bf162(hi[2], hi[3]); dh[2] = pack_bf162(hi[4], hi[5]);
+        dl[0] = pack_bf162(lo[0], lo[1]); dl[1] = pack_bf162(lo[2], lo[3]); dl[2] = pack_bf162(lo[4], lo[5]);
+        // |k|^2 over the 8 points of the head: 4 lanes
+        n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
+        if (sub == 3) {
+          uint4 tail = make_uint4(0, 0, 0, 0);
+          if (seg == 0) {                       // columns that pick up the key-side norm term: (1, 1, 1)
+            tail.x = pack_bf162(1.0f, 1.0f); tail.y = pack_bf162(1.0f, 0.0f);
+          } else {                              // -0.5 c_h |k|^2 split three ways (hi + mid + lo)
+            float nk = -0.5f * ch * n2;
+            float a = __bfloat162float(__float2bfloat16_rn(nk));
+            float m = __bfloat162float(__float2bfloat16_rn(nk - a));
+            float l = nk - a - m;
+            tail.x = pack_bf162(a, m); tail.y = pack_bf162(l, 0.0f);
+          }
+          *reinterpret_cast<uint4*>(base + 56) = tail;
+          *reinterpret_cast<uint4*>(base + 88) = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+  }
+}
+
+// ---- attention core ---------------------------------------------------------------------------------
+struct CoreSmem {
+  // region X (aliased over the four stages of the kernel)
+  static constexpr int kX = 0;
+  static constexpr int kKBuf = 3 * L * 64;           // 24,576: three [128 x 64 B] blocks of one head
+  static constexpr int kQBuf = H * 3 * IB * 64;      // 24,576
+  static constexpr int kQOff = 2 * kKBuf;            // 49,152
+  static constexpr int kXBytes = 2 * kKBuf + kQBuf;  // 73,728
+  static constexpr int kEStage = L * C * 2;          // 16,384
+  static constexpr int kEStages = 4;
+  static constexpr int kVBuf = L * V_W * 2;          // 16,384
+  // region Y: probabilities per head, B operand of the O^T MMA: [h][kb(2)][16 rows][128 B]
+  static constexpr int kPh = kXBytes;
+  static constexpr int kPhBytes = H * 2 * IB * 128;  // 32,768
+  // probabilities of one row, B operand of the pair MMA: [buf(2)][kb(2)][8 rows][128 B]
+  static constexpr int kPi = kPh + kPhBytes;
+  static constexpr int kPiBytes = 2 * 2048;
+  static constexpr int kWpb = kPi + kPiBytes;        // 2,048
+  static constexpr int kMisc = kWpb + 2048;
+  static constexpr int kRedMax = kMisc;              // [2][4][8] f32
+  static constexpr int kRedSum = kRedMax + 256;      // [2][4][16] f32: sums of the bf16- and of the fp16-rounded p
+  static constexpr int kLsum = kRedSum + 512;        // [16][8] f32
+  static constexpr int kBars = kLsum + 512;          // 32 mbarriers
+  static constexpr int kTmemSlot = kBars + 32 * 8;
+  static constexpr int kTotal = kTmemSlot + 16;
+};
+static_assert(CoreSmem::kEStages * CoreSmem::kEStage <= CoreSmem::kXBytes, "e ring must fit region X");
+static_assert(CoreSmem::kTotal <= 113 * 1024, "two CTAs per SM");
+
+enum Bar { K_FULL = 0, K_EMPTY = 2, Q_FULL = 4, S_DONE = 5, E_FULL = 6, E_EMPTY = 10, BIAS = 14, PAIR = 17,
+           V_FULL = 19, V_EMPTY = 21, O_DONE = 23, N_BARS = 24 };
+
+// TMEM columns
+constexpr uint32_t kColS = 0, kColBias = 128, kColPair = 176, kTmemCols = 256;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Reduce 8 per-lane values across the warp with 9 shuffles; lane ends up with the result for head
+// hsel = 4*bit4 + 2*bit3 + bit2 of its lane id (every group of 4 lanes holds the same head).
+template <bool IS_MAX>
+__device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
+  auto op = [](float a, float b) { return IS_MAX ? fmaxf(a, b) : a + b; };
+  const bool u1 = lane & 16, u2 = lane & 8, u3 = lane & 4;
+  float a[4], bq[2];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float send = u1 ? v[k] : v[k + 4], keep = u1 ? v[k + 4] : v[k];
+    a[k] = op(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    float send = u2 ? a[k] : a[k + 2], keep = u2 ? a[k + 2] : a[k];
+    bq[k] = op(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+  }
+  float send = u3 ? bq[0] : bq[1], keep = u3 ? bq[1] : bq[0];
+  float c = op(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+  c = op(c, __shfl_xor_sync(0xffffffffu, c, 2));
+  c = op(c, __shfl_xor_sync(0xffffffffu, c, 1));
+  return c;
+}
+
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(128, 2)
+ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_e,
+                const uint8_t* __restrict__ wpb_op, const float* __restrict__ tc, const float* __restrict__ R,
+                __nv_bfloat16* __restrict__ cat) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using S = CoreSmem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
+  float* red_max = reinterpret_cast<float*>(smem + S::kRedMax);
+  float* red_sum = reinterpret_cast<float*>(smem + S::kRedSum);
+  float* lsum = reinterpret_cast<float*>(smem + S::kLsum);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, i0 = blockIdx.x * IB;
+  const int64_t row0 = (int64_t)b * L + i0;       // first query row (global residue index)
+  const uint32_t smem_base = smem_u32(smem);
+  if ((smem_base & 1023u) != 0) asm volatile("trap;");
+
+  if (tid == 0) {
+    for (int i = 0; i < N_BARS; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
+  // pair-bias operand (2 KB, pre-swizzled by pack_weights): plain copy, then make it visible to the MMA proxy
+  reinterpret_cast<uint4*>(smem + S::kWpb)[tid] = __ldg(reinterpret_cast<const uint4*>(wpb_op) + tid);
+  fence_proxy_async_smem();
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  tcgen05_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_lane = tmem + ((uint32_t)(warp * 32) << 16);
+
+  constexpr uint32_t kIdescS = make_idesc_bf16(128, 16, 0, 0);     // S^T and bias^T
+  constexpr uint32_t kIdescPair = make_idesc_bf16(64, 8, 1, 0);    // A = e tile, MN-major
+  constexpr uint32_t kIdescO = make_idesc_f16(64, 16, 1, 0);       // A = V tile, MN-major, fp16 operands
+
+  // =========================== stage 1: S^T_h = K_h Q_h^T for the 8 heads ===========================
+  if (tid == 0) {
+    uint8_t* qbuf = smem + S::kQOff;
+    mbar_arrive_expect_tx(&bars[Q_FULL], S::kQBuf);
+    for (int blk = 0; blk < H * 3; ++blk)    // [blk][16 rows][64 B], 64B swizzle
+      tma_load_2d(qbuf + blk * (IB * 64), &map_q, &bars[Q_FULL], blk * 32, (int)row0);
+    auto load_k = [&](int h) {
+      int s = h & 1;
+      uint8_t* kb = smem + s * S::kKBuf;
+      mbar_arrive_expect_tx(&bars[K_FULL + s], S::kKBuf);
+      for (int blk = 0; blk < 3; ++blk)
+        tma_load_2d(kb + blk * (L * 64), &map_k, &bars[K_FULL + s], (h * 3 + blk) * 32, b * L);
+    };
+    load_k(0);
+    load_k(1);
+    mbar_wait(&bars[Q_FULL], 0);
+    for (int h = 0; h < H; ++h) {
+      const int s = h & 1;
+      mbar_wait(&bars[K_FULL + s], (h >> 1) & 1);
+      tcgen05_fence_after_sync();
+      const uint32_t ka = smem_base + s * S::kKBuf;
+      const uint32_t qa = smem_base + S::kQOff + h * 3 * (IB * 64);
+      // (A block, B block): scalar.scalar, hi.hi (+ norm columns), hi.lo, lo.hi
+      const int ablk[4] = {0, 1, 1, 2}, bblk[4] = {0, 1, 2, 1};
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          uint64_t da = make_smem_desc(ka + ablk[m] * (L * 64) + k * 32, 16, 512, kSwizzle64B);
+          uint64_t db = make_smem_desc(qa + bblk[m] * (IB * 64) + k * 32, 16, 512, kSwizzle64B);
+          umma_bf16(tmem + kColS + h * 16, da, db, kIdescS, (m | k) != 0);
+        }
+      umma_commit(&bars[K_EMPTY + s]);
+      if (h + 2 < H) {
+        mbar_wait(&bars[K_EMPTY + s], (h >> 1) & 1);
+        load_k(h + 2);
+      }
+    }
+    umma_commit(&bars[S_DONE]);
+    mbar_wait(&bars[S_DONE], 0);   // region X is free again
+    // ---- stage 2 prologue: first four e rows, bias of rows 0 and 1
+    for (int r = 0; r < S::kEStages; ++r) {
+      mbar_arrive_expect_tx(&bars[E_FULL + r], S::kEStage);
+      tma_load_2d(smem + r * S::kEStage, &map_e, &bars[E_FULL + r], 0, (int)((row0 + r) * L));
+    }
+  }
+  auto issue_bias = [&](int i) {   // thread 0 only
+    const int st = i % S::kEStages;
+    mbar_wait(&bars[E_FULL + st], (i / S::kEStages) & 1);
+    tcgen05_fence_after_sync();
+    const uint32_t ea = smem_base + st * S::kEStage, wa = smem_base + S::kWpb;
+#pragma unroll
+    for (int k = 0; k < C / 16; ++k) {
+      uint64_t da = make_smem_desc(ea + k * 32, 16, 1024, kSwizzle128B);
+      uint64_t db = make_smem_desc(wa + k * 32, 16, 1024, kSwizzle128B);
+      umma_bf16(tmem + kColBias + (i % 3) * 16, da, db, kIdescS, k != 0);
+    }
+    umma_commit(&bars[BIAS + (i % 3)]);
+  };
+  if (tid == 0) { issue_bias(0); issue_bias(1); }
+  __syncthreads();
+  tcgen05_fence_after_sync();
+
+  // =========================== stage 2: per query row ===========================
+  float sreg[H][4];
+  const int hsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  auto drain_pair = [&](int i) {   // normalise and store the pair aggregation of row i
+    mbar_wait(&bars[PAIR + (i & 1)], (i >> 1) & 1);
+    tcgen05_fence_after_sync();
+    float v[8];
+    tmem_ld_x8(tmem_lane + kColPair + (i & 1) * 8, v);
+    tmem_wait_ld();
+    const float* rs = red_sum + (i & 1) * 64;   // [4 warps][16]: 0-7 sum of bf16(p) (pair), 8-15 sum of fp16(p) (values)
+    float inv[8];
+#pragma unroll
+    for (int h = 0; h < H; ++h) inv[h] = 1.0f / (rs[h] + rs[16 + h] + rs[32 + h] + rs[48 + h]);
+    if (tid < H) lsum[i * H + tid] = rs[8 + tid] + rs[24 + tid] + rs[40 + tid] + rs[56 + tid];
+    if (lane < 16) {
+      __nv_bfloat16* dst = cat + (row0 + i) * NCAT + NS + warp * 16 + lane;
+#pragma unroll
+      for (int h = 0; h < H; ++h) dst[h * C] = __float2bfloat16_rn(v[h] * inv[h]);
+    }
+    tcgen05_fence_before_sync();
+  };
+
+  for (int i = 0; i < IB; ++i) {
+    if (tid == 0 && i + 2 < IB) issue_bias(i + 2);
+    __syncwarp();   // tcgen05.ld is .sync.aligned: the warp must be converged
+    if ((i & 3) == 0) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) tmem_ld_x4(tmem_lane + kColS + h * 16 + i, sreg[h]);
+    }
+    mbar_wait(&bars[BIAS + (i % 3)], (i / 3) & 1);
+    tcgen05_fence_after_sync();
+    float lg[8];
+    tmem_ld_x8(tmem_lane + kColBias + (i % 3) * 16, lg);
+    tmem_wait_ld();
+#pragma unroll
+    for (int h = 0; h < H; ++h) lg[h] += sreg[h][i & 3];
+    // ---- softmax over j (the 128 lanes of the CTA), in log2 units
+    float wm = warp_reduce8<true>(lg, lane);
+    float* rm = red_max + (i & 1) * 32;
+    if ((lane & 3) == 0) rm[warp * 8 + hsel] = wm;
+    __syncthreads();
+    float p[8], pb[8], ph16[8];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      float m = fmaxf(fmaxf(rm[h], rm[8 + h]), fmaxf(rm[16 + h], rm[24 + h]));
+      p[h] = ex2(lg[h] - m);
+      pb[h] = __bfloat162float(__float2bfloat16_rn(p[h]));   // the values the tensor cores will see:
+      ph16[h] = __half2float(__float2half_rn(p[h]));          // normalise each aggregation by its own sum
+    }
+    float wsb = warp_reduce8<false>(pb, lane), wsh = warp_reduce8<false>(ph16, lane);
+    if ((lane & 3) == 0) {
+      red_sum[(i & 1) * 64 + warp * 16 + hsel] = wsb;
+      red_sum[(i & 1) * 64 + warp * 16 + 8 + hsel] = wsh;
+    }
+    // ---- probabilities -> shared memory in the two operand layouts (K-major, 128B swizzle)
+    {
+      const uint32_t kb = tid >> 6, chunk = (tid & 63) >> 3, e2 = (tid & 7) * 2;
+      uint8_t* pi = smem + S::kPi + (i & 1) * 2048 + kb * 1024;
+      uint8_t* ph = smem + S::kPh + kb * (IB * 128);
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        *reinterpret_cast<__nv_bfloat16*>(pi + swz128_offset(h, chunk) + e2) = __float2bfloat16_rn(p[h]);
+        *reinterpret_cast<__half*>(ph + h * (2 * IB * 128) + swz128_offset(i, chunk) + e2) = __float2half_rn(p[h]);
+      }
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tcgen05_fence_after_sync();
+      const int st = i % S::kEStages;
+      const uint32_t ea = smem_base + st * S::kEStage, pa = smem_base + S::kPi + (i & 1) * 2048;
+#pragma unroll
+      for (int k = 0; k < L / 16; ++k) {
+        // A: e[i] tile [j][c] read MN-major (M = c, 64 wide = one 128 B row; K = j, 16 rows = 2048 B per step)
+        uint64_t da = make_smem_desc(ea + k * 2048, 1024, 1024, kSwizzle128B);
+        uint64_t db = make_smem_desc(pa + (k >> 2) * 1024 + (k & 3) * 32, 16, 1024, kSwizzle128B);
+        umma_bf16(tmem + kColPair + (i & 1) * 8, da, db, kIdescPair, k != 0);
+      }
+      umma_commit(&bars[PAIR + (i & 1)]);
+      umma_commit(&bars[E_EMPTY + st]);
+      if (i >= 1 && i + 3 < IB) {   // refill the stage released by row i-1 with row i+3
+        const int sp = (i - 1) % S::kEStages;
+        mbar_wait(&bars[E_EMPTY + sp], ((i - 1) / S::kEStages) & 1);
+        mbar_arrive_expect_tx(&bars[E_FULL + sp], S::kEStage);
+        tma_load_2d(smem + sp * S::kEStage, &map_e, &bars[E_FULL + sp], 0, (int)((row0 + i + 3) * L));
+      }
+    }
+    __syncwarp();
+    if (i >= 1) drain_pair(i - 1);
+  }
+  drain_pair(IB - 1);
+  tcgen05_fence_before_sync();
+  __syncthreads();
+
+  // =========================== stage 3: O^T_h = [Vs|Vp]_h^T P_h^T ===========================
+  if (tid == 0) {
+    tcgen05_fence_after_sync();
+    auto load_v = [&](int h) {
+      int s = h & 1;
+      mbar_arrive_expect_tx(&bars[V_FULL + s], S::kVBuf);
+      tma_load_2d(smem + s * S::kVBuf, &map_v, &bars[V_FULL + s], h * V_W, b * L);
+    };
+    load_v(0);
+    load_v(1);
+    for (int h = 0; h < H; ++h) {
+      const int s = h & 1;
+      mbar_wait(&bars[V_FULL + s], (h >> 1) & 1);
+      tcgen05_fence_after_sync();
+      const uint32_t va = smem_base + s * S::kVBuf, pa = smem_base + S::kPh + h * (2 * IB * 128);
+#pragma unroll
+      for (int k = 0; k < L / 16; ++k) {
+        uint64_t da = make_smem_desc(va + k * 2048, 1024, 1024, kSwizzle128B);
+        uint64_t db = make_smem_desc(pa + (k >> 2) * (IB * 128) + (k & 3) * 32, 16, 1024, kSwizzle128B);
+        umma_bf16(tmem + kColS + h * 16, da, db, kIdescO, k != 0);
+      }
+      umma_commit(&bars[V_EMPTY + s]);
+      if (h + 2 < H) {
+        mbar_wait(&bars[V_EMPTY + s], (h >> 1) & 1);
+        load_v(h + 2);
+      }
+    }
+    umma_commit(&bars[O_DONE]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[O_DONE], 0);
+  tcgen05_fence_after_sync();
+
+  // =========================== stage 4: epilogue ===========================
+  // M = 64 accumulator layout: row d lives in lane (d % 16) of warp d / 16
+  float* s_og = reinterpret_cast<float*>(smem);   // [16 i][8 h][24] global-frame points (region X is free)
+  {
+    const int d = warp * 16 + lane;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      float o[16];
+      tmem_ld_x16(tmem_lane + kColS + h * 16, o);
+      tmem_wait_ld();
+      if (lane < 16) {
+#pragma unroll
+        for (int i = 0; i < IB; ++i) {
+          float v = o[i] / lsum[i * H + h];
+          if (d < DS) cat[(row0 + i) * NCAT + h * DS + d] = __float2bfloat16_rn(v);
+          else if (d < DS + 3 * P) s_og[(i * H + h) * 24 + (d - DS)] = v;
+        }
+      }
+    }
+  }
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  // inverse frame + norms (diffab_pytorch.py:327-336,453-457): ol[c'] = sum_k (og[k] - t[k]) R[c'][k]
+  for (int task = tid; task < IB * H * P; task += 128) {
+    const int i = task >> 6, hp = task & 63;
+    const int64_t row = row0 + i;
+    const float* g = s_og + (i * H + (hp >> 3)) * 24 + (hp & 7) * 3;
+    const float* Rr = R + row * 9;
+    float gx = g[0] - __ldg(tc + row * 3), gy = g[1] - __ldg(tc + row * 3 + 1), gz = g[2] - __ldg(tc + row * 3 + 2);
+    float lx = gx * __ldg(Rr) + gy * __ldg(Rr + 1) + gz * __ldg(Rr + 2);
+    float ly = gx * __ldg(Rr + 3) + gy * __ldg(Rr + 4) + gz * __ldg(Rr + 5);
+    float lz = gx * __ldg(Rr + 6) + gy * __ldg(Rr + 7) + gz * __ldg(Rr + 8);
+    __nv_bfloat16* dst = cat + row * NCAT + NS + H * C;
+    dst[hp * 3] = __float2bfloat16_rn(lx);
+    dst[hp * 3 + 1] = __float2bfloat16_rn(ly);
+    dst[hp * 3 + 2] = __float2bfloat16_rn(lz);
+    dst[NPT + hp] = __float2bfloat16_rn(sqrtf(lx * lx + ly * ly + lz * lz));
+  }
+  __syncthreads();
+  if (warp == 0) tmem_free(tmem, kTmemCols);
+}
+
+// ---- workspace --------------------------------------------------------------------------------------
+struct Ws {
+  __nv_bfloat16 *xb, *Qp, *Kp, *Vp, *cat;
+  float *proj, *tc;
+  size_t bytes;
+};
+static Ws carve_ws(int B, void* base) {
+  auto al = [](size_t n) { return (n + 1023) / 1024 * 1024; };
+  size_t rows = (size_t)B * L;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  Ws w;
+  w.xb = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * D * 2);
+  w.proj = reinterpret_cast<float*>(p); p += al(rows * NPROJ * 4);
+  w.Qp = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * H * QK_W * 2);
+  w.Kp = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * H * QK_W * 2);
+  w.Vp = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * H * V_W * 2);
+  w.tc = reinterpret_cast<float*>(p); p += al(rows * 3 * 4);
+  w.cat = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * NCAT * 2);
+  w.bytes = (size_t)(p - reinterpret_cast<uint8_t*>(base));
+  return w;
+}
+
+static bool shape_ok(const DabIpaDims* d) {
+  return d && d->L == L && d->D == D && d->C == C && d->H == H && d->ds == DS && d->Pq == P && d->Pv == P && d->B >= 0;
+}
+
+}  // namespace sm100
+}  // namespace dab
+
+using namespace dab;
+using namespace dab::sm100;
 
 extern "C" {
-size_t dab_ipa_packed_bytes(const DabIpaDims*) { return 0; }
-int dab_ipa_pack_weights(const DabIpaDims*, const DabIpaWeights*, void*, void*) {
-  dab::set_error("dab_ipa_pack_weights: sm_100a fast path not built");
-  return DAB_EUNSUPPORTED;
+
+size_t dab_ipa_packed_bytes(const DabIpaDims* d) { return shape_ok(d) ? packed_offsets().total : 0; }
+
+int dab_ipa_pack_weights(const DabIpaDims* d, const DabIpaWeights* w, void* packed, void* stream) {
+  DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
+              "dab_ipa_pack_weights: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
+  DAB_REQUIRE(w && packed && w->w_q_scalar && w->w_k_scalar && w->w_v_scalar && w->w_q_point && w->w_k_point &&
+                  w->w_v_point && w->w_pair_bias && w->gamma && w->w_out && w->b_out,
+              DAB_EINVAL, "dab_ipa_pack_weights: null pointer");
+  DAB_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 1023) == 0, DAB_EINVAL, "dab_ipa_pack_weights: packed buffer must be 1024-byte aligned");
+  pack_weights_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(*w, reinterpret_cast<uint8_t*>(packed));
+  count_launch();
+  return check_launch("dab_ipa_pack_weights");
 }
-size_t dab_ipa_sm100_workspace_bytes(const DabIpaDims*) { return 0; }
-int dab_ipa_fwd_sm100(const DabIpaDims*, const void*, const float*, const void*, const float*, const float*, float*,
-                      void*, size_t, void*) {
-  dab::set_error("dab_ipa_fwd_sm100: sm_100a fast path not built");
-  return DAB_EUNSUPPORTED;
+
+size_t dab_ipa_sm100_workspace_bytes(const DabIpaDims* d) { return shape_ok(d) ? carve_ws(d->B, nullptr).bytes : 0; }
+
+int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16, const float* R,
+                      const float* t, float* y, void* workspace, size_t workspace_bytes, void* stream) {
+  DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
+              "dab_ipa_fwd_sm100: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
+  if (d->B == 0) return DAB_OK;
+  DAB_REQUIRE(packed && x && e_bf16 && R && t && y && workspace, DAB_EINVAL, "dab_ipa_fwd_sm100: null pointer");
+  DAB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0 && (reinterpret_cast<uintptr_t>(packed) & 1023) == 0 &&
+                  (reinterpret_cast<uintptr_t>(e_bf16) & 127) == 0 && aligned16(x) && aligned16(y),
+              DAB_EINVAL, "dab_ipa_fwd_sm100: misaligned pointer (workspace/packed 1024 B, e 128 B, x/y 16 B)");
+  const int B = d->B, M = B * L;
+  Ws ws = carve_ws(B, workspace);
+  DAB_REQUIRE(workspace_bytes >= ws.bytes, DAB_EWORKSPACE, "dab_ipa_fwd_sm100: workspace %zu < %zu", workspace_bytes, ws.bytes);
+  const PackedOffsets po = packed_offsets();
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int phases = phase_mask();
+  if (phases & 1) {
+    if (int rc = dab_cast_f32_to_bf16(x, ws.xb, (int64_t)M * D, stream)) return rc;
+    if (int rc = launch_gemm_bf16<64>(ws.xb, D, pk + po.wcat, D, ws.proj, NPROJ, nullptr, M, NPROJ, D, s)) return rc;
+    ipa_pack_kernel<<<dim3(L / 16, B), 128, 0, s>>>(ws.proj, R, t, reinterpret_cast<const float*>(pk + po.gamma), ws.Qp,
+                                                     ws.Kp, ws.Vp, ws.tc);
+    count_launch();
+  }
+  if (phases & 2) {
+    CUtensorMap mq, mk, mv, me;
+    uint64_t dqk[2] = {(uint64_t)H * QK_W, (uint64_t)M}, sqk[1] = {(uint64_t)H * QK_W * 2};
+    uint32_t bq[2] = {32, IB}, bk[2] = {32, L};
+    if (int rc = make_tensor_map_bf16(&mq, ws.Qp, 2, dqk, sqk, bq, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    if (int rc = make_tensor_map_bf16(&mk, ws.Kp, 2, dqk, sqk, bk, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    uint64_t dv[2] = {(uint64_t)H * V_W, (uint64_t)M}, sv[1] = {(uint64_t)H * V_W * 2};
+    uint32_t bv[2] = {V_W, L};
+    if (int rc = make_tensor_map_bf16(&mv, ws.Vp, 2, dv, sv, bv, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    uint64_t de[2] = {(uint64_t)C, (uint64_t)M * L}, se[1] = {(uint64_t)C * 2};
+    uint32_t be[2] = {C, L};
+    if (int rc = make_tensor_map_bf16(&me, e_bf16, 2, de, se, be, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(ipa_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CoreSmem::kTotal);
+      attr_done = true;
+    }
+    ipa_core_kernel<<<dim3(L / IB, B), 128, CoreSmem::kTotal, s>>>(mq, mk, mv, me, pk + po.wpb, ws.tc, R, ws.cat);
+    count_launch();
+  }
+  if (phases & 4) {
+    if (int rc = launch_gemm_bf16<64>(ws.cat, NCAT, pk + po.wout, NCAT, y, D, reinterpret_cast<const float*>(pk + po.bout),
+                                      M, D, NCAT, s))
+      return rc;
+  }
+  return check_launch("dab_ipa_fwd_sm100");
 }
+
+/* Test hook: C[M,N] = A[M,K] B[N,K]^T + bias on the tcgen05 GEMM (bf16 in, fp32 out). */
+int dab_debug_gemm_bf16(const void* A, const void* Bm, float* Cm, const float* bias, int M, int N, int K, void* stream) {
+  DAB_REQUIRE(A && Bm && Cm, DAB_EINVAL, "dab_debug_gemm_bf16: null pointer");
+  return launch_gemm_bf16<64>(A, K, Bm, K, Cm, N, bias, M, N, K, (cudaStream_t)stream);
 }
+
+/* Test hook: run only the packing stage on a given fp32 projection tensor. */
+int dab_debug_ipa_pack(const float* proj, const float* R, const float* t, const float* gamma, int B, void* Qp, void* Kp,
+                       void* Vp, float* tc, void* stream) {
+  DAB_REQUIRE(proj && R && t && gamma && Qp && Kp && Vp && tc && B > 0, DAB_EINVAL, "dab_debug_ipa_pack: bad argument");
+  ipa_pack_kernel<<<dim3(L / 16, B), 128, 0, (cudaStream_t)stream>>>(proj, R, t, gamma, (__nv_bfloat16*)Qp,
+                                                                      (__nv_bfloat16*)Kp, (__nv_bfloat16*)Vp, tc);
+  count_launch();
+  return check_launch("dab_debug_ipa_pack");
+}
+
+}  // extern "C"

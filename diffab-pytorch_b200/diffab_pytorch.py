@@ -170,7 +170,7 @@ class _IpaFunction(torch.autograd.Function):
     """fp32 IPA layer: ``dab_ipa_fwd_f32`` / ``dab_ipa_bwd_f32``."""
 
     @staticmethod
-    def forward(ctx, layer, x, e, r, t, *weights):
+    def forward(ctx, layer, need_bwd, x, e, r, t, *weights):
         x = _lib.dev(x, torch.float32, "x")
         e = _lib.dev(e, torch.float32, "e")
         r = _lib.dev(r, torch.float32, "r")
@@ -180,7 +180,6 @@ class _IpaFunction(torch.autograd.Function):
         if e.shape != (B, L, L, layer.d_pair_emb) or r.shape != (B, L, 3, 3) or t.shape != (B, L, 3):
             raise ValueError(f"IPA shape mismatch: x {tuple(x.shape)} e {tuple(e.shape)} r {tuple(r.shape)} t {tuple(t.shape)}")
         dims = _ipa_structs(layer, B, L)
-        need_bwd = any(ctx.needs_input_grad)
         lib = _lib.lib()
         nbytes = lib.dab_ipa_f32_workspace_bytes(ctypes.byref(dims), 1 if need_bwd else 0)
         if need_bwd:   # kept for the backward pass: must be private to this call
@@ -201,7 +200,7 @@ class _IpaFunction(torch.autograd.Function):
     def backward(ctx, dy):
         x, e, r, t, ws, *weights = ctx.saved_tensors
         layer = ctx.layer
-        if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
+        if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
             raise NotImplementedError("gradients w.r.t. the frames (r, t) are not provided: in DiffAb they are the "
                                       "noised frames and carry no gradient (diffab_pytorch.py:824-854)")
         B, L, D = x.shape
@@ -215,7 +214,7 @@ class _IpaFunction(torch.autograd.Function):
         _lib.check(_lib.lib().dab_ipa_bwd_f32(ctypes.byref(dims), ctypes.byref(wstruct), ptr(x), ptr(e), ptr(r),
                                               ptr(t), ptr(dy), ptr(dx), ptr(de), ctypes.byref(gstruct), ptr(ws),
                                               ws.numel() * 4, _lib.stream_ptr()), "dab_ipa_bwd_f32")
-        return (None, dx, de, None, None, *grads)
+        return (None, None, dx, de, None, None, *grads)
 
 
 class InvariantPointAttentionLayer(nn.Module):
@@ -266,7 +265,10 @@ class InvariantPointAttentionLayer(nn.Module):
     def forward(self, x, e, r, t):
         if e.dtype == torch.bfloat16:
             return self.forward_fast(x, e, r, t)
-        return _IpaFunction.apply(self, x, e, r, t, *self._weights())
+        ws = self._weights()
+        need_bwd = torch.is_grad_enabled() and (x.requires_grad or e.requires_grad or r.requires_grad or
+                                                t.requires_grad or any(w.requires_grad for w in ws))
+        return _IpaFunction.apply(self, need_bwd, x, e, r, t, *ws)
 
     # ---- sm_100a fast path (inference; train.py configuration only) ----
     def fast_path_supported(self, L):

@@ -162,6 +162,11 @@ size_t dab_ipa_sm100_workspace_bytes(const DabIpaDims* d);
 int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
                       const float* R, const float* t, float* y, void* workspace, size_t workspace_bytes,
                       void* stream);
+/* Test hooks of the sm_100a path (used by tests/ only): the tcgen05 GEMM C[M,N] = A[M,K] B[N,K]^T + bias
+ * (bf16 in, fp32 out; M % 128 == 0, N % 64 == 0, K % 64 == 0) and the operand-packing stage alone. */
+int dab_debug_gemm_bf16(const void* A, const void* Bm, float* C, const float* bias, int M, int N, int K, void* stream);
+int dab_debug_ipa_pack(const float* proj, const float* R, const float* t, const float* gamma, int B, void* Qp, void* Kp,
+                       void* Vp, float* tc, void* stream);
 /* fp32 -> bf16 conversion of the pair tensor (once per patch; round-to-nearest-even). */
 int dab_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
 
