@@ -258,16 +258,19 @@ struct CoreSmem {
   static constexpr int kMisc = kWpb + 2048;
   static constexpr int kRedMax = kMisc;              // [2][4][8] f32
   static constexpr int kRedSum = kRedMax + 256;      // [2][4][16] f32: sums of the bf16- and of the fp16-rounded p
-  static constexpr int kLsum = kRedSum + 512;        // [16][8] f32
-  static constexpr int kBars = kLsum + 512;          // 32 mbarriers
+  static constexpr int kInvO = kRedSum + 512;        // [16][8] f32: 1 / sum_j fp16(p)
+  static constexpr int kBars = kInvO + 512;          // 32 mbarriers
   static constexpr int kTmemSlot = kBars + 32 * 8;
   static constexpr int kTotal = kTmemSlot + 16;
+  // warp-private 512 B staging tiles for coalesced stores: the 8 KB of region X the e ring leaves unused
+  static constexpr int kStaging = kEStages * kEStage;
 };
+static_assert(CoreSmem::kStaging + 4 * 512 <= CoreSmem::kXBytes, "staging must fit behind the e ring");
 static_assert(CoreSmem::kEStages * CoreSmem::kEStage <= CoreSmem::kXBytes, "e ring must fit region X");
 static_assert(CoreSmem::kTotal <= 113 * 1024, "two CTAs per SM");
 
 enum Bar { K_FULL = 0, K_EMPTY = 2, Q_FULL = 4, S_DONE = 5, E_FULL = 6, E_EMPTY = 10, BIAS = 14, PAIR = 17,
-           V_FULL = 19, V_EMPTY = 21, O_DONE = 23, N_BARS = 24 };
+           V_FULL = 19, V_EMPTY = 21, O_DONE = 23, P_READY = 24, N_BARS = 26 };
 
 // TMEM columns
 constexpr uint32_t kColS = 0, kColBias = 128, kColPair = 176, kTmemCols = 256;
@@ -311,18 +314,25 @@ __device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, float (&v)[4]) {
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__global__ void __launch_bounds__(128, 2)
+// Warp roles: warps 0-3 = 128 softmax/epilogue threads (thread t owns key j = t = TMEM lane t);
+// warp 4 lane 0 = issuer of every TMA load and tcgen05.mma.  The roles meet only at mbarriers.
+__global__ void __launch_bounds__(160, 2)
 ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_e,
                 const uint8_t* __restrict__ wpb_op, const float* __restrict__ tc, const float* __restrict__ R,
-                __nv_bfloat16* __restrict__ cat) {
+                __nv_bfloat16* __restrict__ cat, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  // optional per-CTA timeline: slot k of CTA c at dbg[c * 64 + k]
+  long long* dbg_cta = dbg ? dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
+#define DAB_STAMP(k) do { if (dbg_cta && threadIdx.x == 0) dbg_cta[(k)] = clock64(); } while (0)
+#define DAB_STAMP_ISSUER(k) do { if (dbg_cta) dbg_cta[(k)] = clock64(); } while (0)
+  DAB_STAMP(0);
   using S = CoreSmem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
   float* red_max = reinterpret_cast<float*>(smem + S::kRedMax);
   float* red_sum = reinterpret_cast<float*>(smem + S::kRedSum);
-  float* lsum = reinterpret_cast<float*>(smem + S::kLsum);
+  float* inv_o = reinterpret_cast<float*>(smem + S::kInvO);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, i0 = blockIdx.x * IB;
@@ -331,257 +341,330 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if ((smem_base & 1023u) != 0) asm volatile("trap;");
 
   if (tid == 0) {
-    for (int i = 0; i < N_BARS; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < N_BARS; ++i) mbar_init(&bars[i], (i == P_READY || i == P_READY + 1) ? 128u : 1u);
     fence_barrier_init();
-    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
   // pair-bias operand (2 KB, pre-swizzled by pack_weights): plain copy, then make it visible to the MMA proxy
-  reinterpret_cast<uint4*>(smem + S::kWpb)[tid] = __ldg(reinterpret_cast<const uint4*>(wpb_op) + tid);
+  if (tid < 128) reinterpret_cast<uint4*>(smem + S::kWpb)[tid] = __ldg(reinterpret_cast<const uint4*>(wpb_op) + tid);
   fence_proxy_async_smem();
   tcgen05_fence_before_sync();
   __syncthreads();
   tcgen05_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  DAB_STAMP(1);
 
-  constexpr uint32_t kIdescS = make_idesc_bf16(128, 16, 0, 0);     // S^T and bias^T
-  constexpr uint32_t kIdescPair = make_idesc_bf16(64, 8, 1, 0);    // A = e tile, MN-major
-  constexpr uint32_t kIdescO = make_idesc_f16(64, 16, 1, 0);       // A = V tile, MN-major, fp16 operands
-
-  // =========================== stage 1: S^T_h = K_h Q_h^T for the 8 heads ===========================
-  if (tid == 0) {
-    uint8_t* qbuf = smem + S::kQOff;
-    mbar_arrive_expect_tx(&bars[Q_FULL], S::kQBuf);
-    for (int blk = 0; blk < H * 3; ++blk)    // [blk][16 rows][64 B], 64B swizzle
-      tma_load_2d(qbuf + blk * (IB * 64), &map_q, &bars[Q_FULL], blk * 32, (int)row0);
-    auto load_k = [&](int h) {
-      int s = h & 1;
-      uint8_t* kb = smem + s * S::kKBuf;
-      mbar_arrive_expect_tx(&bars[K_FULL + s], S::kKBuf);
-      for (int blk = 0; blk < 3; ++blk)
-        tma_load_2d(kb + blk * (L * 64), &map_k, &bars[K_FULL + s], (h * 3 + blk) * 32, b * L);
-    };
-    load_k(0);
-    load_k(1);
-    mbar_wait(&bars[Q_FULL], 0);
-    for (int h = 0; h < H; ++h) {
-      const int s = h & 1;
-      mbar_wait(&bars[K_FULL + s], (h >> 1) & 1);
-      tcgen05_fence_after_sync();
-      const uint32_t ka = smem_base + s * S::kKBuf;
-      const uint32_t qa = smem_base + S::kQOff + h * 3 * (IB * 64);
-      // (A block, B block): scalar.scalar, hi.hi (+ norm columns), hi.lo, lo.hi
-      const int ablk[4] = {0, 1, 1, 2}, bblk[4] = {0, 1, 2, 1};
-#pragma unroll
-      for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          uint64_t da = make_smem_desc(ka + ablk[m] * (L * 64) + k * 32, 16, 512, kSwizzle64B);
-          uint64_t db = make_smem_desc(qa + bblk[m] * (IB * 64) + k * 32, 16, 512, kSwizzle64B);
-          umma_bf16(tmem + kColS + h * 16, da, db, kIdescS, (m | k) != 0);
-        }
-      umma_commit(&bars[K_EMPTY + s]);
-      if (h + 2 < H) {
-        mbar_wait(&bars[K_EMPTY + s], (h >> 1) & 1);
-        load_k(h + 2);
-      }
-    }
-    umma_commit(&bars[S_DONE]);
-    mbar_wait(&bars[S_DONE], 0);   // region X is free again
-    // ---- stage 2 prologue: first four e rows, bias of rows 0 and 1
-    for (int r = 0; r < S::kEStages; ++r) {
-      mbar_arrive_expect_tx(&bars[E_FULL + r], S::kEStage);
-      tma_load_2d(smem + r * S::kEStage, &map_e, &bars[E_FULL + r], 0, (int)((row0 + r) * L));
-    }
-  }
-  auto issue_bias = [&](int i) {   // thread 0 only
-    const int st = i % S::kEStages;
-    mbar_wait(&bars[E_FULL + st], (i / S::kEStages) & 1);
-    tcgen05_fence_after_sync();
-    const uint32_t ea = smem_base + st * S::kEStage, wa = smem_base + S::kWpb;
-#pragma unroll
-    for (int k = 0; k < C / 16; ++k) {
-      uint64_t da = make_smem_desc(ea + k * 32, 16, 1024, kSwizzle128B);
-      uint64_t db = make_smem_desc(wa + k * 32, 16, 1024, kSwizzle128B);
-      umma_bf16(tmem + kColBias + (i % 3) * 16, da, db, kIdescS, k != 0);
-    }
-    umma_commit(&bars[BIAS + (i % 3)]);
-  };
-  if (tid == 0) { issue_bias(0); issue_bias(1); }
-  __syncthreads();
-  tcgen05_fence_after_sync();
-
-  // =========================== stage 2: per query row ===========================
-  float sreg[H][4];
-  const int hsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-  auto drain_pair = [&](int i) {   // normalise and store the pair aggregation of row i
-    mbar_wait(&bars[PAIR + (i & 1)], (i >> 1) & 1);
-    tcgen05_fence_after_sync();
-    float v[8];
-    tmem_ld_x8(tmem_lane + kColPair + (i & 1) * 8, v);
-    tmem_wait_ld();
-    const float* rs = red_sum + (i & 1) * 64;   // [4 warps][16]: 0-7 sum of bf16(p) (pair), 8-15 sum of fp16(p) (values)
-    float inv[8];
-#pragma unroll
-    for (int h = 0; h < H; ++h) inv[h] = 1.0f / (rs[h] + rs[16 + h] + rs[32 + h] + rs[48 + h]);
-    if (tid < H) lsum[i * H + tid] = rs[8 + tid] + rs[24 + tid] + rs[40 + tid] + rs[56 + tid];
-    if (lane < 16) {
-      __nv_bfloat16* dst = cat + (row0 + i) * NCAT + NS + warp * 16 + lane;
-#pragma unroll
-      for (int h = 0; h < H; ++h) dst[h * C] = __float2bfloat16_rn(v[h] * inv[h]);
-    }
-    tcgen05_fence_before_sync();
-  };
-
-  for (int i = 0; i < IB; ++i) {
-    if (tid == 0 && i + 2 < IB) issue_bias(i + 2);
-    __syncwarp();   // tcgen05.ld is .sync.aligned: the warp must be converged
-    if ((i & 3) == 0) {
-#pragma unroll
-      for (int h = 0; h < H; ++h) tmem_ld_x4(tmem_lane + kColS + h * 16 + i, sreg[h]);
-    }
-    mbar_wait(&bars[BIAS + (i % 3)], (i / 3) & 1);
-    tcgen05_fence_after_sync();
-    float lg[8];
-    tmem_ld_x8(tmem_lane + kColBias + (i % 3) * 16, lg);
-    tmem_wait_ld();
-#pragma unroll
-    for (int h = 0; h < H; ++h) lg[h] += sreg[h][i & 3];
-    // ---- softmax over j (the 128 lanes of the CTA), in log2 units
-    float wm = warp_reduce8<true>(lg, lane);
-    float* rm = red_max + (i & 1) * 32;
-    if ((lane & 3) == 0) rm[warp * 8 + hsel] = wm;
-    __syncthreads();
-    float p[8], pb[8], ph16[8];
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-      float m = fmaxf(fmaxf(rm[h], rm[8 + h]), fmaxf(rm[16 + h], rm[24 + h]));
-      p[h] = ex2(lg[h] - m);
-      pb[h] = __bfloat162float(__float2bfloat16_rn(p[h]));   // the values the tensor cores will see:
-      ph16[h] = __half2float(__float2half_rn(p[h]));          // normalise each aggregation by its own sum
-    }
-    float wsb = warp_reduce8<false>(pb, lane), wsh = warp_reduce8<false>(ph16, lane);
-    if ((lane & 3) == 0) {
-      red_sum[(i & 1) * 64 + warp * 16 + hsel] = wsb;
-      red_sum[(i & 1) * 64 + warp * 16 + 8 + hsel] = wsh;
-    }
-    // ---- probabilities -> shared memory in the two operand layouts (K-major, 128B swizzle)
-    {
-      const uint32_t kb = tid >> 6, chunk = (tid & 63) >> 3, e2 = (tid & 7) * 2;
-      uint8_t* pi = smem + S::kPi + (i & 1) * 2048 + kb * 1024;
-      uint8_t* ph = smem + S::kPh + kb * (IB * 128);
-#pragma unroll
+  if (warp == 4) {
+    // ======================================= issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t kIdescS = make_idesc_bf16(128, 16, 0, 0);     // S^T and bias^T
+      constexpr uint32_t kIdescPair = make_idesc_bf16(64, 8, 1, 0);    // A = e tile, MN-major
+      constexpr uint32_t kIdescO = make_idesc_f16(64, 16, 1, 0);       // A = V tile, MN-major, fp16 operands
+      tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
+      // ---- stage 1: S^T_h = K_h Q_h^T for the 8 heads
+      uint8_t* qbuf = smem + S::kQOff;
+      mbar_arrive_expect_tx(&bars[Q_FULL], S::kQBuf);
+      for (int blk = 0; blk < H * 3; ++blk)    // [blk][16 rows][64 B], 64B swizzle
+        tma_load_2d(qbuf + blk * (IB * 64), &map_q, &bars[Q_FULL], blk * 32, (int)row0);
+      auto load_k = [&](int h) {
+        int s = h & 1;
+        uint8_t* kb = smem + s * S::kKBuf;
+        mbar_arrive_expect_tx(&bars[K_FULL + s], S::kKBuf);
+        for (int blk = 0; blk < 3; ++blk)
+          tma_load_2d(kb + blk * (L * 64), &map_k, &bars[K_FULL + s], (h * 3 + blk) * 32, b * L);
+      };
+      load_k(0);
+      load_k(1);
+      mbar_wait(&bars[Q_FULL], 0);
       for (int h = 0; h < H; ++h) {
-        *reinterpret_cast<__nv_bfloat16*>(pi + swz128_offset(h, chunk) + e2) = __float2bfloat16_rn(p[h]);
-        *reinterpret_cast<__half*>(ph + h * (2 * IB * 128) + swz128_offset(i, chunk) + e2) = __float2half_rn(p[h]);
-      }
-    }
-    fence_proxy_async_smem();
-    tcgen05_fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      tcgen05_fence_after_sync();
-      const int st = i % S::kEStages;
-      const uint32_t ea = smem_base + st * S::kEStage, pa = smem_base + S::kPi + (i & 1) * 2048;
+        const int s = h & 1;
+        mbar_wait(&bars[K_FULL + s], (h >> 1) & 1);
+        tcgen05_fence_after_sync();
+        const uint32_t ka = smem_base + s * S::kKBuf;
+        const uint32_t qa = smem_base + S::kQOff + h * 3 * (IB * 64);
 #pragma unroll
-      for (int k = 0; k < L / 16; ++k) {
-        // A: e[i] tile [j][c] read MN-major (M = c, 64 wide = one 128 B row; K = j, 16 rows = 2048 B per step)
-        uint64_t da = make_smem_desc(ea + k * 2048, 1024, 1024, kSwizzle128B);
-        uint64_t db = make_smem_desc(pa + (k >> 2) * 1024 + (k & 3) * 32, 16, 1024, kSwizzle128B);
-        umma_bf16(tmem + kColPair + (i & 1) * 8, da, db, kIdescPair, k != 0);
+        for (int m = 0; m < 4; ++m) {
+          // (A block, B block): scalar.scalar, hi.hi (+ norm columns), hi.lo, lo.hi
+          const int ablk = (m == 0) ? 0 : (m == 3 ? 2 : 1), bblk = (m == 0) ? 0 : (m == 2 ? 2 : 1);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            uint64_t da = make_smem_desc(ka + ablk * (L * 64) + k * 32, 16, 512, kSwizzle64B);
+            uint64_t db = make_smem_desc(qa + bblk * (IB * 64) + k * 32, 16, 512, kSwizzle64B);
+            umma_bf16(tmem + kColS + h * 16, da, db, kIdescS, (m | k) != 0);
+          }
+        }
+        umma_commit(&bars[K_EMPTY + s]);
+        if (h >= 1 && h + 1 < H) {   // refill the buffer of head h-1 with head h+1 (its MMAs are done or nearly)
+          const int sp = (h - 1) & 1;
+          mbar_wait(&bars[K_EMPTY + sp], ((h - 1) >> 1) & 1);
+          load_k(h + 1);
+        }
       }
-      umma_commit(&bars[PAIR + (i & 1)]);
-      umma_commit(&bars[E_EMPTY + st]);
-      if (i >= 1 && i + 3 < IB) {   // refill the stage released by row i-1 with row i+3
-        const int sp = (i - 1) % S::kEStages;
-        mbar_wait(&bars[E_EMPTY + sp], ((i - 1) / S::kEStages) & 1);
-        mbar_arrive_expect_tx(&bars[E_FULL + sp], S::kEStage);
-        tma_load_2d(smem + sp * S::kEStage, &map_e, &bars[E_FULL + sp], 0, (int)((row0 + i + 3) * L));
+      umma_commit(&bars[S_DONE]);
+      mbar_wait(&bars[S_DONE], 0);   // all K/Q reads done: region X is free again
+      DAB_STAMP_ISSUER(2);
+      // ---- stage 2
+      for (int r = 0; r < S::kEStages; ++r) {
+        mbar_arrive_expect_tx(&bars[E_FULL + r], S::kEStage);
+        tma_load_2d(smem + r * S::kEStage, &map_e, &bars[E_FULL + r], 0, (int)((row0 + r) * L));
       }
+      auto issue_bias = [&](int i) {
+        const int st = i % S::kEStages;
+        mbar_wait(&bars[E_FULL + st], (i / S::kEStages) & 1);
+        tcgen05_fence_after_sync();
+        const uint32_t ea = smem_base + st * S::kEStage, wa = smem_base + S::kWpb;
+#pragma unroll
+        for (int k = 0; k < C / 16; ++k) {
+          uint64_t da = make_smem_desc(ea + k * 32, 16, 1024, kSwizzle128B);
+          uint64_t db = make_smem_desc(wa + k * 32, 16, 1024, kSwizzle128B);
+          umma_bf16(tmem + kColBias + (i % 3) * 16, da, db, kIdescS, k != 0);
+        }
+        umma_commit(&bars[BIAS + (i % 3)]);
+      };
+      issue_bias(0);
+      for (int i = 0; i < IB; ++i) {
+        // one row ahead: bias buffer (i+1)%3 was last read by the softmax of row i-2, whose P_READY we have seen;
+        // row i+1 was requested two iterations ago, so its load has had time to land
+        if (i + 1 < IB) issue_bias(i + 1);
+        mbar_wait(&bars[P_READY + (i & 1)], (i >> 1) & 1);
+        tcgen05_fence_after_sync();
+        const int st = i % S::kEStages;
+        const uint32_t ea = smem_base + st * S::kEStage, pa = smem_base + S::kPi + (i & 1) * 2048;
+#pragma unroll
+        for (int k = 0; k < L / 16; ++k) {
+          // A: e[i] tile [j][c] read MN-major (M = c: one 128 B row; K = j: 16 rows = 2048 B per step)
+          uint64_t da = make_smem_desc(ea + k * 2048, 1024, 1024, kSwizzle128B);
+          uint64_t db = make_smem_desc(pa + (k >> 2) * 1024 + (k & 3) * 32, 16, 1024, kSwizzle128B);
+          umma_bf16(tmem + kColPair + (i & 1) * 8, da, db, kIdescPair, k != 0);
+        }
+        umma_commit(&bars[PAIR + (i & 1)]);
+        umma_commit(&bars[E_EMPTY + st]);
+        if (i >= 1 && i + 3 < IB) {   // refill the stage released by row i-1 with row i+3
+          const int sp = (i - 1) % S::kEStages;
+          mbar_wait(&bars[E_EMPTY + sp], ((i - 1) / S::kEStages) & 1);
+          mbar_arrive_expect_tx(&bars[E_FULL + sp], S::kEStage);
+          tma_load_2d(smem + sp * S::kEStage, &map_e, &bars[E_FULL + sp], 0, (int)((row0 + i + 3) * L));
+        }
+      }
+      // ---- stage 3: O^T_h = [Vs|Vp]_h^T P_h^T ; region X is free once the last two pair MMAs are done
+      mbar_wait(&bars[PAIR + 0], ((IB - 2) >> 1) & 1);
+      mbar_wait(&bars[PAIR + 1], ((IB - 1) >> 1) & 1);
+      DAB_STAMP_ISSUER(3);
+      auto load_v = [&](int h) {
+        int s = h & 1;
+        mbar_arrive_expect_tx(&bars[V_FULL + s], S::kVBuf);
+        tma_load_2d(smem + s * S::kVBuf, &map_v, &bars[V_FULL + s], h * V_W, b * L);
+      };
+      load_v(0);
+      load_v(1);
+      for (int h = 0; h < H; ++h) {
+        const int s = h & 1;
+        mbar_wait(&bars[V_FULL + s], (h >> 1) & 1);
+        tcgen05_fence_after_sync();
+        const uint32_t va = smem_base + s * S::kVBuf, pa = smem_base + S::kPh + h * (2 * IB * 128);
+#pragma unroll
+        for (int k = 0; k < L / 16; ++k) {
+          uint64_t da = make_smem_desc(va + k * 2048, 1024, 1024, kSwizzle128B);
+          uint64_t db = make_smem_desc(pa + (k >> 2) * (IB * 128) + (k & 3) * 32, 16, 1024, kSwizzle128B);
+          umma_bf16(tmem + kColS + h * 16, da, db, kIdescO, k != 0);
+        }
+        umma_commit(&bars[V_EMPTY + s]);
+        if (h >= 1 && h + 1 < H) {
+          const int sp = (h - 1) & 1;
+          mbar_wait(&bars[V_EMPTY + sp], ((h - 1) >> 1) & 1);
+          load_v(h + 1);
+        }
+      }
+      umma_commit(&bars[O_DONE]);
     }
-    __syncwarp();
-    if (i >= 1) drain_pair(i - 1);
-  }
-  drain_pair(IB - 1);
-  tcgen05_fence_before_sync();
-  __syncthreads();
+  } else {
+    // ======================================= softmax / epilogue warps =======================================
+    const uint32_t tmem_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    const int hsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    uint8_t* stage_w = smem + S::kStaging + warp * 512;   // warp-private staging tile
+    auto bar_compute = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
 
-  // =========================== stage 3: O^T_h = [Vs|Vp]_h^T P_h^T ===========================
-  if (tid == 0) {
-    tcgen05_fence_after_sync();
-    auto load_v = [&](int h) {
-      int s = h & 1;
-      mbar_arrive_expect_tx(&bars[V_FULL + s], S::kVBuf);
-      tma_load_2d(smem + s * S::kVBuf, &map_v, &bars[V_FULL + s], h * V_W, b * L);
+    auto drain_pair = [&](int i) {   // normalise and store the pair aggregation of row i
+      mbar_wait(&bars[PAIR + (i & 1)], (i >> 1) & 1);
+      tcgen05_fence_after_sync();
+      float v[8];
+      tmem_ld_x8(tmem_lane + kColPair + (i & 1) * 8, v);
+      tmem_wait_ld();
+      tcgen05_fence_before_sync();
+      const float4* rs = reinterpret_cast<const float4*>(red_sum + (i & 1) * 64);   // [4 warps][16]
+      float4 a0 = rs[0], a1 = rs[1], b0 = rs[4], b1 = rs[5], c0 = rs[8], c1 = rs[9], d0 = rs[12], d1 = rs[13];
+      float inv[8] = {a0.x + b0.x + c0.x + d0.x, a0.y + b0.y + c0.y + d0.y, a0.z + b0.z + c0.z + d0.z,
+                      a0.w + b0.w + c0.w + d0.w, a1.x + b1.x + c1.x + d1.x, a1.y + b1.y + c1.y + d1.y,
+                      a1.z + b1.z + c1.z + d1.z, a1.w + b1.w + c1.w + d1.w};
+      if (tid < H) {   // 1 / sum of the fp16-rounded p: normaliser of the value aggregation of row i
+        const float* rf = red_sum + (i & 1) * 64 + 8 + tid;
+        inv_o[i * H + tid] = 1.0f / (rf[0] + rf[16] + rf[32] + rf[48]);
+      }
+      // M = 64 accumulator: channel c = 16 * warp + lane lives in lanes 0-15; stage [h][16 c] then 16 B stores
+      if (lane < 16) {
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+          reinterpret_cast<__nv_bfloat16*>(stage_w)[h * 16 + lane] = __float2bfloat16_rn(__fdividef(v[h], inv[h]));
+      }
+      __syncwarp();
+      if (lane < 16) {
+        const int h = lane >> 1, half = lane & 1;
+        uint4 val = reinterpret_cast<const uint4*>(stage_w)[lane];
+        *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + NS + h * C + warp * 16 + half * 8) = val;
+      }
+      __syncwarp();
     };
-    load_v(0);
-    load_v(1);
-    for (int h = 0; h < H; ++h) {
-      const int s = h & 1;
-      mbar_wait(&bars[V_FULL + s], (h >> 1) & 1);
-      tcgen05_fence_after_sync();
-      const uint32_t va = smem_base + s * S::kVBuf, pa = smem_base + S::kPh + h * (2 * IB * 128);
-#pragma unroll
-      for (int k = 0; k < L / 16; ++k) {
-        uint64_t da = make_smem_desc(va + k * 2048, 1024, 1024, kSwizzle128B);
-        uint64_t db = make_smem_desc(pa + (k >> 2) * (IB * 128) + (k & 3) * 32, 16, 1024, kSwizzle128B);
-        umma_bf16(tmem + kColS + h * 16, da, db, kIdescO, k != 0);
-      }
-      umma_commit(&bars[V_EMPTY + s]);
-      if (h + 2 < H) {
-        mbar_wait(&bars[V_EMPTY + s], (h >> 1) & 1);
-        load_v(h + 2);
-      }
-    }
-    umma_commit(&bars[O_DONE]);
-  }
-  __syncwarp();
-  mbar_wait(&bars[O_DONE], 0);
-  tcgen05_fence_after_sync();
 
-  // =========================== stage 4: epilogue ===========================
-  // M = 64 accumulator layout: row d lives in lane (d % 16) of warp d / 16
-  float* s_og = reinterpret_cast<float*>(smem);   // [16 i][8 h][24] global-frame points (region X is free)
-  {
-    const int d = warp * 16 + lane;
+    mbar_wait(&bars[S_DONE], 0);
+    tcgen05_fence_after_sync();
+    float sreg[H][4];
+    for (int i = 0; i < IB; ++i) {
+      if ((i & 3) == 0) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) tmem_ld_x4(tmem_lane + kColS + h * 16 + i, sreg[h]);
+      }
+      mbar_wait(&bars[BIAS + (i % 3)], (i / 3) & 1);
+      tcgen05_fence_after_sync();
+      float lg[8];
+      tmem_ld_x8(tmem_lane + kColBias + (i % 3) * 16, lg);
+      tmem_wait_ld();
+      if (i == 8) DAB_STAMP(33);
+#pragma unroll
+      for (int h = 0; h < H; ++h) lg[h] += sreg[h][i & 3];
+      // ---- softmax over j (the 128 lanes), in log2 units
+      float wm = warp_reduce8<true>(lg, lane);
+      float* rm = red_max + (i & 1) * 32;
+      if ((lane & 3) == 0) rm[warp * 8 + hsel] = wm;
+      bar_compute();
+      if (i == 8) DAB_STAMP(34);
+      float p[8], pb[8], ph16[8];
+      {
+        const float4* r4 = reinterpret_cast<const float4*>(rm);
+        float4 a0 = r4[0], a1 = r4[1], b0 = r4[2], b1 = r4[3], c0 = r4[4], c1 = r4[5], d0 = r4[6], d1 = r4[7];
+        float m[8] = {fmaxf(fmaxf(a0.x, b0.x), fmaxf(c0.x, d0.x)), fmaxf(fmaxf(a0.y, b0.y), fmaxf(c0.y, d0.y)),
+                      fmaxf(fmaxf(a0.z, b0.z), fmaxf(c0.z, d0.z)), fmaxf(fmaxf(a0.w, b0.w), fmaxf(c0.w, d0.w)),
+                      fmaxf(fmaxf(a1.x, b1.x), fmaxf(c1.x, d1.x)), fmaxf(fmaxf(a1.y, b1.y), fmaxf(c1.y, d1.y)),
+                      fmaxf(fmaxf(a1.z, b1.z), fmaxf(c1.z, d1.z)), fmaxf(fmaxf(a1.w, b1.w), fmaxf(c1.w, d1.w))};
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          p[h] = ex2(lg[h] - m[h]);
+          pb[h] = __bfloat162float(__float2bfloat16_rn(p[h]));   // the values the tensor cores will see:
+          ph16[h] = __half2float(__float2half_rn(p[h]));          // each aggregation is normalised by its own sum
+        }
+      }
+      float wsb = warp_reduce8<false>(pb, lane), wsh = warp_reduce8<false>(ph16, lane);
+      if ((lane & 3) == 0) {
+        red_sum[(i & 1) * 64 + warp * 16 + hsel] = wsb;
+        red_sum[(i & 1) * 64 + warp * 16 + 8 + hsel] = wsh;
+      }
+      // ---- probabilities -> shared memory in the two operand layouts (K-major, 128B swizzle); neighbouring
+      //      lanes trade heads so that every store is a packed pair (j, j+1)
+      {
+        const int je = tid & ~1;                                  // even key of the pair
+        const uint32_t kb = je >> 6, chunk = (je & 63) >> 3, e2 = (je & 7) * 2;
+        uint8_t* pi = smem + S::kPi + (i & 1) * 2048 + kb * 1024;
+        uint8_t* ph = smem + S::kPh + kb * (IB * 128);
+        const bool odd = lane & 1;
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          float send = odd ? p[2 * hh] : p[2 * hh + 1];
+          float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+          const int h = 2 * hh + (odd ? 1 : 0);
+          float lo = odd ? recv : p[2 * hh], hi = odd ? p[2 * hh + 1] : recv;   // (p_j, p_{j+1}) of head h
+          *reinterpret_cast<uint32_t*>(pi + swz128_offset(h, chunk) + e2) = pack_bf162(lo, hi);
+          *reinterpret_cast<uint32_t*>(ph + h * (2 * IB * 128) + swz128_offset(i, chunk) + e2) = pack_h2(lo, hi);
+        }
+      }
+      if (i == 8) DAB_STAMP(35);
+      fence_proxy_async_smem();
+      tcgen05_fence_before_sync();
+      mbar_arrive(&bars[P_READY + (i & 1)]);
+      if (i == 8) DAB_STAMP(36);
+      if (i >= 1) drain_pair(i - 1);
+      DAB_STAMP(8 + i);
+    }
+    bar_compute();               // red_sum of the last row is complete
+    drain_pair(IB - 1);
+    bar_compute();               // inv_o complete for all rows
+    DAB_STAMP(24);
+
+    // ---- epilogue: O^T (M = 64: row d in lane d % 16 of warp d / 16) -> concat features
+    mbar_wait(&bars[O_DONE], 0);
+    tcgen05_fence_after_sync();
+    DAB_STAMP(4);
+    float* s_og = reinterpret_cast<float*>(smem);   // [16 i][8 h][24] global-frame points (region X is free)
 #pragma unroll
     for (int h = 0; h < H; ++h) {
       float o[16];
       tmem_ld_x16(tmem_lane + kColS + h * 16, o);
       tmem_wait_ld();
-      if (lane < 16) {
+      if (warp < 2) {            // scalar values: d = 16 * warp + lane
+        if (lane < 16) {
 #pragma unroll
-        for (int i = 0; i < IB; ++i) {
-          float v = o[i] / lsum[i * H + h];
-          if (d < DS) cat[(row0 + i) * NCAT + h * DS + d] = __float2bfloat16_rn(v);
-          else if (d < DS + 3 * P) s_og[(i * H + h) * 24 + (d - DS)] = v;
+          for (int i = 0; i < IB; ++i)
+            reinterpret_cast<__nv_bfloat16*>(stage_w)[i * 16 + lane] = __float2bfloat16_rn(o[i] * inv_o[i * H + h]);
+        }
+        __syncwarp();
+        {
+          const int i = lane >> 1, half = lane & 1;
+          uint4 val = reinterpret_cast<const uint4*>(stage_w)[lane];
+          *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + h * DS + warp * 16 + half * 8) = val;
+        }
+        __syncwarp();
+      } else {                   // point coordinates: d - 32 = 16 * (warp - 2) + lane < 24
+        const int dd = (warp - 2) * 16 + lane;
+        if (lane < 16 && dd < 3 * P) {
+#pragma unroll
+          for (int i = 0; i < IB; ++i) s_og[(i * H + h) * 24 + dd] = o[i] * inv_o[i * H + h];
         }
       }
     }
+    tcgen05_fence_before_sync();
+    bar_compute();
+    // inverse frame + norms (diffab_pytorch.py:327-336,453-457): ol[c'] = sum_k (og[k] - t[k]) R[c'][k];
+    // thread (i, h) handles the 8 points of one head -> 48 + 16 contiguous bytes
+    {
+      const int i = tid >> 3, h = tid & 7;
+      const int64_t row = row0 + i;
+      const float* g = s_og + (i * H + h) * 24;
+      float Rm[9];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) Rm[c] = __ldg(R + row * 9 + c);
+      const float tx = __ldg(tc + row * 3), ty = __ldg(tc + row * 3 + 1), tz = __ldg(tc + row * 3 + 2);
+      float out[24], nrm[8];
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        float gx = g[3 * p] - tx, gy = g[3 * p + 1] - ty, gz = g[3 * p + 2] - tz;
+        float lx = gx * Rm[0] + gy * Rm[1] + gz * Rm[2];
+        float ly = gx * Rm[3] + gy * Rm[4] + gz * Rm[5];
+        float lz = gx * Rm[6] + gy * Rm[7] + gz * Rm[8];
+        out[3 * p] = lx; out[3 * p + 1] = ly; out[3 * p + 2] = lz;
+        nrm[p] = sqrtf(lx * lx + ly * ly + lz * lz);
+      }
+      uint4* dpt = reinterpret_cast<uint4*>(cat + row * NCAT + NS + H * C + h * 24);
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        dpt[q] = make_uint4(pack_bf162(out[8 * q], out[8 * q + 1]), pack_bf162(out[8 * q + 2], out[8 * q + 3]),
+                            pack_bf162(out[8 * q + 4], out[8 * q + 5]), pack_bf162(out[8 * q + 6], out[8 * q + 7]));
+      *reinterpret_cast<uint4*>(cat + row * NCAT + NS + H * C + NPT + h * 8) =
+          make_uint4(pack_bf162(nrm[0], nrm[1]), pack_bf162(nrm[2], nrm[3]), pack_bf162(nrm[4], nrm[5]),
+                     pack_bf162(nrm[6], nrm[7]));
+    }
   }
-  tcgen05_fence_before_sync();
   __syncthreads();
-  // inverse frame + norms (diffab_pytorch.py:327-336,453-457): ol[c'] = sum_k (og[k] - t[k]) R[c'][k]
-  for (int task = tid; task < IB * H * P; task += 128) {
-    const int i = task >> 6, hp = task & 63;
-    const int64_t row = row0 + i;
-    const float* g = s_og + (i * H + (hp >> 3)) * 24 + (hp & 7) * 3;
-    const float* Rr = R + row * 9;
-    float gx = g[0] - __ldg(tc + row * 3), gy = g[1] - __ldg(tc + row * 3 + 1), gz = g[2] - __ldg(tc + row * 3 + 2);
-    float lx = gx * __ldg(Rr) + gy * __ldg(Rr + 1) + gz * __ldg(Rr + 2);
-    float ly = gx * __ldg(Rr + 3) + gy * __ldg(Rr + 4) + gz * __ldg(Rr + 5);
-    float lz = gx * __ldg(Rr + 6) + gy * __ldg(Rr + 7) + gz * __ldg(Rr + 8);
-    __nv_bfloat16* dst = cat + row * NCAT + NS + H * C;
-    dst[hp * 3] = __float2bfloat16_rn(lx);
-    dst[hp * 3 + 1] = __float2bfloat16_rn(ly);
-    dst[hp * 3 + 2] = __float2bfloat16_rn(lz);
-    dst[NPT + hp] = __float2bfloat16_rn(sqrtf(lx * lx + ly * ly + lz * lz));
+  DAB_STAMP(5);
+  if (dbg_cta && tid == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    dbg_cta[6] = smid;
   }
-  __syncthreads();
+#undef DAB_STAMP
+#undef DAB_STAMP_ISSUER
   if (warp == 0) tmem_free(tmem, kTmemCols);
 }
+
+static long long* g_core_dbg = nullptr;
 
 // ---- workspace --------------------------------------------------------------------------------------
 struct Ws {
@@ -673,7 +756,8 @@ int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, c
       cudaFuncSetAttribute(ipa_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CoreSmem::kTotal);
       attr_done = true;
     }
-    ipa_core_kernel<<<dim3(L / IB, B), 128, CoreSmem::kTotal, s>>>(mq, mk, mv, me, pk + po.wpb, ws.tc, R, ws.cat);
+    ipa_core_kernel<<<dim3(L / IB, B), 160, CoreSmem::kTotal, s>>>(mq, mk, mv, me, pk + po.wpb, ws.tc, R, ws.cat,
+                                                                    g_core_dbg);
     count_launch();
   }
   if (phases & 4) {
@@ -682,6 +766,12 @@ int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, c
       return rc;
   }
   return check_launch("dab_ipa_fwd_sm100");
+}
+
+/* Profiling hook: per-CTA clock64 timeline of the attention core (64 slots per CTA), NULL to disable. */
+int dab_debug_set_timeline(long long* buf) {
+  g_core_dbg = buf;
+  return DAB_OK;
 }
 
 /* Test hook: C[M,N] = A[M,K] B[N,K]^T + bias on the tcgen05 GEMM (bf16 in, fp32 out). */

@@ -164,6 +164,7 @@ int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, c
                       void* stream);
 /* Test hooks of the sm_100a path (used by tests/ only): the tcgen05 GEMM C[M,N] = A[M,K] B[N,K]^T + bias
  * (bf16 in, fp32 out; M % 128 == 0, N % 64 == 0, K % 64 == 0) and the operand-packing stage alone. */
+int dab_debug_set_timeline(long long* device_buf /* 64 slots per CTA of the attention core, or NULL */);
 int dab_debug_gemm_bf16(const void* A, const void* Bm, float* C, const float* bias, int M, int N, int K, void* stream);
 int dab_debug_ipa_pack(const float* proj, const float* R, const float* t, const float* gamma, int B, void* Qp, void* Kp,
                        void* Vp, float* tc, void* stream);
