@@ -239,41 +239,45 @@ __global__ void __launch_bounds__(128) ipa_pack_kernel(const float* __restrict__
 
 // ---- attention core ---------------------------------------------------------------------------------
 struct CoreSmem {
-  // region X (aliased over the four stages of the kernel)
-  static constexpr int kX = 0;
-  static constexpr int kKBuf = 3 * L * 64;           // 24,576: three [128 x 64 B] blocks of one head
+  // Region X [0, 73,728) is reused by the stages of the kernel:
+  //   stage 1: three K buffers (one head each: three [128 x 64 B] blocks); Q sits in the (not yet used) P_h region
+  //   stage 2: ring of four 16 KB e rows + 4 KB of warp-private staging tiles
+  //   stage 3: four V buffers;   epilogue: global-frame points
+  static constexpr int kKBuf = 3 * L * 64;           // 24,576
+  static constexpr int kKBufs = 3;
+  static constexpr int kXBytes = kKBufs * kKBuf;     // 73,728
   static constexpr int kQBuf = H * 3 * IB * 64;      // 24,576
-  static constexpr int kQOff = 2 * kKBuf;            // 49,152
-  static constexpr int kXBytes = 2 * kKBuf + kQBuf;  // 73,728
+  static constexpr int kQOff = kXBytes;              // inside the P_h region, which is idle during stage 1
   static constexpr int kEStage = L * C * 2;          // 16,384
   static constexpr int kEStages = 4;
+  static constexpr int kStaging = kEStages * kEStage;  // 8 warps x 512 B
   static constexpr int kVBuf = L * V_W * 2;          // 16,384
-  // region Y: probabilities per head, B operand of the O^T MMA: [h][kb(2)][16 rows][128 B]
+  static constexpr int kVBufs = 4;
+  // probabilities per head, B operand of the O^T MMA: [h][kb(2)][16 rows][128 B], fp16
   static constexpr int kPh = kXBytes;
   static constexpr int kPhBytes = H * 2 * IB * 128;  // 32,768
-  // probabilities of one row, B operand of the pair MMA: [buf(2)][kb(2)][8 rows][128 B]
+  // probabilities of one row, B operand of the pair MMA, one buffer per group: [g][kb(2)][8 rows][128 B], bf16
   static constexpr int kPi = kPh + kPhBytes;
   static constexpr int kPiBytes = 2 * 2048;
   static constexpr int kWpb = kPi + kPiBytes;        // 2,048
   static constexpr int kMisc = kWpb + 2048;
-  static constexpr int kRedMax = kMisc;              // [2][4][8] f32
-  static constexpr int kRedSum = kRedMax + 256;      // [2][4][16] f32: sums of the bf16- and of the fp16-rounded p
-  static constexpr int kInvO = kRedSum + 512;        // [16][8] f32: 1 / sum_j fp16(p)
-  static constexpr int kBars = kInvO + 512;          // 32 mbarriers
-  static constexpr int kTmemSlot = kBars + 32 * 8;
+  static constexpr int kRedMax = kMisc;              // [2 groups][2 parity][4 warps][8] f32
+  static constexpr int kRedSum = kRedMax + 512;      // [2][2][4][16] f32: sums of the bf16- and of the fp16-rounded p
+  static constexpr int kInvO = kRedSum + 1024;       // [16][8] f32: 1 / sum_j fp16(p)
+  static constexpr int kBars = kInvO + 512;          // 40 mbarriers
+  static constexpr int kTmemSlot = kBars + 40 * 8;
   static constexpr int kTotal = kTmemSlot + 16;
-  // warp-private 512 B staging tiles for coalesced stores: the 8 KB of region X the e ring leaves unused
-  static constexpr int kStaging = kEStages * kEStage;
 };
-static_assert(CoreSmem::kStaging + 4 * 512 <= CoreSmem::kXBytes, "staging must fit behind the e ring");
-static_assert(CoreSmem::kEStages * CoreSmem::kEStage <= CoreSmem::kXBytes, "e ring must fit region X");
+static_assert(CoreSmem::kEStages * CoreSmem::kEStage + 8 * 512 <= CoreSmem::kXBytes, "e ring + staging must fit region X");
+static_assert(CoreSmem::kVBufs * CoreSmem::kVBuf <= CoreSmem::kXBytes, "V buffers must fit region X");
+static_assert(CoreSmem::kQBuf <= CoreSmem::kPhBytes, "Q must fit the idle P_h region");
 static_assert(CoreSmem::kTotal <= 113 * 1024, "two CTAs per SM");
 
-enum Bar { K_FULL = 0, K_EMPTY = 2, Q_FULL = 4, S_DONE = 5, E_FULL = 6, E_EMPTY = 10, BIAS = 14, PAIR = 17,
-           V_FULL = 19, V_EMPTY = 21, O_DONE = 23, P_READY = 24, N_BARS = 26 };
+enum Bar { K_FULL = 0, K_EMPTY = 3, Q_FULL = 6, S_DONE = 7, E_FULL = 8, E_EMPTY = 12, BIAS = 16, PAIR = 20,
+           V_FULL = 22, V_EMPTY = 26, O_DONE = 30, P_READY = 31, N_BARS = 33 };
 
 // TMEM columns
-constexpr uint32_t kColS = 0, kColBias = 128, kColPair = 176, kTmemCols = 256;
+constexpr uint32_t kColS = 0, kColBias = 128, kColPair = 192, kTmemCols = 256;
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -314,9 +318,10 @@ __device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, float (&v)[4]) {
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Warp roles: warps 0-3 = 128 softmax/epilogue threads (thread t owns key j = t = TMEM lane t);
-// warp 4 lane 0 = issuer of every TMA load and tcgen05.mma.  The roles meet only at mbarriers.
-__global__ void __launch_bounds__(160, 2)
+// Warp roles (288 threads): warps 0-3 and 4-7 are two softmax/epilogue groups of 128 threads (thread t of a
+// group owns key j = t = TMEM lane t; group g handles query rows i = g, g+2, ...), warp 8 lane 0 issues
+// every TMA load and every tcgen05.mma.  The roles meet only at mbarriers.
+__global__ void __launch_bounds__(288, 2)
 ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_e,
                 const uint8_t* __restrict__ wpb_op, const float* __restrict__ tc, const float* __restrict__ R,
@@ -330,8 +335,6 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   using S = CoreSmem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
-  float* red_max = reinterpret_cast<float*>(smem + S::kRedMax);
-  float* red_sum = reinterpret_cast<float*>(smem + S::kRedSum);
   float* inv_o = reinterpret_cast<float*>(smem + S::kInvO);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -355,31 +358,34 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const uint32_t tmem = *tmem_slot;
   DAB_STAMP(1);
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ======================================= issuer =======================================
     if (lane == 0) {
       constexpr uint32_t kIdescS = make_idesc_bf16(128, 16, 0, 0);     // S^T and bias^T
       constexpr uint32_t kIdescPair = make_idesc_bf16(64, 8, 1, 0);    // A = e tile, MN-major
       constexpr uint32_t kIdescO = make_idesc_f16(64, 16, 1, 0);       // A = V tile, MN-major, fp16 operands
       tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
-      // ---- stage 1: S^T_h = K_h Q_h^T for the 8 heads
+      // The shared-memory ring is only four pair rows deep, far less than the HBM latency-bandwidth product, so
+      // rows are pulled HBM -> L2 six rows ahead with TMA prefetches and the ring is fed from L2.
+      constexpr int kL2Ahead = 6;
+      for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
+      // ---- stage 1: S^T_h = K_h Q_h^T for the 8 heads (three K buffers: two loads always in flight)
       uint8_t* qbuf = smem + S::kQOff;
       mbar_arrive_expect_tx(&bars[Q_FULL], S::kQBuf);
       for (int blk = 0; blk < H * 3; ++blk)    // [blk][16 rows][64 B], 64B swizzle
         tma_load_2d(qbuf + blk * (IB * 64), &map_q, &bars[Q_FULL], blk * 32, (int)row0);
       auto load_k = [&](int h) {
-        int s = h & 1;
+        const int s = h % S::kKBufs;
         uint8_t* kb = smem + s * S::kKBuf;
         mbar_arrive_expect_tx(&bars[K_FULL + s], S::kKBuf);
         for (int blk = 0; blk < 3; ++blk)
           tma_load_2d(kb + blk * (L * 64), &map_k, &bars[K_FULL + s], (h * 3 + blk) * 32, b * L);
       };
-      load_k(0);
-      load_k(1);
+      for (int h = 0; h < S::kKBufs; ++h) load_k(h);
       mbar_wait(&bars[Q_FULL], 0);
       for (int h = 0; h < H; ++h) {
-        const int s = h & 1;
-        mbar_wait(&bars[K_FULL + s], (h >> 1) & 1);
+        const int s = h % S::kKBufs;
+        mbar_wait(&bars[K_FULL + s], (h / S::kKBufs) & 1);
         tcgen05_fence_after_sync();
         const uint32_t ka = smem_base + s * S::kKBuf;
         const uint32_t qa = smem_base + S::kQOff + h * 3 * (IB * 64);
@@ -395,10 +401,10 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           }
         }
         umma_commit(&bars[K_EMPTY + s]);
-        if (h >= 1 && h + 1 < H) {   // refill the buffer of head h-1 with head h+1 (its MMAs are done or nearly)
-          const int sp = (h - 1) & 1;
-          mbar_wait(&bars[K_EMPTY + sp], ((h - 1) >> 1) & 1);
-          load_k(h + 1);
+        if (h >= 1 && h - 1 + S::kKBufs < H) {   // refill the buffer of head h-1
+          const int sp = (h - 1) % S::kKBufs;
+          mbar_wait(&bars[K_EMPTY + sp], ((h - 1) / S::kKBufs) & 1);
+          load_k(h - 1 + S::kKBufs);
         }
       }
       umma_commit(&bars[S_DONE]);
@@ -418,17 +424,21 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         for (int k = 0; k < C / 16; ++k) {
           uint64_t da = make_smem_desc(ea + k * 32, 16, 1024, kSwizzle128B);
           uint64_t db = make_smem_desc(wa + k * 32, 16, 1024, kSwizzle128B);
-          umma_bf16(tmem + kColBias + (i % 3) * 16, da, db, kIdescS, k != 0);
+          umma_bf16(tmem + kColBias + (i & 3) * 16, da, db, kIdescS, k != 0);
         }
-        umma_commit(&bars[BIAS + (i % 3)]);
+        umma_commit(&bars[BIAS + (i & 3)]);
       };
       issue_bias(0);
       for (int i = 0; i < IB; ++i) {
-        // one row ahead: bias buffer (i+1)%3 was last read by the softmax of row i-2, whose P_READY we have seen;
-        // row i+1 was requested two iterations ago, so its load has had time to land
+        // bias one row ahead (row i+1 was requested two iterations ago); bias buffer (i+1)%4 was last read by
+        // the softmax of row i-3, whose P_READY we have seen
+        if (i == 8) DAB_STAMP_ISSUER(40);
         if (i + 1 < IB) issue_bias(i + 1);
+        if (i + kL2Ahead < IB) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + i + kL2Ahead) * L));
+        if (i == 8) DAB_STAMP_ISSUER(41);
         mbar_wait(&bars[P_READY + (i & 1)], (i >> 1) & 1);
         tcgen05_fence_after_sync();
+        if (i == 8) DAB_STAMP_ISSUER(42);
         const int st = i % S::kEStages;
         const uint32_t ea = smem_base + st * S::kEStage, pa = smem_base + S::kPi + (i & 1) * 2048;
 #pragma unroll
@@ -440,27 +450,28 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         umma_commit(&bars[PAIR + (i & 1)]);
         umma_commit(&bars[E_EMPTY + st]);
+        if (i == 8) DAB_STAMP_ISSUER(43);
         if (i >= 1 && i + 3 < IB) {   // refill the stage released by row i-1 with row i+3
           const int sp = (i - 1) % S::kEStages;
           mbar_wait(&bars[E_EMPTY + sp], ((i - 1) / S::kEStages) & 1);
           mbar_arrive_expect_tx(&bars[E_FULL + sp], S::kEStage);
           tma_load_2d(smem + sp * S::kEStage, &map_e, &bars[E_FULL + sp], 0, (int)((row0 + i + 3) * L));
         }
+        if (i == 8) DAB_STAMP_ISSUER(44);
       }
       // ---- stage 3: O^T_h = [Vs|Vp]_h^T P_h^T ; region X is free once the last two pair MMAs are done
       mbar_wait(&bars[PAIR + 0], ((IB - 2) >> 1) & 1);
       mbar_wait(&bars[PAIR + 1], ((IB - 1) >> 1) & 1);
       DAB_STAMP_ISSUER(3);
       auto load_v = [&](int h) {
-        int s = h & 1;
+        const int s = h % S::kVBufs;
         mbar_arrive_expect_tx(&bars[V_FULL + s], S::kVBuf);
         tma_load_2d(smem + s * S::kVBuf, &map_v, &bars[V_FULL + s], h * V_W, b * L);
       };
-      load_v(0);
-      load_v(1);
+      for (int h = 0; h < S::kVBufs; ++h) load_v(h);
       for (int h = 0; h < H; ++h) {
-        const int s = h & 1;
-        mbar_wait(&bars[V_FULL + s], (h >> 1) & 1);
+        const int s = h % S::kVBufs;
+        mbar_wait(&bars[V_FULL + s], (h / S::kVBufs) & 1);
         tcgen05_fence_after_sync();
         const uint32_t va = smem_base + s * S::kVBuf, pa = smem_base + S::kPh + h * (2 * IB * 128);
 #pragma unroll
@@ -470,48 +481,54 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           umma_bf16(tmem + kColS + h * 16, da, db, kIdescO, k != 0);
         }
         umma_commit(&bars[V_EMPTY + s]);
-        if (h >= 1 && h + 1 < H) {
-          const int sp = (h - 1) & 1;
-          mbar_wait(&bars[V_EMPTY + sp], ((h - 1) >> 1) & 1);
-          load_v(h + 1);
+        if (h >= 1 && h - 1 + S::kVBufs < H) {
+          const int sp = (h - 1) % S::kVBufs;
+          mbar_wait(&bars[V_EMPTY + sp], ((h - 1) / S::kVBufs) & 1);
+          load_v(h - 1 + S::kVBufs);
         }
       }
       umma_commit(&bars[O_DONE]);
     }
   } else {
-    // ======================================= softmax / epilogue warps =======================================
-    const uint32_t tmem_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    // ======================================= softmax / epilogue groups =======================================
+    const int g = warp >> 2, gw = warp & 3, gt = tid & 127;
+    const uint32_t tmem_lane = tmem + ((uint32_t)(gw * 32) << 16);
     const int hsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
     uint8_t* stage_w = smem + S::kStaging + warp * 512;   // warp-private staging tile
-    auto bar_compute = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+    float* red_max = reinterpret_cast<float*>(smem + S::kRedMax) + g * 64;    // [parity][4 warps][8]
+    float* red_sum = reinterpret_cast<float*>(smem + S::kRedSum) + g * 128;   // [parity][4 warps][16]
+    auto bar_group = [&] { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
+    auto bar_all_compute = [] { asm volatile("bar.sync 3, 256;" ::: "memory"); };
 
-    auto drain_pair = [&](int i) {   // normalise and store the pair aggregation of row i
-      mbar_wait(&bars[PAIR + (i & 1)], (i >> 1) & 1);
+    // normalise and store the pair aggregation of local iteration n (row i = 2n + g)
+    auto drain_pair = [&](int n) {
+      const int i = 2 * n + g;
+      mbar_wait(&bars[PAIR + g], n & 1);
       tcgen05_fence_after_sync();
       float v[8];
-      tmem_ld_x8(tmem_lane + kColPair + (i & 1) * 8, v);
+      tmem_ld_x8(tmem_lane + kColPair + g * 8, v);
       tmem_wait_ld();
       tcgen05_fence_before_sync();
-      const float4* rs = reinterpret_cast<const float4*>(red_sum + (i & 1) * 64);   // [4 warps][16]
+      const float4* rs = reinterpret_cast<const float4*>(red_sum + (n & 1) * 64);   // [4 warps][16]
       float4 a0 = rs[0], a1 = rs[1], b0 = rs[4], b1 = rs[5], c0 = rs[8], c1 = rs[9], d0 = rs[12], d1 = rs[13];
-      float inv[8] = {a0.x + b0.x + c0.x + d0.x, a0.y + b0.y + c0.y + d0.y, a0.z + b0.z + c0.z + d0.z,
+      float sum[8] = {a0.x + b0.x + c0.x + d0.x, a0.y + b0.y + c0.y + d0.y, a0.z + b0.z + c0.z + d0.z,
                       a0.w + b0.w + c0.w + d0.w, a1.x + b1.x + c1.x + d1.x, a1.y + b1.y + c1.y + d1.y,
                       a1.z + b1.z + c1.z + d1.z, a1.w + b1.w + c1.w + d1.w};
-      if (tid < H) {   // 1 / sum of the fp16-rounded p: normaliser of the value aggregation of row i
-        const float* rf = red_sum + (i & 1) * 64 + 8 + tid;
-        inv_o[i * H + tid] = 1.0f / (rf[0] + rf[16] + rf[32] + rf[48]);
+      if (gt < H) {   // 1 / sum of the fp16-rounded p: normaliser of the value aggregation of row i
+        const float* rf = red_sum + (n & 1) * 64 + 8 + gt;
+        inv_o[i * H + gt] = 1.0f / (rf[0] + rf[16] + rf[32] + rf[48]);
       }
-      // M = 64 accumulator: channel c = 16 * warp + lane lives in lanes 0-15; stage [h][16 c] then 16 B stores
+      // M = 64 accumulator: channel c = 16 * gw + lane lives in lanes 0-15; stage [h][16 c] then 16 B stores
       if (lane < 16) {
 #pragma unroll
         for (int h = 0; h < H; ++h)
-          reinterpret_cast<__nv_bfloat16*>(stage_w)[h * 16 + lane] = __float2bfloat16_rn(__fdividef(v[h], inv[h]));
+          reinterpret_cast<__nv_bfloat16*>(stage_w)[h * 16 + lane] = __float2bfloat16_rn(__fdividef(v[h], sum[h]));
       }
       __syncwarp();
       if (lane < 16) {
         const int h = lane >> 1, half = lane & 1;
         uint4 val = reinterpret_cast<const uint4*>(stage_w)[lane];
-        *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + NS + h * C + warp * 16 + half * 8) = val;
+        *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + NS + h * C + gw * 16 + half * 8) = val;
       }
       __syncwarp();
     };
@@ -519,25 +536,28 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     mbar_wait(&bars[S_DONE], 0);
     tcgen05_fence_after_sync();
     float sreg[H][4];
-    for (int i = 0; i < IB; ++i) {
-      if ((i & 3) == 0) {
+    for (int n = 0; n < IB / 2; ++n) {
+      const int i = 2 * n + g;
+      if ((n & 1) == 0) {   // rows 4m .. 4m+3 of S^T; this group uses rows 4m + g and 4m + 2 + g
 #pragma unroll
-        for (int h = 0; h < H; ++h) tmem_ld_x4(tmem_lane + kColS + h * 16 + i, sreg[h]);
+        for (int h = 0; h < H; ++h) tmem_ld_x4(tmem_lane + kColS + h * 16 + 2 * n, sreg[h]);
       }
-      mbar_wait(&bars[BIAS + (i % 3)], (i / 3) & 1);
+      mbar_wait(&bars[BIAS + (i & 3)], (i >> 2) & 1);
       tcgen05_fence_after_sync();
       float lg[8];
-      tmem_ld_x8(tmem_lane + kColBias + (i % 3) * 16, lg);
+      tmem_ld_x8(tmem_lane + kColBias + (i & 3) * 16, lg);
       tmem_wait_ld();
-      if (i == 8) DAB_STAMP(33);
+      tcgen05_fence_before_sync();
+      if (n == 4) DAB_STAMP(33);
+      const int sidx = g + 2 * (n & 1);
 #pragma unroll
-      for (int h = 0; h < H; ++h) lg[h] += sreg[h][i & 3];
+      for (int h = 0; h < H; ++h) lg[h] += (sidx == 0 ? sreg[h][0] : sidx == 1 ? sreg[h][1] : sidx == 2 ? sreg[h][2] : sreg[h][3]);
       // ---- softmax over j (the 128 lanes), in log2 units
       float wm = warp_reduce8<true>(lg, lane);
-      float* rm = red_max + (i & 1) * 32;
-      if ((lane & 3) == 0) rm[warp * 8 + hsel] = wm;
-      bar_compute();
-      if (i == 8) DAB_STAMP(34);
+      float* rm = red_max + (n & 1) * 32;
+      if ((lane & 3) == 0) rm[gw * 8 + hsel] = wm;
+      bar_group();
+      if (n == 4) DAB_STAMP(34);
       float p[8], pb[8], ph16[8];
       {
         const float4* r4 = reinterpret_cast<const float4*>(rm);
@@ -555,15 +575,19 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       float wsb = warp_reduce8<false>(pb, lane), wsh = warp_reduce8<false>(ph16, lane);
       if ((lane & 3) == 0) {
-        red_sum[(i & 1) * 64 + warp * 16 + hsel] = wsb;
-        red_sum[(i & 1) * 64 + warp * 16 + 8 + hsel] = wsh;
+        red_sum[(n & 1) * 64 + gw * 16 + hsel] = wsb;
+        red_sum[(n & 1) * 64 + gw * 16 + 8 + hsel] = wsh;
       }
+      if (n == 4) DAB_STAMP(35);
+      // the previous row of this group must have left the P_i buffer and the TMEM pair buffer before we refill them
+      if (n >= 1) drain_pair(n - 1);
+      if (n == 4) DAB_STAMP(36);
       // ---- probabilities -> shared memory in the two operand layouts (K-major, 128B swizzle); neighbouring
       //      lanes trade heads so that every store is a packed pair (j, j+1)
       {
-        const int je = tid & ~1;                                  // even key of the pair
+        const int je = gt & ~1;                                   // even key of the pair
         const uint32_t kb = je >> 6, chunk = (je & 63) >> 3, e2 = (je & 7) * 2;
-        uint8_t* pi = smem + S::kPi + (i & 1) * 2048 + kb * 1024;
+        uint8_t* pi = smem + S::kPi + g * 2048 + kb * 1024;
         uint8_t* ph = smem + S::kPh + kb * (IB * 128);
         const bool odd = lane & 1;
 #pragma unroll
@@ -576,30 +600,28 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           *reinterpret_cast<uint32_t*>(ph + h * (2 * IB * 128) + swz128_offset(i, chunk) + e2) = pack_h2(lo, hi);
         }
       }
-      if (i == 8) DAB_STAMP(35);
       fence_proxy_async_smem();
       tcgen05_fence_before_sync();
-      mbar_arrive(&bars[P_READY + (i & 1)]);
-      if (i == 8) DAB_STAMP(36);
-      if (i >= 1) drain_pair(i - 1);
-      DAB_STAMP(8 + i);
+      mbar_arrive(&bars[P_READY + g]);
+      if (g == 0) DAB_STAMP(8 + n);
     }
-    bar_compute();               // red_sum of the last row is complete
-    drain_pair(IB - 1);
-    bar_compute();               // inv_o complete for all rows
+    bar_group();                 // red_sum of the last row of this group is complete
+    drain_pair(IB / 2 - 1);
+    bar_all_compute();           // inv_o complete for all rows
     DAB_STAMP(24);
 
-    // ---- epilogue: O^T (M = 64: row d in lane d % 16 of warp d / 16) -> concat features
+    // ---- epilogue: O^T (M = 64: row d in lane d % 16 of warp d / 16) -> concat features; group g takes heads 4g..4g+3
     mbar_wait(&bars[O_DONE], 0);
     tcgen05_fence_after_sync();
     DAB_STAMP(4);
     float* s_og = reinterpret_cast<float*>(smem);   // [16 i][8 h][24] global-frame points (region X is free)
 #pragma unroll
-    for (int h = 0; h < H; ++h) {
+    for (int hh = 0; hh < H / 2; ++hh) {
+      const int h = g * (H / 2) + hh;
       float o[16];
       tmem_ld_x16(tmem_lane + kColS + h * 16, o);
       tmem_wait_ld();
-      if (warp < 2) {            // scalar values: d = 16 * warp + lane
+      if (gw < 2) {              // scalar values: d = 16 * gw + lane
         if (lane < 16) {
 #pragma unroll
           for (int i = 0; i < IB; ++i)
@@ -609,11 +631,11 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         {
           const int i = lane >> 1, half = lane & 1;
           uint4 val = reinterpret_cast<const uint4*>(stage_w)[lane];
-          *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + h * DS + warp * 16 + half * 8) = val;
+          *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + h * DS + gw * 16 + half * 8) = val;
         }
         __syncwarp();
-      } else {                   // point coordinates: d - 32 = 16 * (warp - 2) + lane < 24
-        const int dd = (warp - 2) * 16 + lane;
+      } else {                   // point coordinates: d - 32 = 16 * (gw - 2) + lane < 24
+        const int dd = (gw - 2) * 16 + lane;
         if (lane < 16 && dd < 3 * P) {
 #pragma unroll
           for (int i = 0; i < IB; ++i) s_og[(i * H + h) * 24 + dd] = o[i] * inv_o[i * H + h];
@@ -621,13 +643,13 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
     }
     tcgen05_fence_before_sync();
-    bar_compute();
+    bar_all_compute();
     // inverse frame + norms (diffab_pytorch.py:327-336,453-457): ol[c'] = sum_k (og[k] - t[k]) R[c'][k];
     // thread (i, h) handles the 8 points of one head -> 48 + 16 contiguous bytes
-    {
-      const int i = tid >> 3, h = tid & 7;
+    if (g == 0) {
+      const int i = gt >> 3, h = gt & 7;
       const int64_t row = row0 + i;
-      const float* g = s_og + (i * H + h) * 24;
+      const float* gp = s_og + (i * H + h) * 24;
       float Rm[9];
 #pragma unroll
       for (int c = 0; c < 9; ++c) Rm[c] = __ldg(R + row * 9 + c);
@@ -635,7 +657,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       float out[24], nrm[8];
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        float gx = g[3 * p] - tx, gy = g[3 * p + 1] - ty, gz = g[3 * p + 2] - tz;
+        float gx = gp[3 * p] - tx, gy = gp[3 * p + 1] - ty, gz = gp[3 * p + 2] - tz;
         float lx = gx * Rm[0] + gy * Rm[1] + gz * Rm[2];
         float ly = gx * Rm[3] + gy * Rm[4] + gz * Rm[5];
         float lz = gx * Rm[6] + gy * Rm[7] + gz * Rm[8];
@@ -756,7 +778,7 @@ int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, c
       cudaFuncSetAttribute(ipa_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CoreSmem::kTotal);
       attr_done = true;
     }
-    ipa_core_kernel<<<dim3(L / IB, B), 160, CoreSmem::kTotal, s>>>(mq, mk, mv, me, pk + po.wpb, ws.tc, R, ws.cat,
+    ipa_core_kernel<<<dim3(L / IB, B), 288, CoreSmem::kTotal, s>>>(mq, mk, mv, me, pk + po.wpb, ws.tc, R, ws.cat,
                                                                     g_core_dbg);
     count_launch();
   }

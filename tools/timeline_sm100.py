@@ -30,20 +30,28 @@ with torch.no_grad():
 tl = buf.view(B * 8, 64).cpu().double()
 t0 = tl[:, 0:1]
 names = {1: "setup", 2: "stage1 (S^T) [issuer]", 24: "final drain", 4: "wait O^T (stage 3)", 5: "epilogue"}
-order = [1, 2] + list(range(8, 24)) + [24, 4, 5]
+order = [1, 2] + list(range(8, 16)) + [24, 4, 5]
 prev = tl[:, 0]
 print(f"{B*8} CTAs; mean cycles per phase (clock64), per CTA:")
 for k in order:
     d = tl[:, k] - prev
-    nm = names.get(k, f"row {k-8}")
+    nm = names.get(k, f"group-0 row {2*(k-8)}")
     print(f"  {nm:28s} mean {d.mean():9.0f}  p10 {d.quantile(0.1):9.0f}  p90 {d.quantile(0.9):9.0f}")
     prev = tl[:, k]
 tot = tl[:, 5] - tl[:, 0]
-print(f"total per CTA: mean {tot.mean():.0f} cycles; rows mean {(tl[:,23]-tl[:,2]).mean()/16:.0f} cycles/row; issuer done with pair MMAs at {(tl[:,3]-tl[:,0]).mean():.0f}")
+print(f"total per CTA: mean {tot.mean():.0f} cycles; rows mean {(tl[:,15]-tl[:,2]).mean()/16:.0f} cycles/row; issuer done with pair MMAs at {(tl[:,3]-tl[:,0]).mean():.0f}")
 print("row 8 breakdown (compute thread 0):")
-lab = {33: "S ld + wait bias + tmem ld", 34: "max butterfly + barrier", 35: "exp, sums, P stores", 36: "fence + arrive", 16: "drain_pair(i-1)"}
-prev = tl[:, 15]
-for k in (33, 34, 35, 36, 16):
+lab = {33: "S ld + wait bias + tmem ld", 34: "max butterfly + barrier", 35: "exp, sums", 36: "drain_pair(prev)", 12: "P stores + fence + arrive"}
+prev = tl[:, 11]
+for k in (33, 34, 35, 36, 12):
     d = tl[:, k] - prev
     print(f"  {lab[k]:34s} mean {d.mean():8.0f}  p10 {d.quantile(0.1):8.0f}  p90 {d.quantile(0.9):8.0f}")
+    prev = tl[:, k]
+
+print("issuer, row 8:")
+lab = {41: "issue_bias(i+2) incl. wait e_full", 42: "wait P_READY", 43: "pair MMA issue + commits", 44: "wait e_empty(i-1) + TMA refill"}
+prev = tl[:, 40]
+for k in (41, 42, 43, 44):
+    d = tl[:, k] - prev
+    print(f"  {lab[k]:36s} mean {d.mean():8.0f}  p10 {d.quantile(0.1):8.0f}  p90 {d.quantile(0.9):8.0f}")
     prev = tl[:, k]
