@@ -1,0 +1,249 @@
+// Fused projection stage of the sm_100a IPA path: x (fp32) -> bf16 -> six projections on tcgen05 ->
+// frame transform, logit scales, split-bf16 -> packed attention operands Qp / Kp / Vp (+ centred t).
+//
+// Replaces diffab_pytorch.py:391-413 (to_{q,k,v}_{scalar,point} + euclidean_transform) in one launch:
+// the fp32 projection tensor never exists in HBM.  One CTA per patch (128 residues = the M tile of the MMA).
+//   warps 0-3: convert the x tile to bf16 in shared memory (128B-swizzled, K-major), then run the epilogue:
+//              thread r owns residue r = TMEM lane r, so the frame (R_r, t_r) lives in its registers
+//   warp 4   : streams the 24 weight tiles by TMA (ring of 3) and issues the tcgen05.mma chains
+//              (M=128, N=64 for two heads of scalars, N=48 for two heads of points, K=128) into two
+//              alternating TMEM accumulators, so tile t+1 is computed while tile t is packed.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "sm100_prims.cuh"
+
+namespace dab {
+namespace sm100 {
+
+struct ProjSmem {
+  static constexpr int kA = 0;                        // [kb(2)][128 rows][128 B] bf16
+  static constexpr int kABytes = 2 * 128 * 128;       // 32,768
+  static constexpr int kWStage = 2 * 64 * 128;        // 16,384: [kb(2)][64 rows][128 B]
+  static constexpr int kWStages = 3;
+  static constexpr int kW = kA + kABytes;
+  static constexpr int kMisc = kW + kWStages * kWStage;   // 81,920
+  static constexpr int kBars = kMisc;                 // 16 mbarriers
+  static constexpr int kTmemSlot = kBars + 16 * 8;
+  static constexpr int kCen = kTmemSlot + 16;         // centroid partials [4][3] + result [3]
+  static constexpr int kTotal = kCen + 64;
+};
+enum ProjBar { W_FULL = 0, W_EMPTY = 3, ACC_FULL = 6, ACC_EMPTY = 8, PROJ_N_BARS = 10 };
+
+constexpr int kProjTiles = 24;   // 12 scalar tiles (q,k,v x 4 head pairs) + 12 point tiles
+
+__device__ __forceinline__ uint32_t pk_bf(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ uint32_t pk_h(float a, float b) {
+  __half2 p = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// map_w64 / map_w48: the packed bf16 weight matrix [1344, 128] with boxes {64, 64} / {64, 48}
+__global__ void __launch_bounds__(160, 2)
+ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_constant__ CUtensorMap map_w48,
+                const float* __restrict__ x, const float* __restrict__ R, const float* __restrict__ t,
+                const float* __restrict__ gamma, __nv_bfloat16* __restrict__ Qp, __nv_bfloat16* __restrict__ Kp,
+                __nv_bfloat16* __restrict__ Vp, float* __restrict__ tc) {
+  constexpr int L = 128, D = 128, H = 8, DS = 32, P = 8, QK_W = 96, V_W = 64;
+  constexpr float kLog2e = 1.4426950408889634f;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using S = ProjSmem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
+  float* s_cen = reinterpret_cast<float*>(smem + S::kCen);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x;
+  const uint32_t smem_base = smem_u32(smem);
+  if ((smem_base & 1023u) != 0) asm volatile("trap;");
+
+  if (tid == 0) {
+    for (int i = 0; i < PROJ_N_BARS; ++i) mbar_init(&bars[i], (i == ACC_EMPTY || i == ACC_EMPTY + 1) ? 128u : 1u);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(tmem_slot, 128);
+
+  if (warp < 4) {
+    // ---- x tile: fp32 global (coalesced float4) -> bf16, K-major 128B-swizzled A operand
+    const float* xb = x + (int64_t)b * L * D;
+    const uint32_t kb = lane >> 4, chunk = (lane & 15) >> 1, half = (lane & 1) * 8;
+#pragma unroll 4
+    for (int rr = 0; rr < 32; ++rr) {
+      const int r = warp * 32 + rr;
+      float4 v = __ldg(reinterpret_cast<const float4*>(xb + r * D) + lane);
+      uint2 o = make_uint2(pk_bf(v.x, v.y), pk_bf(v.z, v.w));
+      *reinterpret_cast<uint2*>(smem + S::kA + kb * 16384 + swz128_offset(r, chunk) + half) = o;
+    }
+    // ---- patch centroid of the translations (see ipa_sm100.cu: keeps the expanded distance well conditioned)
+    const float* tp = t + ((int64_t)b * L + tid) * 3;
+    float cx = warp_sum(tp[0]), cy = warp_sum(tp[1]), cz = warp_sum(tp[2]);
+    if (lane == 0) { s_cen[warp * 3] = cx; s_cen[warp * 3 + 1] = cy; s_cen[warp * 3 + 2] = cz; }
+    fence_proxy_async_smem();
+  }
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  tcgen05_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map_w64);
+      tma_prefetch_desc(&map_w48);
+      auto tile_rows = [](int tt) { return tt < 12 ? 64 : 48; };
+      auto tile_row0 = [](int tt) { return tt < 12 ? tt * 64 : 768 + (tt - 12) * 48; };
+      auto load_w = [&](int tt) {
+        const int s = tt % S::kWStages;
+        uint8_t* dst = smem + S::kW + s * S::kWStage;
+        const int rows = tile_rows(tt);
+        mbar_arrive_expect_tx(&bars[W_FULL + s], 2 * rows * 128);
+        const CUtensorMap* m = tt < 12 ? &map_w64 : &map_w48;
+        tma_load_2d(dst, m, &bars[W_FULL + s], 0, tile_row0(tt));            // K 0..63
+        tma_load_2d(dst + rows * 128, m, &bars[W_FULL + s], 64, tile_row0(tt));  // K 64..127
+      };
+      for (int tt = 0; tt < S::kWStages; ++tt) load_w(tt);
+      const uint32_t a_addr = smem_base + S::kA;
+      for (int tt = 0; tt < kProjTiles; ++tt) {
+        const int s = tt % S::kWStages, acc = tt & 1;
+        const int rows = tile_rows(tt);
+        mbar_wait(&bars[W_FULL + s], (tt / S::kWStages) & 1);
+        if (tt >= 2) mbar_wait(&bars[ACC_EMPTY + acc], ((tt >> 1) - 1) & 1);   // epilogue drained this accumulator
+        tcgen05_fence_after_sync();
+        const uint32_t w_addr = smem_base + S::kW + s * S::kWStage;
+        const uint32_t idesc = make_idesc_bf16(128, rows, 0, 0);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          uint64_t da = make_smem_desc(a_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, kSwizzle128B);
+          uint64_t db = make_smem_desc(w_addr + (k >> 2) * (rows * 128) + (k & 3) * 32, 16, 1024, kSwizzle128B);
+          umma_bf16(tmem + acc * 64, da, db, idesc, k != 0);
+        }
+        umma_commit(&bars[ACC_FULL + acc]);
+        umma_commit(&bars[W_EMPTY + s]);
+        if (tt >= 1 && tt - 1 + S::kWStages < kProjTiles) {
+          const int sp = (tt - 1) % S::kWStages;
+          mbar_wait(&bars[W_EMPTY + sp], ((tt - 1) / S::kWStages) & 1);
+          load_w(tt - 1 + S::kWStages);
+        }
+      }
+    }
+  } else {
+    // ---- epilogue: thread = residue
+    const int64_t row = (int64_t)b * L + tid;
+    const uint32_t tmem_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    const float cenx = (s_cen[0] + s_cen[3] + s_cen[6] + s_cen[9]) * (1.0f / L);
+    const float ceny = (s_cen[1] + s_cen[4] + s_cen[7] + s_cen[10]) * (1.0f / L);
+    const float cenz = (s_cen[2] + s_cen[5] + s_cen[8] + s_cen[11]) * (1.0f / L);
+    float Rm[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) Rm[c] = __ldg(R + row * 9 + c);
+    const float tcx = __ldg(t + row * 3) - cenx, tcy = __ldg(t + row * 3 + 1) - ceny, tcz = __ldg(t + row * 3 + 2) - cenz;
+    tc[row * 3] = tcx; tc[row * 3 + 1] = tcy; tc[row * 3 + 2] = tcz;
+    const float ss = rsqrtf((float)DS), sp = rsqrtf(4.5f * P), st = rsqrtf(3.0f);
+    __nv_bfloat16* qrow = Qp + row * (H * QK_W);
+    __nv_bfloat16* krow = Kp + row * (H * QK_W);
+    __nv_bfloat16* vrow = Vp + row * (H * V_W);
+
+    for (int tt = 0; tt < kProjTiles; ++tt) {
+      const int acc = tt & 1;
+      mbar_wait(&bars[ACC_FULL + acc], (tt >> 1) & 1);
+      tcgen05_fence_after_sync();
+      float v[64];
+      {
+        float a[32], c[32];
+        tmem_ld_x32(tmem_lane + acc * 64, a);
+        tmem_ld_x32(tmem_lane + acc * 64 + 32, c);   // columns 48..63 are stale for point tiles (unused)
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { v[i] = a[i]; v[32 + i] = c[i]; }
+      }
+      tcgen05_fence_before_sync();
+      mbar_arrive(&bars[ACC_EMPTY + acc]);
+      if (tt < 12) {
+        // ---------------- two heads of scalars: 32 features each
+        const int seg = tt >> 2, h0 = (tt & 3) * 2;
+        const float sc = seg == 0 ? st * ss * kLog2e : 1.0f;   // scale_total * scale_scalar * log2(e) folded into q
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int h = h0 + hh;
+          uint4* dst = reinterpret_cast<uint4*>(seg == 0 ? qrow + h * QK_W : seg == 1 ? krow + h * QK_W : vrow + h * V_W);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float* s8 = v + hh * 32 + q * 8;
+            uint4 o;
+            if (seg == 2) {
+              o = make_uint4(pk_h(s8[0], s8[1]), pk_h(s8[2], s8[3]), pk_h(s8[4], s8[5]), pk_h(s8[6], s8[7]));
+            } else {
+              o = make_uint4(pk_bf(s8[0] * sc, s8[1] * sc), pk_bf(s8[2] * sc, s8[3] * sc), pk_bf(s8[4] * sc, s8[5] * sc),
+                             pk_bf(s8[6] * sc, s8[7] * sc));
+            }
+            dst[q] = o;
+          }
+        }
+      } else {
+        // ---------------- two heads of points: 8 points x 3 each; euclidean_transform (diffab_pytorch.py:315-324)
+        const int seg = (tt - 12) >> 2, h0 = ((tt - 12) & 3) * 2;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int h = h0 + hh;
+          float g[24];
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            const float px = v[hh * 24 + 3 * p], py = v[hh * 24 + 3 * p + 1], pz = v[hh * 24 + 3 * p + 2];
+            g[3 * p] = px * Rm[0] + py * Rm[3] + pz * Rm[6] + tcx;
+            g[3 * p + 1] = px * Rm[1] + py * Rm[4] + pz * Rm[7] + tcy;
+            g[3 * p + 2] = px * Rm[2] + py * Rm[5] + pz * Rm[8] + tcz;
+          }
+          if (seg == 2) {   // values: fp16 [32..55], zeros [56..63]
+            uint4* dst = reinterpret_cast<uint4*>(vrow + h * V_W + 32);
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+              dst[q] = make_uint4(pk_h(g[8 * q], g[8 * q + 1]), pk_h(g[8 * q + 2], g[8 * q + 3]),
+                                  pk_h(g[8 * q + 4], g[8 * q + 5]), pk_h(g[8 * q + 6], g[8 * q + 7]));
+            dst[3] = make_uint4(0, 0, 0, 0);
+          } else {
+            const float ch = st * sp * __ldg(gamma + h) * kLog2e;
+            const float sc = seg == 0 ? ch : 1.0f;
+            float hi[24], lo[24], n2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 24; ++c) {
+              const float val = g[c] * sc;
+              hi[c] = __bfloat162float(__float2bfloat16_rn(val));
+              lo[c] = val - hi[c];
+              n2 = fmaf(g[c], g[c], n2);
+            }
+            uint4* dh = reinterpret_cast<uint4*>((seg == 0 ? qrow : krow) + h * QK_W + 32);
+            uint4* dl = reinterpret_cast<uint4*>((seg == 0 ? qrow : krow) + h * QK_W + 64);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              dh[q] = make_uint4(pk_bf(hi[8 * q], hi[8 * q + 1]), pk_bf(hi[8 * q + 2], hi[8 * q + 3]),
+                                 pk_bf(hi[8 * q + 4], hi[8 * q + 5]), pk_bf(hi[8 * q + 6], hi[8 * q + 7]));
+              dl[q] = make_uint4(pk_bf(lo[8 * q], lo[8 * q + 1]), pk_bf(lo[8 * q + 2], lo[8 * q + 3]),
+                                 pk_bf(lo[8 * q + 4], lo[8 * q + 5]), pk_bf(lo[8 * q + 6], lo[8 * q + 7]));
+            }
+            uint4 tail = make_uint4(0, 0, 0, 0);
+            if (seg == 0) {                       // columns that pick up the key-side norm term: (1, 1, 1)
+              tail.x = pk_bf(1.0f, 1.0f); tail.y = pk_bf(1.0f, 0.0f);
+            } else {                              // -0.5 c_h |k|^2 split three ways (hi + mid + lo)
+              const float nk = -0.5f * ch * n2;
+              const float a = __bfloat162float(__float2bfloat16_rn(nk));
+              const float m = __bfloat162float(__float2bfloat16_rn(nk - a));
+              tail.x = pk_bf(a, m); tail.y = pk_bf(nk - a - m, 0.0f);
+            }
+            dh[3] = tail;
+            dl[3] = make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_free(tmem, 128);
+}
+
+}  // namespace sm100
+}  // namespace dab

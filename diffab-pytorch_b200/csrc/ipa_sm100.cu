@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "gemm_sm100.cuh"
+#include "ipa_proj_sm100.cuh"
 #include "sm100_prims.cuh"
 
 namespace dab {
@@ -690,8 +691,8 @@ static long long* g_core_dbg = nullptr;
 
 // ---- workspace --------------------------------------------------------------------------------------
 struct Ws {
-  __nv_bfloat16 *xb, *Qp, *Kp, *Vp, *cat;
-  float *proj, *tc;
+  __nv_bfloat16 *Qp, *Kp, *Vp, *cat;
+  float* tc;
   size_t bytes;
 };
 static Ws carve_ws(int B, void* base) {
@@ -699,8 +700,6 @@ static Ws carve_ws(int B, void* base) {
   size_t rows = (size_t)B * L;
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   Ws w;
-  w.xb = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * D * 2);
-  w.proj = reinterpret_cast<float*>(p); p += al(rows * NPROJ * 4);
   w.Qp = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * H * QK_W * 2);
   w.Kp = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * H * QK_W * 2);
   w.Vp = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * H * V_W * 2);
@@ -755,10 +754,18 @@ int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, c
   cudaStream_t s = (cudaStream_t)stream;
   const int phases = phase_mask();
   if (phases & 1) {
-    if (int rc = dab_cast_f32_to_bf16(x, ws.xb, (int64_t)M * D, stream)) return rc;
-    if (int rc = launch_gemm_bf16<64>(ws.xb, D, pk + po.wcat, D, ws.proj, NPROJ, nullptr, M, NPROJ, D, s)) return rc;
-    ipa_pack_kernel<<<dim3(L / 16, B), 128, 0, s>>>(ws.proj, R, t, reinterpret_cast<const float*>(pk + po.gamma), ws.Qp,
-                                                     ws.Kp, ws.Vp, ws.tc);
+    CUtensorMap mw64, mw48;
+    uint64_t dw[2] = {(uint64_t)D, (uint64_t)NPROJ}, sw[1] = {(uint64_t)D * 2};
+    uint32_t b64[2] = {64, 64}, b48[2] = {64, 48};
+    if (int rc = make_tensor_map_bf16(&mw64, pk + po.wcat, 2, dw, sw, b64, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_tensor_map_bf16(&mw48, pk + po.wcat, 2, dw, sw, b48, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    static bool proj_attr_done = false;
+    if (!proj_attr_done) {
+      cudaFuncSetAttribute(ipa_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ProjSmem::kTotal);
+      proj_attr_done = true;
+    }
+    ipa_proj_kernel<<<B, 160, ProjSmem::kTotal, s>>>(mw64, mw48, x, R, t, reinterpret_cast<const float*>(pk + po.gamma),
+                                                     ws.Qp, ws.Kp, ws.Vp, ws.tc);
     count_launch();
   }
   if (phases & 2) {

@@ -15,6 +15,7 @@ loads with ``load_state_dict``.  What runs where:
 Not a LightningModule: ``pytorch_lightning`` is not a dependency; ``training_step`` /
 ``validation_step`` / ``configure_optimizers`` keep their names and return values.
 """
+import contextlib
 import ctypes
 import math
 from typing import Dict, Optional
@@ -33,6 +34,22 @@ from .so3 import vector_to_rotation_matrix
 
 CA_IDX = 1     # protstruc.general.ATOM.CA (diffab_pytorch.py:110,249,820)
 AA_UNK = 20    # protstruc.general.AA.UNK  (diffab_pytorch.py:115,273; assumed)
+
+
+@contextlib.contextmanager
+def _tf32_matmuls(enabled):
+    """TF32 for the library GEMMs of the PyTorch glue (context encoders, embedding / head MLPs).  The
+    reference's own GPU entry point asks for the same (train.py:47, set_float32_matmul_precision("high"));
+    used only by the bf16 sampling path, the fp32 path keeps full-precision matmuls."""
+    if not enabled:
+        yield
+        return
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        yield
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 # =============================================================================================
@@ -564,15 +581,18 @@ class DiffAb(nn.Module):
         s, x, O = seq_idx.clone(), translations.clone().contiguous(), orientations.clone().contiguous()
         B, L = s.shape
         dev = s.device
-        _ = self.so3_reverse  # build the table outside any capture
-        if use_cuda_graph and noises is None:
-            return self._sample_graphed(s, x, O, res_context_emb, pair_context_emb, generation_mask, t_start, t_stop)
-        for step in range(t_start, t_stop - 1, -1):
-            t = torch.full((B,), step, device=dev, dtype=torch.int64)
-            noise = noises[step] if noises is not None else self.draw_step_noise(B, L, dev, generator=generator)
-            out = self.reverse_step(s, x, O, res_context_emb, pair_context_emb, generation_mask, t, noise, inplace=True)
-            s, x, O = out["seq_idx"], out["translations"], out["orientations"]
-        return {"seq_idx": s, "translations": x, "orientations": O}
+        _ = self.so3_reverse.histograms  # build the table outside any capture
+        with _tf32_matmuls(pair_context_emb.dtype == torch.bfloat16):
+            if use_cuda_graph and noises is None:
+                return self._sample_graphed(s, x, O, res_context_emb, pair_context_emb, generation_mask, t_start,
+                                            t_stop)
+            for step in range(t_start, t_stop - 1, -1):
+                t = torch.full((B,), step, device=dev, dtype=torch.int64)
+                noise = noises[step] if noises is not None else self.draw_step_noise(B, L, dev, generator=generator)
+                out = self.reverse_step(s, x, O, res_context_emb, pair_context_emb, generation_mask, t, noise,
+                                        inplace=True)
+                s, x, O = out["seq_idx"], out["translations"], out["orientations"]
+            return {"seq_idx": s, "translations": x, "orientations": O}
 
     def _sample_graphed(self, s, x, O, res_ctx, pair_ctx, generation_mask, t_start, t_stop):
         """One reverse step captured in a CUDA graph and replayed; the step index lives in a device
@@ -635,14 +655,15 @@ class DiffAb(nn.Module):
         use_bf16 = precision == "bf16" and self.denoiser.ipa.layers[0].fast_path_supported(L)
         res_parts, pair_parts = [], []
         from .synth import pairwise_atom_distances
-        for lo in range(0, B, context_chunk):
-            sl = slice(lo, min(B, lo + context_chunk))
-            dm = distmat[sl] if distmat is not None else pairwise_atom_distances(xyz[sl])
-            r, p = self.encode_context(seq_idx[sl], xyz[sl], orientations[sl], backbone_dihedrals[sl], dm,
-                                       pairwise_dihedrals[sl], atom_mask[sl], chain_idx[sl], residue_idx[sl],
-                                       generation_mask[sl], residue_mask[sl])
-            res_parts.append(r)
-            pair_parts.append(cast_pair_to_bf16(p) if use_bf16 else p)
+        with _tf32_matmuls(use_bf16):
+            for lo in range(0, B, context_chunk):
+                sl = slice(lo, min(B, lo + context_chunk))
+                dm = distmat[sl] if distmat is not None else pairwise_atom_distances(xyz[sl])
+                r, p = self.encode_context(seq_idx[sl], xyz[sl], orientations[sl], backbone_dihedrals[sl], dm,
+                                           pairwise_dihedrals[sl], atom_mask[sl], chain_idx[sl], residue_idx[sl],
+                                           generation_mask[sl], residue_mask[sl])
+                res_parts.append(r)
+                pair_parts.append(cast_pair_to_bf16(p) if use_bf16 else p)
         res_ctx, pair_ctx = torch.cat(res_parts), torch.cat(pair_parts)
         # t = T prior on generated residues: s ~ U{0..20}, x ~ N(0, I), O ~ uniform SO(3)
         from .synth import uniform_rotations

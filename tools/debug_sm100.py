@@ -96,7 +96,7 @@ if "layer" in which:
         torch.cuda.synchronize()
         raw = layer._ws
         al = lambda n: (n + 1023) // 1024 * 1024
-        off = al(rows * 128 * 2) + al(rows * 1344 * 4) + 2 * al(rows * 768 * 2) + al(rows * 512 * 2) + al(rows * 12)
+        off = 2 * al(rows * 768 * 2) + al(rows * 512 * 2) + al(rows * 12)
         catb = raw[off:off + rows * 1024 * 2].view(torch.bfloat16).view(rows, 1024).float()
     for name, lo, hi in (("scalar", 0, 256), ("pair", 256, 768), ("point", 768, 960), ("norm", 960, 1024)):
         d = (catb[:, lo:hi] - cat32[:, lo:hi]).abs()
