@@ -64,8 +64,9 @@ EXPORTS = {
     "dab_ipa_packed_bytes": (c_size_t, [POINTER(DabIpaDims)]),
     "dab_ipa_pack_weights": (c_int, [POINTER(DabIpaDims), POINTER(DabIpaWeights), c_void_p, c_void_p]),
     "dab_ipa_sm100_workspace_bytes": (c_size_t, [POINTER(DabIpaDims)]),
+    "dab_ipa_pair_bias": (c_int, [POINTER(DabIpaDims), c_void_p, c_void_p, c_void_p, c_void_p]),
     "dab_ipa_fwd_sm100": (c_int, [POINTER(DabIpaDims), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_size_t, c_void_p]),
+                                  c_void_p, c_void_p, c_size_t, c_void_p]),
     "dab_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dab_debug_set_timeline": (c_int, [c_void_p]),
     "dab_debug_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -100,16 +100,9 @@ __global__ void pack_weights_kernel(DabIpaWeights w, uint8_t* packed) {
     row0 += rows[s];
   }
   for (int i = tid; i < D * NCAT; i += nth) wout[i] = __float2bfloat16_rn(w.w_out[i]);
-  // pair-bias operand: B matrix N=16 (8 heads + 8 zero rows) x K=64, K-major, 128B swizzle; scale_total and
-  // log2(e) folded in (diffab_pytorch.py:385-387,439)
-  uint8_t* wpb = packed + o.wpb;
-  const float st = rsqrtf(3.0f) * kLog2e;
-  for (int i = tid; i < 16 * C; i += nth) {
-    int n = i / C, c = i % C;
-    float v = n < H ? w.w_pair_bias[n * C + c] * st : 0.f;
-    uint32_t off = swz128_offset(n, c >> 3) + (c & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(wpb + off) = __float2bfloat16_rn(v);
-  }
+  // raw fp32 pair-bias weights (H x C), used when a layer call arrives without a precomputed bias plane
+  float* wpb = reinterpret_cast<float*>(packed + o.wpb);
+  for (int i = tid; i < H * C; i += nth) wpb[i] = w.w_pair_bias[i];
   float* bout = reinterpret_cast<float*>(packed + o.bout);
   float* gam = reinterpret_cast<float*>(packed + o.gamma);
   for (int i = tid; i < D; i += nth) bout[i] = w.b_out[i];
@@ -260,8 +253,7 @@ struct CoreSmem {
   // probabilities of one row, B operand of the pair MMA, one buffer per group: [g][kb(2)][8 rows][128 B], bf16
   static constexpr int kPi = kPh + kPhBytes;
   static constexpr int kPiBytes = 2 * 2048;
-  static constexpr int kWpb = kPi + kPiBytes;        // 2,048
-  static constexpr int kMisc = kWpb + 2048;
+  static constexpr int kMisc = kPi + kPiBytes;
   static constexpr int kRedMax = kMisc;              // [2 groups][2 parity][4 warps][8] f32
   static constexpr int kRedSum = kRedMax + 512;      // [2][2][4][16] f32: sums of the bf16- and of the fp16-rounded p
   static constexpr int kInvO = kRedSum + 1024;       // [16][8] f32: 1 / sum_j fp16(p)
@@ -274,11 +266,11 @@ static_assert(CoreSmem::kVBufs * CoreSmem::kVBuf <= CoreSmem::kXBytes, "V buffer
 static_assert(CoreSmem::kQBuf <= CoreSmem::kPhBytes, "Q must fit the idle P_h region");
 static_assert(CoreSmem::kTotal <= 113 * 1024, "two CTAs per SM");
 
-enum Bar { K_FULL = 0, K_EMPTY = 3, Q_FULL = 6, S_DONE = 7, E_FULL = 8, E_EMPTY = 12, BIAS = 16, PAIR = 20,
-           V_FULL = 22, V_EMPTY = 26, O_DONE = 30, P_READY = 31, N_BARS = 33 };
+enum Bar { K_FULL = 0, K_EMPTY = 3, Q_FULL = 6, S_DONE = 7, E_FULL = 8, E_EMPTY = 12, PAIR = 16,
+           V_FULL = 18, V_EMPTY = 22, O_DONE = 26, P_READY = 27, N_BARS = 29 };
 
 // TMEM columns
-constexpr uint32_t kColS = 0, kColBias = 128, kColPair = 192, kTmemCols = 256;
+constexpr uint32_t kColS = 0, kColPair = 128, kTmemCols = 256;
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -319,13 +311,16 @@ __device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, float (&v)[4]) {
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Warp roles (288 threads): warps 0-3 and 4-7 are two softmax/epilogue groups of 128 threads (thread t of a
-// group owns key j = t = TMEM lane t; group g handles query rows i = g, g+2, ...), warp 8 lane 0 issues
-// every TMA load and every tcgen05.mma.  The roles meet only at mbarriers.
-__global__ void __launch_bounds__(288, 2)
+// Warp roles (320 threads): warps 0-3 and 4-7 are two softmax/epilogue groups of 128 threads (thread t of a
+// group owns key j = t = TMEM lane t; group g handles query rows i = g, g+2, ...); warp 8 lane 0 issues every
+// tcgen05.mma; warp 9 lane 0 issues every TMA load.  The roles meet only at mbarriers.
+// `bias` is the layer's precomputed pair bias, fp16 [B*L rows i][128 j][8 h], already scaled by
+// scale_total * log2(e) (dab_ipa_pair_bias): e is constant over the six layers and the T steps, so the
+// e . Wpb contraction is hoisted out of the sampling loop entirely.
+__global__ void __launch_bounds__(320, 2)
 ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_e,
-                const uint8_t* __restrict__ wpb_op, const float* __restrict__ tc, const float* __restrict__ R,
+                const uint4* __restrict__ bias, const float* __restrict__ tc, const float* __restrict__ R,
                 __nv_bfloat16* __restrict__ cat, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // optional per-CTA timeline: slot k of CTA c at dbg[c * 64 + k]
@@ -350,39 +345,58 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
-  // pair-bias operand (2 KB, pre-swizzled by pack_weights): plain copy, then make it visible to the MMA proxy
-  if (tid < 128) reinterpret_cast<uint4*>(smem + S::kWpb)[tid] = __ldg(reinterpret_cast<const uint4*>(wpb_op) + tid);
-  fence_proxy_async_smem();
   tcgen05_fence_before_sync();
   __syncthreads();
   tcgen05_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   DAB_STAMP(1);
 
-  if (warp == 8) {
-    // ======================================= issuer =======================================
+  if (warp == 9) {
+    // ======================================= TMA producer =======================================
     if (lane == 0) {
-      constexpr uint32_t kIdescS = make_idesc_bf16(128, 16, 0, 0);     // S^T and bias^T
-      constexpr uint32_t kIdescPair = make_idesc_bf16(64, 8, 1, 0);    // A = e tile, MN-major
-      constexpr uint32_t kIdescO = make_idesc_f16(64, 16, 1, 0);       // A = V tile, MN-major, fp16 operands
       tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
       // The shared-memory ring is only four pair rows deep, far less than the HBM latency-bandwidth product, so
       // rows are pulled HBM -> L2 six rows ahead with TMA prefetches and the ring is fed from L2.
       constexpr int kL2Ahead = 6;
       for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
-      // ---- stage 1: S^T_h = K_h Q_h^T for the 8 heads (three K buffers: two loads always in flight)
+      // ---- stage 1 operands: Q rows of this CTA, K of the patch head by head (ring of three)
       uint8_t* qbuf = smem + S::kQOff;
       mbar_arrive_expect_tx(&bars[Q_FULL], S::kQBuf);
       for (int blk = 0; blk < H * 3; ++blk)    // [blk][16 rows][64 B], 64B swizzle
         tma_load_2d(qbuf + blk * (IB * 64), &map_q, &bars[Q_FULL], blk * 32, (int)row0);
-      auto load_k = [&](int h) {
+      for (int h = 0; h < H; ++h) {
         const int s = h % S::kKBufs;
+        if (h >= S::kKBufs) mbar_wait(&bars[K_EMPTY + s], ((h / S::kKBufs) - 1) & 1);
         uint8_t* kb = smem + s * S::kKBuf;
         mbar_arrive_expect_tx(&bars[K_FULL + s], S::kKBuf);
         for (int blk = 0; blk < 3; ++blk)
           tma_load_2d(kb + blk * (L * 64), &map_k, &bars[K_FULL + s], (h * 3 + blk) * 32, b * L);
-      };
-      for (int h = 0; h < S::kKBufs; ++h) load_k(h);
+      }
+      // ---- stage 2: the pair rows (ring of four); region X is free once every S^T MMA has completed
+      mbar_wait(&bars[S_DONE], 0);
+      for (int r = 0; r < IB; ++r) {
+        const int s = r % S::kEStages;
+        if (r >= S::kEStages) mbar_wait(&bars[E_EMPTY + s], ((r / S::kEStages) - 1) & 1);
+        mbar_arrive_expect_tx(&bars[E_FULL + s], S::kEStage);
+        tma_load_2d(smem + s * S::kEStage, &map_e, &bars[E_FULL + s], 0, (int)((row0 + r) * L));
+        if (r + kL2Ahead < IB) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r + kL2Ahead) * L));
+      }
+      // ---- stage 3: V of the patch head by head (ring of four) once the last pair MMAs have released region X
+      for (int s = 0; s < S::kEStages; ++s) mbar_wait(&bars[E_EMPTY + s], ((IB / S::kEStages) - 1) & 1);
+      for (int h = 0; h < H; ++h) {
+        const int s = h % S::kVBufs;
+        if (h >= S::kVBufs) mbar_wait(&bars[V_EMPTY + s], ((h / S::kVBufs) - 1) & 1);
+        mbar_arrive_expect_tx(&bars[V_FULL + s], S::kVBuf);
+        tma_load_2d(smem + s * S::kVBuf, &map_v, &bars[V_FULL + s], h * V_W, b * L);
+      }
+    }
+  } else if (warp == 8) {
+    // ======================================= MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t kIdescS = make_idesc_bf16(128, 16, 0, 0);     // S^T
+      constexpr uint32_t kIdescPair = make_idesc_bf16(64, 8, 1, 0);    // A = e tile, MN-major
+      constexpr uint32_t kIdescO = make_idesc_f16(64, 16, 1, 0);       // A = V tile, MN-major, fp16 operands
+      // ---- stage 1: S^T_h = K_h Q_h^T for the 8 heads
       mbar_wait(&bars[Q_FULL], 0);
       for (int h = 0; h < H; ++h) {
         const int s = h % S::kKBufs;
@@ -402,45 +416,18 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           }
         }
         umma_commit(&bars[K_EMPTY + s]);
-        if (h >= 1 && h - 1 + S::kKBufs < H) {   // refill the buffer of head h-1
-          const int sp = (h - 1) % S::kKBufs;
-          mbar_wait(&bars[K_EMPTY + sp], ((h - 1) / S::kKBufs) & 1);
-          load_k(h - 1 + S::kKBufs);
-        }
       }
       umma_commit(&bars[S_DONE]);
-      mbar_wait(&bars[S_DONE], 0);   // all K/Q reads done: region X is free again
       DAB_STAMP_ISSUER(2);
-      // ---- stage 2
-      for (int r = 0; r < S::kEStages; ++r) {
-        mbar_arrive_expect_tx(&bars[E_FULL + r], S::kEStage);
-        tma_load_2d(smem + r * S::kEStage, &map_e, &bars[E_FULL + r], 0, (int)((row0 + r) * L));
-      }
-      auto issue_bias = [&](int i) {
-        const int st = i % S::kEStages;
-        mbar_wait(&bars[E_FULL + st], (i / S::kEStages) & 1);
-        tcgen05_fence_after_sync();
-        const uint32_t ea = smem_base + st * S::kEStage, wa = smem_base + S::kWpb;
-#pragma unroll
-        for (int k = 0; k < C / 16; ++k) {
-          uint64_t da = make_smem_desc(ea + k * 32, 16, 1024, kSwizzle128B);
-          uint64_t db = make_smem_desc(wa + k * 32, 16, 1024, kSwizzle128B);
-          umma_bf16(tmem + kColBias + (i & 3) * 16, da, db, kIdescS, k != 0);
-        }
-        umma_commit(&bars[BIAS + (i & 3)]);
-      };
-      issue_bias(0);
+      // ---- stage 2: pair_i^T = e[i]^T P_i^T as soon as a group has published the probabilities of row i
       for (int i = 0; i < IB; ++i) {
-        // bias one row ahead (row i+1 was requested two iterations ago); bias buffer (i+1)%4 was last read by
-        // the softmax of row i-3, whose P_READY we have seen
+        const int st = i % S::kEStages;
         if (i == 8) DAB_STAMP_ISSUER(40);
-        if (i + 1 < IB) issue_bias(i + 1);
-        if (i + kL2Ahead < IB) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + i + kL2Ahead) * L));
+        mbar_wait(&bars[E_FULL + st], (i / S::kEStages) & 1);
         if (i == 8) DAB_STAMP_ISSUER(41);
         mbar_wait(&bars[P_READY + (i & 1)], (i >> 1) & 1);
         tcgen05_fence_after_sync();
         if (i == 8) DAB_STAMP_ISSUER(42);
-        const int st = i % S::kEStages;
         const uint32_t ea = smem_base + st * S::kEStage, pa = smem_base + S::kPi + (i & 1) * 2048;
 #pragma unroll
         for (int k = 0; k < L / 16; ++k) {
@@ -452,24 +439,9 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         umma_commit(&bars[PAIR + (i & 1)]);
         umma_commit(&bars[E_EMPTY + st]);
         if (i == 8) DAB_STAMP_ISSUER(43);
-        if (i >= 1 && i + 3 < IB) {   // refill the stage released by row i-1 with row i+3
-          const int sp = (i - 1) % S::kEStages;
-          mbar_wait(&bars[E_EMPTY + sp], ((i - 1) / S::kEStages) & 1);
-          mbar_arrive_expect_tx(&bars[E_FULL + sp], S::kEStage);
-          tma_load_2d(smem + sp * S::kEStage, &map_e, &bars[E_FULL + sp], 0, (int)((row0 + i + 3) * L));
-        }
-        if (i == 8) DAB_STAMP_ISSUER(44);
       }
-      // ---- stage 3: O^T_h = [Vs|Vp]_h^T P_h^T ; region X is free once the last two pair MMAs are done
-      mbar_wait(&bars[PAIR + 0], ((IB - 2) >> 1) & 1);
-      mbar_wait(&bars[PAIR + 1], ((IB - 1) >> 1) & 1);
       DAB_STAMP_ISSUER(3);
-      auto load_v = [&](int h) {
-        const int s = h % S::kVBufs;
-        mbar_arrive_expect_tx(&bars[V_FULL + s], S::kVBuf);
-        tma_load_2d(smem + s * S::kVBuf, &map_v, &bars[V_FULL + s], h * V_W, b * L);
-      };
-      for (int h = 0; h < S::kVBufs; ++h) load_v(h);
+      // ---- stage 3: O^T_h = [Vs|Vp]_h^T P_h^T (all P_h rows are published: P_READY of row 15 has been seen)
       for (int h = 0; h < H; ++h) {
         const int s = h % S::kVBufs;
         mbar_wait(&bars[V_FULL + s], (h / S::kVBufs) & 1);
@@ -482,11 +454,6 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           umma_bf16(tmem + kColS + h * 16, da, db, kIdescO, k != 0);
         }
         umma_commit(&bars[V_EMPTY + s]);
-        if (h >= 1 && h - 1 + S::kVBufs < H) {
-          const int sp = (h - 1) % S::kVBufs;
-          mbar_wait(&bars[V_EMPTY + sp], ((h - 1) / S::kVBufs) & 1);
-          load_v(h - 1 + S::kVBufs);
-        }
       }
       umma_commit(&bars[O_DONE]);
     }
@@ -534,25 +501,37 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       __syncwarp();
     };
 
+    // pair bias of this thread's key for the group's rows, two rows ahead in registers (16 B each, coalesced)
+    const uint4* bias_t = bias + (row0 + g) * L + gt;      // row i = 2n + g  ->  + n * 2 * L
+    uint4 b_cur = __ldg(bias_t), b_nxt = __ldg(bias_t + 2 * L);
     mbar_wait(&bars[S_DONE], 0);
     tcgen05_fence_after_sync();
     float sreg[H][4];
     for (int n = 0; n < IB / 2; ++n) {
       const int i = 2 * n + g;
+      const uint4 b_use = b_cur;
+      b_cur = b_nxt;
+      if (n + 2 < IB / 2) b_nxt = __ldg(bias_t + (size_t)(n + 2) * 2 * L);
       if ((n & 1) == 0) {   // rows 4m .. 4m+3 of S^T; this group uses rows 4m + g and 4m + 2 + g
 #pragma unroll
         for (int h = 0; h < H; ++h) tmem_ld_x4(tmem_lane + kColS + h * 16 + 2 * n, sreg[h]);
+        tmem_wait_ld();
+        if (n == IB / 2 - 2) tcgen05_fence_before_sync();
       }
-      mbar_wait(&bars[BIAS + (i & 3)], (i >> 2) & 1);
-      tcgen05_fence_after_sync();
-      float lg[8];
-      tmem_ld_x8(tmem_lane + kColBias + (i & 3) * 16, lg);
-      tmem_wait_ld();
-      tcgen05_fence_before_sync();
       if (n == 4) DAB_STAMP(33);
-      const int sidx = g + 2 * (n & 1);
+      float lg[8];
+      {
+        const __half2* hb = reinterpret_cast<const __half2*>(&b_use);
+        const int sidx = g + 2 * (n & 1);
 #pragma unroll
-      for (int h = 0; h < H; ++h) lg[h] += (sidx == 0 ? sreg[h][0] : sidx == 1 ? sreg[h][1] : sidx == 2 ? sreg[h][2] : sreg[h][3]);
+        for (int q = 0; q < 4; ++q) {
+          float2 f = __half22float2(hb[q]);
+          lg[2 * q] = f.x; lg[2 * q + 1] = f.y;
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+          lg[h] += (sidx == 0 ? sreg[h][0] : sidx == 1 ? sreg[h][1] : sidx == 2 ? sreg[h][2] : sreg[h][3]);
+      }
       // ---- softmax over j (the 128 lanes), in log2 units
       float wm = warp_reduce8<true>(lg, lane);
       float* rm = red_max + (n & 1) * 32;
@@ -687,12 +666,48 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (warp == 0) tmem_free(tmem, kTmemCols);
 }
 
+// Pair bias of one layer for every (patch, i, j): bias[row i][j][h] = scale_total * log2(e) * sum_c e[i,j,c] Wpb[h,c]
+// (to_pair_bias, diffab_pytorch.py:423,439) stored as fp16.  The pair tensor is constant over the T sampling
+// steps, so this runs once per sampling run per layer, not once per step.  One thread per (i, j) pair reads its
+// 128-byte e row (coalesced 16 B vectors across the warp's consecutive j) against the weights in shared memory.
+__global__ void __launch_bounds__(128) ipa_pair_bias_kernel(const uint4* __restrict__ e, const float* __restrict__ wpb,
+                                                            uint4* __restrict__ bias, int64_t n_pairs) {
+  __shared__ float s_w[H * C];
+  const float st = rsqrtf(3.0f) * kLog2e;
+  for (int i = threadIdx.x; i < H * C; i += blockDim.x) s_w[i] = wpb[i] * st;
+  __syncthreads();
+  const int64_t pair = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= n_pairs) return;
+  float acc[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) acc[h] = 0.f;
+  const uint4* ep = e + pair * (C * 2 / 16);
+#pragma unroll
+  for (int q = 0; q < C * 2 / 16; ++q) {
+    uint4 v = __ldg(ep + q);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 t2 = __bfloat1622float2(b2[k]);
+      f[2 * k] = t2.x; f[2 * k + 1] = t2.y;
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[h] = fmaf(f[k], s_w[h * C + q * 8 + k], acc[h]);
+  }
+  bias[pair] = make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]), pack_h2(acc[4], acc[5]),
+                          pack_h2(acc[6], acc[7]));
+}
+
 static long long* g_core_dbg = nullptr;
 
 // ---- workspace --------------------------------------------------------------------------------------
 struct Ws {
   __nv_bfloat16 *Qp, *Kp, *Vp, *cat;
   float* tc;
+  uint4* bias;   // fallback plane when the caller did not precompute the layer's pair bias
   size_t bytes;
 };
 static Ws carve_ws(int B, void* base) {
@@ -705,6 +720,7 @@ static Ws carve_ws(int B, void* base) {
   w.Vp = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * H * V_W * 2);
   w.tc = reinterpret_cast<float*>(p); p += al(rows * 3 * 4);
   w.cat = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * NCAT * 2);
+  w.bias = reinterpret_cast<uint4*>(p); p += al(rows * L * 16);
   w.bytes = (size_t)(p - reinterpret_cast<uint8_t*>(base));
   return w;
 }
@@ -737,8 +753,22 @@ int dab_ipa_pack_weights(const DabIpaDims* d, const DabIpaWeights* w, void* pack
 
 size_t dab_ipa_sm100_workspace_bytes(const DabIpaDims* d) { return shape_ok(d) ? carve_ws(d->B, nullptr).bytes : 0; }
 
-int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16, const float* R,
-                      const float* t, float* y, void* workspace, size_t workspace_bytes, void* stream) {
+int dab_ipa_pair_bias(const DabIpaDims* d, const void* e_bf16, const float* w_pair_bias, void* bias_f16, void* stream) {
+  DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
+              "dab_ipa_pair_bias: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
+  if (d->B == 0) return DAB_OK;
+  DAB_REQUIRE(e_bf16 && w_pair_bias && bias_f16 && aligned16(e_bf16) && aligned16(bias_f16), DAB_EINVAL,
+              "dab_ipa_pair_bias: null or misaligned pointer");
+  const int64_t n_pairs = (int64_t)d->B * L * L;
+  ipa_pair_bias_kernel<<<(unsigned)((n_pairs + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(e_bf16), w_pair_bias, reinterpret_cast<uint4*>(bias_f16), n_pairs);
+  count_launch();
+  return check_launch("dab_ipa_pair_bias");
+}
+
+int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
+                      const void* bias_f16, const float* R, const float* t, float* y, void* workspace,
+                      size_t workspace_bytes, void* stream) {
   DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
               "dab_ipa_fwd_sm100: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
   if (d->B == 0) return DAB_OK;
@@ -769,6 +799,14 @@ int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, c
     count_launch();
   }
   if (phases & 2) {
+    const uint4* bias = reinterpret_cast<const uint4*>(bias_f16);
+    if (bias == nullptr) {   // one-off call without a precomputed bias: build this layer's plane now
+      const int64_t n_pairs = (int64_t)M * L;
+      ipa_pair_bias_kernel<<<(unsigned)((n_pairs + 127) / 128), 128, 0, s>>>(
+          reinterpret_cast<const uint4*>(e_bf16), reinterpret_cast<const float*>(pk + po.wpb), ws.bias, n_pairs);
+      count_launch();
+      bias = ws.bias;
+    }
     CUtensorMap mq, mk, mv, me;
     uint64_t dqk[2] = {(uint64_t)H * QK_W, (uint64_t)M}, sqk[1] = {(uint64_t)H * QK_W * 2};
     uint32_t bq[2] = {32, IB}, bk[2] = {32, L};
@@ -785,8 +823,7 @@ int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, c
       cudaFuncSetAttribute(ipa_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CoreSmem::kTotal);
       attr_done = true;
     }
-    ipa_core_kernel<<<dim3(L / IB, B), 288, CoreSmem::kTotal, s>>>(mq, mk, mv, me, pk + po.wpb, ws.tc, R, ws.cat,
-                                                                    g_core_dbg);
+    ipa_core_kernel<<<dim3(L / IB, B), 320, CoreSmem::kTotal, s>>>(mq, mk, mv, me, bias, ws.tc, R, ws.cat, g_core_dbg);
     count_launch();
   }
   if (phases & 4) {

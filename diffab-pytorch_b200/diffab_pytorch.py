@@ -279,9 +279,9 @@ class InvariantPointAttentionLayer(nn.Module):
                 self.to_k_point.weight, self.to_v_point.weight, self.to_pair_bias.weight, self.gamma,
                 self.to_out.weight, self.to_out.bias)
 
-    def forward(self, x, e, r, t):
+    def forward(self, x, e, r, t, pair_bias=None):
         if e.dtype == torch.bfloat16:
-            return self.forward_fast(x, e, r, t)
+            return self.forward_fast(x, e, r, t, pair_bias)
         ws = self._weights()
         need_bwd = torch.is_grad_enabled() and (x.requires_grad or e.requires_grad or r.requires_grad or
                                                 t.requires_grad or any(w.requires_grad for w in ws))
@@ -306,7 +306,19 @@ class InvariantPointAttentionLayer(nn.Module):
             self._packed = (key, buf)
         return self._packed[1]
 
-    def forward_fast(self, x, e_bf16, r, t):
+    def pair_bias(self, e_bf16):
+        """This layer's pair bias for every (i, j) as fp16 (B, L, L, H), scale_total and log2(e) folded in.
+        The pair tensor is constant over the sampling loop, so ``DiffAb.sample`` computes this once per run."""
+        e = _lib.dev(e_bf16, torch.bfloat16, "e")
+        B, L = e.shape[0], e.shape[1]
+        dims = _ipa_structs(self, B, L)
+        out = torch.empty(B, L, L, self.n_head, device=e.device, dtype=torch.float16)
+        w = _lib.dev(self.to_pair_bias.weight.detach(), torch.float32, "to_pair_bias.weight")
+        _lib.check(_lib.lib().dab_ipa_pair_bias(ctypes.byref(dims), ptr(e), ptr(w), ptr(out), _lib.stream_ptr()),
+                   "dab_ipa_pair_bias")
+        return out
+
+    def forward_fast(self, x, e_bf16, r, t, pair_bias=None):
         if torch.is_grad_enabled() and (x.requires_grad or any(w.requires_grad for w in self._weights())):
             raise RuntimeError("the bf16 tensor-core IPA path is inference-only; run under torch.no_grad()")
         x = _lib.dev(x, torch.float32, "x")
@@ -323,8 +335,12 @@ class InvariantPointAttentionLayer(nn.Module):
         nbytes = lib.dab_ipa_sm100_workspace_bytes(ctypes.byref(dims))
         ws = self._workspace(max(nbytes, 16), x.device)
         y = torch.empty(B, L, D, device=x.device, dtype=torch.float32)
-        _lib.check(lib.dab_ipa_fwd_sm100(ctypes.byref(dims), ptr(packed), ptr(x), ptr(e), ptr(r), ptr(t), ptr(y),
-                                         ptr(ws), ws.numel(), _lib.stream_ptr()), "dab_ipa_fwd_sm100")
+        if pair_bias is not None:
+            pair_bias = _lib.dev(pair_bias, torch.float16, "pair_bias")
+            if tuple(pair_bias.shape) != (B, L, L, self.n_head):
+                raise ValueError(f"pair_bias shape {tuple(pair_bias.shape)} != {(B, L, L, self.n_head)}")
+        _lib.check(lib.dab_ipa_fwd_sm100(ctypes.byref(dims), ptr(packed), ptr(x), ptr(e), ptr(pair_bias), ptr(r), ptr(t),
+                                         ptr(y), ptr(ws), ws.numel(), _lib.stream_ptr()), "dab_ipa_fwd_sm100")
         return y
 
 
@@ -338,10 +354,17 @@ class InvariantPointAttentionModule(nn.Module):
             InvariantPointAttentionLayer(d_residue_emb, d_pair_emb, d_scalar_per_head, n_query_point_per_head,
                                          n_value_point_per_head, n_head) for _ in range(n_layers)])
 
-    def forward(self, res_emb, pair_emb, orientations, translations):
-        for layer in self.layers:
-            res_emb = layer(res_emb, pair_emb, orientations, translations)
+    def forward(self, res_emb, pair_emb, orientations, translations, pair_bias=None):
+        for k, layer in enumerate(self.layers):
+            if pair_bias is not None:
+                res_emb = layer(res_emb, pair_emb, orientations, translations, pair_bias[k])
+            else:
+                res_emb = layer(res_emb, pair_emb, orientations, translations)
         return res_emb
+
+    def precompute_pair_bias(self, pair_emb_bf16):
+        """Per-layer pair-bias planes for the sm_100a path (once per sampling run)."""
+        return [layer.pair_bias(pair_emb_bf16) for layer in self.layers]
 
 
 def cast_pair_to_bf16(pair_emb):
@@ -368,12 +391,13 @@ class Denoiser(nn.Module):
         self.sequence_denoising = _mlp([D + 3, D, D, aa_vocab_size])
         self.sequence_denoising.append(nn.Softmax(dim=-1))
 
-    def heads(self, seq_idx_t, translations_t, orientations_t, res_context_emb, pair_context_emb, beta):
+    def heads(self, seq_idx_t, translations_t, orientations_t, res_context_emb, pair_context_emb, beta,
+              pair_bias=None):
         """Everything up to the three head outputs; returns (eps, rotvec, seq_posterior)."""
         n_residues = seq_idx_t.shape[1]
         h = torch.cat([res_context_emb, self.sequence_embedding(seq_idx_t)], dim=-1)
         h = self.to_res_emb(h)
-        h = self.ipa(h, pair_context_emb, orientations_t, translations_t)
+        h = self.ipa(h, pair_context_emb, orientations_t, translations_t, pair_bias)
         t_emb = torch.stack([beta, torch.sin(beta), torch.cos(beta)], dim=-1)
         h = torch.cat([h, t_emb[:, None, :].expand(-1, n_residues, -1)], dim=-1)
         return self.coordinate_denoising(h), self.orientation_denoising(h), self.sequence_denoising(h)
@@ -561,11 +585,11 @@ class DiffAb(nn.Module):
 
     @torch.no_grad()
     def reverse_step(self, seq_idx_t, translations_t, orientations_t, res_context_emb, pair_context_emb,
-                     generation_mask, t, noise, inplace=False):
+                     generation_mask, t, noise, inplace=False, pair_bias=None):
         """One reverse-diffusion step: epsilon network + fused update kernel.  ``t`` is (B,) int64."""
         beta = self.dsched.tensors["beta"][t]
         eps, v_eps, post = self.denoiser.heads(seq_idx_t, translations_t, orientations_t, res_context_emb,
-                                               pair_context_emb, beta)
+                                               pair_context_emb, beta, pair_bias)
         return _diffusion.fused_reverse_step(self.dsched, self.so3_reverse, seq_idx_t, translations_t,
                                              orientations_t, eps, v_eps, post, generation_mask, t, noise,
                                              inplace=inplace)
@@ -586,13 +610,21 @@ class DiffAb(nn.Module):
             if use_cuda_graph and noises is None:
                 return self._sample_graphed(s, x, O, res_context_emb, pair_context_emb, generation_mask, t_start,
                                             t_stop)
+            pair_bias = self._pair_bias_planes(pair_context_emb)
             for step in range(t_start, t_stop - 1, -1):
                 t = torch.full((B,), step, device=dev, dtype=torch.int64)
                 noise = noises[step] if noises is not None else self.draw_step_noise(B, L, dev, generator=generator)
                 out = self.reverse_step(s, x, O, res_context_emb, pair_context_emb, generation_mask, t, noise,
-                                        inplace=True)
+                                        inplace=True, pair_bias=pair_bias)
                 s, x, O = out["seq_idx"], out["translations"], out["orientations"]
             return {"seq_idx": s, "translations": x, "orientations": O}
+
+    def _pair_bias_planes(self, pair_ctx):
+        """Per-layer pair-bias planes of the tensor-core path (None on the fp32 path): the e . Wpb contraction
+        depends on neither the step nor the state, so it is hoisted out of the T-step loop."""
+        if pair_ctx.dtype != torch.bfloat16:
+            return None
+        return self.denoiser.ipa.precompute_pair_bias(pair_ctx)
 
     def _sample_graphed(self, s, x, O, res_ctx, pair_ctx, generation_mask, t_start, t_stop):
         """One reverse step captured in a CUDA graph and replayed; the step index lives in a device
@@ -604,20 +636,20 @@ class DiffAb(nn.Module):
         if cache is None or cache["key"] != key:
             st = {"key": key, "s": torch.empty_like(s), "x": torch.empty_like(x), "O": torch.empty_like(O),
                   "t": torch.full((B,), t_start, device=dev, dtype=torch.int64),
-                  "keep": (res_ctx, pair_ctx, generation_mask)}
+                  "keep": (res_ctx, pair_ctx, generation_mask), "bias": self._pair_bias_planes(pair_ctx)}
             st["s"].copy_(s); st["x"].copy_(x); st["O"].copy_(O)
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 for _ in range(2):  # warm-up outside capture (allocator, lazy init, weight packing)
                     self.reverse_step(st["s"].clone(), st["x"].clone(), st["O"].clone(), res_ctx, pair_ctx,
-                                      generation_mask, st["t"], self.draw_step_noise(B, L, dev))
+                                      generation_mask, st["t"], self.draw_step_noise(B, L, dev), pair_bias=st["bias"])
             torch.cuda.current_stream(dev).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 noise = self.draw_step_noise(B, L, dev)
                 self.reverse_step(st["s"], st["x"], st["O"], res_ctx, pair_ctx, generation_mask, st["t"], noise,
-                                  inplace=True)
+                                  inplace=True, pair_bias=st["bias"])
                 st["t"].sub_(1)
             st["graph"] = graph
             self._graph_cache = cache = st

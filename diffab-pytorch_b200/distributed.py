@@ -1,0 +1,143 @@
+"""Multi-GPU plumbing: one process per GPU, patches sharded across ranks.
+
+The reference is single-process (``train.py:98-100``, ``devices=1``).  Patches never interact
+(every einsum keeps the batch index, ``diffab_pytorch.py:417-452``; losses sum over the batch,
+``:868-878``), so both sampling and the training step shard over patches with no data-path
+collective.  NCCL is used for exactly two things:
+
+* sampling - one all-gather of the sampled structures (7,168 B per patch) at the end of a run;
+* training - one all-reduce of the flat gradient bucket (2,538,468 fp32 = 10.15 MB) per step, plus
+  a 1-element all-reduce of the loss-mask count so that the sharded step is EXACTLY the
+  single-process large-batch step (the reference divides by the global mask count, ``:869``).
+
+Everything here takes a ``torch.distributed`` process group, so the same code runs on ``gloo``
+(CPU, used by the world_size-2 tests) and ``nccl``.
+"""
+from typing import Callable, Dict, Iterable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def world_info(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_bounds(n: int, world: int):
+    """Contiguous split of n patches over `world` ranks: sizes differ by at most one."""
+    base, extra = divmod(n, world)
+    bounds, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < extra else 0)
+        bounds.append((lo, hi))
+        lo = hi
+    return bounds
+
+
+def shard_batch(batch: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[str, torch.Tensor]:
+    n = next(iter(batch.values())).shape[0]
+    lo, hi = shard_bounds(n, world)[rank]
+    return {k: v[lo:hi] for k, v in batch.items()}
+
+
+def all_gather_samples(samples: Dict[str, torch.Tensor], n_total: int, group=None) -> Dict[str, torch.Tensor]:
+    """Gather per-rank sample dicts (leading dim = local patches) into the full batch on every rank.
+    Shards may be ragged (n_total not divisible by world): every rank pads to the largest shard."""
+    rank, world = world_info(group)
+    if world == 1:
+        return samples
+    bounds = shard_bounds(n_total, world)
+    width = max(hi - lo for lo, hi in bounds)
+    out = {}
+    for k, v in samples.items():
+        v = v.contiguous()
+        pad = torch.zeros((width,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+        pad[: v.shape[0]] = v
+        buf = torch.empty((world * width,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+        dist.all_gather_into_tensor(buf, pad, group=group)
+        buf = buf.view((world, width) + tuple(v.shape[1:]))
+        out[k] = torch.cat([buf[r, : hi - lo] for r, (lo, hi) in enumerate(bounds)], dim=0)
+    return out
+
+
+def sample_sharded(model, batch: Dict[str, torch.Tensor], group=None, **sample_kwargs) -> Dict[str, torch.Tensor]:
+    """``DiffAb.sample`` on this rank's contiguous shard of `batch`, then an all-gather of the results."""
+    rank, world = world_info(group)
+    n = batch["seq_idx"].shape[0]
+    local = shard_batch(batch, rank, world)
+    out = model.sample(local["seq_idx"], local["xyz"], local["orientations"], local.get("backbone_dihedrals"),
+                       local.get("distmat"), local.get("pairwise_dihedrals"), local.get("atom_mask"),
+                       local.get("chain_idx"), local.get("residue_idx"), local["generation_mask"],
+                       local.get("residue_mask"), **sample_kwargs)
+    return all_gather_samples(out, n, group=group)
+
+
+class GradientBucket:
+    """One flat fp32 bucket over all parameters; gradients are views into it, so the all-reduce
+    needs no packing copies after the first step."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off: off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def rebind(self):
+        """Optimizers / zero_grad(set_to_none=True) may drop .grad; point it back at the bucket."""
+        off = 0
+        for p in self.params:
+            view = self.flat[off: off + p.numel()].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                if p.grad is not None:
+                    view.copy_(p.grad)
+                p.grad = view
+            off += p.numel()
+
+    def all_reduce(self, group=None):
+        _, world = world_info(group)
+        if world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+
+
+def ddp_step(loss_terms: Callable[[], "tuple[torch.Tensor, torch.Tensor]"], bucket: GradientBucket,
+             optimizer: Optional[torch.optim.Optimizer] = None, group=None) -> torch.Tensor:
+    """One data-parallel step that reproduces the single-process large-batch step exactly.
+
+    ``loss_terms()`` runs the local forward and returns ``(numerator, count)``: the SUM of the masked
+    per-residue losses on this rank's shard and the number of masked residues (the reference's
+    ``loss_denom``, ``diffab_pytorch.py:868-878``).  The global loss is sum(numerators) / sum(counts);
+    each rank back-propagates numerator / global_count and the gradient bucket is summed over ranks.
+    """
+    bucket.rebind()
+    bucket.zero()
+    num, cnt = loss_terms()
+    cnt = cnt.detach().to(num.dtype).reshape(1).clone()
+    _, world = world_info(group)
+    if world > 1:
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+    local = num / cnt[0]
+    local.backward()
+    bucket.all_reduce(group)
+    if optimizer is not None:
+        optimizer.step()
+    total = local.detach().reshape(1).clone()
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return total[0]
+
+
+def diffab_loss_terms(model, batch, t=None, noise=None):
+    """(numerator, count) of the DiffAb training loss on a local shard: the three masked-mean losses of
+    ``_shared_step`` share one denominator, so numerator = (seq + pos + rot) * count."""
+    seq_loss, pos_loss, rot_loss = model._shared_step(batch, 0, t=t, noise=noise)
+    cnt = (batch["generation_mask"] & batch["residue_mask"]).sum()
+    return (seq_loss + pos_loss + rot_loss) * cnt, cnt

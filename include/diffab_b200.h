@@ -159,9 +159,14 @@ int dab_ipa_bwd_f32(const DabIpaDims* d, const DabIpaWeights* w, const float* x,
 size_t dab_ipa_packed_bytes(const DabIpaDims* d);
 int dab_ipa_pack_weights(const DabIpaDims* d, const DabIpaWeights* w, void* packed, void* stream);
 size_t dab_ipa_sm100_workspace_bytes(const DabIpaDims* d);
+/* Pair bias of one layer, hoisted out of the sampling loop: bias_f16[B*L*L*8] (fp16, [b][i][j][h]) =
+ * scale_total * log2(e) * e . w_pair_bias^T (to_pair_bias, diffab_pytorch.py:423,439).  The pair tensor is
+ * constant over the T reverse steps, so this is computed once per sampling run per layer. */
+int dab_ipa_pair_bias(const DabIpaDims* d, const void* e_bf16, const float* w_pair_bias, void* bias_f16, void* stream);
+/* bias_f16: the layer's plane from dab_ipa_pair_bias, or NULL (then it is rebuilt inside the call). */
 int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
-                      const float* R, const float* t, float* y, void* workspace, size_t workspace_bytes,
-                      void* stream);
+                      const void* bias_f16, const float* R, const float* t, float* y, void* workspace,
+                      size_t workspace_bytes, void* stream);
 /* Test hooks of the sm_100a path (used by tests/ only): the tcgen05 GEMM C[M,N] = A[M,K] B[N,K]^T + bias
  * (bf16 in, fp32 out; M % 128 == 0, N % 64 == 0, K % 64 == 0) and the operand-packing stage alone. */
 int dab_debug_set_timeline(long long* device_buf /* 64 slots per CTA of the attention core, or NULL */);

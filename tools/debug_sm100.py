@@ -93,10 +93,12 @@ if "layer" in which:
         layer._ws = None
         eb = cast_pair_to_bf16(e)
         yb = layer(x, eb, R, t)
+        yb2 = layer(x, eb, R, t, layer.pair_bias(eb))
         torch.cuda.synchronize()
+        print("precomputed-bias call identical:", torch.equal(yb, yb2))
         raw = layer._ws
         al = lambda n: (n + 1023) // 1024 * 1024
-        off = 2 * al(rows * 768 * 2) + al(rows * 512 * 2) + al(rows * 12)
+        off = 2 * al(rows * 768 * 2) + al(rows * 512 * 2) + al(rows * 12)  # Qp, Kp, Vp, tc precede cat
         catb = raw[off:off + rows * 1024 * 2].view(torch.bfloat16).view(rows, 1024).float()
     for name, lo, hi in (("scalar", 0, 256), ("pair", 256, 768), ("point", 768, 960), ("norm", 960, 1024)):
         d = (catb[:, lo:hi] - cat32[:, lo:hi]).abs()

@@ -41,7 +41,7 @@ for k in order:
 tot = tl[:, 5] - tl[:, 0]
 print(f"total per CTA: mean {tot.mean():.0f} cycles; rows mean {(tl[:,15]-tl[:,2]).mean()/16:.0f} cycles/row; issuer done with pair MMAs at {(tl[:,3]-tl[:,0]).mean():.0f}")
 print("row 8 breakdown (compute thread 0):")
-lab = {33: "S ld + wait bias + tmem ld", 34: "max butterfly + barrier", 35: "exp, sums", 36: "drain_pair(prev)", 12: "P stores + fence + arrive"}
+lab = {33: "bias regs + S tmem ld", 34: "max butterfly + barrier", 35: "exp, sums", 36: "drain_pair(prev)", 12: "P stores + fence + arrive"}
 prev = tl[:, 11]
 for k in (33, 34, 35, 36, 12):
     d = tl[:, k] - prev
@@ -49,9 +49,9 @@ for k in (33, 34, 35, 36, 12):
     prev = tl[:, k]
 
 print("issuer, row 8:")
-lab = {41: "issue_bias(i+2) incl. wait e_full", 42: "wait P_READY", 43: "pair MMA issue + commits", 44: "wait e_empty(i-1) + TMA refill"}
+lab = {41: "wait e_full", 42: "wait P_READY", 43: "pair MMA issue + commits"}
 prev = tl[:, 40]
-for k in (41, 42, 43, 44):
+for k in (41, 42, 43):
     d = tl[:, k] - prev
     print(f"  {lab[k]:36s} mean {d.mean():8.0f}  p10 {d.quantile(0.1):8.0f}  p90 {d.quantile(0.9):8.0f}")
     prev = tl[:, k]
