@@ -197,13 +197,13 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
             g[3 * p + 1] = px * Rm[1] + py * Rm[4] + pz * Rm[7] + tcy;
             g[3 * p + 2] = px * Rm[2] + py * Rm[5] + pz * Rm[8] + tcz;
           }
-          if (seg == 2) {   // values: fp16 [32..55], zeros [56..63]
+          if (seg == 2) {   // values: fp16 [32..55]; column 56 = 1 (the O^T MMA then returns sum_j p), zeros after
             uint4* dst = reinterpret_cast<uint4*>(vrow + h * V_W + 32);
 #pragma unroll
             for (int q = 0; q < 3; ++q)
               dst[q] = make_uint4(pk_h(g[8 * q], g[8 * q + 1]), pk_h(g[8 * q + 2], g[8 * q + 3]),
                                   pk_h(g[8 * q + 4], g[8 * q + 5]), pk_h(g[8 * q + 6], g[8 * q + 7]));
-            dst[3] = make_uint4(0, 0, 0, 0);
+            dst[3] = make_uint4(pk_h(1.0f, 0.0f), 0, 0, 0);
           } else {
             const float ch = st * sp * __ldg(gamma + h) * kLog2e;
             const float sc = seg == 0 ? ch : 1.0f;

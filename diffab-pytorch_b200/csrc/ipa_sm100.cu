@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(128) ipa_pack_kernel(const float* __restrict__
         __nv_bfloat16* dst = Vp + row * (H * V_W) + h * V_W + 32 + sub * 6;
         uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
         d32[0] = pack_h2(g[0], g[1]); d32[1] = pack_h2(g[2], g[3]); d32[2] = pack_h2(g[4], g[5]);
-        if (sub == 3) *reinterpret_cast<uint4*>(Vp + row * (H * V_W) + h * V_W + 56) = make_uint4(0, 0, 0, 0);
+        if (sub == 3)   // column 56 = 1: the O^T MMA then also returns the row sum of the probabilities
+          *reinterpret_cast<uint4*>(Vp + row * (H * V_W) + h * V_W + 56) = make_uint4(pack_h2(1.0f, 0.0f), 0, 0, 0);
       } else {
         const float sc = seg == 0 ? ch : 1.0f;
         float hi[6], lo[6], n2 = 0.f;
@@ -245,6 +246,7 @@ struct CoreSmem {
   static constexpr int kEStage = L * C * 2;          // 16,384
   static constexpr int kEStages = 4;
   static constexpr int kStaging = kEStages * kEStage;  // 8 warps x 512 B
+  static constexpr int kPi2 = kStaging + 8 * 512;      // second P_i buffer of each group (4 KB of region-X slack)
   static constexpr int kVBuf = L * V_W * 2;          // 16,384
   static constexpr int kVBufs = 4;
   // probabilities per head, B operand of the O^T MMA: [h][kb(2)][16 rows][128 B], fp16
@@ -254,23 +256,22 @@ struct CoreSmem {
   static constexpr int kPi = kPh + kPhBytes;
   static constexpr int kPiBytes = 2 * 2048;
   static constexpr int kMisc = kPi + kPiBytes;
-  static constexpr int kRedMax = kMisc;              // [2 groups][2 parity][4 warps][8] f32
-  static constexpr int kRedSum = kRedMax + 512;      // [2][2][4][16] f32: sums of the bf16- and of the fp16-rounded p
-  static constexpr int kInvO = kRedSum + 1024;       // [16][8] f32: 1 / sum_j fp16(p)
+  static constexpr int kRedMax = kMisc;              // [2 groups][2 parity][4 warps][16] f32
+  static constexpr int kInvO = kRedMax + 1024;       // [16][8] f32: 1 / sum_j p (from the ones column of V)
   static constexpr int kBars = kInvO + 512;          // 40 mbarriers
   static constexpr int kTmemSlot = kBars + 40 * 8;
   static constexpr int kTotal = kTmemSlot + 16;
 };
-static_assert(CoreSmem::kEStages * CoreSmem::kEStage + 8 * 512 <= CoreSmem::kXBytes, "e ring + staging must fit region X");
+static_assert(CoreSmem::kPi2 + 2 * 2048 <= CoreSmem::kXBytes, "e ring + staging + spare P_i buffers must fit region X");
 static_assert(CoreSmem::kVBufs * CoreSmem::kVBuf <= CoreSmem::kXBytes, "V buffers must fit region X");
 static_assert(CoreSmem::kQBuf <= CoreSmem::kPhBytes, "Q must fit the idle P_h region");
 static_assert(CoreSmem::kTotal <= 113 * 1024, "two CTAs per SM");
 
-enum Bar { K_FULL = 0, K_EMPTY = 3, Q_FULL = 6, S_DONE = 7, E_FULL = 8, E_EMPTY = 12, PAIR = 16,
-           V_FULL = 18, V_EMPTY = 22, O_DONE = 26, P_READY = 27, N_BARS = 29 };
+enum Bar { K_FULL = 0, K_EMPTY = 3, Q_FULL = 6, S_DONE = 7, E_FULL = 8, E_EMPTY = 12, PAIR = 16 /* [group][slot] */,
+           V_FULL = 20, V_EMPTY = 24, O_DONE = 28, P_READY = 29 /* [group][slot], 128 arrivals */, N_BARS = 33 };
 
 // TMEM columns
-constexpr uint32_t kColS = 0, kColPair = 128, kTmemCols = 256;
+constexpr uint32_t kColS = 0, kColPair = 128 /* 16 rows x 8 */, kTmemCols = 256;
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -300,6 +301,31 @@ __device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
   c = op(c, __shfl_xor_sync(0xffffffffu, c, 2));
   c = op(c, __shfl_xor_sync(0xffffffffu, c, 1));
   return c;
+}
+
+// Maximum of 16 per-lane values across the warp with 16 shuffles; lane ends up with the result for value
+// index 8*bit4 + 4*bit3 + 2*bit2 + bit1 of its lane id (lane pairs hold the same value).
+__device__ __forceinline__ float warp_reduce16_max(const float (&v)[16], int lane) {
+  const bool u1 = lane & 16, u2 = lane & 8, u3 = lane & 4, u4 = lane & 2;
+  float a[8], b4[4], c2[2];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float send = u1 ? v[k] : v[k + 8], keep = u1 ? v[k + 8] : v[k];
+    a[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float send = u2 ? a[k] : a[k + 4], keep = u2 ? a[k + 4] : a[k];
+    b4[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    float send = u3 ? b4[k] : b4[k + 2], keep = u3 ? b4[k + 2] : b4[k];
+    c2[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+  }
+  float send = u4 ? c2[0] : c2[1], keep = u4 ? c2[1] : c2[0];
+  float d = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+  return fmaxf(d, __shfl_xor_sync(0xffffffffu, d, 1));
 }
 
 __device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, float (&v)[4]) {
@@ -340,7 +366,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if ((smem_base & 1023u) != 0) asm volatile("trap;");
 
   if (tid == 0) {
-    for (int i = 0; i < N_BARS; ++i) mbar_init(&bars[i], (i == P_READY || i == P_READY + 1) ? 128u : 1u);
+    for (int i = 0; i < N_BARS; ++i) mbar_init(&bars[i], (i >= P_READY && i < P_READY + 4) ? 128u : 1u);
     fence_barrier_init();
   }
   __syncwarp();
@@ -358,19 +384,25 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       // The shared-memory ring is only four pair rows deep, far less than the HBM latency-bandwidth product, so
       // rows are pulled HBM -> L2 six rows ahead with TMA prefetches and the ring is fed from L2.
       constexpr int kL2Ahead = 6;
-      for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
-      // ---- stage 1 operands: Q rows of this CTA, K of the patch head by head (ring of three)
-      uint8_t* qbuf = smem + S::kQOff;
-      mbar_arrive_expect_tx(&bars[Q_FULL], S::kQBuf);
-      for (int blk = 0; blk < H * 3; ++blk)    // [blk][16 rows][64 B], 64B swizzle
-        tma_load_2d(qbuf + blk * (IB * 64), &map_q, &bars[Q_FULL], blk * 32, (int)row0);
-      for (int h = 0; h < H; ++h) {
+      // ---- stage 1 operands: K of the patch head by head (ring of three), Q rows of this CTA
+      auto load_k = [&](int h) {
         const int s = h % S::kKBufs;
-        if (h >= S::kKBufs) mbar_wait(&bars[K_EMPTY + s], ((h / S::kKBufs) - 1) & 1);
         uint8_t* kb = smem + s * S::kKBuf;
         mbar_arrive_expect_tx(&bars[K_FULL + s], S::kKBuf);
         for (int blk = 0; blk < 3; ++blk)
           tma_load_2d(kb + blk * (L * 64), &map_k, &bars[K_FULL + s], (h * 3 + blk) * 32, b * L);
+      };
+      load_k(0);
+      uint8_t* qbuf = smem + S::kQOff;
+      mbar_arrive_expect_tx(&bars[Q_FULL], S::kQBuf);
+      for (int blk = 0; blk < H * 3; ++blk)    // [blk][16 rows][64 B], 64B swizzle
+        tma_load_2d(qbuf + blk * (IB * 64), &map_q, &bars[Q_FULL], blk * 32, (int)row0);
+      load_k(1);
+      load_k(2);
+      for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
+      for (int h = S::kKBufs; h < H; ++h) {
+        mbar_wait(&bars[K_EMPTY + h % S::kKBufs], ((h / S::kKBufs) - 1) & 1);
+        load_k(h);
       }
       // ---- stage 2: the pair rows (ring of four); region X is free once every S^T MMA has completed
       mbar_wait(&bars[S_DONE], 0);
@@ -425,18 +457,22 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (i == 8) DAB_STAMP_ISSUER(40);
         mbar_wait(&bars[E_FULL + st], (i / S::kEStages) & 1);
         if (i == 8) DAB_STAMP_ISSUER(41);
-        mbar_wait(&bars[P_READY + (i & 1)], (i >> 1) & 1);
+        // one barrier per (group, P_i buffer): a group may run a row ahead of the issuer, and a shared barrier
+        // would then be two phases ahead of this wait (parity aliasing)
+        mbar_wait(&bars[P_READY + (i & 1) * 2 + ((i >> 1) & 1)], (i >> 2) & 1);
         tcgen05_fence_after_sync();
         if (i == 8) DAB_STAMP_ISSUER(42);
-        const uint32_t ea = smem_base + st * S::kEStage, pa = smem_base + S::kPi + (i & 1) * 2048;
+        const int slot = (i >> 1) & 1;   // each group alternates between two P_i buffers
+        const uint32_t ea = smem_base + st * S::kEStage;
+        const uint32_t pa = smem_base + (slot ? S::kPi2 : S::kPi) + (i & 1) * 2048;
 #pragma unroll
         for (int k = 0; k < L / 16; ++k) {
           // A: e[i] tile [j][c] read MN-major (M = c: one 128 B row; K = j: 16 rows = 2048 B per step)
           uint64_t da = make_smem_desc(ea + k * 2048, 1024, 1024, kSwizzle128B);
           uint64_t db = make_smem_desc(pa + (k >> 2) * 1024 + (k & 3) * 32, 16, 1024, kSwizzle128B);
-          umma_bf16(tmem + kColPair + (i & 1) * 8, da, db, kIdescPair, k != 0);
+          umma_bf16(tmem + kColPair + i * 8, da, db, kIdescPair, k != 0);
         }
-        umma_commit(&bars[PAIR + (i & 1)]);
+        umma_commit(&bars[PAIR + (i & 1) * 2 + slot]);
         umma_commit(&bars[E_EMPTY + st]);
         if (i == 8) DAB_STAMP_ISSUER(43);
       }
@@ -461,139 +497,130 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // ======================================= softmax / epilogue groups =======================================
     const int g = warp >> 2, gw = warp & 3, gt = tid & 127;
     const uint32_t tmem_lane = tmem + ((uint32_t)(gw * 32) << 16);
-    const int hsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    // value index this lane ends up with after warp_reduce16: 8*bit4 + 4*bit3 + 2*bit2 + bit1
+    const int vsel = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
     uint8_t* stage_w = smem + S::kStaging + warp * 512;   // warp-private staging tile
-    float* red_max = reinterpret_cast<float*>(smem + S::kRedMax) + g * 64;    // [parity][4 warps][8]
-    float* red_sum = reinterpret_cast<float*>(smem + S::kRedSum) + g * 128;   // [parity][4 warps][16]
+    float* red_max = reinterpret_cast<float*>(smem + S::kRedMax) + g * 128;    // [parity][4 warps][16]
     auto bar_group = [&] { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
     auto bar_all_compute = [] { asm volatile("bar.sync 3, 256;" ::: "memory"); };
 
-    // normalise and store the pair aggregation of local iteration n (row i = 2n + g)
-    auto drain_pair = [&](int n) {
-      const int i = 2 * n + g;
-      mbar_wait(&bars[PAIR + g], n & 1);
-      tcgen05_fence_after_sync();
-      float v[8];
-      tmem_ld_x8(tmem_lane + kColPair + g * 8, v);
-      tmem_wait_ld();
-      tcgen05_fence_before_sync();
-      const float4* rs = reinterpret_cast<const float4*>(red_sum + (n & 1) * 64);   // [4 warps][16]
-      float4 a0 = rs[0], a1 = rs[1], b0 = rs[4], b1 = rs[5], c0 = rs[8], c1 = rs[9], d0 = rs[12], d1 = rs[13];
-      float sum[8] = {a0.x + b0.x + c0.x + d0.x, a0.y + b0.y + c0.y + d0.y, a0.z + b0.z + c0.z + d0.z,
-                      a0.w + b0.w + c0.w + d0.w, a1.x + b1.x + c1.x + d1.x, a1.y + b1.y + c1.y + d1.y,
-                      a1.z + b1.z + c1.z + d1.z, a1.w + b1.w + c1.w + d1.w};
-      if (gt < H) {   // 1 / sum of the fp16-rounded p: normaliser of the value aggregation of row i
-        const float* rf = red_sum + (n & 1) * 64 + 8 + gt;
-        inv_o[i * H + gt] = 1.0f / (rf[0] + rf[16] + rf[32] + rf[48]);
-      }
-      // M = 64 accumulator: channel c = 16 * gw + lane lives in lanes 0-15; stage [h][16 c] then 16 B stores
-      if (lane < 16) {
-#pragma unroll
-        for (int h = 0; h < H; ++h)
-          reinterpret_cast<__nv_bfloat16*>(stage_w)[h * 16 + lane] = __float2bfloat16_rn(__fdividef(v[h], sum[h]));
-      }
-      __syncwarp();
-      if (lane < 16) {
-        const int h = lane >> 1, half = lane & 1;
-        uint4 val = reinterpret_cast<const uint4*>(stage_w)[lane];
-        *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + NS + h * C + gw * 16 + half * 8) = val;
-      }
-      __syncwarp();
-    };
-
-    // pair bias of this thread's key for the group's rows, two rows ahead in registers (16 B each, coalesced)
-    const uint4* bias_t = bias + (row0 + g) * L + gt;      // row i = 2n + g  ->  + n * 2 * L
-    uint4 b_cur = __ldg(bias_t), b_nxt = __ldg(bias_t + 2 * L);
+    // pair bias of this thread's key for the group's rows, one quarter (two rows) ahead in registers
+    const uint4* bias_t = bias + (row0 + g) * L + gt;      // local row n (i = 2n + g)  ->  + n * 2 * L
+    uint4 b_cur[2] = {__ldg(bias_t), __ldg(bias_t + 2 * L)};
+    uint4 b_nxt[2] = {__ldg(bias_t + 4 * L), __ldg(bias_t + 6 * L)};
     mbar_wait(&bars[S_DONE], 0);
     tcgen05_fence_after_sync();
-    float sreg[H][4];
-    for (int n = 0; n < IB / 2; ++n) {
-      const int i = 2 * n + g;
-      const uint4 b_use = b_cur;
-      b_cur = b_nxt;
-      if (n + 2 < IB / 2) b_nxt = __ldg(bias_t + (size_t)(n + 2) * 2 * L);
-      if ((n & 1) == 0) {   // rows 4m .. 4m+3 of S^T; this group uses rows 4m + g and 4m + 2 + g
-#pragma unroll
-        for (int h = 0; h < H; ++h) tmem_ld_x4(tmem_lane + kColS + h * 16 + 2 * n, sreg[h]);
-        tmem_wait_ld();
-        if (n == IB / 2 - 2) tcgen05_fence_before_sync();
+    // Four quarters of the 16 query rows; this group owns rows 4q + g and 4q + 2 + g of each quarter and
+    // treats them together: one butterfly and one group barrier give the 2 x 8 row maxima.
+    for (int q = 0; q < IB / 4; ++q) {
+      const uint4 b_use[2] = {b_cur[0], b_cur[1]};
+      b_cur[0] = b_nxt[0]; b_cur[1] = b_nxt[1];
+      if (q + 2 < IB / 4) {
+        b_nxt[0] = __ldg(bias_t + (size_t)(2 * q + 4) * 2 * L);
+        b_nxt[1] = __ldg(bias_t + (size_t)(2 * q + 5) * 2 * L);
       }
-      if (n == 4) DAB_STAMP(33);
-      float lg[8];
-      {
-        const __half2* hb = reinterpret_cast<const __half2*>(&b_use);
-        const int sidx = g + 2 * (n & 1);
+      float sreg[H][4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float2 f = __half22float2(hb[q]);
-          lg[2 * q] = f.x; lg[2 * q + 1] = f.y;
+      for (int h = 0; h < H; ++h) tmem_ld_x4(tmem_lane + kColS + h * 16 + 4 * q, sreg[h]);
+      tmem_wait_ld();
+      if (q == IB / 4 - 1) tcgen05_fence_before_sync();
+      if (q == 2) DAB_STAMP(33);
+      float lg[16];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const __half2* hb = reinterpret_cast<const __half2*>(&b_use[r]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 f = __half22float2(hb[k]);
+          lg[r * 8 + 2 * k] = f.x; lg[r * 8 + 2 * k + 1] = f.y;
         }
-#pragma unroll
-        for (int h = 0; h < H; ++h)
-          lg[h] += (sidx == 0 ? sreg[h][0] : sidx == 1 ? sreg[h][1] : sidx == 2 ? sreg[h][2] : sreg[h][3]);
-      }
-      // ---- softmax over j (the 128 lanes), in log2 units
-      float wm = warp_reduce8<true>(lg, lane);
-      float* rm = red_max + (n & 1) * 32;
-      if ((lane & 3) == 0) rm[gw * 8 + hsel] = wm;
-      bar_group();
-      if (n == 4) DAB_STAMP(34);
-      float p[8], pb[8], ph16[8];
-      {
-        const float4* r4 = reinterpret_cast<const float4*>(rm);
-        float4 a0 = r4[0], a1 = r4[1], b0 = r4[2], b1 = r4[3], c0 = r4[4], c1 = r4[5], d0 = r4[6], d1 = r4[7];
-        float m[8] = {fmaxf(fmaxf(a0.x, b0.x), fmaxf(c0.x, d0.x)), fmaxf(fmaxf(a0.y, b0.y), fmaxf(c0.y, d0.y)),
-                      fmaxf(fmaxf(a0.z, b0.z), fmaxf(c0.z, d0.z)), fmaxf(fmaxf(a0.w, b0.w), fmaxf(c0.w, d0.w)),
-                      fmaxf(fmaxf(a1.x, b1.x), fmaxf(c1.x, d1.x)), fmaxf(fmaxf(a1.y, b1.y), fmaxf(c1.y, d1.y)),
-                      fmaxf(fmaxf(a1.z, b1.z), fmaxf(c1.z, d1.z)), fmaxf(fmaxf(a1.w, b1.w), fmaxf(c1.w, d1.w))};
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-          p[h] = ex2(lg[h] - m[h]);
-          pb[h] = __bfloat162float(__float2bfloat16_rn(p[h]));   // the values the tensor cores will see:
-          ph16[h] = __half2float(__float2half_rn(p[h]));          // each aggregation is normalised by its own sum
+          const float sv = g == 0 ? (r == 0 ? sreg[h][0] : sreg[h][2]) : (r == 0 ? sreg[h][1] : sreg[h][3]);
+          lg[r * 8 + h] += sv;
         }
       }
-      float wsb = warp_reduce8<false>(pb, lane), wsh = warp_reduce8<false>(ph16, lane);
-      if ((lane & 3) == 0) {
-        red_sum[(n & 1) * 64 + gw * 16 + hsel] = wsb;
-        red_sum[(n & 1) * 64 + gw * 16 + 8 + hsel] = wsh;
-      }
-      if (n == 4) DAB_STAMP(35);
-      // the previous row of this group must have left the P_i buffer and the TMEM pair buffer before we refill them
-      if (n >= 1) drain_pair(n - 1);
-      if (n == 4) DAB_STAMP(36);
-      // ---- probabilities -> shared memory in the two operand layouts (K-major, 128B swizzle); neighbouring
-      //      lanes trade heads so that every store is a packed pair (j, j+1)
+      // ---- row maxima over j (the 128 lanes), in log2 units
+      float wm = warp_reduce16_max(lg, lane);
+      float* rm = red_max + (q & 1) * 64;
+      if ((lane & 1) == 0) rm[gw * 16 + vsel] = wm;
+      bar_group();
+      if (q == 2) DAB_STAMP(34);
+      float mx[16];
       {
-        const int je = gt & ~1;                                   // even key of the pair
-        const uint32_t kb = je >> 6, chunk = (je & 63) >> 3, e2 = (je & 7) * 2;
-        uint8_t* pi = smem + S::kPi + g * 2048 + kb * 1024;
-        uint8_t* ph = smem + S::kPh + kb * (IB * 128);
-        const bool odd = lane & 1;
+        const float4* r4 = reinterpret_cast<const float4*>(rm);
 #pragma unroll
-        for (int hh = 0; hh < 4; ++hh) {
-          float send = odd ? p[2 * hh] : p[2 * hh + 1];
-          float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-          const int h = 2 * hh + (odd ? 1 : 0);
-          float lo = odd ? recv : p[2 * hh], hi = odd ? p[2 * hh + 1] : recv;   // (p_j, p_{j+1}) of head h
-          *reinterpret_cast<uint32_t*>(pi + swz128_offset(h, chunk) + e2) = pack_bf162(lo, hi);
-          *reinterpret_cast<uint32_t*>(ph + h * (2 * IB * 128) + swz128_offset(i, chunk) + e2) = pack_h2(lo, hi);
+        for (int k = 0; k < 4; ++k) {
+          float4 a = r4[k], bb = r4[4 + k], c = r4[8 + k], dd = r4[12 + k];
+          mx[4 * k] = fmaxf(fmaxf(a.x, bb.x), fmaxf(c.x, dd.x));
+          mx[4 * k + 1] = fmaxf(fmaxf(a.y, bb.y), fmaxf(c.y, dd.y));
+          mx[4 * k + 2] = fmaxf(fmaxf(a.z, bb.z), fmaxf(c.z, dd.z));
+          mx[4 * k + 3] = fmaxf(fmaxf(a.w, bb.w), fmaxf(c.w, dd.w));
         }
       }
-      fence_proxy_async_smem();
-      tcgen05_fence_before_sync();
-      mbar_arrive(&bars[P_READY + g]);
-      if (g == 0) DAB_STAMP(8 + n);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int n = 2 * q + r, i = 2 * n + g;
+        float p[8];
+#pragma unroll
+        for (int h = 0; h < H; ++h) p[h] = ex2(lg[r * 8 + h] - mx[r * 8 + h]);
+        // the pair MMA that last read this P_i buffer (row n-2 of this group) must have completed
+        if (n >= 2) mbar_wait(&bars[PAIR + g * 2 + (n & 1)], ((n >> 1) - 1) & 1);
+        // ---- probabilities -> shared memory in the two operand layouts (K-major, 128B swizzle); neighbouring
+        //      lanes trade heads so that every store is a packed pair (j, j+1).  Un-normalised: the row sums come
+        //      out of the O^T MMA itself (ones column of the V operand) and are applied in the epilogue.
+        {
+          const int je = gt & ~1;                                   // even key of the pair
+          const uint32_t kb = je >> 6, chunk = (je & 63) >> 3, e2 = (je & 7) * 2;
+          uint8_t* pi = smem + ((n & 1) ? S::kPi2 : S::kPi) + g * 2048 + kb * 1024;
+          uint8_t* ph = smem + S::kPh + kb * (IB * 128);
+          const bool odd = lane & 1;
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh) {
+            float send = odd ? p[2 * hh] : p[2 * hh + 1];
+            float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            const int h = 2 * hh + (odd ? 1 : 0);
+            float lo = odd ? recv : p[2 * hh], hi = odd ? p[2 * hh + 1] : recv;   // (p_j, p_{j+1}) of head h
+            *reinterpret_cast<uint32_t*>(pi + swz128_offset(h, chunk) + e2) = pack_bf162(lo, hi);
+            *reinterpret_cast<uint32_t*>(ph + h * (2 * IB * 128) + swz128_offset(i, chunk) + e2) = pack_h2(lo, hi);
+          }
+        }
+        fence_proxy_async_smem();
+        tcgen05_fence_before_sync();
+        mbar_arrive(&bars[P_READY + g * 2 + (n & 1)]);
+        if (g == 0) DAB_STAMP(8 + n);
+      }
     }
-    bar_group();                 // red_sum of the last row of this group is complete
-    drain_pair(IB / 2 - 1);
-    bar_all_compute();           // inv_o complete for all rows
     DAB_STAMP(24);
 
-    // ---- epilogue: O^T (M = 64: row d in lane d % 16 of warp d / 16) -> concat features; group g takes heads 4g..4g+3
+    // ---- epilogue.  O^T (M = 64: row d in lane d % 16 of warp d / 16): d < 32 scalar values, 32..55 point
+    //      coordinates, d = 56 the row sum of the probabilities (ones column of V).  Group g takes heads 4g..4g+3.
+    // frame of the (residue, head) task this thread finishes with: fetched now, used after the O^T MMAs
+    float Rm[9], tfr[3];
+    {
+      const int64_t row = row0 + (gt >> 3);
+#pragma unroll
+      for (int c = 0; c < 9; ++c) Rm[c] = __ldg(R + row * 9 + c);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tfr[c] = __ldg(tc + row * 3 + c);
+    }
     mbar_wait(&bars[O_DONE], 0);
     tcgen05_fence_after_sync();
     DAB_STAMP(4);
+    if (gw == 3) {               // d = 48 + lane: lane 8 holds the normalisers
+#pragma unroll
+      for (int hh = 0; hh < H / 2; ++hh) {
+        const int h = g * (H / 2) + hh;
+        float o[16];
+        tmem_ld_x16(tmem_lane + kColS + h * 16, o);
+        tmem_wait_ld();
+        if (lane == 8) {
+#pragma unroll
+          for (int i = 0; i < IB; ++i) inv_o[i * H + h] = __fdividef(1.0f, o[i]);
+        }
+      }
+    }
+    bar_all_compute();
     float* s_og = reinterpret_cast<float*>(smem);   // [16 i][8 h][24] global-frame points (region X is free)
 #pragma unroll
     for (int hh = 0; hh < H / 2; ++hh) {
@@ -622,6 +649,35 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
       }
     }
+    // pair aggregation (M = 64: channel c = 16 * gw + lane in lanes 0-15; one 8-column accumulator per row).
+    // The last pair MMA is older than the O^T MMAs, so O_DONE covers it.  Group g drains rows i = g, g+2, ...
+    for (int n = 0; n < IB / 2; n += 2) {   // two rows per pass: lanes 0-15 store row iA, lanes 16-31 row iB
+      const int iA = 2 * n + g, iB = iA + 2;
+      float va[8], vb[8];
+      tmem_ld_x8(tmem_lane + kColPair + iA * 8, va);
+      tmem_ld_x8(tmem_lane + kColPair + iB * 8, vb);
+      tmem_wait_ld();
+      if (lane < 16) {
+        const float4 a0 = *reinterpret_cast<const float4*>(inv_o + iA * H), a1 = *reinterpret_cast<const float4*>(inv_o + iA * H + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(inv_o + iB * H), b1 = *reinterpret_cast<const float4*>(inv_o + iB * H + 4);
+        const float na[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float nb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        __nv_bfloat16* st16 = reinterpret_cast<__nv_bfloat16*>(stage_w);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          st16[h * 16 + lane] = __float2bfloat16_rn(va[h] * na[h]);
+          st16[128 + h * 16 + lane] = __float2bfloat16_rn(vb[h] * nb[h]);
+        }
+      }
+      __syncwarp();
+      {
+        const int i = (lane < 16) ? iA : iB, l16 = lane & 15;
+        const int h = l16 >> 1, half = l16 & 1;
+        uint4 val = reinterpret_cast<const uint4*>(stage_w)[lane];
+        *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + NS + h * C + gw * 16 + half * 8) = val;
+      }
+      __syncwarp();
+    }
     tcgen05_fence_before_sync();
     bar_all_compute();
     // inverse frame + norms (diffab_pytorch.py:327-336,453-457): ol[c'] = sum_k (og[k] - t[k]) R[c'][k];
@@ -630,10 +686,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const int i = gt >> 3, h = gt & 7;
       const int64_t row = row0 + i;
       const float* gp = s_og + (i * H + h) * 24;
-      float Rm[9];
-#pragma unroll
-      for (int c = 0; c < 9; ++c) Rm[c] = __ldg(R + row * 9 + c);
-      const float tx = __ldg(tc + row * 3), ty = __ldg(tc + row * 3 + 1), tz = __ldg(tc + row * 3 + 2);
+      const float tx = tfr[0], ty = tfr[1], tz = tfr[2];
       float out[24], nrm[8];
 #pragma unroll
       for (int p = 0; p < P; ++p) {

@@ -80,7 +80,7 @@ if "pack" in which:
     nk = -0.5 * ch[..., 0] * (kk ** 2).sum(-1)
     print("K norm err", (Kp[:, :, 56:59].float().sum(-1) - nk).abs().max().item(), "max", nk.abs().max().item())
     print("Q ones", Qp[0, 0, 56:64].tolist(), "K pad", Kp[0, 0, 59:64].tolist(), Kp[0, 0, 88:96].tolist())
-    print("V point err", (Vh[:, :, 32:56].float() - vp.reshape(rows, 8, 24)).abs().max().item(), "pad", Vh[0, 0, 56:64].tolist())
+    print("V point err", (Vh[:, :, 32:56].float() - vp.reshape(rows, 8, 24)).abs().max().item(), "ones+pad", Vh[0, 0, 56:64].tolist())
 
 if "layer" in which:
     from oracle import ipa as oipa

@@ -41,9 +41,9 @@ for k in order:
 tot = tl[:, 5] - tl[:, 0]
 print(f"total per CTA: mean {tot.mean():.0f} cycles; rows mean {(tl[:,15]-tl[:,2]).mean()/16:.0f} cycles/row; issuer done with pair MMAs at {(tl[:,3]-tl[:,0]).mean():.0f}")
 print("row 8 breakdown (compute thread 0):")
-lab = {33: "bias regs + S tmem ld", 34: "max butterfly + barrier", 35: "exp, sums", 36: "drain_pair(prev)", 12: "P stores + fence + arrive"}
+lab = {33: "bias regs + S tmem ld", 34: "max butterfly + barrier", 12: "row A: exp, P stores, arrive", 13: "row B: exp, P stores, arrive"}
 prev = tl[:, 11]
-for k in (33, 34, 35, 36, 12):
+for k in (33, 34, 12, 13):
     d = tl[:, k] - prev
     print(f"  {lab[k]:34s} mean {d.mean():8.0f}  p10 {d.quantile(0.1):8.0f}  p90 {d.quantile(0.9):8.0f}")
     prev = tl[:, k]
