@@ -133,12 +133,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, skip=0):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = self.rows[skip:] if len(self.rows) > skip else self.rows[-3:]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -237,6 +238,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()                     # nvidia-smi needs ~1 s to start: begin before the warm-up steps
     for _ in range(n_warm):
         one_step()
     barrier()
@@ -245,8 +248,7 @@ def main():
     model.sample_from_context(s0, x0, O0, res_ctx, pair_ctx, m, use_cuda_graph=False, t_start=T, t_stop=T)
     launches_per_reverse_step = lib.dab_launch_count() - c0
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    n_clock_warm = len(clocks.rows)    # samples taken before the timed region are dropped
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -255,7 +257,7 @@ def main():
     ev1.record()
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
-    clock_info = clocks.stop()
+    clock_info = clocks.stop(skip=n_clock_warm)
     if dist is not None:
         tmax = torch.tensor([elapsed_ms], device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -281,7 +283,13 @@ def main():
         line["profile_only"] = True
 
     if rank == 0 and not args.skip_extras:
+        # ---- roofline of the dominant kernel (IPA attention core), measured live ---------------
+        line["roofline"] = measure_roofline(model, layer0, res_ctx, pair_ctx, x0, O0, precision, hbm_peak, peak_src)
         # ---- e2e through DiffAb.sample() from pinned host memory -------------------------------
+        # (the resident tensors of the kernel-path measurement are released first: sample() builds its own)
+        model._graph_cache = None
+        del res_ctx, pair_ctx, s0, x0, O0, b
+        torch.cuda.empty_cache()
         sample_e2e()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -294,8 +302,6 @@ def main():
         line["e2e"] = {"value": B / e2e_s, "unit": "patches/s", "h2d_bytes_per_step": h2d_bytes,
                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1000 * e2e_s, "n_gpus_measured": 1}
 
-        # ---- roofline of the dominant kernel (IPA attention core), measured live ---------------
-        line["roofline"] = measure_roofline(model, layer0, res_ctx, pair_ctx, x0, O0, precision, hbm_peak, peak_src)
         line["ipa_fwd_bwd"] = measure_ipa_fwd_bwd(dev)
 
         # ---- CPU baseline on this box's host cores ----------------------------------------------
@@ -320,18 +326,20 @@ def measure_roofline(model, layer, res_ctx, pair_ctx, x0, O0, precision, hbm_pea
     lib = _lib.lib()
     B = res_ctx.shape[0]
     x = res_ctx.contiguous()
+    bias = layer.pair_bias(pair_ctx) if precision == "bf16" else None   # hoisted out of the loop, as in sample()
+    call = (lambda: layer(x, pair_ctx, O0, x0, bias)) if precision == "bf16" else (lambda: layer(x, pair_ctx, O0, x0))
     with torch.no_grad():
-        layer(x, pair_ctx, O0, x0)            # full call: fills the workspace the core kernel reads
+        call()                                # full call: fills the workspace the core kernel reads
         torch.cuda.synchronize()
         # inference calls reuse the layer's persistent workspace, which the phase-mask contract needs
         lib.dab_debug_set_phase_mask(2)
         try:
             for _ in range(3):
-                layer(x, pair_ctx, O0, x0)
+                call()
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
             for a, b_ in evs:
                 a.record()
-                layer(x, pair_ctx, O0, x0)
+                call()
                 b_.record()
             torch.cuda.synchronize()
         finally:
@@ -339,14 +347,24 @@ def measure_roofline(model, layer, res_ctx, pair_ctx, x0, O0, precision, hbm_pea
     us = statistics.mean(a.elapsed_time(b_) for a, b_ in evs) * 1000.0
     sz = pair_ctx.element_size()
     if precision == "bf16":
-        # core kernel: reads e (bf16), packed q/k/v operands, writes concat features
-        alg = B * (L * L * 64 * sz) + B * L * (1344 + 1024) * 4
+        # attention core (DESIGN.md "Algorithmic bytes"): e row (bf16) + precomputed bias row (fp16, 8 heads) per
+        # (i, j) pair; packed Q/K (2 x 768 bf16) + V (512 fp16) operands + centred t in, concat features (1024 bf16) out
+        alg = B * L * (L * 64 * 2 + L * 8 * 2 + (768 + 768 + 512 + 1024) * 2 + 12 + 36)
     else:
-        alg = B * (L * L * 64 * sz) + B * L * (1344 + 1024) * 4
+        # fp32 core: e (fp32) twice is NOT algorithmic (second read is a cache hit by design): e once, projections in,
+        # concat features out
+        alg = B * L * (L * 64 * 4 + (1344 + 1024) * 4 + 48)
     achieved = alg / (us * 1e-6) / 1e9
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the same launch shape from the committed ncu capture
+        prof = json.load(open(os.path.join(ROOT, "profiles", "core_ncu_summary.json")))
+        if prof.get("precision") == precision and prof.get("patches_per_launch") == B:
+            traffic = prof["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
     return {"bound": "hbm", "kernel": "ipa attention core (" + precision + ")", "achieved": achieved,
             "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": None, "us_per_launch": us, "algorithmic_bytes_per_launch": alg, "patches_per_launch": B}
+            "traffic": traffic, "us_per_launch": us, "algorithmic_bytes_per_launch": alg, "patches_per_launch": B}
 
 
 def measure_ipa_fwd_bwd(dev, B=32, iters=5):

@@ -138,7 +138,7 @@ class PairEmbedding(nn.Module):
         self.mlp = _mlp([3 * d_feat + d_dihedral, d_feat, d_feat, d_feat])
 
     def forward(self, seq_idx, distmat, dihedrals, residue_idx, chain_idx, atom_mask, structure_context_mask,
-                sequence_context_mask):
+                sequence_context_mask, distmat_is_squared=False):
         B, L = seq_idx.shape
         am = atom_mask
         atom_pair = (am[:, :, None, :, None] * am[:, None, :, None, :]).flatten(-2)
@@ -155,7 +155,8 @@ class PairEmbedding(nn.Module):
         f_rel = self.relpos_embedding(rel + self.max_dist_to_consider) * chain_prod[..., None]
         coef = F.softplus(self.pair2distcoef(pair_type))
         d = distmat.flatten(-2)
-        f_dist = self.distance_embedding(torch.exp(-1 * coef * d**2) * atom_pair)
+        d2 = d if distmat_is_squared else d**2   # sample() hands over squared distances it computed itself
+        f_dist = self.distance_embedding(torch.exp(-1 * coef * d2) * atom_pair)
         f_dih = self.dihedral_embedding(dihedrals)
         return self.mlp(torch.cat([f_type, f_rel, f_dist, f_dih], dim=-1)) * res_pair[..., None]
 
@@ -488,15 +489,16 @@ class DiffAb(nn.Module):
     # ---- reference API ----
     def encode_context(self, seq_idx_t0, xyz_t0, orientations_t0, backbone_dihedrals, distmat, pairwise_dihedrals,
                        atom_mask, chain_idx, residue_idx, generation_mask, residue_mask, generate_structure=True,
-                       generate_sequence=True):
-        """diffab_pytorch.py:680-724."""
+                       generate_sequence=True, distmat_is_squared=False):
+        """diffab_pytorch.py:680-724 (``distmat_is_squared`` is ours: lets ``sample`` skip a sqrt / square pair)."""
         context_mask = residue_mask & (~generation_mask)
         structure_context_mask = context_mask if generate_structure else None
         sequence_context_mask = context_mask if generate_sequence else None
         res = self.residue_context_embedding(seq_idx_t0, xyz_t0, orientations_t0, backbone_dihedrals, chain_idx,
                                              atom_mask, structure_context_mask, sequence_context_mask)
         pair = self.pair_context_embedding(seq_idx_t0, distmat, pairwise_dihedrals, residue_idx, chain_idx, atom_mask,
-                                           structure_context_mask, sequence_context_mask)
+                                           structure_context_mask, sequence_context_mask,
+                                           distmat_is_squared=distmat_is_squared)
         return res, pair
 
     def denoise(self, seq_idx_t, translations_t, orientations_t, res_context_emb, pair_context_emb, beta,
@@ -686,14 +688,17 @@ class DiffAb(nn.Module):
         distmat = mv(distmat)
         use_bf16 = precision == "bf16" and self.denoiser.ipa.layers[0].fast_path_supported(L)
         res_parts, pair_parts = [], []
-        from .synth import pairwise_atom_distances
+        from .synth import pairwise_atom_distances, pairwise_atom_sq_distances
+        # distances derived on the device: exact differences on the fp32 path, the cheaper Gram-matrix form
+        # (|a|^2 + |b|^2 - 2 a.b, ~1e-3 A^2 absolute error) on the bf16 path
+        derive = pairwise_atom_sq_distances if use_bf16 else (lambda v: pairwise_atom_distances(v).pow(2))
         with _tf32_matmuls(use_bf16):
             for lo in range(0, B, context_chunk):
                 sl = slice(lo, min(B, lo + context_chunk))
-                dm = distmat[sl] if distmat is not None else pairwise_atom_distances(xyz[sl])
+                dm = distmat[sl] if distmat is not None else derive(xyz[sl])
                 r, p = self.encode_context(seq_idx[sl], xyz[sl], orientations[sl], backbone_dihedrals[sl], dm,
                                            pairwise_dihedrals[sl], atom_mask[sl], chain_idx[sl], residue_idx[sl],
-                                           generation_mask[sl], residue_mask[sl])
+                                           generation_mask[sl], residue_mask[sl], distmat_is_squared=distmat is None)
                 res_parts.append(r)
                 pair_parts.append(cast_pair_to_bf16(p) if use_bf16 else p)
         res_ctx, pair_ctx = torch.cat(res_parts), torch.cat(pair_parts)

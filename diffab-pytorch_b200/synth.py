@@ -29,6 +29,23 @@ def pairwise_atom_distances(xyz):
     return d.norm(dim=-1)
 
 
+def pairwise_atom_sq_distances(xyz):
+    """(B,L,A,3) -> (B,L,L,A,A) SQUARED distances via |a|^2 + |b|^2 - 2 a.b on patch-centred coordinates
+    (one small batched matmul instead of a (B,L,L,A,A,3) difference tensor).  The product runs in full fp32
+    (TF32 would destroy the cancellation); centring keeps the absolute error ~1e-4 A^2."""
+    B, L, A, _ = xyz.shape
+    flat = (xyz - xyz[:, :, 1].mean(dim=1)[:, None, None, :]).reshape(B, L * A, 3)
+    n2 = flat.pow(2).sum(-1)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        gram = torch.bmm(flat, flat.transpose(1, 2))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    d2 = (n2[:, :, None] + n2[:, None, :] - 2 * gram).clamp_min_(0)
+    return d2.view(B, L, A, L, A).permute(0, 1, 3, 2, 4).contiguous()
+
+
 def make_patches(B, L=128, A=15, seed=0, with_distmat=True, cdr=(56, 72)):
     """One batch of synthetic patches on CPU (fp32 / int64 / bool)."""
     g = torch.Generator().manual_seed(seed)
