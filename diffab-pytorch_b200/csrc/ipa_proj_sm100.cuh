@@ -3,11 +3,12 @@
 //
 // Replaces diffab_pytorch.py:391-413 (to_{q,k,v}_{scalar,point} + euclidean_transform) in one launch:
 // the fp32 projection tensor never exists in HBM.  One CTA per patch (128 residues = the M tile of the MMA).
-//   warps 0-3: convert the x tile to bf16 in shared memory (128B-swizzled, K-major), then run the epilogue:
-//              thread r owns residue r = TMEM lane r, so the frame (R_r, t_r) lives in its registers
-//   warp 4   : streams the 24 weight tiles by TMA (ring of 3) and issues the tcgen05.mma chains
-//              (M=128, N=64 for two heads of scalars, N=48 for two heads of points, K=128) into two
-//              alternating TMEM accumulators, so tile t+1 is computed while tile t is packed.
+//   warps 0-7: convert the x tile to bf16 in shared memory (128B-swizzled, K-major), then run the epilogue as
+//              two groups of 128 threads, one per TMEM accumulator (group g packs tiles t = g, g+2, ...):
+//              thread r of a group owns residue r = TMEM lane r, so the frame (R_r, t_r) lives in its registers
+//   warp 8   : streams the 24 weight tiles by TMA (ring of 3) and issues the tcgen05.mma chains
+//              (M=128, N=64 for two heads of scalars, N=48 for two heads of points, K=128) into the two
+//              alternating accumulators, so two tiles are packed while the next ones are computed.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -28,7 +29,9 @@ struct ProjSmem {
   static constexpr int kBars = kMisc;                 // 16 mbarriers
   static constexpr int kTmemSlot = kBars + 16 * 8;
   static constexpr int kCen = kTmemSlot + 16;         // centroid partials [4][3] + result [3]
-  static constexpr int kTotal = kCen + 64;
+  static constexpr int kStage = kCen + 64;            // per-warp staging: 32 rows x 80 B pitch (64 B payload)
+  static constexpr int kStageWarp = 32 * 80;
+  static constexpr int kTotal = kStage + 8 * kStageWarp;
 };
 enum ProjBar { W_FULL = 0, W_EMPTY = 3, ACC_FULL = 6, ACC_EMPTY = 8, PROJ_N_BARS = 10 };
 
@@ -44,11 +47,14 @@ __device__ __forceinline__ uint32_t pk_h(float a, float b) {
 }
 
 // map_w64 / map_w48: the packed bf16 weight matrix [1344, 128] with boxes {64, 64} / {64, 48}
-__global__ void __launch_bounds__(160, 2)
+__global__ void __launch_bounds__(288, 2)
 ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_constant__ CUtensorMap map_w48,
                 const float* __restrict__ x, const float* __restrict__ R, const float* __restrict__ t,
                 const float* __restrict__ gamma, __nv_bfloat16* __restrict__ Qp, __nv_bfloat16* __restrict__ Kp,
-                __nv_bfloat16* __restrict__ Vp, float* __restrict__ tc) {
+                __nv_bfloat16* __restrict__ Vp, float* __restrict__ tc, long long* __restrict__ dbg) {
+  long long* dbg_cta = dbg ? dbg + (size_t)blockIdx.x * 64 : nullptr;
+#define PROJ_STAMP(k) do { if (dbg_cta && threadIdx.x == 0) dbg_cta[(k)] = clock64(); } while (0)
+  PROJ_STAMP(0);
   constexpr int L = 128, D = 128, H = 8, DS = 32, P = 8, QK_W = 96, V_W = 64;
   constexpr float kLog2e = 1.4426950408889634f;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -68,29 +74,32 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
   __syncwarp();
   if (warp == 0) tmem_alloc(tmem_slot, 128);
 
-  if (warp < 4) {
-    // ---- x tile: fp32 global (coalesced float4) -> bf16, K-major 128B-swizzled A operand
+  if (warp < 8) {
+    // ---- x tile: fp32 global (coalesced float4) -> bf16, K-major 128B-swizzled A operand (16 rows per warp)
     const float* xb = x + (int64_t)b * L * D;
     const uint32_t kb = lane >> 4, chunk = (lane & 15) >> 1, half = (lane & 1) * 8;
 #pragma unroll 4
-    for (int rr = 0; rr < 32; ++rr) {
-      const int r = warp * 32 + rr;
+    for (int rr = 0; rr < 16; ++rr) {
+      const int r = warp * 16 + rr;
       float4 v = __ldg(reinterpret_cast<const float4*>(xb + r * D) + lane);
       uint2 o = make_uint2(pk_bf(v.x, v.y), pk_bf(v.z, v.w));
       *reinterpret_cast<uint2*>(smem + S::kA + kb * 16384 + swz128_offset(r, chunk) + half) = o;
     }
     // ---- patch centroid of the translations (see ipa_sm100.cu: keeps the expanded distance well conditioned)
-    const float* tp = t + ((int64_t)b * L + tid) * 3;
-    float cx = warp_sum(tp[0]), cy = warp_sum(tp[1]), cz = warp_sum(tp[2]);
-    if (lane == 0) { s_cen[warp * 3] = cx; s_cen[warp * 3 + 1] = cy; s_cen[warp * 3 + 2] = cz; }
+    if (warp < 4) {
+      const float* tp = t + ((int64_t)b * L + tid) * 3;
+      float cx = warp_sum(tp[0]), cy = warp_sum(tp[1]), cz = warp_sum(tp[2]);
+      if (lane == 0) { s_cen[warp * 3] = cx; s_cen[warp * 3 + 1] = cy; s_cen[warp * 3 + 2] = cz; }
+    }
     fence_proxy_async_smem();
   }
   tcgen05_fence_before_sync();
   __syncthreads();
   tcgen05_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  PROJ_STAMP(1);
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&map_w64);
       tma_prefetch_desc(&map_w48);
@@ -131,9 +140,10 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
       }
     }
   } else {
-    // ---- epilogue: thread = residue
-    const int64_t row = (int64_t)b * L + tid;
-    const uint32_t tmem_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    // ---- epilogue: thread = residue; group g = warp / 4 owns accumulator g
+    const int g = warp >> 2, gt = tid & 127;
+    const int64_t row = (int64_t)b * L + gt;
+    const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float cenx = (s_cen[0] + s_cen[3] + s_cen[6] + s_cen[9]) * (1.0f / L);
     const float ceny = (s_cen[1] + s_cen[4] + s_cen[7] + s_cen[10]) * (1.0f / L);
     const float cenz = (s_cen[2] + s_cen[5] + s_cen[8] + s_cen[11]) * (1.0f / L);
@@ -141,16 +151,31 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
 #pragma unroll
     for (int c = 0; c < 9; ++c) Rm[c] = __ldg(R + row * 9 + c);
     const float tcx = __ldg(t + row * 3) - cenx, tcy = __ldg(t + row * 3 + 1) - ceny, tcz = __ldg(t + row * 3 + 2) - cenz;
-    tc[row * 3] = tcx; tc[row * 3 + 1] = tcy; tc[row * 3 + 2] = tcz;
+    if (g == 0) { tc[row * 3] = tcx; tc[row * 3 + 1] = tcy; tc[row * 3 + 2] = tcz; }
     const float ss = rsqrtf((float)DS), sp = rsqrtf(4.5f * P), st = rsqrtf(3.0f);
-    __nv_bfloat16* qrow = Qp + row * (H * QK_W);
-    __nv_bfloat16* krow = Kp + row * (H * QK_W);
-    __nv_bfloat16* vrow = Vp + row * (H * V_W);
+    // Every 64-byte output segment of a row goes through a warp-private staging tile so that global stores are
+    // runs of four consecutive 16 B chunks per row (thread-per-row 16 B stores scattered over 32 rows cost
+    // ~7k cycles per tile; measured).
+    uint4* stage = reinterpret_cast<uint4*>(smem + S::kStage + warp * S::kStageWarp);
+    const int wrow0 = (warp & 3) * 32;   // first row of this warp inside the patch
+    auto flush = [&](const uint4 (&seg)[4], __nv_bfloat16* base, int row_elems, int col_elems) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) stage[lane * 5 + q] = seg[q];
+      __syncwarp();
+      uint8_t* gbase = reinterpret_cast<uint8_t*>(base + ((int64_t)b * L + wrow0) * row_elems + col_elems);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = k * 8 + (lane >> 2), c = lane & 3;
+        *reinterpret_cast<uint4*>(gbase + (size_t)r * row_elems * 2 + c * 16) = stage[r * 5 + c];
+      }
+      __syncwarp();
+    };
 
-    for (int tt = 0; tt < kProjTiles; ++tt) {
-      const int acc = tt & 1;
+    for (int tt = g; tt < kProjTiles; tt += 2) {
+      const int acc = g;
       mbar_wait(&bars[ACC_FULL + acc], (tt >> 1) & 1);
       tcgen05_fence_after_sync();
+      if (tt == 4 || tt == 16) PROJ_STAMP(tt == 4 ? 2 : 5);
       float v[64];
       {
         float a[32], c[32];
@@ -162,6 +187,7 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
       }
       tcgen05_fence_before_sync();
       mbar_arrive(&bars[ACC_EMPTY + acc]);
+      if (tt == 4 || tt == 16) PROJ_STAMP(tt == 4 ? 3 : 6);
       if (tt < 12) {
         // ---------------- two heads of scalars: 32 features each
         const int seg = tt >> 2, h0 = (tt & 3) * 2;
@@ -169,19 +195,20 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const int h = h0 + hh;
-          uint4* dst = reinterpret_cast<uint4*>(seg == 0 ? qrow + h * QK_W : seg == 1 ? krow + h * QK_W : vrow + h * V_W);
+          uint4 o[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float* s8 = v + hh * 32 + q * 8;
-            uint4 o;
             if (seg == 2) {
-              o = make_uint4(pk_h(s8[0], s8[1]), pk_h(s8[2], s8[3]), pk_h(s8[4], s8[5]), pk_h(s8[6], s8[7]));
+              o[q] = make_uint4(pk_h(s8[0], s8[1]), pk_h(s8[2], s8[3]), pk_h(s8[4], s8[5]), pk_h(s8[6], s8[7]));
             } else {
-              o = make_uint4(pk_bf(s8[0] * sc, s8[1] * sc), pk_bf(s8[2] * sc, s8[3] * sc), pk_bf(s8[4] * sc, s8[5] * sc),
-                             pk_bf(s8[6] * sc, s8[7] * sc));
+              o[q] = make_uint4(pk_bf(s8[0] * sc, s8[1] * sc), pk_bf(s8[2] * sc, s8[3] * sc),
+                                pk_bf(s8[4] * sc, s8[5] * sc), pk_bf(s8[6] * sc, s8[7] * sc));
             }
-            dst[q] = o;
           }
+          if (seg == 0) flush(o, Qp, H * QK_W, h * QK_W);
+          else if (seg == 1) flush(o, Kp, H * QK_W, h * QK_W);
+          else flush(o, Vp, H * V_W, h * V_W);
         }
       } else {
         // ---------------- two heads of points: 8 points x 3 each; euclidean_transform (diffab_pytorch.py:315-324)
@@ -189,39 +216,39 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const int h = h0 + hh;
-          float g[24];
+          float gl[24];
 #pragma unroll
           for (int p = 0; p < P; ++p) {
             const float px = v[hh * 24 + 3 * p], py = v[hh * 24 + 3 * p + 1], pz = v[hh * 24 + 3 * p + 2];
-            g[3 * p] = px * Rm[0] + py * Rm[3] + pz * Rm[6] + tcx;
-            g[3 * p + 1] = px * Rm[1] + py * Rm[4] + pz * Rm[7] + tcy;
-            g[3 * p + 2] = px * Rm[2] + py * Rm[5] + pz * Rm[8] + tcz;
+            gl[3 * p] = px * Rm[0] + py * Rm[3] + pz * Rm[6] + tcx;
+            gl[3 * p + 1] = px * Rm[1] + py * Rm[4] + pz * Rm[7] + tcy;
+            gl[3 * p + 2] = px * Rm[2] + py * Rm[5] + pz * Rm[8] + tcz;
           }
           if (seg == 2) {   // values: fp16 [32..55]; column 56 = 1 (the O^T MMA then returns sum_j p), zeros after
-            uint4* dst = reinterpret_cast<uint4*>(vrow + h * V_W + 32);
+            uint4 o[4];
 #pragma unroll
             for (int q = 0; q < 3; ++q)
-              dst[q] = make_uint4(pk_h(g[8 * q], g[8 * q + 1]), pk_h(g[8 * q + 2], g[8 * q + 3]),
-                                  pk_h(g[8 * q + 4], g[8 * q + 5]), pk_h(g[8 * q + 6], g[8 * q + 7]));
-            dst[3] = make_uint4(pk_h(1.0f, 0.0f), 0, 0, 0);
+              o[q] = make_uint4(pk_h(gl[8 * q], gl[8 * q + 1]), pk_h(gl[8 * q + 2], gl[8 * q + 3]),
+                                pk_h(gl[8 * q + 4], gl[8 * q + 5]), pk_h(gl[8 * q + 6], gl[8 * q + 7]));
+            o[3] = make_uint4(pk_h(1.0f, 0.0f), 0, 0, 0);
+            flush(o, Vp, H * V_W, h * V_W + 32);
           } else {
             const float ch = st * sp * __ldg(gamma + h) * kLog2e;
             const float sc = seg == 0 ? ch : 1.0f;
             float hi[24], lo[24], n2 = 0.f;
 #pragma unroll
             for (int c = 0; c < 24; ++c) {
-              const float val = g[c] * sc;
+              const float val = gl[c] * sc;
               hi[c] = __bfloat162float(__float2bfloat16_rn(val));
               lo[c] = val - hi[c];
-              n2 = fmaf(g[c], g[c], n2);
+              n2 = fmaf(gl[c], gl[c], n2);
             }
-            uint4* dh = reinterpret_cast<uint4*>((seg == 0 ? qrow : krow) + h * QK_W + 32);
-            uint4* dl = reinterpret_cast<uint4*>((seg == 0 ? qrow : krow) + h * QK_W + 64);
+            uint4 oh[4], ol[4];
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
-              dh[q] = make_uint4(pk_bf(hi[8 * q], hi[8 * q + 1]), pk_bf(hi[8 * q + 2], hi[8 * q + 3]),
+              oh[q] = make_uint4(pk_bf(hi[8 * q], hi[8 * q + 1]), pk_bf(hi[8 * q + 2], hi[8 * q + 3]),
                                  pk_bf(hi[8 * q + 4], hi[8 * q + 5]), pk_bf(hi[8 * q + 6], hi[8 * q + 7]));
-              dl[q] = make_uint4(pk_bf(lo[8 * q], lo[8 * q + 1]), pk_bf(lo[8 * q + 2], lo[8 * q + 3]),
+              ol[q] = make_uint4(pk_bf(lo[8 * q], lo[8 * q + 1]), pk_bf(lo[8 * q + 2], lo[8 * q + 3]),
                                  pk_bf(lo[8 * q + 4], lo[8 * q + 5]), pk_bf(lo[8 * q + 6], lo[8 * q + 7]));
             }
             uint4 tail = make_uint4(0, 0, 0, 0);
@@ -233,15 +260,21 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
               const float m = __bfloat162float(__float2bfloat16_rn(nk - a));
               tail.x = pk_bf(a, m); tail.y = pk_bf(nk - a - m, 0.0f);
             }
-            dh[3] = tail;
-            dl[3] = make_uint4(0, 0, 0, 0);
+            oh[3] = tail;
+            ol[3] = make_uint4(0, 0, 0, 0);
+            __nv_bfloat16* dstp = seg == 0 ? Qp : Kp;
+            flush(oh, dstp, H * QK_W, h * QK_W + 32);
+            flush(ol, dstp, H * QK_W, h * QK_W + 64);
           }
         }
       }
+      if (tt == 4 || tt == 16) PROJ_STAMP(tt == 4 ? 4 : 7);
     }
   }
   tcgen05_fence_before_sync();
   __syncthreads();
+  PROJ_STAMP(8);
+#undef PROJ_STAMP
   if (warp == 0) tmem_free(tmem, 128);
 }
 

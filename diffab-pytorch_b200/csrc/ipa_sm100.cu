@@ -61,6 +61,8 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
 
 namespace sm100 {
 
+static long long* g_core_dbg = nullptr;   // optional timeline buffer (dab_debug_set_timeline)
+
 // fixed configuration of the fast path
 constexpr int L = 128, D = 128, C = 64, H = 8, DS = 32, P = 8;
 constexpr int NS = H * DS;            // 256
@@ -754,7 +756,6 @@ __global__ void __launch_bounds__(128) ipa_pair_bias_kernel(const uint4* __restr
                           pack_h2(acc[6], acc[7]));
 }
 
-static long long* g_core_dbg = nullptr;
 
 // ---- workspace --------------------------------------------------------------------------------------
 struct Ws {
@@ -847,8 +848,8 @@ int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, c
       cudaFuncSetAttribute(ipa_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ProjSmem::kTotal);
       proj_attr_done = true;
     }
-    ipa_proj_kernel<<<B, 160, ProjSmem::kTotal, s>>>(mw64, mw48, x, R, t, reinterpret_cast<const float*>(pk + po.gamma),
-                                                     ws.Qp, ws.Kp, ws.Vp, ws.tc);
+    ipa_proj_kernel<<<B, 288, ProjSmem::kTotal, s>>>(mw64, mw48, x, R, t, reinterpret_cast<const float*>(pk + po.gamma),
+                                                     ws.Qp, ws.Kp, ws.Vp, ws.tc, g_core_dbg ? g_core_dbg + (1 << 20) : nullptr);
     count_launch();
   }
   if (phases & 2) {
@@ -880,8 +881,8 @@ int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, c
     count_launch();
   }
   if (phases & 4) {
-    if (int rc = launch_gemm_bf16<64>(ws.cat, NCAT, pk + po.wout, NCAT, y, D, reinterpret_cast<const float*>(pk + po.bout),
-                                      M, D, NCAT, s))
+    if (int rc = launch_gemm_bf16<128>(ws.cat, NCAT, pk + po.wout, NCAT, y, D, reinterpret_cast<const float*>(pk + po.bout),
+                                       M, D, NCAT, s))
       return rc;
   }
   return check_launch("dab_ipa_fwd_sm100");

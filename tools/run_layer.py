@@ -19,7 +19,8 @@ e = torch.randn(B, 128, 128, 64, device=dev, generator=g).bfloat16()
 R = synth.uniform_rotations(B, 128, device=dev)
 t = 10 * torch.randn(B, 128, 3, device=dev, generator=g)
 with torch.no_grad():
+    bias = layer.pair_bias(e)      # hoisted out of the sampling loop by DiffAb.sample
     for _ in range(n):
-        y = layer(x, e, R, t)
+        y = layer(x, e, R, t, bias)
 torch.cuda.synchronize()
 print("ok", float(y.abs().max()))

@@ -22,12 +22,13 @@ t = 10 * torch.randn(B, 128, 3, device=dev, generator=g)
 with torch.no_grad():
     for _ in range(3):
         layer(x, e, R, t)
-    buf = torch.zeros(B * 8 * 64, dtype=torch.int64, device=dev)
+    buf = torch.zeros((1 << 20) + B * 64, dtype=torch.int64, device=dev)
     lib.dab_debug_set_timeline(ptr(buf))
     layer(x, e, R, t)
     torch.cuda.synchronize()
     lib.dab_debug_set_timeline(None)
-tl = buf.view(B * 8, 64).cpu().double()
+tl = buf[: B * 8 * 64].view(B * 8, 64).cpu().double()
+pt = buf[1 << 20:].view(B, 64).cpu().double()
 t0 = tl[:, 0:1]
 names = {1: "setup", 2: "stage1 (S^T) [issuer]", 24: "final drain", 4: "wait O^T (stage 3)", 5: "epilogue"}
 order = [1, 2] + list(range(8, 16)) + [24, 4, 5]
@@ -55,3 +56,12 @@ for k in (41, 42, 43):
     d = tl[:, k] - prev
     print(f"  {lab[k]:36s} mean {d.mean():8.0f}  p10 {d.quantile(0.1):8.0f}  p90 {d.quantile(0.9):8.0f}")
     prev = tl[:, k]
+
+print("projection kernel (per CTA, thread 0 = group 0):")
+lab = {1: "x->bf16 smem, centroid, sync", 2: "... until tile 4 accumulator ready", 3: "tile 4: tmem ld + release", 4: "tile 4 (scalar): pack + stores", 5: "... until tile 16 ready", 6: "tile 16: tmem ld + release", 7: "tile 16 (points): transform, split, stores", 8: "... to the end"}
+prev = pt[:, 0]
+for k in range(1, 9):
+    d = pt[:, k] - prev
+    print(f"  {lab[k]:44s} mean {d.mean():8.0f}  p10 {d.quantile(0.1):8.0f}  p90 {d.quantile(0.9):8.0f}")
+    prev = pt[:, k]
+print(f"  total {(pt[:,8]-pt[:,0]).mean():.0f} cycles")
