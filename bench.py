@@ -287,13 +287,12 @@ def main():
         line["roofline"] = measure_roofline(model, layer0, res_ctx, pair_ctx, x0, O0, precision, hbm_peak, peak_src)
         # ---- e2e through DiffAb.sample() from pinned host memory -------------------------------
         # (the resident tensors of the kernel-path measurement are released first: sample() builds its own)
-        model._graph_cache = None
         del res_ctx, pair_ctx, s0, x0, O0, b
         torch.cuda.empty_cache()
         sample_e2e()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        n_e2e = max(1, min(args.steps, 2))
+        n_e2e = max(1, min(args.steps, 3))
         for _ in range(n_e2e):
             res = sample_e2e()
         torch.cuda.synchronize()

@@ -307,13 +307,16 @@ class InvariantPointAttentionLayer(nn.Module):
             self._packed = (key, buf)
         return self._packed[1]
 
-    def pair_bias(self, e_bf16):
+    def pair_bias(self, e_bf16, out=None):
         """This layer's pair bias for every (i, j) as fp16 (B, L, L, H), scale_total and log2(e) folded in.
         The pair tensor is constant over the sampling loop, so ``DiffAb.sample`` computes this once per run."""
         e = _lib.dev(e_bf16, torch.bfloat16, "e")
         B, L = e.shape[0], e.shape[1]
         dims = _ipa_structs(self, B, L)
-        out = torch.empty(B, L, L, self.n_head, device=e.device, dtype=torch.float16)
+        if out is None:
+            out = torch.empty(B, L, L, self.n_head, device=e.device, dtype=torch.float16)
+        elif out.dtype != torch.float16 or tuple(out.shape) != (B, L, L, self.n_head) or not out.is_contiguous():
+            raise ValueError("pair_bias: `out` must be a contiguous fp16 (B, L, L, H) tensor")
         w = _lib.dev(self.to_pair_bias.weight.detach(), torch.float32, "to_pair_bias.weight")
         _lib.check(_lib.lib().dab_ipa_pair_bias(ctypes.byref(dims), ptr(e), ptr(w), ptr(out), _lib.stream_ptr()),
                    "dab_ipa_pair_bias")
@@ -629,37 +632,49 @@ class DiffAb(nn.Module):
         return self.denoiser.ipa.precompute_pair_bias(pair_ctx)
 
     def _sample_graphed(self, s, x, O, res_ctx, pair_ctx, generation_mask, t_start, t_stop):
-        """One reverse step captured in a CUDA graph and replayed; the step index lives in a device
-        tensor.  The graph is cached for as long as the context tensors stay the same objects."""
+        """One reverse step captured in a CUDA graph and replayed; the step index lives in a device tensor.
+        The graph works on static buffers (state, context, mask, pair-bias planes) and is cached per shape, so
+        repeated ``sample()`` calls only copy their context in (~1 GB device-to-device, well under a millisecond)."""
         B, L = s.shape
         dev = s.device
-        key = (B, L, res_ctx.data_ptr(), pair_ctx.data_ptr(), generation_mask.data_ptr(), pair_ctx.dtype)
+        key = (B, L, tuple(res_ctx.shape), tuple(pair_ctx.shape), pair_ctx.dtype, str(dev))
         cache = getattr(self, "_graph_cache", None)
-        if cache is None or cache["key"] != key:
-            st = {"key": key, "s": torch.empty_like(s), "x": torch.empty_like(x), "O": torch.empty_like(O),
-                  "t": torch.full((B,), t_start, device=dev, dtype=torch.int64),
-                  "keep": (res_ctx, pair_ctx, generation_mask), "bias": self._pair_bias_planes(pair_ctx)}
+        fresh = cache is None or cache["key"] != key
+        if fresh:
+            cache = {"key": key, "s": torch.empty_like(s), "x": torch.empty_like(x), "O": torch.empty_like(O),
+                     "t": torch.full((B,), t_start, device=dev, dtype=torch.int64),
+                     "res": torch.empty_like(res_ctx), "pair": torch.empty_like(pair_ctx),
+                     "mask": torch.empty_like(generation_mask), "bias": None, "graph": None}
+        st = cache
+        st["res"].copy_(res_ctx); st["pair"].copy_(pair_ctx); st["mask"].copy_(generation_mask)
+        if pair_ctx.dtype == torch.bfloat16:   # per-layer pair-bias planes, written straight into the static buffers
+            layers = self.denoiser.ipa.layers
+            if st["bias"] is None:
+                st["bias"] = [torch.empty(B, L, L, l.n_head, device=dev, dtype=torch.float16) for l in layers]
+            for l, plane in zip(layers, st["bias"]):
+                l.pair_bias(st["pair"], out=plane)
+        if fresh:
             st["s"].copy_(s); st["x"].copy_(x); st["O"].copy_(O)
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 for _ in range(2):  # warm-up outside capture (allocator, lazy init, weight packing)
-                    self.reverse_step(st["s"].clone(), st["x"].clone(), st["O"].clone(), res_ctx, pair_ctx,
-                                      generation_mask, st["t"], self.draw_step_noise(B, L, dev), pair_bias=st["bias"])
+                    self.reverse_step(st["s"].clone(), st["x"].clone(), st["O"].clone(), st["res"], st["pair"],
+                                      st["mask"], st["t"], self.draw_step_noise(B, L, dev), pair_bias=st["bias"])
             torch.cuda.current_stream(dev).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 noise = self.draw_step_noise(B, L, dev)
-                self.reverse_step(st["s"], st["x"], st["O"], res_ctx, pair_ctx, generation_mask, st["t"], noise,
+                self.reverse_step(st["s"], st["x"], st["O"], st["res"], st["pair"], st["mask"], st["t"], noise,
                                   inplace=True, pair_bias=st["bias"])
                 st["t"].sub_(1)
             st["graph"] = graph
-            self._graph_cache = cache = st
-        cache["s"].copy_(s); cache["x"].copy_(x); cache["O"].copy_(O)
-        cache["t"].fill_(t_start)
+            self._graph_cache = st
+        st["s"].copy_(s); st["x"].copy_(x); st["O"].copy_(O)
+        st["t"].fill_(t_start)
         for _ in range(t_start, t_stop - 1, -1):
-            cache["graph"].replay()
-        return {"seq_idx": cache["s"].clone(), "translations": cache["x"].clone(), "orientations": cache["O"].clone()}
+            st["graph"].replay()
+        return {"seq_idx": st["s"].clone(), "translations": st["x"].clone(), "orientations": st["O"].clone()}
 
     @torch.no_grad()
     def sample(self, seq_idx, xyz, orientations, backbone_dihedrals=None, distmat=None, pairwise_dihedrals=None,
