@@ -1,0 +1,873 @@
+// sm_100a backward of one InvariantPointAttentionLayer (train.py configuration), i.e. the autograd backward of
+// diffab_pytorch.py:389-465 of the reference, from the upstream gradient of the concat features (dcat = dy Wout)
+// down to the gradient of the six projections (dproj), of the pair tensor (de), of to_pair_bias and of gamma.
+// The four plain GEMMs around it (dcat = dy Wout, dWout = dy^T cat, dx = dproj Wcat, dWcat = dproj^T x) are
+// library GEMMs issued by the caller.
+//
+// With P = softmax_j(l), l_ij,h = a qs_i.ks_j + st b_ij,h - c_h/2 |q~_i - k~_j|^2 (q~, k~: global-frame points):
+//   dP_ij,h = dos_i,h . vs_j,h + dog_i,h . v~_j,h + dopair_i,h . e_ij          (gradient of the three aggregations)
+//   dl_ij,h = P_ij,h (dP_ij,h - Delta_i,h),   Delta_i,h = sum_j P dP = <dO_i,h, O_i,h>  (from the saved outputs)
+//   de_ij   = sum_h P_ij,h dopair_i,h + dl_ij,h st Wpb_h                         dWpb_h = st sum_ij dl_ij,h e_ij
+//   dq_i,h  = sum_j dl_ij,h [a ks_j | c_h k~_j]  - c_h q~_i sum_j dl_ij,h        (query side: this kernel)
+//   dk_j,h  = sum_i dl_ij,h [a qs_i | c_h q~_i]  - c_h k~_j sum_i dl_ij,h        (key side: second kernel)
+//   dv_j,h  = sum_i P_ij,h [dos_i,h | dog_i,h]
+//   dgamma_h = (1/gamma_h) sum_ij dl_ij,h lp_ij,h,  lp = l - ls - lb, each sum obtained from quantities at hand:
+//              sum dl l from the logits in registers, sum dl ls = <qs, dqs>, sum dl lb = <st Wpb, sum dl e>.
+//
+// Launch sequence (dab_ipa_bwd_sm100):
+//   1. bwd_prep_kernel      : dcat, cat -> dO (fp16, per-row power-of-two scaling; bf16 copy), dopair (bf16), Delta
+//   2. ipa_bwd_core_kernel  : per CTA = (patch, 16 query rows), thread = key j = TMEM lane (as the forward core):
+//        S^T_h  = K_h Q_h^T                (recompute logits)             M=128 j, N=16 i, K=32+3*32   bf16
+//        dPv^T_h = V_h dO_h^T              (value part of dP)             M=128 j, N=16 i, K=64        fp16
+//        per query row i, on the TMA-staged pair row e[i] (read from HBM once):
+//          dPp_i = e[i] dopair_i^T         (pair part of dP)              M=128 j, N=16(8 h), K=64 c
+//          de_i  = [P_i | dl_i] [dopair_i ; st Wpb]                       M=128 j, N=64 c, K=16        -> HBM (bf16)
+//          Z    += e[i]^T dl_i             (to_pair_bias gradient)        M=64 c,  N=8 h,  K=128 j
+//        dQ^T_h = K_h[:, :64]^T dl_h       (scalar + point-hi columns)    M=64,    N=16 i, K=128 j
+//      P and dl also go to HBM as bf16 [b][h][i][j] for the key side.
+//   3. ipa_bwd_keyside_kernel: per (patch, head): dV_h = P_h^T dO_h, dK_h = dl_h^T Q_h[:, :64]   M=128 j, N=64, K=128 i
+//   4. bwd_assemble_kernel  : scales, the -c q~ sum dl corrections, global -> local frame -> dproj rows
+//   5. bwd_finalize_kernel  : reduces the per-CTA partials into dWpb and dgamma
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "ipa_sm100_layout.cuh"
+#include "sm100_prims.cuh"
+
+namespace dab {
+namespace sm100 {
+
+constexpr float kLn2 = 0.6931471805599453f;
+
+// ---- backward workspace ---------------------------------------------------------------------------------
+struct BwdWs {
+  __half* dO16;             // [rows][8][64] fp16, scaled by 2^k(row): [dos 32 | dog 24 | 0 x 8]
+  __nv_bfloat16* dObf;      // same, unscaled bf16 (key side)
+  __nv_bfloat16* dopair;    // [rows][8][64] bf16
+  float* delta;             // [rows][8]
+  float* rscale;            // [rows] 1 / 2^k(row)
+  __nv_bfloat16 *Pn, *dL;   // [B][8][128 i][128 j] bf16
+  float *dQ, *dK, *dV;      // [rows][8][64] fp32
+  float *p_wpb, *p_g1, *p_g2;   // partials: [B*8][512], [B*8][8], [rows/32][8]
+  size_t bytes;
+};
+inline BwdWs carve_bwd(int B, void* base) {
+  auto al = [](size_t n) { return (n + 1023) / 1024 * 1024; };
+  const size_t rows = (size_t)B * L;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  BwdWs w;
+  w.dO16 = reinterpret_cast<__half*>(p); p += al(rows * H * 64 * 2);
+  w.dObf = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * H * 64 * 2);
+  w.dopair = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * H * 64 * 2);
+  w.delta = reinterpret_cast<float*>(p); p += al(rows * H * 4);
+  w.rscale = reinterpret_cast<float*>(p); p += al(rows * 4);
+  w.Pn = reinterpret_cast<__nv_bfloat16*>(p); p += al((size_t)B * H * L * L * 2);
+  w.dL = reinterpret_cast<__nv_bfloat16*>(p); p += al((size_t)B * H * L * L * 2);
+  w.dQ = reinterpret_cast<float*>(p); p += al(rows * H * 64 * 4);
+  w.dK = reinterpret_cast<float*>(p); p += al(rows * H * 64 * 4);
+  w.dV = reinterpret_cast<float*>(p); p += al(rows * H * 64 * 4);
+  w.p_wpb = reinterpret_cast<float*>(p); p += al((size_t)B * 8 * 512 * 4);
+  w.p_g1 = reinterpret_cast<float*>(p); p += al((size_t)B * 8 * 8 * 4);
+  w.p_g2 = reinterpret_cast<float*>(p); p += al((rows / 32) * 8 * 4);
+  w.bytes = (size_t)(p - reinterpret_cast<uint8_t*>(base));
+  return w;
+}
+
+// ---- 1. prep ----------------------------------------------------------------------------------------------
+// One block per residue row, warp = head.  cat row layout (diffab_pytorch.py:456-462):
+// [scalar (h d) 256 | pair (h c) 512 | local points (h p c) 192 | norms (h p) 64].
+__global__ void __launch_bounds__(256) bwd_prep_kernel(const float* __restrict__ dcat, const __nv_bfloat16* __restrict__ cat,
+                                                       const float* __restrict__ R, const float* __restrict__ tc,
+                                                       __half* __restrict__ dO16, __nv_bfloat16* __restrict__ dObf,
+                                                       __nv_bfloat16* __restrict__ dopair, float* __restrict__ delta,
+                                                       float* __restrict__ rscale) {
+  __shared__ float s_max[8];
+  const int64_t row = blockIdx.x;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* dc = dcat + row * NCAT;
+  const __nv_bfloat16* ct = cat + row * NCAT;
+  const float dos = dc[h * DS + lane];
+  const float os = __bfloat162float(ct[h * DS + lane]);
+  const float dp0 = dc[NS + h * C + lane], dp1 = dc[NS + h * C + 32 + lane];
+  const float op0 = __bfloat162float(ct[NS + h * C + lane]), op1 = __bfloat162float(ct[NS + h * C + 32 + lane]);
+  float acc = dos * os + dp0 * op0 + dp1 * op1;
+  float dog[3] = {0.f, 0.f, 0.f};
+  if (lane < P) {
+    // ol = (og - t) R^T, nrm = |ol| (diffab_pytorch.py:327-336,453-457)  ->  d_ol += dnrm ol / nrm; dog = d_ol R
+    const int o = NS + H * C + h * (P * 3) + lane * 3;
+    float ol[3], dl[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { ol[c] = __bfloat162float(ct[o + c]); dl[c] = dc[o + c]; }
+    const float dn = dc[NS + H * C + NPT + h * P + lane];
+    const float nrm = sqrtf(ol[0] * ol[0] + ol[1] * ol[1] + ol[2] * ol[2]);
+    if (nrm > 0.f) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dl[c] += dn * ol[c] / nrm;
+    }
+    const float* Rr = R + row * 9;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dog[k] = dl[0] * Rr[k] + dl[1] * Rr[3 + k] + dl[2] * Rr[6 + k];
+    // <dog, og> with og = ol R + t:  (d_ol R).(ol R) = d_ol . ol  (R orthogonal)
+    acc += dl[0] * ol[0] + dl[1] * ol[1] + dl[2] * ol[2] + dog[0] * tc[row * 3] + dog[1] * tc[row * 3 + 1] +
+           dog[2] * tc[row * 3 + 2];
+  }
+  acc = warp_sum(acc);
+  float mx = fmaxf(fabsf(dos), fmaxf(fabsf(dog[0]), fmaxf(fabsf(dog[1]), fabsf(dog[2]))));
+  mx = warp_max(mx);
+  if (lane == 0) { s_max[h] = mx; delta[row * H + h] = acc; }
+  __syncthreads();
+  float m = s_max[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) m = fmaxf(m, s_max[k]);
+  // power-of-two scale that puts the largest entry of the row in [2^11, 2^12): fp16 keeps >= 11 bits for
+  // everything within 2^-25 of it, whatever the magnitude of the upstream gradient
+  float s = 1.0f;
+  if (m > 0.f && m < 3.0e38f) {
+    int ex;
+    frexpf(m, &ex);
+    s = ldexpf(1.0f, max(-100, min(100, 12 - ex)));
+  }
+  if (threadIdx.x == 0) rscale[row] = 1.0f / s;
+  const int64_t base = (row * H + h) * 64;
+  dO16[base + lane] = __float2half_rn(dos * s);
+  dObf[base + lane] = __float2bfloat16_rn(dos);
+  if (lane < P) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      dO16[base + 32 + lane * 3 + k] = __float2half_rn(dog[k] * s);
+      dObf[base + 32 + lane * 3 + k] = __float2bfloat16_rn(dog[k]);
+    }
+  } else if (lane < 16) {
+    dO16[base + 48 + lane] = __float2half_rn(0.f);
+    dObf[base + 48 + lane] = __float2bfloat16_rn(0.f);
+  }
+  dopair[base + lane] = __float2bfloat16_rn(dp0);
+  dopair[base + 32 + lane] = __float2bfloat16_rn(dp1);
+}
+
+// ---- 2. query-side core ---------------------------------------------------------------------------------------
+struct BwdSmem {
+  // region X: stage 1 = K ring (3 heads) + V ring (3 heads); stage 2 = ring of seven pair rows; stage 3 = K ring again
+  static constexpr int kKBuf = 3 * L * 64;           // 24,576: one head, three [128 x 64 B] blocks
+  static constexpr int kKBufs = 3;
+  static constexpr int kVOff = kKBufs * kKBuf;       // 73,728
+  static constexpr int kVBuf = L * V_W * 2;          // 16,384
+  static constexpr int kVBufs = 3;
+  static constexpr int kEStage = L * C * 2;          // 16,384
+  static constexpr int kEStages = 7;
+  static constexpr int kK2Buf = 2 * L * 64;          // 16,384: scalar + point-hi blocks of one head
+  static constexpr int kK2Bufs = 3;
+  static constexpr int kXBytes = kVOff + kVBufs * kVBuf;   // 122,880
+  // region Y: stage 1 = Q rows + dO rows of this CTA; stage 2/3 = dl_h (B operand of dQ^T) + ring of dopair rows
+  static constexpr int kY = kXBytes;
+  static constexpr int kQOff = kY;                   // 24,576
+  static constexpr int kDoOff = kY + 24576;          // [h][16 i][128 B] fp16, 16,384
+  static constexpr int kDlh = kY;                    // [h][kb(2)][16 i][128 B] bf16, 32,768
+  static constexpr int kDop = kY + 32768;            // 7 x [8 h][128 B] bf16 (+ 1 KB slack read as garbage N rows)
+  static constexpr int kYBytes = 40960;
+  static constexpr int kWpb = kY + kYBytes;          // [8 h][128 B] bf16: st * Wpb
+  static constexpr int kPcat = kWpb + 1024;          // 4 x { [128 j][16 B] P | [128 j][16 B] dl } bf16
+  static constexpr int kStats = kPcat + 4 * 4096;    // [16 i][16] f32
+  static constexpr int kDelta = kStats + 1024;       // [16 i][8] f32
+  static constexpr int kRs = kDelta + 512;           // [16] f32
+  static constexpr int kRed = kRs + 64;              // [8 warps][8] f32
+  static constexpr int kBars = kRed + 256;           // 64 mbarriers
+  static constexpr int kTmemSlot = kBars + 512;
+  static constexpr int kTotal = kTmemSlot + 16;
+};
+static_assert(BwdSmem::kEStages * BwdSmem::kEStage <= BwdSmem::kXBytes, "e ring must fit region X");
+static_assert(BwdSmem::kDop + (BwdSmem::kEStages + 1) * 1024 <= BwdSmem::kY + BwdSmem::kYBytes, "dopair ring must fit region Y");
+static_assert(BwdSmem::kTotal <= 227 * 1024, "shared memory");
+
+enum BBar { BK_FULL = 0, BK_EMPTY = 3, BV_FULL = 6, BV_EMPTY = 9, BQ_FULL = 12, BS_DONE = 13, BE_FULL = 14, BE_EMPTY = 21,
+            DPP_DONE = 28, DPP_FREE = 32 /* 128 arrivals */, PCAT_READY = 36 /* [g][slot], 128 arrivals */, PCAT_FREE = 40,
+            DE_DONE = 44 /* [g] */, K2_FULL = 46, K2_EMPTY = 49, DQ_DONE = 52, B_N_BARS = 53 };
+
+constexpr uint32_t kBColS = 0, kBColDPV = 128, kBColDPP = 256 /* 4 x 16 */, kBColDE = 320 /* 2 x 64 */, kBColWPB = 448;
+
+__device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
+  return make_uint4(pack_bf162(v[0], v[1]), pack_bf162(v[2], v[3]), pack_bf162(v[4], v[5]), pack_bf162(v[6], v[7]));
+}
+
+__global__ void __launch_bounds__(320, 1)
+ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_e,
+                    const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_dop,
+                    const uint4* __restrict__ bias, const float* __restrict__ stats, const float* __restrict__ delta,
+                    const float* __restrict__ rscale, const float* __restrict__ wpb, __nv_bfloat16* __restrict__ de,
+                    __nv_bfloat16* __restrict__ Pn, __nv_bfloat16* __restrict__ dL, float* __restrict__ dQ,
+                    float* __restrict__ p_wpb, float* __restrict__ p_g1) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using S = BwdSmem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
+  float* s_stats = reinterpret_cast<float*>(smem + S::kStats);
+  float* s_delta = reinterpret_cast<float*>(smem + S::kDelta);
+  float* s_rs = reinterpret_cast<float*>(smem + S::kRs);
+  float* s_red = reinterpret_cast<float*>(smem + S::kRed);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, i0 = blockIdx.x * IB;
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+  const int64_t row0 = (int64_t)b * L + i0;
+  const uint32_t smem_base = smem_u32(smem);
+  if ((smem_base & 1023u) != 0) asm volatile("trap;");
+
+  if (tid == 0) {
+    for (int i = 0; i < B_N_BARS; ++i) {
+      const bool many = (i >= DPP_FREE && i < DPP_FREE + 4) || (i >= PCAT_READY && i < PCAT_READY + 4);
+      mbar_init(&bars[i], many ? 128u : 1u);
+    }
+    fence_barrier_init();
+  }
+  // per-row constants of this CTA and the st * Wpb operand tile ([8 h][64 c] bf16, 128B-swizzled rows)
+  if (tid < 256) s_stats[tid] = stats[row0 * 16 + tid];
+  if (tid < 128) s_delta[tid] = delta[row0 * 8 + tid];
+  if (tid < 16) s_rs[tid] = rscale[row0 + tid];
+  if (tid < 256) {
+    const float st = rsqrtf(3.0f);
+    const int hh = tid >> 5, c2 = (tid & 31) * 2;   // two consecutive channels
+    *reinterpret_cast<uint32_t*>(smem + S::kWpb + swz128_offset(hh, c2 >> 3) + (c2 & 7) * 2) =
+        pack_bf162(st * wpb[hh * C + c2], st * wpb[hh * C + c2 + 1]);
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  tcgen05_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  // issue order of the rows inside a block of four: group 0 works on rows {0,1}, group 1 on rows {2,3} at the same time
+  auto ord = [](int k) { return (k & ~3) + ((k & 1) << 1) + ((k >> 1) & 1); };
+
+  if (warp == 9) {
+    // ======================================= TMA producer =======================================
+    if (lane == 0) {
+      tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
+      tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_dop);
+      constexpr int kL2Ahead = 8;
+      auto load_k = [&](int h) {
+        const int s = h % S::kKBufs;
+        uint8_t* kb = smem + s * S::kKBuf;
+        mbar_arrive_expect_tx(&bars[BK_FULL + s], S::kKBuf);
+        for (int blk = 0; blk < 3; ++blk)
+          tma_load_2d(kb + blk * (L * 64), &map_k, &bars[BK_FULL + s], (h * 3 + blk) * 32, b * L);
+      };
+      auto load_v = [&](int h) {
+        const int s = h % S::kVBufs;
+        mbar_arrive_expect_tx(&bars[BV_FULL + s], S::kVBuf);
+        tma_load_2d(smem + S::kVOff + s * S::kVBuf, &map_v, &bars[BV_FULL + s], h * V_W, b * L);
+      };
+      load_k(0);
+      mbar_arrive_expect_tx(&bars[BQ_FULL], 24576 + 16384);
+      for (int blk = 0; blk < H * 3; ++blk)
+        tma_load_2d(smem + S::kQOff + blk * (IB * 64), &map_q, &bars[BQ_FULL], blk * 32, (int)row0);
+      for (int h = 0; h < H; ++h)
+        tma_load_2d(smem + S::kDoOff + h * 2048, &map_do, &bars[BQ_FULL], h * 64, (int)row0);
+      load_v(0);
+      load_k(1); load_v(1);
+      load_k(2); load_v(2);
+      for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
+      for (int h = 3; h < H; ++h) {
+        mbar_wait(&bars[BK_EMPTY + h % 3], ((h / 3) - 1) & 1);
+        load_k(h);
+        mbar_wait(&bars[BV_EMPTY + h % 3], ((h / 3) - 1) & 1);
+        load_v(h);
+      }
+      // ---- stage 2: pair rows + their dopair tiles
+      mbar_wait(&bars[BS_DONE], 0);
+      for (int r = 0; r < IB; ++r) {
+        const int s = r % S::kEStages;
+        if (r >= S::kEStages) mbar_wait(&bars[BE_EMPTY + s], ((r / S::kEStages) - 1) & 1);
+        mbar_arrive_expect_tx(&bars[BE_FULL + s], S::kEStage + 1024);
+        tma_load_2d(smem + s * S::kEStage, &map_e, &bars[BE_FULL + s], 0, (int)((row0 + r) * L));
+        tma_load_2d(smem + S::kDop + s * 1024, &map_dop, &bars[BE_FULL + s], 0, (int)((row0 + r) * H));
+        if (r + kL2Ahead < IB) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r + kL2Ahead) * L));
+      }
+      // ---- stage 3: scalar + point-hi blocks of K, head by head, once every pair row has been released
+      for (int s = 0; s < S::kEStages; ++s) {
+        const int uses = (IB - s + S::kEStages - 1) / S::kEStages;
+        mbar_wait(&bars[BE_EMPTY + s], (uses - 1) & 1);
+      }
+      for (int h = 0; h < H; ++h) {
+        const int s = h % S::kK2Bufs;
+        if (h >= S::kK2Bufs) mbar_wait(&bars[K2_EMPTY + s], ((h / S::kK2Bufs) - 1) & 1);
+        mbar_arrive_expect_tx(&bars[K2_FULL + s], S::kK2Buf);
+        for (int blk = 0; blk < 2; ++blk)
+          tma_load_2d(smem + s * S::kK2Buf + blk * (L * 64), &map_k, &bars[K2_FULL + s], (h * 3 + blk) * 32, b * L);
+      }
+    }
+  } else if (warp == 8) {
+    // ======================================= MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t kIdescS = make_idesc_bf16(128, 16, 0, 0);
+      constexpr uint32_t kIdescDPV = make_idesc_f16(128, 16, 0, 0);
+      constexpr uint32_t kIdescDPP = make_idesc_bf16(128, 16, 0, 0);
+      constexpr uint32_t kIdescDE = make_idesc_bf16(128, 64, 0, 1);    // B = [dopair_i ; st Wpb], MN-major
+      constexpr uint32_t kIdescZ = make_idesc_bf16(64, 8, 1, 1);       // A = e tile MN-major, B = dl chunk MN-major
+      constexpr uint32_t kIdescDQ = make_idesc_bf16(64, 16, 1, 0);     // A = K blocks MN-major
+      // ---- stage 1
+      mbar_wait(&bars[BQ_FULL], 0);
+      for (int h = 0; h < H; ++h) {
+        const int s = h % 3;
+        mbar_wait(&bars[BK_FULL + s], (h / 3) & 1);
+        tcgen05_fence_after_sync();
+        const uint32_t ka = smem_base + s * S::kKBuf;
+        const uint32_t qa = smem_base + S::kQOff + h * 3 * (IB * 64);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int ablk = (m == 0) ? 0 : (m == 3 ? 2 : 1), bblk = (m == 0) ? 0 : (m == 2 ? 2 : 1);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            uint64_t da = make_smem_desc(ka + ablk * (L * 64) + k * 32, 16, 512, kSwizzle64B);
+            uint64_t db = make_smem_desc(qa + bblk * (IB * 64) + k * 32, 16, 512, kSwizzle64B);
+            umma_bf16(tmem + kBColS + h * 16, da, db, kIdescS, (m | k) != 0);
+          }
+        }
+        umma_commit(&bars[BK_EMPTY + s]);
+        mbar_wait(&bars[BV_FULL + s], (h / 3) & 1);
+        tcgen05_fence_after_sync();
+        const uint32_t va = smem_base + S::kVOff + s * S::kVBuf;
+        const uint32_t oa = smem_base + S::kDoOff + h * 2048;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint64_t da = make_smem_desc(va + k * 32, 16, 1024, kSwizzle128B);
+          uint64_t db = make_smem_desc(oa + k * 32, 16, 1024, kSwizzle128B);
+          umma_bf16(tmem + kBColDPV + h * 16, da, db, kIdescDPV, k != 0);
+        }
+        umma_commit(&bars[BV_EMPTY + s]);
+      }
+      umma_commit(&bars[BS_DONE]);
+      // ---- stage 2
+      auto issue_dpp = [&](int r) {
+        const int s = r % S::kEStages;
+        mbar_wait(&bars[BE_FULL + s], (r / S::kEStages) & 1);
+        if (r >= 4) mbar_wait(&bars[DPP_FREE + (r & 3)], ((r >> 2) - 1) & 1);
+        tcgen05_fence_after_sync();
+        const uint32_t ea = smem_base + s * S::kEStage, da0 = smem_base + S::kDop + s * 1024;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint64_t da = make_smem_desc(ea + k * 32, 16, 1024, kSwizzle128B);
+          uint64_t db = make_smem_desc(da0 + k * 32, 16, 1024, kSwizzle128B);
+          umma_bf16(tmem + kBColDPP + (r & 3) * 16, da, db, kIdescDPP, k != 0);
+        }
+        umma_commit(&bars[DPP_DONE + (r & 3)]);
+      };
+      for (int k = 0; k < 4; ++k) issue_dpp(ord(k));
+      for (int k = 0; k < IB; ++k) {
+        const int r = ord(k);
+        const int g = (r >> 1) & 1, n = 2 * (r >> 2) + (r & 1), slot = n & 1;
+        const int s = r % S::kEStages;
+        mbar_wait(&bars[PCAT_READY + g * 2 + slot], (n >> 1) & 1);
+        tcgen05_fence_after_sync();
+        const uint32_t pc = smem_base + S::kPcat + (g * 2 + slot) * 4096;
+        const uint32_t dop = smem_base + S::kDop + s * 1024;
+        {
+          // A: [128 j][16] K-major, no swizzle: core matrices of 8 rows x 16 B; K chunks 2048 B apart (LBO),
+          //    8-row groups 128 B apart (SBO).  B: [16 k][64 c] MN-major 128B-swizzled, two 8-row atoms:
+          //    dopair_i, then st Wpb (SBO = distance between the two tiles).
+          uint64_t da = make_smem_desc(pc, 2048, 128, kSwizzleNone);
+          uint64_t db = make_smem_desc(dop, 1024, (smem_base + S::kWpb) - dop, kSwizzle128B);
+          umma_bf16(tmem + kBColDE + g * 64, da, db, kIdescDE, false);
+        }
+        umma_commit(&bars[DE_DONE + g]);
+        const uint32_t ea = smem_base + s * S::kEStage;
+#pragma unroll
+        for (int kk = 0; kk < L / 16; ++kk) {
+          // A: e[i] tile read MN-major (M = c).  B: dl chunk [128 j][8 h] MN-major, no swizzle: 8-row (K) groups
+          //    128 B apart (LBO)
+          uint64_t da = make_smem_desc(ea + kk * 2048, 1024, 1024, kSwizzle128B);
+          uint64_t db = make_smem_desc(pc + 2048 + kk * 256, 128, 2048, kSwizzleNone);
+          umma_bf16(tmem + kBColWPB, da, db, kIdescZ, (k | kk) != 0);
+        }
+        umma_commit(&bars[BE_EMPTY + s]);
+        umma_commit(&bars[PCAT_FREE + g * 2 + slot]);
+        if (k + 4 < IB) issue_dpp(ord(k + 4));
+      }
+      // ---- stage 3: dQ^T_h = K_h[:, :64]^T dl_h
+      for (int h = 0; h < H; ++h) {
+        const int s = h % S::kK2Bufs;
+        mbar_wait(&bars[K2_FULL + s], (h / S::kK2Bufs) & 1);
+        tcgen05_fence_after_sync();
+        const uint32_t ka = smem_base + s * S::kK2Buf, pa = smem_base + S::kDlh + h * (2 * IB * 128);
+#pragma unroll
+        for (int k = 0; k < L / 16; ++k) {
+          // A: two [128 j][64 B] 64B-swizzled blocks read MN-major: M = 64 = two 32-wide atoms 8192 B apart (LBO),
+          //    8-row (K) groups 512 B apart (SBO)
+          uint64_t da = make_smem_desc(ka + k * 1024, L * 64, 512, kSwizzle64B);
+          uint64_t db = make_smem_desc(pa + (k >> 2) * (IB * 128) + (k & 3) * 32, 16, 1024, kSwizzle128B);
+          umma_bf16(tmem + kBColS + h * 16, da, db, kIdescDQ, k != 0);
+        }
+        umma_commit(&bars[K2_EMPTY + s]);
+      }
+      umma_commit(&bars[DQ_DONE]);
+    }
+  } else {
+    // ======================================= softmax-gradient groups =======================================
+    const int g = warp >> 2, gw = warp & 3, gt = tid & 127;
+    const uint32_t tmem_lane = tmem + ((uint32_t)(gw * 32) << 16);
+    auto bar_all_compute = [] { asm volatile("bar.sync 3, 256;" ::: "memory"); };
+    float accg[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) accg[h] = 0.f;
+
+    // de of the group's row with local index np: TMEM -> bf16 -> 128 contiguous bytes per key
+    auto drain_de = [&](int np) {
+      const int ip = 4 * (np >> 1) + 2 * g + (np & 1);
+      mbar_wait(&bars[DE_DONE + g], np & 1);
+      tcgen05_fence_after_sync();
+      uint4* dst = reinterpret_cast<uint4*>(de + ((row0 + ip) * L + gt) * C);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tmem_ld_x32(tmem_lane + kBColDE + g * 64 + half * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          dst[half * 4 + q] = make_uint4(pack_bf162(v[8 * q], v[8 * q + 1]), pack_bf162(v[8 * q + 2], v[8 * q + 3]),
+                                         pack_bf162(v[8 * q + 4], v[8 * q + 5]), pack_bf162(v[8 * q + 6], v[8 * q + 7]));
+      }
+      tcgen05_fence_before_sync();
+    };
+
+    const uint4* bias_t = bias + (row0 + 2 * g) * L + gt;     // row 4q + 2g + rr  ->  + (4q + rr) * L
+    uint4 b_nxt[2] = {__ldg(bias_t), __ldg(bias_t + L)};
+    mbar_wait(&bars[BS_DONE], 0);
+    tcgen05_fence_after_sync();
+    for (int q = 0; q < IB / 4; ++q) {
+      const uint4 b_use[2] = {b_nxt[0], b_nxt[1]};
+      if (q + 1 < IB / 4) {
+        b_nxt[0] = __ldg(bias_t + (size_t)(4 * (q + 1)) * L);
+        b_nxt[1] = __ldg(bias_t + (size_t)(4 * (q + 1) + 1) * L);
+      }
+      float sreg[H][2], dpv[H][2];
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        tmem_ld_x2(tmem_lane + kBColS + h * 16 + 4 * q + 2 * g, sreg[h]);
+        tmem_ld_x2(tmem_lane + kBColDPV + h * 16 + 4 * q + 2 * g, dpv[h]);
+      }
+      tmem_wait_ld();
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int i = 4 * q + 2 * g + rr, n = 2 * q + rr;
+        float lm[H], p[H], dl[H];
+        {
+          const __half2* hb = reinterpret_cast<const __half2*>(&b_use[rr]);
+          const float4* st4 = reinterpret_cast<const float4*>(s_stats + i * 16);
+          const float4 m0 = st4[0], m1 = st4[1], v0 = st4[2], v1 = st4[3];
+          const float m2[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          const float inv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(hb[k]);
+            lm[2 * k] = f.x; lm[2 * k + 1] = f.y;
+          }
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            lm[h] = lm[h] + sreg[h][rr] - m2[h];       // log2 of the un-normalised probability (<= 0)
+            p[h] = ex2(lm[h]) * inv[h];
+          }
+        }
+        // pair part of dP for this row
+        mbar_wait(&bars[DPP_DONE + (i & 3)], (i >> 2) & 1);
+        tcgen05_fence_after_sync();
+        float dpp[8];
+        tmem_ld_x8(tmem_lane + kBColDPP + (i & 3) * 16, dpp);
+        tmem_wait_ld();
+        tcgen05_fence_before_sync();
+        mbar_arrive(&bars[DPP_FREE + (i & 3)]);
+        {
+          const float rs = s_rs[i];
+          const float4 d0 = *reinterpret_cast<const float4*>(s_delta + i * 8), d1 = *reinterpret_cast<const float4*>(s_delta + i * 8 + 4);
+          const float dlt[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            const float dP = fmaf(dpv[h][rr], rs, dpp[h]);
+            dl[h] = p[h] * (dP - dlt[h]);
+            accg[h] = fmaf(dl[h], lm[h], accg[h]);
+          }
+        }
+        if (n >= 1) drain_de(n - 1);
+        if (n >= 2) mbar_wait(&bars[PCAT_FREE + g * 2 + (n & 1)], ((n >> 1) - 1) & 1);
+        // ---- [P | dl] of this key: A operand of the de MMA, and (dl half) B operand of the Z MMA
+        {
+          uint8_t* pc = smem + S::kPcat + (g * 2 + (n & 1)) * 4096;
+          *reinterpret_cast<uint4*>(pc + gt * 16) = pack8_bf16(p);
+          *reinterpret_cast<uint4*>(pc + 2048 + gt * 16) = pack8_bf16(dl);
+        }
+        // ---- P and dl as [h][i][j] rows: shared memory (B operand of dQ^T) and HBM (key side); neighbouring lanes
+        //      trade heads so that every store is a packed pair (j, j+1)
+        {
+          const int je = gt & ~1;
+          const uint32_t kb = je >> 6, chunk = (je & 63) >> 3, e2 = (je & 7) * 2;
+          uint8_t* dlh = smem + S::kDlh + kb * (IB * 128);
+          const bool odd = lane & 1;
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh) {
+            const int h = 2 * hh + (odd ? 1 : 0);
+            const float ps = odd ? p[2 * hh] : p[2 * hh + 1];
+            const float pr = __shfl_xor_sync(0xffffffffu, ps, 1);
+            const float ds = odd ? dl[2 * hh] : dl[2 * hh + 1];
+            const float dr = __shfl_xor_sync(0xffffffffu, ds, 1);
+            const uint32_t pv = odd ? pack_bf162(pr, p[2 * hh + 1]) : pack_bf162(p[2 * hh], pr);
+            const uint32_t dv = odd ? pack_bf162(dr, dl[2 * hh + 1]) : pack_bf162(dl[2 * hh], dr);
+            const size_t go = (((size_t)b * H + h) * L + (i0 + i)) * L + je;
+            *reinterpret_cast<uint32_t*>(Pn + go) = pv;
+            *reinterpret_cast<uint32_t*>(dL + go) = dv;
+            *reinterpret_cast<uint32_t*>(dlh + h * (2 * IB * 128) + swz128_offset(i, chunk) + e2) = dv;
+          }
+        }
+        fence_proxy_async_smem();
+        tcgen05_fence_before_sync();
+        mbar_arrive(&bars[PCAT_READY + g * 2 + (n & 1)]);
+      }
+    }
+    drain_de(IB / 2 - 1);
+
+    // ---- sum_ij dl (l - m) per head (natural-log units) for dgamma
+#pragma unroll
+    for (int h = 0; h < H; ++h) accg[h] = warp_sum(accg[h]);
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) s_red[warp * 8 + h] = accg[h];
+    }
+    bar_all_compute();
+    if (tid < 8) {
+      float s = 0.f;
+      for (int w = 0; w < 8; ++w) s += s_red[w * 8 + tid];
+      p_g1[(size_t)cta * 8 + tid] = s * kLn2;
+    }
+    // ---- dQ^T (M = 64: packed column m = 16 gw + lane in lanes 0-15) and the to_pair_bias partial
+    mbar_wait(&bars[DQ_DONE], 0);
+    tcgen05_fence_after_sync();
+#pragma unroll
+    for (int hh = 0; hh < H / 2; ++hh) {
+      const int h = g * (H / 2) + hh;
+      float o[16];
+      tmem_ld_x16(tmem_lane + kBColS + h * 16, o);
+      tmem_wait_ld();
+      if (lane < 16) {
+        float* dst = dQ + ((row0 * H + h) * 64) + gw * 16 + lane;
+#pragma unroll
+        for (int i = 0; i < IB; ++i) dst[(size_t)i * H * 64] = o[i];
+      }
+    }
+    if (g == 0) {
+      float z[8];
+      tmem_ld_x8(tmem_lane + kBColWPB, z);
+      tmem_wait_ld();
+      if (lane < 16) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) p_wpb[(size_t)cta * 512 + h * C + gw * 16 + lane] = z[h];
+      }
+    }
+  }
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_free(tmem, 512);
+}
+
+// ---- 3. key side -------------------------------------------------------------------------------------------
+struct KsSmem {
+  static constexpr int kPn = 0;          // two [128 i][64 j] boxes, 128B-swizzled
+  static constexpr int kDl = 32768;
+  static constexpr int kDo = 65536;      // [128 i][64 d]
+  static constexpr int kQ = 81920;       // [128 i][64: scalar | point hi]
+  static constexpr int kBars = 98304;
+  static constexpr int kTmemSlot = kBars + 64;
+  static constexpr int kTotal = kTmemSlot + 16;
+};
+
+__global__ void __launch_bounds__(160, 2)
+ipa_bwd_keyside_kernel(const __grid_constant__ CUtensorMap map_pn, const __grid_constant__ CUtensorMap map_dl,
+                       const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_q64,
+                       float* __restrict__ dK, float* __restrict__ dV) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using S = KsSmem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const uint32_t smem_base = smem_u32(smem);
+  if ((smem_base & 1023u) != 0) asm volatile("trap;");
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  tcgen05_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars[0], 98304);
+      const int prow = (b * H + h) * L;
+      tma_load_2d(smem + S::kPn, &map_pn, &bars[0], 0, prow);
+      tma_load_2d(smem + S::kPn + 16384, &map_pn, &bars[0], 64, prow);
+      tma_load_2d(smem + S::kDl, &map_dl, &bars[0], 0, prow);
+      tma_load_2d(smem + S::kDl + 16384, &map_dl, &bars[0], 64, prow);
+      tma_load_2d(smem + S::kDo, &map_do, &bars[0], h * 64, b * L);
+      tma_load_2d(smem + S::kQ, &map_q64, &bars[0], h * QK_W, b * L);
+      mbar_wait(&bars[0], 0);
+      tcgen05_fence_after_sync();
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+#pragma unroll
+      for (int k = 0; k < L / 16; ++k) {
+        // A: [i][j] tile read MN-major (M = j): two 64-wide atoms 16 KB apart (LBO), 8-row (K = i) groups 1 KB apart
+        uint64_t da = make_smem_desc(smem_base + S::kPn + k * 2048, 16384, 1024, kSwizzle128B);
+        uint64_t db = make_smem_desc(smem_base + S::kDo + k * 2048, 1024, 1024, kSwizzle128B);
+        umma_bf16(tmem, da, db, idesc, k != 0);
+      }
+#pragma unroll
+      for (int k = 0; k < L / 16; ++k) {
+        uint64_t da = make_smem_desc(smem_base + S::kDl + k * 2048, 16384, 1024, kSwizzle128B);
+        uint64_t db = make_smem_desc(smem_base + S::kQ + k * 2048, 1024, 1024, kSwizzle128B);
+        umma_bf16(tmem + 64, da, db, idesc, k != 0);
+      }
+      umma_commit(&bars[1]);
+    }
+  } else {
+    mbar_wait(&bars[1], 0);
+    tcgen05_fence_after_sync();
+    const uint32_t tmem_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    const size_t o = (((size_t)b * L + tid) * H + h) * 64;
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+      float v[32];
+      tmem_ld_x32(tmem_lane + part * 32, v);
+      tmem_wait_ld();
+      float4* dst = reinterpret_cast<float4*>((part < 2 ? dV : dK) + o + (part & 1) * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+  }
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_free(tmem, 128);
+}
+
+// ---- 4. assemble dproj ---------------------------------------------------------------------------------------
+// thread = (residue row, head); block = 32 rows.  dproj row layout = rows of Wcat:
+// [q_s 256 | k_s 256 | v_s 256 | q_p 192 | k_p 192 | v_p 192], (h d) / (h p c) inside each segment.
+__global__ void __launch_bounds__(256) bwd_assemble_kernel(const float* __restrict__ dQ, const float* __restrict__ dK,
+                                                           const float* __restrict__ dV, const __nv_bfloat16* __restrict__ Qp,
+                                                           const __nv_bfloat16* __restrict__ Kp, const float* __restrict__ R,
+                                                           const float* __restrict__ gamma, float* __restrict__ dproj,
+                                                           float* __restrict__ p_g2) {
+  __shared__ float s_g2[8][8];
+  const int64_t row = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
+  const int h = threadIdx.x & 7;
+  const float ss = rsqrtf((float)DS), sp = rsqrtf(4.5f * P), st = rsqrtf(3.0f);
+  const float c1 = st * sp * gamma[h];
+  const size_t o = (row * H + h) * 64;
+  float U[64], Rm[9];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) Rm[c] = R[row * 9 + c];
+  float* out = dproj + row * NPROJ;
+  auto load64 = [&](const float* src) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(src + o + 4 * q);
+      U[4 * q] = v.x; U[4 * q + 1] = v.y; U[4 * q + 2] = v.z; U[4 * q + 3] = v.w;
+    }
+  };
+  auto store_scalars = [&](int seg, float scale) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<float4*>(out + seg * NS + h * DS + 4 * q) =
+          make_float4(U[4 * q] * scale, U[4 * q + 1] * scale, U[4 * q + 2] * scale, U[4 * q + 3] * scale);
+  };
+  // global-frame gradient g[24] -> local frame (p_glob = p_loc R + t  =>  dp_loc = dp_glob R^T) -> dproj
+  auto store_points = [&](int seg, const float (&gp)[24]) {
+    float loc[24];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const float x = gp[3 * p], y = gp[3 * p + 1], z = gp[3 * p + 2];
+      loc[3 * p] = x * Rm[0] + y * Rm[1] + z * Rm[2];
+      loc[3 * p + 1] = x * Rm[3] + y * Rm[4] + z * Rm[5];
+      loc[3 * p + 2] = x * Rm[6] + y * Rm[7] + z * Rm[8];
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+      *reinterpret_cast<float4*>(out + 3 * NS + seg * NPT + h * 24 + 4 * q) =
+          make_float4(loc[4 * q], loc[4 * q + 1], loc[4 * q + 2], loc[4 * q + 3]);
+  };
+  auto load_points = [&](const __nv_bfloat16* src, float (&pt)[24]) {   // hi + lo of the packed row
+    const __nv_bfloat16* r = src + row * (H * QK_W) + h * QK_W;
+#pragma unroll
+    for (int c = 0; c < 24; ++c) pt[c] = __bfloat162float(r[32 + c]) + __bfloat162float(r[64 + c]);
+  };
+  float gp[24], pt[24];
+  // ---- query side: U = sum_j dl [ks | k~hi | norm columns | 1]
+  load64(dQ);
+  float g2 = 0.f;
+  {
+    const __nv_bfloat16* qr = Qp + row * (H * QK_W) + h * QK_W;
+#pragma unroll
+    for (int d = 0; d < DS; ++d) g2 = fmaf(__bfloat162float(qr[d]), U[d], g2);   // Qp_s = st ss log2e qs
+    g2 *= kLn2;
+  }
+  store_scalars(0, st * ss);
+  load_points(Qp, pt);                       // = c_h log2e q~
+  {
+    const float si = U[59];
+#pragma unroll
+    for (int c = 0; c < 24; ++c) gp[c] = c1 * U[32 + c] - pt[c] * kLn2 * si;
+  }
+  store_points(0, gp);
+  // ---- key side: W = sum_i dl [st ss log2e qs | c_h log2e q~hi | 1 1 1 | 0]
+  load64(dK);
+  store_scalars(1, kLn2);
+  load_points(Kp, pt);                       // = k~
+  {
+    const float rj = U[56];
+#pragma unroll
+    for (int c = 0; c < 24; ++c) gp[c] = U[32 + c] * kLn2 - c1 * pt[c] * rj;
+  }
+  store_points(1, gp);
+  // ---- values
+  load64(dV);
+  store_scalars(2, 1.0f);
+#pragma unroll
+  for (int c = 0; c < 24; ++c) gp[c] = U[32 + c];
+  store_points(2, gp);
+  // ---- sum_i <qs, dqs> per head (lanes with equal h: xor 8, 16; then across the 8 warps)
+  g2 += __shfl_xor_sync(0xffffffffu, g2, 8);
+  g2 += __shfl_xor_sync(0xffffffffu, g2, 16);
+  if ((threadIdx.x & 31) < 8) s_g2[threadIdx.x >> 5][h] = g2;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += s_g2[w][threadIdx.x];
+    p_g2[(size_t)blockIdx.x * 8 + threadIdx.x] = s;
+  }
+}
+
+// ---- 5. finalize -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) bwd_finalize_kernel(const float* __restrict__ p_wpb, int n_cta,
+                                                           const float* __restrict__ p_g1, const float* __restrict__ p_g2,
+                                                           int n_blk, const float* __restrict__ wpb,
+                                                           const float* __restrict__ gamma, float* __restrict__ d_wpb,
+                                                           float* __restrict__ d_gamma) {
+  __shared__ float s_g3[512];
+  const int t = threadIdx.x;   // = h * 64 + c
+  const float st = rsqrtf(3.0f);
+  float z = 0.f;
+  for (int k = 0; k < n_cta; ++k) z += p_wpb[(size_t)k * 512 + t];
+  d_wpb[t] += st * z;
+  s_g3[t] = st * wpb[t] * z;
+  __syncthreads();
+  if (t < 8) {
+    float g3 = 0.f;
+    for (int c = 0; c < C; ++c) g3 += s_g3[t * C + c];
+    float g1 = 0.f, g2 = 0.f;
+    for (int k = 0; k < n_cta; ++k) g1 += p_g1[(size_t)k * 8 + t];
+    for (int k = 0; k < n_blk; ++k) g2 += p_g2[(size_t)k * 8 + t];
+    const float gm = gamma[t];
+    // lp = gamma * (dlp/dgamma)  =>  dgamma = sum dl lp / gamma (0 when gamma == 0: the point term is then absent)
+    if (gm != 0.f) d_gamma[t] += (g1 - g2 - g3) / gm;
+  }
+}
+
+}  // namespace sm100
+}  // namespace dab
+
+using namespace dab;
+using namespace dab::sm100;
+
+extern "C" {
+
+size_t dab_ipa_bwd_sm100_workspace_bytes(const DabIpaDims* d) { return shape_ok(d) ? carve_bwd(d->B, nullptr).bytes : 0; }
+
+int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf16, const float* R, const float* dcat,
+                      void* saved, size_t saved_bytes, float* dproj, void* de_bf16, float* d_w_pair_bias, float* d_gamma,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
+              "dab_ipa_bwd_sm100: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
+  if (d->B == 0) return DAB_OK;
+  DAB_REQUIRE(packed && e_bf16 && R && dcat && saved && dproj && de_bf16 && d_w_pair_bias && d_gamma && workspace,
+              DAB_EINVAL, "dab_ipa_bwd_sm100: null pointer");
+  DAB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0 && (reinterpret_cast<uintptr_t>(saved) & 1023) == 0 &&
+                  (reinterpret_cast<uintptr_t>(e_bf16) & 127) == 0 && (reinterpret_cast<uintptr_t>(de_bf16) & 127) == 0 &&
+                  aligned16(dcat) && aligned16(dproj),
+              DAB_EINVAL, "dab_ipa_bwd_sm100: misaligned pointer (workspaces 1024 B, e/de 128 B, dcat/dproj 16 B)");
+  const int B = d->B, M = B * L;
+  Ws ws = carve_ws(B, saved);
+  BwdWs bw = carve_bwd(B, workspace);
+  DAB_REQUIRE(saved_bytes >= ws.bytes, DAB_EWORKSPACE, "dab_ipa_bwd_sm100: saved workspace %zu < %zu", saved_bytes, ws.bytes);
+  DAB_REQUIRE(workspace_bytes >= bw.bytes, DAB_EWORKSPACE, "dab_ipa_bwd_sm100: workspace %zu < %zu", workspace_bytes, bw.bytes);
+  const PackedOffsets po = packed_offsets();
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
+  const float* wpb = reinterpret_cast<const float*>(pk + po.wpb);
+  const float* gamma = reinterpret_cast<const float*>(pk + po.gamma);
+  cudaStream_t s = (cudaStream_t)stream;
+
+  bwd_prep_kernel<<<M, 256, 0, s>>>(dcat, ws.cat, R, ws.tc, bw.dO16, bw.dObf, bw.dopair, bw.delta, bw.rscale);
+  count_launch();
+
+  CUtensorMap mq, mk, mv, me, mdo, mdop;
+  {
+    uint64_t dqk[2] = {(uint64_t)H * QK_W, (uint64_t)M}, sqk[1] = {(uint64_t)H * QK_W * 2};
+    uint32_t bq[2] = {32, IB}, bk[2] = {32, L};
+    if (int rc = make_tensor_map_bf16(&mq, ws.Qp, 2, dqk, sqk, bq, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    if (int rc = make_tensor_map_bf16(&mk, ws.Kp, 2, dqk, sqk, bk, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    uint64_t dv[2] = {(uint64_t)H * V_W, (uint64_t)M}, sv[1] = {(uint64_t)H * V_W * 2};
+    uint32_t bv[2] = {V_W, L}, bdo[2] = {64, IB};
+    if (int rc = make_tensor_map_bf16(&mv, ws.Vp, 2, dv, sv, bv, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_tensor_map_bf16(&mdo, bw.dO16, 2, dv, sv, bdo, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    uint64_t de_[2] = {(uint64_t)C, (uint64_t)M * L}, se[1] = {(uint64_t)C * 2};
+    uint32_t be[2] = {C, L};
+    if (int rc = make_tensor_map_bf16(&me, e_bf16, 2, de_, se, be, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    uint64_t ddp[2] = {64, (uint64_t)M * H}, sdp[1] = {128};
+    uint32_t bdp[2] = {64, H};
+    if (int rc = make_tensor_map_bf16(&mdop, bw.dopair, 2, ddp, sdp, bdp, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(ipa_bwd_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal);
+    cudaFuncSetAttribute(ipa_bwd_keyside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KsSmem::kTotal);
+    attr_done = true;
+  }
+  ipa_bwd_core_kernel<<<dim3(L / IB, B), 320, BwdSmem::kTotal, s>>>(
+      mq, mk, mv, me, mdo, mdop, ws.bias, ws.stats, bw.delta, bw.rscale, wpb, reinterpret_cast<__nv_bfloat16*>(de_bf16),
+      bw.Pn, bw.dL, bw.dQ, bw.p_wpb, bw.p_g1);
+  count_launch();
+
+  CUtensorMap mpn, mdl, mdob, mq64;
+  {
+    uint64_t dp[2] = {(uint64_t)L, (uint64_t)B * H * L}, sp_[1] = {(uint64_t)L * 2};
+    uint32_t bp[2] = {64, L};
+    if (int rc = make_tensor_map_bf16(&mpn, bw.Pn, 2, dp, sp_, bp, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_tensor_map_bf16(&mdl, bw.dL, 2, dp, sp_, bp, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    uint64_t dv[2] = {(uint64_t)H * 64, (uint64_t)M}, sv[1] = {(uint64_t)H * 64 * 2};
+    uint32_t bv[2] = {64, L};
+    if (int rc = make_tensor_map_bf16(&mdob, bw.dObf, 2, dv, sv, bv, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    uint64_t dqk[2] = {(uint64_t)H * QK_W, (uint64_t)M}, sqk[1] = {(uint64_t)H * QK_W * 2};
+    if (int rc = make_tensor_map_bf16(&mq64, ws.Qp, 2, dqk, sqk, bv, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  }
+  ipa_bwd_keyside_kernel<<<B * H, 160, KsSmem::kTotal, s>>>(mpn, mdl, mdob, mq64, bw.dK, bw.dV);
+  count_launch();
+
+  bwd_assemble_kernel<<<M / 32, 256, 0, s>>>(bw.dQ, bw.dK, bw.dV, ws.Qp, ws.Kp, R, gamma, dproj, bw.p_g2);
+  count_launch();
+  bwd_finalize_kernel<<<1, 512, 0, s>>>(bw.p_wpb, B * 8, bw.p_g1, bw.p_g2, M / 32, wpb, gamma, d_w_pair_bias, d_gamma);
+  count_launch();
+  return check_launch("dab_ipa_bwd_sm100");
+}
+
+/* Test hook: the intermediate buffers of the last dab_ipa_bwd_sm100 call on `workspace` (device pointers). */
+int dab_debug_bwd_sm100_buffers(const DabIpaDims* d, void* workspace, void** out /* 10 pointers */) {
+  DAB_REQUIRE(shape_ok(d) && workspace && out, DAB_EINVAL, "dab_debug_bwd_sm100_buffers: bad argument");
+  BwdWs bw = carve_bwd(d->B, workspace);
+  out[0] = bw.dO16; out[1] = bw.dObf; out[2] = bw.dopair; out[3] = bw.delta; out[4] = bw.rscale;
+  out[5] = bw.Pn; out[6] = bw.dL; out[7] = bw.dQ; out[8] = bw.dK; out[9] = bw.dV;
+  return DAB_OK;
+}
+
+}  // extern "C"

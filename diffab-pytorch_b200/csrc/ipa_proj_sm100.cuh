@@ -258,7 +258,8 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
               const float nk = -0.5f * ch * n2;
               const float a = __bfloat162float(__float2bfloat16_rn(nk));
               const float m = __bfloat162float(__float2bfloat16_rn(nk - a));
-              tail.x = pk_bf(a, m); tail.y = pk_bf(nk - a - m, 0.0f);
+              // column 59 = 1 (its Q counterpart is 0): the backward's dQ^T MMA then also returns sum_j dlogit
+              tail.x = pk_bf(a, m); tail.y = pk_bf(nk - a - m, 1.0f);
             }
             oh[3] = tail;
             ol[3] = make_uint4(0, 0, 0, 0);

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "gemm_sm100.cuh"
 #include "ipa_proj_sm100.cuh"
+#include "ipa_sm100_layout.cuh"
 #include "sm100_prims.cuh"
 
 namespace dab {
@@ -63,31 +64,6 @@ namespace sm100 {
 
 static long long* g_core_dbg = nullptr;   // optional timeline buffer (dab_debug_set_timeline)
 
-// fixed configuration of the fast path
-constexpr int L = 128, D = 128, C = 64, H = 8, DS = 32, P = 8;
-constexpr int NS = H * DS;            // 256
-constexpr int NPT = H * P * 3;        // 192
-constexpr int NPROJ = 3 * NS + 3 * NPT;  // 1344
-constexpr int NCAT = NS + H * C + NPT + H * P;  // 1024
-constexpr int QK_W = 96;              // packed q/k row per head: [scalar 32 | point hi 24 + 3 + pad 5 | point lo 24 + pad 8]
-constexpr int V_W = 64;               // packed v row per head:   [scalar 32 | point 24 | pad 8]
-constexpr int IB = 16;                // query rows per CTA
-constexpr float kLog2e = 1.4426950408889634f;
-
-struct PackedOffsets {
-  size_t wcat, wout, wpb, bout, gamma, total;
-};
-__host__ __device__ inline PackedOffsets packed_offsets() {
-  PackedOffsets o;
-  o.wcat = 0;
-  o.wout = o.wcat + (size_t)NPROJ * D * 2;          // 344,064
-  o.wpb = o.wout + (size_t)D * NCAT * 2;            // +262,144
-  o.bout = o.wpb + 2048;
-  o.gamma = o.bout + 512;
-  o.total = o.gamma + 64;
-  return o;
-}
-
 // ---- weight packing (once per layer) --------------------------------------------------------------
 __global__ void pack_weights_kernel(DabIpaWeights w, uint8_t* packed) {
   const PackedOffsets o = packed_offsets();
@@ -102,6 +78,18 @@ __global__ void pack_weights_kernel(DabIpaWeights w, uint8_t* packed) {
     row0 += rows[s];
   }
   for (int i = tid; i < D * NCAT; i += nth) wout[i] = __float2bfloat16_rn(w.w_out[i]);
+  // transposed copies (backward data-gradient GEMMs): wcat_t[d][f] = wcat[f][d], wout_t[f][d] = wout[d][f]
+  __nv_bfloat16* wcat_t = reinterpret_cast<__nv_bfloat16*>(packed + o.wcat_t);
+  __nv_bfloat16* wout_t = reinterpret_cast<__nv_bfloat16*>(packed + o.wout_t);
+  row0 = 0;
+  for (int s = 0; s < 6; ++s) {
+    for (int i = tid; i < rows[s] * D; i += nth) {
+      const int f = row0 + i / D, dd = i % D;
+      wcat_t[(size_t)dd * NPROJ + f] = __float2bfloat16_rn(src[s][i]);
+    }
+    row0 += rows[s];
+  }
+  for (int i = tid; i < D * NCAT; i += nth) wout_t[(size_t)(i % NCAT) * D + i / NCAT] = __float2bfloat16_rn(w.w_out[i]);
   // raw fp32 pair-bias weights (H x C), used when a layer call arrives without a precomputed bias plane
   float* wpb = reinterpret_cast<float*>(packed + o.wpb);
   for (int i = tid; i < H * C; i += nth) wpb[i] = w.w_pair_bias[i];
@@ -112,15 +100,6 @@ __global__ void pack_weights_kernel(DabIpaWeights w, uint8_t* packed) {
 }
 
 // ---- operand packing (per call) --------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
-  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&p);
-}
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  __half2 p = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&p);
-}
-
 // grid (L/16, B), 128 threads; warp w handles rows i0 + 4w .. 4w+3, lanes spread over features.
 __global__ void __launch_bounds__(128) ipa_pack_kernel(const float* __restrict__ proj, const float* __restrict__ R,
                                                        const float* __restrict__ t, const float* __restrict__ gamma,
@@ -224,7 +203,8 @@ __global__ void __launch_bounds__(128) ipa_pack_kernel(const float* __restrict__
             float a = __bfloat162float(__float2bfloat16_rn(nk));
             float m = __bfloat162float(__float2bfloat16_rn(nk - a));
             float l = nk - a - m;
-            tail.x = pack_bf162(a, m); tail.y = pack_bf162(l, 0.0f);
+            // column 59 = 1 (its Q counterpart is 0): the backward's dQ^T MMA then also returns sum_j dlogit
+            tail.x = pack_bf162(a, m); tail.y = pack_bf162(l, 1.0f);
           }
           *reinterpret_cast<uint4*>(base + 56) = tail;
           *reinterpret_cast<uint4*>(base + 88) = make_uint4(0, 0, 0, 0);
@@ -274,12 +254,6 @@ enum Bar { K_FULL = 0, K_EMPTY = 3, Q_FULL = 6, S_DONE = 7, E_FULL = 8, E_EMPTY 
 
 // TMEM columns
 constexpr uint32_t kColS = 0, kColPair = 128 /* 16 rows x 8 */, kTmemCols = 256;
-
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 // Reduce 8 per-lane values across the warp with 9 shuffles; lane ends up with the result for head
 // hsel = 4*bit4 + 2*bit3 + bit2 of its lane id (every group of 4 lanes holds the same head).
@@ -349,7 +323,7 @@ __global__ void __launch_bounds__(320, 2)
 ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_e,
                 const uint4* __restrict__ bias, const float* __restrict__ tc, const float* __restrict__ R,
-                __nv_bfloat16* __restrict__ cat, long long* __restrict__ dbg) {
+                __nv_bfloat16* __restrict__ cat, float* __restrict__ stats, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // optional per-CTA timeline: slot k of CTA c at dbg[c * 64 + k]
   long long* dbg_cta = dbg ? dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
@@ -560,6 +534,12 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           mx[4 * k + 3] = fmaxf(fmaxf(a.w, bb.w), fmaxf(c.w, dd.w));
         }
       }
+      if (stats && gt < 16) {   // row maxima (log2 units) of the group's two rows, kept for the backward
+        float v = mx[0];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) v = (k == gt) ? mx[k] : v;
+        stats[(row0 + 2 * (2 * q + (gt >> 3)) + g) * 16 + (gt & 7)] = v;
+      }
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int n = 2 * q + r, i = 2 * n + g;
@@ -623,6 +603,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
     }
     bar_all_compute();
+    if (stats && g == 0) stats[(row0 + (gt >> 3)) * 16 + 8 + (gt & 7)] = inv_o[gt];
     float* s_og = reinterpret_cast<float*>(smem);   // [16 i][8 h][24] global-frame points (region X is free)
 #pragma unroll
     for (int hh = 0; hh < H / 2; ++hh) {
@@ -757,32 +738,6 @@ __global__ void __launch_bounds__(128) ipa_pair_bias_kernel(const uint4* __restr
 }
 
 
-// ---- workspace --------------------------------------------------------------------------------------
-struct Ws {
-  __nv_bfloat16 *Qp, *Kp, *Vp, *cat;
-  float* tc;
-  uint4* bias;   // fallback plane when the caller did not precompute the layer's pair bias
-  size_t bytes;
-};
-static Ws carve_ws(int B, void* base) {
-  auto al = [](size_t n) { return (n + 1023) / 1024 * 1024; };
-  size_t rows = (size_t)B * L;
-  uint8_t* p = reinterpret_cast<uint8_t*>(base);
-  Ws w;
-  w.Qp = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * H * QK_W * 2);
-  w.Kp = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * H * QK_W * 2);
-  w.Vp = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * H * V_W * 2);
-  w.tc = reinterpret_cast<float*>(p); p += al(rows * 3 * 4);
-  w.cat = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * NCAT * 2);
-  w.bias = reinterpret_cast<uint4*>(p); p += al(rows * L * 16);
-  w.bytes = (size_t)(p - reinterpret_cast<uint8_t*>(base));
-  return w;
-}
-
-static bool shape_ok(const DabIpaDims* d) {
-  return d && d->L == L && d->D == D && d->C == C && d->H == H && d->ds == DS && d->Pq == P && d->Pv == P && d->B >= 0;
-}
-
 }  // namespace sm100
 }  // namespace dab
 
@@ -807,6 +762,18 @@ int dab_ipa_pack_weights(const DabIpaDims* d, const DabIpaWeights* w, void* pack
 
 size_t dab_ipa_sm100_workspace_bytes(const DabIpaDims* d) { return shape_ok(d) ? carve_ws(d->B, nullptr).bytes : 0; }
 
+/* Byte offsets of the workspace sections: Qp, Kp, Vp, tc, cat, bias, stats (the caller's library GEMMs of the
+ * backward read `cat`; tests read the rest). */
+int dab_ipa_sm100_workspace_layout(const DabIpaDims* d, size_t* offsets /* 7 */) {
+  DAB_REQUIRE(shape_ok(d) && offsets, DAB_EINVAL, "dab_ipa_sm100_workspace_layout: bad argument");
+  Ws w = carve_ws(d->B, nullptr);
+  offsets[0] = reinterpret_cast<size_t>(w.Qp); offsets[1] = reinterpret_cast<size_t>(w.Kp);
+  offsets[2] = reinterpret_cast<size_t>(w.Vp); offsets[3] = reinterpret_cast<size_t>(w.tc);
+  offsets[4] = reinterpret_cast<size_t>(w.cat); offsets[5] = reinterpret_cast<size_t>(w.bias);
+  offsets[6] = reinterpret_cast<size_t>(w.stats);
+  return DAB_OK;
+}
+
 int dab_ipa_pair_bias(const DabIpaDims* d, const void* e_bf16, const float* w_pair_bias, void* bias_f16, void* stream) {
   DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
               "dab_ipa_pair_bias: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
@@ -820,9 +787,9 @@ int dab_ipa_pair_bias(const DabIpaDims* d, const void* e_bf16, const float* w_pa
   return check_launch("dab_ipa_pair_bias");
 }
 
-int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
-                      const void* bias_f16, const float* R, const float* t, float* y, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
+                          const void* bias_f16, const float* R, const float* t, float* y, void* workspace,
+                          size_t workspace_bytes, bool save_for_bwd, void* stream) {
   DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
               "dab_ipa_fwd_sm100: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
   if (d->B == 0) return DAB_OK;
@@ -877,7 +844,8 @@ int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, c
       cudaFuncSetAttribute(ipa_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CoreSmem::kTotal);
       attr_done = true;
     }
-    ipa_core_kernel<<<dim3(L / IB, B), 320, CoreSmem::kTotal, s>>>(mq, mk, mv, me, bias, ws.tc, R, ws.cat, g_core_dbg);
+    ipa_core_kernel<<<dim3(L / IB, B), 320, CoreSmem::kTotal, s>>>(mq, mk, mv, me, bias, ws.tc, R, ws.cat,
+                                                                   save_for_bwd ? ws.stats : nullptr, g_core_dbg);
     count_launch();
   }
   if (phases & 4) {
@@ -886,6 +854,19 @@ int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, c
       return rc;
   }
   return check_launch("dab_ipa_fwd_sm100");
+}
+
+int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
+                      const void* bias_f16, const float* R, const float* t, float* y, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  return fwd_sm100_impl(d, packed, x, e_bf16, bias_f16, R, t, y, workspace, workspace_bytes, false, stream);
+}
+
+/* Training forward: same launches; the workspace additionally keeps what dab_ipa_bwd_sm100 needs (packed operands,
+ * concat features, the layer's pair-bias plane and the softmax statistics) and must be handed to it untouched. */
+int dab_ipa_fwd_sm100_train(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
+                            const float* R, const float* t, float* y, void* saved, size_t saved_bytes, void* stream) {
+  return fwd_sm100_impl(d, packed, x, e_bf16, nullptr, R, t, y, saved, saved_bytes, true, stream);
 }
 
 /* Profiling hook: per-CTA clock64 timeline of the attention core (64 slots per CTA), NULL to disable. */

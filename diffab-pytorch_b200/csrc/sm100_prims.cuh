@@ -115,6 +115,12 @@ __device__ __forceinline__ void tmem_free(uint32_t addr, uint32_t ncols) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 32 bit, N consecutive columns -> N registers per thread (thread = lane of its warp's subpartition)
+__device__ __forceinline__ void tmem_ld_x2(uint32_t taddr, float (&v)[2]) {
+  uint32_t r[2];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+  v[0] = __uint_as_float(r[0]);
+  v[1] = __uint_as_float(r[1]);
+}
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

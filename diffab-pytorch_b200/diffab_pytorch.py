@@ -235,6 +235,69 @@ class _IpaFunction(torch.autograd.Function):
         return (None, None, dx, de, None, None, *grads)
 
 
+class _IpaFastFunction(torch.autograd.Function):
+    """bf16 tensor-core IPA layer with gradients: ``dab_ipa_fwd_sm100_train`` / ``dab_ipa_bwd_sm100``.
+    The four plain GEMMs of the backward (through ``to_out`` and through the six projections) are library
+    GEMMs (TF32); everything between them runs in the library's tcgen05 kernels."""
+
+    @staticmethod
+    def forward(ctx, layer, x, e, r, t, *weights):
+        x = _lib.dev(x, torch.float32, "x")
+        e = _lib.dev(e, torch.bfloat16, "e")
+        r = _lib.dev(r, torch.float32, "r")
+        t = _lib.dev(t, torch.float32, "t")
+        B, L, D = x.shape
+        dims = _ipa_structs(layer, B, L)
+        lib = _lib.lib()
+        packed = layer._packed_weights(dims)
+        nbytes = lib.dab_ipa_sm100_workspace_bytes(ctypes.byref(dims))
+        saved = torch.empty(max(nbytes, 16), device=x.device, dtype=torch.uint8)   # private: kept for the backward
+        y = torch.empty(B, L, D, device=x.device, dtype=torch.float32)
+        _lib.check(lib.dab_ipa_fwd_sm100_train(ctypes.byref(dims), ptr(packed), ptr(x), ptr(e), ptr(r), ptr(t), ptr(y),
+                                               ptr(saved), saved.numel(), _lib.stream_ptr()), "dab_ipa_fwd_sm100_train")
+        ctx.save_for_backward(x, e, r, saved, packed, *[w.detach() for w in weights])
+        ctx.layer = layer
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, e, r, saved, packed, *weights = ctx.saved_tensors
+        layer = ctx.layer
+        if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
+            raise NotImplementedError("gradients w.r.t. the frames (r, t) are not provided: in DiffAb they are the "
+                                      "noised frames and carry no gradient (diffab_pytorch.py:824-854)")
+        B, L, D = x.shape
+        M = B * L
+        dims = _ipa_structs(layer, B, L)
+        lib = _lib.lib()
+        offs = (ctypes.c_size_t * 7)()
+        _lib.check(lib.dab_ipa_sm100_workspace_layout(ctypes.byref(dims), offs), "dab_ipa_sm100_workspace_layout")
+        w_out = weights[8]
+        ncat = w_out.shape[1]
+        cat = saved[offs[4]: offs[4] + M * ncat * 2].view(torch.bfloat16).view(M, ncat)
+        dy2 = _lib.dev(dy, torch.float32, "dy").view(M, D)
+        with _tf32_matmuls(True):
+            dcat = dy2 @ w_out                                   # (M, 1024)
+            d_w_out = dy2.t() @ cat.float()
+        d_b_out = dy2.sum(0)
+        w_cat = torch.cat(weights[:6], dim=0)                    # (1344, D)
+        dproj = torch.empty(M, w_cat.shape[0], device=x.device, dtype=torch.float32)
+        de = torch.empty_like(e)
+        d_wpb = torch.zeros_like(weights[6])
+        d_gamma = torch.zeros_like(weights[7])
+        bws = torch.empty(max(lib.dab_ipa_bwd_sm100_workspace_bytes(ctypes.byref(dims)), 16), device=x.device,
+                          dtype=torch.uint8)
+        _lib.check(lib.dab_ipa_bwd_sm100(ctypes.byref(dims), ptr(packed), ptr(e), ptr(r), ptr(dcat), ptr(saved),
+                                         saved.numel(), ptr(dproj), ptr(de), ptr(d_wpb), ptr(d_gamma), ptr(bws),
+                                         bws.numel(), _lib.stream_ptr()), "dab_ipa_bwd_sm100")
+        layer._last_bwd_ws = bws   # kept for tools/debug_bwd.py (intermediate buffers of the last backward)
+        with _tf32_matmuls(True):
+            dx = (dproj @ w_cat).view(B, L, D)
+            d_w_cat = dproj.t() @ x.view(M, D)
+        d_proj_w = torch.split(d_w_cat, [w.shape[0] for w in weights[:6]], dim=0)
+        return (None, dx, de, None, None, *d_proj_w, d_wpb, d_gamma, d_w_out, d_b_out)
+
+
 class InvariantPointAttentionLayer(nn.Module):
     """diffab_pytorch.py:339-465.  Parameters keep the reference's names and shapes."""
 
@@ -323,8 +386,12 @@ class InvariantPointAttentionLayer(nn.Module):
         return out
 
     def forward_fast(self, x, e_bf16, r, t, pair_bias=None):
-        if torch.is_grad_enabled() and (x.requires_grad or any(w.requires_grad for w in self._weights())):
-            raise RuntimeError("the bf16 tensor-core IPA path is inference-only; run under torch.no_grad()")
+        if torch.is_grad_enabled() and (x.requires_grad or e_bf16.requires_grad or
+                                        any(w.requires_grad for w in self._weights())):
+            if not self.fast_path_supported(x.shape[1]):
+                raise RuntimeError("bf16 pair tensor given but the sm_100a path only supports the train.py "
+                                   "configuration (L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8)")
+            return _IpaFastFunction.apply(self, x, e_bf16, r, t, *self._weights())
         x = _lib.dev(x, torch.float32, "x")
         e = _lib.dev(e_bf16, torch.bfloat16, "e")
         r = _lib.dev(r, torch.float32, "r")

@@ -167,6 +167,25 @@ int dab_ipa_pair_bias(const DabIpaDims* d, const void* e_bf16, const float* w_pa
 int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
                       const void* bias_f16, const float* R, const float* t, float* y, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* Training pair of the sm_100a path (bf16 pair tensor, fp32 x / y).  The forward is dab_ipa_fwd_sm100 with the
+ * pair bias rebuilt inside the call; `saved` (dab_ipa_sm100_workspace_bytes) additionally keeps the packed
+ * operands, the concat features, the bias plane and the softmax statistics, and must reach the backward untouched. */
+int dab_ipa_fwd_sm100_train(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
+                            const float* R, const float* t, float* y, void* saved, size_t saved_bytes, void* stream);
+/* Backward of the attention part of the layer (autograd of diffab_pytorch.py:389-462) on tcgen05:
+ *   in : dcat[B*L,1024] fp32 = dy . to_out.weight (gradient of the concat features; a plain GEMM of the caller),
+ *        e_bf16, R, `saved` from dab_ipa_fwd_sm100_train, `packed` weights;
+ *   out: dproj[B*L,1344] fp32 = gradient of the six projections in the row order of
+ *        [to_q_scalar; to_k_scalar; to_v_scalar; to_q_point; to_k_point; to_v_point] (so dx = dproj . Wcat and
+ *        dWcat = dproj^T . x are plain GEMMs of the caller), de_bf16[B,L,L,C] bf16 (overwritten),
+ *        d_w_pair_bias[8,64] and d_gamma[8] (accumulated into).
+ * R and t are treated as constants, as in dab_ipa_bwd_f32. */
+int dab_ipa_sm100_workspace_layout(const DabIpaDims* d, size_t* offsets /* 7: Qp, Kp, Vp, tc, cat, bias, stats */);
+size_t dab_ipa_bwd_sm100_workspace_bytes(const DabIpaDims* d);
+int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf16, const float* R, const float* dcat,
+                      void* saved, size_t saved_bytes, float* dproj, void* de_bf16, float* d_w_pair_bias, float* d_gamma,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int dab_debug_bwd_sm100_buffers(const DabIpaDims* d, void* workspace, void** out /* 10 device pointers */);
 /* Test hooks of the sm_100a path (used by tests/ only): the tcgen05 GEMM C[M,N] = A[M,K] B[N,K]^T + bias
  * (bf16 in, fp32 out; M % 128 == 0, N % 64 == 0, K % 64 == 0) and the operand-packing stage alone. */
 int dab_debug_set_timeline(long long* device_buf /* 64 slots per CTA of the attention core, or NULL */);
