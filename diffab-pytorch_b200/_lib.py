@@ -73,6 +73,7 @@ EXPORTS = {
     "dab_ipa_bwd_sm100_workspace_bytes": (c_size_t, [POINTER(DabIpaDims)]),
     "dab_ipa_bwd_sm100": (c_int, [POINTER(DabIpaDims), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dab_debug_set_bwd_timeline": (c_int, [c_void_p]),
     "dab_debug_bwd_sm100_buffers": (c_int, [POINTER(DabIpaDims), c_void_p, c_void_p]),
     "dab_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dab_debug_set_timeline": (c_int, [c_void_p]),

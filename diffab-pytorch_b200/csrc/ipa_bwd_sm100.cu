@@ -40,6 +40,7 @@ namespace dab {
 namespace sm100 {
 
 constexpr float kLn2 = 0.6931471805599453f;
+static long long* g_bwd_dbg = nullptr;   // optional per-CTA clock64 timeline (dab_debug_set_bwd_timeline)
 
 // ---- backward workspace ---------------------------------------------------------------------------------
 struct BwdWs {
@@ -51,6 +52,7 @@ struct BwdWs {
   __nv_bfloat16 *Pn, *dL;   // [B][8][128 i][128 j] bf16
   float *dQ, *dK, *dV;      // [rows][8][64] fp32
   float *p_wpb, *p_g1, *p_g2;   // partials: [B*8][512], [B*8][8], [rows/32][8]
+  float* r_part;                // [32][528] second-level partials
   size_t bytes;
 };
 inline BwdWs carve_bwd(int B, void* base) {
@@ -71,6 +73,7 @@ inline BwdWs carve_bwd(int B, void* base) {
   w.p_wpb = reinterpret_cast<float*>(p); p += al((size_t)B * 8 * 512 * 4);
   w.p_g1 = reinterpret_cast<float*>(p); p += al((size_t)B * 8 * 8 * 4);
   w.p_g2 = reinterpret_cast<float*>(p); p += al((rows / 32) * 8 * 4);
+  w.r_part = reinterpret_cast<float*>(p); p += al(32 * 528 * 4);
   w.bytes = (size_t)(p - reinterpret_cast<uint8_t*>(base));
   return w;
 }
@@ -148,62 +151,63 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const float* __restrict__
 }
 
 // ---- 2. query-side core ---------------------------------------------------------------------------------------
+// The forward saved the un-normalised probabilities Pu[b][i][j][8 h] (bf16) and 1 / sum_j p, so the logits are not
+// recomputed: no Q / K operands here (dQ moved to the key-side kernel, where dl_h is a resident tile anyway).
 struct BwdSmem {
-  // region X: stage 1 = K ring (3 heads) + V ring (3 heads); stage 2 = ring of seven pair rows; stage 3 = K ring again
-  static constexpr int kKBuf = 3 * L * 64;           // 24,576: one head, three [128 x 64 B] blocks
-  static constexpr int kKBufs = 3;
-  static constexpr int kVOff = kKBufs * kKBuf;       // 73,728
+  // region X: stage 1 = ring of four V heads; stage 2 = ring of four pair rows
   static constexpr int kVBuf = L * V_W * 2;          // 16,384
-  static constexpr int kVBufs = 3;
+  static constexpr int kVBufs = 4;
   static constexpr int kEStage = L * C * 2;          // 16,384
-  static constexpr int kEStages = 7;
-  static constexpr int kK2Buf = 2 * L * 64;          // 16,384: scalar + point-hi blocks of one head
-  static constexpr int kK2Bufs = 3;
-  static constexpr int kXBytes = kVOff + kVBufs * kVBuf;   // 122,880
-  // region Y: stage 1 = Q rows + dO rows of this CTA; stage 2/3 = dl_h (B operand of dQ^T) + ring of dopair rows
-  static constexpr int kY = kXBytes;
-  static constexpr int kQOff = kY;                   // 24,576
-  static constexpr int kDoOff = kY + 24576;          // [h][16 i][128 B] fp16, 16,384
-  static constexpr int kDlh = kY;                    // [h][kb(2)][16 i][128 B] bf16, 32,768
-  static constexpr int kDop = kY + 32768;            // 7 x [8 h][128 B] bf16 (+ 1 KB slack read as garbage N rows)
-  static constexpr int kYBytes = 40960;
-  static constexpr int kWpb = kY + kYBytes;          // [8 h][128 B] bf16: st * Wpb
-  static constexpr int kPcat = kWpb + 1024;          // 4 x { [128 j][16 B] P | [128 j][16 B] dl } bf16
-  static constexpr int kStats = kPcat + 4 * 4096;    // [16 i][16] f32
-  static constexpr int kDelta = kStats + 1024;       // [16 i][8] f32
+  static constexpr int kEStages = 4;
+  static constexpr int kXBytes = kEStages * kEStage;   // 65,536
+  // region P: stage 1 = dO rows of this CTA ([h][16 i][128 B] fp16); stage 2 = four [P | dl] operand buffers
+  static constexpr int kDoOff = kXBytes;             // 16,384
+  static constexpr int kPcat = kXBytes;              // 4 x { [128 j][16 B] P | [128 j][16 B] dl } bf16
+  static constexpr int kDop = kPcat + 16384;         // ring of four [8 h][128 B] bf16 dopair rows ...
+  static constexpr int kWpb = kDop + kEStages * 1024;   // ... directly followed by [8 h][128 B] bf16: st * Wpb
+  static constexpr int kInv = kWpb + 1024;           // [16 i][8] f32: 1 / sum_j p
+  static constexpr int kDelta = kInv + 512;          // [16 i][8] f32
   static constexpr int kRs = kDelta + 512;           // [16] f32
   static constexpr int kRed = kRs + 64;              // [8 warps][8] f32
-  static constexpr int kBars = kRed + 256;           // 64 mbarriers
-  static constexpr int kTmemSlot = kBars + 512;
+  static constexpr int kBars = kRed + 256;           // 48 mbarriers
+  static constexpr int kTmemSlot = kBars + 384;
   static constexpr int kTotal = kTmemSlot + 16;
 };
-static_assert(BwdSmem::kEStages * BwdSmem::kEStage <= BwdSmem::kXBytes, "e ring must fit region X");
-static_assert(BwdSmem::kDop + (BwdSmem::kEStages + 1) * 1024 <= BwdSmem::kY + BwdSmem::kYBytes, "dopair ring must fit region Y");
-static_assert(BwdSmem::kTotal <= 227 * 1024, "shared memory");
+static_assert(BwdSmem::kVBufs * BwdSmem::kVBuf <= BwdSmem::kXBytes, "V ring must fit region X");
+static_assert(BwdSmem::kTotal <= 113 * 1024, "two CTAs per SM");
 
-enum BBar { BK_FULL = 0, BK_EMPTY = 3, BV_FULL = 6, BV_EMPTY = 9, BQ_FULL = 12, BS_DONE = 13, BE_FULL = 14, BE_EMPTY = 21,
-            DPP_DONE = 28, DPP_FREE = 32 /* 128 arrivals */, PCAT_READY = 36 /* [g][slot], 128 arrivals */, PCAT_FREE = 40,
-            DE_DONE = 44 /* [g] */, K2_FULL = 46, K2_EMPTY = 49, DQ_DONE = 52, B_N_BARS = 53 };
+enum BBar { BV_FULL = 0, BV_EMPTY = 4, BQ_FULL = 8, BS_DONE = 9, BE_FULL = 10, BE_EMPTY = 14,
+            DPP_DONE = 18 /* 3 */, DPP_FREE = 21 /* 3, 128 arrivals */, PCAT_READY = 24 /* [g][slot], 128 arrivals */,
+            PCAT_FREE = 28, DE_DONE = 32 /* [g] */, DE_FREE = 34 /* 128 arrivals */, B_N_BARS = 35 };
 
-constexpr uint32_t kBColS = 0, kBColDPV = 128, kBColDPP = 256 /* 4 x 16 */, kBColDE = 320 /* 2 x 64 */, kBColWPB = 448;
+// TMEM columns (256 per CTA): value part of dP for the 16 rows, ring of three pair parts, de, to_pair_bias gradient
+constexpr uint32_t kBColDPV = 0, kBColDPP = 128 /* 3 x 16 */, kBColDE = 176 /* 64 */, kBColWPB = 240 /* 8 */;
 
 __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
   return make_uint4(pack_bf162(v[0], v[1]), pack_bf162(v[2], v[3]), pack_bf162(v[4], v[5]), pack_bf162(v[6], v[7]));
 }
+__device__ __forceinline__ float lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-__global__ void __launch_bounds__(320, 1)
-ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                    const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_e,
+__global__ void __launch_bounds__(320, 2)
+ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_e,
                     const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_dop,
-                    const uint4* __restrict__ bias, const float* __restrict__ stats, const float* __restrict__ delta,
+                    const uint4* __restrict__ Pu, const float* __restrict__ stats, const float* __restrict__ delta,
                     const float* __restrict__ rscale, const float* __restrict__ wpb, __nv_bfloat16* __restrict__ de,
-                    __nv_bfloat16* __restrict__ Pn, __nv_bfloat16* __restrict__ dL, float* __restrict__ dQ,
-                    float* __restrict__ p_wpb, float* __restrict__ p_g1) {
+                    __nv_bfloat16* __restrict__ Pn, __nv_bfloat16* __restrict__ dL, float* __restrict__ p_wpb,
+                    float* __restrict__ p_g1, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  long long* dbg_cta = dbg ? dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
+#define BWD_STAMP(k) do { if (dbg_cta && threadIdx.x == 0) dbg_cta[(k)] = clock64(); } while (0)
+#define BWD_STAMP_ISSUER(k) do { if (dbg_cta) dbg_cta[(k)] = clock64(); } while (0)
+  BWD_STAMP(0);
   using S = BwdSmem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
-  float* s_stats = reinterpret_cast<float*>(smem + S::kStats);
+  float* s_inv = reinterpret_cast<float*>(smem + S::kInv);
   float* s_delta = reinterpret_cast<float*>(smem + S::kDelta);
   float* s_rs = reinterpret_cast<float*>(smem + S::kRs);
   float* s_red = reinterpret_cast<float*>(smem + S::kRed);
@@ -217,14 +221,16 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
   if (tid == 0) {
     for (int i = 0; i < B_N_BARS; ++i) {
-      const bool many = (i >= DPP_FREE && i < DPP_FREE + 4) || (i >= PCAT_READY && i < PCAT_READY + 4);
+      const bool many = (i >= DPP_FREE && i < DPP_FREE + 3) || (i >= PCAT_READY && i < PCAT_READY + 4) || i == DE_FREE;
       mbar_init(&bars[i], many ? 128u : 1u);
     }
     fence_barrier_init();
   }
   // per-row constants of this CTA and the st * Wpb operand tile ([8 h][64 c] bf16, 128B-swizzled rows)
-  if (tid < 256) s_stats[tid] = stats[row0 * 16 + tid];
-  if (tid < 128) s_delta[tid] = delta[row0 * 8 + tid];
+  if (tid < 128) {
+    s_inv[tid] = stats[(row0 + (tid >> 3)) * 16 + 8 + (tid & 7)];
+    s_delta[tid] = delta[row0 * 8 + tid];
+  }
   if (tid < 16) s_rs[tid] = rscale[row0 + tid];
   if (tid < 256) {
     const float st = rsqrtf(3.0f);
@@ -234,50 +240,38 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   }
   fence_proxy_async_smem();
   __syncwarp();
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
   tcgen05_fence_before_sync();
   __syncthreads();
   tcgen05_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  BWD_STAMP(1);
 
-  // issue order of the rows inside a block of four: group 0 works on rows {0,1}, group 1 on rows {2,3} at the same time
+  // Issue order of the rows: group 0 works on rows {0,1} of a block of four while group 1 works on rows {2,3}, so
+  // the rows become ready in the order 0,2,1,3.  ord() swaps the two low bits and is its own inverse: ord(row) is
+  // the row's position in the issue order.
   auto ord = [](int k) { return (k & ~3) + ((k & 1) << 1) + ((k >> 1) & 1); };
 
   if (warp == 9) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
-      tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
-      tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_dop);
-      constexpr int kL2Ahead = 8;
-      auto load_k = [&](int h) {
-        const int s = h % S::kKBufs;
-        uint8_t* kb = smem + s * S::kKBuf;
-        mbar_arrive_expect_tx(&bars[BK_FULL + s], S::kKBuf);
-        for (int blk = 0; blk < 3; ++blk)
-          tma_load_2d(kb + blk * (L * 64), &map_k, &bars[BK_FULL + s], (h * 3 + blk) * 32, b * L);
-      };
+      tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e); tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_dop);
+      constexpr int kL2Ahead = 6;
       auto load_v = [&](int h) {
         const int s = h % S::kVBufs;
         mbar_arrive_expect_tx(&bars[BV_FULL + s], S::kVBuf);
-        tma_load_2d(smem + S::kVOff + s * S::kVBuf, &map_v, &bars[BV_FULL + s], h * V_W, b * L);
+        tma_load_2d(smem + s * S::kVBuf, &map_v, &bars[BV_FULL + s], h * V_W, b * L);
       };
-      load_k(0);
-      mbar_arrive_expect_tx(&bars[BQ_FULL], 24576 + 16384);
-      for (int blk = 0; blk < H * 3; ++blk)
-        tma_load_2d(smem + S::kQOff + blk * (IB * 64), &map_q, &bars[BQ_FULL], blk * 32, (int)row0);
+      mbar_arrive_expect_tx(&bars[BQ_FULL], 16384);
       for (int h = 0; h < H; ++h)
         tma_load_2d(smem + S::kDoOff + h * 2048, &map_do, &bars[BQ_FULL], h * 64, (int)row0);
-      load_v(0);
-      load_k(1); load_v(1);
-      load_k(2); load_v(2);
+      for (int h = 0; h < S::kVBufs; ++h) load_v(h);
       for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
-      for (int h = 3; h < H; ++h) {
-        mbar_wait(&bars[BK_EMPTY + h % 3], ((h / 3) - 1) & 1);
-        load_k(h);
-        mbar_wait(&bars[BV_EMPTY + h % 3], ((h / 3) - 1) & 1);
+      for (int h = S::kVBufs; h < H; ++h) {
+        mbar_wait(&bars[BV_EMPTY + h % S::kVBufs], ((h / S::kVBufs) - 1) & 1);
         load_v(h);
       }
-      // ---- stage 2: pair rows + their dopair tiles
+      // ---- stage 2: pair rows + their dopair tiles (region X / P are free once every dPv MMA has completed)
       mbar_wait(&bars[BS_DONE], 0);
       for (int r = 0; r < IB; ++r) {
         const int s = r % S::kEStages;
@@ -287,50 +281,21 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         tma_load_2d(smem + S::kDop + s * 1024, &map_dop, &bars[BE_FULL + s], 0, (int)((row0 + r) * H));
         if (r + kL2Ahead < IB) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r + kL2Ahead) * L));
       }
-      // ---- stage 3: scalar + point-hi blocks of K, head by head, once every pair row has been released
-      for (int s = 0; s < S::kEStages; ++s) {
-        const int uses = (IB - s + S::kEStages - 1) / S::kEStages;
-        mbar_wait(&bars[BE_EMPTY + s], (uses - 1) & 1);
-      }
-      for (int h = 0; h < H; ++h) {
-        const int s = h % S::kK2Bufs;
-        if (h >= S::kK2Bufs) mbar_wait(&bars[K2_EMPTY + s], ((h / S::kK2Bufs) - 1) & 1);
-        mbar_arrive_expect_tx(&bars[K2_FULL + s], S::kK2Buf);
-        for (int blk = 0; blk < 2; ++blk)
-          tma_load_2d(smem + s * S::kK2Buf + blk * (L * 64), &map_k, &bars[K2_FULL + s], (h * 3 + blk) * 32, b * L);
-      }
     }
   } else if (warp == 8) {
     // ======================================= MMA issuer =======================================
     if (lane == 0) {
-      constexpr uint32_t kIdescS = make_idesc_bf16(128, 16, 0, 0);
       constexpr uint32_t kIdescDPV = make_idesc_f16(128, 16, 0, 0);
       constexpr uint32_t kIdescDPP = make_idesc_bf16(128, 16, 0, 0);
       constexpr uint32_t kIdescDE = make_idesc_bf16(128, 64, 0, 1);    // B = [dopair_i ; st Wpb], MN-major
       constexpr uint32_t kIdescZ = make_idesc_bf16(64, 8, 1, 1);       // A = e tile MN-major, B = dl chunk MN-major
-      constexpr uint32_t kIdescDQ = make_idesc_bf16(64, 16, 1, 0);     // A = K blocks MN-major
-      // ---- stage 1
+      // ---- stage 1: dPv^T_h = V_h dO_h^T
       mbar_wait(&bars[BQ_FULL], 0);
       for (int h = 0; h < H; ++h) {
-        const int s = h % 3;
-        mbar_wait(&bars[BK_FULL + s], (h / 3) & 1);
+        const int s = h % S::kVBufs;
+        mbar_wait(&bars[BV_FULL + s], (h / S::kVBufs) & 1);
         tcgen05_fence_after_sync();
-        const uint32_t ka = smem_base + s * S::kKBuf;
-        const uint32_t qa = smem_base + S::kQOff + h * 3 * (IB * 64);
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const int ablk = (m == 0) ? 0 : (m == 3 ? 2 : 1), bblk = (m == 0) ? 0 : (m == 2 ? 2 : 1);
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            uint64_t da = make_smem_desc(ka + ablk * (L * 64) + k * 32, 16, 512, kSwizzle64B);
-            uint64_t db = make_smem_desc(qa + bblk * (IB * 64) + k * 32, 16, 512, kSwizzle64B);
-            umma_bf16(tmem + kBColS + h * 16, da, db, kIdescS, (m | k) != 0);
-          }
-        }
-        umma_commit(&bars[BK_EMPTY + s]);
-        mbar_wait(&bars[BV_FULL + s], (h / 3) & 1);
-        tcgen05_fence_after_sync();
-        const uint32_t va = smem_base + S::kVOff + s * S::kVBuf;
+        const uint32_t va = smem_base + s * S::kVBuf;
         const uint32_t oa = smem_base + S::kDoOff + h * 2048;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -341,27 +306,31 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         umma_commit(&bars[BV_EMPTY + s]);
       }
       umma_commit(&bars[BS_DONE]);
+      BWD_STAMP_ISSUER(2);
       // ---- stage 2
-      auto issue_dpp = [&](int r) {
-        const int s = r % S::kEStages;
+      auto issue_dpp = [&](int pos) {   // pair part of dP for the row at issue position pos
+        const int r = ord(pos), s = r % S::kEStages, ds = pos % 3;
         mbar_wait(&bars[BE_FULL + s], (r / S::kEStages) & 1);
-        if (r >= 4) mbar_wait(&bars[DPP_FREE + (r & 3)], ((r >> 2) - 1) & 1);
+        if (pos >= 3) mbar_wait(&bars[DPP_FREE + ds], ((pos / 3) - 1) & 1);
         tcgen05_fence_after_sync();
         const uint32_t ea = smem_base + s * S::kEStage, da0 = smem_base + S::kDop + s * 1024;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+          // N = 16: rows 8..15 of B are whatever follows the dopair tile (next ring slot or the Wpb tile) and
+          // land in accumulator columns 8..15, which nobody reads
           uint64_t da = make_smem_desc(ea + k * 32, 16, 1024, kSwizzle128B);
           uint64_t db = make_smem_desc(da0 + k * 32, 16, 1024, kSwizzle128B);
-          umma_bf16(tmem + kBColDPP + (r & 3) * 16, da, db, kIdescDPP, k != 0);
+          umma_bf16(tmem + kBColDPP + ds * 16, da, db, kIdescDPP, k != 0);
         }
-        umma_commit(&bars[DPP_DONE + (r & 3)]);
+        umma_commit(&bars[DPP_DONE + ds]);
       };
-      for (int k = 0; k < 4; ++k) issue_dpp(ord(k));
+      for (int k = 0; k < 3; ++k) issue_dpp(k);
       for (int k = 0; k < IB; ++k) {
         const int r = ord(k);
         const int g = (r >> 1) & 1, n = 2 * (r >> 2) + (r & 1), slot = n & 1;
         const int s = r % S::kEStages;
         mbar_wait(&bars[PCAT_READY + g * 2 + slot], (n >> 1) & 1);
+        if (k >= 1) mbar_wait(&bars[DE_FREE], (k - 1) & 1);     // previous de drained out of the accumulator
         tcgen05_fence_after_sync();
         const uint32_t pc = smem_base + S::kPcat + (g * 2 + slot) * 4096;
         const uint32_t dop = smem_base + S::kDop + s * 1024;
@@ -371,7 +340,7 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           //    dopair_i, then st Wpb (SBO = distance between the two tiles).
           uint64_t da = make_smem_desc(pc, 2048, 128, kSwizzleNone);
           uint64_t db = make_smem_desc(dop, 1024, (smem_base + S::kWpb) - dop, kSwizzle128B);
-          umma_bf16(tmem + kBColDE + g * 64, da, db, kIdescDE, false);
+          umma_bf16(tmem + kBColDE, da, db, kIdescDE, false);
         }
         umma_commit(&bars[DE_DONE + g]);
         const uint32_t ea = smem_base + s * S::kEStage;
@@ -385,25 +354,10 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
         umma_commit(&bars[BE_EMPTY + s]);
         umma_commit(&bars[PCAT_FREE + g * 2 + slot]);
-        if (k + 4 < IB) issue_dpp(ord(k + 4));
+        if (k + 3 < IB) issue_dpp(k + 3);
+        BWD_STAMP_ISSUER(32 + k);
       }
-      // ---- stage 3: dQ^T_h = K_h[:, :64]^T dl_h
-      for (int h = 0; h < H; ++h) {
-        const int s = h % S::kK2Bufs;
-        mbar_wait(&bars[K2_FULL + s], (h / S::kK2Bufs) & 1);
-        tcgen05_fence_after_sync();
-        const uint32_t ka = smem_base + s * S::kK2Buf, pa = smem_base + S::kDlh + h * (2 * IB * 128);
-#pragma unroll
-        for (int k = 0; k < L / 16; ++k) {
-          // A: two [128 j][64 B] 64B-swizzled blocks read MN-major: M = 64 = two 32-wide atoms 8192 B apart (LBO),
-          //    8-row (K) groups 512 B apart (SBO)
-          uint64_t da = make_smem_desc(ka + k * 1024, L * 64, 512, kSwizzle64B);
-          uint64_t db = make_smem_desc(pa + (k >> 2) * (IB * 128) + (k & 3) * 32, 16, 1024, kSwizzle128B);
-          umma_bf16(tmem + kBColS + h * 16, da, db, kIdescDQ, k != 0);
-        }
-        umma_commit(&bars[K2_EMPTY + s]);
-      }
-      umma_commit(&bars[DQ_DONE]);
+      BWD_STAMP_ISSUER(3);
     }
   } else {
     // ======================================= softmax-gradient groups =======================================
@@ -414,71 +368,48 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
     for (int h = 0; h < H; ++h) accg[h] = 0.f;
 
-    // de of the group's row with local index np: TMEM -> bf16 -> 128 contiguous bytes per key
-    auto drain_de = [&](int np) {
-      const int ip = 4 * (np >> 1) + 2 * g + (np & 1);
-      mbar_wait(&bars[DE_DONE + g], np & 1);
-      tcgen05_fence_after_sync();
-      uint4* dst = reinterpret_cast<uint4*>(de + ((row0 + ip) * L + gt) * C);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float v[32];
-        tmem_ld_x32(tmem_lane + kBColDE + g * 64 + half * 32, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          dst[half * 4 + q] = make_uint4(pack_bf162(v[8 * q], v[8 * q + 1]), pack_bf162(v[8 * q + 2], v[8 * q + 3]),
-                                         pack_bf162(v[8 * q + 4], v[8 * q + 5]), pack_bf162(v[8 * q + 6], v[8 * q + 7]));
-      }
-      tcgen05_fence_before_sync();
-    };
-
-    const uint4* bias_t = bias + (row0 + 2 * g) * L + gt;     // row 4q + 2g + rr  ->  + (4q + rr) * L
-    uint4 b_nxt[2] = {__ldg(bias_t), __ldg(bias_t + L)};
+    const uint4* pu_t = Pu + (row0 + 2 * g) * L + gt;     // row 4q + 2g + rr  ->  + (4q + rr) * L
+    uint4 u_nxt[2] = {__ldg(pu_t), __ldg(pu_t + L)};
     mbar_wait(&bars[BS_DONE], 0);
     tcgen05_fence_after_sync();
+    BWD_STAMP(4);
     for (int q = 0; q < IB / 4; ++q) {
-      const uint4 b_use[2] = {b_nxt[0], b_nxt[1]};
+      const uint4 u_use[2] = {u_nxt[0], u_nxt[1]};
       if (q + 1 < IB / 4) {
-        b_nxt[0] = __ldg(bias_t + (size_t)(4 * (q + 1)) * L);
-        b_nxt[1] = __ldg(bias_t + (size_t)(4 * (q + 1) + 1) * L);
+        u_nxt[0] = __ldg(pu_t + (size_t)(4 * (q + 1)) * L);
+        u_nxt[1] = __ldg(pu_t + (size_t)(4 * (q + 1) + 1) * L);
       }
-      float sreg[H][2], dpv[H][2];
+      float dpv[H][2];
 #pragma unroll
-      for (int h = 0; h < H; ++h) {
-        tmem_ld_x2(tmem_lane + kBColS + h * 16 + 4 * q + 2 * g, sreg[h]);
-        tmem_ld_x2(tmem_lane + kBColDPV + h * 16 + 4 * q + 2 * g, dpv[h]);
-      }
+      for (int h = 0; h < H; ++h) tmem_ld_x2(tmem_lane + kBColDPV + h * 16 + 4 * q + 2 * g, dpv[h]);
       tmem_wait_ld();
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
-        const int i = 4 * q + 2 * g + rr, n = 2 * q + rr;
+        const int i = 4 * q + 2 * g + rr, n = 2 * q + rr, pos = ord(i);
         float lm[H], p[H], dl[H];
         {
-          const __half2* hb = reinterpret_cast<const __half2*>(&b_use[rr]);
-          const float4* st4 = reinterpret_cast<const float4*>(s_stats + i * 16);
-          const float4 m0 = st4[0], m1 = st4[1], v0 = st4[2], v1 = st4[3];
-          const float m2[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          const __nv_bfloat162* ub = reinterpret_cast<const __nv_bfloat162*>(&u_use[rr]);
+          const float4 v0 = *reinterpret_cast<const float4*>(s_inv + i * 8), v1 = *reinterpret_cast<const float4*>(s_inv + i * 8 + 4);
           const float inv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float2 f = __half22float2(hb[k]);
-            lm[2 * k] = f.x; lm[2 * k + 1] = f.y;
+            const float2 f = __bfloat1622float2(ub[k]);
+            p[2 * k] = f.x; p[2 * k + 1] = f.y;
           }
 #pragma unroll
           for (int h = 0; h < H; ++h) {
-            lm[h] = lm[h] + sreg[h][rr] - m2[h];       // log2 of the un-normalised probability (<= 0)
-            p[h] = ex2(lm[h]) * inv[h];
+            lm[h] = p[h] > 0.f ? lg2(p[h]) : 0.f;      // log2 of the un-normalised probability (<= 0)
+            p[h] *= inv[h];
           }
         }
         // pair part of dP for this row
-        mbar_wait(&bars[DPP_DONE + (i & 3)], (i >> 2) & 1);
+        mbar_wait(&bars[DPP_DONE + pos % 3], (pos / 3) & 1);
         tcgen05_fence_after_sync();
         float dpp[8];
-        tmem_ld_x8(tmem_lane + kBColDPP + (i & 3) * 16, dpp);
+        tmem_ld_x8(tmem_lane + kBColDPP + (pos % 3) * 16, dpp);
         tmem_wait_ld();
         tcgen05_fence_before_sync();
-        mbar_arrive(&bars[DPP_FREE + (i & 3)]);
+        mbar_arrive(&bars[DPP_FREE + pos % 3]);
         {
           const float rs = s_rs[i];
           const float4 d0 = *reinterpret_cast<const float4*>(s_delta + i * 8), d1 = *reinterpret_cast<const float4*>(s_delta + i * 8 + 4);
@@ -490,7 +421,6 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             accg[h] = fmaf(dl[h], lm[h], accg[h]);
           }
         }
-        if (n >= 1) drain_de(n - 1);
         if (n >= 2) mbar_wait(&bars[PCAT_FREE + g * 2 + (n & 1)], ((n >> 1) - 1) & 1);
         // ---- [P | dl] of this key: A operand of the de MMA, and (dl half) B operand of the Z MMA
         {
@@ -498,12 +428,13 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           *reinterpret_cast<uint4*>(pc + gt * 16) = pack8_bf16(p);
           *reinterpret_cast<uint4*>(pc + 2048 + gt * 16) = pack8_bf16(dl);
         }
-        // ---- P and dl as [h][i][j] rows: shared memory (B operand of dQ^T) and HBM (key side); neighbouring lanes
-        //      trade heads so that every store is a packed pair (j, j+1)
+        fence_proxy_async_smem();
+        tcgen05_fence_before_sync();
+        mbar_arrive(&bars[PCAT_READY + g * 2 + (n & 1)]);
+        // ---- P and dl as [h][i][j] rows for the key side; neighbouring lanes trade heads so that every store is a
+        //      packed pair (j, j+1).  Runs while the issuer turns the operands above into de_i.
         {
           const int je = gt & ~1;
-          const uint32_t kb = je >> 6, chunk = (je & 63) >> 3, e2 = (je & 7) * 2;
-          uint8_t* dlh = smem + S::kDlh + kb * (IB * 128);
           const bool odd = lane & 1;
 #pragma unroll
           for (int hh = 0; hh < 4; ++hh) {
@@ -517,15 +448,32 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             const size_t go = (((size_t)b * H + h) * L + (i0 + i)) * L + je;
             *reinterpret_cast<uint32_t*>(Pn + go) = pv;
             *reinterpret_cast<uint32_t*>(dL + go) = dv;
-            *reinterpret_cast<uint32_t*>(dlh + h * (2 * IB * 128) + swz128_offset(i, chunk) + e2) = dv;
           }
         }
-        fence_proxy_async_smem();
-        tcgen05_fence_before_sync();
-        mbar_arrive(&bars[PCAT_READY + g * 2 + (n & 1)]);
+        // ---- de_i: TMEM -> bf16 -> 128 contiguous bytes per key; then hand the accumulator back
+        {
+          mbar_wait(&bars[DE_DONE + g], n & 1);
+          tcgen05_fence_after_sync();
+          uint4* dst = reinterpret_cast<uint4*>(de + ((row0 + i) * L + gt) * C);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tmem_ld_x32(tmem_lane + kBColDE + half * 32, v);
+            tmem_wait_ld();
+            if (half == 1) {
+              tcgen05_fence_before_sync();
+              mbar_arrive(&bars[DE_FREE]);
+            }
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq)
+              dst[half * 4 + qq] = make_uint4(pack_bf162(v[8 * qq], v[8 * qq + 1]), pack_bf162(v[8 * qq + 2], v[8 * qq + 3]),
+                                              pack_bf162(v[8 * qq + 4], v[8 * qq + 5]), pack_bf162(v[8 * qq + 6], v[8 * qq + 7]));
+          }
+        }
+        BWD_STAMP(8 + n);
       }
     }
-    drain_de(IB / 2 - 1);
+    BWD_STAMP(5);
 
     // ---- sum_ij dl (l - m) per head (natural-log units) for dgamma
 #pragma unroll
@@ -540,22 +488,10 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       for (int w = 0; w < 8; ++w) s += s_red[w * 8 + tid];
       p_g1[(size_t)cta * 8 + tid] = s * kLn2;
     }
-    // ---- dQ^T (M = 64: packed column m = 16 gw + lane in lanes 0-15) and the to_pair_bias partial
-    mbar_wait(&bars[DQ_DONE], 0);
-    tcgen05_fence_after_sync();
-#pragma unroll
-    for (int hh = 0; hh < H / 2; ++hh) {
-      const int h = g * (H / 2) + hh;
-      float o[16];
-      tmem_ld_x16(tmem_lane + kBColS + h * 16, o);
-      tmem_wait_ld();
-      if (lane < 16) {
-        float* dst = dQ + ((row0 * H + h) * 64) + gw * 16 + lane;
-#pragma unroll
-        for (int i = 0; i < IB; ++i) dst[(size_t)i * H * 64] = o[i];
-      }
-    }
-    if (g == 0) {
+    // ---- to_pair_bias partial (M = 64: channel c = 16 gw + lane in lanes 0-15)
+    if (g == 1) {
+      mbar_wait(&bars[PCAT_FREE + 3], 1);   // 4th completion of [g=1][slot=1]: commit behind the Z MMAs of the last row
+      tcgen05_fence_after_sync();
       float z[8];
       tmem_ld_x8(tmem_lane + kBColWPB, z);
       tmem_wait_ld();
@@ -564,27 +500,38 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int h = 0; h < H; ++h) p_wpb[(size_t)cta * 512 + h * C + gw * 16 + lane] = z[h];
       }
     }
+    BWD_STAMP(6);
   }
   tcgen05_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_free(tmem, 512);
+  BWD_STAMP(7);
+#undef BWD_STAMP
+#undef BWD_STAMP_ISSUER
+  if (warp == 0) tmem_free(tmem, 256);
 }
 
-// ---- 3. key side -------------------------------------------------------------------------------------------
+// ---- 3. key side (and dQ) --------------------------------------------------------------------------------------
+// Per (patch, head): the [128 i][128 j] tiles of P and dl are resident, so all three contractions over them run here:
+//   dV_h = P_h^T dO_h           (M = j, N = 64, K = i)      A = P tile read MN-major
+//   dK_h = dl_h^T Q_h[:, :64]   (M = j, N = 64, K = i)      A = dl tile read MN-major
+//   dQ_h = dl_h K_h[:, :64]     (M = i, N = 64, K = j)      A = the same dl tile read K-major
 struct KsSmem {
   static constexpr int kPn = 0;          // two [128 i][64 j] boxes, 128B-swizzled
   static constexpr int kDl = 32768;
   static constexpr int kDo = 65536;      // [128 i][64 d]
-  static constexpr int kQ = 81920;       // [128 i][64: scalar | point hi]
-  static constexpr int kBars = 98304;
+  static constexpr int kQ = 81920;       // [128 i][64: scalar | point hi | 1 1 1]
+  static constexpr int kK = 98304;       // [128 j][64: scalar | point hi | norm terms | 1]
+  static constexpr int kBars = 114688;
   static constexpr int kTmemSlot = kBars + 64;
   static constexpr int kTotal = kTmemSlot + 16;
 };
+static_assert(KsSmem::kTotal <= 113 * 1024, "two CTAs per SM");
 
 __global__ void __launch_bounds__(160, 2)
 ipa_bwd_keyside_kernel(const __grid_constant__ CUtensorMap map_pn, const __grid_constant__ CUtensorMap map_dl,
                        const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_q64,
-                       float* __restrict__ dK, float* __restrict__ dV) {
+                       const __grid_constant__ CUtensorMap map_k64, float* __restrict__ dQ, float* __restrict__ dK,
+                       float* __restrict__ dV) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using S = KsSmem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
@@ -596,60 +543,73 @@ ipa_bwd_keyside_kernel(const __grid_constant__ CUtensorMap map_pn, const __grid_
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
     fence_barrier_init();
   }
   __syncwarp();
-  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
   tcgen05_fence_before_sync();
   __syncthreads();
   tcgen05_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   if (warp == 4) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(&bars[0], 98304);
       const int prow = (b * H + h) * L;
+      mbar_arrive_expect_tx(&bars[0], 32768 + 16384);
       tma_load_2d(smem + S::kPn, &map_pn, &bars[0], 0, prow);
       tma_load_2d(smem + S::kPn + 16384, &map_pn, &bars[0], 64, prow);
-      tma_load_2d(smem + S::kDl, &map_dl, &bars[0], 0, prow);
-      tma_load_2d(smem + S::kDl + 16384, &map_dl, &bars[0], 64, prow);
       tma_load_2d(smem + S::kDo, &map_do, &bars[0], h * 64, b * L);
-      tma_load_2d(smem + S::kQ, &map_q64, &bars[0], h * QK_W, b * L);
+      mbar_arrive_expect_tx(&bars[1], 32768 + 32768);
+      tma_load_2d(smem + S::kDl, &map_dl, &bars[1], 0, prow);
+      tma_load_2d(smem + S::kDl + 16384, &map_dl, &bars[1], 64, prow);
+      tma_load_2d(smem + S::kQ, &map_q64, &bars[1], h * QK_W, b * L);
+      tma_load_2d(smem + S::kK, &map_k64, &bars[1], h * QK_W, b * L);
+      constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, 1, 1);
+      constexpr uint32_t idesc_q = make_idesc_bf16(128, 64, 0, 1);
       mbar_wait(&bars[0], 0);
       tcgen05_fence_after_sync();
-      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
 #pragma unroll
       for (int k = 0; k < L / 16; ++k) {
         // A: [i][j] tile read MN-major (M = j): two 64-wide atoms 16 KB apart (LBO), 8-row (K = i) groups 1 KB apart
         uint64_t da = make_smem_desc(smem_base + S::kPn + k * 2048, 16384, 1024, kSwizzle128B);
         uint64_t db = make_smem_desc(smem_base + S::kDo + k * 2048, 1024, 1024, kSwizzle128B);
-        umma_bf16(tmem, da, db, idesc, k != 0);
+        umma_bf16(tmem, da, db, idesc_t, k != 0);
       }
+      mbar_wait(&bars[1], 0);
+      tcgen05_fence_after_sync();
 #pragma unroll
       for (int k = 0; k < L / 16; ++k) {
         uint64_t da = make_smem_desc(smem_base + S::kDl + k * 2048, 16384, 1024, kSwizzle128B);
         uint64_t db = make_smem_desc(smem_base + S::kQ + k * 2048, 1024, 1024, kSwizzle128B);
-        umma_bf16(tmem + 64, da, db, idesc, k != 0);
+        umma_bf16(tmem + 64, da, db, idesc_t, k != 0);
       }
-      umma_commit(&bars[1]);
+#pragma unroll
+      for (int k = 0; k < L / 16; ++k) {
+        // A: the dl tile read K-major (M = i rows of 128 B; K = j: box k / 4, 32 B per step inside the row)
+        uint64_t da = make_smem_desc(smem_base + S::kDl + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, kSwizzle128B);
+        uint64_t db = make_smem_desc(smem_base + S::kK + k * 2048, 1024, 1024, kSwizzle128B);
+        umma_bf16(tmem + 128, da, db, idesc_q, k != 0);
+      }
+      umma_commit(&bars[2]);
     }
   } else {
-    mbar_wait(&bars[1], 0);
+    mbar_wait(&bars[2], 0);
     tcgen05_fence_after_sync();
     const uint32_t tmem_lane = tmem + ((uint32_t)(warp * 32) << 16);
     const size_t o = (((size_t)b * L + tid) * H + h) * 64;
 #pragma unroll
-    for (int part = 0; part < 4; ++part) {
+    for (int part = 0; part < 6; ++part) {
       float v[32];
       tmem_ld_x32(tmem_lane + part * 32, v);
       tmem_wait_ld();
-      float4* dst = reinterpret_cast<float4*>((part < 2 ? dV : dK) + o + (part & 1) * 32);
+      float4* dst = reinterpret_cast<float4*>((part < 2 ? dV : (part < 4 ? dK : dQ)) + o + (part & 1) * 32);
 #pragma unroll
       for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
   }
   tcgen05_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_free(tmem, 128);
+  if (warp == 0) tmem_free(tmem, 256);
 }
 
 // ---- 4. assemble dproj ---------------------------------------------------------------------------------------
@@ -750,16 +710,42 @@ __global__ void __launch_bounds__(256) bwd_assemble_kernel(const float* __restri
 }
 
 // ---- 5. finalize -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) bwd_finalize_kernel(const float* __restrict__ p_wpb, int n_cta,
-                                                           const float* __restrict__ p_g1, const float* __restrict__ p_g2,
-                                                           int n_blk, const float* __restrict__ wpb,
+// Deterministic two-level reduction of the per-CTA partials.  Level 1: block k sums a slice of the core CTAs
+// (and of the assemble blocks) into r_part[k][512 + 16].
+constexpr int kRedBlocks = 32;
+__global__ void __launch_bounds__(512) bwd_reduce_kernel(const float* __restrict__ p_wpb, int n_cta,
+                                                         const float* __restrict__ p_g1, const float* __restrict__ p_g2,
+                                                         int n_blk, float* __restrict__ r_part) {
+  const int t = threadIdx.x, k = blockIdx.x;
+  const int c0 = (int)((int64_t)n_cta * k / kRedBlocks), c1 = (int)((int64_t)n_cta * (k + 1) / kRedBlocks);
+  float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
+  int c = c0;
+  for (; c + 3 < c1; c += 4) {
+    z0 += p_wpb[(size_t)c * 512 + t]; z1 += p_wpb[(size_t)(c + 1) * 512 + t];
+    z2 += p_wpb[(size_t)(c + 2) * 512 + t]; z3 += p_wpb[(size_t)(c + 3) * 512 + t];
+  }
+  for (; c < c1; ++c) z0 += p_wpb[(size_t)c * 512 + t];
+  r_part[(size_t)k * 528 + t] = (z0 + z1) + (z2 + z3);
+  if (t < 8) {
+    float g1 = 0.f;
+    for (int q = c0; q < c1; ++q) g1 += p_g1[(size_t)q * 8 + t];
+    r_part[(size_t)k * 528 + 512 + t] = g1;
+  } else if (t < 16) {
+    const int b0 = (int)((int64_t)n_blk * k / kRedBlocks), b1 = (int)((int64_t)n_blk * (k + 1) / kRedBlocks);
+    float g2 = 0.f;
+    for (int q = b0; q < b1; ++q) g2 += p_g2[(size_t)q * 8 + (t - 8)];
+    r_part[(size_t)k * 528 + 512 + t] = g2;
+  }
+}
+// Level 2: one block.  dWpb = st Z; dgamma = (sum dl l - sum dl ls - sum dl lb) / gamma.
+__global__ void __launch_bounds__(512) bwd_finalize_kernel(const float* __restrict__ r_part, const float* __restrict__ wpb,
                                                            const float* __restrict__ gamma, float* __restrict__ d_wpb,
                                                            float* __restrict__ d_gamma) {
   __shared__ float s_g3[512];
   const int t = threadIdx.x;   // = h * 64 + c
   const float st = rsqrtf(3.0f);
   float z = 0.f;
-  for (int k = 0; k < n_cta; ++k) z += p_wpb[(size_t)k * 512 + t];
+  for (int k = 0; k < kRedBlocks; ++k) z += r_part[(size_t)k * 528 + t];
   d_wpb[t] += st * z;
   s_g3[t] = st * wpb[t] * z;
   __syncthreads();
@@ -767,8 +753,7 @@ __global__ void __launch_bounds__(512) bwd_finalize_kernel(const float* __restri
     float g3 = 0.f;
     for (int c = 0; c < C; ++c) g3 += s_g3[t * C + c];
     float g1 = 0.f, g2 = 0.f;
-    for (int k = 0; k < n_cta; ++k) g1 += p_g1[(size_t)k * 8 + t];
-    for (int k = 0; k < n_blk; ++k) g2 += p_g2[(size_t)k * 8 + t];
+    for (int k = 0; k < kRedBlocks; ++k) { g1 += r_part[(size_t)k * 528 + 512 + t]; g2 += r_part[(size_t)k * 528 + 520 + t]; }
     const float gm = gamma[t];
     // lp = gamma * (dlp/dgamma)  =>  dgamma = sum dl lp / gamma (0 when gamma == 0: the point term is then absent)
     if (gm != 0.f) d_gamma[t] += (g1 - g2 - g3) / gm;
@@ -811,12 +796,8 @@ int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf1
   bwd_prep_kernel<<<M, 256, 0, s>>>(dcat, ws.cat, R, ws.tc, bw.dO16, bw.dObf, bw.dopair, bw.delta, bw.rscale);
   count_launch();
 
-  CUtensorMap mq, mk, mv, me, mdo, mdop;
+  CUtensorMap mv, me, mdo, mdop;
   {
-    uint64_t dqk[2] = {(uint64_t)H * QK_W, (uint64_t)M}, sqk[1] = {(uint64_t)H * QK_W * 2};
-    uint32_t bq[2] = {32, IB}, bk[2] = {32, L};
-    if (int rc = make_tensor_map_bf16(&mq, ws.Qp, 2, dqk, sqk, bq, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
-    if (int rc = make_tensor_map_bf16(&mk, ws.Kp, 2, dqk, sqk, bk, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
     uint64_t dv[2] = {(uint64_t)H * V_W, (uint64_t)M}, sv[1] = {(uint64_t)H * V_W * 2};
     uint32_t bv[2] = {V_W, L}, bdo[2] = {64, IB};
     if (int rc = make_tensor_map_bf16(&mv, ws.Vp, 2, dv, sv, bv, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
@@ -835,11 +816,11 @@ int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf1
     attr_done = true;
   }
   ipa_bwd_core_kernel<<<dim3(L / IB, B), 320, BwdSmem::kTotal, s>>>(
-      mq, mk, mv, me, mdo, mdop, ws.bias, ws.stats, bw.delta, bw.rscale, wpb, reinterpret_cast<__nv_bfloat16*>(de_bf16),
-      bw.Pn, bw.dL, bw.dQ, bw.p_wpb, bw.p_g1);
+      mv, me, mdo, mdop, ws.pu, ws.stats, bw.delta, bw.rscale, wpb, reinterpret_cast<__nv_bfloat16*>(de_bf16), bw.Pn,
+      bw.dL, bw.p_wpb, bw.p_g1, g_bwd_dbg);
   count_launch();
 
-  CUtensorMap mpn, mdl, mdob, mq64;
+  CUtensorMap mpn, mdl, mdob, mq64, mk64;
   {
     uint64_t dp[2] = {(uint64_t)L, (uint64_t)B * H * L}, sp_[1] = {(uint64_t)L * 2};
     uint32_t bp[2] = {64, L};
@@ -850,15 +831,24 @@ int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf1
     if (int rc = make_tensor_map_bf16(&mdob, bw.dObf, 2, dv, sv, bv, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     uint64_t dqk[2] = {(uint64_t)H * QK_W, (uint64_t)M}, sqk[1] = {(uint64_t)H * QK_W * 2};
     if (int rc = make_tensor_map_bf16(&mq64, ws.Qp, 2, dqk, sqk, bv, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_tensor_map_bf16(&mk64, ws.Kp, 2, dqk, sqk, bv, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
-  ipa_bwd_keyside_kernel<<<B * H, 160, KsSmem::kTotal, s>>>(mpn, mdl, mdob, mq64, bw.dK, bw.dV);
+  ipa_bwd_keyside_kernel<<<B * H, 160, KsSmem::kTotal, s>>>(mpn, mdl, mdob, mq64, mk64, bw.dQ, bw.dK, bw.dV);
   count_launch();
 
   bwd_assemble_kernel<<<M / 32, 256, 0, s>>>(bw.dQ, bw.dK, bw.dV, ws.Qp, ws.Kp, R, gamma, dproj, bw.p_g2);
   count_launch();
-  bwd_finalize_kernel<<<1, 512, 0, s>>>(bw.p_wpb, B * 8, bw.p_g1, bw.p_g2, M / 32, wpb, gamma, d_w_pair_bias, d_gamma);
+  bwd_reduce_kernel<<<kRedBlocks, 512, 0, s>>>(bw.p_wpb, B * 8, bw.p_g1, bw.p_g2, M / 32, bw.r_part);
+  count_launch();
+  bwd_finalize_kernel<<<1, 512, 0, s>>>(bw.r_part, wpb, gamma, d_w_pair_bias, d_gamma);
   count_launch();
   return check_launch("dab_ipa_bwd_sm100");
+}
+
+/* Profiling hook: per-CTA clock64 timeline of the backward core (64 slots per CTA), NULL to disable. */
+int dab_debug_set_bwd_timeline(long long* buf) {
+  g_bwd_dbg = buf;
+  return DAB_OK;
 }
 
 /* Test hook: the intermediate buffers of the last dab_ipa_bwd_sm100 call on `workspace` (device pointers). */

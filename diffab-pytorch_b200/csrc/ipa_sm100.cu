@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(320, 2)
 ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_e,
                 const uint4* __restrict__ bias, const float* __restrict__ tc, const float* __restrict__ R,
-                __nv_bfloat16* __restrict__ cat, float* __restrict__ stats, long long* __restrict__ dbg) {
+                __nv_bfloat16* __restrict__ cat, float* __restrict__ stats, uint4* __restrict__ pu,
+                long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // optional per-CTA timeline: slot k of CTA c at dbg[c * 64 + k]
   long long* dbg_cta = dbg ? dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
@@ -546,6 +547,9 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         float p[8];
 #pragma unroll
         for (int h = 0; h < H; ++h) p[h] = ex2(lg[r * 8 + h] - mx[r * 8 + h]);
+        if (pu)   // training: keep the un-normalised probabilities (bf16, [i][j][h]) for the backward
+          pu[(row0 + i) * L + gt] = make_uint4(pack_bf162(p[0], p[1]), pack_bf162(p[2], p[3]), pack_bf162(p[4], p[5]),
+                                               pack_bf162(p[6], p[7]));
         // the pair MMA that last read this P_i buffer (row n-2 of this group) must have completed
         if (n >= 2) mbar_wait(&bars[PAIR + g * 2 + (n & 1)], ((n >> 1) - 1) & 1);
         // ---- probabilities -> shared memory in the two operand layouts (K-major, 128B swizzle); neighbouring
@@ -845,7 +849,8 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
       attr_done = true;
     }
     ipa_core_kernel<<<dim3(L / IB, B), 320, CoreSmem::kTotal, s>>>(mq, mk, mv, me, bias, ws.tc, R, ws.cat,
-                                                                   save_for_bwd ? ws.stats : nullptr, g_core_dbg);
+                                                                   save_for_bwd ? ws.stats : nullptr,
+                                                                   save_for_bwd ? ws.pu : nullptr, g_core_dbg);
     count_launch();
   }
   if (phases & 4) {

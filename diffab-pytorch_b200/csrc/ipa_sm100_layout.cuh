@@ -59,6 +59,7 @@ struct Ws {
   float* tc;
   uint4* bias;   // fallback plane when the caller did not precompute the layer's pair bias
   float* stats;  // [rows][16]: row maxima (log2 units) [8 heads] | 1 / sum_j p [8 heads]; written for the backward
+  uint4* pu;     // [rows][128 j][8 h] bf16: un-normalised probabilities 2^(l - max), written for the backward
   size_t bytes;
 };
 inline Ws carve_ws(int B, void* base) {
@@ -73,6 +74,7 @@ inline Ws carve_ws(int B, void* base) {
   w.cat = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * NCAT * 2);
   w.bias = reinterpret_cast<uint4*>(p); p += al(rows * L * 16);
   w.stats = reinterpret_cast<float*>(p); p += al(rows * 16 * 4);
+  w.pu = reinterpret_cast<uint4*>(p); p += al(rows * L * 16);
   w.bytes = (size_t)(p - reinterpret_cast<uint8_t*>(base));
   return w;
 }

@@ -185,6 +185,7 @@ size_t dab_ipa_bwd_sm100_workspace_bytes(const DabIpaDims* d);
 int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf16, const float* R, const float* dcat,
                       void* saved, size_t saved_bytes, float* dproj, void* de_bf16, float* d_w_pair_bias, float* d_gamma,
                       void* workspace, size_t workspace_bytes, void* stream);
+int dab_debug_set_bwd_timeline(long long* device_buf /* 64 slots per CTA of the backward core, or NULL */);
 int dab_debug_bwd_sm100_buffers(const DabIpaDims* d, void* workspace, void** out /* 10 device pointers */);
 /* Test hooks of the sm_100a path (used by tests/ only): the tcgen05 GEMM C[M,N] = A[M,K] B[N,K]^T + bias
  * (bf16 in, fp32 out; M % 128 == 0, N % 64 == 0, K % 64 == 0) and the operand-packing stage alone. */
