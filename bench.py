@@ -301,7 +301,8 @@ def main():
         line["e2e"] = {"value": B / e2e_s, "unit": "patches/s", "h2d_bytes_per_step": h2d_bytes,
                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1000 * e2e_s, "n_gpus_measured": 1}
 
-        line["ipa_fwd_bwd"] = measure_ipa_fwd_bwd(dev)
+        line["ipa_fwd_bwd"] = measure_ipa_fwd_bwd_bf16(dev)
+        line["ipa_fwd_bwd"]["fp32_path"] = measure_ipa_fwd_bwd(dev)
 
         # ---- CPU baseline on this box's host cores ----------------------------------------------
         threads = os.cpu_count() or 1
@@ -396,6 +397,60 @@ def measure_ipa_fwd_bwd(dev, B=32, iters=5):
     us = a.elapsed_time(b_) * 1000 / iters
     alg = 3 * B * L * L * 64 * 4 + 6 * B * L * 128 * 4
     return {"metric": "IPA fwd+bwd us/layer (B=32, K=128, fp32)", "value": us, "unit": "us",
+            "algorithmic_bytes": alg, "hbm_roofline_us": alg / 6528.4e9 * 1e6}
+
+
+def measure_ipa_fwd_bwd_bf16(dev, B=32, iters=20):
+    """Secondary metric of BASELINE.json: one IPA layer fwd+bwd, B=32 patches x K=128 (config 2), bf16 pair tensor,
+    tensor-core kernels (dab_ipa_fwd_sm100_train / dab_ipa_bwd_sm100 + the four library GEMMs).  The whole
+    fwd+bwd is one CUDA graph; L2 is flushed (256 MB write) before every timed replay; also timed eagerly."""
+    from diffab_pytorch_b200 import synth
+    from diffab_pytorch_b200.diffab_pytorch import InvariantPointAttentionLayer
+    layer = InvariantPointAttentionLayer(128, 64, 32, 8, 8, 8).to(dev)
+    layer.load_state_dict(synth.synthetic_state(synth.ipa_layer_shapes(128, 64, 8, 32, 8, 8), seed=0))
+    x, e, R, t = (v.to(dev) for v in synth.make_ipa_inputs(B, L, 128, 64, seed=0))
+    x = x.requires_grad_(True)
+    e = e.to(torch.bfloat16).requires_grad_(True)
+    gy = torch.randn(B, L, 128, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        layer(x, e, R, t).backward(gy)
+
+    def clear():
+        x.grad = None; e.grad = None
+        for p in layer.parameters():
+            p.grad = None
+
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step(); clear()
+    torch.cuda.current_stream(dev).wait_stream(side)
+
+    def timed(fn):
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b_.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b_) * 1000)
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    eager_us = timed(lambda: (step(), clear()))
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    us = timed(graph.replay)
+    ok = bool(torch.isfinite(x.grad).all() and torch.isfinite(e.grad.float()).all())
+    del graph
+    clear()
+    alg = 3 * B * L * L * 64 * 2 + 6 * B * L * 128 * 4
+    return {"metric": "IPA fwd+bwd us/layer (B=32, K=128, bf16 pair tensor, tcgen05)", "value": us, "unit": "us",
+            "eager_us": eager_us, "cuda_graph": True, "l2": "256 MB flush before every replay", "finite": ok,
             "algorithmic_bytes": alg, "hbm_roofline_us": alg / 6528.4e9 * 1e6}
 
 

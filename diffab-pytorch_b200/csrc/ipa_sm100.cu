@@ -706,41 +706,131 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (warp == 0) tmem_free(tmem, kTmemCols);
 }
 
-// Pair bias of one layer for every (patch, i, j): bias[row i][j][h] = scale_total * log2(e) * sum_c e[i,j,c] Wpb[h,c]
-// (to_pair_bias, diffab_pytorch.py:423,439) stored as fp16.  The pair tensor is constant over the T sampling
-// steps, so this runs once per sampling run per layer, not once per step.  One thread per (i, j) pair reads its
-// 128-byte e row (coalesced 16 B vectors across the warp's consecutive j) against the weights in shared memory.
-__global__ void __launch_bounds__(128) ipa_pair_bias_kernel(const uint4* __restrict__ e, const float* __restrict__ wpb,
-                                                            uint4* __restrict__ bias, int64_t n_pairs) {
-  __shared__ float s_w[H * C];
-  const float st = rsqrtf(3.0f) * kLog2e;
-  for (int i = threadIdx.x; i < H * C; i += blockDim.x) s_w[i] = wpb[i] * st;
-  __syncthreads();
-  const int64_t pair = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pair >= n_pairs) return;
-  float acc[H];
-#pragma unroll
-  for (int h = 0; h < H; ++h) acc[h] = 0.f;
-  const uint4* ep = e + pair * (C * 2 / 16);
-#pragma unroll
-  for (int q = 0; q < C * 2 / 16; ++q) {
-    uint4 v = __ldg(ep + q);
-    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&v);
-    float f[8];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float2 t2 = __bfloat1622float2(b2[k]);
-      f[2 * k] = t2.x; f[2 * k + 1] = t2.y;
-    }
-#pragma unroll
-    for (int h = 0; h < H; ++h)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[h] = fmaf(f[k], s_w[h * C + q * 8 + k], acc[h]);
+// Pair bias of up to six layers in ONE pass over the pair tensor, on the tensor cores:
+//   plane_l[pair][h] = scale_total * log2(e) * sum_c e[pair, c] Wpb_l[h, c]      (fp16, [layer][B*L*L][8])
+// Persistent CTAs stream [128 pairs x 64 c] tiles by TMA (ring of four); one tcgen05.mma chain per tile
+// (M = 128 pairs, N = 16 * n_layers: the scaled weights as bf16 hi rows then bf16 lo rows, K = 64) into one of two
+// TMEM accumulators; thread = pair adds hi + lo and stores 16 bytes per layer (coalesced).
+struct BiasSmem {
+  static constexpr int kStage = 128 * C * 2;         // 16,384
+  static constexpr int kStages = 4;
+  static constexpr int kW = kStages * kStage;        // up to [96 rows][128 B] bf16, 128B-swizzled
+  static constexpr int kBars = kW + 96 * 128;
+  static constexpr int kTmemSlot = kBars + 16 * 8;
+  static constexpr int kTotal = kTmemSlot + 16;
+};
+__global__ void __launch_bounds__(192, 2)
+ipa_pair_bias_mma_kernel(const __grid_constant__ CUtensorMap map_e, const float* __restrict__ wpb /* [nl][8][64] */,
+                         int nl, uint4* __restrict__ planes, int64_t n_pairs, int n_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using S = BiasSmem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);   // full[4], empty[4], acc_full[2], acc_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem_base = smem_u32(smem);
+  if ((smem_base & 1023u) != 0) asm volatile("trap;");
+  const int N = 16 * nl;
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&bars[8], 1); mbar_init(&bars[9], 1);
+    mbar_init(&bars[10], 128); mbar_init(&bars[11], 128);
+    fence_barrier_init();
   }
-  bias[pair] = make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]), pack_h2(acc[4], acc[5]),
-                          pack_h2(acc[6], acc[7]));
+  {  // weights: row r < 8 nl = hi of (layer r / 8, head r % 8), rows 8 nl .. 16 nl = lo
+    const float sc = rsqrtf(3.0f) * kLog2e;
+    for (int i = tid; i < 8 * nl * (C / 2); i += blockDim.x) {
+      const int r = i / (C / 2), c2 = (i % (C / 2)) * 2;
+      const float a = wpb[r * C + c2] * sc, bq = wpb[r * C + c2 + 1] * sc;
+      const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(bq));
+      *reinterpret_cast<uint32_t*>(smem + S::kW + swz128_offset(r, c2 >> 3) + (c2 & 7) * 2) = pack_bf162(ah, bh);
+      *reinterpret_cast<uint32_t*>(smem + S::kW + swz128_offset(8 * nl + r, c2 >> 3) + (c2 & 7) * 2) =
+          pack_bf162(a - ah, bq - bh);
+    }
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  tcgen05_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const int n_mine = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map_e);
+      for (int k = 0; k < n_mine; ++k) {
+        const int s = k % S::kStages;
+        if (k >= S::kStages) mbar_wait(&bars[4 + s], ((k / S::kStages) - 1) & 1);
+        mbar_arrive_expect_tx(&bars[s], S::kStage);
+        tma_load_2d(smem + s * S::kStage, &map_e, &bars[s], 0, (int)(((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * 128));
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+      for (int k = 0; k < n_mine; ++k) {
+        const int s = k % S::kStages, acc = k & 1;
+        mbar_wait(&bars[s], (k / S::kStages) & 1);
+        if (k >= 2) mbar_wait(&bars[10 + acc], ((k >> 1) - 1) & 1);
+        tcgen05_fence_after_sync();
+#pragma unroll
+        for (int kk = 0; kk < C / 16; ++kk) {
+          uint64_t da = make_smem_desc(smem_base + s * S::kStage + kk * 32, 16, 1024, kSwizzle128B);
+          uint64_t db = make_smem_desc(smem_base + S::kW + kk * 32, 16, 1024, kSwizzle128B);
+          umma_bf16(tmem + acc * 128, da, db, idesc, kk != 0);
+        }
+        umma_commit(&bars[4 + s]);
+        umma_commit(&bars[8 + acc]);
+      }
+    }
+  } else {
+    const uint32_t tmem_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int k = 0; k < n_mine; ++k) {
+      const int acc = k & 1;
+      const int64_t pair = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * 128 + tid;
+      mbar_wait(&bars[8 + acc], (k >> 1) & 1);
+      tcgen05_fence_after_sync();
+      for (int l0 = 0; l0 < nl; l0 += 2) {   // two layers per pass: 16 hi + 16 lo columns
+        float hi[16], lo[16];
+        tmem_ld_x16(tmem_lane + acc * 128 + l0 * 8, hi);
+        tmem_ld_x16(tmem_lane + acc * 128 + 8 * nl + l0 * 8, lo);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (l0 + q < nl && pair < n_pairs)
+            planes[(int64_t)(l0 + q) * n_pairs + pair] =
+                make_uint4(pack_h2(hi[8 * q] + lo[8 * q], hi[8 * q + 1] + lo[8 * q + 1]),
+                           pack_h2(hi[8 * q + 2] + lo[8 * q + 2], hi[8 * q + 3] + lo[8 * q + 3]),
+                           pack_h2(hi[8 * q + 4] + lo[8 * q + 4], hi[8 * q + 5] + lo[8 * q + 5]),
+                           pack_h2(hi[8 * q + 6] + lo[8 * q + 6], hi[8 * q + 7] + lo[8 * q + 7]));
+        }
+      }
+      tcgen05_fence_before_sync();
+      mbar_arrive(&bars[10 + acc]);
+    }
+  }
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_free(tmem, 256);
 }
 
+static int launch_pair_bias(const void* e_bf16, const float* wpb, int nl, void* planes, int64_t n_pairs, cudaStream_t s) {
+  CUtensorMap me;
+  uint64_t de[2] = {(uint64_t)C, (uint64_t)n_pairs}, se[1] = {(uint64_t)C * 2};
+  uint32_t be[2] = {C, 128};
+  if (int rc = make_tensor_map_bf16(&me, e_bf16, 2, de, se, be, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(ipa_pair_bias_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BiasSmem::kTotal);
+    attr_done = true;
+  }
+  const int n_tiles = (int)((n_pairs + 127) / 128);
+  const int grid = n_tiles < 296 ? n_tiles : 296;
+  ipa_pair_bias_mma_kernel<<<grid, 192, BiasSmem::kTotal, s>>>(me, wpb, nl, reinterpret_cast<uint4*>(planes), n_pairs,
+                                                               n_tiles);
+  count_launch();
+  return DAB_OK;
+}
 
 }  // namespace sm100
 }  // namespace dab
@@ -782,13 +872,28 @@ int dab_ipa_pair_bias(const DabIpaDims* d, const void* e_bf16, const float* w_pa
   DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
               "dab_ipa_pair_bias: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
   if (d->B == 0) return DAB_OK;
-  DAB_REQUIRE(e_bf16 && w_pair_bias && bias_f16 && aligned16(e_bf16) && aligned16(bias_f16), DAB_EINVAL,
-              "dab_ipa_pair_bias: null or misaligned pointer");
+  DAB_REQUIRE(e_bf16 && w_pair_bias && bias_f16 && (reinterpret_cast<uintptr_t>(e_bf16) & 127) == 0 &&
+                  aligned16(bias_f16),
+              DAB_EINVAL, "dab_ipa_pair_bias: null or misaligned pointer (e 128 B, bias 16 B)");
   const int64_t n_pairs = (int64_t)d->B * L * L;
-  ipa_pair_bias_kernel<<<(unsigned)((n_pairs + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4*>(e_bf16), w_pair_bias, reinterpret_cast<uint4*>(bias_f16), n_pairs);
-  count_launch();
+  if (int rc = launch_pair_bias(e_bf16, w_pair_bias, 1, bias_f16, n_pairs, (cudaStream_t)stream)) return rc;
   return check_launch("dab_ipa_pair_bias");
+}
+
+/* Same for n_layers <= 6 layers in one pass over the pair tensor: w_pair_bias[n_layers][8][64] fp32 (contiguous),
+ * planes_f16[n_layers][B*L*L][8] fp16 (contiguous). */
+int dab_ipa_pair_bias_multi(const DabIpaDims* d, const void* e_bf16, const float* w_pair_bias, int n_layers,
+                            void* planes_f16, void* stream) {
+  DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
+              "dab_ipa_pair_bias_multi: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
+  DAB_REQUIRE(n_layers >= 1 && n_layers <= 6, DAB_EUNSUPPORTED, "dab_ipa_pair_bias_multi: 1 <= n_layers <= 6");
+  if (d->B == 0) return DAB_OK;
+  DAB_REQUIRE(e_bf16 && w_pair_bias && planes_f16 && (reinterpret_cast<uintptr_t>(e_bf16) & 127) == 0 &&
+                  aligned16(planes_f16),
+              DAB_EINVAL, "dab_ipa_pair_bias_multi: null or misaligned pointer");
+  const int64_t n_pairs = (int64_t)d->B * L * L;
+  if (int rc = launch_pair_bias(e_bf16, w_pair_bias, n_layers, planes_f16, n_pairs, (cudaStream_t)stream)) return rc;
+  return check_launch("dab_ipa_pair_bias_multi");
 }
 
 static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
@@ -826,10 +931,8 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
   if (phases & 2) {
     const uint4* bias = reinterpret_cast<const uint4*>(bias_f16);
     if (bias == nullptr) {   // one-off call without a precomputed bias: build this layer's plane now
-      const int64_t n_pairs = (int64_t)M * L;
-      ipa_pair_bias_kernel<<<(unsigned)((n_pairs + 127) / 128), 128, 0, s>>>(
-          reinterpret_cast<const uint4*>(e_bf16), reinterpret_cast<const float*>(pk + po.wpb), ws.bias, n_pairs);
-      count_launch();
+      if (int rc = launch_pair_bias(e_bf16, reinterpret_cast<const float*>(pk + po.wpb), 1, ws.bias, (int64_t)M * L, s))
+        return rc;
       bias = ws.bias;
     }
     CUtensorMap mq, mk, mv, me;
@@ -868,10 +971,11 @@ int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, c
 }
 
 /* Training forward: same launches; the workspace additionally keeps what dab_ipa_bwd_sm100 needs (packed operands,
- * concat features, the layer's pair-bias plane and the softmax statistics) and must be handed to it untouched. */
+ * concat features, un-normalised probabilities and the softmax statistics) and must be handed to it untouched. */
 int dab_ipa_fwd_sm100_train(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
-                            const float* R, const float* t, float* y, void* saved, size_t saved_bytes, void* stream) {
-  return fwd_sm100_impl(d, packed, x, e_bf16, nullptr, R, t, y, saved, saved_bytes, true, stream);
+                            const void* bias_f16, const float* R, const float* t, float* y, void* saved,
+                            size_t saved_bytes, void* stream) {
+  return fwd_sm100_impl(d, packed, x, e_bf16, bias_f16, R, t, y, saved, saved_bytes, true, stream);
 }
 
 /* Profiling hook: per-CTA clock64 timeline of the attention core (64 slots per CTA), NULL to disable. */

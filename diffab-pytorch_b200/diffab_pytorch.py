@@ -241,7 +241,7 @@ class _IpaFastFunction(torch.autograd.Function):
     GEMMs (TF32); everything between them runs in the library's tcgen05 kernels."""
 
     @staticmethod
-    def forward(ctx, layer, x, e, r, t, *weights):
+    def forward(ctx, layer, pair_bias, x, e, r, t, *weights):
         x = _lib.dev(x, torch.float32, "x")
         e = _lib.dev(e, torch.bfloat16, "e")
         r = _lib.dev(r, torch.float32, "r")
@@ -253,8 +253,13 @@ class _IpaFastFunction(torch.autograd.Function):
         nbytes = lib.dab_ipa_sm100_workspace_bytes(ctypes.byref(dims))
         saved = torch.empty(max(nbytes, 16), device=x.device, dtype=torch.uint8)   # private: kept for the backward
         y = torch.empty(B, L, D, device=x.device, dtype=torch.float32)
-        _lib.check(lib.dab_ipa_fwd_sm100_train(ctypes.byref(dims), ptr(packed), ptr(x), ptr(e), ptr(r), ptr(t), ptr(y),
-                                               ptr(saved), saved.numel(), _lib.stream_ptr()), "dab_ipa_fwd_sm100_train")
+        if pair_bias is not None:
+            pair_bias = _lib.dev(pair_bias, torch.float16, "pair_bias")
+            if tuple(pair_bias.shape) != (B, L, L, layer.n_head):
+                raise ValueError(f"pair_bias shape {tuple(pair_bias.shape)} != {(B, L, L, layer.n_head)}")
+        _lib.check(lib.dab_ipa_fwd_sm100_train(ctypes.byref(dims), ptr(packed), ptr(x), ptr(e), ptr(pair_bias), ptr(r),
+                                               ptr(t), ptr(y), ptr(saved), saved.numel(), _lib.stream_ptr()),
+                   "dab_ipa_fwd_sm100_train")
         ctx.save_for_backward(x, e, r, saved, packed, *[w.detach() for w in weights])
         ctx.layer = layer
         return y
@@ -263,7 +268,7 @@ class _IpaFastFunction(torch.autograd.Function):
     def backward(ctx, dy):
         x, e, r, saved, packed, *weights = ctx.saved_tensors
         layer = ctx.layer
-        if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
+        if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
             raise NotImplementedError("gradients w.r.t. the frames (r, t) are not provided: in DiffAb they are the "
                                       "noised frames and carry no gradient (diffab_pytorch.py:824-854)")
         B, L, D = x.shape
@@ -295,7 +300,7 @@ class _IpaFastFunction(torch.autograd.Function):
             dx = (dproj @ w_cat).view(B, L, D)
             d_w_cat = dproj.t() @ x.view(M, D)
         d_proj_w = torch.split(d_w_cat, [w.shape[0] for w in weights[:6]], dim=0)
-        return (None, dx, de, None, None, *d_proj_w, d_wpb, d_gamma, d_w_out, d_b_out)
+        return (None, None, dx, de, None, None, *d_proj_w, d_wpb, d_gamma, d_w_out, d_b_out)
 
 
 class InvariantPointAttentionLayer(nn.Module):
@@ -391,7 +396,7 @@ class InvariantPointAttentionLayer(nn.Module):
             if not self.fast_path_supported(x.shape[1]):
                 raise RuntimeError("bf16 pair tensor given but the sm_100a path only supports the train.py "
                                    "configuration (L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8)")
-            return _IpaFastFunction.apply(self, x, e_bf16, r, t, *self._weights())
+            return _IpaFastFunction.apply(self, pair_bias, x, e_bf16, r, t, *self._weights())
         x = _lib.dev(x, torch.float32, "x")
         e = _lib.dev(e_bf16, torch.bfloat16, "e")
         r = _lib.dev(r, torch.float32, "r")
@@ -426,6 +431,11 @@ class InvariantPointAttentionModule(nn.Module):
                                          n_value_point_per_head, n_head) for _ in range(n_layers)])
 
     def forward(self, res_emb, pair_emb, orientations, translations, pair_bias=None):
+        if (pair_bias is None and pair_emb.dtype == torch.bfloat16 and
+                self.layers[0].fast_path_supported(pair_emb.shape[1])):
+            # tensor-core path: the bias planes of all layers in one pass over the pair tensor (their gradient
+            # w.r.t. to_pair_bias and the pair tensor is produced by the layers' own backward kernels)
+            pair_bias = self.precompute_pair_bias(pair_emb.detach())
         for k, layer in enumerate(self.layers):
             if pair_bias is not None:
                 res_emb = layer(res_emb, pair_emb, orientations, translations, pair_bias[k])
@@ -433,9 +443,26 @@ class InvariantPointAttentionModule(nn.Module):
                 res_emb = layer(res_emb, pair_emb, orientations, translations)
         return res_emb
 
-    def precompute_pair_bias(self, pair_emb_bf16):
-        """Per-layer pair-bias planes for the sm_100a path (once per sampling run)."""
-        return [layer.pair_bias(pair_emb_bf16) for layer in self.layers]
+    def precompute_pair_bias(self, pair_emb_bf16, out=None):
+        """Per-layer pair-bias planes for the sm_100a path: one pass over the pair tensor for all layers
+        (once per sampling run / once per training step).  Returns a list of (B, L, L, H) fp16 views of one
+        (n_layers, B, L, L, H) tensor (``out`` if given)."""
+        e = _lib.dev(pair_emb_bf16, torch.bfloat16, "e")
+        B, L = e.shape[0], e.shape[1]
+        n, H = len(self.layers), self.layers[0].n_head
+        if out is None:
+            out = torch.empty(n, B, L, L, H, device=e.device, dtype=torch.float16)
+        elif out.dtype != torch.float16 or tuple(out.shape) != (n, B, L, L, H) or not out.is_contiguous():
+            raise ValueError("precompute_pair_bias: `out` must be a contiguous fp16 (n_layers, B, L, L, H) tensor")
+        lib = _lib.lib()
+        dims = _ipa_structs(self.layers[0], B, L)
+        for lo in range(0, n, 6):   # the kernel takes up to six layers per pass
+            hi = min(n, lo + 6)
+            w = torch.stack([_lib.dev(l.to_pair_bias.weight.detach(), torch.float32, "to_pair_bias.weight")
+                             for l in self.layers[lo:hi]]).contiguous()
+            _lib.check(lib.dab_ipa_pair_bias_multi(ctypes.byref(dims), ptr(e), ptr(w), hi - lo, ptr(out[lo:hi]),
+                                                   _lib.stream_ptr()), "dab_ipa_pair_bias_multi")
+        return list(out.unbind(0))
 
 
 def cast_pair_to_bf16(pair_emb):
@@ -599,7 +626,9 @@ class DiffAb(nn.Module):
 
     def _shared_step(self, batch, batch_idx, t=None, noise=None):
         """diffab_pytorch.py:808-880.  ``t`` / ``noise`` may be injected (tests); otherwise drawn on the
-        device in the reference's order (#1 t, then the six noising draws)."""
+        device in the reference's order (#1 t, then the six noising draws).  ``self.train_precision``
+        ("fp32" default, "bf16") picks the IPA path: with "bf16" the pair embedding is cast once per step and
+        the six IPA layers run forward and backward on the tensor-core kernels."""
         device = batch["generation_mask"].device
         bsz = batch["generation_mask"].size(0)
         if t is None:
@@ -615,9 +644,14 @@ class DiffAb(nn.Module):
             seq_idx_t0, xyz_t0, orientations_t0, batch["backbone_dihedrals"], batch["distmat"],
             batch["pairwise_dihedrals"], batch["atom_mask"], batch["chain_idx"], batch["residue_idx"],
             batch["generation_mask"], batch["residue_mask"])
-        denoised = self.denoise(noised["seq_idx_t"], noised["translations_t"], noised["orientations_t"],
-                                res_context_emb, pair_context_emb, beta, batch["generation_mask"],
-                                batch["residue_mask"])
+        bf16 = (getattr(self, "train_precision", "fp32") == "bf16" and
+                self.denoiser.ipa.layers[0].fast_path_supported(pair_context_emb.shape[1]))
+        if bf16:
+            pair_context_emb = pair_context_emb.to(torch.bfloat16)   # autograd-aware cast (grad comes back as bf16)
+        with _tf32_matmuls(bf16):
+            denoised = self.denoise(noised["seq_idx_t"], noised["translations_t"], noised["orientations_t"],
+                                    res_context_emb, pair_context_emb, beta, batch["generation_mask"],
+                                    batch["residue_mask"])
         return self._losses(denoised, noised, batch["orientations"], batch["generation_mask"], batch["residue_mask"])
 
     def training_step(self, batch, batch_idx):
@@ -717,9 +751,9 @@ class DiffAb(nn.Module):
         if pair_ctx.dtype == torch.bfloat16:   # per-layer pair-bias planes, written straight into the static buffers
             layers = self.denoiser.ipa.layers
             if st["bias"] is None:
-                st["bias"] = [torch.empty(B, L, L, l.n_head, device=dev, dtype=torch.float16) for l in layers]
-            for l, plane in zip(layers, st["bias"]):
-                l.pair_bias(st["pair"], out=plane)
+                st["bias_all"] = torch.empty(len(layers), B, L, L, layers[0].n_head, device=dev, dtype=torch.float16)
+                st["bias"] = list(st["bias_all"].unbind(0))
+            self.denoiser.ipa.precompute_pair_bias(st["pair"], out=st["bias_all"])
         if fresh:
             st["s"].copy_(s); st["x"].copy_(x); st["O"].copy_(O)
             side = torch.cuda.Stream(device=dev)

@@ -163,15 +163,21 @@ size_t dab_ipa_sm100_workspace_bytes(const DabIpaDims* d);
  * scale_total * log2(e) * e . w_pair_bias^T (to_pair_bias, diffab_pytorch.py:423,439).  The pair tensor is
  * constant over the T reverse steps, so this is computed once per sampling run per layer. */
 int dab_ipa_pair_bias(const DabIpaDims* d, const void* e_bf16, const float* w_pair_bias, void* bias_f16, void* stream);
+/* Same for n_layers <= 6 layers in ONE pass over the pair tensor (the six layers of the epsilon network share it):
+ * w_pair_bias[n_layers][8][64] fp32 contiguous, planes_f16[n_layers][B*L*L][8] fp16 contiguous. */
+int dab_ipa_pair_bias_multi(const DabIpaDims* d, const void* e_bf16, const float* w_pair_bias, int n_layers,
+                            void* planes_f16, void* stream);
 /* bias_f16: the layer's plane from dab_ipa_pair_bias, or NULL (then it is rebuilt inside the call). */
 int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
                       const void* bias_f16, const float* R, const float* t, float* y, void* workspace,
                       size_t workspace_bytes, void* stream);
-/* Training pair of the sm_100a path (bf16 pair tensor, fp32 x / y).  The forward is dab_ipa_fwd_sm100 with the
- * pair bias rebuilt inside the call; `saved` (dab_ipa_sm100_workspace_bytes) additionally keeps the packed
- * operands, the concat features, the bias plane and the softmax statistics, and must reach the backward untouched. */
+/* Training pair of the sm_100a path (bf16 pair tensor, fp32 x / y).  The forward is dab_ipa_fwd_sm100 (the pair
+ * bias is rebuilt inside the call when bias_f16 is NULL); `saved` (dab_ipa_sm100_workspace_bytes) additionally keeps
+ * the packed operands, the concat features, the un-normalised probabilities and the softmax statistics, and must
+ * reach the backward untouched. */
 int dab_ipa_fwd_sm100_train(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
-                            const float* R, const float* t, float* y, void* saved, size_t saved_bytes, void* stream);
+                            const void* bias_f16 /* plane of this layer or NULL */, const float* R, const float* t,
+                            float* y, void* saved, size_t saved_bytes, void* stream);
 /* Backward of the attention part of the layer (autograd of diffab_pytorch.py:389-462) on tcgen05:
  *   in : dcat[B*L,1024] fp32 = dy . to_out.weight (gradient of the concat features; a plain GEMM of the caller),
  *        e_bf16, R, `saved` from dab_ipa_fwd_sm100_train, `packed` weights;

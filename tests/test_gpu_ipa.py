@@ -162,3 +162,20 @@ def test_tensor_core_backward_rejects_frame_grads():
     y = layer(x.to(DEV).requires_grad_(True), e.to(torch.bfloat16).to(DEV), R.to(DEV), tt)
     with pytest.raises(NotImplementedError):
         y.sum().backward()
+
+
+def test_pair_bias_planes_single_pass_for_all_layers():
+    """dab_ipa_pair_bias_multi: the planes of six layers from one pass over the pair tensor (tensor cores, weights
+    as bf16 hi + lo) against e . Wpb^T in fp64; and the single-layer entry point gives the same bits."""
+    torch.manual_seed(0)
+    B = 2
+    mod = InvariantPointAttentionModule(6, 128, 64, 32, 8, 8, 8).to(DEV)
+    e = torch.randn(B, 128, 128, 64, device=DEV).bfloat16()
+    planes = mod.precompute_pair_bias(e)
+    assert len(planes) == 6
+    sc = 3 ** -0.5 * 1.4426950408889634
+    for k, layer in enumerate(mod.layers):
+        ref = torch.einsum("bijc,hc->bijh", e.double(), layer.to_pair_bias.weight.detach().double()) * sc
+        assert planes[k].dtype == torch.float16 and planes[k].shape == (B, 128, 128, 8)
+        assert float((planes[k].double() - ref).abs().max()) < 2e-3 * float(ref.abs().max())   # fp16 storage
+        assert torch.equal(layer.pair_bias(e), planes[k])

@@ -153,3 +153,35 @@ def test_sample_end_to_end_graph_and_eager():
         assert torch.isfinite(out["translations"]).all()
     with pytest.raises(ValueError):
         model.sample(batch["seq_idx"], batch["xyz"], batch["orientations"])
+
+
+def test_bf16_training_step_matches_fp32_path():
+    """_shared_step with train_precision="bf16" (six tensor-core IPA layers forward + backward, pair embedding cast
+    once, bias planes of all layers from one pass) against the fp32 kernels under the same injected draws.
+    The per-layer gradient bar (2e-2 max-normalised) is tests/test_gpu_ipa.py; through the whole randomly
+    initialised network (six chained IPA layers, no normalisation, sharply peaked attention) gradients are
+    ill-conditioned - merely switching the glue GEMMs of the fp32 path to TF32 moves them by up to 19 %
+    max-normalised (tools/chk_bf16_step.py) - so this test asks for: losses within 2e-2 relative, every gradient
+    finite and aligned with the fp32 gradient (cosine >= 0.97; measured >= 0.986)."""
+    g = load_golden("shared_step.pt")
+    batch = _to(synth.make_patches(2, 128, seed=g["seed_patches"]))
+    torch.manual_seed(g["seed_step"])
+    t = torch.randint(low=1, high=101, size=(2,)).to(DEV)
+    noise = _to(odiff.draw_add_noise_tensors(2, 128))
+    grads, losses = {}, {}
+    for prec in ("fp32", "bf16"):
+        model = _model(g["seed_state"]).train()
+        model.train_precision = prec
+        model.zero_grad()
+        ls = model._shared_step(batch, 0, t=t, noise=noise)
+        sum(ls).backward()
+        losses[prec] = torch.stack(ls).detach().cpu()
+        grads[prec] = {n: p.grad.detach().cpu().double().flatten() for n, p in model.named_parameters()
+                       if p.grad is not None}
+    assert torch.allclose(losses["bf16"], losses["fp32"], rtol=2e-2), (losses["bf16"], losses["fp32"])
+    assert set(grads["bf16"]) == set(grads["fp32"])
+    for n, ref in grads["fp32"].items():
+        got = grads["bf16"][n]
+        assert torch.isfinite(got).all(), n
+        cos = float(got @ ref / (got.norm() * ref.norm()).clamp_min(1e-300))
+        assert cos >= 0.97, (n, cos)
