@@ -21,6 +21,7 @@
 #include <cuda_fp16.h>
 
 #include <mutex>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_sm100.cuh"
@@ -324,7 +325,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_e,
                 const uint4* __restrict__ bias, const float* __restrict__ tc, const float* __restrict__ R,
                 __nv_bfloat16* __restrict__ cat, float* __restrict__ stats, uint4* __restrict__ pu,
-                long long* __restrict__ dbg) {
+                long long* __restrict__ dbg, const uint8_t* __restrict__ xk, const uint8_t* __restrict__ xv) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // optional per-CTA timeline: slot k of CTA c at dbg[c * 64 + k]
   long long* dbg_cta = dbg ? dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
@@ -366,6 +367,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int s = h % S::kKBufs;
         uint8_t* kb = smem + s * S::kKBuf;
         mbar_arrive_expect_tx(&bars[K_FULL + s], S::kKBuf);
+        if (xk) { bulk_load_1d(kb, xk + ((size_t)b * H + h) * S::kKBuf, S::kKBuf, &bars[K_FULL + s]); return; }
         for (int blk = 0; blk < 3; ++blk)
           tma_load_2d(kb + blk * (L * 64), &map_k, &bars[K_FULL + s], (h * 3 + blk) * 32, b * L);
       };
@@ -396,6 +398,8 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int s = h % S::kVBufs;
         if (h >= S::kVBufs) mbar_wait(&bars[V_EMPTY + s], ((h / S::kVBufs) - 1) & 1);
         mbar_arrive_expect_tx(&bars[V_FULL + s], S::kVBuf);
+        if (xv) bulk_load_1d(smem + s * S::kVBuf, xv + ((size_t)b * H + h) * S::kVBuf, S::kVBuf, &bars[V_FULL + s]);
+        else
         tma_load_2d(smem + s * S::kVBuf, &map_v, &bars[V_FULL + s], h * V_W, b * L);
       }
     }
@@ -403,14 +407,15 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // ======================================= MMA issuer =======================================
     if (lane == 0) {
       constexpr uint32_t kIdescS = make_idesc_bf16(128, 16, 0, 0);     // S^T
-      constexpr uint32_t kIdescPair = make_idesc_bf16(64, 8, 1, 0);    // A = e tile, MN-major
-      constexpr uint32_t kIdescO = make_idesc_f16(64, 16, 1, 0);       // A = V tile, MN-major, fp16 operands
+      constexpr uint32_t kIdescPair = make_idesc_bf16(128, 16, 1, 0);  // A = two e tiles, MN-major
+      constexpr uint32_t kIdescO = make_idesc_f16(128, 32, 1, 0);      // A = two V tiles, MN-major, fp16 operands
       // ---- stage 1: S^T_h = K_h Q_h^T for the 8 heads
       mbar_wait(&bars[Q_FULL], 0);
       for (int h = 0; h < H; ++h) {
         const int s = h % S::kKBufs;
         mbar_wait(&bars[K_FULL + s], (h / S::kKBufs) & 1);
         tcgen05_fence_after_sync();
+        DAB_STAMP_ISSUER(48 + h);
         const uint32_t ka = smem_base + s * S::kKBuf;
         const uint32_t qa = smem_base + S::kQOff + h * 3 * (IB * 64);
 #pragma unroll
@@ -428,45 +433,55 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       umma_commit(&bars[S_DONE]);
       DAB_STAMP_ISSUER(2);
-      // ---- stage 2: pair_i^T = e[i]^T P_i^T as soon as a group has published the probabilities of row i
-      for (int i = 0; i < IB; ++i) {
-        const int st = i % S::kEStages;
-        if (i == 8) DAB_STAMP_ISSUER(40);
-        mbar_wait(&bars[E_FULL + st], (i / S::kEStages) & 1);
-        if (i == 8) DAB_STAMP_ISSUER(41);
-        // one barrier per (group, P_i buffer): a group may run a row ahead of the issuer, and a shared barrier
-        // would then be two phases ahead of this wait (parity aliasing)
-        mbar_wait(&bars[P_READY + (i & 1) * 2 + ((i >> 1) & 1)], (i >> 2) & 1);
+      // ---- stage 2: pair aggregation of TWO rows per MMA chain (rows 2n and 2n+1, one from each softmax group):
+      //      [pair_2n ; pair_2n+1]^T = [e[2n] | e[2n+1]]^T [P_2n ; P_2n+1]^T  (M = 128: 64 channels of each row,
+      //      N = 16: 8 heads of each row, K = 128 j).  The two off-diagonal blocks (row 2n channels x row 2n+1
+      //      probabilities and vice versa) are computed and ignored: a small tcgen05.mma costs the same ~90 cycles
+      //      whatever its shape, so halving the instruction count is what matters.
+      for (int n = 0; n < IB / 2; ++n) {
+        const int st = (2 * n) % S::kEStages;     // rows 2n, 2n+1 sit in consecutive ring stages
+        const int slot = n & 1;
+        if (n == 4) DAB_STAMP_ISSUER(40);
+        mbar_wait(&bars[E_FULL + st], ((2 * n) / S::kEStages) & 1);
+        mbar_wait(&bars[E_FULL + st + 1], ((2 * n) / S::kEStages) & 1);
+        if (n == 4) DAB_STAMP_ISSUER(41);
+        mbar_wait(&bars[P_READY + slot], (n >> 1) & 1);          // group 0, row 2n
+        mbar_wait(&bars[P_READY + 2 + slot], (n >> 1) & 1);      // group 1, row 2n + 1
         tcgen05_fence_after_sync();
-        if (i == 8) DAB_STAMP_ISSUER(42);
-        const int slot = (i >> 1) & 1;   // each group alternates between two P_i buffers
+        if (n == 4) DAB_STAMP_ISSUER(42);
         const uint32_t ea = smem_base + st * S::kEStage;
-        const uint32_t pa = smem_base + (slot ? S::kPi2 : S::kPi) + (i & 1) * 2048;
+        const uint32_t pa = smem_base + (slot ? S::kPi2 : S::kPi);
 #pragma unroll
         for (int k = 0; k < L / 16; ++k) {
-          // A: e[i] tile [j][c] read MN-major (M = c: one 128 B row; K = j: 16 rows = 2048 B per step)
-          uint64_t da = make_smem_desc(ea + k * 2048, 1024, 1024, kSwizzle128B);
-          uint64_t db = make_smem_desc(pa + (k >> 2) * 1024 + (k & 3) * 32, 16, 1024, kSwizzle128B);
-          umma_bf16(tmem + kColPair + i * 8, da, db, kIdescPair, k != 0);
+          // A: two e tiles [j][c] read MN-major: M = 128 = two 64-wide atoms one ring stage apart (LBO);
+          //    K = j: 16 rows = 2048 B per step, 8-row groups 1024 B apart (SBO)
+          uint64_t da = make_smem_desc(ea + k * 2048, S::kEStage, 1024, kSwizzle128B);
+          uint64_t db = make_smem_desc(pa + (k >> 2) * 2048 + (k & 3) * 32, 16, 1024, kSwizzle128B);
+          umma_bf16(tmem + kColPair + n * 16, da, db, kIdescPair, k != 0);
         }
-        umma_commit(&bars[PAIR + (i & 1) * 2 + slot]);
+        umma_commit(&bars[PAIR + slot]);
         umma_commit(&bars[E_EMPTY + st]);
-        if (i == 8) DAB_STAMP_ISSUER(43);
+        umma_commit(&bars[E_EMPTY + st + 1]);
+        if (n == 4) DAB_STAMP_ISSUER(43);
       }
       DAB_STAMP_ISSUER(3);
-      // ---- stage 3: O^T_h = [Vs|Vp]_h^T P_h^T (all P_h rows are published: P_READY of row 15 has been seen)
-      for (int h = 0; h < H; ++h) {
-        const int s = h % S::kVBufs;
-        mbar_wait(&bars[V_FULL + s], (h / S::kVBufs) & 1);
+      // ---- stage 3: O^T of TWO heads per MMA chain: [O_2m ; O_2m+1]^T = [V_2m | V_2m+1]^T [P_2m ; P_2m+1]^T
+      //      (M = 128: 64 value columns of each head, N = 32: 16 rows of each head, K = 128 j)
+      for (int m = 0; m < H / 2; ++m) {
+        const int s = (2 * m) % S::kVBufs;
+        mbar_wait(&bars[V_FULL + s], ((2 * m) / S::kVBufs) & 1);
+        mbar_wait(&bars[V_FULL + s + 1], ((2 * m) / S::kVBufs) & 1);
         tcgen05_fence_after_sync();
-        const uint32_t va = smem_base + s * S::kVBuf, pa = smem_base + S::kPh + h * (2 * IB * 128);
+        DAB_STAMP_ISSUER(56 + m);
+        const uint32_t va = smem_base + s * S::kVBuf, pa = smem_base + S::kPh + (2 * m) * (IB * 128);
 #pragma unroll
         for (int k = 0; k < L / 16; ++k) {
-          uint64_t da = make_smem_desc(va + k * 2048, 1024, 1024, kSwizzle128B);
-          uint64_t db = make_smem_desc(pa + (k >> 2) * (IB * 128) + (k & 3) * 32, 16, 1024, kSwizzle128B);
-          umma_bf16(tmem + kColS + h * 16, da, db, kIdescO, k != 0);
+          uint64_t da = make_smem_desc(va + k * 2048, S::kVBuf, 1024, kSwizzle128B);
+          uint64_t db = make_smem_desc(pa + (k >> 2) * (H * IB * 128) + (k & 3) * 32, 16, 1024, kSwizzle128B);
+          umma_bf16(tmem + kColS + m * 32, da, db, kIdescO, k != 0);
         }
         umma_commit(&bars[V_EMPTY + s]);
+        umma_commit(&bars[V_EMPTY + s + 1]);
       }
       umma_commit(&bars[O_DONE]);
     }
@@ -551,15 +566,15 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           pu[(row0 + i) * L + gt] = make_uint4(pack_bf162(p[0], p[1]), pack_bf162(p[2], p[3]), pack_bf162(p[4], p[5]),
                                                pack_bf162(p[6], p[7]));
         // the pair MMA that last read this P_i buffer (row n-2 of this group) must have completed
-        if (n >= 2) mbar_wait(&bars[PAIR + g * 2 + (n & 1)], ((n >> 1) - 1) & 1);
+        if (n >= 2) mbar_wait(&bars[PAIR + (n & 1)], ((n >> 1) - 1) & 1);
         // ---- probabilities -> shared memory in the two operand layouts (K-major, 128B swizzle); neighbouring
         //      lanes trade heads so that every store is a packed pair (j, j+1).  Un-normalised: the row sums come
         //      out of the O^T MMA itself (ones column of the V operand) and are applied in the epilogue.
         {
           const int je = gt & ~1;                                   // even key of the pair
           const uint32_t kb = je >> 6, chunk = (je & 63) >> 3, e2 = (je & 7) * 2;
-          uint8_t* pi = smem + ((n & 1) ? S::kPi2 : S::kPi) + g * 2048 + kb * 1024;
-          uint8_t* ph = smem + S::kPh + kb * (IB * 128);
+          uint8_t* pi = smem + ((n & 1) ? S::kPi2 : S::kPi) + kb * 2048 + g * 1024;   // [kb][row = 8 g + h][128 B]
+          uint8_t* ph = smem + S::kPh + kb * (H * IB * 128);                            // [kb][h][16 i][128 B]
           const bool odd = lane & 1;
 #pragma unroll
           for (int hh = 0; hh < 4; ++hh) {
@@ -568,7 +583,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             const int h = 2 * hh + (odd ? 1 : 0);
             float lo = odd ? recv : p[2 * hh], hi = odd ? p[2 * hh + 1] : recv;   // (p_j, p_{j+1}) of head h
             *reinterpret_cast<uint32_t*>(pi + swz128_offset(h, chunk) + e2) = pack_bf162(lo, hi);
-            *reinterpret_cast<uint32_t*>(ph + h * (2 * IB * 128) + swz128_offset(i, chunk) + e2) = pack_h2(lo, hi);
+            *reinterpret_cast<uint32_t*>(ph + h * (IB * 128) + swz128_offset(i, chunk) + e2) = pack_h2(lo, hi);
           }
         }
         fence_proxy_async_smem();
@@ -579,8 +594,10 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
     DAB_STAMP(24);
 
-    // ---- epilogue.  O^T (M = 64: row d in lane d % 16 of warp d / 16): d < 32 scalar values, 32..55 point
-    //      coordinates, d = 56 the row sum of the probabilities (ones column of V).  Group g takes heads 4g..4g+3.
+    // ---- epilogue.  O^T of head pair m sits in columns 32 m .. 32 m + 31 (M = 128): TMEM lane d (warps 0, 1)
+    //      = value column d of head 2m with the 16 rows in columns 0..15; lane 64 + d (warps 2, 3) = head 2m + 1
+    //      with its rows in columns 16..31.  d < 32 scalar values, 32..55 point coordinates, d = 56 the row sum of
+    //      the probabilities (ones column of V).  Group g takes head pairs 2g, 2g + 1.
     // frame of the (residue, head) task this thread finishes with: fetched now, used after the O^T MMAs
     float Rm[9], tfr[3];
     {
@@ -590,17 +607,20 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
       for (int c = 0; c < 3; ++c) tfr[c] = __ldg(tc + row * 3 + c);
     }
+    uint8_t* stage_e = smem + S::kStaging + warp * 1024;   // 1 KB per warp (the P_i buffers are dead by now)
     mbar_wait(&bars[O_DONE], 0);
     tcgen05_fence_after_sync();
     DAB_STAMP(4);
-    if (gw == 3) {               // d = 48 + lane: lane 8 holds the normalisers
+    const int hsel = gw >> 1;                    // which head of the pair this warp's lanes hold
+    const uint32_t ocol = kColS + (uint32_t)hsel * 16;
+    if (gw & 1) {                // d = 32 + lane: lane 24 holds the normalisers
 #pragma unroll
-      for (int hh = 0; hh < H / 2; ++hh) {
-        const int h = g * (H / 2) + hh;
+      for (int mm = 0; mm < 2; ++mm) {
+        const int m = 2 * g + mm, h = 2 * m + hsel;
         float o[16];
-        tmem_ld_x16(tmem_lane + kColS + h * 16, o);
+        tmem_ld_x16(tmem_lane + ocol + m * 32, o);
         tmem_wait_ld();
-        if (lane == 8) {
+        if (lane == 24) {
 #pragma unroll
           for (int i = 0; i < IB; ++i) inv_o[i * H + h] = __fdividef(1.0f, o[i]);
         }
@@ -610,58 +630,47 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (stats && g == 0) stats[(row0 + (gt >> 3)) * 16 + 8 + (gt & 7)] = inv_o[gt];
     float* s_og = reinterpret_cast<float*>(smem);   // [16 i][8 h][24] global-frame points (region X is free)
 #pragma unroll
-    for (int hh = 0; hh < H / 2; ++hh) {
-      const int h = g * (H / 2) + hh;
+    for (int mm = 0; mm < 2; ++mm) {
+      const int m = 2 * g + mm, h = 2 * m + hsel;
       float o[16];
-      tmem_ld_x16(tmem_lane + kColS + h * 16, o);
+      tmem_ld_x16(tmem_lane + ocol + m * 32, o);
       tmem_wait_ld();
-      if (gw < 2) {              // scalar values: d = 16 * gw + lane
-        if (lane < 16) {
+      if ((gw & 1) == 0) {       // scalar values: d = lane
+        __nv_bfloat16* st16 = reinterpret_cast<__nv_bfloat16*>(stage_e);
 #pragma unroll
-          for (int i = 0; i < IB; ++i)
-            reinterpret_cast<__nv_bfloat16*>(stage_w)[i * 16 + lane] = __float2bfloat16_rn(o[i] * inv_o[i * H + h]);
+        for (int i = 0; i < IB; ++i) st16[i * 32 + lane] = __float2bfloat16_rn(o[i] * inv_o[i * H + h]);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {   // [16 i][64 B] -> 64 chunks of 16 B, two per lane
+          const int q = lane + 32 * r, i = q >> 2, part = q & 3;
+          *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + h * DS + part * 8) = reinterpret_cast<const uint4*>(stage_e)[q];
         }
         __syncwarp();
-        {
-          const int i = lane >> 1, half = lane & 1;
-          uint4 val = reinterpret_cast<const uint4*>(stage_w)[lane];
-          *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + h * DS + gw * 16 + half * 8) = val;
-        }
-        __syncwarp();
-      } else {                   // point coordinates: d - 32 = 16 * (gw - 2) + lane < 24
-        const int dd = (gw - 2) * 16 + lane;
-        if (lane < 16 && dd < 3 * P) {
+      } else if (lane < 3 * P) { // point coordinates: d - 32 = lane
 #pragma unroll
-          for (int i = 0; i < IB; ++i) s_og[(i * H + h) * 24 + dd] = o[i] * inv_o[i * H + h];
-        }
+        for (int i = 0; i < IB; ++i) s_og[(i * H + h) * 24 + lane] = o[i] * inv_o[i * H + h];
       }
     }
-    // pair aggregation (M = 64: channel c = 16 * gw + lane in lanes 0-15; one 8-column accumulator per row).
-    // The last pair MMA is older than the O^T MMAs, so O_DONE covers it.  Group g drains rows i = g, g+2, ...
-    for (int n = 0; n < IB / 2; n += 2) {   // two rows per pass: lanes 0-15 store row iA, lanes 16-31 row iB
-      const int iA = 2 * n + g, iB = iA + 2;
-      float va[8], vb[8];
-      tmem_ld_x8(tmem_lane + kColPair + iA * 8, va);
-      tmem_ld_x8(tmem_lane + kColPair + iB * 8, vb);
+    // pair aggregation: accumulator n (16 columns) holds rows 2n (lanes 0-63 = channel c, columns 0-7 = heads) and
+    // 2n + 1 (lanes 64-127, columns 8-15).  The last pair MMA is older than the O^T MMAs, so O_DONE covers it.
+    // Group g drains the accumulators n = g, g + 2, ...; warp gw holds channels 32 (gw & 1) .. + 31 of row 2n + hsel.
+    for (int n = g; n < IB / 2; n += 2) {
+      const int i = 2 * n + hsel;
+      float v[8];
+      tmem_ld_x8(tmem_lane + kColPair + n * 16 + hsel * 8, v);
       tmem_wait_ld();
-      if (lane < 16) {
-        const float4 a0 = *reinterpret_cast<const float4*>(inv_o + iA * H), a1 = *reinterpret_cast<const float4*>(inv_o + iA * H + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(inv_o + iB * H), b1 = *reinterpret_cast<const float4*>(inv_o + iB * H + 4);
+      {
+        const float4 a0 = *reinterpret_cast<const float4*>(inv_o + i * H), a1 = *reinterpret_cast<const float4*>(inv_o + i * H + 4);
         const float na[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float nb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        __nv_bfloat16* st16 = reinterpret_cast<__nv_bfloat16*>(stage_w);
+        __nv_bfloat16* st16 = reinterpret_cast<__nv_bfloat16*>(stage_e);
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-          st16[h * 16 + lane] = __float2bfloat16_rn(va[h] * na[h]);
-          st16[128 + h * 16 + lane] = __float2bfloat16_rn(vb[h] * nb[h]);
-        }
+        for (int h = 0; h < H; ++h) st16[h * 32 + lane] = __float2bfloat16_rn(v[h] * na[h]);
       }
       __syncwarp();
-      {
-        const int i = (lane < 16) ? iA : iB, l16 = lane & 15;
-        const int h = l16 >> 1, half = l16 & 1;
-        uint4 val = reinterpret_cast<const uint4*>(stage_w)[lane];
-        *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + NS + h * C + gw * 16 + half * 8) = val;
+      {   // [8 h][64 B] -> 32 chunks of 16 B, one per lane
+        const int h = lane >> 2, part = lane & 3;
+        *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + NS + h * C + (gw & 1) * 32 + part * 8) =
+            reinterpret_cast<const uint4*>(stage_e)[lane];
       }
       __syncwarp();
     }
@@ -953,7 +962,9 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
     }
     ipa_core_kernel<<<dim3(L / IB, B), 320, CoreSmem::kTotal, s>>>(mq, mk, mv, me, bias, ws.tc, R, ws.cat,
                                                                    save_for_bwd ? ws.stats : nullptr,
-                                                                   save_for_bwd ? ws.pu : nullptr, g_core_dbg);
+                                                                   save_for_bwd ? ws.pu : nullptr, g_core_dbg,
+                                                                   getenv("DAB_X_BULK") ? (const uint8_t*)ws.Kp : nullptr,
+                                                                   getenv("DAB_X_BULK") ? (const uint8_t*)ws.Vp : nullptr);
     count_launch();
   }
   if (phases & 4) {

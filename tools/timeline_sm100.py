@@ -57,6 +57,8 @@ for k in (41, 42, 43):
     print(f"  {lab[k]:36s} mean {d.mean():8.0f}  p10 {d.quantile(0.1):8.0f}  p90 {d.quantile(0.9):8.0f}")
     prev = tl[:, k]
 
+print("issuer, stage 1: cycles since CTA start when K_h is in shared memory:", [int((tl[:, 48 + h] - tl[:, 0]).mean()) for h in range(8)])
+print("issuer, stage 3: cycles since pair MMAs were all issued when V_h is in shared memory:", [int((tl[:, 56 + h] - tl[:, 3]).mean()) for h in range(8)], " O_DONE seen by compute at", int((tl[:, 4] - tl[:, 3]).mean()))
 print("projection kernel (per CTA, thread 0 = group 0):")
 lab = {1: "x->bf16 smem, centroid, sync", 2: "... until tile 4 accumulator ready", 3: "tile 4: tmem ld + release", 4: "tile 4 (scalar): pack + stores", 5: "... until tile 16 ready", 6: "tile 16: tmem ld + release", 7: "tile 16 (points): transform, split, stores", 8: "... to the end"}
 prev = pt[:, 0]
