@@ -282,6 +282,12 @@ def main():
     if args.reverse_steps != T:
         line["profile_only"] = True
 
+    if not args.skip_extras and args.reverse_steps == T:
+        # ---- BASELINE config 5: training step, B=64 patches per GPU, all ranks (DDP all-reduce over NCCL) ------
+        train = measure_train_step(dev, dist, world, shapes)
+        if rank == 0:
+            line["train_step"] = train
+
     if rank == 0 and not args.skip_extras:
         # ---- roofline of the dominant kernel (IPA attention core), measured live ---------------
         line["roofline"] = measure_roofline(model, layer0, res_ctx, pair_ctx, x0, O0, precision, hbm_peak, peak_src)
@@ -398,6 +404,51 @@ def measure_ipa_fwd_bwd(dev, B=32, iters=5):
     alg = 3 * B * L * L * 64 * 4 + 6 * B * L * 128 * 4
     return {"metric": "IPA fwd+bwd us/layer (B=32, K=128, fp32)", "value": us, "unit": "us",
             "algorithmic_bytes": alg, "hbm_roofline_us": alg / 6528.4e9 * 1e6}
+
+
+def measure_train_step(dev, dist, world, shapes, B=64, steps=5, warmup=3):
+    """BASELINE config 5: noising + context encoders + epsilon network forward + losses + backward + gradient
+    all-reduce + Adam, B=64 synthetic patches per GPU, bf16 tensor-core IPA path (train_precision="bf16").
+    Device time over `steps` steps (CUDA events), max over ranks; weak scaling (every rank has its own 64 patches)."""
+    from diffab_pytorch_b200 import synth
+    from diffab_pytorch_b200.diffab_pytorch import DiffAb
+    from diffab_pytorch_b200.distributed import GradientBucket, ddp_step, diffab_loss_terms
+    rank = dist.get_rank() if dist is not None else 0
+    model = DiffAb(*TRAIN_CFG, device=dev).train()
+    model.load_state_dict(synth.synthetic_state(shapes, seed=0))
+    model.train_precision = "bf16"
+    bucket = GradientBucket(model.parameters())
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    batch = {k: v.to(dev) for k, v in synth.make_patches(B, L, seed=2000 + rank, with_distmat=False).items()}
+    batch["distmat"] = torch.cat([synth.pairwise_atom_distances(batch["xyz"][i:i + 8]) for i in range(0, B, 8)])
+    group = dist.group.WORLD if dist is not None else None
+
+    def step():
+        return ddp_step(lambda: diffab_loss_terms(model, batch), bucket, opt, group=group)
+
+    for _ in range(warmup):
+        loss = step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        loss = step()
+    b_.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b_) / steps
+    if dist is not None:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax)
+    finite = bool(torch.isfinite(loss))
+    del model, bucket, opt, batch
+    torch.cuda.empty_cache()
+    return {"metric": "training steps/s (config 5: B=64 patches per GPU, noising + fwd + losses + bwd + "
+                      "all-reduce + Adam, bf16 tensor-core IPA)", "value": 1000.0 / ms, "unit": "steps/s",
+            "patches_per_s": B * world * 1000.0 / ms, "ms_per_step": ms, "patches_per_gpu": B, "n_gpus": world,
+            "loss_finite": finite}
 
 
 def measure_ipa_fwd_bwd_bf16(dev, B=32, iters=20):

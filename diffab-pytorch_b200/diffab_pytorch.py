@@ -500,6 +500,57 @@ class Denoiser(nn.Module):
         h = torch.cat([h, t_emb[:, None, :].expand(-1, n_residues, -1)], dim=-1)
         return self.coordinate_denoising(h), self.orientation_denoising(h), self.sequence_denoising(h)
 
+    # ---- sampling fast path of the dense glue (same arithmetic, regrouped; inference only) ----
+    @torch.no_grad()
+    def sampling_cache(self, res_context_emb, cache=None):
+        """Everything of the glue that does not change over the T reverse steps, computed once per run:
+        * to_res_emb layer 1 (:572-574) acts on [res_ctx | emb(s_t)]: its res_ctx half (+ bias) is a constant
+          (B, L, D) tensor and its embedding half a 25-row table, so per step layer 1 is a gather + add + relu;
+        * the three heads (:591-599) act on [h | beta, sin beta, cos beta]: their first layers are concatenated
+          into one (3D, D) matrix, the 3 time columns become a per-patch bias; layers 2 / 3 run as one batched GEMM each.
+        ``cache`` (a previous result) is refreshed in place so CUDA graphs keep their addresses."""
+        D = self.to_res_emb[0].out_features
+        w1, b1 = self.to_res_emb[0].weight, self.to_res_emb[0].bias
+        c = torch.addmm(b1, res_context_emb.reshape(-1, D), w1[:, :D].t()).view(res_context_emb.shape)
+        if cache is not None:
+            cache["c"].copy_(c)
+            return cache
+        heads = (self.coordinate_denoising, self.orientation_denoising, self.sequence_denoising)
+        n_out = max(h[4].out_features for h in heads)
+        w3 = torch.zeros(3, D, n_out, device=c.device)
+        b3 = torch.zeros(3, 1, n_out, device=c.device)
+        for k, h in enumerate(heads):
+            w3[k, :, : h[4].out_features] = h[4].weight.t()
+            b3[k, 0, : h[4].out_features] = h[4].bias
+        wc1 = torch.cat([h[0].weight for h in heads], dim=0)             # (3D, D + 3)
+        return {
+            "c": c, "t1": (self.sequence_embedding.weight @ w1[:, D:].t()).contiguous(),        # (25, D)
+            "w2t": self.to_res_emb[2].weight.t().contiguous(), "b2": self.to_res_emb[2].bias,
+            "wh1": wc1[:, :D].t().contiguous(),                                                  # (D, 3D)
+            "wt1": wc1[:, D:].t().contiguous(), "bh1": torch.cat([h[0].bias for h in heads]),   # (3, 3D), (3D)
+            "wh2": torch.stack([h[2].weight.t() for h in heads]).contiguous(),                  # (3, D, D)
+            "bh2": torch.stack([h[2].bias for h in heads])[:, None, :].contiguous(),            # (3, 1, D)
+            "wh3": w3, "bh3": b3, "n_out": [h[4].out_features for h in heads],
+        }
+
+    @torch.no_grad()
+    def heads_fast(self, seq_idx_t, translations_t, orientations_t, cache, pair_context_emb, beta, pair_bias=None):
+        """``heads`` with the per-run constants of ``sampling_cache``; returns (eps, rotvec, seq_posterior)."""
+        B, L = seq_idx_t.shape
+        D = cache["c"].shape[-1]
+        h = torch.relu_(cache["c"] + F.embedding(seq_idx_t, cache["t1"]))
+        h = torch.addmm(cache["b2"], h.view(-1, D), cache["w2t"]).view(B, L, D)
+        h = self.ipa(h, pair_context_emb, orientations_t, translations_t, pair_bias)
+        t_emb = torch.stack([beta, torch.sin(beta), torch.cos(beta)], dim=-1)                   # (B, 3)
+        pb = torch.addmm(cache["bh1"], t_emb, cache["wt1"])                                      # (B, 3D)
+        a = torch.baddbmm(pb[:, None, :], h, cache["wh1"][None].expand(B, D, 3 * D)).relu_()     # (B, L, 3D)
+        a = a.view(B * L, 3, D).transpose(0, 1)                                                  # (3, B L, D) strided
+        a = torch.baddbmm(cache["bh2"], a, cache["wh2"]).relu_()                                 # (3, B L, D)
+        o = torch.baddbmm(cache["bh3"], a, cache["wh3"])                                         # (3, B L, n_out)
+        n = cache["n_out"]
+        return (o[0, :, : n[0]].reshape(B, L, n[0]), o[1, :, : n[1]].reshape(B, L, n[1]),
+                torch.softmax(o[2, :, : n[2]], dim=-1).view(B, L, n[2]))
+
     def forward(self, seq_idx_t, translations_t, orientations_t, res_context_emb, pair_context_emb, beta,
                 generation_mask=None, residue_mask=None):
         # the two masks are accepted and unused, as in the reference (:566-567)
@@ -691,11 +742,16 @@ class DiffAb(nn.Module):
 
     @torch.no_grad()
     def reverse_step(self, seq_idx_t, translations_t, orientations_t, res_context_emb, pair_context_emb,
-                     generation_mask, t, noise, inplace=False, pair_bias=None):
-        """One reverse-diffusion step: epsilon network + fused update kernel.  ``t`` is (B,) int64."""
+                     generation_mask, t, noise, inplace=False, pair_bias=None, glue_cache=None):
+        """One reverse-diffusion step: epsilon network + fused update kernel.  ``t`` is (B,) int64.
+        ``glue_cache`` (``Denoiser.sampling_cache``) switches the dense glue to its regrouped form."""
         beta = self.dsched.tensors["beta"][t]
-        eps, v_eps, post = self.denoiser.heads(seq_idx_t, translations_t, orientations_t, res_context_emb,
-                                               pair_context_emb, beta, pair_bias)
+        if glue_cache is not None:
+            eps, v_eps, post = self.denoiser.heads_fast(seq_idx_t, translations_t, orientations_t, glue_cache,
+                                                        pair_context_emb, beta, pair_bias)
+        else:
+            eps, v_eps, post = self.denoiser.heads(seq_idx_t, translations_t, orientations_t, res_context_emb,
+                                                   pair_context_emb, beta, pair_bias)
         return _diffusion.fused_reverse_step(self.dsched, self.so3_reverse, seq_idx_t, translations_t,
                                              orientations_t, eps, v_eps, post, generation_mask, t, noise,
                                              inplace=inplace)
@@ -717,11 +773,12 @@ class DiffAb(nn.Module):
                 return self._sample_graphed(s, x, O, res_context_emb, pair_context_emb, generation_mask, t_start,
                                             t_stop)
             pair_bias = self._pair_bias_planes(pair_context_emb)
+            glue = self.denoiser.sampling_cache(res_context_emb) if pair_context_emb.dtype == torch.bfloat16 else None
             for step in range(t_start, t_stop - 1, -1):
                 t = torch.full((B,), step, device=dev, dtype=torch.int64)
                 noise = noises[step] if noises is not None else self.draw_step_noise(B, L, dev, generator=generator)
                 out = self.reverse_step(s, x, O, res_context_emb, pair_context_emb, generation_mask, t, noise,
-                                        inplace=True, pair_bias=pair_bias)
+                                        inplace=True, pair_bias=pair_bias, glue_cache=glue)
                 s, x, O = out["seq_idx"], out["translations"], out["orientations"]
             return {"seq_idx": s, "translations": x, "orientations": O}
 
@@ -745,7 +802,7 @@ class DiffAb(nn.Module):
             cache = {"key": key, "s": torch.empty_like(s), "x": torch.empty_like(x), "O": torch.empty_like(O),
                      "t": torch.full((B,), t_start, device=dev, dtype=torch.int64),
                      "res": torch.empty_like(res_ctx), "pair": torch.empty_like(pair_ctx),
-                     "mask": torch.empty_like(generation_mask), "bias": None, "graph": None}
+                     "mask": torch.empty_like(generation_mask), "bias": None, "graph": None, "glue": None}
         st = cache
         st["res"].copy_(res_ctx); st["pair"].copy_(pair_ctx); st["mask"].copy_(generation_mask)
         if pair_ctx.dtype == torch.bfloat16:   # per-layer pair-bias planes, written straight into the static buffers
@@ -754,6 +811,7 @@ class DiffAb(nn.Module):
                 st["bias_all"] = torch.empty(len(layers), B, L, L, layers[0].n_head, device=dev, dtype=torch.float16)
                 st["bias"] = list(st["bias_all"].unbind(0))
             self.denoiser.ipa.precompute_pair_bias(st["pair"], out=st["bias_all"])
+            st["glue"] = self.denoiser.sampling_cache(st["res"], cache=st["glue"])
         if fresh:
             st["s"].copy_(s); st["x"].copy_(x); st["O"].copy_(O)
             side = torch.cuda.Stream(device=dev)
@@ -761,13 +819,14 @@ class DiffAb(nn.Module):
             with torch.cuda.stream(side):
                 for _ in range(2):  # warm-up outside capture (allocator, lazy init, weight packing)
                     self.reverse_step(st["s"].clone(), st["x"].clone(), st["O"].clone(), st["res"], st["pair"],
-                                      st["mask"], st["t"], self.draw_step_noise(B, L, dev), pair_bias=st["bias"])
+                                      st["mask"], st["t"], self.draw_step_noise(B, L, dev), pair_bias=st["bias"],
+                                      glue_cache=st["glue"])
             torch.cuda.current_stream(dev).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 noise = self.draw_step_noise(B, L, dev)
                 self.reverse_step(st["s"], st["x"], st["O"], st["res"], st["pair"], st["mask"], st["t"], noise,
-                                  inplace=True, pair_bias=st["bias"])
+                                  inplace=True, pair_bias=st["bias"], glue_cache=st["glue"])
                 st["t"].sub_(1)
             st["graph"] = graph
             self._graph_cache = st

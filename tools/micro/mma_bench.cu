@@ -25,10 +25,12 @@ __global__ void __launch_bounds__(128) k_mma(long long* out, int n_mma, int smem
     uint32_t a = smem_u32(smem), b = a + 16384;
     long long t0 = clock64();
     for (int i = 0; i < n_mma; ++i) {
-      uint64_t da = AMN ? make_smem_desc(a + (i & 7) * 2048, 1024, 1024, kSwizzle128B)
-                        : make_smem_desc(a + (i & 3) * 32, 16, 1024, kSwizzle128B);
+      uint64_t da = AMN ? make_smem_desc(a + (i & 7) * 2048, 16384, 1024, kSwizzle128B)
+                        : (smem_pad == 64 ? make_smem_desc(a + (i & 1) * 32, 16, 512, kSwizzle64B)
+                                          : make_smem_desc(a + (i & 3) * 32, 16, 1024, kSwizzle128B));
       uint64_t db = BMN ? make_smem_desc(b + (i & 7) * 2048, 1024, 1024, kSwizzle128B)
-                        : make_smem_desc(b + (i & 3) * 32, 16, 1024, kSwizzle128B);
+                        : (smem_pad == 64 ? make_smem_desc(b + (i & 1) * 32, 16, 512, kSwizzle64B)
+                                          : make_smem_desc(b + (i & 3) * 32, 16, 1024, kSwizzle128B));
       umma_bf16(tmem + (i % NACC) * 64, da, db, idesc, i >= NACC);
     }
     long long t1 = clock64();
@@ -42,12 +44,13 @@ __global__ void __launch_bounds__(128) k_mma(long long* out, int n_mma, int smem
   if (threadIdx.x < 32) tmem_free(tmem, 256);
 }
 
+static int g_pad = 0;
 template <int M, int N, int AMN, int NACC = 1, int BMN = 0>
 void run(const char* name, int grid, int smem_bytes, int n_mma) {
   long long* d;
   cudaMalloc(&d, grid * 16);
   cudaFuncSetAttribute(k_mma<M, N, AMN, NACC, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-  for (int rep = 0; rep < 2; ++rep) k_mma<M, N, AMN, NACC, BMN><<<grid, 128, smem_bytes>>>(d, n_mma, 0);
+  for (int rep = 0; rep < 2; ++rep) k_mma<M, N, AMN, NACC, BMN><<<grid, 128, smem_bytes>>>(d, n_mma, g_pad);
   cudaError_t e = cudaDeviceSynchronize();
   std::vector<long long> h(grid * 2);
   cudaMemcpy(h.data(), d, grid * 16, cudaMemcpyDeviceToHost);
@@ -82,5 +85,16 @@ int main() {
   run<64, 64, 0, 4, 1>("M64 N64 A-K B-MN 4 acc", 148, 200 * 1024, n);
   run<128, 64, 0, 1, 1>("M128 N64 A-K B-MN", 148, 200 * 1024, n);
   run<128, 64, 0, 2, 1>("M128 N64 A-K B-MN 2acc", 296, 100 * 1024, n);
+  printf("---- shapes of the attention core\n");
+  run<128, 16, 0>("M128 N16 K-major SW128", 296, 100 * 1024, n);
+  g_pad = 64;
+  run<128, 16, 0>("M128 N16 K-major SW64", 296, 100 * 1024, n);
+  run<128, 16, 0>("M128 N16 K-major SW64", 148, 200 * 1024, n);
+  g_pad = 0;
+  run<128, 16, 1>("M128 N16 A-MN (pair x2)", 296, 100 * 1024, n);
+  run<128, 32, 1>("M128 N32 A-MN (O^T x2)", 296, 100 * 1024, n);
+  run<128, 32, 0>("M128 N32 K-major", 296, 100 * 1024, n);
+  run<128, 64, 0>("M128 N64 K-major", 296, 100 * 1024, n);
+  run<64, 16, 0>("M64 N16 K-major", 296, 100 * 1024, n);
   return 0;
 }
