@@ -36,6 +36,10 @@ class DabIpaGrads(Structure):
     _fields_ = [(n, c_void_p) for n in _W_FIELDS]
 
 
+class DabHeadWeights(Structure):
+    _fields_ = [(f"{h}_{n}", c_void_p) for h in ("c", "o", "s") for n in ("w1", "b1", "w2", "b2", "w3", "b3")]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "dab_version": (c_int, []),
@@ -76,6 +80,11 @@ EXPORTS = {
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dab_debug_set_bwd_timeline": (c_int, [c_void_p]),
     "dab_debug_bwd_sm100_buffers": (c_int, [POINTER(DabIpaDims), c_void_p, c_void_p]),
+    "dab_heads_packed_bytes": (c_size_t, []),
+    "dab_heads_pack_weights": (c_int, [POINTER(DabHeadWeights), c_void_p, c_void_p]),
+    "dab_heads_fwd_sm100": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dab_front_fwd_sm100": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
     "dab_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dab_debug_set_timeline": (c_int, [c_void_p]),
     "dab_debug_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -120,6 +129,13 @@ def dev(t, dtype, name):
     if t.dtype != dtype:
         raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     return t.contiguous()
+
+
+def aligned_empty(nbytes, device, align=1024):
+    """uint8 buffer whose data pointer is `align`-byte aligned (TMA / tcgen05 operands want 1024)."""
+    buf = torch.empty(nbytes + align, device=device, dtype=torch.uint8)
+    off = (-buf.data_ptr()) % align
+    return buf[off: off + nbytes]
 
 
 def ptr(t):

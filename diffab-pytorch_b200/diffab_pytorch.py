@@ -251,7 +251,7 @@ class _IpaFastFunction(torch.autograd.Function):
         lib = _lib.lib()
         packed = layer._packed_weights(dims)
         nbytes = lib.dab_ipa_sm100_workspace_bytes(ctypes.byref(dims))
-        saved = torch.empty(max(nbytes, 16), device=x.device, dtype=torch.uint8)   # private: kept for the backward
+        saved = _lib.aligned_empty(max(nbytes, 16), x.device)   # private: kept for the backward
         y = torch.empty(B, L, D, device=x.device, dtype=torch.float32)
         if pair_bias is not None:
             pair_bias = _lib.dev(pair_bias, torch.float16, "pair_bias")
@@ -290,8 +290,7 @@ class _IpaFastFunction(torch.autograd.Function):
         de = torch.empty_like(e)
         d_wpb = torch.zeros_like(weights[6])
         d_gamma = torch.zeros_like(weights[7])
-        bws = torch.empty(max(lib.dab_ipa_bwd_sm100_workspace_bytes(ctypes.byref(dims)), 16), device=x.device,
-                          dtype=torch.uint8)
+        bws = _lib.aligned_empty(max(lib.dab_ipa_bwd_sm100_workspace_bytes(ctypes.byref(dims)), 16), x.device)
         _lib.check(lib.dab_ipa_bwd_sm100(ctypes.byref(dims), ptr(packed), ptr(e), ptr(r), ptr(dcat), ptr(saved),
                                          saved.numel(), ptr(dproj), ptr(de), ptr(d_wpb), ptr(d_gamma), ptr(bws),
                                          bws.numel(), _lib.stream_ptr()), "dab_ipa_bwd_sm100")
@@ -339,7 +338,7 @@ class InvariantPointAttentionLayer(nn.Module):
     def _workspace(self, nbytes, device):
         ws = getattr(self, "_ws", None)
         if ws is None or ws.numel() < nbytes or ws.device != device:
-            ws = torch.empty((nbytes + 255) // 256 * 256, device=device, dtype=torch.uint8)
+            ws = _lib.aligned_empty((nbytes + 255) // 256 * 256, device)
             self._ws = ws
         return ws[: (nbytes // 4) * 4]
 
@@ -368,7 +367,7 @@ class InvariantPointAttentionLayer(nn.Module):
         if self._packed is None or self._packed[0] != key:
             lib = _lib.lib()
             nbytes = lib.dab_ipa_packed_bytes(ctypes.byref(dims))
-            buf = torch.empty(max(nbytes, 16), device=ws[0].device, dtype=torch.uint8)
+            buf = _lib.aligned_empty(max(nbytes, 16), ws[0].device)
             wstruct = _weights_struct([_lib.dev(w.detach(), torch.float32, "weight") for w in ws])
             _lib.check(lib.dab_ipa_pack_weights(ctypes.byref(dims), ctypes.byref(wstruct), ptr(buf), _lib.stream_ptr()),
                        "dab_ipa_pack_weights")
@@ -523,7 +522,21 @@ class Denoiser(nn.Module):
             w3[k, :, : h[4].out_features] = h[4].weight.t()
             b3[k, 0, : h[4].out_features] = h[4].bias
         wc1 = torch.cat([h[0].weight for h in heads], dim=0)             # (3D, D + 3)
+        packed = None
+        if (D == 128 and res_context_emb.shape[1] == 128 and [h[4].out_features for h in heads] == [3, 3, 21] and
+                all(h[0].in_features == D + 3 for h in heads)):
+            # fused tcgen05 heads kernel (csrc/heads_sm100.cu): weights packed once per run
+            lib = _lib.lib()
+            packed = _lib.aligned_empty(lib.dab_heads_packed_bytes(), c.device)
+            ws = [_lib.dev(p.detach(), torch.float32, "head weight") for h in heads
+                  for p in (h[0].weight, h[0].bias, h[2].weight, h[2].bias, h[4].weight, h[4].bias)]
+            hw = _lib.DabHeadWeights(*(w.data_ptr() for w in ws))
+            _lib.check(lib.dab_heads_pack_weights(ctypes.byref(hw), ptr(packed), _lib.stream_ptr()),
+                       "dab_heads_pack_weights")
         return {
+            "heads_packed": packed,
+            "w2_bf16": self.to_res_emb[2].weight.detach().to(torch.bfloat16).contiguous() if packed is not None else None,
+            "a_scratch": torch.empty(c.shape, device=c.device, dtype=torch.bfloat16) if packed is not None else None,
             "c": c, "t1": (self.sequence_embedding.weight @ w1[:, D:].t()).contiguous(),        # (25, D)
             "w2t": self.to_res_emb[2].weight.t().contiguous(), "b2": self.to_res_emb[2].bias,
             "wh1": wc1[:, :D].t().contiguous(),                                                  # (D, 3D)
@@ -538,9 +551,24 @@ class Denoiser(nn.Module):
         """``heads`` with the per-run constants of ``sampling_cache``; returns (eps, rotvec, seq_posterior)."""
         B, L = seq_idx_t.shape
         D = cache["c"].shape[-1]
-        h = torch.relu_(cache["c"] + F.embedding(seq_idx_t, cache["t1"]))
-        h = torch.addmm(cache["b2"], h.view(-1, D), cache["w2t"]).view(B, L, D)
+        if cache.get("w2_bf16") is not None and pair_context_emb.dtype == torch.bfloat16 and (B * L) % 128 == 0:
+            h = torch.empty(B, L, D, device=seq_idx_t.device)
+            _lib.check(_lib.lib().dab_front_fwd_sm100(ptr(cache["c"]), ptr(cache["t1"]), ptr(seq_idx_t.contiguous()),
+                                                      B * L, ptr(cache["w2_bf16"]), ptr(cache["b2"]),
+                                                      ptr(cache["a_scratch"]), ptr(h), _lib.stream_ptr()),
+                       "dab_front_fwd_sm100")
+        else:
+            h = torch.relu_(cache["c"] + F.embedding(seq_idx_t, cache["t1"]))
+            h = torch.addmm(cache["b2"], h.view(-1, D), cache["w2t"]).view(B, L, D)
         h = self.ipa(h, pair_context_emb, orientations_t, translations_t, pair_bias)
+        if cache.get("heads_packed") is not None and pair_context_emb.dtype == torch.bfloat16:
+            eps = torch.empty(B, L, 3, device=h.device)
+            rot = torch.empty(B, L, 3, device=h.device)
+            post = torch.empty(B, L, 21, device=h.device)
+            _lib.check(_lib.lib().dab_heads_fwd_sm100(ptr(cache["heads_packed"]), ptr(h.contiguous()),
+                                                      ptr(beta.contiguous()), B, L, ptr(eps), ptr(rot), ptr(post),
+                                                      _lib.stream_ptr()), "dab_heads_fwd_sm100")
+            return eps, rot, post
         t_emb = torch.stack([beta, torch.sin(beta), torch.cos(beta)], dim=-1)                   # (B, 3)
         pb = torch.addmm(cache["bh1"], t_emb, cache["wt1"])                                      # (B, 3D)
         a = torch.baddbmm(pb[:, None, :], h, cache["wh1"][None].expand(B, D, 3 * D)).relu_()     # (B, L, 3D)

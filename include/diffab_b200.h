@@ -193,6 +193,29 @@ int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf1
                       void* workspace, size_t workspace_bytes, void* stream);
 int dab_debug_set_bwd_timeline(long long* device_buf /* 64 slots per CTA of the backward core, or NULL */);
 int dab_debug_bwd_sm100_buffers(const DabIpaDims* d, void* workspace, void** out /* 10 device pointers */);
+/* ------------------------------------------------------------------ epsilon-network tail
+ * The three denoising heads of Denoiser.forward (diffab_pytorch.py:584-599) for d_residue_emb = 128, L = 128, fused
+ * into one tcgen05 kernel: [x | beta, sin beta, cos beta] -> MLP(131 -> 128 -> 128 -> {3, 3, 21}) x 3, softmax on
+ * the sequence head.  Weights are the state-dict tensors of coordinate_denoising / orientation_denoising /
+ * sequence_denoising (layers .0, .2, .4), nn.Linear layout (out, in) row-major. */
+typedef struct DabHeadWeights {
+  const float *c_w1, *c_b1, *c_w2, *c_b2, *c_w3, *c_b3; /* coordinate_denoising:  (128,131) (128) (128,128) (128) (3,128) (3) */
+  const float *o_w1, *o_b1, *o_w2, *o_b2, *o_w3, *o_b3; /* orientation_denoising: same shapes */
+  const float *s_w1, *s_b1, *s_w2, *s_b2, *s_w3, *s_b3; /* sequence_denoising:    last layer (21,128) (21) */
+} DabHeadWeights;
+size_t dab_heads_packed_bytes(void);
+int dab_heads_pack_weights(const DabHeadWeights* w, void* packed, void* stream);
+/* x[n_patches*L,128] fp32, beta[n_patches] fp32 -> eps[.,3], rotvec[.,3], seq_posterior[.,21] fp32. */
+int dab_heads_fwd_sm100(const void* packed, const float* x, const float* beta, int n_patches, int L, float* eps,
+                        float* rotvec, float* seq_posterior, void* stream);
+
+/* Front of the epsilon network during sampling (diffab_pytorch.py:572-574, to_res_emb on [res_ctx | emb(s_t)]):
+ * x0[n_rows,128] = relu(c[row] + t1[seq[row]]) . w2^T + b2, where c = res_ctx . W1[:, :128]^T + b1 (per-run constant,
+ * fp32 [n_rows,128]) and t1 = emb . W1[:, 128:]^T (fp32 [25,128]) are computed once per run by the caller;
+ * w2_bf16 = to_res_emb.2.weight in bf16 [128][128]; a_scratch holds n_rows*128 bf16. */
+int dab_front_fwd_sm100(const float* c, const float* t1, const int64_t* seq, int64_t n_rows, const void* w2_bf16,
+                        const float* b2, void* a_scratch, float* x0, void* stream);
+
 /* Test hooks of the sm_100a path (used by tests/ only): the tcgen05 GEMM C[M,N] = A[M,K] B[N,K]^T + bias
  * (bf16 in, fp32 out; M % 128 == 0, N % 64 == 0, K % 64 == 0) and the operand-packing stage alone. */
 int dab_debug_set_timeline(long long* device_buf /* 64 slots per CTA of the attention core, or NULL */);

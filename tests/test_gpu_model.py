@@ -206,8 +206,15 @@ def test_regrouped_sampling_glue_matches_module_path():
         for r, g_ in zip(ref, got):
             assert r.shape == g_.shape
             assert _rel(g_, r.cpu()) < 1e-4
-        # bf16 sampling loop, eager, same noises
+        # fused tcgen05 heads kernel (bf16 operands, fp32 accumulation) behind the same call on the bf16 path
         pair16 = cast_pair_to_bf16(pair)
+        assert cache["heads_packed"] is not None
+        ref16 = model.denoiser.heads(b["seq_idx"], x, b["orientations"], res, pair16, beta)
+        got16 = model.denoiser.heads_fast(b["seq_idx"], x, b["orientations"], cache, pair16, beta)
+        assert _rel(got16[0], ref16[0].cpu()) < 2e-2 and _rel(got16[1], ref16[1].cpu()) < 2e-2
+        assert float((got16[2] - ref16[2]).abs().max()) < 1e-2
+        assert torch.allclose(got16[2].sum(-1), torch.ones_like(got16[2].sum(-1)), atol=1e-5)
+        # bf16 sampling loop, eager, same noises
         gen = torch.Generator().manual_seed(5)
         s, xx, O = osamp.draw_initial_state(batch["seq_idx"], batch["xyz"][:, :, 1], batch["orientations"],
                                             batch["generation_mask"], generator=gen)
