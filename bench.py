@@ -282,12 +282,6 @@ def main():
     if args.reverse_steps != T:
         line["profile_only"] = True
 
-    if not args.skip_extras and args.reverse_steps == T:
-        # ---- BASELINE config 5: training step, B=64 patches per GPU, all ranks (DDP all-reduce over NCCL) ------
-        train = measure_train_step(dev, dist, world, shapes)
-        if rank == 0:
-            line["train_step"] = train
-
     if rank == 0 and not args.skip_extras:
         # ---- roofline of the dominant kernel (IPA attention core), measured live ---------------
         line["roofline"] = measure_roofline(model, layer0, res_ctx, pair_ctx, x0, O0, precision, hbm_peak, peak_src)
@@ -318,6 +312,11 @@ def main():
                                 "single_thread_value": rate1,
                                 "sample": f"2 patches x 2 of {T} reverse steps (oracle port of the reference's PyTorch "
                                           f"CPU path, fp32, {per_call:.2f} s per call), extrapolated x50 to T={T}"}
+    if not args.skip_extras and args.reverse_steps == T:
+        # ---- BASELINE config 5: training step, B=64 patches per GPU, all ranks (DDP all-reduce over NCCL) ------
+        train = measure_train_step(dev, dist, world, shapes)
+        if rank == 0:
+            line["train_step"] = train
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

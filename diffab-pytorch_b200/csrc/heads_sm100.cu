@@ -114,8 +114,8 @@ denoiser_heads_kernel(const __grid_constant__ CUtensorMap map_w128, const __grid
     // x tile: fp32 global (coalesced float4) -> bf16, K-major 128B-swizzled A operand (16 rows per warp)
     const float* xb = x + (int64_t)b * 128 * HD;
     const uint32_t kb = lane >> 4, chunk = (lane & 15) >> 1, half = (lane & 1) * 8;
-#pragma unroll 4
-    for (int rr = 0; rr < 16; ++rr) {
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {   // all 16 loads of the warp in flight before the first conversion
       const int r = warp * 16 + rr;
       const float4 v = __ldg(reinterpret_cast<const float4*>(xb + r * HD) + lane);
       *reinterpret_cast<uint2*>(smem + S::kA + kb * 16384 + swz128_offset(r, chunk) + half) =

@@ -29,9 +29,9 @@ struct ProjSmem {
   static constexpr int kBars = kMisc;                 // 16 mbarriers
   static constexpr int kTmemSlot = kBars + 16 * 8;
   static constexpr int kCen = kTmemSlot + 16;         // centroid partials [4][3] + result [3]
-  static constexpr int kStage = kCen + 64;            // per-warp staging: 32 rows x 80 B pitch (64 B payload)
-  static constexpr int kStageWarp = 32 * 80;
-  static constexpr int kTotal = kStage + 8 * kStageWarp;
+  static constexpr int kStage = kMisc + 512;          // per-group staging: two [128 rows][64 B] tiles, 64B-swizzled
+  static constexpr int kStageGroup = 2 * 8192;        // (512-byte aligned), the source of the TMA stores
+  static constexpr int kTotal = kStage + 2 * kStageGroup;   // 115,200: two CTAs per SM, exactly
 };
 enum ProjBar { W_FULL = 0, W_EMPTY = 3, ACC_FULL = 6, ACC_EMPTY = 8, PROJ_N_BARS = 10 };
 
@@ -49,7 +49,8 @@ __device__ __forceinline__ uint32_t pk_h(float a, float b) {
 // map_w64 / map_w48: the packed bf16 weight matrix [1344, 128] with boxes {64, 64} / {64, 48}
 __global__ void __launch_bounds__(288, 2)
 ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_constant__ CUtensorMap map_w48,
-                const float* __restrict__ x, const float* __restrict__ R, const float* __restrict__ t,
+                const __grid_constant__ CUtensorMap map_sq, const __grid_constant__ CUtensorMap map_sk,
+                const __grid_constant__ CUtensorMap map_sv, const float* __restrict__ x, const float* __restrict__ R, const float* __restrict__ t,
                 const float* __restrict__ gamma, __nv_bfloat16* __restrict__ Qp, __nv_bfloat16* __restrict__ Kp,
                 __nv_bfloat16* __restrict__ Vp, float* __restrict__ tc, long long* __restrict__ dbg) {
   long long* dbg_cta = dbg ? dbg + (size_t)blockIdx.x * 64 : nullptr;
@@ -78,8 +79,8 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
     // ---- x tile: fp32 global (coalesced float4) -> bf16, K-major 128B-swizzled A operand (16 rows per warp)
     const float* xb = x + (int64_t)b * L * D;
     const uint32_t kb = lane >> 4, chunk = (lane & 15) >> 1, half = (lane & 1) * 8;
-#pragma unroll 4
-    for (int rr = 0; rr < 16; ++rr) {
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {   // all 16 loads of the warp in flight before the first conversion
       const int r = warp * 16 + rr;
       float4 v = __ldg(reinterpret_cast<const float4*>(xb + r * D) + lane);
       uint2 o = make_uint2(pk_bf(v.x, v.y), pk_bf(v.z, v.w));
@@ -153,22 +154,32 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
     const float tcx = __ldg(t + row * 3) - cenx, tcy = __ldg(t + row * 3 + 1) - ceny, tcz = __ldg(t + row * 3 + 2) - cenz;
     if (g == 0) { tc[row * 3] = tcx; tc[row * 3 + 1] = tcy; tc[row * 3 + 2] = tcz; }
     const float ss = rsqrtf((float)DS), sp = rsqrtf(4.5f * P), st = rsqrtf(3.0f);
-    // Every 64-byte output segment of a row goes through a warp-private staging tile so that global stores are
-    // runs of four consecutive 16 B chunks per row (thread-per-row 16 B stores scattered over 32 rows cost
-    // ~7k cycles per tile; measured).
-    uint4* stage = reinterpret_cast<uint4*>(smem + S::kStage + warp * S::kStageWarp);
-    const int wrow0 = (warp & 3) * 32;   // first row of this warp inside the patch
-    auto flush = [&](const uint4 (&seg)[4], __nv_bfloat16* base, int row_elems, int col_elems) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) stage[lane * 5 + q] = seg[q];
-      __syncwarp();
-      uint8_t* gbase = reinterpret_cast<uint8_t*>(base + ((int64_t)b * L + wrow0) * row_elems + col_elems);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = k * 8 + (lane >> 2), c = lane & 3;
-        *reinterpret_cast<uint4*>(gbase + (size_t)r * row_elems * 2 + c * 16) = stage[r * 5 + c];
+    // Every output segment is 64 bytes per residue (a head's scalars, point-hi or point-lo columns).  A thread
+    // drops its segment into a [128 rows][64 B] shared-memory tile (64B swizzle: conflict-free 16-byte stores) and
+    // one thread of the group hands the whole tile to the TMA as a 2-D store (row pitch = the packed row).  Two
+    // tiles per group and round; a round = fill, fence, group barrier, issue.
+    uint8_t* stg = smem + S::kStage + g * S::kStageGroup;
+    auto bar_group = [&] { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
+    bool first_round = true;
+    auto begin_round = [&] {      // the previous round's stores must have finished reading the tiles
+      if (!first_round) {
+        if (gt == 0) tma_store_wait_read();
+        bar_group();
       }
-      __syncwarp();
+      first_round = false;
+    };
+    auto put = [&](int slot, const uint4 (&seg)[4]) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(stg + slot * 8192 + swz64_offset(gt, q)) = seg[q];
+    };
+    auto end_round = [&](const CUtensorMap* m0, int col0, const CUtensorMap* m1, int col1) {
+      fence_proxy_async_smem();
+      bar_group();
+      if (gt == 0) {
+        tma_store_2d(m0, stg, col0, b * L);
+        tma_store_2d(m1, stg + 8192, col1, b * L);
+        tma_store_commit();
+      }
     };
 
     for (int tt = g; tt < kProjTiles; tt += 2) {
@@ -206,9 +217,13 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
                                 pk_bf(s8[4] * sc, s8[5] * sc), pk_bf(s8[6] * sc, s8[7] * sc));
             }
           }
-          if (seg == 0) flush(o, Qp, H * QK_W, h * QK_W);
-          else if (seg == 1) flush(o, Kp, H * QK_W, h * QK_W);
-          else flush(o, Vp, H * V_W, h * V_W);
+          if (hh == 0) begin_round();
+          put(hh, o);
+        }
+        {
+          const CUtensorMap* m = seg == 0 ? &map_sq : (seg == 1 ? &map_sk : &map_sv);
+          const int w = seg == 2 ? V_W : QK_W;
+          end_round(m, h0 * w, m, (h0 + 1) * w);
         }
       } else {
         // ---------------- two heads of points: 8 points x 3 each; euclidean_transform (diffab_pytorch.py:315-324)
@@ -231,7 +246,9 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
               o[q] = make_uint4(pk_h(gl[8 * q], gl[8 * q + 1]), pk_h(gl[8 * q + 2], gl[8 * q + 3]),
                                 pk_h(gl[8 * q + 4], gl[8 * q + 5]), pk_h(gl[8 * q + 6], gl[8 * q + 7]));
             o[3] = make_uint4(pk_h(1.0f, 0.0f), 0, 0, 0);
-            flush(o, Vp, H * V_W, h * V_W + 32);
+            if (hh == 0) begin_round();
+            put(hh, o);
+            if (hh == 1) end_round(&map_sv, h0 * V_W + 32, &map_sv, (h0 + 1) * V_W + 32);
           } else {
             const float ch = st * sp * __ldg(gamma + h) * kLog2e;
             const float sc = seg == 0 ? ch : 1.0f;
@@ -263,14 +280,17 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
             }
             oh[3] = tail;
             ol[3] = make_uint4(0, 0, 0, 0);
-            __nv_bfloat16* dstp = seg == 0 ? Qp : Kp;
-            flush(oh, dstp, H * QK_W, h * QK_W + 32);
-            flush(ol, dstp, H * QK_W, h * QK_W + 64);
+            const CUtensorMap* m = seg == 0 ? &map_sq : &map_sk;
+            begin_round();
+            put(0, oh);
+            put(1, ol);
+            end_round(m, h * QK_W + 32, m, h * QK_W + 64);
           }
         }
       }
       if (tt == 4 || tt == 16) PROJ_STAMP(tt == 4 ? 4 : 7);
     }
+    if (gt == 0) tma_store_wait_all();
   }
   tcgen05_fence_before_sync();
   __syncthreads();

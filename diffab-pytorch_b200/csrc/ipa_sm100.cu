@@ -933,7 +933,16 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
       cudaFuncSetAttribute(ipa_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ProjSmem::kTotal);
       proj_attr_done = true;
     }
-    ipa_proj_kernel<<<B, 288, ProjSmem::kTotal, s>>>(mw64, mw48, x, R, t, reinterpret_cast<const float*>(pk + po.gamma),
+    CUtensorMap msq, msk, msv;   // TMA-store views of the packed operands: 64-byte segments of 128 rows
+    {
+      uint64_t dqk[2] = {(uint64_t)H * QK_W, (uint64_t)M}, sqk[1] = {(uint64_t)H * QK_W * 2};
+      uint64_t dv[2] = {(uint64_t)H * V_W, (uint64_t)M}, sv[1] = {(uint64_t)H * V_W * 2};
+      uint32_t bs[2] = {32, L};
+      if (int rc = make_tensor_map_bf16(&msq, ws.Qp, 2, dqk, sqk, bs, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+      if (int rc = make_tensor_map_bf16(&msk, ws.Kp, 2, dqk, sqk, bs, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+      if (int rc = make_tensor_map_bf16(&msv, ws.Vp, 2, dv, sv, bs, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    }
+    ipa_proj_kernel<<<B, 288, ProjSmem::kTotal, s>>>(mw64, mw48, msq, msk, msv, x, R, t, reinterpret_cast<const float*>(pk + po.gamma),
                                                      ws.Qp, ws.Kp, ws.Vp, ws.tc, g_core_dbg ? g_core_dbg + (1 << 20) : nullptr);
     count_launch();
   }
