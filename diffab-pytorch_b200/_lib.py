@@ -79,6 +79,7 @@ EXPORTS = {
     "dab_ipa_bwd_sm100": (c_int, [POINTER(DabIpaDims), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dab_debug_set_bwd_timeline": (c_int, [c_void_p]),
+    "dab_debug_bwd_keep_qkv": (c_int, [c_int]),
     "dab_debug_bwd_sm100_buffers": (c_int, [POINTER(DabIpaDims), c_void_p, c_void_p]),
     "dab_heads_packed_bytes": (c_size_t, []),
     "dab_heads_pack_weights": (c_int, [POINTER(DabHeadWeights), c_void_p, c_void_p]),

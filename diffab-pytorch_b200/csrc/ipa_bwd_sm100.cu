@@ -25,9 +25,9 @@
 //          Z    += e[i]^T dl_i             (to_pair_bias gradient)        M=64 c,  N=8 h,  K=128 j
 //        dQ^T_h = K_h[:, :64]^T dl_h       (scalar + point-hi columns)    M=64,    N=16 i, K=128 j
 //      P and dl also go to HBM as bf16 [b][h][i][j] for the key side.
-//   3. ipa_bwd_keyside_kernel: per (patch, head): dV_h = P_h^T dO_h, dK_h = dl_h^T Q_h[:, :64]   M=128 j, N=64, K=128 i
-//   4. bwd_assemble_kernel  : scales, the -c q~ sum dl corrections, global -> local frame -> dproj rows
-//   5. bwd_finalize_kernel  : reduces the per-CTA partials into dWpb and dgamma
+//   3. ipa_bwd_keyside_kernel: per (patch, head): dV_h = P_h^T dO_h, dK_h = dl_h^T Q_h[:, :64], dQ_h = dl_h K_h[:, :64]
+//      and, in its epilogue: scales, the -c q~ sum dl corrections, global -> local frame -> dproj rows (bf16)
+//   4. bwd_reduce_kernel / bwd_finalize_kernel: reduce the per-CTA partials into dWpb and dgamma
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <math.h>
@@ -41,6 +41,7 @@ namespace sm100 {
 
 constexpr float kLn2 = 0.6931471805599453f;
 static long long* g_bwd_dbg = nullptr;   // optional per-CTA clock64 timeline (dab_debug_set_bwd_timeline)
+static int g_bwd_keep_qkv = 0;           // test hook: also write the raw dQ / dK / dV accumulators
 
 // ---- backward workspace ---------------------------------------------------------------------------------
 struct BwdWs {
@@ -50,8 +51,8 @@ struct BwdWs {
   float* delta;             // [rows][8]
   float* rscale;            // [rows] 1 / 2^k(row)
   __nv_bfloat16 *Pn, *dL;   // [B][8][128 i][128 j] bf16
-  float *dQ, *dK, *dV;      // [rows][8][64] fp32
-  float *p_wpb, *p_g1, *p_g2;   // partials: [B*8][512], [B*8][8], [rows/32][8]
+  float *dQ, *dK, *dV;      // [rows][8][64] fp32: raw key-side accumulators, written only for tests (contiguous)
+  float *p_wpb, *p_g1, *p_g2;   // partials: [B*8][512], [B*8][8], [B][8]
   float* r_part;                // [32][528] second-level partials
   size_t bytes;
 };
@@ -72,7 +73,7 @@ inline BwdWs carve_bwd(int B, void* base) {
   w.dV = reinterpret_cast<float*>(p); p += al(rows * H * 64 * 4);
   w.p_wpb = reinterpret_cast<float*>(p); p += al((size_t)B * 8 * 512 * 4);
   w.p_g1 = reinterpret_cast<float*>(p); p += al((size_t)B * 8 * 8 * 4);
-  w.p_g2 = reinterpret_cast<float*>(p); p += al((rows / 32) * 8 * 4);
+  w.p_g2 = reinterpret_cast<float*>(p); p += al((size_t)B * 8 * 4);
   w.r_part = reinterpret_cast<float*>(p); p += al(32 * 528 * 4);
   w.bytes = (size_t)(p - reinterpret_cast<uint8_t*>(base));
   return w;
@@ -530,8 +531,9 @@ static_assert(KsSmem::kTotal <= 113 * 1024, "two CTAs per SM");
 __global__ void __launch_bounds__(160, 2)
 ipa_bwd_keyside_kernel(const __grid_constant__ CUtensorMap map_pn, const __grid_constant__ CUtensorMap map_dl,
                        const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_q64,
-                       const __grid_constant__ CUtensorMap map_k64, float* __restrict__ dQ, float* __restrict__ dK,
-                       float* __restrict__ dV) {
+                       const __grid_constant__ CUtensorMap map_k64, const __nv_bfloat16* __restrict__ Qp,
+                       const __nv_bfloat16* __restrict__ Kp, const float* __restrict__ R, const float* __restrict__ gamma,
+                       __nv_bfloat16* __restrict__ dproj, float* __restrict__ p_g2, float* __restrict__ dbg_qkv) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using S = KsSmem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
@@ -593,120 +595,124 @@ ipa_bwd_keyside_kernel(const __grid_constant__ CUtensorMap map_pn, const __grid_
       umma_commit(&bars[2]);
     }
   } else {
+    // ---- epilogue: thread = residue (key row j for dV / dK, query row i for dQ), head h.  Scales, the
+    //      -c q~ sum dl corrections, global -> local frame, and the result goes straight into the dproj row
+    //      (bf16; row layout = rows of Wcat: [q_s 256 | k_s 256 | v_s 256 | q_p 192 | k_p 192 | v_p 192]).
+    float* s_g2 = reinterpret_cast<float*>(smem + S::kBars + 32);
+    const int64_t row = (int64_t)b * L + tid;
+    float Rm[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) Rm[c] = __ldg(R + row * 9 + c);
+    const float ss = rsqrtf((float)DS), sp = rsqrtf(4.5f * P), st = rsqrtf(3.0f);
+    const float c1 = st * sp * __ldg(gamma + h);
+    __nv_bfloat16* out = dproj + row * NPROJ;
     mbar_wait(&bars[2], 0);
     tcgen05_fence_after_sync();
     const uint32_t tmem_lane = tmem + ((uint32_t)(warp * 32) << 16);
-    const size_t o = (((size_t)b * L + tid) * H + h) * 64;
-#pragma unroll
-    for (int part = 0; part < 6; ++part) {
-      float v[32];
-      tmem_ld_x32(tmem_lane + part * 32, v);
+    float U[64];
+    auto load64 = [&](int m) {
+      float a[32], c[32];
+      tmem_ld_x32(tmem_lane + m * 64, a);
+      tmem_ld_x32(tmem_lane + m * 64 + 32, c);
       tmem_wait_ld();
-      float4* dst = reinterpret_cast<float4*>((part < 2 ? dV : (part < 4 ? dK : dQ)) + o + (part & 1) * 32);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      for (int i = 0; i < 32; ++i) { U[i] = a[i]; U[32 + i] = c[i]; }
+      if (dbg_qkv) {   // test hook: raw accumulators [matrix][row][head][64]
+        float* d = dbg_qkv + (((size_t)(2 - m) * (gridDim.x / H) * L + row) * H + h) * 64;   // slots dQ, dK, dV
+#pragma unroll
+        for (int i = 0; i < 64; ++i) d[i] = U[i];
+      }
+    };
+    auto store_scalars = [&](int seg, float scale) {
+      uint4* dst = reinterpret_cast<uint4*>(out + seg * NS + h * DS);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        dst[q] = make_uint4(pack_bf162(U[8 * q] * scale, U[8 * q + 1] * scale), pack_bf162(U[8 * q + 2] * scale, U[8 * q + 3] * scale),
+                            pack_bf162(U[8 * q + 4] * scale, U[8 * q + 5] * scale), pack_bf162(U[8 * q + 6] * scale, U[8 * q + 7] * scale));
+    };
+    // global-frame gradient gp[24] -> local frame (p_glob = p_loc R + t  =>  dp_loc = dp_glob R^T)
+    auto store_points = [&](int seg, const float (&gp)[24]) {
+      float loc[24];
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const float x = gp[3 * p], y = gp[3 * p + 1], z = gp[3 * p + 2];
+        loc[3 * p] = x * Rm[0] + y * Rm[1] + z * Rm[2];
+        loc[3 * p + 1] = x * Rm[3] + y * Rm[4] + z * Rm[5];
+        loc[3 * p + 2] = x * Rm[6] + y * Rm[7] + z * Rm[8];
+      }
+      uint4* dst = reinterpret_cast<uint4*>(out + 3 * NS + seg * NPT + h * 24);
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        dst[q] = make_uint4(pack_bf162(loc[8 * q], loc[8 * q + 1]), pack_bf162(loc[8 * q + 2], loc[8 * q + 3]),
+                            pack_bf162(loc[8 * q + 4], loc[8 * q + 5]), pack_bf162(loc[8 * q + 6], loc[8 * q + 7]));
+    };
+    auto load_points = [&](const __nv_bfloat16* src, float (&pt)[24]) {   // hi + lo of the packed row
+      const uint4* r = reinterpret_cast<const uint4*>(src + row * (H * QK_W) + h * QK_W);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const uint4 hi = __ldg(r + 4 + q), lo = __ldg(r + 8 + q);
+        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&hi);
+        const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&lo);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = __bfloat1622float2(hp[e]), c = __bfloat1622float2(lp[e]);
+          pt[8 * q + 2 * e] = a.x + c.x;
+          pt[8 * q + 2 * e + 1] = a.y + c.y;
+        }
+      }
+    };
+    float gp[24], pt[24];
+    // ---- values: dV = sum_i P [dos | dog]
+    load64(0);
+    store_scalars(2, 1.0f);
+#pragma unroll
+    for (int c = 0; c < 24; ++c) gp[c] = U[32 + c];
+    store_points(2, gp);
+    // ---- key side: W = sum_i dl [st ss log2e qs | c_h log2e q~hi | 1 1 1 | 0]
+    load64(1);
+    store_scalars(1, kLn2);
+    load_points(Kp, pt);                       // = k~
+    {
+      const float rj = U[56];
+#pragma unroll
+      for (int c = 0; c < 24; ++c) gp[c] = U[32 + c] * kLn2 - c1 * pt[c] * rj;
     }
+    store_points(1, gp);
+    // ---- query side: U = sum_j dl [ks | k~hi | norm columns | 1]
+    load64(2);
+    float g2 = 0.f;
+    {
+      const uint4* qr = reinterpret_cast<const uint4*>(Qp + row * (H * QK_W) + h * QK_W);   // Qp_s = st ss log2e qs
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 v = __ldg(qr + q);
+        const __nv_bfloat162* vp = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = __bfloat1622float2(vp[e]);
+          g2 = fmaf(a.x, U[8 * q + 2 * e], g2);
+          g2 = fmaf(a.y, U[8 * q + 2 * e + 1], g2);
+        }
+      }
+      g2 *= kLn2;
+    }
+    store_scalars(0, st * ss);
+    load_points(Qp, pt);                       // = c_h log2e q~
+    {
+      const float si = U[59];
+#pragma unroll
+      for (int c = 0; c < 24; ++c) gp[c] = c1 * U[32 + c] - pt[c] * kLn2 * si;
+    }
+    store_points(0, gp);
+    // ---- sum_i <qs, dqs> of this (patch, head) for dgamma
+    g2 = warp_sum(g2);
+    if (lane == 0) s_g2[warp] = g2;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (tid == 0) p_g2[blockIdx.x] = s_g2[0] + s_g2[1] + s_g2[2] + s_g2[3];
   }
   tcgen05_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_free(tmem, 256);
-}
-
-// ---- 4. assemble dproj ---------------------------------------------------------------------------------------
-// thread = (residue row, head); block = 32 rows.  dproj row layout = rows of Wcat:
-// [q_s 256 | k_s 256 | v_s 256 | q_p 192 | k_p 192 | v_p 192], (h d) / (h p c) inside each segment.
-__global__ void __launch_bounds__(256) bwd_assemble_kernel(const float* __restrict__ dQ, const float* __restrict__ dK,
-                                                           const float* __restrict__ dV, const __nv_bfloat16* __restrict__ Qp,
-                                                           const __nv_bfloat16* __restrict__ Kp, const float* __restrict__ R,
-                                                           const float* __restrict__ gamma, float* __restrict__ dproj,
-                                                           float* __restrict__ p_g2) {
-  __shared__ float s_g2[8][8];
-  const int64_t row = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
-  const int h = threadIdx.x & 7;
-  const float ss = rsqrtf((float)DS), sp = rsqrtf(4.5f * P), st = rsqrtf(3.0f);
-  const float c1 = st * sp * gamma[h];
-  const size_t o = (row * H + h) * 64;
-  float U[64], Rm[9];
-#pragma unroll
-  for (int c = 0; c < 9; ++c) Rm[c] = R[row * 9 + c];
-  float* out = dproj + row * NPROJ;
-  auto load64 = [&](const float* src) {
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const float4 v = *reinterpret_cast<const float4*>(src + o + 4 * q);
-      U[4 * q] = v.x; U[4 * q + 1] = v.y; U[4 * q + 2] = v.z; U[4 * q + 3] = v.w;
-    }
-  };
-  auto store_scalars = [&](int seg, float scale) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      *reinterpret_cast<float4*>(out + seg * NS + h * DS + 4 * q) =
-          make_float4(U[4 * q] * scale, U[4 * q + 1] * scale, U[4 * q + 2] * scale, U[4 * q + 3] * scale);
-  };
-  // global-frame gradient g[24] -> local frame (p_glob = p_loc R + t  =>  dp_loc = dp_glob R^T) -> dproj
-  auto store_points = [&](int seg, const float (&gp)[24]) {
-    float loc[24];
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-      const float x = gp[3 * p], y = gp[3 * p + 1], z = gp[3 * p + 2];
-      loc[3 * p] = x * Rm[0] + y * Rm[1] + z * Rm[2];
-      loc[3 * p + 1] = x * Rm[3] + y * Rm[4] + z * Rm[5];
-      loc[3 * p + 2] = x * Rm[6] + y * Rm[7] + z * Rm[8];
-    }
-#pragma unroll
-    for (int q = 0; q < 6; ++q)
-      *reinterpret_cast<float4*>(out + 3 * NS + seg * NPT + h * 24 + 4 * q) =
-          make_float4(loc[4 * q], loc[4 * q + 1], loc[4 * q + 2], loc[4 * q + 3]);
-  };
-  auto load_points = [&](const __nv_bfloat16* src, float (&pt)[24]) {   // hi + lo of the packed row
-    const __nv_bfloat16* r = src + row * (H * QK_W) + h * QK_W;
-#pragma unroll
-    for (int c = 0; c < 24; ++c) pt[c] = __bfloat162float(r[32 + c]) + __bfloat162float(r[64 + c]);
-  };
-  float gp[24], pt[24];
-  // ---- query side: U = sum_j dl [ks | k~hi | norm columns | 1]
-  load64(dQ);
-  float g2 = 0.f;
-  {
-    const __nv_bfloat16* qr = Qp + row * (H * QK_W) + h * QK_W;
-#pragma unroll
-    for (int d = 0; d < DS; ++d) g2 = fmaf(__bfloat162float(qr[d]), U[d], g2);   // Qp_s = st ss log2e qs
-    g2 *= kLn2;
-  }
-  store_scalars(0, st * ss);
-  load_points(Qp, pt);                       // = c_h log2e q~
-  {
-    const float si = U[59];
-#pragma unroll
-    for (int c = 0; c < 24; ++c) gp[c] = c1 * U[32 + c] - pt[c] * kLn2 * si;
-  }
-  store_points(0, gp);
-  // ---- key side: W = sum_i dl [st ss log2e qs | c_h log2e q~hi | 1 1 1 | 0]
-  load64(dK);
-  store_scalars(1, kLn2);
-  load_points(Kp, pt);                       // = k~
-  {
-    const float rj = U[56];
-#pragma unroll
-    for (int c = 0; c < 24; ++c) gp[c] = U[32 + c] * kLn2 - c1 * pt[c] * rj;
-  }
-  store_points(1, gp);
-  // ---- values
-  load64(dV);
-  store_scalars(2, 1.0f);
-#pragma unroll
-  for (int c = 0; c < 24; ++c) gp[c] = U[32 + c];
-  store_points(2, gp);
-  // ---- sum_i <qs, dqs> per head (lanes with equal h: xor 8, 16; then across the 8 warps)
-  g2 += __shfl_xor_sync(0xffffffffu, g2, 8);
-  g2 += __shfl_xor_sync(0xffffffffu, g2, 16);
-  if ((threadIdx.x & 31) < 8) s_g2[threadIdx.x >> 5][h] = g2;
-  __syncthreads();
-  if (threadIdx.x < 8) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += s_g2[w][threadIdx.x];
-    p_g2[(size_t)blockIdx.x * 8 + threadIdx.x] = s;
-  }
 }
 
 // ---- 5. finalize -------------------------------------------------------------------------------------------
@@ -771,16 +777,16 @@ extern "C" {
 size_t dab_ipa_bwd_sm100_workspace_bytes(const DabIpaDims* d) { return shape_ok(d) ? carve_bwd(d->B, nullptr).bytes : 0; }
 
 int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf16, const float* R, const float* dcat,
-                      void* saved, size_t saved_bytes, float* dproj, void* de_bf16, float* d_w_pair_bias, float* d_gamma,
+                      void* saved, size_t saved_bytes, void* dproj_bf16, void* de_bf16, float* d_w_pair_bias, float* d_gamma,
                       void* workspace, size_t workspace_bytes, void* stream) {
   DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
               "dab_ipa_bwd_sm100: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
   if (d->B == 0) return DAB_OK;
-  DAB_REQUIRE(packed && e_bf16 && R && dcat && saved && dproj && de_bf16 && d_w_pair_bias && d_gamma && workspace,
+  DAB_REQUIRE(packed && e_bf16 && R && dcat && saved && dproj_bf16 && de_bf16 && d_w_pair_bias && d_gamma && workspace,
               DAB_EINVAL, "dab_ipa_bwd_sm100: null pointer");
   DAB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0 && (reinterpret_cast<uintptr_t>(saved) & 1023) == 0 &&
                   (reinterpret_cast<uintptr_t>(e_bf16) & 127) == 0 && (reinterpret_cast<uintptr_t>(de_bf16) & 127) == 0 &&
-                  aligned16(dcat) && aligned16(dproj),
+                  aligned16(dcat) && aligned16(dproj_bf16),
               DAB_EINVAL, "dab_ipa_bwd_sm100: misaligned pointer (workspaces 1024 B, e/de 128 B, dcat/dproj 16 B)");
   const int B = d->B, M = B * L;
   Ws ws = carve_ws(B, saved);
@@ -833,16 +839,21 @@ int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf1
     if (int rc = make_tensor_map_bf16(&mq64, ws.Qp, 2, dqk, sqk, bv, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (int rc = make_tensor_map_bf16(&mk64, ws.Kp, 2, dqk, sqk, bv, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
-  ipa_bwd_keyside_kernel<<<B * H, 160, KsSmem::kTotal, s>>>(mpn, mdl, mdob, mq64, mk64, bw.dQ, bw.dK, bw.dV);
+  ipa_bwd_keyside_kernel<<<B * H, 160, KsSmem::kTotal, s>>>(mpn, mdl, mdob, mq64, mk64, ws.Qp, ws.Kp, R, gamma,
+                                                            reinterpret_cast<__nv_bfloat16*>(dproj_bf16), bw.p_g2,
+                                                            g_bwd_keep_qkv ? bw.dQ : nullptr);
   count_launch();
-
-  bwd_assemble_kernel<<<M / 32, 256, 0, s>>>(bw.dQ, bw.dK, bw.dV, ws.Qp, ws.Kp, R, gamma, dproj, bw.p_g2);
-  count_launch();
-  bwd_reduce_kernel<<<kRedBlocks, 512, 0, s>>>(bw.p_wpb, B * 8, bw.p_g1, bw.p_g2, M / 32, bw.r_part);
+  bwd_reduce_kernel<<<kRedBlocks, 512, 0, s>>>(bw.p_wpb, B * 8, bw.p_g1, bw.p_g2, B, bw.r_part);
   count_launch();
   bwd_finalize_kernel<<<1, 512, 0, s>>>(bw.r_part, wpb, gamma, d_w_pair_bias, d_gamma);
   count_launch();
   return check_launch("dab_ipa_bwd_sm100");
+}
+
+/* Test hook: keep the raw key-side accumulators (dQ, dK, dV of dab_debug_bwd_sm100_buffers) on later calls. */
+int dab_debug_bwd_keep_qkv(int on) {
+  g_bwd_keep_qkv = on;
+  return DAB_OK;
 }
 
 /* Profiling hook: per-CTA clock64 timeline of the backward core (64 slots per CTA), NULL to disable. */

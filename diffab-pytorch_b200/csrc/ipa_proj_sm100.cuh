@@ -53,7 +53,7 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
                 const __grid_constant__ CUtensorMap map_sv, const float* __restrict__ x, const float* __restrict__ R, const float* __restrict__ t,
                 const float* __restrict__ gamma, __nv_bfloat16* __restrict__ Qp, __nv_bfloat16* __restrict__ Kp,
                 __nv_bfloat16* __restrict__ Vp, float* __restrict__ tc, long long* __restrict__ dbg) {
-  long long* dbg_cta = dbg ? dbg + (size_t)blockIdx.x * 64 : nullptr;
+  long long* dbg_cta = dbg ? dbg + (size_t)blockIdx.y * 64 : nullptr;   // (split 0 of) one patch per record
 #define PROJ_STAMP(k) do { if (dbg_cta && threadIdx.x == 0) dbg_cta[(k)] = clock64(); } while (0)
   PROJ_STAMP(0);
   constexpr int L = 128, D = 128, H = 8, DS = 32, P = 8, QK_W = 96, V_W = 64;
@@ -64,7 +64,8 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
   float* s_cen = reinterpret_cast<float*>(smem + S::kCen);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x;
+  // grid (n_split, B): CTA (s, b) computes tiles s, s + n_split, ... of patch b (small batches: more CTAs per patch)
+  const int b = blockIdx.y, split = blockIdx.x, n_split = gridDim.x, n_local = kProjTiles / n_split;
   const uint32_t smem_base = smem_u32(smem);
   if ((smem_base & 1023u) != 0) asm volatile("trap;");
 
@@ -106,8 +107,8 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
       tma_prefetch_desc(&map_w48);
       auto tile_rows = [](int tt) { return tt < 12 ? 64 : 48; };
       auto tile_row0 = [](int tt) { return tt < 12 ? tt * 64 : 768 + (tt - 12) * 48; };
-      auto load_w = [&](int tt) {
-        const int s = tt % S::kWStages;
+      auto load_w = [&](int tt, int k) {
+        const int s = k % S::kWStages;
         uint8_t* dst = smem + S::kW + s * S::kWStage;
         const int rows = tile_rows(tt);
         mbar_arrive_expect_tx(&bars[W_FULL + s], 2 * rows * 128);
@@ -115,28 +116,29 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
         tma_load_2d(dst, m, &bars[W_FULL + s], 0, tile_row0(tt));            // K 0..63
         tma_load_2d(dst + rows * 128, m, &bars[W_FULL + s], 64, tile_row0(tt));  // K 64..127
       };
-      for (int tt = 0; tt < S::kWStages; ++tt) load_w(tt);
+      for (int k = 0; k < S::kWStages && k < n_local; ++k) load_w(split + k * n_split, k);
       const uint32_t a_addr = smem_base + S::kA;
-      for (int tt = 0; tt < kProjTiles; ++tt) {
-        const int s = tt % S::kWStages, acc = tt & 1;
+      for (int k = 0; k < n_local; ++k) {       // k-th tile of this CTA = global tile tt
+        const int tt = split + k * n_split;
+        const int s = k % S::kWStages, acc = k & 1;
         const int rows = tile_rows(tt);
-        mbar_wait(&bars[W_FULL + s], (tt / S::kWStages) & 1);
-        if (tt >= 2) mbar_wait(&bars[ACC_EMPTY + acc], ((tt >> 1) - 1) & 1);   // epilogue drained this accumulator
+        mbar_wait(&bars[W_FULL + s], (k / S::kWStages) & 1);
+        if (k >= 2) mbar_wait(&bars[ACC_EMPTY + acc], ((k >> 1) - 1) & 1);   // epilogue drained this accumulator
         tcgen05_fence_after_sync();
         const uint32_t w_addr = smem_base + S::kW + s * S::kWStage;
         const uint32_t idesc = make_idesc_bf16(128, rows, 0, 0);
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          uint64_t da = make_smem_desc(a_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, kSwizzle128B);
-          uint64_t db = make_smem_desc(w_addr + (k >> 2) * (rows * 128) + (k & 3) * 32, 16, 1024, kSwizzle128B);
-          umma_bf16(tmem + acc * 64, da, db, idesc, k != 0);
+        for (int kk = 0; kk < D / 16; ++kk) {
+          uint64_t da = make_smem_desc(a_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, kSwizzle128B);
+          uint64_t db = make_smem_desc(w_addr + (kk >> 2) * (rows * 128) + (kk & 3) * 32, 16, 1024, kSwizzle128B);
+          umma_bf16(tmem + acc * 64, da, db, idesc, kk != 0);
         }
         umma_commit(&bars[ACC_FULL + acc]);
         umma_commit(&bars[W_EMPTY + s]);
-        if (tt >= 1 && tt - 1 + S::kWStages < kProjTiles) {
-          const int sp = (tt - 1) % S::kWStages;
-          mbar_wait(&bars[W_EMPTY + sp], ((tt - 1) / S::kWStages) & 1);
-          load_w(tt - 1 + S::kWStages);
+        if (k >= 1 && k - 1 + S::kWStages < n_local) {
+          const int sp = (k - 1) % S::kWStages;
+          mbar_wait(&bars[W_EMPTY + sp], ((k - 1) / S::kWStages) & 1);
+          load_w(split + (k - 1 + S::kWStages) * n_split, k - 1 + S::kWStages);
         }
       }
     }
@@ -152,7 +154,7 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
 #pragma unroll
     for (int c = 0; c < 9; ++c) Rm[c] = __ldg(R + row * 9 + c);
     const float tcx = __ldg(t + row * 3) - cenx, tcy = __ldg(t + row * 3 + 1) - ceny, tcz = __ldg(t + row * 3 + 2) - cenz;
-    if (g == 0) { tc[row * 3] = tcx; tc[row * 3 + 1] = tcy; tc[row * 3 + 2] = tcz; }
+    if (g == 0 && split == 0) { tc[row * 3] = tcx; tc[row * 3 + 1] = tcy; tc[row * 3 + 2] = tcz; }
     const float ss = rsqrtf((float)DS), sp = rsqrtf(4.5f * P), st = rsqrtf(3.0f);
     // Every output segment is 64 bytes per residue (a head's scalars, point-hi or point-lo columns).  A thread
     // drops its segment into a [128 rows][64 B] shared-memory tile (64B swizzle: conflict-free 16-byte stores) and
@@ -182,9 +184,10 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
       }
     };
 
-    for (int tt = g; tt < kProjTiles; tt += 2) {
+    for (int k = g; k < n_local; k += 2) {
+      const int tt = split + k * n_split;
       const int acc = g;
-      mbar_wait(&bars[ACC_FULL + acc], (tt >> 1) & 1);
+      mbar_wait(&bars[ACC_FULL + acc], (k >> 1) & 1);
       tcgen05_fence_after_sync();
       if (tt == 4 || tt == 16) PROJ_STAMP(tt == 4 ? 2 : 5);
       float v[64];

@@ -942,7 +942,8 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
       if (int rc = make_tensor_map_bf16(&msk, ws.Kp, 2, dqk, sqk, bs, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
       if (int rc = make_tensor_map_bf16(&msv, ws.Vp, 2, dv, sv, bs, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
     }
-    ipa_proj_kernel<<<B, 288, ProjSmem::kTotal, s>>>(mw64, mw48, msq, msk, msv, x, R, t, reinterpret_cast<const float*>(pk + po.gamma),
+    const int n_split = B >= 128 ? 1 : (B >= 64 ? 2 : 4);   // small batches: several CTAs per patch
+    ipa_proj_kernel<<<dim3(n_split, B), 288, ProjSmem::kTotal, s>>>(mw64, mw48, msq, msk, msv, x, R, t, reinterpret_cast<const float*>(pk + po.gamma),
                                                      ws.Qp, ws.Kp, ws.Vp, ws.tc, g_core_dbg ? g_core_dbg + (1 << 20) : nullptr);
     count_launch();
   }
@@ -977,8 +978,10 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
     count_launch();
   }
   if (phases & 4) {
-    if (int rc = launch_gemm_bf16<128>(ws.cat, NCAT, pk + po.wout, NCAT, y, D, reinterpret_cast<const float*>(pk + po.bout),
-                                       M, D, NCAT, s))
+    // y = cat Wout^T + b: one 128-wide N tile per CTA when the batch fills the GPU, four 32-wide ones otherwise
+    const float* bo = reinterpret_cast<const float*>(pk + po.bout);
+    if (int rc = (M / kGemmBM >= 148) ? launch_gemm_bf16<128>(ws.cat, NCAT, pk + po.wout, NCAT, y, D, bo, M, D, NCAT, s)
+                                      : launch_gemm_bf16<32>(ws.cat, NCAT, pk + po.wout, NCAT, y, D, bo, M, D, NCAT, s))
       return rc;
   }
   return check_launch("dab_ipa_fwd_sm100");

@@ -281,12 +281,15 @@ class _IpaFastFunction(torch.autograd.Function):
         ncat = w_out.shape[1]
         cat = saved[offs[4]: offs[4] + M * ncat * 2].view(torch.bfloat16).view(M, ncat)
         dy2 = _lib.dev(dy, torch.float32, "dy").view(M, D)
-        with _tf32_matmuls(True):
-            dcat = dy2 @ w_out                                   # (M, 1024)
-            d_w_out = dy2.t() @ cat.float()
-        d_b_out = dy2.sum(0)
+        # the four plain GEMMs of the backward: library GEMMs on bf16 operands with fp32 accumulation and output
+        # (the forward ran the same products on bf16 operands)
+        bf = torch.bfloat16
+        dy_bf = dy2.to(bf)
+        dcat = torch.mm(dy_bf, w_out.to(bf), out_dtype=torch.float32)          # (M, 1024)
+        d_w_out = torch.mm(dy_bf.t(), cat, out_dtype=torch.float32)            # (D, 1024)
+        d_b_out = torch.mv(dy2.t(), torch.ones(M, device=dy2.device))
         w_cat = torch.cat(weights[:6], dim=0)                    # (1344, D)
-        dproj = torch.empty(M, w_cat.shape[0], device=x.device, dtype=torch.float32)
+        dproj = torch.empty(M, w_cat.shape[0], device=x.device, dtype=bf)
         de = torch.empty_like(e)
         d_wpb = torch.zeros_like(weights[6])
         d_gamma = torch.zeros_like(weights[7])
@@ -295,9 +298,8 @@ class _IpaFastFunction(torch.autograd.Function):
                                          saved.numel(), ptr(dproj), ptr(de), ptr(d_wpb), ptr(d_gamma), ptr(bws),
                                          bws.numel(), _lib.stream_ptr()), "dab_ipa_bwd_sm100")
         layer._last_bwd_ws = bws   # kept for tools/debug_bwd.py (intermediate buffers of the last backward)
-        with _tf32_matmuls(True):
-            dx = (dproj @ w_cat).view(B, L, D)
-            d_w_cat = dproj.t() @ x.view(M, D)
+        dx = torch.mm(dproj, w_cat.to(bf), out_dtype=torch.float32).view(B, L, D)
+        d_w_cat = torch.mm(dproj.t(), x.view(M, D).to(bf), out_dtype=torch.float32)
         d_proj_w = torch.split(d_w_cat, [w.shape[0] for w in weights[:6]], dim=0)
         return (None, None, dx, de, None, None, *d_proj_w, d_wpb, d_gamma, d_w_out, d_b_out)
 

@@ -181,7 +181,7 @@ int dab_ipa_fwd_sm100_train(const DabIpaDims* d, const void* packed, const float
 /* Backward of the attention part of the layer (autograd of diffab_pytorch.py:389-462) on tcgen05:
  *   in : dcat[B*L,1024] fp32 = dy . to_out.weight (gradient of the concat features; a plain GEMM of the caller),
  *        e_bf16, R, `saved` from dab_ipa_fwd_sm100_train, `packed` weights;
- *   out: dproj[B*L,1344] fp32 = gradient of the six projections in the row order of
+ *   out: dproj_bf16[B*L,1344] bf16 = gradient of the six projections in the row order of
  *        [to_q_scalar; to_k_scalar; to_v_scalar; to_q_point; to_k_point; to_v_point] (so dx = dproj . Wcat and
  *        dWcat = dproj^T . x are plain GEMMs of the caller), de_bf16[B,L,L,C] bf16 (overwritten),
  *        d_w_pair_bias[8,64] and d_gamma[8] (accumulated into).
@@ -189,9 +189,10 @@ int dab_ipa_fwd_sm100_train(const DabIpaDims* d, const void* packed, const float
 int dab_ipa_sm100_workspace_layout(const DabIpaDims* d, size_t* offsets /* 7: Qp, Kp, Vp, tc, cat, bias, stats */);
 size_t dab_ipa_bwd_sm100_workspace_bytes(const DabIpaDims* d);
 int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf16, const float* R, const float* dcat,
-                      void* saved, size_t saved_bytes, float* dproj, void* de_bf16, float* d_w_pair_bias, float* d_gamma,
+                      void* saved, size_t saved_bytes, void* dproj_bf16, void* de_bf16, float* d_w_pair_bias, float* d_gamma,
                       void* workspace, size_t workspace_bytes, void* stream);
 int dab_debug_set_bwd_timeline(long long* device_buf /* 64 slots per CTA of the backward core, or NULL */);
+int dab_debug_bwd_keep_qkv(int on);
 int dab_debug_bwd_sm100_buffers(const DabIpaDims* d, void* workspace, void** out /* 10 device pointers */);
 /* ------------------------------------------------------------------ epsilon-network tail
  * The three denoising heads of Denoiser.forward (diffab_pytorch.py:584-599) for d_residue_emb = 128, L = 128, fused

@@ -43,6 +43,7 @@ logit.retain_grad()
 (yd * gy.double()).sum().backward()
 
 # ---- kernel path
+lib.dab_debug_bwd_keep_qkv(1)
 xg = x.clone().requires_grad_(True)
 eg = e16.clone().requires_grad_(True)
 y = layer(xg, eg, R, t)
