@@ -156,6 +156,11 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference_arm(args)
+    # stdout must carry exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version banner there)
+    # are sent to stderr for the whole run and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import diffab_pytorch_b200  # noqa: F401
     from diffab_pytorch_b200 import _lib, synth
@@ -321,7 +326,9 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
 
 
 def measure_roofline(model, layer, res_ctx, pair_ctx, x0, O0, precision, hbm_peak, peak_src, iters=20):
