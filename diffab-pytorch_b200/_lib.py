@@ -40,6 +40,11 @@ class DabHeadWeights(Structure):
     _fields_ = [(f"{h}_{n}", c_void_p) for h in ("c", "o", "s") for n in ("w1", "b1", "w2", "b2", "w3", "b3")]
 
 
+class DabPairEmbedWeights(Structure):
+    _fields_ = [(n, c_void_p) for n in ("type_emb", "relpos_emb", "pair2distcoef", "d_w1", "d_b1", "d_w2", "d_b2",
+                                        "m_w1", "m_b1", "m_w2", "m_b2", "m_w3", "m_b3")]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "dab_version": (c_int, []),
@@ -86,6 +91,9 @@ EXPORTS = {
     "dab_heads_fwd_sm100": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dab_front_fwd_sm100": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
+    "dab_pair_embed_packed_bytes": (c_size_t, []),
+    "dab_pair_embed_pack_weights": (c_int, [POINTER(DabPairEmbedWeights), c_void_p, c_void_p]),
+    "dab_pair_embed_fwd_sm100": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p, c_void_p]),
     "dab_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dab_debug_set_timeline": (c_int, [c_void_p]),
     "dab_debug_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

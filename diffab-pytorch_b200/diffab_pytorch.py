@@ -137,6 +137,39 @@ class PairEmbedding(nn.Module):
         d_dihedral = self.dihedral_embedding.get_output_dimension(2)
         self.mlp = _mlp([3 * d_feat + d_dihedral, d_feat, d_feat, d_feat])
 
+    def fused_supported(self, L, A):
+        """Shapes the fused tcgen05 kernel (csrc/pair_embed_sm100.cu) covers."""
+        return (L == 128 and A == 15 and self.d_feat == 64 and self.max_dist_to_consider == 32 and
+                self.pair2distcoef.weight.shape[1] == 225)
+
+    @torch.no_grad()
+    def forward_fused_bf16(self, seq_idx, xyz, dihedrals, residue_idx, chain_idx, atom_mask, sequence_context_mask):
+        """The whole module in one kernel, distances computed from ``xyz`` on the fly, output in bf16 (sampling)."""
+        B, L = seq_idx.shape
+        A = xyz.shape[2]
+        if sequence_context_mask is not None:
+            seq_idx = torch.where(sequence_context_mask.bool(), seq_idx, torch.full_like(seq_idx, AA_UNK))
+        lib = _lib.lib()
+        ws = (self.aa_pair_type_embedding.weight, self.relpos_embedding.weight, self.pair2distcoef.weight,
+              self.distance_embedding[0].weight, self.distance_embedding[0].bias, self.distance_embedding[2].weight,
+              self.distance_embedding[2].bias, self.mlp[0].weight, self.mlp[0].bias, self.mlp[2].weight,
+              self.mlp[2].bias, self.mlp[4].weight, self.mlp[4].bias)
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        if getattr(self, "_packed", None) is None or self._packed[0] != key:
+            buf = _lib.aligned_empty(lib.dab_pair_embed_packed_bytes(), xyz.device)
+            wd = [_lib.dev(w.detach(), torch.float32, "pair embedding weight") for w in ws]
+            st = _lib.DabPairEmbedWeights(*(w.data_ptr() for w in wd))
+            _lib.check(lib.dab_pair_embed_pack_weights(ctypes.byref(st), ptr(buf), _lib.stream_ptr()),
+                       "dab_pair_embed_pack_weights")
+            self._packed = (key, buf)
+        out = torch.empty(B, L, L, self.d_feat, device=xyz.device, dtype=torch.bfloat16)
+        _lib.check(lib.dab_pair_embed_fwd_sm100(
+            ptr(self._packed[1]), ptr(_lib.dev(seq_idx, torch.int64, "seq_idx")),
+            ptr(_lib.dev(xyz, torch.float32, "xyz")), ptr(_lib.dev(dihedrals, torch.float32, "pairwise_dihedrals")),
+            ptr(_lib.dev(residue_idx, torch.int64, "residue_idx")), ptr(_lib.dev(chain_idx, torch.int64, "chain_idx")),
+            ptr(_lib.mask_u8(atom_mask, "atom_mask")), B, L, A, ptr(out), _lib.stream_ptr()), "dab_pair_embed_fwd_sm100")
+        return out
+
     def forward(self, seq_idx, distmat, dihedrals, residue_idx, chain_idx, atom_mask, structure_context_mask,
                 sequence_context_mask, distmat_is_squared=False):
         B, L = seq_idx.shape
@@ -893,20 +926,30 @@ class DiffAb(nn.Module):
         distmat = mv(distmat)
         use_bf16 = precision == "bf16" and self.denoiser.ipa.layers[0].fast_path_supported(L)
         res_parts, pair_parts = [], []
+        fused_pair = (use_bf16 and distmat is None and self.pair_context_embedding.fused_supported(L, A))
         from .synth import pairwise_atom_distances, pairwise_atom_sq_distances
         # distances derived on the device: exact differences on the fp32 path, the cheaper Gram-matrix form
         # (|a|^2 + |b|^2 - 2 a.b, ~1e-3 A^2 absolute error) on the bf16 path
         derive = pairwise_atom_sq_distances if use_bf16 else (lambda v: pairwise_atom_distances(v).pow(2))
         with _tf32_matmuls(use_bf16):
-            for lo in range(0, B, context_chunk):
-                sl = slice(lo, min(B, lo + context_chunk))
-                dm = distmat[sl] if distmat is not None else derive(xyz[sl])
-                r, p = self.encode_context(seq_idx[sl], xyz[sl], orientations[sl], backbone_dihedrals[sl], dm,
-                                           pairwise_dihedrals[sl], atom_mask[sl], chain_idx[sl], residue_idx[sl],
-                                           generation_mask[sl], residue_mask[sl], distmat_is_squared=distmat is None)
-                res_parts.append(r)
-                pair_parts.append(cast_pair_to_bf16(p) if use_bf16 else p)
-        res_ctx, pair_ctx = torch.cat(res_parts), torch.cat(pair_parts)
+            if fused_pair:
+                # pair context from one fused tcgen05 kernel (bf16, distances from xyz inside the kernel); the small
+                # residue encoder stays a PyTorch module
+                ctx_mask = residue_mask & (~generation_mask)
+                res_ctx = self.residue_context_embedding(seq_idx, xyz, orientations, backbone_dihedrals, chain_idx,
+                                                         atom_mask, ctx_mask, ctx_mask)
+                pair_ctx = self.pair_context_embedding.forward_fused_bf16(seq_idx, xyz, pairwise_dihedrals, residue_idx,
+                                                                          chain_idx, atom_mask, ctx_mask)
+            else:
+                for lo in range(0, B, context_chunk):
+                    sl = slice(lo, min(B, lo + context_chunk))
+                    dm = distmat[sl] if distmat is not None else derive(xyz[sl])
+                    r, p = self.encode_context(seq_idx[sl], xyz[sl], orientations[sl], backbone_dihedrals[sl], dm,
+                                               pairwise_dihedrals[sl], atom_mask[sl], chain_idx[sl], residue_idx[sl],
+                                               generation_mask[sl], residue_mask[sl], distmat_is_squared=distmat is None)
+                    res_parts.append(r)
+                    pair_parts.append(cast_pair_to_bf16(p) if use_bf16 else p)
+                res_ctx, pair_ctx = torch.cat(res_parts), torch.cat(pair_parts)
         # t = T prior on generated residues: s ~ U{0..20}, x ~ N(0, I), O ~ uniform SO(3)
         from .synth import uniform_rotations
         m = generation_mask

@@ -217,6 +217,25 @@ int dab_heads_fwd_sm100(const void* packed, const float* x, const float* beta, i
 int dab_front_fwd_sm100(const float* c, const float* t1, const int64_t* seq, int64_t n_rows, const void* w2_bf16,
                         const float* b2, void* a_scratch, float* x0, void* stream);
 
+/* ------------------------------------------------------------------ pair context encoder
+ * PairEmbedding.forward (diffab_pytorch.py:186-312) fused into one tcgen05 kernel that writes the pair tensor in bf16
+ * (inference / sampling; L = 128 residues, 15 atoms, d_pair_emb = 64, max_dist_to_consider = 32).  Distances are
+ * computed from xyz inside the kernel.  Weights: the module's state-dict tensors, nn.Linear layout (out, in). */
+typedef struct DabPairEmbedWeights {
+  const float* type_emb;      /* aa_pair_type_embedding.weight (441, 64) */
+  const float* relpos_emb;    /* relpos_embedding.weight       (65, 64)  */
+  const float* pair2distcoef; /* pair2distcoef.weight          (441, 225) */
+  const float *d_w1, *d_b1, *d_w2, *d_b2;               /* distance_embedding.{0,2}: (64,225) (64) (64,64) (64) */
+  const float *m_w1, *m_b1, *m_w2, *m_b2, *m_w3, *m_b3; /* mlp.{0,2,4}: (64,210) (64) (64,64) (64) (64,64) (64) */
+} DabPairEmbedWeights;
+size_t dab_pair_embed_packed_bytes(void);
+int dab_pair_embed_pack_weights(const DabPairEmbedWeights* w, void* packed, void* stream);
+/* seq_masked[B,L] int64 (sequence with non-context residues already replaced by UNK, :271-273), xyz[B,L,A,3],
+ * pairwise_dihedrals[B,L,L,2], residue_idx / chain_idx [B,L] int64, atom_mask[B,L,A] uint8 -> e_bf16[B,L,L,64]. */
+int dab_pair_embed_fwd_sm100(const void* packed, const int64_t* seq_masked, const float* xyz, const float* pairwise_dihedrals,
+                             const int64_t* residue_idx, const int64_t* chain_idx, const uint8_t* atom_mask, int B, int L,
+                             int A, void* e_bf16, void* stream);
+
 /* Test hooks of the sm_100a path (used by tests/ only): the tcgen05 GEMM C[M,N] = A[M,K] B[N,K]^T + bias
  * (bf16 in, fp32 out; M % 128 == 0, N % 64 == 0, K % 64 == 0) and the operand-packing stage alone. */
 int dab_debug_set_timeline(long long* device_buf /* 64 slots per CTA of the attention core, or NULL */);

@@ -233,3 +233,33 @@ def test_regrouped_sampling_glue_matches_module_path():
     m = b["generation_mask"]
     assert (outs[0][0] != outs[1][0])[m].float().mean() <= 0.02
     assert (outs[0][1] - outs[1][1]).norm(dim=-1)[m].max() < 1e-2
+
+
+def test_fused_pair_embedding_matches_module():
+    """csrc/pair_embed_sm100.cu (PairEmbedding.forward in one tcgen05 kernel, bf16 out, distances from xyz) against the
+    PyTorch module on exact distances: bf16 operands -> 3e-2 max-normalised; masked residues give exact zeros."""
+    model = _model(0)
+    batch = synth.make_patches(3, 128, seed=21)
+    batch["atom_mask"][1, 5] = False           # a residue without atoms and one without CA
+    batch["atom_mask"][2, 17, 1] = False
+    batch["atom_mask"][0, 40, 7:] = False
+    b = _to(batch)
+    ctx = b["residue_mask"] & ~b["generation_mask"]
+    pe = model.pair_context_embedding
+    assert pe.fused_supported(128, 15)
+    with torch.no_grad():
+        ref = pe(b["seq_idx"], b["distmat"], b["pairwise_dihedrals"], b["residue_idx"], b["chain_idx"], b["atom_mask"],
+                 ctx, ctx)
+        got = pe.forward_fused_bf16(b["seq_idx"], b["xyz"], b["pairwise_dihedrals"], b["residue_idx"], b["chain_idx"],
+                                    b["atom_mask"], ctx)
+    assert got.dtype == torch.bfloat16 and got.shape == ref.shape
+    assert torch.isfinite(got.float()).all()
+    assert _rel(got.float(), ref.cpu()) < 3e-2
+    assert float(got[1, 5].float().abs().max()) == 0.0 and float(got[2, :, 17].float().abs().max()) == 0.0
+    # sampling end to end through the fused context path (bf16): frozen residues untouched, outputs finite
+    out = model.sample(batch["seq_idx"], batch["xyz"], batch["orientations"], batch["backbone_dihedrals"], None,
+                       batch["pairwise_dihedrals"], batch["atom_mask"], batch["chain_idx"], batch["residue_idx"],
+                       batch["generation_mask"], batch["residue_mask"], t_start=4, use_cuda_graph=False)
+    m = batch["generation_mask"]
+    assert torch.equal(out["seq_idx"].cpu()[~m], batch["seq_idx"][~m])
+    assert torch.isfinite(out["translations"]).all() and torch.isfinite(out["orientations"]).all()
