@@ -423,6 +423,10 @@ def measure_train_step(dev, dist, world, shapes, B=64, steps=5, warmup=3):
     model = DiffAb(*TRAIN_CFG, device=dev).train()
     model.load_state_dict(synth.synthetic_state(shapes, seed=0))
     model.train_precision = "bf16"
+    # the reference's own training entry point runs its fp32 GEMMs as TF32 (train.py:47,
+    # torch.set_float32_matmul_precision("high")); set globally so that autograd's backward GEMMs are covered too
+    prev_prec = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("high")
     bucket = GradientBucket(model.parameters())
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
     batch = {k: v.to(dev) for k, v in synth.make_patches(B, L, seed=2000 + rank, with_distmat=False).items()}
@@ -449,12 +453,14 @@ def measure_train_step(dev, dist, world, shapes, B=64, steps=5, warmup=3):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms = float(tmax)
     finite = bool(torch.isfinite(loss))
+    torch.set_float32_matmul_precision(prev_prec)
     del model, bucket, opt, batch
     torch.cuda.empty_cache()
     return {"metric": "training steps/s (config 5: B=64 patches per GPU, noising + fwd + losses + bwd + "
                       "all-reduce + Adam, bf16 tensor-core IPA)", "value": 1000.0 / ms, "unit": "steps/s",
             "patches_per_s": B * world * 1000.0 / ms, "ms_per_step": ms, "patches_per_gpu": B, "n_gpus": world,
-            "loss_finite": finite}
+            "matmul_precision": "bf16 tensor-core IPA kernels; TF32 for the PyTorch glue and context encoders "
+                                "(as the reference's train.py:47)", "loss_finite": finite}
 
 
 def measure_ipa_fwd_bwd_bf16(dev, B=32, iters=20):

@@ -220,12 +220,25 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
   const uint32_t smem_base = smem_u32(smem);
   if ((smem_base & 1023u) != 0) asm volatile("trap;");
 
-  if (tid == 0) {
+  auto load_v = [&](int h) {
+    const int s = h % S::kVBufs;
+    mbar_arrive_expect_tx(&bars[BV_FULL + s], S::kVBuf);
+    tma_load_2d(smem + s * S::kVBuf, &map_v, &bars[BV_FULL + s], h * V_W, b * L);
+  };
+  constexpr int kL2Ahead = 6;
+  if (warp == 9 && lane == 0) {
+    // the producer lane initialises the barriers and starts the stage-1 loads before the CTA-wide synchronisation
     for (int i = 0; i < B_N_BARS; ++i) {
       const bool many = (i >= DPP_FREE && i < DPP_FREE + 3) || (i >= PCAT_READY && i < PCAT_READY + 4) || i == DE_FREE;
       mbar_init(&bars[i], many ? 128u : 1u);
     }
     fence_barrier_init();
+    tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e); tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_dop);
+    mbar_arrive_expect_tx(&bars[BQ_FULL], 16384);
+    for (int h = 0; h < H; ++h)
+      tma_load_2d(smem + S::kDoOff + h * 2048, &map_do, &bars[BQ_FULL], h * 64, (int)row0);
+    for (int h = 0; h < S::kVBufs; ++h) load_v(h);
+    for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
   }
   // per-row constants of this CTA and the st * Wpb operand tile ([8 h][64 c] bf16, 128B-swizzled rows)
   if (tid < 128) {
@@ -256,18 +269,6 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
   if (warp == 9) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
-      tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e); tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_dop);
-      constexpr int kL2Ahead = 6;
-      auto load_v = [&](int h) {
-        const int s = h % S::kVBufs;
-        mbar_arrive_expect_tx(&bars[BV_FULL + s], S::kVBuf);
-        tma_load_2d(smem + s * S::kVBuf, &map_v, &bars[BV_FULL + s], h * V_W, b * L);
-      };
-      mbar_arrive_expect_tx(&bars[BQ_FULL], 16384);
-      for (int h = 0; h < H; ++h)
-        tma_load_2d(smem + S::kDoOff + h * 2048, &map_do, &bars[BQ_FULL], h * 64, (int)row0);
-      for (int h = 0; h < S::kVBufs; ++h) load_v(h);
-      for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
       for (int h = S::kVBufs; h < H; ++h) {
         mbar_wait(&bars[BV_EMPTY + h % S::kVBufs], ((h / S::kVBufs) - 1) & 1);
         load_v(h);

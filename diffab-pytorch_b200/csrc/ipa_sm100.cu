@@ -21,7 +21,6 @@
 #include <cuda_fp16.h>
 
 #include <mutex>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_sm100.cuh"
@@ -325,7 +324,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_e,
                 const uint4* __restrict__ bias, const float* __restrict__ tc, const float* __restrict__ R,
                 __nv_bfloat16* __restrict__ cat, float* __restrict__ stats, uint4* __restrict__ pu,
-                long long* __restrict__ dbg, const uint8_t* __restrict__ xk, const uint8_t* __restrict__ xv) {
+                long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // optional per-CTA timeline: slot k of CTA c at dbg[c * 64 + k]
   long long* dbg_cta = dbg ? dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
@@ -343,9 +342,31 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const uint32_t smem_base = smem_u32(smem);
   if ((smem_base & 1023u) != 0) asm volatile("trap;");
 
-  if (tid == 0) {
+  // stage 1 operands: K of the patch head by head (ring of three), Q rows of this CTA
+  auto load_k = [&](int h) {
+    const int s = h % S::kKBufs;
+    uint8_t* kb = smem + s * S::kKBuf;
+    mbar_arrive_expect_tx(&bars[K_FULL + s], S::kKBuf);
+    for (int blk = 0; blk < 3; ++blk)
+      tma_load_2d(kb + blk * (L * 64), &map_k, &bars[K_FULL + s], (h * 3 + blk) * 32, b * L);
+  };
+  // The shared-memory ring is only four pair rows deep, far less than the HBM latency-bandwidth product, so
+  // rows are pulled HBM -> L2 six rows ahead with TMA prefetches and the ring is fed from L2.
+  constexpr int kL2Ahead = 6;
+  if (warp == 9 && lane == 0) {
+    // The producer lane initialises the barriers itself and starts the first loads right away: they are in flight
+    // while the rest of the CTA allocates TMEM and synchronises (first-load latency is ~10 % of a CTA's life).
     for (int i = 0; i < N_BARS; ++i) mbar_init(&bars[i], (i >= P_READY && i < P_READY + 4) ? 128u : 1u);
     fence_barrier_init();
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
+    load_k(0);
+    uint8_t* qbuf = smem + S::kQOff;
+    mbar_arrive_expect_tx(&bars[Q_FULL], S::kQBuf);
+    for (int blk = 0; blk < H * 3; ++blk)    // [blk][16 rows][64 B], 64B swizzle
+      tma_load_2d(qbuf + blk * (IB * 64), &map_q, &bars[Q_FULL], blk * 32, (int)row0);
+    load_k(1);
+    load_k(2);
+    for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
@@ -358,27 +379,6 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (warp == 9) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
-      tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
-      // The shared-memory ring is only four pair rows deep, far less than the HBM latency-bandwidth product, so
-      // rows are pulled HBM -> L2 six rows ahead with TMA prefetches and the ring is fed from L2.
-      constexpr int kL2Ahead = 6;
-      // ---- stage 1 operands: K of the patch head by head (ring of three), Q rows of this CTA
-      auto load_k = [&](int h) {
-        const int s = h % S::kKBufs;
-        uint8_t* kb = smem + s * S::kKBuf;
-        mbar_arrive_expect_tx(&bars[K_FULL + s], S::kKBuf);
-        if (xk) { bulk_load_1d(kb, xk + ((size_t)b * H + h) * S::kKBuf, S::kKBuf, &bars[K_FULL + s]); return; }
-        for (int blk = 0; blk < 3; ++blk)
-          tma_load_2d(kb + blk * (L * 64), &map_k, &bars[K_FULL + s], (h * 3 + blk) * 32, b * L);
-      };
-      load_k(0);
-      uint8_t* qbuf = smem + S::kQOff;
-      mbar_arrive_expect_tx(&bars[Q_FULL], S::kQBuf);
-      for (int blk = 0; blk < H * 3; ++blk)    // [blk][16 rows][64 B], 64B swizzle
-        tma_load_2d(qbuf + blk * (IB * 64), &map_q, &bars[Q_FULL], blk * 32, (int)row0);
-      load_k(1);
-      load_k(2);
-      for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
       for (int h = S::kKBufs; h < H; ++h) {
         mbar_wait(&bars[K_EMPTY + h % S::kKBufs], ((h / S::kKBufs) - 1) & 1);
         load_k(h);
@@ -398,8 +398,6 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int s = h % S::kVBufs;
         if (h >= S::kVBufs) mbar_wait(&bars[V_EMPTY + s], ((h / S::kVBufs) - 1) & 1);
         mbar_arrive_expect_tx(&bars[V_FULL + s], S::kVBuf);
-        if (xv) bulk_load_1d(smem + s * S::kVBuf, xv + ((size_t)b * H + h) * S::kVBuf, S::kVBuf, &bars[V_FULL + s]);
-        else
         tma_load_2d(smem + s * S::kVBuf, &map_v, &bars[V_FULL + s], h * V_W, b * L);
       }
     }
@@ -972,9 +970,7 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
     }
     ipa_core_kernel<<<dim3(L / IB, B), 320, CoreSmem::kTotal, s>>>(mq, mk, mv, me, bias, ws.tc, R, ws.cat,
                                                                    save_for_bwd ? ws.stats : nullptr,
-                                                                   save_for_bwd ? ws.pu : nullptr, g_core_dbg,
-                                                                   getenv("DAB_X_BULK") ? (const uint8_t*)ws.Kp : nullptr,
-                                                                   getenv("DAB_X_BULK") ? (const uint8_t*)ws.Vp : nullptr);
+                                                                   save_for_bwd ? ws.pu : nullptr, g_core_dbg);
     count_launch();
   }
   if (phases & 4) {

@@ -754,12 +754,13 @@ class DiffAb(nn.Module):
         orientations_t0 = batch["orientations"]
         generation_mask = batch["generation_mask"]
         noised = self._add_noise(seq_idx_t0, translations_t0, orientations_t0, generation_mask, t, noise=noise)
-        res_context_emb, pair_context_emb = self.encode_context(
-            seq_idx_t0, xyz_t0, orientations_t0, batch["backbone_dihedrals"], batch["distmat"],
-            batch["pairwise_dihedrals"], batch["atom_mask"], batch["chain_idx"], batch["residue_idx"],
-            batch["generation_mask"], batch["residue_mask"])
         bf16 = (getattr(self, "train_precision", "fp32") == "bf16" and
-                self.denoiser.ipa.layers[0].fast_path_supported(pair_context_emb.shape[1]))
+                self.denoiser.ipa.layers[0].fast_path_supported(seq_idx_t0.shape[1]))
+        with _tf32_matmuls(bf16):   # mixed-precision step: the context encoders' GEMMs on the tensor cores too (TF32)
+            res_context_emb, pair_context_emb = self.encode_context(
+                seq_idx_t0, xyz_t0, orientations_t0, batch["backbone_dihedrals"], batch["distmat"],
+                batch["pairwise_dihedrals"], batch["atom_mask"], batch["chain_idx"], batch["residue_idx"],
+                batch["generation_mask"], batch["residue_mask"])
         if bf16:
             pair_context_emb = pair_context_emb.to(torch.bfloat16)   # autograd-aware cast (grad comes back as bf16)
         with _tf32_matmuls(bf16):
