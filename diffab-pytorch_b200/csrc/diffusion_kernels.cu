@@ -30,70 +30,91 @@ __device__ __forceinline__ int argmax_ratio(F prob, const float* __restrict__ q)
   float best_key = -1.0f;
 #pragma unroll
   for (int k = 0; k < DAB_VOCAB; ++k) {
-    float key = __fdiv_rn(prob(k), __ldg(q + k));
+    float key = __fdiv_rn(prob(k), q[k]);   // q may live in shared memory: plain (generic) load
     if (key > best_key) { best_key = key; best = k; }
   }
   return best;
 }
 
+// One thread per residue, 128 residues per block.  Every per-residue record (21 exponential draws, 21 posterior
+// probabilities, 9 + 9 rotation entries, 3 + 3 + 3 coordinates) is a short odd-strided row, so a thread-per-row
+// global access pattern wastes most of each sector; the block's records are contiguous, so they go through shared
+// memory with fully coalesced global traffic (odd row strides: conflict-free shared-memory access).
 __global__ void __launch_bounds__(128) forward_noise_kernel(
     Sched sc, const int64_t* __restrict__ seq0, const float* __restrict__ x0, const float* __restrict__ O0,
     const uint8_t* __restrict__ mask, const int64_t* __restrict__ t, int B, int L,
     const float* __restrict__ seq_exp, const float* __restrict__ eps, const float* __restrict__ rotvec,
     int64_t* __restrict__ seq_t, float* __restrict__ posterior, float* __restrict__ x_t, float* __restrict__ O_t) {
-  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= (int64_t)B * L) return;
-  int b = (int)(r / L);
-  int tt = (int)t[b];
-  bool gen = mask[r] != 0;
-  int s0 = (int)seq0[r];
+  __shared__ float s_v[128 * DAB_VOCAB];   // exponential draws in, posterior out
+  __shared__ float s_o[128 * 9];           // O_0 in, O_t out
+  __shared__ float s_x[128 * 3], s_e[128 * 3], s_r[128 * 3];
+  const int64_t n = (int64_t)B * L;
+  const int64_t r0 = (int64_t)blockIdx.x * 128;
+  const int nv = (int)min((int64_t)128, n - r0);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < nv * DAB_VOCAB; i += 128) s_v[i] = __ldg(seq_exp + r0 * DAB_VOCAB + i);
+  for (int i = tid; i < nv * 9; i += 128) s_o[i] = __ldg(O0 + r0 * 9 + i);
+  for (int i = tid; i < nv * 3; i += 128) {
+    s_x[i] = __ldg(x0 + r0 * 3 + i);
+    s_e[i] = __ldg(eps + r0 * 3 + i);
+    s_r[i] = __ldg(rotvec + r0 * 3 + i);
+  }
+  __syncthreads();
+  const int64_t r = r0 + tid;
+  if (tid < nv) {
+    int b = (int)(r / L);
+    int tt = (int)t[b];
+    bool gen = mask[r] != 0;
+    int s0 = (int)seq0[r];
 
-  // ---- sequence: s_t ~ Multinomial(abar_t onehot + (1-abar_t)/21)   diffusion.py:105-158
-  float ab = __ldg(sc.alpha_bar + tt);
-  float one_m_ab = __fsub_rn(1.0f, ab);
-  int st = argmax_ratio([&](int k) { return mix_prob(k == s0, ab, one_m_ab, gen); }, seq_exp + r * DAB_VOCAB);
-  seq_t[r] = st;
-  // ---- posterior q(s_{t-1} | s_t, s_0) ∝ p_single(s_t, t) * p_from_t0(s_0, t-1)   diffusion.py:168-192
-  float beta = __ldg(sc.beta + tt);
-  float one_m_beta = __fsub_rn(1.0f, beta);
-  int tm1 = tt - 1;
-  if (tm1 < 0) tm1 += sc.T + 1;  // python negative index wrap (reference is never called with t = 0)
-  float abm = __ldg(sc.alpha_bar + tm1);
-  float one_m_abm = __fsub_rn(1.0f, abm);
-  float p[DAB_VOCAB];
-  float sum = 0.f;
+    // ---- sequence: s_t ~ Multinomial(abar_t onehot + (1-abar_t)/21)   diffusion.py:105-158
+    float ab = __ldg(sc.alpha_bar + tt);
+    float one_m_ab = __fsub_rn(1.0f, ab);
+    int st = argmax_ratio([&](int k) { return mix_prob(k == s0, ab, one_m_ab, gen); }, s_v + tid * DAB_VOCAB);
+    seq_t[r] = st;
+    // ---- posterior q(s_{t-1} | s_t, s_0) ∝ p_single(s_t, t) * p_from_t0(s_0, t-1)   diffusion.py:168-192
+    float beta = __ldg(sc.beta + tt);
+    float one_m_beta = __fsub_rn(1.0f, beta);
+    int tm1 = tt - 1;
+    if (tm1 < 0) tm1 += sc.T + 1;  // python negative index wrap (reference is never called with t = 0)
+    float abm = __ldg(sc.alpha_bar + tm1);
+    float one_m_abm = __fsub_rn(1.0f, abm);
+    float p[DAB_VOCAB];
+    float sum = 0.f;
 #pragma unroll
-  for (int k = 0; k < DAB_VOCAB; ++k) {
-    p[k] = __fmul_rn(mix_prob(k == st, one_m_beta, beta, gen), mix_prob(k == s0, abm, one_m_abm, gen));
-    sum = __fadd_rn(sum, p[k]);
-  }
+    for (int k = 0; k < DAB_VOCAB; ++k) {
+      p[k] = __fmul_rn(mix_prob(k == st, one_m_beta, beta, gen), mix_prob(k == s0, abm, one_m_abm, gen));
+      sum = __fadd_rn(sum, p[k]);
+    }
 #pragma unroll
-  for (int k = 0; k < DAB_VOCAB; ++k) posterior[r * DAB_VOCAB + k] = __fdiv_rn(p[k], sum);
+    for (int k = 0; k < DAB_VOCAB; ++k) s_v[tid * DAB_VOCAB + k] = __fdiv_rn(p[k], sum);   // own row: draws consumed
 
-  // ---- positions: x_t = sqrt(abar) x_0 + sqrt(1-abar) eps   diffusion.py:219-231
-  float a = __ldg(sc.alpha_bar_sqrt + tt), s = __ldg(sc.one_minus_alpha_bar_sqrt + tt);
+    // ---- positions: x_t = sqrt(abar) x_0 + sqrt(1-abar) eps   diffusion.py:219-231
+    float a = __ldg(sc.alpha_bar_sqrt + tt), s = __ldg(sc.one_minus_alpha_bar_sqrt + tt);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float v0 = __ldg(x0 + r * 3 + c);
-    float v = __fadd_rn(__fmul_rn(a, v0), __fmul_rn(s, __ldg(eps + r * 3 + c)));
-    x_t[r * 3 + c] = gen ? v : v0;
+    for (int c = 0; c < 3; ++c) {
+      float v0 = s_x[tid * 3 + c];
+      float v = __fadd_rn(__fmul_rn(a, v0), __fmul_rn(s, s_e[tid * 3 + c]));
+      s_x[tid * 3 + c] = gen ? v : v0;
+    }
+    // ---- orientations: O_t = scale_rot(O_0, sqrt(abar)) @ exp(rotvec)   diffusion.py:280-292
+    if (gen) {
+      float R0[9], Rm[9], Rn[9], Ro[9];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) R0[c] = s_o[tid * 9 + c];
+      float lx, ly, lz;
+      so3_log(R0, lx, ly, lz);
+      so3_exp(a * lx, a * ly, a * lz, Rm);
+      so3_exp(s_r[tid * 3], s_r[tid * 3 + 1], s_r[tid * 3 + 2], Rn);
+      mat3_mul(Rm, Rn, Ro);
+#pragma unroll
+      for (int c = 0; c < 9; ++c) s_o[tid * 9 + c] = Ro[c];
+    }
   }
-  // ---- orientations: O_t = scale_rot(O_0, sqrt(abar)) @ exp(rotvec)   diffusion.py:280-292
-  float R0[9], Rm[9], Rn[9], Ro[9];
-#pragma unroll
-  for (int c = 0; c < 9; ++c) R0[c] = __ldg(O0 + r * 9 + c);
-  if (gen) {
-    float lx, ly, lz;
-    so3_log(R0, lx, ly, lz);
-    so3_exp(a * lx, a * ly, a * lz, Rm);
-    so3_exp(__ldg(rotvec + r * 3), __ldg(rotvec + r * 3 + 1), __ldg(rotvec + r * 3 + 2), Rn);
-    mat3_mul(Rm, Rn, Ro);
-#pragma unroll
-    for (int c = 0; c < 9; ++c) O_t[r * 9 + c] = Ro[c];
-  } else {
-#pragma unroll
-    for (int c = 0; c < 9; ++c) O_t[r * 9 + c] = R0[c];
-  }
+  __syncthreads();
+  for (int i = tid; i < nv * DAB_VOCAB; i += 128) posterior[r0 * DAB_VOCAB + i] = s_v[i];
+  for (int i = tid; i < nv * 9; i += 128) O_t[r0 * 9 + i] = s_o[i];
+  for (int i = tid; i < nv * 3; i += 128) x_t[r0 * 3 + i] = s_x[i];
 }
 
 __global__ void __launch_bounds__(128) seq_probs_kernel(Sched sc, int kind, const int64_t* __restrict__ seq,
