@@ -179,3 +179,43 @@ def test_pair_bias_planes_single_pass_for_all_layers():
         assert planes[k].dtype == torch.float16 and planes[k].shape == (B, 128, 128, 8)
         assert float((planes[k].double() - ref).abs().max()) < 2e-3 * float(ref.abs().max())   # fp16 storage
         assert torch.equal(layer.pair_bias(e), planes[k])
+
+
+@pytest.mark.parametrize("B", [1, 3, 65])
+def test_tensor_core_training_pair_other_batch_sizes(B):
+    """Batch sizes that exercise the small-batch launch variants (projection tiles split over 4 / 2 CTAs per patch,
+    32-wide to_out tiles, partial-reduction blocks without work): bf16 forward + backward against the fp32 kernels on
+    the same bf16-rounded pair tensor."""
+    torch.manual_seed(B)
+    layer = InvariantPointAttentionLayer(128, 64, 32, 8, 8, 8).to(DEV)
+    layer.load_state_dict(synth.synthetic_state(synth.ipa_layer_shapes(128, 64, 8, 32, 8, 8), seed=1))
+    x, e, R, t = (v.to(DEV) for v in synth.make_ipa_inputs(B, 128, 128, 64, seed=7 + B))
+    e16 = e.to(torch.bfloat16)
+    gy = torch.randn(B, 128, 128, device=DEV)
+    grads = {}
+    for name, pair in (("fp32", e16.float()), ("bf16", e16)):
+        for p in layer.parameters():
+            p.grad = None
+        xg, eg = x.clone().requires_grad_(True), pair.clone().requires_grad_(True)
+        y = layer(xg, eg, R, t)
+        (y * gy).sum().backward()
+        grads[name] = {"y": y.detach(), "dx": xg.grad, "de": eg.grad.float(),
+                       **{n: p.grad.clone() for n, p in layer.named_parameters()}}
+    for k, ref in grads["fp32"].items():
+        assert torch.isfinite(grads["bf16"][k]).all(), k
+        assert _rel(grads["bf16"][k], ref.cpu()) < 2e-2, k
+
+
+def test_tensor_core_path_empty_batch_and_wrong_shape():
+    layer = InvariantPointAttentionLayer(128, 64, 32, 8, 8, 8).to(DEV)
+    x = torch.zeros(0, 128, 128, device=DEV)
+    e = torch.zeros(0, 128, 128, 64, device=DEV, dtype=torch.bfloat16)
+    R = torch.zeros(0, 128, 3, 3, device=DEV)
+    t = torch.zeros(0, 128, 3, device=DEV)
+    with torch.no_grad():
+        assert layer(x, e, R, t).shape == (0, 128, 128)
+    small = InvariantPointAttentionLayer(32, 16, 16, 4, 4, 8).to(DEV)
+    with pytest.raises(RuntimeError, match="train.py"):
+        with torch.no_grad():
+            small(torch.rand(2, 16, 32, device=DEV), torch.rand(2, 16, 16, 16, device=DEV).bfloat16(),
+                  torch.rand(2, 16, 3, 3, device=DEV), torch.rand(2, 16, 3, device=DEV))
