@@ -118,6 +118,37 @@ class ResidueEmbedding(nn.Module):
         return self.mlp(torch.cat([aa, coord, dih, chain], dim=-1))
 
 
+class _RbfFunction(torch.autograd.Function):
+    """exp(-softplus(C[pair type]) d^2) * atom-pair mask as ONE pass forward (bf16 out, 232 columns) and one pass
+    backward (``dab_rbf_fwd`` / ``dab_rbf_bwd``); gradient w.r.t. the coefficient table only (distances are data)."""
+
+    @staticmethod
+    def forward(ctx, distmat, seq_idx, atom_mask, coef, squared):
+        B, L = seq_idx.shape
+        d = _lib.dev(distmat, torch.float32, "distmat").view(B, L, L, -1)
+        s = _lib.dev(seq_idx, torch.int64, "seq_idx")
+        m = _lib.mask_u8(atom_mask, "atom_mask")
+        c = _lib.dev(coef.detach(), torch.float32, "pair2distcoef.weight")
+        if d.shape[-1] != 225 or tuple(c.shape) != (441, 225):
+            raise ValueError("fused RBF needs 15 atoms per residue and a (441, 225) coefficient table")
+        out = torch.empty(B, L, L, 232, device=d.device, dtype=torch.bfloat16)
+        _lib.check(_lib.lib().dab_rbf_fwd(ptr(d), ptr(s), ptr(m), ptr(c), B, L, int(squared), ptr(out),
+                                          _lib.stream_ptr()), "dab_rbf_fwd")
+        ctx.save_for_backward(d, s, m, c)
+        ctx.squared = int(squared)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        d, s, m, c = ctx.saved_tensors
+        B, L = s.shape
+        dc = torch.zeros_like(c)
+        g = _lib.dev(g, torch.bfloat16, "grad")
+        _lib.check(_lib.lib().dab_rbf_bwd(ptr(g), ptr(d), ptr(s), ptr(m), ptr(c), B, L, ctx.squared, ptr(dc),
+                                          _lib.stream_ptr()), "dab_rbf_bwd")
+        return None, None, None, dc, None
+
+
 class PairEmbedding(nn.Module):
     """diffab_pytorch.py:186-312.  The two in-place ``distmat *= mask`` lines (:296,:301) do not
     affect the forward result (``dist_feat`` is computed before them) and break autograd in the
@@ -186,10 +217,18 @@ class PairEmbedding(nn.Module):
         rel = (residue_idx[:, :, None] - residue_idx[:, None, :]).clamp(-self.max_dist_to_consider,
                                                                          self.max_dist_to_consider)
         f_rel = self.relpos_embedding(rel + self.max_dist_to_consider) * chain_prod[..., None]
-        coef = F.softplus(self.pair2distcoef(pair_type))
-        d = distmat.flatten(-2)
-        d2 = d if distmat_is_squared else d**2   # sample() hands over squared distances it computed itself
-        f_dist = self.distance_embedding(torch.exp(-1 * coef * d2) * atom_pair)
+        if getattr(self, "fused_rbf", False) and distmat.is_cuda and distmat.shape[-1] * distmat.shape[-2] == 225:
+            # mixed-precision training: the six (B, L, L, 225) passes collapse into one kernel each way; the first
+            # distance layer then runs as an aligned bf16 GEMM (K padded 225 -> 232) with fp32 accumulation
+            rbf = _RbfFunction.apply(distmat, seq_idx, atom_mask, self.pair2distcoef.weight, distmat_is_squared)
+            lin = self.distance_embedding[0]
+            a1 = F.linear(rbf, F.pad(lin.weight, (0, 7)).to(torch.bfloat16)).float() + lin.bias
+            f_dist = self.distance_embedding[1:](a1)
+        else:
+            coef = F.softplus(self.pair2distcoef(pair_type))
+            d = distmat.flatten(-2)
+            d2 = d if distmat_is_squared else d**2   # sample() hands over squared distances it computed itself
+            f_dist = self.distance_embedding(torch.exp(-1 * coef * d2) * atom_pair)
         f_dih = self.dihedral_embedding(dihedrals)
         return self.mlp(torch.cat([f_type, f_rel, f_dist, f_dih], dim=-1)) * res_pair[..., None]
 
@@ -756,6 +795,7 @@ class DiffAb(nn.Module):
         noised = self._add_noise(seq_idx_t0, translations_t0, orientations_t0, generation_mask, t, noise=noise)
         bf16 = (getattr(self, "train_precision", "fp32") == "bf16" and
                 self.denoiser.ipa.layers[0].fast_path_supported(seq_idx_t0.shape[1]))
+        self.pair_context_embedding.fused_rbf = bf16
         with _tf32_matmuls(bf16):   # mixed-precision step: the context encoders' GEMMs on the tensor cores too (TF32)
             res_context_emb, pair_context_emb = self.encode_context(
                 seq_idx_t0, xyz_t0, orientations_t0, batch["backbone_dihedrals"], batch["distmat"],

@@ -236,6 +236,13 @@ int dab_pair_embed_fwd_sm100(const void* packed, const int64_t* seq_masked, cons
                              const int64_t* residue_idx, const int64_t* chain_idx, const uint8_t* atom_mask, int B, int L,
                              int A, void* e_bf16, void* stream);
 
+/* Distance radial-basis features of PairEmbedding for training (diffab_pytorch.py:287-294): one pass forward
+ * (rbf_bf16[B,L,L,232], columns 225..231 zero), one pass backward (d_coef[441,225] accumulated into). */
+int dab_rbf_fwd(const float* distmat, const int64_t* seq_masked, const uint8_t* atom_mask, const float* coef, int B, int L,
+                int squared, void* rbf_bf16, void* stream);
+int dab_rbf_bwd(const void* grad_bf16, const float* distmat, const int64_t* seq_masked, const uint8_t* atom_mask,
+                const float* coef, int B, int L, int squared, float* d_coef, void* stream);
+
 /* Test hooks of the sm_100a path (used by tests/ only): the tcgen05 GEMM C[M,N] = A[M,K] B[N,K]^T + bias
  * (bf16 in, fp32 out; M % 128 == 0, N % 64 == 0, K % 64 == 0) and the operand-packing stage alone. */
 int dab_debug_set_timeline(long long* device_buf /* 64 slots per CTA of the attention core, or NULL */);

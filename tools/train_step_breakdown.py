@@ -15,6 +15,7 @@ shapes = torch.load(os.path.join(ROOT, "tests", "golden", "state_shapes.pt"), we
 model = DiffAb(128, 64, 6, 32, 8, 8, 8, device=dev).train()
 model.load_state_dict(synth.synthetic_state(shapes, seed=0))
 model.train_precision = "bf16"
+model.pair_context_embedding.fused_rbf = True
 opt = torch.optim.Adam(model.parameters(), lr=1e-4)
 b = {k: v.to(dev) for k, v in synth.make_patches(B, 128, seed=2000, with_distmat=False).items()}
 b["distmat"] = torch.cat([synth.pairwise_atom_distances(b["xyz"][i:i + 8]) for i in range(0, B, 8)])
