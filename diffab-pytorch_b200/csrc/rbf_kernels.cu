@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(256) rbf_kernel(const float* __restrict__ dist
                                                   const uint8_t* __restrict__ atom_mask, const float* __restrict__ coef,
                                                   int L, int squared, __nv_bfloat16* __restrict__ rbf,
                                                   const __nv_bfloat16* __restrict__ grad, float* __restrict__ dcoef) {
-  extern __shared__ float s_tab[];                 // [21][225]: softplus(C) (forward) or gradient accumulators (backward)
+  extern __shared__ float s_tab[];                 // [21][225] softplus(C); backward: [21][225] gradient accumulators first
   __shared__ int s_seq[512];
   __shared__ unsigned s_mask[512];
   const int64_t row = blockIdx.x;                  // (b, i)
@@ -43,35 +43,44 @@ __global__ void __launch_bounds__(256) rbf_kernel(const float* __restrict__ dist
 #pragma unroll
     for (int s = 0; s < RBF_V; ++s) sp[s] = softplus_f(__ldg(crow + s * RBF_K + tid));
   }
+  float* s_sp = BWD ? s_tab + RBF_V * RBF_K : s_tab;   // backward: accumulators first, softplus table second
   if (BWD) {
     for (int i = tid; i < RBF_V * RBF_K; i += blockDim.x) s_tab[i] = 0.f;
-  } else if (tid < RBF_K) {
+  }
+  if (tid < RBF_K) {
 #pragma unroll
-    for (int s = 0; s < RBF_V; ++s) s_tab[s * RBF_K + tid] = sp[s];
+    for (int s = 0; s < RBF_V; ++s) s_sp[s * RBF_K + tid] = sp[s];
   }
   __syncthreads();
   const int a = tid / RBF_A, ap = tid % RBF_A;
   const bool ai = tid < RBF_K && ((mi >> a) & 1u);
-  for (int j = 0; j < L; ++j) {
-    const int64_t p = row * L + j;
+  constexpr int U = 8;                               // keys per iteration: U independent loads in flight per thread
+  for (int j0 = 0; j0 < L; j0 += U) {
+    const int64_t p0 = row * L + j0;
     if (tid < RBF_K) {
-      const int sj = s_seq[j];
-      float d = __ldg(dist + p * RBF_K + tid);
-      const float d2 = squared ? d : d * d;
-      const bool on = ai && ((s_mask[j] >> ap) & 1u);
-      if (!BWD) {
-        const float v = on ? __expf(-s_tab[sj * RBF_K + tid] * d2) : 0.f;
-        rbf[p * RBF_KP + tid] = __float2bfloat16_rn(v);
-      } else if (on) {
-        // d rbf / d C = rbf * (-d2) * sigmoid(C); the sigmoid factor is applied once at the end
-        float spv = sp[0];
+      float d[U], g[U];
 #pragma unroll
-        for (int s = 1; s < RBF_V; ++s) spv = (s == sj) ? sp[s] : spv;
-        const float v = __expf(-spv * d2);
-        s_tab[sj * RBF_K + tid] += __bfloat162float(grad[p * RBF_KP + tid]) * v * (-d2);   // own column: no race
+      for (int u = 0; u < U; ++u) {
+        const bool in = j0 + u < L;
+        d[u] = in ? __ldg(dist + (p0 + u) * RBF_K + tid) : 0.f;
+        if (BWD) g[u] = in ? __bfloat162float(grad[(p0 + u) * RBF_KP + tid]) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (j0 + u >= L) break;
+        const int sj = s_seq[j0 + u];
+        const float d2 = squared ? d[u] : d[u] * d[u];
+        const bool on = ai && ((s_mask[j0 + u] >> ap) & 1u);
+        if (!BWD) {
+          const float v = on ? __expf(-s_sp[sj * RBF_K + tid] * d2) : 0.f;
+          rbf[(p0 + u) * RBF_KP + tid] = __float2bfloat16_rn(v);
+        } else if (on) {
+          // d rbf / d C = rbf * (-d2) * sigmoid(C); the sigmoid factor is applied once at the end
+          s_tab[sj * RBF_K + tid] += g[u] * __expf(-s_sp[sj * RBF_K + tid] * d2) * (-d2);   // own column: no race
+        }
       }
     } else if (!BWD && tid < RBF_KP) {
-      rbf[p * RBF_KP + tid] = __float2bfloat16_rn(0.f);
+      for (int u = 0; u < U && j0 + u < L; ++u) rbf[(p0 + u) * RBF_KP + tid] = __float2bfloat16_rn(0.f);
     }
   }
   if (BWD && tid < RBF_K) {
@@ -112,7 +121,7 @@ int dab_rbf_bwd(const void* grad_bf16, const float* distmat, const int64_t* seq_
   DAB_REQUIRE(B >= 0 && L >= 0 && L <= 512, DAB_EUNSUPPORTED, "dab_rbf_bwd: 0 <= L <= 512 required");
   if ((int64_t)B * L == 0) return DAB_OK;
   DAB_REQUIRE(grad_bf16 && distmat && seq_masked && atom_mask && coef && d_coef, DAB_EINVAL, "dab_rbf_bwd: null pointer");
-  rbf_kernel<true><<<B * L, 256, RBF_V * RBF_K * 4, (cudaStream_t)stream>>>(
+  rbf_kernel<true><<<B * L, 256, 2 * RBF_V * RBF_K * 4, (cudaStream_t)stream>>>(
       distmat, seq_masked, atom_mask, coef, L, squared, nullptr, reinterpret_cast<const __nv_bfloat16*>(grad_bf16), d_coef);
   count_launch();
   return check_launch("dab_rbf_bwd");

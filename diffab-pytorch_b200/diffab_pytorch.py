@@ -211,24 +211,34 @@ class PairEmbedding(nn.Module):
         if sequence_context_mask is not None:
             seq_idx = torch.where(sequence_context_mask.bool(), seq_idx, torch.full_like(seq_idx, AA_UNK))
         pair_type = seq_idx[:, :, None] * self.max_n_aa_types + seq_idx[:, None, :]
-        f_type = self.aa_pair_type_embedding(pair_type)
         # note: the reference multiplies by the PRODUCT of chain indices, not an equality mask (:279,285)
         chain_prod = chain_idx[:, :, None] * chain_idx[:, None, :]
         rel = (residue_idx[:, :, None] - residue_idx[:, None, :]).clamp(-self.max_dist_to_consider,
                                                                          self.max_dist_to_consider)
-        f_rel = self.relpos_embedding(rel + self.max_dist_to_consider) * chain_prod[..., None]
         if getattr(self, "fused_rbf", False) and distmat.is_cuda and distmat.shape[-1] * distmat.shape[-2] == 225:
-            # mixed-precision training: the six (B, L, L, 225) passes collapse into one kernel each way; the first
-            # distance layer then runs as an aligned bf16 GEMM (K padded 225 -> 232) with fp32 accumulation
+            # Mixed-precision training.  (1) The six (B, L, L, 225) passes collapse into one kernel each way; the first
+            # distance layer then runs as an aligned bf16 GEMM (K padded 225 -> 232) with fp32 accumulation.
             rbf = _RbfFunction.apply(distmat, seq_idx, atom_mask, self.pair2distcoef.weight, distmat_is_squared)
             lin = self.distance_embedding[0]
             a1 = F.linear(rbf, F.pad(lin.weight, (0, 7)).to(torch.bfloat16)).float() + lin.bias
             f_dist = self.distance_embedding[1:](a1)
-        else:
-            coef = F.softplus(self.pair2distcoef(pair_type))
-            d = distmat.flatten(-2)
-            d2 = d if distmat_is_squared else d**2   # sample() hands over squared distances it computed itself
-            f_dist = self.distance_embedding(torch.exp(-1 * coef * d2) * atom_pair)
+            # (2) The first mlp layer acts on cat[f_type | f_rel | f_dist | f_dih]: its embedding blocks are applied to
+            # the TABLES (441 and 65 rows) and gathered, so neither the embeddings nor the 210-wide concat are
+            # materialised per pair and the remaining products have K = 64 and K = 18.
+            D = self.d_feat
+            w1, b1 = self.mlp[0].weight, self.mlp[0].bias
+            h = F.embedding(pair_type, self.aa_pair_type_embedding.weight @ w1[:, :D].t())
+            h = h + F.embedding(rel + self.max_dist_to_consider,
+                                self.relpos_embedding.weight @ w1[:, D:2 * D].t()) * chain_prod[..., None]
+            f_dih = F.pad(self.dihedral_embedding(dihedrals), (0, 6))           # K = 18 -> 24: aligned GEMM
+            h = h + F.linear(f_dist, w1[:, 2 * D:3 * D]) + F.linear(f_dih, F.pad(w1[:, 3 * D:], (0, 6)), b1)
+            return self.mlp[1:](h) * res_pair[..., None]
+        f_type = self.aa_pair_type_embedding(pair_type)
+        f_rel = self.relpos_embedding(rel + self.max_dist_to_consider) * chain_prod[..., None]
+        coef = F.softplus(self.pair2distcoef(pair_type))
+        d = distmat.flatten(-2)
+        d2 = d if distmat_is_squared else d**2   # sample() hands over squared distances it computed itself
+        f_dist = self.distance_embedding(torch.exp(-1 * coef * d2) * atom_pair)
         f_dih = self.dihedral_embedding(dihedrals)
         return self.mlp(torch.cat([f_type, f_rel, f_dist, f_dih], dim=-1)) * res_pair[..., None]
 
