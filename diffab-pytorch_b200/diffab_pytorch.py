@@ -8,7 +8,8 @@ loads with ``load_state_dict``.  What runs where:
   sm_100a kernels behind the C ABI (``csrc/``);
 * context encoders (``ResidueEmbedding``, ``PairEmbedding``; once per patch, out of scope per
   SURVEY §2) and the small dense glue of ``Denoiser`` (embedding + MLP heads, "next" row N1): PyTorch
-  modules on the GPU (library GEMMs);
+  modules on the GPU (library GEMMs) on the exact fp32 path and in training; on the bf16 sampling path the
+  glue runs in ``csrc/heads_sm100.cu`` and ``PairEmbedding`` in ``csrc/pair_embed_sm100.cu`` ("next" rows N1, N3);
 * ``sample()`` - an empty stub in the reference (``diffab_pytorch.py:770-776``) - is implemented
   here following oracle/sampler.py.
 
