@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/diffab_b200.h"
 
 namespace dab {
@@ -22,6 +24,20 @@ inline int check_launch(const char* what) {
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Opt a kernel in to `bytes` of dynamic shared memory once per (kernel, device): the attribute is per device, and the
+// library may be called from several host threads (an atomic bit mask per call site; a repeated set is harmless).
+#define DAB_ENSURE_SMEM(kernel, bytes)                                                                    \
+  do {                                                                                                    \
+    static std::atomic<unsigned long long> dab_done_mask{0};                                              \
+    int dab_dev = 0;                                                                                      \
+    cudaGetDevice(&dab_dev);                                                                              \
+    const unsigned long long dab_bit = 1ull << (dab_dev & 63);                                            \
+    if (!(dab_done_mask.load(std::memory_order_acquire) & dab_bit)) {                                     \
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));           \
+      dab_done_mask.fetch_or(dab_bit, std::memory_order_release);                                        \
+    }                                                                                                     \
+  } while (0)
 
 #define DAB_REQUIRE(cond, code, ...)  \
   do {                                \

@@ -3,9 +3,9 @@
 //   C[M, N] (fp32, row-major, ldc) = A[M, K] (bf16, K contiguous) * B[N, K]^T (bf16, K contiguous) + bias[N]
 //
 // Used for the IPA projections (K = 128) and to_out (K = 1024), i.e. the nn.Linear layers of
-// diffab_pytorch.py:391-403,464.  One CTA computes a 128 x BN tile: one thread issues the TMA loads
-// (128B-swizzled 64-wide K chunks, ring of kStages) and the tcgen05.mma chain (M = 128, N = BN, K = 16
-// per instruction, fp32 accumulator in TMEM); all four warps then read the accumulator with tcgen05.ld
+// diffab_pytorch.py:391-403,464.  One CTA computes a 128 x BN tile: one lane issues the TMA loads
+// (128B-swizzled 64-wide K chunks, ring of kStages), a lane of another warp the tcgen05.mma chain (M = 128,
+// N = BN, K = 16 per instruction, fp32 accumulator in TMEM); all four warps then read the accumulator with tcgen05.ld
 // (warp w owns TMEM lanes 32w..32w+31 = tile rows), add the bias and store.
 #pragma once
 #include "common.cuh"
@@ -61,21 +61,24 @@ __global__ void __launch_bounds__(128) gemm_bf16_kernel(const __grid_constant__ 
 
   const int nk = K / kGemmBK;
   if (threadIdx.x == 0) {
-    constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, BN, 0, 0);
-    auto issue_load = [&](int kc) {
-      int s = kc % kGemmStages;
+    // ---- TMA producer: keeps the whole ring in flight, refilling a slot as soon as its MMAs have read it
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % kGemmStages;
+      if (kc >= kGemmStages) mbar_wait(&empty[s], ((kc / kGemmStages) - 1) & 1);
       uint8_t* a = smem + s * S::kStageBytes;
       mbar_arrive_expect_tx(&full[s], S::kStageBytes);
       tma_load_2d(a, &map_a, &full[s], kc * kGemmBK, m0);
       tma_load_2d(a + S::kABytes, &map_b, &full[s], kc * kGemmBK, n0);
-    };
-    for (int kc = 0; kc < nk && kc < kGemmStages; ++kc) issue_load(kc);
+    }
+  } else if (threadIdx.x == 32) {
+    // ---- tcgen05.mma issuer (a different warp, so loads and MMAs never wait for each other's bookkeeping)
+    constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, BN, 0, 0);
     for (int kc = 0; kc < nk; ++kc) {
-      int s = kc % kGemmStages;
+      const int s = kc % kGemmStages;
       mbar_wait(&full[s], (kc / kGemmStages) & 1);
       tcgen05_fence_after_sync();
-      uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
-      uint32_t b_addr = a_addr + S::kABytes;
+      const uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
+      const uint32_t b_addr = a_addr + S::kABytes;
 #pragma unroll
       for (int k = 0; k < kGemmBK / 16; ++k) {
         // K-major, 128B swizzle: 8-row groups are 1024 B apart (SBO); a K step of 16 bf16 is +32 B
@@ -84,11 +87,6 @@ __global__ void __launch_bounds__(128) gemm_bf16_kernel(const __grid_constant__ 
         umma_bf16(tmem_base, da, db, idesc, (kc | k) != 0);
       }
       umma_commit(&empty[s]);  // slot reusable once these MMAs have read it
-      // refill the slot of the PREVIOUS chunk (its MMAs finish while this chunk's are queued)
-      if (kc >= 1 && kc - 1 + kGemmStages < nk) {
-        mbar_wait(&empty[(kc - 1) % kGemmStages], ((kc - 1) / kGemmStages) & 1);
-        issue_load(kc - 1 + kGemmStages);
-      }
     }
     umma_commit(done);
   }
@@ -132,11 +130,7 @@ int launch_gemm_bf16(const void* A, int64_t lda, const void* Bm, int64_t ldb, fl
   uint32_t box_a[2] = {kGemmBK, kGemmBM}, box_b[2] = {kGemmBK, (uint32_t)BN};
   if (int rc = make_tensor_map_bf16(&ma, A, 2, dims_a, str_a, box_a, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   if (int rc = make_tensor_map_bf16(&mb, Bm, 2, dims_b, str_b, box_b, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal);
-    attr_done = true;
-  }
+  DAB_ENSURE_SMEM(gemm_bf16_kernel<BN>, GemmSmem<BN>::kTotal);
   dim3 grid(N / BN, M / kGemmBM);
   gemm_bf16_kernel<BN><<<grid, 128, GemmSmem<BN>::kTotal, stream>>>(ma, mb, C, ldc, bias, K);
   count_launch();

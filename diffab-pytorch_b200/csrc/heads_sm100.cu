@@ -313,11 +313,7 @@ int dab_heads_fwd_sm100(const void* packed, const float* x, const float* beta, i
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
   if (int rc = make_tensor_map_bf16(&m128, pk + HeadsPacked::kW, 2, dims, strides, b128, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   if (int rc = make_tensor_map_bf16(&m32, pk + HeadsPacked::kW, 2, dims, strides, b32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(denoiser_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HeadsSmem::kTotal);
-    attr_done = true;
-  }
+  DAB_ENSURE_SMEM(denoiser_heads_kernel, HeadsSmem::kTotal);
   denoiser_heads_kernel<<<n_patches, 288, HeadsSmem::kTotal, (cudaStream_t)stream>>>(m128, m32, x, beta, pk, eps, rotvec, post);
   count_launch();
   return check_launch("dab_heads_fwd_sm100");

@@ -816,12 +816,8 @@ int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf1
     uint32_t bdp[2] = {64, H};
     if (int rc = make_tensor_map_bf16(&mdop, bw.dopair, 2, ddp, sdp, bdp, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(ipa_bwd_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal);
-    cudaFuncSetAttribute(ipa_bwd_keyside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KsSmem::kTotal);
-    attr_done = true;
-  }
+  DAB_ENSURE_SMEM(ipa_bwd_core_kernel, BwdSmem::kTotal);
+  DAB_ENSURE_SMEM(ipa_bwd_keyside_kernel, KsSmem::kTotal);
   ipa_bwd_core_kernel<<<dim3(L / IB, B), 320, BwdSmem::kTotal, s>>>(
       mv, me, mdo, mdop, ws.pu, ws.stats, bw.delta, bw.rscale, wpb, reinterpret_cast<__nv_bfloat16*>(de_bf16), bw.Pn,
       bw.dL, bw.p_wpb, bw.p_g1, g_bwd_dbg);

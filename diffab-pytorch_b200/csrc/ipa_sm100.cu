@@ -826,11 +826,7 @@ static int launch_pair_bias(const void* e_bf16, const float* wpb, int nl, void* 
   uint64_t de[2] = {(uint64_t)C, (uint64_t)n_pairs}, se[1] = {(uint64_t)C * 2};
   uint32_t be[2] = {C, 128};
   if (int rc = make_tensor_map_bf16(&me, e_bf16, 2, de, se, be, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(ipa_pair_bias_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BiasSmem::kTotal);
-    attr_done = true;
-  }
+  DAB_ENSURE_SMEM(ipa_pair_bias_mma_kernel, BiasSmem::kTotal);
   const int n_tiles = (int)((n_pairs + 127) / 128);
   const int grid = n_tiles < 296 ? n_tiles : 296;
   ipa_pair_bias_mma_kernel<<<grid, 192, BiasSmem::kTotal, s>>>(me, wpb, nl, reinterpret_cast<uint4*>(planes), n_pairs,
@@ -926,11 +922,7 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
     uint32_t b64[2] = {64, 64}, b48[2] = {64, 48};
     if (int rc = make_tensor_map_bf16(&mw64, pk + po.wcat, 2, dw, sw, b64, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (int rc = make_tensor_map_bf16(&mw48, pk + po.wcat, 2, dw, sw, b48, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    static bool proj_attr_done = false;
-    if (!proj_attr_done) {
-      cudaFuncSetAttribute(ipa_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ProjSmem::kTotal);
-      proj_attr_done = true;
-    }
+    DAB_ENSURE_SMEM(ipa_proj_kernel, ProjSmem::kTotal);
     CUtensorMap msq, msk, msv;   // TMA-store views of the packed operands: 64-byte segments of 128 rows
     {
       uint64_t dqk[2] = {(uint64_t)H * QK_W, (uint64_t)M}, sqk[1] = {(uint64_t)H * QK_W * 2};
@@ -963,11 +955,7 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
     uint64_t de[2] = {(uint64_t)C, (uint64_t)M * L}, se[1] = {(uint64_t)C * 2};
     uint32_t be[2] = {C, L};
     if (int rc = make_tensor_map_bf16(&me, e_bf16, 2, de, se, be, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaFuncSetAttribute(ipa_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CoreSmem::kTotal);
-      attr_done = true;
-    }
+    DAB_ENSURE_SMEM(ipa_core_kernel, CoreSmem::kTotal);
     ipa_core_kernel<<<dim3(L / IB, B), 320, CoreSmem::kTotal, s>>>(mq, mk, mv, me, bias, ws.tc, R, ws.cat,
                                                                    save_for_bwd ? ws.stats : nullptr,
                                                                    save_for_bwd ? ws.pu : nullptr, g_core_dbg);

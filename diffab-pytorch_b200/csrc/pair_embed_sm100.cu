@@ -431,11 +431,7 @@ int dab_pair_embed_fwd_sm100(const void* packed, const int64_t* seq_masked, cons
   if (int rc = make_tensor_map_bf16(&mw, reinterpret_cast<const uint8_t*>(packed) + PePacked::kW, 2, dims, strides, box,
                                     CU_TENSOR_MAP_SWIZZLE_128B))
     return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(pair_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PeSmem::kTotal);
-    attr_done = true;
-  }
+  DAB_ENSURE_SMEM(pair_embed_kernel, PeSmem::kTotal);
   const int n_rows = B * PE_L;
   const int grid = n_rows < 148 ? n_rows : 148;
   pair_embed_kernel<<<grid, 288, PeSmem::kTotal, (cudaStream_t)stream>>>(
