@@ -910,7 +910,9 @@ class DiffAb(nn.Module):
         repeated ``sample()`` calls only copy their context in (~1 GB device-to-device, well under a millisecond)."""
         B, L = s.shape
         dev = s.device
-        key = (B, L, tuple(res_ctx.shape), tuple(pair_ctx.shape), pair_ctx.dtype, str(dev))
+        # the captured graph bakes in packed weights and per-run weight products: recapture when any parameter changed
+        wkey = tuple((p.data_ptr(), p._version) for p in self.denoiser.parameters())
+        key = (B, L, tuple(res_ctx.shape), tuple(pair_ctx.shape), pair_ctx.dtype, str(dev), wkey)
         cache = getattr(self, "_graph_cache", None)
         fresh = cache is None or cache["key"] != key
         if fresh:

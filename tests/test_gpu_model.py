@@ -299,3 +299,27 @@ def test_fused_rbf_training_op_matches_module():
             assert float(got @ rf / (got.norm() * rf.norm())) > 0.995
         else:
             assert _rel(grads[True][n], ref.cpu()) < 3e-2, n
+
+
+def test_graphed_sampling_follows_weight_updates():
+    """The CUDA-graph cache of sample() is keyed on the parameter versions: after an in-place weight update the next
+    call must not replay a graph that baked in the old packed weights.  The update makes the sequence head predict
+    class 0 with certainty, so every generated residue must come out as 0 whatever the random draws."""
+    model = _model(0)
+    batch = synth.make_patches(2, 128, seed=41, with_distmat=False)
+    args = (batch["seq_idx"], batch["xyz"], batch["orientations"], batch["backbone_dihedrals"], None,
+            batch["pairwise_dihedrals"], batch["atom_mask"], batch["chain_idx"], batch["residue_idx"],
+            batch["generation_mask"], batch["residue_mask"])
+    m = batch["generation_mask"].to(DEV)
+    a = model.sample(*args, t_start=3)
+    g0 = model._graph_cache["graph"]
+    model.sample(*args, t_start=3)
+    assert model._graph_cache["graph"] is g0                      # unchanged weights: the graph is reused
+    assert int((a["seq_idx"][m] != 0).sum()) > 0
+    with torch.no_grad():
+        model.denoiser.sequence_denoising[4].weight.mul_(0.0)
+        model.denoiser.sequence_denoising[4].bias.copy_(torch.tensor([100.0] + [0.0] * 20, device=DEV))
+    b = model.sample(*args, t_start=3)
+    assert model._graph_cache["graph"] is not g0
+    assert int((b["seq_idx"][m] != 0).sum()) == 0
+    assert torch.equal(b["seq_idx"].cpu()[~batch["generation_mask"]], batch["seq_idx"][~batch["generation_mask"]])
