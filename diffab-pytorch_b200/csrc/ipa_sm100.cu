@@ -250,7 +250,9 @@ static_assert(CoreSmem::kQBuf <= CoreSmem::kPhBytes, "Q must fit the idle P_h re
 static_assert(CoreSmem::kTotal <= 113 * 1024, "two CTAs per SM");
 
 enum Bar { K_FULL = 0, K_EMPTY = 3, Q_FULL = 6, S_DONE = 7, E_FULL = 8, E_EMPTY = 12, PAIR = 16 /* [group][slot] */,
-           V_FULL = 20, V_EMPTY = 24, O_DONE = 28, P_READY = 29 /* [group][slot], 128 arrivals */, N_BARS = 33 };
+           V_FULL = 20, V_EMPTY = 24, O_DONE = 28, P_READY = 29 /* [group][slot], 128 arrivals */,
+           EPI_TMEM = 33 /* 256 arrivals: epilogue has read every accumulator */, EPI_DONE = 34 /* 256: region X free */,
+           N_BARS = 35 };
 
 // TMEM columns
 constexpr uint32_t kColS = 0, kColPair = 128 /* 16 rows x 8 */, kTmemCols = 256;
@@ -324,10 +326,13 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_e,
                 const uint4* __restrict__ bias, const float* __restrict__ tc, const float* __restrict__ R,
                 __nv_bfloat16* __restrict__ cat, float* __restrict__ stats, uint4* __restrict__ pu,
-                long long* __restrict__ dbg) {
+                int n_tiles, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  // optional per-CTA timeline: slot k of CTA c at dbg[c * 64 + k]
-  long long* dbg_cta = dbg ? dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
+  // Persistent CTAs: CTA c works on tiles c, c + gridDim.x, ...; tile = (patch, block of 16 query rows).  While the
+  // epilogue of a tile runs, the producer already loads Q and the first K tiles of the next one (the first-load
+  // latency of a fresh CTA was ~6k of its 45k cycles), and TMEM / barriers are set up once.
+  // optional per-tile timeline: slot k of tile c at dbg[c * 64 + k]
+  long long* dbg_cta = dbg ? dbg + (size_t)blockIdx.x * 64 : nullptr;
 #define DAB_STAMP(k) do { if (dbg_cta && threadIdx.x == 0) dbg_cta[(k)] = clock64(); } while (0)
 #define DAB_STAMP_ISSUER(k) do { if (dbg_cta) dbg_cta[(k)] = clock64(); } while (0)
   DAB_STAMP(0);
@@ -337,18 +342,25 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   float* inv_o = reinterpret_cast<float*>(smem + S::kInvO);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y, i0 = blockIdx.x * IB;
-  const int64_t row0 = (int64_t)b * L + i0;       // first query row (global residue index)
   const uint32_t smem_base = smem_u32(smem);
   if ((smem_base & 1023u) != 0) asm volatile("trap;");
+  // completions per tile of the K ring barriers (8 heads over 3 buffers); every other ring completes an even
+  // number of times per tile, so only these and the once-per-tile barriers need the tile counter in their parity
+  auto kc = [](int s) { return s == 2 ? 2 : 3; };
 
-  // stage 1 operands: K of the patch head by head (ring of three), Q rows of this CTA
-  auto load_k = [&](int h) {
+  // stage 1 operands: K of the patch head by head (ring of three), Q rows of this tile
+  auto load_k = [&](int h, int b) {
     const int s = h % S::kKBufs;
     uint8_t* kb = smem + s * S::kKBuf;
     mbar_arrive_expect_tx(&bars[K_FULL + s], S::kKBuf);
     for (int blk = 0; blk < 3; ++blk)
       tma_load_2d(kb + blk * (L * 64), &map_k, &bars[K_FULL + s], (h * 3 + blk) * 32, b * L);
+  };
+  auto load_q = [&](int64_t row0) {
+    uint8_t* qbuf = smem + S::kQOff;
+    mbar_arrive_expect_tx(&bars[Q_FULL], S::kQBuf);
+    for (int blk = 0; blk < H * 3; ++blk)    // [blk][16 rows][64 B], 64B swizzle
+      tma_load_2d(qbuf + blk * (IB * 64), &map_q, &bars[Q_FULL], blk * 32, (int)row0);
   };
   // The shared-memory ring is only four pair rows deep, far less than the HBM latency-bandwidth product, so
   // rows are pulled HBM -> L2 six rows ahead with TMA prefetches and the ring is fed from L2.
@@ -356,16 +368,16 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (warp == 9 && lane == 0) {
     // The producer lane initialises the barriers itself and starts the first loads right away: they are in flight
     // while the rest of the CTA allocates TMEM and synchronises (first-load latency is ~10 % of a CTA's life).
-    for (int i = 0; i < N_BARS; ++i) mbar_init(&bars[i], (i >= P_READY && i < P_READY + 4) ? 128u : 1u);
+    for (int i = 0; i < N_BARS; ++i)
+      mbar_init(&bars[i], (i >= P_READY && i < P_READY + 4) ? 128u : ((i == EPI_TMEM || i == EPI_DONE) ? 256u : 1u));
     fence_barrier_init();
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
-    load_k(0);
-    uint8_t* qbuf = smem + S::kQOff;
-    mbar_arrive_expect_tx(&bars[Q_FULL], S::kQBuf);
-    for (int blk = 0; blk < H * 3; ++blk)    // [blk][16 rows][64 B], 64B swizzle
-      tma_load_2d(qbuf + blk * (IB * 64), &map_q, &bars[Q_FULL], blk * 32, (int)row0);
-    load_k(1);
-    load_k(2);
+    const int b = (int)blockIdx.x >> 3;
+    const int64_t row0 = (int64_t)b * L + ((int)blockIdx.x & 7) * IB;
+    load_k(0, b);
+    load_q(row0);
+    load_k(1, b);
+    load_k(2, b);
     for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
   }
   __syncwarp();
@@ -379,12 +391,16 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (warp == 9) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
+     for (int n = 0, tile = blockIdx.x; tile < n_tiles; ++n, tile += gridDim.x) {
+      const int b = tile >> 3;
+      const int64_t row0 = (int64_t)b * L + (tile & 7) * IB;
       for (int h = S::kKBufs; h < H; ++h) {
-        mbar_wait(&bars[K_EMPTY + h % S::kKBufs], ((h / S::kKBufs) - 1) & 1);
-        load_k(h);
+        const int s = h % S::kKBufs;
+        mbar_wait(&bars[K_EMPTY + s], (n * kc(s) + (h / S::kKBufs) - 1) & 1);
+        load_k(h, b);
       }
       // ---- stage 2: the pair rows (ring of four); region X is free once every S^T MMA has completed
-      mbar_wait(&bars[S_DONE], 0);
+      mbar_wait(&bars[S_DONE], n & 1);
       for (int r = 0; r < IB; ++r) {
         const int s = r % S::kEStages;
         if (r >= S::kEStages) mbar_wait(&bars[E_EMPTY + s], ((r / S::kEStages) - 1) & 1);
@@ -400,6 +416,21 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         mbar_arrive_expect_tx(&bars[V_FULL + s], S::kVBuf);
         tma_load_2d(smem + s * S::kVBuf, &map_v, &bars[V_FULL + s], h * V_W, b * L);
       }
+      // ---- next tile: Q and the first two K tiles as soon as the O^T MMAs have released the V ring and the P_h
+      //      region, its first pair rows towards L2, the third K tile once the epilogue has left region X
+      const int nt = tile + gridDim.x;
+      if (nt < n_tiles) {
+        const int nb = nt >> 3;
+        const int64_t nrow0 = (int64_t)nb * L + (nt & 7) * IB;
+        mbar_wait(&bars[O_DONE], n & 1);
+        load_k(0, nb);
+        load_q(nrow0);
+        load_k(1, nb);
+        for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((nrow0 + r) * L));
+        mbar_wait(&bars[EPI_DONE], n & 1);
+        load_k(2, nb);
+      }
+     }
     }
   } else if (warp == 8) {
     // ======================================= MMA issuer =======================================
@@ -407,11 +438,17 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       constexpr uint32_t kIdescS = make_idesc_bf16(128, 16, 0, 0);     // S^T
       constexpr uint32_t kIdescPair = make_idesc_bf16(128, 16, 1, 0);  // A = two e tiles, MN-major
       constexpr uint32_t kIdescO = make_idesc_f16(128, 32, 1, 0);      // A = two V tiles, MN-major, fp16 operands
+     for (int n = 0, tile = blockIdx.x; tile < n_tiles; ++n, tile += gridDim.x) {
+      dbg_cta = dbg ? dbg + (size_t)tile * 64 : nullptr;
       // ---- stage 1: S^T_h = K_h Q_h^T for the 8 heads
-      mbar_wait(&bars[Q_FULL], 0);
+      mbar_wait(&bars[Q_FULL], n & 1);
+      if (n > 0) {                                   // the previous tile's epilogue has read every accumulator
+        mbar_wait(&bars[EPI_TMEM], (n - 1) & 1);
+        tcgen05_fence_after_sync();
+      }
       for (int h = 0; h < H; ++h) {
         const int s = h % S::kKBufs;
-        mbar_wait(&bars[K_FULL + s], (h / S::kKBufs) & 1);
+        mbar_wait(&bars[K_FULL + s], (n * kc(s) + h / S::kKBufs) & 1);
         tcgen05_fence_after_sync();
         DAB_STAMP_ISSUER(48 + h);
         const uint32_t ka = smem_base + s * S::kKBuf;
@@ -482,6 +519,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         umma_commit(&bars[V_EMPTY + s + 1]);
       }
       umma_commit(&bars[O_DONE]);
+     }
     }
   } else {
     // ======================================= softmax / epilogue groups =======================================
@@ -494,11 +532,16 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     auto bar_group = [&] { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
     auto bar_all_compute = [] { asm volatile("bar.sync 3, 256;" ::: "memory"); };
 
+   for (int tn = 0, tile = blockIdx.x; tile < n_tiles; ++tn, tile += gridDim.x) {
+    const int b = tile >> 3, i0 = (tile & 7) * IB;
+    const int64_t row0 = (int64_t)b * L + i0;       // first query row (global residue index)
+    (void)i0;
+    dbg_cta = dbg ? dbg + (size_t)tile * 64 : nullptr;
     // pair bias of this thread's key for the group's rows, one quarter (two rows) ahead in registers
     const uint4* bias_t = bias + (row0 + g) * L + gt;      // local row n (i = 2n + g)  ->  + n * 2 * L
     uint4 b_cur[2] = {__ldg(bias_t), __ldg(bias_t + 2 * L)};
     uint4 b_nxt[2] = {__ldg(bias_t + 4 * L), __ldg(bias_t + 6 * L)};
-    mbar_wait(&bars[S_DONE], 0);
+    mbar_wait(&bars[S_DONE], tn & 1);
     tcgen05_fence_after_sync();
     // Four quarters of the 16 query rows; this group owns rows 4q + g and 4q + 2 + g of each quarter and
     // treats them together: one butterfly and one group barrier give the 2 x 8 row maxima.
@@ -606,7 +649,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       for (int c = 0; c < 3; ++c) tfr[c] = __ldg(tc + row * 3 + c);
     }
     uint8_t* stage_e = smem + S::kStaging + warp * 1024;   // 1 KB per warp (the P_i buffers are dead by now)
-    mbar_wait(&bars[O_DONE], 0);
+    mbar_wait(&bars[O_DONE], tn & 1);
     tcgen05_fence_after_sync();
     DAB_STAMP(4);
     const int hsel = gw >> 1;                    // which head of the pair this warp's lanes hold
@@ -626,7 +669,8 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
     bar_all_compute();
     if (stats && g == 0) stats[(row0 + (gt >> 3)) * 16 + 8 + (gt & 7)] = inv_o[gt];
-    float* s_og = reinterpret_cast<float*>(smem);   // [16 i][8 h][24] global-frame points (region X is free)
+    // [16 i][8 h][24] global-frame points, in the third K buffer: the first two already take the next tile's K
+    float* s_og = reinterpret_cast<float*>(smem + 2 * S::kKBuf);
 #pragma unroll
     for (int mm = 0; mm < 2; ++mm) {
       const int m = 2 * g + mm, h = 2 * m + hsel;
@@ -673,6 +717,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       __syncwarp();
     }
     tcgen05_fence_before_sync();
+    mbar_arrive(&bars[EPI_TMEM]);     // every accumulator of this tile has been read: the next tile's MMAs may start
     bar_all_compute();
     // inverse frame + norms (diffab_pytorch.py:327-336,453-457): ol[c'] = sum_k (og[k] - t[k]) R[c'][k];
     // thread (i, h) handles the 8 points of one head -> 48 + 16 contiguous bytes
@@ -700,9 +745,12 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           make_uint4(pack_bf162(nrm[0], nrm[1]), pack_bf162(nrm[2], nrm[3]), pack_bf162(nrm[4], nrm[5]),
                      pack_bf162(nrm[6], nrm[7]));
     }
+    DAB_STAMP(5);
+    mbar_arrive(&bars[EPI_DONE]);     // staging tiles and s_og are no longer read: region X belongs to the next tile
+   }
   }
+  tcgen05_fence_before_sync();
   __syncthreads();
-  DAB_STAMP(5);
   if (dbg_cta && tid == 0) {
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -956,9 +1004,17 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
     uint32_t be[2] = {C, L};
     if (int rc = make_tensor_map_bf16(&me, e_bf16, 2, de, se, be, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     DAB_ENSURE_SMEM(ipa_core_kernel, CoreSmem::kTotal);
-    ipa_core_kernel<<<dim3(L / IB, B), 320, CoreSmem::kTotal, s>>>(mq, mk, mv, me, bias, ws.tc, R, ws.cat,
-                                                                   save_for_bwd ? ws.stats : nullptr,
-                                                                   save_for_bwd ? ws.pu : nullptr, g_core_dbg);
+    const int n_tiles = B * (L / IB);
+    int n_sm = 148;
+    {
+      int dev_id = 0;
+      cudaGetDevice(&dev_id);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev_id);
+    }
+    const int grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;     // persistent: two CTAs per SM
+    ipa_core_kernel<<<grid, 320, CoreSmem::kTotal, s>>>(mq, mk, mv, me, bias, ws.tc, R, ws.cat,
+                                                        save_for_bwd ? ws.stats : nullptr,
+                                                        save_for_bwd ? ws.pu : nullptr, n_tiles, g_core_dbg);
     count_launch();
   }
   if (phases & 4) {
