@@ -648,7 +648,8 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
       for (int c = 0; c < 3; ++c) tfr[c] = __ldg(tc + row * 3 + c);
     }
-    uint8_t* stage_e = smem + S::kStaging + warp * 1024;   // 1 KB per warp (the P_i buffers are dead by now)
+    // 1 KB per warp in the tail of the P_h region (its first 24 KB receive the next tile's Q during the epilogue)
+    uint8_t* stage_e = smem + S::kPh + S::kQBuf + warp * 1024;
     mbar_wait(&bars[O_DONE], tn & 1);
     tcgen05_fence_after_sync();
     DAB_STAMP(4);
@@ -693,31 +694,6 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         for (int i = 0; i < IB; ++i) s_og[(i * H + h) * 24 + lane] = o[i] * inv_o[i * H + h];
       }
     }
-    // pair aggregation: accumulator n (16 columns) holds rows 2n (lanes 0-63 = channel c, columns 0-7 = heads) and
-    // 2n + 1 (lanes 64-127, columns 8-15).  The last pair MMA is older than the O^T MMAs, so O_DONE covers it.
-    // Group g drains the accumulators n = g, g + 2, ...; warp gw holds channels 32 (gw & 1) .. + 31 of row 2n + hsel.
-    for (int n = g; n < IB / 2; n += 2) {
-      const int i = 2 * n + hsel;
-      float v[8];
-      tmem_ld_x8(tmem_lane + kColPair + n * 16 + hsel * 8, v);
-      tmem_wait_ld();
-      {
-        const float4 a0 = *reinterpret_cast<const float4*>(inv_o + i * H), a1 = *reinterpret_cast<const float4*>(inv_o + i * H + 4);
-        const float na[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        __nv_bfloat16* st16 = reinterpret_cast<__nv_bfloat16*>(stage_e);
-#pragma unroll
-        for (int h = 0; h < H; ++h) st16[h * 32 + lane] = __float2bfloat16_rn(v[h] * na[h]);
-      }
-      __syncwarp();
-      {   // [8 h][64 B] -> 32 chunks of 16 B, one per lane
-        const int h = lane >> 2, part = lane & 3;
-        *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + NS + h * C + (gw & 1) * 32 + part * 8) =
-            reinterpret_cast<const uint4*>(stage_e)[lane];
-      }
-      __syncwarp();
-    }
-    tcgen05_fence_before_sync();
-    mbar_arrive(&bars[EPI_TMEM]);     // every accumulator of this tile has been read: the next tile's MMAs may start
     bar_all_compute();
     // inverse frame + norms (diffab_pytorch.py:327-336,453-457): ol[c'] = sum_k (og[k] - t[k]) R[c'][k];
     // thread (i, h) handles the 8 points of one head -> 48 + 16 contiguous bytes
@@ -745,8 +721,33 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           make_uint4(pack_bf162(nrm[0], nrm[1]), pack_bf162(nrm[2], nrm[3]), pack_bf162(nrm[4], nrm[5]),
                      pack_bf162(nrm[6], nrm[7]));
     }
+    mbar_arrive(&bars[EPI_DONE]);     // s_og is no longer read: the whole of region X belongs to the next tile
+    // pair aggregation: accumulator n (16 columns) holds rows 2n (lanes 0-63 = channel c, columns 0-7 = heads) and
+    // 2n + 1 (lanes 64-127, columns 8-15).  The last pair MMA is older than the O^T MMAs, so O_DONE covers it.
+    // Group g drains the accumulators n = g, g + 2, ...; warp gw holds channels 32 (gw & 1) .. + 31 of row 2n + hsel.
+    for (int n = g; n < IB / 2; n += 2) {
+      const int i = 2 * n + hsel;
+      float v[8];
+      tmem_ld_x8(tmem_lane + kColPair + n * 16 + hsel * 8, v);
+      tmem_wait_ld();
+      {
+        const float4 a0 = *reinterpret_cast<const float4*>(inv_o + i * H), a1 = *reinterpret_cast<const float4*>(inv_o + i * H + 4);
+        const float na[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        __nv_bfloat16* st16 = reinterpret_cast<__nv_bfloat16*>(stage_e);
+#pragma unroll
+        for (int h = 0; h < H; ++h) st16[h * 32 + lane] = __float2bfloat16_rn(v[h] * na[h]);
+      }
+      __syncwarp();
+      {   // [8 h][64 B] -> 32 chunks of 16 B, one per lane
+        const int h = lane >> 2, part = lane & 3;
+        *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + NS + h * C + (gw & 1) * 32 + part * 8) =
+            reinterpret_cast<const uint4*>(stage_e)[lane];
+      }
+      __syncwarp();
+    }
+    tcgen05_fence_before_sync();
+    mbar_arrive(&bars[EPI_TMEM]);     // every accumulator of this tile has been read: the next tile's MMAs may start
     DAB_STAMP(5);
-    mbar_arrive(&bars[EPI_DONE]);     // staging tiles and s_og are no longer read: region X belongs to the next tile
    }
   }
   tcgen05_fence_before_sync();
