@@ -252,7 +252,7 @@ static_assert(CoreSmem::kTotal <= 113 * 1024, "two CTAs per SM");
 enum Bar { K_FULL = 0, K_EMPTY = 3, Q_FULL = 6, S_DONE = 7, E_FULL = 8, E_EMPTY = 12, PAIR = 16 /* [group][slot] */,
            V_FULL = 20, V_EMPTY = 24, O_DONE = 28, P_READY = 29 /* [group][slot], 128 arrivals */,
            EPI_TMEM = 33 /* 256 arrivals: epilogue has read every accumulator */, EPI_DONE = 34 /* 256: region X free */,
-           N_BARS = 35 };
+           EPI_SFREE = 35 /* 256: the O^T accumulators (columns of S^T) have been read */, N_BARS = 36 };
 
 // TMEM columns
 constexpr uint32_t kColS = 0, kColPair = 128 /* 16 rows x 8 */, kTmemCols = 256;
@@ -369,7 +369,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // The producer lane initialises the barriers itself and starts the first loads right away: they are in flight
     // while the rest of the CTA allocates TMEM and synchronises (first-load latency is ~10 % of a CTA's life).
     for (int i = 0; i < N_BARS; ++i)
-      mbar_init(&bars[i], (i >= P_READY && i < P_READY + 4) ? 128u : ((i == EPI_TMEM || i == EPI_DONE) ? 256u : 1u));
+      mbar_init(&bars[i], (i >= P_READY && i < P_READY + 4) ? 128u : (i >= EPI_TMEM ? 256u : 1u));
     fence_barrier_init();
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
     const int b = (int)blockIdx.x >> 3;
@@ -442,8 +442,8 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       dbg_cta = dbg ? dbg + (size_t)tile * 64 : nullptr;
       // ---- stage 1: S^T_h = K_h Q_h^T for the 8 heads
       mbar_wait(&bars[Q_FULL], n & 1);
-      if (n > 0) {                                   // the previous tile's epilogue has read every accumulator
-        mbar_wait(&bars[EPI_TMEM], (n - 1) & 1);
+      if (n > 0) {                                   // the previous tile's epilogue has read the O^T accumulators
+        mbar_wait(&bars[EPI_SFREE], (n - 1) & 1);    // (same columns as S^T; the pair accumulators are waited for below)
         tcgen05_fence_after_sync();
       }
       for (int h = 0; h < H; ++h) {
@@ -473,6 +473,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       //      N = 16: 8 heads of each row, K = 128 j).  The two off-diagonal blocks (row 2n channels x row 2n+1
       //      probabilities and vice versa) are computed and ignored: a small tcgen05.mma costs the same ~90 cycles
       //      whatever its shape, so halving the instruction count is what matters.
+      if (n > 0) mbar_wait(&bars[EPI_TMEM], (n - 1) & 1);    // previous tile's pair accumulators drained
       for (int n = 0; n < IB / 2; ++n) {
         const int st = (2 * n) % S::kEStages;     // rows 2n, 2n+1 sit in consecutive ring stages
         const int slot = n & 1;
@@ -694,6 +695,8 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         for (int i = 0; i < IB; ++i) s_og[(i * H + h) * 24 + lane] = o[i] * inv_o[i * H + h];
       }
     }
+    tcgen05_fence_before_sync();
+    mbar_arrive(&bars[EPI_SFREE]);    // O^T read: the next tile's S^T MMAs may overwrite these columns
     bar_all_compute();
     // inverse frame + norms (diffab_pytorch.py:327-336,453-457): ol[c'] = sum_k (og[k] - t[k]) R[c'][k];
     // thread (i, h) handles the 8 points of one head -> 48 + 16 contiguous bytes
