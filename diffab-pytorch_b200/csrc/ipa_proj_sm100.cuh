@@ -29,8 +29,8 @@ struct ProjSmem {
   static constexpr int kBars = kMisc;                 // 16 mbarriers
   static constexpr int kTmemSlot = kBars + 16 * 8;
   static constexpr int kCen = kTmemSlot + 16;         // centroid partials [4][3] + result [3]
-  static constexpr int kStage = kMisc + 512;          // per-group staging: two [128 rows][64 B] tiles, 64B-swizzled
-  static constexpr int kStageGroup = 2 * 8192;        // (512-byte aligned), the source of the TMA stores
+  static constexpr int kStage = kMisc + 512;          // per-warp staging: two [32 rows][64 B] tiles, 64B-swizzled
+  static constexpr int kStageGroup = 2 * 8192;        // (512-byte aligned), the source of the TMA stores; 4 warps per group
   static constexpr int kTotal = kStage + 2 * kStageGroup;   // 115,200: two CTAs per SM, exactly
 };
 enum ProjBar { W_FULL = 0, W_EMPTY = 3, ACC_FULL = 6, ACC_EMPTY = 8, PROJ_N_BARS = 10 };
@@ -157,29 +157,29 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
     if (g == 0 && split == 0) { tc[row * 3] = tcx; tc[row * 3 + 1] = tcy; tc[row * 3 + 2] = tcz; }
     const float ss = rsqrtf((float)DS), sp = rsqrtf(4.5f * P), st = rsqrtf(3.0f);
     // Every output segment is 64 bytes per residue (a head's scalars, point-hi or point-lo columns).  A thread
-    // drops its segment into a [128 rows][64 B] shared-memory tile (64B swizzle: conflict-free 16-byte stores) and
-    // one thread of the group hands the whole tile to the TMA as a 2-D store (row pitch = the packed row).  Two
-    // tiles per group and round; a round = fill, fence, group barrier, issue.
-    uint8_t* stg = smem + S::kStage + g * S::kStageGroup;
-    auto bar_group = [&] { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
+    // drops its segment into a warp-private [32 rows][64 B] shared-memory tile (64B swizzle: conflict-free 16-byte
+    // stores) and lane 0 hands the tile to the TMA as a 2-D store (row pitch = the packed row).  Two tiles per warp
+    // and round; a round = fill, fence, __syncwarp, issue - no block-level barrier anywhere in the epilogue.
+    uint8_t* stg = smem + S::kStage + warp * 4096;            // 2 x 2 KB
+    const int lrow = gt & 31, grow0 = b * L + (gt & ~31);     // row inside the warp's tile; first row of the tile
     bool first_round = true;
     auto begin_round = [&] {      // the previous round's stores must have finished reading the tiles
       if (!first_round) {
-        if (gt == 0) tma_store_wait_read();
-        bar_group();
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
       }
       first_round = false;
     };
     auto put = [&](int slot, const uint4 (&seg)[4]) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(stg + slot * 8192 + swz64_offset(gt, q)) = seg[q];
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(stg + slot * 2048 + swz64_offset(lrow, q)) = seg[q];
     };
     auto end_round = [&](const CUtensorMap* m0, int col0, const CUtensorMap* m1, int col1) {
       fence_proxy_async_smem();
-      bar_group();
-      if (gt == 0) {
-        tma_store_2d(m0, stg, col0, b * L);
-        tma_store_2d(m1, stg + 8192, col1, b * L);
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(m0, stg, col0, grow0);
+        tma_store_2d(m1, stg + 2048, col1, grow0);
         tma_store_commit();
       }
     };
@@ -293,7 +293,7 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
       }
       if (tt == 4 || tt == 16) PROJ_STAMP(tt == 4 ? 4 : 7);
     }
-    if (gt == 0) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   }
   tcgen05_fence_before_sync();
   __syncthreads();

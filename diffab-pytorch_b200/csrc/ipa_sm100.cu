@@ -975,11 +975,11 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
     if (int rc = make_tensor_map_bf16(&mw64, pk + po.wcat, 2, dw, sw, b64, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (int rc = make_tensor_map_bf16(&mw48, pk + po.wcat, 2, dw, sw, b48, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     DAB_ENSURE_SMEM(ipa_proj_kernel, ProjSmem::kTotal);
-    CUtensorMap msq, msk, msv;   // TMA-store views of the packed operands: 64-byte segments of 128 rows
+    CUtensorMap msq, msk, msv;   // TMA-store views of the packed operands: 64-byte segments of 32 rows
     {
       uint64_t dqk[2] = {(uint64_t)H * QK_W, (uint64_t)M}, sqk[1] = {(uint64_t)H * QK_W * 2};
       uint64_t dv[2] = {(uint64_t)H * V_W, (uint64_t)M}, sv[1] = {(uint64_t)H * V_W * 2};
-      uint32_t bs[2] = {32, L};
+      uint32_t bs[2] = {32, 32};     // one warp's rows
       if (int rc = make_tensor_map_bf16(&msq, ws.Qp, 2, dqk, sqk, bs, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
       if (int rc = make_tensor_map_bf16(&msk, ws.Kp, 2, dqk, sqk, bs, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
       if (int rc = make_tensor_map_bf16(&msv, ws.Vp, 2, dv, sv, bs, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
