@@ -464,7 +464,7 @@ def measure_train_step(dev, dist, world, shapes, B=64, steps=5, warmup=3):
     Device time over `steps` steps (CUDA events), max over ranks; weak scaling (every rank has its own 64 patches)."""
     from diffab_pytorch_b200 import synth
     from diffab_pytorch_b200.diffab_pytorch import DiffAb
-    from diffab_pytorch_b200.distributed import GradientBucket, ddp_step, diffab_loss_terms
+    from diffab_pytorch_b200.distributed import GradientBucket, GraphedTrainStep, diffab_loss_terms
     rank = dist.get_rank() if dist is not None else 0
     model = DiffAb(*TRAIN_CFG, device=dev).train()
     model.load_state_dict(synth.synthetic_state(shapes, seed=0))
@@ -474,13 +474,13 @@ def measure_train_step(dev, dist, world, shapes, B=64, steps=5, warmup=3):
     prev_prec = torch.get_float32_matmul_precision()
     torch.set_float32_matmul_precision("high")
     bucket = GradientBucket(model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
     batch = {k: v.to(dev) for k, v in synth.make_patches(B, L, seed=2000 + rank, with_distmat=False).items()}
     batch["distmat"] = torch.cat([synth.pairwise_atom_distances(batch["xyz"][i:i + 8]) for i in range(0, B, 8)])
     group = dist.group.WORLD if dist is not None else None
-
-    def step():
-        return ddp_step(lambda: diffab_loss_terms(model, batch), bucket, opt, group=group)
+    # zero + forward + backward (+ Adam) captured in CUDA graphs; timesteps and noise are drawn inside the step, so every
+    # replay is a different optimisation step on the resident batch
+    step = GraphedTrainStep(lambda: diffab_loss_terms(model, batch), bucket, opt, group=group)
 
     for _ in range(warmup):
         loss = step()
@@ -500,11 +500,13 @@ def measure_train_step(dev, dist, world, shapes, B=64, steps=5, warmup=3):
         ms = float(tmax)
     finite = bool(torch.isfinite(loss))
     torch.set_float32_matmul_precision(prev_prec)
-    del model, bucket, opt, batch
+    del step, model, bucket, opt, batch
     torch.cuda.empty_cache()
     return {"metric": "training steps/s (config 5: B=64 patches per GPU, noising + fwd + losses + bwd + "
                       "all-reduce + Adam, bf16 tensor-core IPA)", "value": 1000.0 / ms, "unit": "steps/s",
             "patches_per_s": B * world * 1000.0 / ms, "ms_per_step": ms, "patches_per_gpu": B, "n_gpus": world,
+            "cuda_graph": "whole step (zero, forward, backward, Adam) replayed from CUDA graphs; gradient all-reduce "
+                          "between the backward and the optimizer graph when n_gpus > 1",
             "matmul_precision": "bf16 tensor-core IPA kernels; TF32 for the PyTorch glue and context encoders "
                                 "(as the reference's train.py:47)", "loss_finite": finite}
 

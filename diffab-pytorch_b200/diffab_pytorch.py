@@ -62,8 +62,10 @@ class AngularEncoding(nn.Module):
     def __init__(self, num_funcs=3):
         super().__init__()
         self.num_funcs = num_funcs
-        self.freq_bands = torch.tensor([float(i + 1) for i in range(num_funcs)] +
-                                       [1.0 / (i + 1) for i in range(num_funcs)])
+        # a non-persistent buffer: follows the module's device (no per-call host-to-device copy, CUDA-graph safe)
+        # without appearing in the state dict
+        self.register_buffer("freq_bands", torch.tensor([float(i + 1) for i in range(num_funcs)] +
+                                                        [1.0 / (i + 1) for i in range(num_funcs)]), persistent=False)
 
     def get_output_dimension(self, d_in):
         return d_in * (4 * self.num_funcs + 1)
@@ -81,6 +83,33 @@ def _mlp(dims, final_relu=False):
         if i + 2 < len(dims) or final_relu:
             layers.append(nn.ReLU())
     return nn.Sequential(*layers)
+
+
+class _SmallVocabEmbedding(torch.autograd.Function):
+    """nn.Embedding lookup whose weight gradient is one_hot(idx)^T @ grad (a small GEMM) instead of PyTorch's
+    sort-and-segment kernels (~100 us per call for the 8192 residues of a training batch).  Same values."""
+
+    @staticmethod
+    def forward(ctx, idx, weight, padding_idx):
+        ctx.save_for_backward(idx)
+        ctx.vocab, ctx.padding_idx = weight.shape[0], padding_idx
+        return F.embedding(idx, weight)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        onehot = F.one_hot(idx.reshape(-1), ctx.vocab).to(g.dtype)
+        dw = onehot.t() @ g.reshape(-1, g.shape[-1])
+        if ctx.padding_idx is not None:
+            dw[ctx.padding_idx] = 0          # nn.Embedding(padding_idx=...) never updates that row
+        return None, dw, None
+
+
+def _embed(module, idx):
+    """``module(idx)`` for a small-vocabulary nn.Embedding; on the GPU with the gradient through a one-hot GEMM."""
+    if idx.is_cuda and torch.is_grad_enabled() and module.weight.requires_grad:
+        return _SmallVocabEmbedding.apply(idx, module.weight, module.padding_idx)
+    return module(idx)
 
 
 class ResidueEmbedding(nn.Module):
@@ -103,9 +132,12 @@ class ResidueEmbedding(nn.Module):
         A = self.max_n_atoms_per_residue
         if sequence_context_mask is not None:
             seq_idx = torch.where(sequence_context_mask.bool(), seq_idx, torch.full_like(seq_idx, AA_UNK))
-        aa = self.amino_acid_type_embedding(seq_idx)
+        aa = _embed(self.amino_acid_type_embedding, seq_idx)
         rel = xyz - xyz[:, :, CA_IDX:CA_IDX + 1, :]
-        local = torch.einsum("blji,blaj->blai", orientation, rel) * atom_mask[..., None]   # O^T (x - x_CA)
+        if xyz.is_cuda:
+            local = _so3.small_matmul(rel, orientation) * atom_mask[..., None]             # O^T (x - x_CA), row vectors
+        else:
+            local = torch.einsum("blji,blaj->blai", orientation, rel) * atom_mask[..., None]
         # place the (A,3) local block in the slot of the residue's amino-acid type, zeros elsewhere
         coord = torch.zeros(B, L, self.max_n_aa_types, A * 3, device=xyz.device, dtype=local.dtype)
         coord.scatter_(2, seq_idx[:, :, None, None].expand(B, L, 1, A * 3), local.reshape(B, L, 1, A * 3))
@@ -115,7 +147,7 @@ class ResidueEmbedding(nn.Module):
             sm = structure_context_mask
             coord = coord * sm[:, :, None]
             dih = dih * (sm & torch.roll(sm, shifts=-1, dims=1))[:, :, None]
-        chain = self.chain_embedding(chain_idx)
+        chain = _embed(self.chain_embedding, chain_idx)
         return self.mlp(torch.cat([aa, coord, dih, chain], dim=-1))
 
 
@@ -148,6 +180,101 @@ class _RbfFunction(torch.autograd.Function):
         _lib.check(_lib.lib().dab_rbf_bwd(ptr(g), ptr(d), ptr(s), ptr(m), ptr(c), B, L, ctx.squared, ptr(dc),
                                           _lib.stream_ptr()), "dab_rbf_bwd")
         return None, None, None, dc, None
+
+
+class _PairMlpFunction(torch.autograd.Function):
+    """PairEmbedding's two MLPs with bf16 activations and hand-written gradients (mixed-precision training).
+
+    Forward: tensor-core GEMMs with fused bias / ReLU epilogues on bf16 activations (fp32 accumulation).  The first
+    mlp layer acts on cat[f_type | f_rel | f_dist | f_dih] (diffab_pytorch.py:307 of the reference): its embedding
+    blocks are applied to the TABLES (441 and 65 rows) and ``dab_pair_base_fwd`` turns them, the residue-level index
+    vectors and the pairwise dihedrals into the per-pair pre-activation in one pass, so neither the (B, L, L) index
+    tensors nor the 210-wide concat exist.
+    Backward: every parameter gradient is a bf16 GEMM contracted over the B*L*L pairs with an fp32 result (bias
+    gradients included: a GEMM against the 0/1 residue-pair mask); the two embedding tables receive theirs through
+    ``dab_pair_table_grad`` (class sums in shared memory) instead of sorting 10^6 indices per table.  Only ``rbf``
+    among the inputs carries a gradient (-> ``_RbfFunction`` -> pair2distcoef)."""
+
+    @staticmethod
+    def forward(ctx, rbf, dihedrals, seq_idx, residue_idx, chain_idx, res_mask, max_dist, e_type, e_rel, wd1, bd1, wd2,
+                bd2, w1, b1, w2, b2, w3, b3):
+        bf = torch.bfloat16
+        B, L = seq_idx.shape
+        P = B * L * L
+        D = w2.shape[0]
+        lib, st = _lib.lib(), _lib.stream_ptr()
+        if D != 64 or w1.shape[1] != 3 * D + 18 or e_type.shape[0] != 441 or e_rel.shape[0] != 2 * max_dist + 1:
+            raise ValueError("mixed-precision PairEmbedding needs d_feat = 64, 21 residue types and 2 pairwise dihedrals")
+        seq_idx = _lib.dev(seq_idx, torch.int64, "seq_idx")
+        residue_idx = _lib.dev(residue_idx, torch.int64, "residue_idx")
+        chain_idx = _lib.dev(chain_idx, torch.int64, "chain_idx")
+        res_mask = _lib.mask_u8(res_mask, "residue mask")
+        x0 = rbf.reshape(P, -1)
+        kpad = x0.shape[1] - wd1.shape[1]
+        wd1p = F.pad(wd1, (0, kpad)).to(bf)
+        a1 = torch._addmm_activation(bd1.to(bf), x0, wd1p.t())                     # relu(rbf Wd1^T + bd1)
+        fd = torch._addmm_activation(bd2.to(bf), a1, wd2.to(bf).t())                # f_dist
+        t_type = (e_type @ w1[:, :D].t() + b1).to(bf)                               # (441, D): W1 on the table, bias folded in
+        t_rel = (e_rel @ w1[:, D:2 * D].t()).to(bf)                                 # (65, D)
+        base = torch.empty(P, D, device=rbf.device, dtype=bf)
+        xh = torch.empty(P, 32, device=rbf.device, dtype=bf)
+        _lib.check(lib.dab_pair_base_fwd(ptr(seq_idx), ptr(residue_idx), ptr(chain_idx),
+                                         ptr(_lib.dev(dihedrals, torch.float32, "pairwise_dihedrals")), ptr(t_type), ptr(t_rel),
+                                         B, L, max_dist, ptr(base), ptr(xh), st), "dab_pair_base_fwd")
+        w1h = F.pad(w1[:, 3 * D:], (0, xh.shape[1] - (w1.shape[1] - 3 * D))).to(bf)
+        h1 = base.addmm_(fd, w1[:, 2 * D:3 * D].to(bf).t()).addmm_(xh, w1h.t()).relu_()
+        h2 = torch._addmm_activation(b2.to(bf), h1, w2.to(bf).t())
+        out = torch.addmm(b3.to(bf), h2, w3.to(bf).t())
+        # `* pair_mask` (:309-311): masked rows of the output are zeroed, and so are those of h2 - its only other use is
+        # the backward pass, where zero rows switch the whole pair off (threshold_backward, weight-gradient GEMMs)
+        _lib.check(lib.dab_pair_zero_masked(ptr(out), ptr(res_mask), B, L, st), "dab_pair_zero_masked")
+        _lib.check(lib.dab_pair_zero_masked(ptr(h2), ptr(res_mask), B, L, st), "dab_pair_zero_masked")
+        ctx.save_for_backward(x0, xh, a1, fd, h1, h2, seq_idx, residue_idx, chain_idx, res_mask, e_type, e_rel, wd1p, wd2,
+                              w1, w2, w3)
+        ctx.kpad, ctx.max_dist = kpad, max_dist
+        return out.view(B, L, L, D)
+
+    @staticmethod
+    def backward(ctx, g):
+        bf, f32 = torch.bfloat16, torch.float32
+        (x0, xh, a1, fd, h1, h2, seq_idx, residue_idx, chain_idx, res_mask, e_type, e_rel, wd1p, wd2, w1, w2,
+         w3) = ctx.saved_tensors
+        B, L = seq_idx.shape
+        P, D = h2.shape
+        lib, st = _lib.lib(), _lib.stream_ptr()
+        mm32 = lambda a, b: torch.mm(a, b, out_dtype=f32)
+        tb = torch.ops.aten.threshold_backward
+        rm = res_mask.to(bf)
+        pair_mask = (rm[:, :, None] * rm[:, None, :]).reshape(P, 1).expand(P, 8).contiguous()
+        ones = torch.ones(P, 8, device=g.device, dtype=bf)
+        colsum = lambda a: mm32(a.t(), ones)[:, 0]        # bias gradients as GEMMs: faster than a column reduction
+        g3 = _lib.dev(g.reshape(P, D), bf, "grad")         # masked pairs: h2 rows are zero, pair_mask handles the bias
+        d_w3, d_b3 = mm32(g3.t(), h2), mm32(g3.t(), pair_mask)[:, 0]
+        g2 = tb(torch.mm(g3, w3.to(bf)), h2, 0)
+        d_w2, d_b2 = mm32(g2.t(), h1), colsum(g2)
+        g1 = tb(torch.mm(g2, w2.to(bf)), h1, 0)
+        del g2
+        d_b1 = colsum(g1)
+        d_w1 = torch.empty_like(w1)
+        d_w1[:, 2 * D:3 * D] = mm32(g1.t(), fd)
+        d_w1[:, 3 * D:] = mm32(g1.t(), xh)[:, :w1.shape[1] - 3 * D]
+        # embedding tables: S_type[s_i*21 + s_j] / S_rel[offset] = class sums of g1 over the pairs
+        s_type = torch.zeros(e_type.shape[0], D, device=g.device, dtype=f32)
+        s_rel = torch.zeros(e_rel.shape[0], D, device=g.device, dtype=f32)
+        _lib.check(lib.dab_pair_table_grad(ptr(g1), ptr(seq_idx), ptr(residue_idx), ptr(chain_idx), B, L, ctx.max_dist,
+                                           ptr(s_type), ptr(s_rel), st), "dab_pair_table_grad")
+        d_w1[:, :D] = s_type.t() @ e_type
+        d_w1[:, D:2 * D] = s_rel.t() @ e_rel
+        d_type, d_rel = s_type @ w1[:, :D], s_rel @ w1[:, D:2 * D]
+        gd2 = tb(torch.mm(g1, w1[:, 2 * D:3 * D].to(bf)), fd, 0)
+        del g1
+        d_wd2, d_bd2 = mm32(gd2.t(), a1), colsum(gd2)
+        gd1 = tb(torch.mm(gd2, wd2.to(bf)), a1, 0)
+        del gd2
+        d_wd1, d_bd1 = mm32(gd1.t(), x0)[:, :x0.shape[1] - ctx.kpad], colsum(gd1)
+        d_rbf = torch.mm(gd1, wd1p).view(B, L, L, -1) if ctx.needs_input_grad[0] else None
+        return (d_rbf, None, None, None, None, None, None, d_type, d_rel, d_wd1, d_bd1, d_wd2, d_bd2, d_w1, d_b1, d_w2,
+                d_b2, d_w3, d_b3)
 
 
 class PairEmbedding(nn.Module):
@@ -206,39 +333,32 @@ class PairEmbedding(nn.Module):
                 sequence_context_mask, distmat_is_squared=False):
         B, L = seq_idx.shape
         am = atom_mask
-        atom_pair = (am[:, :, None, :, None] * am[:, None, :, None, :]).flatten(-2)
         res_mask = am[:, :, CA_IDX]
-        res_pair = res_mask[:, :, None] * res_mask[:, None, :]
         if sequence_context_mask is not None:
             seq_idx = torch.where(sequence_context_mask.bool(), seq_idx, torch.full_like(seq_idx, AA_UNK))
+        if getattr(self, "fused_rbf", False) and distmat.is_cuda and distmat.shape[-1] * distmat.shape[-2] == 225:
+            # Mixed-precision training.  (1) The six (B, L, L, 225) passes collapse into one kernel each way; the first
+            # distance layer then runs as an aligned bf16 GEMM (K padded 225 -> 232) with fp32 accumulation.
+            rbf = _RbfFunction.apply(distmat, seq_idx, atom_mask, self.pair2distcoef.weight, distmat_is_squared)
+            # (2) Both MLPs on bf16 activations with hand-written gradients (_PairMlpFunction); the result is the bf16
+            # pair tensor the tensor-core IPA layers stream.
+            de, mlp = self.distance_embedding, self.mlp
+            return _PairMlpFunction.apply(
+                rbf, dihedrals, seq_idx, residue_idx, chain_idx, res_mask, self.max_dist_to_consider,
+                self.aa_pair_type_embedding.weight, self.relpos_embedding.weight, de[0].weight, de[0].bias, de[2].weight,
+                de[2].bias, mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias, mlp[4].weight, mlp[4].bias)
+        res_pair = res_mask[:, :, None] * res_mask[:, None, :]
         pair_type = seq_idx[:, :, None] * self.max_n_aa_types + seq_idx[:, None, :]
         # note: the reference multiplies by the PRODUCT of chain indices, not an equality mask (:279,285)
         chain_prod = chain_idx[:, :, None] * chain_idx[:, None, :]
         rel = (residue_idx[:, :, None] - residue_idx[:, None, :]).clamp(-self.max_dist_to_consider,
                                                                          self.max_dist_to_consider)
-        if getattr(self, "fused_rbf", False) and distmat.is_cuda and distmat.shape[-1] * distmat.shape[-2] == 225:
-            # Mixed-precision training.  (1) The six (B, L, L, 225) passes collapse into one kernel each way; the first
-            # distance layer then runs as an aligned bf16 GEMM (K padded 225 -> 232) with fp32 accumulation.
-            rbf = _RbfFunction.apply(distmat, seq_idx, atom_mask, self.pair2distcoef.weight, distmat_is_squared)
-            lin = self.distance_embedding[0]
-            a1 = F.linear(rbf, F.pad(lin.weight, (0, 7)).to(torch.bfloat16)).float() + lin.bias
-            f_dist = self.distance_embedding[1:](a1)
-            # (2) The first mlp layer acts on cat[f_type | f_rel | f_dist | f_dih]: its embedding blocks are applied to
-            # the TABLES (441 and 65 rows) and gathered, so neither the embeddings nor the 210-wide concat are
-            # materialised per pair and the remaining products have K = 64 and K = 18.
-            D = self.d_feat
-            w1, b1 = self.mlp[0].weight, self.mlp[0].bias
-            h = F.embedding(pair_type, self.aa_pair_type_embedding.weight @ w1[:, :D].t())
-            h = h + F.embedding(rel + self.max_dist_to_consider,
-                                self.relpos_embedding.weight @ w1[:, D:2 * D].t()) * chain_prod[..., None]
-            f_dih = F.pad(self.dihedral_embedding(dihedrals), (0, 6))           # K = 18 -> 24: aligned GEMM
-            h = h + F.linear(f_dist, w1[:, 2 * D:3 * D]) + F.linear(f_dih, F.pad(w1[:, 3 * D:], (0, 6)), b1)
-            return self.mlp[1:](h) * res_pair[..., None]
         f_type = self.aa_pair_type_embedding(pair_type)
         f_rel = self.relpos_embedding(rel + self.max_dist_to_consider) * chain_prod[..., None]
         coef = F.softplus(self.pair2distcoef(pair_type))
         d = distmat.flatten(-2)
         d2 = d if distmat_is_squared else d**2   # sample() hands over squared distances it computed itself
+        atom_pair = (am[:, :, None, :, None] * am[:, None, :, None, :]).flatten(-2)
         f_dist = self.distance_embedding(torch.exp(-1 * coef * d2) * atom_pair)
         f_dih = self.dihedral_embedding(dihedrals)
         return self.mlp(torch.cat([f_type, f_rel, f_dist, f_dih], dim=-1)) * res_pair[..., None]
@@ -577,7 +697,7 @@ class Denoiser(nn.Module):
               pair_bias=None):
         """Everything up to the three head outputs; returns (eps, rotvec, seq_posterior)."""
         n_residues = seq_idx_t.shape[1]
-        h = torch.cat([res_context_emb, self.sequence_embedding(seq_idx_t)], dim=-1)
+        h = torch.cat([res_context_emb, _embed(self.sequence_embedding, seq_idx_t)], dim=-1)
         h = self.to_res_emb(h)
         h = self.ipa(h, pair_context_emb, orientations_t, translations_t, pair_bias)
         t_emb = torch.stack([beta, torch.sin(beta), torch.cos(beta)], dim=-1)
@@ -669,7 +789,7 @@ class Denoiser(nn.Module):
         # the two masks are accepted and unused, as in the reference (:566-567)
         eps, v_eps, post = self.heads(seq_idx_t, translations_t, orientations_t, res_context_emb, pair_context_emb,
                                       beta)
-        o_denoised = orientations_t @ vector_to_rotation_matrix(v_eps)   # :594-596
+        o_denoised = _so3.small_matmul(orientations_t, vector_to_rotation_matrix(v_eps))   # :594-596
         return {"translations_eps": eps, "orientations_t0": o_denoised, "seq_posterior": post}
 
 
@@ -681,7 +801,10 @@ class OrientationLoss(nn.Module):
         self.reduction = reduction
 
     def forward(self, pred_rotmat, target_rotmat):
-        d = torch.einsum("blij,blik->bljk", pred_rotmat, target_rotmat)
+        if pred_rotmat.is_cuda:
+            d = _so3.small_matmul(pred_rotmat.transpose(-1, -2), target_rotmat)
+        else:
+            d = torch.einsum("blij,blik->bljk", pred_rotmat, target_rotmat)
         eye = torch.eye(3, device=d.device, dtype=d.dtype).expand_as(d)
         return F.mse_loss(d, eye, reduction=self.reduction)
 

@@ -135,6 +135,73 @@ def ddp_step(loss_terms: Callable[[], "tuple[torch.Tensor, torch.Tensor]"], buck
     return total[0]
 
 
+class GraphedTrainStep:
+    """``ddp_step`` with the device work captured in CUDA graphs (a training step is ~550 kernel launches; issued
+    eagerly the host, not the GPU, sets the step time).
+
+    Graph A: zero the gradient bucket, forward, backward of the local loss NUMERATOR.  Between the graphs, eagerly:
+    all-reduce of the mask count and of the flat bucket (``world > 1``), division by the global count - the gradient of
+    numerator / global_count, exactly what ``ddp_step`` back-propagates.  Graph B: ``optimizer.step()`` (the optimizer
+    must be constructed with ``capturable=True``).  With one rank everything is ONE graph.
+
+    The tensors of ``batch`` (and of ``t`` / ``noise`` when given) are the graphs' static inputs: refill them in
+    place (``tensor.copy_``) for the next batch.  Random draws made inside the step (timesteps, noise) advance with
+    every replay, as in eager mode.  Shapes are fixed by the capture."""
+
+    def __init__(self, loss_terms: Callable[[], "tuple[torch.Tensor, torch.Tensor]"], bucket: GradientBucket,
+                 optimizer: torch.optim.Optimizer, group=None, warmup: int = 3):
+        self.bucket, self.optimizer, self.group = bucket, optimizer, group
+        _, self.world = world_info(group)
+        for pg in optimizer.param_groups:
+            if not pg.get("capturable", False):
+                raise ValueError("GraphedTrainStep: construct the optimizer with capturable=True")
+        bucket.rebind()
+        self._loss_terms = loss_terms
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm-up off the capture: lazy initialisations, autotuning, workspaces
+            for _ in range(warmup):
+                self._backward_part()
+                self._reduce_part()
+                optimizer.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph_a = torch.cuda.CUDAGraph()
+        self.graph_b = None
+        with torch.cuda.graph(self.graph_a):
+            self._backward_part()
+            if self.world == 1:
+                self._reduce_part()
+                optimizer.step()
+        if self.world > 1:
+            self.graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
+                optimizer.step()
+
+    def _backward_part(self):
+        self.bucket.zero()
+        num, cnt = self._loss_terms()
+        num.backward()
+        self._num = num.detach().reshape(1)
+        self._cnt = cnt.detach().to(num.dtype).reshape(1).clone()
+
+    def _reduce_part(self):
+        if self.world > 1:
+            dist.all_reduce(self._cnt, op=dist.ReduceOp.SUM, group=self.group)
+            self.bucket.all_reduce(self.group)
+        self.bucket.flat.div_(self._cnt)
+        self._loss = self._num / self._cnt
+
+    def __call__(self) -> torch.Tensor:
+        """One optimisation step; returns this rank's share of the global loss (sum over ranks = global loss), as a
+        1-element device tensor that the next call overwrites."""
+        self.graph_a.replay()
+        if self.world > 1:
+            self._reduce_part()
+            self.graph_b.replay()
+        return self._loss
+
+
 def diffab_loss_terms(model, batch, t=None, noise=None):
     """(numerator, count) of the DiffAb training loss on a local shard: the three masked-mean losses of
     ``_shared_step`` share one denominator, so numerator = (seq + pos + rot) * count."""

@@ -243,6 +243,19 @@ int dab_rbf_fwd(const float* distmat, const int64_t* seq_masked, const uint8_t* 
 int dab_rbf_bwd(const void* grad_bf16, const float* distmat, const int64_t* seq_masked, const uint8_t* atom_mask,
                 const float* coef, int B, int L, int squared, float* d_coef, void* stream);
 
+/* Per-pair glue of PairEmbedding's first mlp layer for training (diffab_pytorch.py:262-285,303-311; csrc/pair_train_kernels.cu).
+ * dab_pair_base_fwd: base_bf16[B,L,L,64] = t_type[s_i*21+s_j] + chain_i*chain_j * t_rel[clamp(r_i-r_j)+max_dist] and the angular
+ * encoding of the pairwise dihedrals xh_bf16[B,L,L,32] (columns 18..31 zero); t_type_bf16[441,64], t_rel_bf16[2*max_dist+1,64].
+ * dab_pair_table_grad: class sums of the per-pair gradient g1_bf16[B,L,L,64], accumulated into s_type[441,64] and
+ * s_rel[2*max_dist+1,64] (the latter weighted by chain_i*chain_j).
+ * dab_pair_zero_masked: x_bf16[B,L,L,64] rows with res_mask[b,i] == 0 or res_mask[b,j] == 0 set to zero in place. */
+int dab_pair_base_fwd(const int64_t* seq_masked, const int64_t* residue_idx, const int64_t* chain_idx,
+                      const float* pairwise_dihedrals, const void* t_type_bf16, const void* t_rel_bf16, int B, int L,
+                      int max_dist, void* base_bf16, void* xh_bf16, void* stream);
+int dab_pair_table_grad(const void* g1_bf16, const int64_t* seq_masked, const int64_t* residue_idx, const int64_t* chain_idx,
+                        int B, int L, int max_dist, float* s_type, float* s_rel, void* stream);
+int dab_pair_zero_masked(void* x_bf16, const uint8_t* res_mask, int B, int L, void* stream);
+
 /* Test hooks of the sm_100a path (used by tests/ only): the tcgen05 GEMM C[M,N] = A[M,K] B[N,K]^T + bias
  * (bf16 in, fp32 out; M % 128 == 0, N % 64 == 0, K % 64 == 0) and the operand-packing stage alone. */
 int dab_debug_set_timeline(long long* device_buf /* 64 slots per CTA of the attention core, or NULL */);

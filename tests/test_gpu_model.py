@@ -187,6 +187,39 @@ def test_bf16_training_step_matches_fp32_path():
         assert cos >= 0.97, (n, cos)
 
 
+def test_graphed_training_step_matches_eager_step():
+    """GraphedTrainStep (zero + forward + backward + count division + Adam in one CUDA graph) leaves the same gradient
+    bucket and the same loss as the eager ddp_step under the same injected timesteps and noise (fp32 atomics in the
+    table-gradient kernels make the two runs differ in the last bits), and a replay with refilled static inputs
+    follows the new inputs."""
+    from diffab_pytorch_b200 import distributed as dd
+    batch = _to(synth.make_patches(2, 128, seed=51))
+    torch.manual_seed(3)
+    t = torch.randint(low=1, high=101, size=(2,)).to(DEV)
+    noise = _to(odiff.draw_add_noise_tensors(2, 128))
+    results = {}
+    for mode in ("eager", "graph"):
+        model = _model(0).train()
+        model.train_precision = "bf16"
+        bucket = dd.GradientBucket(model.parameters())
+        opt = torch.optim.Adam(model.parameters(), lr=0.0, capturable=True)    # lr = 0: the weights stay put
+        terms = lambda: dd.diffab_loss_terms(model, batch, t=t, noise=noise)
+        if mode == "eager":
+            loss = dd.ddp_step(terms, bucket, opt)
+        else:
+            step = dd.GraphedTrainStep(terms, bucket, opt, warmup=2)
+            loss = step()
+        results[mode] = (float(loss), bucket.flat.detach().clone())
+    (le, ge), (lg, gg) = results["eager"], results["graph"]
+    assert abs(le - lg) <= 1e-4 * abs(le)
+    assert torch.isfinite(gg).all()
+    assert float((ge - gg).norm() / ge.norm()) < 1e-3
+    # refill a static input in place: the replay must see it
+    t.copy_(torch.full_like(t, 100))
+    l2 = float(step())
+    assert abs(l2 - lg) > 1e-3 * abs(lg)
+
+
 def test_regrouped_sampling_glue_matches_module_path():
     """Denoiser.heads_fast (per-run constants hoisted, heads batched) against Denoiser.heads on the same inputs,
     and a few bf16 reverse steps with / without it under the same injected noise."""
@@ -266,8 +299,9 @@ def test_fused_pair_embedding_matches_module():
 
 
 def test_fused_rbf_training_op_matches_module():
-    """dab_rbf_fwd / dab_rbf_bwd (PairEmbedding's distance features in one pass each way) against the PyTorch ops:
-    output (bf16) and the gradients of pair2distcoef / distance_embedding within bf16 tolerance."""
+    """Mixed-precision PairEmbedding (dab_rbf_fwd / dab_rbf_bwd for the distance features, _PairMlpFunction for the two
+    MLPs on bf16 activations with hand-written gradients) against the fp32 PyTorch module: output (bf16) and every
+    parameter gradient within bf16 tolerance."""
     model = _model(0).train()
     pe = model.pair_context_embedding
     torch.nn.init.normal_(pe.pair2distcoef.weight, std=0.5)     # the reference initialises this table to zeros
@@ -283,22 +317,21 @@ def test_fused_rbf_training_op_matches_module():
         pe.zero_grad()
         y = pe(*args)
         (y * gy).sum().backward()
-        out[fused] = y.detach()
+        assert y.dtype == (torch.bfloat16 if fused else torch.float32)
+        out[fused] = y.detach().float()
         grads[fused] = {n: p.grad.clone() for n, p in pe.named_parameters() if p.grad is not None}
     pe.fused_rbf = False
     assert _rel(out[True], out[False].cpu()) < 2e-2
     assert set(grads[True]) == set(grads[False])
     for n, ref in grads[False].items():
         assert torch.isfinite(grads[True][n]).all(), n
-        if n.startswith(("pair2distcoef", "distance_embedding")):
-            # the two gradients contracted over all B*L*L pairs from bf16 tensors: every entry sums ~10^5 terms of both
-            # signs (the fp32 PyTorch path itself is 2 % off fp64 at its worst entry, tools/dbg_rbf.py); measured
-            # Frobenius error 5-6 %, cosine 0.998
-            got, rf = grads[True][n].double().flatten().cpu(), ref.double().flatten().cpu()
-            assert float((got - rf).norm() / rf.norm()) < 0.1
-            assert float(got @ rf / (got.norm() * rf.norm())) > 0.995
-        else:
-            assert _rel(grads[True][n], ref.cpu()) < 3e-2, n
+        # gradients contracted over all B*L*L pairs from bf16 activations: a ReLU whose bf16 pre-activation lands on the
+        # other side of zero flips a whole term, and with a random upstream gradient nothing averages that out (the fp32
+        # PyTorch path itself is 2 % off fp64 at its worst pair2distcoef entry, tools/dbg_pair_mlp.py); measured
+        # Frobenius error 4-7 %, cosine 0.998 below the ReLUs, 0.4 % for the last layer
+        got, rf = grads[True][n].double().flatten().cpu(), ref.double().flatten().cpu()
+        assert float((got - rf).norm() / rf.norm()) < (0.02 if n.startswith("mlp.4") else 0.1), n
+        assert float(got @ rf / (got.norm() * rf.norm())) > 0.995, n
 
 
 def test_graphed_sampling_follows_weight_updates():
