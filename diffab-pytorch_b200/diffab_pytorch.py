@@ -165,8 +165,9 @@ class _RbfFunction(torch.autograd.Function):
         if d.shape[-1] != 225 or tuple(c.shape) != (441, 225):
             raise ValueError("fused RBF needs 15 atoms per residue and a (441, 225) coefficient table")
         out = torch.empty(B, L, L, 232, device=d.device, dtype=torch.bfloat16)
-        _lib.check(_lib.lib().dab_rbf_fwd(ptr(d), ptr(s), ptr(m), ptr(c), B, L, int(squared), ptr(out),
-                                          _lib.stream_ptr()), "dab_rbf_fwd")
+        ws = torch.empty(_lib.lib().dab_rbf_workspace_bytes(B, L), device=d.device, dtype=torch.uint8)
+        _lib.check(_lib.lib().dab_rbf_fwd(ptr(d), ptr(s), ptr(m), ptr(c), B, L, int(squared), ptr(out), ptr(ws),
+                                          ws.numel(), _lib.stream_ptr()), "dab_rbf_fwd")
         ctx.save_for_backward(d, s, m, c)
         ctx.squared = int(squared)
         return out
@@ -177,8 +178,9 @@ class _RbfFunction(torch.autograd.Function):
         B, L = s.shape
         dc = torch.zeros_like(c)
         g = _lib.dev(g, torch.bfloat16, "grad")
-        _lib.check(_lib.lib().dab_rbf_bwd(ptr(g), ptr(d), ptr(s), ptr(m), ptr(c), B, L, ctx.squared, ptr(dc),
-                                          _lib.stream_ptr()), "dab_rbf_bwd")
+        ws = torch.empty(_lib.lib().dab_rbf_workspace_bytes(B, L), device=d.device, dtype=torch.uint8)
+        _lib.check(_lib.lib().dab_rbf_bwd(ptr(g), ptr(d), ptr(s), ptr(m), ptr(c), B, L, ctx.squared, ptr(dc), ptr(ws),
+                                          ws.numel(), _lib.stream_ptr()), "dab_rbf_bwd")
         return None, None, None, dc, None
 
 
@@ -243,35 +245,41 @@ class _PairMlpFunction(torch.autograd.Function):
         P, D = h2.shape
         lib, st = _lib.lib(), _lib.stream_ptr()
         mm32 = lambda a, b: torch.mm(a, b, out_dtype=f32)
-        tb = torch.ops.aten.threshold_backward
+        bias_grads = torch.zeros(4, D, device=g.device, dtype=f32)
+
+        def relu_bwd(grad, act, slot):
+            """grad * (act > 0) in place, with the bias gradient (column sums) accumulated in the same pass."""
+            _lib.check(lib.dab_relu_bwd_colsum(ptr(grad), ptr(act), P, ptr(grad), ptr(bias_grads[slot]), st),
+                       "dab_relu_bwd_colsum")
+            return grad
+
         rm = res_mask.to(bf)
         pair_mask = (rm[:, :, None] * rm[:, None, :]).reshape(P, 1).expand(P, 8).contiguous()
-        ones = torch.ones(P, 8, device=g.device, dtype=bf)
-        colsum = lambda a: mm32(a.t(), ones)[:, 0]        # bias gradients as GEMMs: faster than a column reduction
         g3 = _lib.dev(g.reshape(P, D), bf, "grad")         # masked pairs: h2 rows are zero, pair_mask handles the bias
         d_w3, d_b3 = mm32(g3.t(), h2), mm32(g3.t(), pair_mask)[:, 0]
-        g2 = tb(torch.mm(g3, w3.to(bf)), h2, 0)
-        d_w2, d_b2 = mm32(g2.t(), h1), colsum(g2)
-        g1 = tb(torch.mm(g2, w2.to(bf)), h1, 0)
+        g2 = relu_bwd(torch.mm(g3, w3.to(bf)), h2, 0)
+        d_w2, d_b2 = mm32(g2.t(), h1), bias_grads[0]
+        g1 = relu_bwd(torch.mm(g2, w2.to(bf)), h1, 1)
         del g2
-        d_b1 = colsum(g1)
+        d_b1 = bias_grads[1]
         d_w1 = torch.empty_like(w1)
         d_w1[:, 2 * D:3 * D] = mm32(g1.t(), fd)
         d_w1[:, 3 * D:] = mm32(g1.t(), xh)[:, :w1.shape[1] - 3 * D]
         # embedding tables: S_type[s_i*21 + s_j] / S_rel[offset] = class sums of g1 over the pairs
         s_type = torch.zeros(e_type.shape[0], D, device=g.device, dtype=f32)
         s_rel = torch.zeros(e_rel.shape[0], D, device=g.device, dtype=f32)
+        ws = torch.empty(lib.dab_pair_table_grad_workspace_bytes(B, L, ctx.max_dist) // 4, device=g.device, dtype=f32)
         _lib.check(lib.dab_pair_table_grad(ptr(g1), ptr(seq_idx), ptr(residue_idx), ptr(chain_idx), B, L, ctx.max_dist,
-                                           ptr(s_type), ptr(s_rel), st), "dab_pair_table_grad")
+                                           ptr(s_type), ptr(s_rel), ptr(ws), ws.numel() * 4, st), "dab_pair_table_grad")
         d_w1[:, :D] = s_type.t() @ e_type
         d_w1[:, D:2 * D] = s_rel.t() @ e_rel
         d_type, d_rel = s_type @ w1[:, :D], s_rel @ w1[:, D:2 * D]
-        gd2 = tb(torch.mm(g1, w1[:, 2 * D:3 * D].to(bf)), fd, 0)
+        gd2 = relu_bwd(torch.mm(g1, w1[:, 2 * D:3 * D].to(bf)), fd, 2)
         del g1
-        d_wd2, d_bd2 = mm32(gd2.t(), a1), colsum(gd2)
-        gd1 = tb(torch.mm(gd2, wd2.to(bf)), a1, 0)
+        d_wd2, d_bd2 = mm32(gd2.t(), a1), bias_grads[2]
+        gd1 = relu_bwd(torch.mm(gd2, wd2.to(bf)), a1, 3)
         del gd2
-        d_wd1, d_bd1 = mm32(gd1.t(), x0)[:, :x0.shape[1] - ctx.kpad], colsum(gd1)
+        d_wd1, d_bd1 = mm32(gd1.t(), x0)[:, :x0.shape[1] - ctx.kpad], bias_grads[3]
         d_rbf = torch.mm(gd1, wd1p).view(B, L, L, -1) if ctx.needs_input_grad[0] else None
         return (d_rbf, None, None, None, None, None, None, d_type, d_rel, d_wd1, d_bd1, d_wd2, d_bd2, d_w1, d_b1, d_w2,
                 d_b2, d_w3, d_b3)

@@ -238,10 +238,12 @@ int dab_pair_embed_fwd_sm100(const void* packed, const int64_t* seq_masked, cons
 
 /* Distance radial-basis features of PairEmbedding for training (diffab_pytorch.py:287-294): one pass forward
  * (rbf_bf16[B,L,L,232], columns 225..231 zero), one pass backward (d_coef[441,225] accumulated into). */
+size_t dab_rbf_workspace_bytes(int B, int L);
 int dab_rbf_fwd(const float* distmat, const int64_t* seq_masked, const uint8_t* atom_mask, const float* coef, int B, int L,
-                int squared, void* rbf_bf16, void* stream);
+                int squared, void* rbf_bf16, void* workspace, size_t workspace_bytes, void* stream);
 int dab_rbf_bwd(const void* grad_bf16, const float* distmat, const int64_t* seq_masked, const uint8_t* atom_mask,
-                const float* coef, int B, int L, int squared, float* d_coef, void* stream);
+                const float* coef, int B, int L, int squared, float* d_coef, void* workspace, size_t workspace_bytes,
+                void* stream);
 
 /* Per-pair glue of PairEmbedding's first mlp layer for training (diffab_pytorch.py:262-285,303-311; csrc/pair_train_kernels.cu).
  * dab_pair_base_fwd: base_bf16[B,L,L,64] = t_type[s_i*21+s_j] + chain_i*chain_j * t_rel[clamp(r_i-r_j)+max_dist] and the angular
@@ -252,9 +254,14 @@ int dab_rbf_bwd(const void* grad_bf16, const float* distmat, const int64_t* seq_
 int dab_pair_base_fwd(const int64_t* seq_masked, const int64_t* residue_idx, const int64_t* chain_idx,
                       const float* pairwise_dihedrals, const void* t_type_bf16, const void* t_rel_bf16, int B, int L,
                       int max_dist, void* base_bf16, void* xh_bf16, void* stream);
+size_t dab_pair_table_grad_workspace_bytes(int B, int L, int max_dist);
 int dab_pair_table_grad(const void* g1_bf16, const int64_t* seq_masked, const int64_t* residue_idx, const int64_t* chain_idx,
-                        int B, int L, int max_dist, float* s_type, float* s_rel, void* stream);
+                        int B, int L, int max_dist, float* s_type, float* s_rel, void* workspace, size_t workspace_bytes,
+                        void* stream);
 int dab_pair_zero_masked(void* x_bf16, const uint8_t* res_mask, int B, int L, void* stream);
+/* ReLU backward of a 64-channel bf16 layer fused with its bias gradient: g_out = g_in where y > 0 else 0 (may alias g_in),
+ * colsum[64] += column sums of g_out. */
+int dab_relu_bwd_colsum(const void* g_in_bf16, const void* y_bf16, int64_t n, void* g_out_bf16, float* colsum, void* stream);
 
 /* Test hooks of the sm_100a path (used by tests/ only): the tcgen05 GEMM C[M,N] = A[M,K] B[N,K]^T + bias
  * (bf16 in, fp32 out; M % 128 == 0, N % 64 == 0, K % 64 == 0) and the operand-packing stage alone. */
