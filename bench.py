@@ -287,25 +287,32 @@ def main():
     if args.reverse_steps != T:
         line["profile_only"] = True
 
-    if rank == 0 and not args.skip_extras:
+    if not args.skip_extras:
         # ---- roofline of the dominant kernel (IPA attention core), measured live ---------------
-        line["roofline"] = measure_roofline(model, layer0, res_ctx, pair_ctx, x0, O0, precision, hbm_peak, peak_src)
-        # ---- e2e through DiffAb.sample() from pinned host memory -------------------------------
+        if rank == 0:
+            line["roofline"] = measure_roofline(model, layer0, res_ctx, pair_ctx, x0, O0, precision, hbm_peak, peak_src)
+        # ---- e2e through DiffAb.sample() from pinned host memory, every rank on its own patches -----------------
         # (the resident tensors of the kernel-path measurement are released first: sample() builds its own)
         del res_ctx, pair_ctx, s0, x0, O0, b
         torch.cuda.empty_cache()
         sample_e2e()
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         n_e2e = max(1, min(args.steps, 3))
         for _ in range(n_e2e):
             res = sample_e2e()
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / n_e2e
+        if dist is not None:
+            tmax = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            e2e_s = float(tmax)
         d2h_bytes = sum(v.numel() * v.element_size() for v in res.values())
-        line["e2e"] = {"value": B / e2e_s, "unit": "patches/s", "h2d_bytes_per_step": h2d_bytes,
-                       "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1000 * e2e_s, "n_gpus_measured": 1}
-
+        line["e2e"] = {"value": B * n_gpus / e2e_s, "unit": "patches/s", "h2d_bytes_per_step": h2d_bytes,
+                       "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1000 * e2e_s, "n_gpus_measured": n_gpus,
+                       "note": "host wall clock around DiffAb.sample() on pinned host inputs, max over ranks; bytes are "
+                               "per rank"}
+    if rank == 0 and not args.skip_extras:
         line["bf16_vs_fp32"] = measure_drift(model, dev)
         line["ipa_fwd_bwd"] = measure_ipa_fwd_bwd_bf16(dev)
         line["ipa_fwd_bwd"]["fp32_path"] = measure_ipa_fwd_bwd(dev)
