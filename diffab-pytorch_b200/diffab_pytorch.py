@@ -817,6 +817,38 @@ class OrientationLoss(nn.Module):
         return F.mse_loss(d, eye, reduction=self.reduction)
 
 
+class _FusedLosses(torch.autograd.Function):
+    """The three masked losses of ``_shared_step`` (:856-880) in one kernel each way: ``dab_losses_fwd`` /
+    ``dab_losses_bwd`` (gradients with respect to the three predictions only; targets are data)."""
+
+    @staticmethod
+    def forward(ctx, post_pred, post_tgt, eps_pred, eps_tgt, o_pred, o_true, mask):
+        f32 = torch.float32
+        tensors = [_lib.dev(t.detach(), f32, n) for t, n in ((post_pred, "seq_posterior"), (post_tgt, "seq_posterior target"),
+                                                             (eps_pred, "translations_eps"), (eps_tgt, "translations_eps target"),
+                                                             (o_pred, "orientations_t0"), (o_true, "orientations target"))]
+        m = _lib.mask_u8(mask, "loss mask")
+        n = m.numel()
+        if tensors[0].numel() != n * 21 or tensors[2].numel() != n * 3 or tensors[4].numel() != n * 9:
+            raise ValueError("fused losses: shapes must be (B, L, 21), (B, L, 3), (B, L, 3, 3) and a (B, L) mask")
+        acc = torch.zeros(8, device=m.device, dtype=f32)
+        out = torch.empty(4, device=m.device, dtype=f32)
+        _lib.check(_lib.lib().dab_losses_fwd(*(ptr(t) for t in tensors), ptr(m), n, ptr(acc), ptr(out), _lib.stream_ptr()),
+                   "dab_losses_fwd")
+        ctx.save_for_backward(*tensors, m, out)
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, g_seq, g_pos, g_rot):
+        *tensors, m, out = ctx.saved_tensors
+        zero = out.new_zeros(())
+        g = torch.stack([x.to(out.dtype) if x is not None else zero for x in (g_seq, g_pos, g_rot)]).contiguous()
+        d_post, d_eps, d_o = torch.empty_like(tensors[0]), torch.empty_like(tensors[2]), torch.empty_like(tensors[4])
+        _lib.check(_lib.lib().dab_losses_bwd(*(ptr(t) for t in tensors), ptr(m), m.numel(), ptr(g), ptr(out), ptr(d_post),
+                                             ptr(d_eps), ptr(d_o), _lib.stream_ptr()), "dab_losses_bwd")
+        return d_post, None, d_eps, None, d_o, None, None
+
+
 # =============================================================================================
 # DiffAb
 # =============================================================================================
@@ -909,7 +941,11 @@ class DiffAb(nn.Module):
                                           orientations_t0, generation_mask, t, noise)
 
     def _losses(self, denoised, noised, orientations_t0, generation_mask, residue_mask):
-        """diffab_pytorch.py:856-880."""
+        """diffab_pytorch.py:856-880.  On the GPU the three masked means are one fused kernel each way."""
+        if denoised["seq_posterior"].is_cuda and denoised["seq_posterior"].dtype == torch.float32:
+            return _FusedLosses.apply(denoised["seq_posterior"], noised["seq_posterior"], denoised["translations_eps"],
+                                      noised["translations_eps"], denoised["orientations_t0"], orientations_t0,
+                                      generation_mask & residue_mask)
         seq_loss = self.aa_loss(denoised["seq_posterior"].log(), noised["seq_posterior"])
         translations_loss = self.coordinate_loss(denoised["translations_eps"], noised["translations_eps"])
         orientations_loss = self.orientation_loss(denoised["orientations_t0"], orientations_t0)

@@ -263,6 +263,17 @@ int dab_pair_zero_masked(void* x_bf16, const uint8_t* res_mask, int B, int L, vo
  * colsum[64] += column sums of g_out. */
 int dab_relu_bwd_colsum(const void* g_in_bf16, const void* y_bf16, int64_t n, void* g_out_bf16, float* colsum, void* stream);
 
+/* The three masked training losses in one pass each way (DiffAb._shared_step, diffab_pytorch.py:856-880 with KLDivLoss / MSELoss /
+ * OrientationLoss :610-625, reduction "none", then masked mean; csrc/loss_kernels.cu).  n = B*L residues; post_*[n,21],
+ * eps_*[n,3], O_*[n,3,3] fp32, mask[n] uint8 = generation_mask & residue_mask.  Forward: acc = 8 zeroed floats of scratch,
+ * out[0..2] = sequence / translation / orientation loss, out[3] = number of masked residues.  Backward: g[3] = upstream
+ * gradients of the three losses, fwd_out = the forward's out; writes d_post[n,21], d_eps[n,3], d_O[n,3,3]. */
+int dab_losses_fwd(const float* post_pred, const float* post_tgt, const float* eps_pred, const float* eps_tgt, const float* O_pred,
+                   const float* O_true, const uint8_t* mask, int64_t n, float* acc, float* out, void* stream);
+int dab_losses_bwd(const float* post_pred, const float* post_tgt, const float* eps_pred, const float* eps_tgt, const float* O_pred,
+                   const float* O_true, const uint8_t* mask, int64_t n, const float* g, const float* fwd_out, float* d_post,
+                   float* d_eps, float* d_O, void* stream);
+
 /* Test hooks of the sm_100a path (used by tests/ only): the tcgen05 GEMM C[M,N] = A[M,K] B[N,K]^T + bias
  * (bf16 in, fp32 out; M % 128 == 0, N % 64 == 0, K % 64 == 0) and the operand-packing stage alone. */
 int dab_debug_set_timeline(long long* device_buf /* 64 slots per CTA of the attention core, or NULL */);

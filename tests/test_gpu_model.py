@@ -2,6 +2,7 @@
 oracle sampler (our composition), CUDA-graph replay vs eager."""
 import pytest
 import torch
+import torch.nn.functional as F
 
 from conftest import load_golden
 from diffab_pytorch_b200 import synth
@@ -218,6 +219,45 @@ def test_graphed_training_step_matches_eager_step():
     t.copy_(torch.full_like(t, 100))
     l2 = float(step())
     assert abs(l2 - lg) > 1e-3 * abs(lg)
+
+
+def test_fused_losses_match_the_module_losses():
+    """dab_losses_fwd / dab_losses_bwd against KLDivLoss / MSELoss / OrientationLoss + the masked mean of the reference
+    (diffab_pytorch.py:856-880): the three values and the gradients with respect to the three predictions, including
+    exact zeros in the target posterior and masked-out residues."""
+    from diffab_pytorch_b200.diffab_pytorch import _FusedLosses
+    model = _model(0)
+    gen = torch.Generator().manual_seed(17)
+    B, L = 3, 128
+    post = torch.softmax(torch.randn(B, L, 21, generator=gen), -1)
+    tgt = torch.softmax(4 * torch.randn(B, L, 21, generator=gen), -1)
+    tgt[:, ::3] = F.one_hot(torch.randint(0, 21, (B, (L + 2) // 3), generator=gen), 21).float()     # exact zeros: xlogy(0, 0) = 0
+    eps, eps_t = torch.randn(B, L, 3, generator=gen), torch.randn(B, L, 3, generator=gen)
+    o_pred = synth.uniform_rotations(B, L) + 0.05 * torch.randn(B, L, 3, 3, generator=gen)
+    o_true = synth.uniform_rotations(B, L)
+    gm = torch.zeros(B, L, dtype=torch.bool)
+    gm[:, 40:70] = True
+    rm = torch.ones(B, L, dtype=torch.bool)
+    rm[1, 50:60] = False
+    w = torch.tensor([0.7, 1.3, 2.1])
+    res = {}
+    for mode in ("module", "fused"):
+        p, e, o = (t.clone().to(DEV).requires_grad_(True) for t in (post, eps, o_pred))
+        if mode == "module":
+            seq = model.aa_loss(p.log(), tgt.to(DEV))
+            pos = model.coordinate_loss(e, eps_t.to(DEV))
+            rot = model.orientation_loss(o, o_true.to(DEV))
+            lm = (gm & rm).to(DEV)
+            den = lm.sum()
+            ls = ((seq * lm[..., None]).sum() / den, (pos * lm[..., None]).sum() / den, (rot * lm[..., None, None]).sum() / den)
+        else:
+            ls = _FusedLosses.apply(p, tgt.to(DEV), e, eps_t.to(DEV), o, o_true.to(DEV), (gm & rm).to(DEV))
+        sum(wi * li for wi, li in zip(w.to(DEV), ls)).backward()
+        res[mode] = (torch.stack([l.detach() for l in ls]).cpu(), p.grad.cpu(), e.grad.cpu(), o.grad.cpu())
+    assert torch.allclose(res["fused"][0], res["module"][0], rtol=1e-5)
+    for got, ref in zip(res["fused"][1:], res["module"][1:]):
+        assert _rel(got, ref) < 1e-5
+        assert torch.equal(got == 0, ref == 0)          # masked residues: exact zeros in both
 
 
 def test_regrouped_sampling_glue_matches_module_path():
