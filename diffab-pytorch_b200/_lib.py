@@ -102,6 +102,7 @@ EXPORTS = {
     "dab_pair_base_fwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dab_pair_table_grad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dab_pair_table_grad": (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dab_sum_bf16": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "dab_relu_bwd_colsum": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "dab_pair_zero_masked": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "dab_losses_fwd": (c_int, [c_void_p] * 7 + [c_int64, c_void_p, c_void_p, c_void_p]),

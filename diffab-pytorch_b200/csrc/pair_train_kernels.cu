@@ -333,6 +333,25 @@ __global__ void __launch_bounds__(256) pair_zero_masked_kernel(__nv_bfloat16* __
   if (!(__ldg(res_mask + row) && __ldg(res_mask + b * L + j))) reinterpret_cast<uint4*>(x)[idx] = make_uint4(0, 0, 0, 0);
 }
 
+// out = sum of up to 8 bf16 tensors, accumulated in fp32, one pass (the pair-tensor gradients of the IPA layers)
+struct SumPtrs { const uint4* p[8]; };
+__global__ void __launch_bounds__(256) sum_bf16_kernel(SumPtrs src, int n_src, int64_t n_chunks, uint4* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_chunks; idx += stride) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < n_src) {
+        float v[8];
+        pt_unpack8(__ldg(src.p[k] + idx), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += v[e];
+      }
+    }
+    out[idx] = make_uint4(pt_pk(acc[0], acc[1]), pt_pk(acc[2], acc[3]), pt_pk(acc[4], acc[5]), pt_pk(acc[6], acc[7]));
+  }
+}
+
 }  // namespace dab
 
 using namespace dab;
@@ -427,6 +446,28 @@ int dab_relu_bwd_colsum(const void* g_in_bf16, const void* y_bf16, int64_t n, vo
       reinterpret_cast<__nv_bfloat16*>(g_out_bf16), colsum);
   count_launch();
   return check_launch("dab_relu_bwd_colsum");
+}
+
+/* out_bf16[n] = sum of the n_src (1..8) bf16 tensors src[k][n], accumulated in fp32; n a multiple of 8, 16-byte aligned. */
+int dab_sum_bf16(const void* const* src, int n_src, int64_t n, void* out_bf16, void* stream) {
+  DAB_REQUIRE(src && out_bf16 && n_src >= 1 && n_src <= 8 && n >= 0 && n % 8 == 0, DAB_EINVAL,
+              "dab_sum_bf16: 1 <= n_src <= 8 tensors of n %% 8 == 0 elements required");
+  if (n == 0) return DAB_OK;
+  SumPtrs sp;
+  for (int k = 0; k < 8; ++k) {
+    sp.p[k] = reinterpret_cast<const uint4*>(src[k < n_src ? k : 0]);
+    DAB_REQUIRE(sp.p[k] && aligned16(sp.p[k]), DAB_EINVAL, "dab_sum_bf16: null or misaligned source %d", k);
+  }
+  DAB_REQUIRE(aligned16(out_bf16), DAB_EINVAL, "dab_sum_bf16: output must be 16-byte aligned");
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t n_chunks = n / 8;
+  int64_t grid = (n_chunks + 255) / 256;
+  if (grid > (int64_t)n_sm * 16) grid = (int64_t)n_sm * 16;
+  sum_bf16_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(sp, n_src, n_chunks, reinterpret_cast<uint4*>(out_bf16));
+  count_launch();
+  return check_launch("dab_sum_bf16");
 }
 
 /* x_bf16[B,L,L,64]: rows (b,i,j) with res_mask[b,i] == 0 or res_mask[b,j] == 0 are set to zero, in place. */

@@ -446,6 +446,31 @@ class _IpaFunction(torch.autograd.Function):
         return (None, None, dx, de, None, None, *grads)
 
 
+class _PairFanOut(torch.autograd.Function):
+    """The bf16 pair tensor handed to n layers as n aliases: the n gradients come back together and are summed in ONE
+    pass with fp32 accumulation (``dab_sum_bf16``) instead of autograd's n - 1 pairwise bf16 adds."""
+
+    @staticmethod
+    def forward(ctx, e, n):
+        return tuple(e.view_as(e) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        gs = [_lib.dev(g, torch.bfloat16, "pair gradient") for g in grads if g is not None]
+        if not gs:
+            return None, None
+        if len(gs) == 1:
+            return gs[0], None
+        out = torch.empty_like(gs[0])
+        total = None
+        for lo in range(0, len(gs), 7):       # up to 8 sources per launch (the running total is one of them)
+            part = ([total] if total is not None else []) + gs[lo:lo + 7]
+            ptrs = (ctypes.c_void_p * len(part))(*(t.data_ptr() for t in part))
+            _lib.check(_lib.lib().dab_sum_bf16(ptrs, len(part), out.numel(), ptr(out), _lib.stream_ptr()), "dab_sum_bf16")
+            total = out
+        return out, None
+
+
 class _IpaFastFunction(torch.autograd.Function):
     """bf16 tensor-core IPA layer with gradients: ``dab_ipa_fwd_sm100_train`` / ``dab_ipa_bwd_sm100``.
     The four plain GEMMs of the backward (through ``to_out`` and through the six projections) are library
@@ -648,11 +673,15 @@ class InvariantPointAttentionModule(nn.Module):
             # tensor-core path: the bias planes of all layers in one pass over the pair tensor (their gradient
             # w.r.t. to_pair_bias and the pair tensor is produced by the layers' own backward kernels)
             pair_bias = self.precompute_pair_bias(pair_emb.detach())
+        pairs = [pair_emb] * len(self.layers)
+        if (pair_emb.is_cuda and pair_emb.dtype == torch.bfloat16 and pair_emb.requires_grad and torch.is_grad_enabled()
+                and pair_emb.numel() % 8 == 0 and len(self.layers) > 1):
+            pairs = _PairFanOut.apply(pair_emb, len(self.layers))    # one fused sum of the layers' pair gradients
         for k, layer in enumerate(self.layers):
             if pair_bias is not None:
-                res_emb = layer(res_emb, pair_emb, orientations, translations, pair_bias[k])
+                res_emb = layer(res_emb, pairs[k], orientations, translations, pair_bias[k])
             else:
-                res_emb = layer(res_emb, pair_emb, orientations, translations)
+                res_emb = layer(res_emb, pairs[k], orientations, translations)
         return res_emb
 
     def precompute_pair_bias(self, pair_emb_bf16, out=None):

@@ -259,6 +259,9 @@ int dab_pair_table_grad(const void* g1_bf16, const int64_t* seq_masked, const in
                         int B, int L, int max_dist, float* s_type, float* s_rel, void* workspace, size_t workspace_bytes,
                         void* stream);
 int dab_pair_zero_masked(void* x_bf16, const uint8_t* res_mask, int B, int L, void* stream);
+/* out_bf16[n] = sum of n_src (1..8) bf16 tensors, fp32 accumulation, one pass: the pair-tensor gradients of the IPA layers
+ * (autograd would add them pairwise, five passes and five bf16 roundings for six layers). */
+int dab_sum_bf16(const void* const* src, int n_src, int64_t n, void* out_bf16, void* stream);
 /* ReLU backward of a 64-channel bf16 layer fused with its bias gradient: g_out = g_in where y > 0 else 0 (may alias g_in),
  * colsum[64] += column sums of g_out. */
 int dab_relu_bwd_colsum(const void* g_in_bf16, const void* y_bf16, int64_t n, void* g_out_bf16, float* colsum, void* stream);

@@ -181,6 +181,36 @@ def test_pair_bias_planes_single_pass_for_all_layers():
         assert torch.equal(layer.pair_bias(e), planes[k])
 
 
+def test_pair_gradient_of_the_layer_stack_is_one_fused_sum():
+    """InvariantPointAttentionModule hands the bf16 pair tensor to its layers through _PairFanOut: the layers' pair
+    gradients are summed in one fp32-accumulated pass (dab_sum_bf16).  Against the fp32 sum of the per-layer gradients
+    (captured with hooks) the result is within one bf16 rounding; autograd's pairwise bf16 adds are not."""
+    from diffab_pytorch_b200 import diffab_pytorch as dp
+    torch.manual_seed(1)
+    B = 2
+    mod = InvariantPointAttentionModule(3, 128, 64, 32, 8, 8, 8).to(DEV)
+    x, e, R, t = (v.to(DEV) for v in synth.make_ipa_inputs(B, 128, 128, 64, seed=5))
+    e = e.bfloat16().requires_grad_(True)
+    gy = torch.randn(B, 128, 128, device=DEV)
+    per_layer = []
+    orig = dp._PairFanOut.backward
+
+    def spy(ctx, *grads):
+        per_layer.extend(g.detach().float().clone() for g in grads)
+        return orig(ctx, *grads)
+
+    dp._PairFanOut.backward = staticmethod(spy)
+    try:
+        mod(x, e, R, t).backward(gy)
+    finally:
+        dp._PairFanOut.backward = staticmethod(orig)
+    assert len(per_layer) == 3
+    ref = sum(per_layer)
+    got = e.grad.float()
+    assert torch.equal(got, ref.bfloat16().float())                 # exactly the rounded fp32 sum
+    assert torch.isfinite(got).all()
+
+
 @pytest.mark.parametrize("B", [1, 3, 65])
 def test_tensor_core_training_pair_other_batch_sizes(B):
     """Batch sizes that exercise the small-batch launch variants (projection tiles split over 4 / 2 CTAs per patch,
