@@ -181,6 +181,33 @@ def test_pair_bias_planes_single_pass_for_all_layers():
         assert torch.equal(layer.pair_bias(e), planes[k])
 
 
+def test_tensor_core_layer_full_size_properties():
+    """Size-independent properties of the tensor-core IPA layer at the benchmark size (B = 256 patches, BASELINE config 3):
+    patches never mix (a sub-batch gives the same rows, a permuted batch permuted rows - other launch shapes, so only
+    within accumulation-order noise) and the layer is invariant under a global rigid motion of all frames."""
+    torch.manual_seed(0)
+    B = 256
+    layer = InvariantPointAttentionLayer(128, 64, 32, 8, 8, 8).to(DEV)
+    layer.load_state_dict(synth.synthetic_state(synth.ipa_layer_shapes(128, 64, 8, 32, 8, 8), seed=0))
+    x, e, R, t = (v.to(DEV) for v in synth.make_ipa_inputs(B, 128, 128, 64, seed=9))
+    e = e.bfloat16()
+    with torch.no_grad():
+        y = layer(x, e, R, t)
+        assert torch.isfinite(y).all()
+        assert torch.equal(y, layer(x, e, R, t))                                 # deterministic
+        sub = slice(100, 108)
+        ys = layer(x[sub], e[sub].contiguous(), R[sub], t[sub])
+        assert _rel(ys, y[sub].cpu()) < 1e-5                                      # patches are independent
+        perm = torch.randperm(B, device=DEV)
+        yp = layer(x[perm], e[perm].contiguous(), R[perm], t[perm])
+        assert torch.equal(yp, y[perm])                                           # same launch shape: same bits
+        # global rigid motion: frames (R, t) -> (R G, t G + s) (row-vector convention of the reference)
+        G = synth.uniform_rotations(1, 1, device=DEV)[0, 0]
+        shift = torch.tensor([3.0, -7.0, 11.0], device=DEV)
+        ym = layer(x, e, R @ G, t @ G + shift)
+        assert _rel(ym, y.cpu()) < 2e-2                                           # bf16 operands: tolerance of the path
+
+
 def test_pair_gradient_of_the_layer_stack_is_one_fused_sum():
     """InvariantPointAttentionModule hands the bf16 pair tensor to its layers through _PairFanOut: the layers' pair
     gradients are summed in one fp32-accumulated pass (dab_sum_bf16).  Against the fp32 sum of the per-layer gradients
