@@ -167,6 +167,8 @@ def ptr(t):
 def mask_u8(mask, name="mask"):
     if not mask.is_cuda:
         raise RuntimeError(f"{name}: expected a CUDA tensor - diffab_pytorch_b200 has no CPU path")
+    if mask.dtype == torch.bool:      # one byte per element, values 0 / 1: reinterpret, no kernel
+        return mask.contiguous().view(torch.uint8)
     return mask.to(torch.uint8).contiguous() if mask.dtype != torch.uint8 else mask.contiguous()
 
 

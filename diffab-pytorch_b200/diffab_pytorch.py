@@ -1051,12 +1051,29 @@ class DiffAb(nn.Module):
             "gauss": torch.randn(B, L, device=device, generator=g),
         }
 
+    @staticmethod
+    def draw_block_noise(n_steps, B, L, device, n_bins=8192):
+        """The draws of ``n_steps`` consecutive reverse steps in six launches (leading dimension = step); used by the
+        multi-step CUDA graph of ``sample``.  Same distributions as ``draw_step_noise``, another stream order."""
+        return {
+            "seq_exp": torch.empty(n_steps, B * L, 21, device=device).exponential_(),
+            "z": torch.randn(n_steps, B, L, 3, device=device),
+            "axis": torch.randn(n_steps, B, L, 3, device=device),
+            "hist_exp": torch.empty(n_steps, B, n_bins, device=device).exponential_(),
+            "jitter": torch.rand(n_steps, B, L, device=device),
+            "gauss": torch.randn(n_steps, B, L, device=device),
+        }
+
+    graph_block_steps = 20   # reverse steps per replay of the multi-step graph (static noise: ~12 MB per step at B = 256)
+
     @torch.no_grad()
     def reverse_step(self, seq_idx_t, translations_t, orientations_t, res_context_emb, pair_context_emb,
-                     generation_mask, t, noise, inplace=False, pair_bias=None, glue_cache=None):
+                     generation_mask, t, noise, inplace=False, pair_bias=None, glue_cache=None, beta=None):
         """One reverse-diffusion step: epsilon network + fused update kernel.  ``t`` is (B,) int64.
-        ``glue_cache`` (``Denoiser.sampling_cache``) switches the dense glue to its regrouped form."""
-        beta = self.dsched.tensors["beta"][t]
+        ``glue_cache`` (``Denoiser.sampling_cache``) switches the dense glue to its regrouped form; ``beta`` = the
+        schedule's beta at ``t`` when the caller has already gathered it."""
+        if beta is None:
+            beta = self.dsched.tensors["beta"][t]
         if glue_cache is not None:
             eps, v_eps, post = self.denoiser.heads_fast(seq_idx_t, translations_t, orientations_t, glue_cache,
                                                         pair_context_emb, beta, pair_bias)
@@ -1115,7 +1132,8 @@ class DiffAb(nn.Module):
             cache = {"key": key, "s": torch.empty_like(s), "x": torch.empty_like(x), "O": torch.empty_like(O),
                      "t": torch.full((B,), t_start, device=dev, dtype=torch.int64),
                      "res": torch.empty_like(res_ctx), "pair": torch.empty_like(pair_ctx),
-                     "mask": torch.empty_like(generation_mask), "bias": None, "graph": None, "glue": None}
+                     "mask": torch.empty_like(generation_mask), "bias": None, "graph": None, "glue": None,
+                     "graph_block": None}
         st = cache
         st["res"].copy_(res_ctx); st["pair"].copy_(pair_ctx); st["mask"].copy_(generation_mask)
         if pair_ctx.dtype == torch.bfloat16:   # per-layer pair-bias planes, written straight into the static buffers
@@ -1143,9 +1161,32 @@ class DiffAb(nn.Module):
                 st["t"].sub_(1)
             st["graph"] = graph
             self._graph_cache = st
+        # Long runs replay a second graph that holds `graph_block_steps` consecutive steps: their random draws are six
+        # launches per block instead of six per step (9 of the 32 launches of a step are PyTorch RNG / index kernels).
+        U = int(self.graph_block_steps)
+        n_steps = t_start - t_stop + 1
+        n_blocks = n_steps // U if U > 1 else 0
+        if n_blocks > 0 and (st["graph_block"] is None or st["graph_block"][0] != U):
+            block = torch.cuda.CUDAGraph()
+            st["s"].copy_(s); st["x"].copy_(x); st["O"].copy_(O)
+            st["t"].fill_(t_start)
+            # (a graph input: must live as long as the graph, so it is kept in the cache next to it)
+            st["steps_back"] = steps_back = torch.arange(U, device=dev, dtype=torch.int64)[:, None]
+            with torch.cuda.graph(block):
+                noises = self.draw_block_noise(U, B, L, dev)
+                t_blk = st["t"][None, :] - steps_back                  # (U, B): the block's step indices ...
+                beta_blk = self.dsched.tensors["beta"][t_blk]          # ... and betas, one gather per block
+                for u in range(U):
+                    self.reverse_step(st["s"], st["x"], st["O"], st["res"], st["pair"], st["mask"], t_blk[u],
+                                      {k: v[u] for k, v in noises.items()}, inplace=True, pair_bias=st["bias"],
+                                      glue_cache=st["glue"], beta=beta_blk[u])
+                st["t"].sub_(U)
+            st["graph_block"] = (U, block)
         st["s"].copy_(s); st["x"].copy_(x); st["O"].copy_(O)
         st["t"].fill_(t_start)
-        for _ in range(t_start, t_stop - 1, -1):
+        for _ in range(n_blocks):
+            st["graph_block"][1].replay()
+        for _ in range(n_steps - n_blocks * U):
             st["graph"].replay()
         return {"seq_idx": st["s"].clone(), "translations": st["x"].clone(), "orientations": st["O"].clone()}
 

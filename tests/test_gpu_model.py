@@ -185,6 +185,14 @@ def test_full_size_sampling_properties():
     assert float((torch.linalg.det(O) - 1).abs().max()) < 1e-4
     for k in out:
         assert torch.equal(outs[1][k], out[k]), k
+    # a later call replays the cached graphs (single-step and 20-step block): everything they read must still be alive
+    junk = [torch.randn(1 << 20, device=DEV) for _ in range(8)]
+    del junk
+    torch.cuda.empty_cache()
+    again = {k: v.cpu() for k, v in model.sample(*args, precision="bf16").items()}
+    assert torch.equal(again["seq_idx"][~m], batch["seq_idx"][~m])
+    assert torch.equal(again["orientations"][~m], batch["orientations"][~m])
+    assert torch.isfinite(again["translations"]).all()
 
 
 def test_bf16_training_step_matches_fp32_path():
