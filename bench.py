@@ -82,6 +82,12 @@ def cpu_reverse_sample_rate(n_patches, n_timesteps, repeats, threads):
     return n_patches / (per_call * T / n_timesteps), per_call
 
 
+def workload_name(patches_per_gpu):
+    """The workload both arms are quoted on (BASELINE config 3)."""
+    return (f"full reverse sampling T={T} over {patches_per_gpu} synthetic 128-residue CDR-H3 patches per GPU "
+            "(BASELINE config 3), train.py model config, random-init weights")
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -100,8 +106,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * elapsed / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"reverse sampling T={T}, L={L}, train.py config (D=128,C=64,6 IPA layers,H=8)",
-                   "patches_per_gpu": args.patches},
+        "config": {"workload": workload_name(args.patches), "patches_per_gpu": args.patches, "L": L, "T": T,
+                   "precision": "fp32 (CPU)"},
         "cpu_baseline": {"value": value, "unit": "patches/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -274,8 +280,7 @@ def main():
         "warmup": n_warm, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32",
         "data": "synthetic",
-        "config": {"workload": f"full reverse sampling T={T} over {B} synthetic 128-residue CDR-H3 patches per GPU "
-                               "(BASELINE config 3), train.py model config, random-init weights",
+        "config": {"workload": workload_name(B),
                    "patches_per_gpu": B, "L": L, "T": T, "precision": precision,
                    "cuda_graph": not args.no_graph,
                    "l2": f"pair tensor {pair_ctx.numel() * pair_ctx.element_size() / 1e6:.0f} MB per GPU > 126 MB L2 "
