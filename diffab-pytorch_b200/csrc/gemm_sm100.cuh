@@ -8,6 +8,8 @@
 // N = BN, K = 16 per instruction, fp32 accumulator in TMEM); all four warps then read the accumulator with tcgen05.ld
 // (warp w owns TMEM lanes 32w..32w+31 = tile rows), add the bias and store.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "sm100_prims.cuh"
 
@@ -30,7 +32,8 @@ template <int BN>
 __global__ void __launch_bounds__(128) gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
                                                         const __grid_constant__ CUtensorMap map_b,
                                                         float* __restrict__ C, int64_t ldc,
-                                                        const float* __restrict__ bias, int K) {
+                                                        const float* __restrict__ bias, int K,
+                                                        __nv_bfloat16* __restrict__ C16 = nullptr) {
   static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "BN");
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled operands need 1024-byte aligned tiles
@@ -97,11 +100,26 @@ __global__ void __launch_bounds__(128) gemm_bf16_kernel(const __grid_constant__ 
   // epilogue: thread (warp, lane) owns tile row 32*warp + lane
   const int row = m0 + warp * 32 + lane;
   float* crow = C + (int64_t)row * ldc + n0;
+  __nv_bfloat16* crow16 = C16 ? C16 + (int64_t)row * ldc + n0 : nullptr;
 #pragma unroll
   for (int c0 = 0; c0 < BN; c0 += 16) {
     float v[16];
     tmem_ld_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
     tmem_wait_ld();
+    if (crow16) {      // bf16 output (round-to-nearest-even, what the consumer's own fp32 -> bf16 conversion would give)
+      float o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = v[i] + (bias ? __ldg(bias + n0 + c0 + i) : 0.f);
+      uint4* dst = reinterpret_cast<uint4*>(crow16 + c0);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(o[8 * h], o[8 * h + 1]), p1 = __floats2bfloat162_rn(o[8 * h + 2], o[8 * h + 3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(o[8 * h + 4], o[8 * h + 5]), p3 = __floats2bfloat162_rn(o[8 * h + 6], o[8 * h + 7]);
+        dst[h] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                            *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+      }
+      continue;
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float4 o;
@@ -117,11 +135,12 @@ __global__ void __launch_bounds__(128) gemm_bf16_kernel(const __grid_constant__ 
   if (warp == 0) tmem_free(tmem_base, kTmemCols);
 }
 
-// Host launcher.  A: [M, K] bf16 row-major (lda elements), B: [N, K] bf16 row-major (ldb), M % 128 == 0,
+// Host launcher.  A: [M, K] bf16 row-major (lda elements), B: [N, K] bf16 row-major (ldb), C fp32 - or, when C_bf16 is
+// given, bf16 with the same leading dimension -, M % 128 == 0,
 // N % BN == 0, K % 64 == 0.
 template <int BN>
 int launch_gemm_bf16(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* C, int64_t ldc, const float* bias,
-                     int M, int N, int K, cudaStream_t stream) {
+                     int M, int N, int K, cudaStream_t stream, void* C_bf16 = nullptr) {
   DAB_REQUIRE(M % kGemmBM == 0 && N % BN == 0 && K % kGemmBK == 0 && K > 0, DAB_EUNSUPPORTED,
               "gemm_bf16: M %% 128, N %% %d, K %% 64 required (M=%d N=%d K=%d)", BN, M, N, K);
   CUtensorMap ma, mb;
@@ -132,7 +151,8 @@ int launch_gemm_bf16(const void* A, int64_t lda, const void* Bm, int64_t ldb, fl
   if (int rc = make_tensor_map_bf16(&mb, Bm, 2, dims_b, str_b, box_b, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   DAB_ENSURE_SMEM(gemm_bf16_kernel<BN>, GemmSmem<BN>::kTotal);
   dim3 grid(N / BN, M / kGemmBM);
-  gemm_bf16_kernel<BN><<<grid, 128, GemmSmem<BN>::kTotal, stream>>>(ma, mb, C, ldc, bias, K);
+  gemm_bf16_kernel<BN><<<grid, 128, GemmSmem<BN>::kTotal, stream>>>(ma, mb, C, ldc, bias, K,
+                                                                     reinterpret_cast<__nv_bfloat16*>(C_bf16));
   count_launch();
   return check_launch("gemm_bf16");
 }

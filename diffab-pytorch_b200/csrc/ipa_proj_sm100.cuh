@@ -52,7 +52,8 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
                 const __grid_constant__ CUtensorMap map_sq, const __grid_constant__ CUtensorMap map_sk,
                 const __grid_constant__ CUtensorMap map_sv, const float* __restrict__ x, const float* __restrict__ R, const float* __restrict__ t,
                 const float* __restrict__ gamma, __nv_bfloat16* __restrict__ Qp, __nv_bfloat16* __restrict__ Kp,
-                __nv_bfloat16* __restrict__ Vp, float* __restrict__ tc, long long* __restrict__ dbg) {
+                __nv_bfloat16* __restrict__ Vp, float* __restrict__ tc, long long* __restrict__ dbg,
+                const __nv_bfloat16* __restrict__ x16) {
   long long* dbg_cta = dbg ? dbg + (size_t)blockIdx.y * 64 : nullptr;   // (split 0 of) one patch per record
 #define PROJ_STAMP(k) do { if (dbg_cta && threadIdx.x == 0) dbg_cta[(k)] = clock64(); } while (0)
   PROJ_STAMP(0);
@@ -78,14 +79,24 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
 
   if (warp < 8) {
     // ---- x tile: fp32 global (coalesced float4) -> bf16, K-major 128B-swizzled A operand (16 rows per warp)
-    const float* xb = x + (int64_t)b * L * D;
     const uint32_t kb = lane >> 4, chunk = (lane & 15) >> 1, half = (lane & 1) * 8;
+    if (x16 != nullptr) {   // the previous layer's to_out GEMM already rounded its output to bf16: straight copy
+      const __nv_bfloat16* xb = x16 + (int64_t)b * L * D;
 #pragma unroll
-    for (int rr = 0; rr < 16; ++rr) {   // all 16 loads of the warp in flight before the first conversion
-      const int r = warp * 16 + rr;
-      float4 v = __ldg(reinterpret_cast<const float4*>(xb + r * D) + lane);
-      uint2 o = make_uint2(pk_bf(v.x, v.y), pk_bf(v.z, v.w));
-      *reinterpret_cast<uint2*>(smem + S::kA + kb * 16384 + swz128_offset(r, chunk) + half) = o;
+      for (int rr = 0; rr < 16; ++rr) {
+        const int r = warp * 16 + rr;
+        const uint2 o = __ldg(reinterpret_cast<const uint2*>(xb + r * D) + lane);
+        *reinterpret_cast<uint2*>(smem + S::kA + kb * 16384 + swz128_offset(r, chunk) + half) = o;
+      }
+    } else {
+      const float* xb = x + (int64_t)b * L * D;
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) {   // all 16 loads of the warp in flight before the first conversion
+        const int r = warp * 16 + rr;
+        float4 v = __ldg(reinterpret_cast<const float4*>(xb + r * D) + lane);
+        uint2 o = make_uint2(pk_bf(v.x, v.y), pk_bf(v.z, v.w));
+        *reinterpret_cast<uint2*>(smem + S::kA + kb * 16384 + swz128_offset(r, chunk) + half) = o;
+      }
     }
     // ---- patch centroid of the translations (see ipa_sm100.cu: keeps the expanded distance well conditioned)
     if (warp < 4) {

@@ -951,15 +951,19 @@ int dab_ipa_pair_bias_multi(const DabIpaDims* d, const void* e_bf16, const float
   return check_launch("dab_ipa_pair_bias_multi");
 }
 
+// x / y: fp32, or (x_bf16 / y_bf16 non-null) bf16 - the residue stream handed from layer to layer already rounded
 static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
                           const void* bias_f16, const float* R, const float* t, float* y, void* workspace,
-                          size_t workspace_bytes, bool save_for_bwd, void* stream) {
+                          size_t workspace_bytes, bool save_for_bwd, void* stream, const void* x_bf16 = nullptr,
+                          void* y_bf16 = nullptr) {
   DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
               "dab_ipa_fwd_sm100: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
   if (d->B == 0) return DAB_OK;
-  DAB_REQUIRE(packed && x && e_bf16 && R && t && y && workspace, DAB_EINVAL, "dab_ipa_fwd_sm100: null pointer");
+  DAB_REQUIRE(packed && (x || x_bf16) && e_bf16 && R && t && (y || y_bf16) && workspace, DAB_EINVAL,
+              "dab_ipa_fwd_sm100: null pointer");
   DAB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0 && (reinterpret_cast<uintptr_t>(packed) & 1023) == 0 &&
-                  (reinterpret_cast<uintptr_t>(e_bf16) & 127) == 0 && aligned16(x) && aligned16(y),
+                  (reinterpret_cast<uintptr_t>(e_bf16) & 127) == 0 && aligned16(x) && aligned16(y) && aligned16(x_bf16) &&
+                  aligned16(y_bf16),
               DAB_EINVAL, "dab_ipa_fwd_sm100: misaligned pointer (workspace/packed 1024 B, e 128 B, x/y 16 B)");
   const int B = d->B, M = B * L;
   Ws ws = carve_ws(B, workspace);
@@ -986,7 +990,8 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
     }
     const int n_split = B >= 128 ? 1 : (B >= 64 ? 2 : 4);   // small batches: several CTAs per patch
     ipa_proj_kernel<<<dim3(n_split, B), 288, ProjSmem::kTotal, s>>>(mw64, mw48, msq, msk, msv, x, R, t, reinterpret_cast<const float*>(pk + po.gamma),
-                                                     ws.Qp, ws.Kp, ws.Vp, ws.tc, g_core_dbg ? g_core_dbg + (1 << 20) : nullptr);
+                                                     ws.Qp, ws.Kp, ws.Vp, ws.tc, g_core_dbg ? g_core_dbg + (1 << 20) : nullptr,
+                                                     reinterpret_cast<const __nv_bfloat16*>(x_bf16));
     count_launch();
   }
   if (phases & 2) {
@@ -1024,8 +1029,8 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
   if (phases & 4) {
     // y = cat Wout^T + b: one 128-wide N tile per CTA when the batch fills the GPU, four 32-wide ones otherwise
     const float* bo = reinterpret_cast<const float*>(pk + po.bout);
-    if (int rc = (M / kGemmBM >= 148) ? launch_gemm_bf16<128>(ws.cat, NCAT, pk + po.wout, NCAT, y, D, bo, M, D, NCAT, s)
-                                      : launch_gemm_bf16<32>(ws.cat, NCAT, pk + po.wout, NCAT, y, D, bo, M, D, NCAT, s))
+    if (int rc = (M / kGemmBM >= 148) ? launch_gemm_bf16<128>(ws.cat, NCAT, pk + po.wout, NCAT, y, D, bo, M, D, NCAT, s, y_bf16)
+                                      : launch_gemm_bf16<32>(ws.cat, NCAT, pk + po.wout, NCAT, y, D, bo, M, D, NCAT, s, y_bf16))
       return rc;
   }
   return check_launch("dab_ipa_fwd_sm100");
@@ -1035,6 +1040,17 @@ int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, c
                       const void* bias_f16, const float* R, const float* t, float* y, void* workspace,
                       size_t workspace_bytes, void* stream) {
   return fwd_sm100_impl(d, packed, x, e_bf16, bias_f16, R, t, y, workspace, workspace_bytes, false, stream);
+}
+
+/* Same layer with the residue stream in bf16 on either side: exactly one of x / x_bf16 and one of y / y_bf16 is given.
+ * Between the layers of a stack the stream is consumed as bf16 anyway (the projections' A operand), so handing it over
+ * already rounded changes no bit of the result and halves its HBM traffic. */
+int dab_ipa_fwd_sm100_io(const DabIpaDims* d, const void* packed, const float* x, const void* x_bf16, const void* e_bf16,
+                         const void* bias_f16, const float* R, const float* t, float* y, void* y_bf16, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  DAB_REQUIRE((x == nullptr) != (x_bf16 == nullptr) && (y == nullptr) != (y_bf16 == nullptr), DAB_EINVAL,
+              "dab_ipa_fwd_sm100_io: give exactly one of x / x_bf16 and one of y / y_bf16");
+  return fwd_sm100_impl(d, packed, x, e_bf16, bias_f16, R, t, y, workspace, workspace_bytes, false, stream, x_bf16, y_bf16);
 }
 
 /* Training forward: same launches; the workspace additionally keeps what dab_ipa_bwd_sm100 needs (packed operands,

@@ -656,6 +656,31 @@ class InvariantPointAttentionLayer(nn.Module):
                                          ptr(y), ptr(ws), ws.numel(), _lib.stream_ptr()), "dab_ipa_fwd_sm100")
         return y
 
+    @torch.no_grad()
+    def forward_fast_io(self, x, e_bf16, r, t, pair_bias, out_dtype):
+        """Inference on the sm_100a path with the residue stream in fp32 or bf16 on either side (``x.dtype`` /
+        ``out_dtype``): the layers of a stack hand it over already rounded to bf16 - what the next layer's projections
+        consume anyway, so no bit of the result changes - via ``dab_ipa_fwd_sm100_io``."""
+        B, L, D = x.shape
+        if not self.fast_path_supported(L):
+            raise RuntimeError("the sm_100a fast path only supports the train.py configuration")
+        x = _lib.dev(x, x.dtype if x.dtype == torch.bfloat16 else torch.float32, "x")
+        e = _lib.dev(e_bf16, torch.bfloat16, "e")
+        r = _lib.dev(r, torch.float32, "r")
+        t = _lib.dev(t, torch.float32, "t")
+        bias = None if pair_bias is None else _lib.dev(pair_bias, torch.float16, "pair_bias")
+        dims = _ipa_structs(self, B, L)
+        lib = _lib.lib()
+        packed = self._packed_weights(dims)
+        ws = self._workspace(max(lib.dab_ipa_sm100_workspace_bytes(ctypes.byref(dims)), 16), x.device)
+        y = torch.empty(B, L, D, device=x.device, dtype=out_dtype)
+        x32, x16 = (None, x) if x.dtype == torch.bfloat16 else (x, None)
+        y32, y16 = (None, y) if out_dtype == torch.bfloat16 else (y, None)
+        _lib.check(lib.dab_ipa_fwd_sm100_io(ctypes.byref(dims), ptr(packed), ptr(x32), ptr(x16), ptr(e), ptr(bias), ptr(r),
+                                            ptr(t), ptr(y32), ptr(y16), ptr(ws), ws.numel(), _lib.stream_ptr()),
+                   "dab_ipa_fwd_sm100_io")
+        return y
+
 
 class InvariantPointAttentionModule(nn.Module):
     """diffab_pytorch.py:468-498: plain chain, same (pair_emb, R, t) for every layer."""
@@ -673,6 +698,16 @@ class InvariantPointAttentionModule(nn.Module):
             # tensor-core path: the bias planes of all layers in one pass over the pair tensor (their gradient
             # w.r.t. to_pair_bias and the pair tensor is produced by the layers' own backward kernels)
             pair_bias = self.precompute_pair_bias(pair_emb.detach())
+        needs_grad = torch.is_grad_enabled() and (res_emb.requires_grad or pair_emb.requires_grad or
+                                                  any(p.requires_grad for p in self.parameters()))
+        if (not needs_grad and pair_bias is not None and pair_emb.dtype == torch.bfloat16 and len(self.layers) > 1 and
+                self.layers[0].fast_path_supported(pair_emb.shape[1])):
+            # inference on the tensor-core path: the residue stream travels between the layers as bf16
+            n = len(self.layers)
+            for k, layer in enumerate(self.layers):
+                res_emb = layer.forward_fast_io(res_emb, pair_emb, orientations, translations, pair_bias[k],
+                                                torch.float32 if k == n - 1 else torch.bfloat16)
+            return res_emb
         pairs = [pair_emb] * len(self.layers)
         if (pair_emb.is_cuda and pair_emb.dtype == torch.bfloat16 and pair_emb.requires_grad and torch.is_grad_enabled()
                 and pair_emb.numel() % 8 == 0 and len(self.layers) > 1):

@@ -171,6 +171,12 @@ int dab_ipa_pair_bias_multi(const DabIpaDims* d, const void* e_bf16, const float
 int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
                       const void* bias_f16, const float* R, const float* t, float* y, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* dab_ipa_fwd_sm100 with the residue stream in bf16 on either side (exactly one of x / x_bf16 and one of y / y_bf16 non-NULL):
+ * used between the layers of InvariantPointAttentionModule (diffab_pytorch.py:494-498), where the next layer's projections
+ * consume x as bf16 anyway - same bits, half the traffic. */
+int dab_ipa_fwd_sm100_io(const DabIpaDims* d, const void* packed, const float* x, const void* x_bf16, const void* e_bf16,
+                         const void* bias_f16, const float* R, const float* t, float* y, void* y_bf16, void* workspace,
+                         size_t workspace_bytes, void* stream);
 /* Training pair of the sm_100a path (bf16 pair tensor, fp32 x / y).  The forward is dab_ipa_fwd_sm100 (the pair
  * bias is rebuilt inside the call when bias_f16 is NULL); `saved` (dab_ipa_sm100_workspace_bytes) additionally keeps
  * the packed operands, the concat features, the un-normalised probabilities and the softmax statistics, and must

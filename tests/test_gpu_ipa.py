@@ -208,6 +208,27 @@ def test_tensor_core_layer_full_size_properties():
         assert _rel(ym, y.cpu()) < 2e-2                                           # bf16 operands: tolerance of the path
 
 
+def test_layer_stack_bf16_handoff_changes_no_bit():
+    """Inference through InvariantPointAttentionModule hands the residue stream from layer to layer as bf16
+    (dab_ipa_fwd_sm100_io: the to_out GEMM rounds, the next projections copy); the projections round their fp32 input
+    the same way, so the result must equal the layer-by-layer fp32 hand-off bit for bit."""
+    torch.manual_seed(2)
+    B = 4
+    mod = InvariantPointAttentionModule(4, 128, 64, 32, 8, 8, 8).to(DEV)
+    for layer in mod.layers:
+        layer.load_state_dict(synth.synthetic_state(synth.ipa_layer_shapes(128, 64, 8, 32, 8, 8), seed=3))
+    x, e, R, t = (v.to(DEV) for v in synth.make_ipa_inputs(B, 128, 128, 64, seed=6))
+    e = e.bfloat16()
+    with torch.no_grad():
+        y = mod(x, e, R, t)                          # bf16 hand-off (planes precomputed inside)
+        planes = mod.precompute_pair_bias(e)
+        ref = x
+        for k, layer in enumerate(mod.layers):       # fp32 hand-off, one public layer call at a time
+            ref = layer(ref, e, R, t, planes[k])
+    assert y.dtype == torch.float32 and torch.isfinite(y).all()
+    assert torch.equal(y, ref)
+
+
 def test_pair_gradient_of_the_layer_stack_is_one_fused_sum():
     """InvariantPointAttentionModule hands the bf16 pair tensor to its layers through _PairFanOut: the layers' pair
     gradients are summed in one fp32-accumulated pass (dab_sum_bf16).  Against the fp32 sum of the per-layer gradients
