@@ -91,7 +91,7 @@ EXPORTS = {
     "dab_heads_pack_weights": (c_int, [POINTER(DabHeadWeights), c_void_p, c_void_p]),
     "dab_heads_fwd_sm100": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dab_front_fwd_sm100": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
-                                    c_void_p]),
+                                    c_void_p, c_void_p]),
     "dab_pair_embed_packed_bytes": (c_size_t, []),
     "dab_pair_embed_pack_weights": (c_int, [POINTER(DabPairEmbedWeights), c_void_p, c_void_p]),
     "dab_pair_embed_fwd_sm100": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -320,20 +320,22 @@ int dab_heads_fwd_sm100(const void* packed, const float* x, const float* beta, i
 }
 
 /* x0[n_rows,128] = relu(c[row] + t1[seq[row]]) . w2^T + b2  (to_res_emb during sampling; n_rows % 128 == 0).
- * w2_bf16: to_res_emb.2.weight as bf16 [128][128]; a_scratch: n_rows * 128 bf16. */
+ * w2_bf16: to_res_emb.2.weight as bf16 [128][128]; a_scratch: n_rows * 128 bf16.  Exactly one of x0 (fp32) and x0_bf16
+ * (rounded to bf16: the form the first IPA layer's projections consume) is given. */
 int dab_front_fwd_sm100(const float* c, const float* t1, const int64_t* seq, int64_t n_rows, const void* w2_bf16,
-                        const float* b2, void* a_scratch, float* x0, void* stream) {
+                        const float* b2, void* a_scratch, float* x0, void* x0_bf16, void* stream) {
   DAB_REQUIRE(n_rows >= 0 && n_rows % 128 == 0, DAB_EUNSUPPORTED, "dab_front_fwd_sm100: n_rows must be a multiple of 128");
   if (n_rows == 0) return DAB_OK;
-  DAB_REQUIRE(c && t1 && seq && w2_bf16 && b2 && a_scratch && x0, DAB_EINVAL, "dab_front_fwd_sm100: null pointer");
-  DAB_REQUIRE(aligned16(c) && aligned16(t1) && aligned16(w2_bf16) && aligned16(a_scratch) && aligned16(x0), DAB_EINVAL,
-              "dab_front_fwd_sm100: pointers must be 16-byte aligned");
+  DAB_REQUIRE(c && t1 && seq && w2_bf16 && b2 && a_scratch && ((x0 == nullptr) != (x0_bf16 == nullptr)), DAB_EINVAL,
+              "dab_front_fwd_sm100: null pointer (exactly one of x0 / x0_bf16 must be given)");
+  DAB_REQUIRE(aligned16(c) && aligned16(t1) && aligned16(w2_bf16) && aligned16(a_scratch) && aligned16(x0) && aligned16(x0_bf16),
+              DAB_EINVAL, "dab_front_fwd_sm100: pointers must be 16-byte aligned");
   const int64_t n4 = n_rows * (HD / 4);
   front_act_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(c), reinterpret_cast<const float4*>(t1), seq, n_rows,
       reinterpret_cast<uint2*>(a_scratch));
   count_launch();
-  if (int rc = launch_gemm_bf16<128>(a_scratch, HD, w2_bf16, HD, x0, HD, b2, (int)n_rows, HD, HD, (cudaStream_t)stream))
+  if (int rc = launch_gemm_bf16<128>(a_scratch, HD, w2_bf16, HD, x0, HD, b2, (int)n_rows, HD, HD, (cudaStream_t)stream, x0_bf16))
     return rc;
   return check_launch("dab_front_fwd_sm100");
 }

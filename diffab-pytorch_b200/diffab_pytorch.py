@@ -829,10 +829,13 @@ class Denoiser(nn.Module):
         B, L = seq_idx_t.shape
         D = cache["c"].shape[-1]
         if cache.get("w2_bf16") is not None and pair_context_emb.dtype == torch.bfloat16 and (B * L) % 128 == 0:
-            h = torch.empty(B, L, D, device=seq_idx_t.device)
+            # bf16 out when the layer stack takes it (its first projection kernel rounds an fp32 input the same way)
+            h16 = pair_bias is not None and len(self.ipa.layers) > 1 and self.ipa.layers[0].fast_path_supported(L)
+            h = torch.empty(B, L, D, device=seq_idx_t.device, dtype=torch.bfloat16 if h16 else torch.float32)
             _lib.check(_lib.lib().dab_front_fwd_sm100(ptr(cache["c"]), ptr(cache["t1"]), ptr(seq_idx_t.contiguous()),
                                                       B * L, ptr(cache["w2_bf16"]), ptr(cache["b2"]),
-                                                      ptr(cache["a_scratch"]), ptr(h), _lib.stream_ptr()),
+                                                      ptr(cache["a_scratch"]), None if h16 else ptr(h),
+                                                      ptr(h) if h16 else None, _lib.stream_ptr()),
                        "dab_front_fwd_sm100")
         else:
             h = torch.relu_(cache["c"] + F.embedding(seq_idx_t, cache["t1"]))

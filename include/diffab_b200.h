@@ -219,9 +219,10 @@ int dab_heads_fwd_sm100(const void* packed, const float* x, const float* beta, i
 /* Front of the epsilon network during sampling (diffab_pytorch.py:572-574, to_res_emb on [res_ctx | emb(s_t)]):
  * x0[n_rows,128] = relu(c[row] + t1[seq[row]]) . w2^T + b2, where c = res_ctx . W1[:, :128]^T + b1 (per-run constant,
  * fp32 [n_rows,128]) and t1 = emb . W1[:, 128:]^T (fp32 [25,128]) are computed once per run by the caller;
- * w2_bf16 = to_res_emb.2.weight in bf16 [128][128]; a_scratch holds n_rows*128 bf16. */
+ * w2_bf16 = to_res_emb.2.weight in bf16 [128][128]; a_scratch holds n_rows*128 bf16.  Exactly one of x0 (fp32) and
+ * x0_bf16 (the same values rounded to bf16, the form dab_ipa_fwd_sm100_io takes) is non-NULL. */
 int dab_front_fwd_sm100(const float* c, const float* t1, const int64_t* seq, int64_t n_rows, const void* w2_bf16,
-                        const float* b2, void* a_scratch, float* x0, void* stream);
+                        const float* b2, void* a_scratch, float* x0, void* x0_bf16, void* stream);
 
 /* ------------------------------------------------------------------ pair context encoder
  * PairEmbedding.forward (diffab_pytorch.py:186-312) fused into one tcgen05 kernel that writes the pair tensor in bf16
