@@ -72,6 +72,7 @@ EXPORTS = {
                                 c_void_p, c_void_p, c_void_p, POINTER(DabIpaGrads), c_void_p, c_size_t, c_void_p]),
     "dab_ipa_packed_bytes": (c_size_t, [POINTER(DabIpaDims)]),
     "dab_ipa_pack_weights": (c_int, [POINTER(DabIpaDims), POINTER(DabIpaWeights), c_void_p, c_void_p]),
+    "dab_ipa_packed_layout": (c_int, [POINTER(DabIpaDims), POINTER(c_size_t)]),
     "dab_ipa_sm100_workspace_bytes": (c_size_t, [POINTER(DabIpaDims)]),
     "dab_ipa_pair_bias": (c_int, [POINTER(DabIpaDims), c_void_p, c_void_p, c_void_p, c_void_p]),
     "dab_ipa_pair_bias_multi": (c_int, [POINTER(DabIpaDims), c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

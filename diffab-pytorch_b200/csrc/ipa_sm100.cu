@@ -1042,6 +1042,18 @@ int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, c
   return fwd_sm100_impl(d, packed, x, e_bf16, bias_f16, R, t, y, workspace, workspace_bytes, false, stream);
 }
 
+/* Byte offsets inside the packed weights: offs[0..6] = Wcat bf16 [1344][128] (rows: to_q_scalar, to_k_scalar, to_v_scalar,
+ * to_q_point, to_k_point, to_v_point), Wout bf16 [128][1024], to_pair_bias fp32 [8][64], b_out fp32 [128], gamma fp32 [8],
+ * Wcat^T bf16 [128][1344], Wout^T bf16 [1024][128] - so that a caller's own GEMMs can reuse the bf16 copies. */
+int dab_ipa_packed_layout(const DabIpaDims* d, size_t* offs) {
+  DAB_REQUIRE(d && offs, DAB_EINVAL, "dab_ipa_packed_layout: null pointer");
+  DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED, "dab_ipa_packed_layout: the sm_100a fast path needs the train.py configuration");
+  const PackedOffsets po = packed_offsets();
+  offs[0] = po.wcat; offs[1] = po.wout; offs[2] = po.wpb; offs[3] = po.bout; offs[4] = po.gamma; offs[5] = po.wcat_t;
+  offs[6] = po.wout_t;
+  return DAB_OK;
+}
+
 /* Same layer with the residue stream in bf16 on either side: exactly one of x / x_bf16 and one of y / y_bf16 is given.
  * Between the layers of a stack the stream is consumed as bf16 anyway (the projections' A operand), so handing it over
  * already rounded changes no bit of the result and halves its HBM traffic. */

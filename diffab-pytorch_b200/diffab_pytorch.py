@@ -520,21 +520,27 @@ class _IpaFastFunction(torch.autograd.Function):
         # the four plain GEMMs of the backward: library GEMMs on bf16 operands with fp32 accumulation and output
         # (the forward ran the same products on bf16 operands)
         bf = torch.bfloat16
+        # bf16 copies of the weights as the forward used them (rows of Wcat: q/k/v scalars, q/k/v points)
+        poffs = (ctypes.c_size_t * 7)()
+        _lib.check(lib.dab_ipa_packed_layout(ctypes.byref(dims), poffs), "dab_ipa_packed_layout")
+        n_proj = sum(w.shape[0] for w in weights[:6])
+        w_cat_bf = packed[poffs[0]: poffs[0] + n_proj * D * 2].view(bf).view(n_proj, D)
+        w_out_bf = packed[poffs[1]: poffs[1] + D * ncat * 2].view(bf).view(D, ncat)
         dy_bf = dy2.to(bf)
-        dcat = torch.mm(dy_bf, w_out.to(bf), out_dtype=torch.float32)          # (M, 1024)
+        dcat = torch.mm(dy_bf, w_out_bf, out_dtype=torch.float32)              # (M, 1024)
         d_w_out = torch.mm(dy_bf.t(), cat, out_dtype=torch.float32)            # (D, 1024)
-        d_b_out = torch.mv(dy2.t(), torch.ones(M, device=dy2.device))
-        w_cat = torch.cat(weights[:6], dim=0)                    # (1344, D)
-        dproj = torch.empty(M, w_cat.shape[0], device=x.device, dtype=bf)
+        d_b_out = dy2.sum(0)
+        dproj = torch.empty(M, n_proj, device=x.device, dtype=bf)
         de = torch.empty_like(e)
-        d_wpb = torch.zeros_like(weights[6])
-        d_gamma = torch.zeros_like(weights[7])
+        zeros = torch.zeros(weights[6].numel() + weights[7].numel(), device=x.device, dtype=torch.float32)   # one fill
+        d_wpb = zeros[: weights[6].numel()].view_as(weights[6])
+        d_gamma = zeros[weights[6].numel():].view_as(weights[7])
         bws = _lib.aligned_empty(max(lib.dab_ipa_bwd_sm100_workspace_bytes(ctypes.byref(dims)), 16), x.device)
         _lib.check(lib.dab_ipa_bwd_sm100(ctypes.byref(dims), ptr(packed), ptr(e), ptr(r), ptr(dcat), ptr(saved),
                                          saved.numel(), ptr(dproj), ptr(de), ptr(d_wpb), ptr(d_gamma), ptr(bws),
                                          bws.numel(), _lib.stream_ptr()), "dab_ipa_bwd_sm100")
         layer._last_bwd_ws = bws   # kept for tools/debug_bwd.py (intermediate buffers of the last backward)
-        dx = torch.mm(dproj, w_cat.to(bf), out_dtype=torch.float32).view(B, L, D)
+        dx = torch.mm(dproj, w_cat_bf, out_dtype=torch.float32).view(B, L, D)
         d_w_cat = torch.mm(dproj.t(), x.view(M, D).to(bf), out_dtype=torch.float32)
         d_proj_w = torch.split(d_w_cat, [w.shape[0] for w in weights[:6]], dim=0)
         return (None, None, dx, de, None, None, *d_proj_w, d_wpb, d_gamma, d_w_out, d_b_out)

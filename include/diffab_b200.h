@@ -158,6 +158,10 @@ int dab_ipa_bwd_f32(const DabIpaDims* d, const DabIpaWeights* w, const float* x,
  * out, e_bf16[B,L,L,C] bf16. */
 size_t dab_ipa_packed_bytes(const DabIpaDims* d);
 int dab_ipa_pack_weights(const DabIpaDims* d, const DabIpaWeights* w, void* packed, void* stream);
+/* offs[0..6]: byte offsets of Wcat bf16 [1344][128] (rows in the order to_q_scalar, to_k_scalar, to_v_scalar, to_q_point,
+ * to_k_point, to_v_point), Wout bf16 [128][1024], to_pair_bias fp32, b_out fp32, gamma fp32, Wcat^T bf16, Wout^T bf16 inside
+ * `packed` - the caller's own backward GEMMs reuse the bf16 copies instead of casting the weights again. */
+int dab_ipa_packed_layout(const DabIpaDims* d, size_t* offs);
 size_t dab_ipa_sm100_workspace_bytes(const DabIpaDims* d);
 /* Pair bias of one layer, hoisted out of the sampling loop: bias_f16[B*L*L*8] (fp16, [b][i][j][h]) =
  * scale_total * log2(e) * e . w_pair_bias^T (to_pair_bias, diffab_pytorch.py:423,439).  The pair tensor is
