@@ -322,15 +322,19 @@ __global__ void __launch_bounds__(256) relu_bwd_colsum_kernel(const __nv_bfloat1
 }
 
 // x[b,i,j,:] = 0 wherever residue i or residue j is masked out (the reference's `* pair_mask`, :309-311, for 0/1 masks).
+// One thread per pair: with every residue valid (the usual case) the pass only reads the two mask bytes.
 __global__ void __launch_bounds__(256) pair_zero_masked_kernel(__nv_bfloat16* __restrict__ x, const uint8_t* __restrict__ res_mask,
-                                                               int64_t n_chunks, int L) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_chunks) return;
-  const int64_t pair = idx >> 3;
+                                                               int64_t n_pairs, int L) {
+  const int64_t pair = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= n_pairs) return;
   const int64_t row = pair / L;       // b * L + i
   const int64_t b = row / L;
   const int j = (int)(pair - row * L);
-  if (!(__ldg(res_mask + row) && __ldg(res_mask + b * L + j))) reinterpret_cast<uint4*>(x)[idx] = make_uint4(0, 0, 0, 0);
+  if (!(__ldg(res_mask + row) && __ldg(res_mask + b * L + j))) {
+    uint4* dst = reinterpret_cast<uint4*>(x) + pair * 8;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dst[q] = make_uint4(0, 0, 0, 0);
+  }
 }
 
 // out = sum of up to 8 bf16 tensors, accumulated in fp32, one pass (the pair-tensor gradients of the IPA layers)
@@ -476,9 +480,9 @@ int dab_pair_zero_masked(void* x_bf16, const uint8_t* res_mask, int B, int L, vo
   if ((int64_t)B * L == 0) return DAB_OK;
   DAB_REQUIRE(x_bf16 && res_mask, DAB_EINVAL, "dab_pair_zero_masked: null pointer");
   DAB_REQUIRE(aligned16(x_bf16), DAB_EINVAL, "dab_pair_zero_masked: x must be 16-byte aligned");
-  const int64_t n_chunks = (int64_t)B * L * L * 8;
-  pair_zero_masked_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<__nv_bfloat16*>(x_bf16), res_mask, n_chunks, L);
+  const int64_t n_pairs = (int64_t)B * L * L;
+  pair_zero_masked_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<__nv_bfloat16*>(x_bf16), res_mask, n_pairs, L);
   count_launch();
   return check_launch("dab_pair_zero_masked");
 }
