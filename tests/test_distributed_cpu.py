@@ -92,3 +92,13 @@ def test_single_process_paths_need_no_process_group():
     assert torch.isfinite(loss)
     assert model.weight.grad.data_ptr() == bucket.flat.data_ptr()
     assert dd.all_gather_samples({"a": x}, 4)["a"] is x
+
+
+def test_graphed_step_rejects_a_non_capturable_optimizer():
+    """GraphedTrainStep captures optimizer.step() in a CUDA graph: an optimizer built without capturable=True keeps
+    its step counters on the host and must be refused before anything is captured."""
+    model = torch.nn.Linear(3, 2)
+    bucket = dd.GradientBucket(model.parameters())
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    with pytest.raises(ValueError, match="capturable"):
+        dd.GraphedTrainStep(lambda: (model(torch.randn(4, 3)).pow(2).sum(), torch.tensor(4.0)), bucket, opt)
