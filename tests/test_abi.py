@@ -31,6 +31,15 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(_lib.lib().dab_last_error(), bytes)
 
 
+def test_integration_guide_names_every_entry_point():
+    """INTEGRATION.md is the binding surface a reference maintainer reads: every exported entry point (the debug hooks
+    as a family) must appear there next to the reference function it replaces."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in _declared_symbols() if not n.startswith("dab_debug") and n not in doc]
+    assert not missing, missing
+    assert "dab_debug_" in doc
+
+
 def test_workspace_queries_run_without_a_gpu():
     d = _lib.DabIpaDims(32, 128, 128, 64, 8, 32, 8, 8)
     fwd = _lib.lib().dab_ipa_f32_workspace_bytes(ctypes.byref(d), 0)
