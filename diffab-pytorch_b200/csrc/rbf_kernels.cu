@@ -53,7 +53,7 @@ __device__ __forceinline__ float rbf_ex2(float x) {
 // pass accumulates in a register, touching shared memory once per run - the inner loop is one global load (+ one store /
 // one more load) per element.
 // dynamic smem: [21][225] softplus * log2(e) rows of the current s_i; backward: + [21][225] gradient accumulators
-template <bool BWD>
+template <bool BWD, bool FULL>   // FULL: L is a multiple of the keys per iteration - no bounds checks in the inner loop
 __global__ void __launch_bounds__(256) rbf_kernel(const float* __restrict__ dist, const int64_t* __restrict__ seq,
                                                   const uint8_t* __restrict__ atom_mask, const float* __restrict__ sp_table,
                                                   const float* __restrict__ sig_table, const int* __restrict__ order,
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) rbf_kernel(const float* __restrict__ dist
     float c = 0.f, acc = 0.f;
     for (int j0 = 0; j0 < L; j0 += U) {
       unsigned kw[U];
-      if (j0 + U <= L) {
+      if (FULL || j0 + U <= L) {
 #pragma unroll
         for (int v = 0; v < U / 4; ++v) {
           const uint4 k4 = *reinterpret_cast<const uint4*>(s_key + j0 + 4 * v);
@@ -139,14 +139,14 @@ __global__ void __launch_bounds__(256) rbf_kernel(const float* __restrict__ dist
         float d[U], g[BWD ? U : 1];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const bool in = kw[u] != 0xffffffffu;
+          const bool in = FULL || kw[u] != 0xffffffffu;
           const int j = kw[u] & 511;
           d[u] = in ? __ldg(dp + j * RBF_K) : 0.f;
           if (BWD) g[u] = in ? __bfloat162float(gp[j * RBF_KP]) : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (kw[u] == 0xffffffffu) break;
+          if (!FULL && kw[u] == 0xffffffffu) break;
           const int t = (kw[u] >> 9) & 31;
           if (t != cur_t) {                         // uniform over the block: every thread walks the same keys
             if (BWD && cur_t >= 0) s_g[cur_t * RBF_K + tid] += acc;     // own column: no race
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) rbf_kernel(const float* __restrict__ dist
       } else if (!BWD && tid < RBF_KP) {
 #pragma unroll
         for (int u = 0; u < U; ++u)
-          if (kw[u] != 0xffffffffu) op[(kw[u] & 511) * RBF_KP] = __float2bfloat16_rn(0.f);
+          if (FULL || kw[u] != 0xffffffffu) op[(kw[u] & 511) * RBF_KP] = __float2bfloat16_rn(0.f);
       }
     }
     if (BWD && col && cur_t >= 0) s_g[cur_t * RBF_K + tid] += acc;
@@ -209,7 +209,8 @@ int dab_rbf_fwd(const float* distmat, const int64_t* seq_masked, const uint8_t* 
   rbf_softplus_kernel<<<(RBF_T + 255) / 256, 256, 0, (cudaStream_t)stream>>>(coef, sp, nullptr);
   count_launch();
   const int n_rows = B * L;
-  rbf_kernel<false><<<rbf_grid(n_rows, 8), 256, RBF_V * RBF_K * 4, (cudaStream_t)stream>>>(
+  // (the check-free variant of the forward kernel compiles to 32 registers with its loads serialised and is slower)
+  rbf_kernel<false, false><<<rbf_grid(n_rows, 8), 256, RBF_V * RBF_K * 4, (cudaStream_t)stream>>>(
       distmat, seq_masked, atom_mask, sp, nullptr, nullptr, n_rows, L, squared, reinterpret_cast<__nv_bfloat16*>(rbf_bf16),
       nullptr, nullptr);
   count_launch();
@@ -234,7 +235,8 @@ int dab_rbf_bwd(const void* grad_bf16, const float* distmat, const int64_t* seq_
   count_launch();
   rbf_sort_rows_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(seq_masked, n_rows, order);
   count_launch();
-  rbf_kernel<true><<<rbf_grid(n_rows, 4), 256, 2 * RBF_V * RBF_K * 4, (cudaStream_t)stream>>>(
+  auto kernel = L % 8 == 0 ? rbf_kernel<true, true> : rbf_kernel<true, false>;
+  kernel<<<rbf_grid(n_rows, 4), 256, 2 * RBF_V * RBF_K * 4, (cudaStream_t)stream>>>(
       distmat, seq_masked, atom_mask, sp, sig, order, n_rows, L, squared, nullptr,
       reinterpret_cast<const __nv_bfloat16*>(grad_bf16), d_coef);
   count_launch();
