@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(256) rbf_kernel(const float* __restrict__ dist
     __syncthreads();
     const unsigned mi = s_mask[row - b * L];
     const bool ai = col && ((mi >> a) & 1u);
+    const unsigned key_bit = ai ? 1u << (14 + ap) : 0u;       // this column's atom of key j present (and atom a of row i)
     const int c_col = col ? tid : 0;
     const float* dp = dist + row * L * RBF_K + c_col;
     const __nv_bfloat16* gp = BWD ? grad + row * L * RBF_KP + c_col : nullptr;
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(256) rbf_kernel(const float* __restrict__ dist
             c = s_sp[t * RBF_K + tid];
           }
           const float d2 = squared ? d[u] : d[u] * d[u];
-          const bool on = ai && ((kw[u] >> (14 + ap)) & 1u);
+          const bool on = (kw[u] & key_bit) != 0u;
           if (!BWD) {
             op[(kw[u] & 511) * RBF_KP] = __float2bfloat16_rn(on ? rbf_ex2(-c * d2) : 0.f);
           } else if (on) {
