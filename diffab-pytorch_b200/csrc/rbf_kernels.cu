@@ -53,6 +53,14 @@ __device__ __forceinline__ float rbf_ex2(float x) {
 // pass accumulates in a register, touching shared memory once per run - the inner loop is one global load (+ one store /
 // one more load) per element.
 // dynamic smem: [21][225] softplus * log2(e) rows of the current s_i; backward: + [21][225] gradient accumulators
+// Run switch of the backward pass (the keys are walked in residue-type order): flush the finished run's accumulator into
+// its shared-memory slot and fetch the next run's coefficient.  Deliberately not inlined: inlined, its five instructions
+// are predicated into every element of the loop; as a call they cost only at the ~21 run boundaries of a row.
+__device__ __noinline__ float rbf_switch_run(float* s_g_col, const float* s_sp_col, int cur_t, int t, float acc) {
+  if (cur_t >= 0) s_g_col[cur_t * RBF_K] += acc;
+  return s_sp_col[t * RBF_K];
+}
+
 template <bool BWD, bool FULL>   // FULL: L is a multiple of the keys per iteration - no bounds checks in the inner loop
 __global__ void __launch_bounds__(256) rbf_kernel(const float* __restrict__ dist, const int64_t* __restrict__ seq,
                                                   const uint8_t* __restrict__ atom_mask, const float* __restrict__ sp_table,
@@ -150,10 +158,13 @@ __global__ void __launch_bounds__(256) rbf_kernel(const float* __restrict__ dist
           if (!FULL && kw[u] == 0xffffffffu) break;
           const int t = (kw[u] >> 9) & 31;
           if (t != cur_t) {                         // uniform over the block: every thread walks the same keys
-            if (BWD && cur_t >= 0) s_g[cur_t * RBF_K + tid] += acc;     // own column: no race
+            if (BWD) {
+              c = rbf_switch_run(s_g + tid, s_sp + tid, cur_t, t, acc);   // own column: no race
+            } else {
+              c = s_sp[t * RBF_K + tid];
+            }
             acc = 0.f;
             cur_t = t;
-            c = s_sp[t * RBF_K + tid];
           }
           const float d2 = squared ? d[u] : d[u] * d[u];
           const bool on = (kw[u] & key_bit) != 0u;
