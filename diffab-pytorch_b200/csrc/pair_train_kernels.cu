@@ -93,9 +93,8 @@ __global__ void __launch_bounds__(256) pair_base_fwd_kernel(
           make_uint4(pt_pk(ty[0], ty[1]), pt_pk(ty[2], ty[3]), pt_pk(ty[4], ty[5]), pt_pk(ty[6], ty[7]));
     }
     // ---- angular encoding of the two pairwise dihedrals (:20-54): per angle [x, sin(f x) x4, cos(f x) x4], f = 1, 2, 1, 1/2;
-    //      4 lanes per pair, lane q writes 16 bytes of the 64-byte padded feature row
-    for (int idx = tid; idx < L * 4; idx += blockDim.x) {
-      const int j = idx >> 2, q = idx & 3;
+    //      one thread per pair writes the 64-byte padded feature row (18 features, zeros after)
+    for (int j = tid; j < L; j += blockDim.x) {
       const float2 d = __ldg(reinterpret_cast<const float2*>(dihedrals) + row * L + j);
       float f[24];
       const float ang[2] = {d.x, d.y};
@@ -112,13 +111,12 @@ __global__ void __launch_bounds__(256) pair_base_fwd_kernel(
       }
 #pragma unroll
       for (int k = 18; k < 24; ++k) f[k] = 0.f;
-      uint4 o = make_uint4(0, 0, 0, 0);
+      uint4* dst = reinterpret_cast<uint4*>(xh + (row * L + j) * PT_DIHP);
 #pragma unroll
-      for (int qq = 0; qq < 3; ++qq)
-        if (q == qq)
-          o = make_uint4(pt_pk(f[8 * qq], f[8 * qq + 1]), pt_pk(f[8 * qq + 2], f[8 * qq + 3]), pt_pk(f[8 * qq + 4], f[8 * qq + 5]),
-                         pt_pk(f[8 * qq + 6], f[8 * qq + 7]));
-      *(reinterpret_cast<uint4*>(xh + (row * L + j) * PT_DIHP) + q) = o;
+      for (int q = 0; q < 3; ++q)
+        dst[q] = make_uint4(pt_pk(f[8 * q], f[8 * q + 1]), pt_pk(f[8 * q + 2], f[8 * q + 3]), pt_pk(f[8 * q + 4], f[8 * q + 5]),
+                            pt_pk(f[8 * q + 6], f[8 * q + 7]));
+      dst[3] = make_uint4(0, 0, 0, 0);
     }
   }
 }
