@@ -779,6 +779,17 @@ class Denoiser(nn.Module):
         h = self.to_res_emb(h)
         h = self.ipa(h, pair_context_emb, orientations_t, translations_t, pair_bias)
         t_emb = torch.stack([beta, torch.sin(beta), torch.cos(beta)], dim=-1)
+        if h.is_cuda:
+            # [h | t_emb] @ W1^T = h @ W1[:, :D]^T + (t_emb @ W1[:, D:]^T): the three time columns are a per-patch bias,
+            # and the residue part is a K = 128 GEMM (K = 131 sends forward and both backward GEMMs to unaligned kernels)
+            D = h.shape[-1]
+            outs = []
+            for head in (self.coordinate_denoising, self.orientation_denoising, self.sequence_denoising):
+                w1, b1 = head[0].weight, head[0].bias
+                pb = torch.addmm(b1, t_emb, w1[:, D:].t())                                  # (B, D)
+                a = torch.relu(F.linear(h, w1[:, :D].contiguous()) + pb[:, None, :])
+                outs.append(head[2:](a))
+            return tuple(outs)
         h = torch.cat([h, t_emb[:, None, :].expand(-1, n_residues, -1)], dim=-1)
         return self.coordinate_denoising(h), self.orientation_denoising(h), self.sequence_denoising(h)
 
