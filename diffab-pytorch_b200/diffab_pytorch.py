@@ -529,7 +529,7 @@ class _IpaFastFunction(torch.autograd.Function):
         dy_bf = dy2.to(bf)
         dcat = torch.mm(dy_bf, w_out_bf, out_dtype=torch.float32)              # (M, 1024)
         d_w_out = torch.mm(dy_bf.t(), cat, out_dtype=torch.float32)            # (D, 1024)
-        d_b_out = dy2.sum(0)
+        d_b_out = torch.mv(dy2.t(), torch.ones(M, device=dy2.device))   # a 4 us gemv; a column reduction takes 13 us here
         dproj = torch.empty(M, n_proj, device=x.device, dtype=bf)
         de = torch.empty_like(e)
         zeros = torch.zeros(weights[6].numel() + weights[7].numel(), device=x.device, dtype=torch.float32)   # one fill
