@@ -2,7 +2,7 @@
 """Headline benchmark: reverse-diffusion patches/s (K=128 residues, T=100 steps) on N B200.
 
     python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels)
-    python bench.py --impl reference --steps K --warmup W    # CPU baseline arm (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the reference's own modules on the host cores
 
 One "step" = one full reverse-diffusion pass (T=100 denoise + update steps) over the rank's batch of
 synthetic 128-residue CDR-H3 patches (BASELINE config 3: 256 patches per GPU; weak scaling: every
@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-extras", action="store_true", help="skip e2e / roofline / cpu_baseline passes")
+    ap.add_argument("--full-pass", action="store_true",
+                    help="--impl reference only: every timed step runs all T reverse steps (minutes per step)")
     ap.add_argument("--reverse-steps", type=int, default=T,
                     help="PROFILING ONLY: run this many of the T reverse steps per pass (ncu launch lists); "
                          "the JSON line is then marked profile_only and is not a bench value")
@@ -49,37 +51,35 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline (oracle port of the reference's algorithm; the only place bench.py executes oracle/)
+# CPU arm (the only place bench.py executes oracle/): the UNMODIFIED reference from baseline/_ref when it is installed
+# (its encode_context + denoise, stock fp32 CPU path, all host threads; the reverse update itself is the oracle's because
+# the reference's sample() is a stub), else the oracle port.
 # ------------------------------------------------------------------------------------------------
-def cpu_reverse_sample_rate(n_patches, n_timesteps, repeats, threads):
-    """Times `n_timesteps` reverse steps of `n_patches` patches with the oracle on host cores and
-    returns (patches/s extrapolated to T=100, seconds per call)."""
-    from diffab_pytorch_b200 import synth
-    from oracle import diffusion as odiff
-    from oracle import sampler as osamp
+REF_PATCHES = int(os.environ.get("DIFFAB_REF_PATCHES", "32"))   # patches per bounded sample (threads saturate at ~32)
+REF_STEPS = (T, 5)    # reverse steps of a bounded sample: one on the Gaussian IGSO(3) branch, one on the histogram branch
 
-    torch.set_num_threads(threads)
+
+def cpu_sample(n_patches, steps, threads, seed=0, with_context=True):
+    """One bounded sample of the workload on the host: context encoding of `n_patches` synthetic patches + the reverse
+    steps `steps`; returns the runner's timing record with the T=100 rate it implies."""
+    from diffab_pytorch_b200 import synth
+    from oracle import reference_runner as rr
+
     shapes = torch.load(os.path.join(ROOT, "tests", "golden", "state_shapes.pt"), weights_only=False)
     state = synth.synthetic_state(shapes, seed=0)
-    sched = odiff.cosine_schedule(T, s=0.01, beta_max=0.999)
-    g = torch.Generator().manual_seed(0)
-    batch = synth.make_patches(n_patches, L, seed=0, with_distmat=False)
-    res_ctx = torch.randn(n_patches, L, 128, generator=g)
-    pair_ctx = torch.randn(n_patches, L, L, 64, generator=g)
-    s, x, O = osamp.draw_initial_state(batch["seq_idx"], batch["xyz"][:, :, 1], batch["orientations"],
-                                       batch["generation_mask"], generator=g)
-    # steps T..T-n+1 use sigma = sqrt(beta) >= 0.1 (gaussian branch): the histogram rows are not needed
-    hist_rev = torch.ones(T + 1, 8192)
-    noises = {t: osamp.draw_step_noise(n_patches, L, generator=g) for t in range(T, T - n_timesteps, -1)}
-    times = []
-    with torch.no_grad():
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            osamp.sample_loop(state, sched, hist_rev, s, x, O, res_ctx, pair_ctx, batch["generation_mask"], 6, 8,
-                              noises, t_start=T, t_stop=T - n_timesteps + 1)
-            times.append(time.perf_counter() - t0)
-    per_call = min(times)
-    return n_patches / (per_call * T / n_timesteps), per_call
+    batch = synth.make_patches(n_patches, L, seed=seed, with_distmat=False)
+    r = rr.timed_pass(state, batch, list(steps), threads, with_context=with_context, seed=seed)
+    r["patches_per_s"] = rr.patches_per_s(r, T)
+    return r
+
+
+def cpu_sample_text(r):
+    what = ("the UNMODIFIED reference (baseline/_ref: DiffAb.encode_context + DiffAb.denoise, stock fp32 CPU path) + the "
+            "oracle's reverse update (the reference's sample() is a stub)" if r["kind"] == "reference" else
+            "oracle port of the reference's PyTorch CPU path, fp32 (reference not installed); context encoders not run")
+    return (f"{r['n_patches']} patches: context encoding once ({r['t_context_s']:.2f} s) + {r['n_steps']} of {T} reverse steps "
+            f"({r['t_steps_s'] / max(r['n_steps'], 1):.2f} s each; one Gaussian-branch step, one histogram-branch step) on "
+            f"{r['threads']} threads; patches/s = patches / (t_context + {T} x t_step); {what}")
 
 
 def workload_name(patches_per_gpu):
@@ -88,27 +88,43 @@ def workload_name(patches_per_gpu):
             "(BASELINE config 3), train.py model config, random-init weights")
 
 
+def bench_config(patches_per_gpu, world):
+    """`config` of the JSON line: identical for both arms (the workload the metric is quoted on, and how each arm
+    samples it); arm-specific facts live under `arm`."""
+    return {"workload": workload_name(patches_per_gpu), "patches_per_gpu": patches_per_gpu, "L": L, "T": T,
+            "l2": f"pair tensor {patches_per_gpu * L * L * 64 * 2 / 1e6:.0f} MB per GPU (bf16) > 126 MB L2 "
+                  "(inputs larger than L2, no flush)",
+            "gather": "nccl all_gather of results inside the timed region" if world > 1 else "none",
+            "reference_arm_sample": f"--impl reference times a BOUNDED sample per step: {REF_PATCHES} patches, context "
+                                    f"encoding + reverse steps t={list(REF_STEPS)}, rate extrapolated to T={T} "
+                                    "(every reverse step costs the same on the CPU); --full-pass runs all T steps"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_patches, n_ts = 4, 2
-    for _ in range(args.warmup):
-        cpu_reverse_sample_rate(n_patches, n_ts, 1, threads)
+    steps = list(range(T, 0, -1)) if args.full_pass else list(REF_STEPS)
+    for _ in range(args.warmup if not args.full_pass else 0):
+        cpu_sample(REF_PATCHES, REF_STEPS, threads)
+    if args.warmup == 0 or args.full_pass:
+        cpu_sample(min(REF_PATCHES, 4), (T,), threads)      # model construction (IGSO(3) table) is not timed
     t0 = time.perf_counter()
-    rates = [cpu_reverse_sample_rate(n_patches, n_ts, 1, threads)[0] for _ in range(args.steps)]
+    recs = [cpu_sample(REF_PATCHES, steps, threads, seed=k) for k in range(args.steps)]
     elapsed = time.perf_counter() - t0
-    value = statistics.mean(rates)
-    sample = (f"{n_patches} patches x {n_ts} of {T} reverse steps per timed step (oracle port of the reference's "
-              f"PyTorch CPU path, fp32), extrapolated x{T // n_ts} to T={T}")
+    value = statistics.mean(r["patches_per_s"] for r in recs)
+    r = recs[-1]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * elapsed / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.patches), "patches_per_gpu": args.patches, "L": L, "T": T,
-                   "precision": "fp32 (CPU)"},
-        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": bench_config(args.patches, args.gpus),
+        "arm": {"impl": r["kind"], "reference_root": r["root"], "patches_run": r["n_patches"],
+                "reverse_steps_run": r["n_steps"], "context_encoding_in_timed_region": r["with_context"],
+                "full_pass": bool(args.full_pass), "precision": "fp32 (CPU)", "finite": r["finite"]},
+        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": threads, "kind": r["kind"],
+                         "sample": cpu_sample_text(r)},
         "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -179,10 +195,20 @@ def main():
         raise SystemExit("bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # ---- CPU baseline on this box's host cores: rank 0 alone, BEFORE the process group exists (the other ranks sit idle
+    # in the rendezvous instead of spinning in NCCL), on a bounded sample of the same workload ----
+    cpu_line = None
+    if rank == 0 and not args.skip_extras:
+        threads = os.cpu_count() or 1
+        cpu_sample(min(REF_PATCHES, 4), (T,), threads)          # model construction / first-touch, not timed
+        r = cpu_sample(REF_PATCHES, REF_STEPS, threads)
+        cpu_line = {"value": r["patches_per_s"], "unit": "patches/s", "cores": threads, "kind": r["kind"],
+                    "sample": cpu_sample_text(r)}
     dist = None
     if world > 1:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=20))
     n_gpus = world
     lib = _lib.lib()
     peaks = {}
@@ -280,12 +306,8 @@ def main():
         "warmup": n_warm, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(B),
-                   "patches_per_gpu": B, "L": L, "T": T, "precision": precision,
-                   "cuda_graph": not args.no_graph,
-                   "l2": f"pair tensor {pair_ctx.numel() * pair_ctx.element_size() / 1e6:.0f} MB per GPU > 126 MB L2 "
-                         "(inputs larger than L2, no flush)",
-                   "gather": "nccl all_gather of results inside the timed region" if dist is not None else "none"},
+        "config": bench_config(B, n_gpus),
+        "arm": {"impl": "b200", "precision": precision, "cuda_graph": not args.no_graph},
         "clocks": clock_info,
         "gpu_launches": int(launches_per_reverse_step) * args.reverse_steps * args.steps,
     }
@@ -322,14 +344,7 @@ def main():
         line["ipa_fwd_bwd"] = measure_ipa_fwd_bwd_bf16(dev)
         line["ipa_fwd_bwd"]["fp32_path"] = measure_ipa_fwd_bwd(dev)
 
-        # ---- CPU baseline on this box's host cores ----------------------------------------------
-        threads = os.cpu_count() or 1
-        rate, per_call = cpu_reverse_sample_rate(2, 2, 2, threads)
-        rate1, _ = cpu_reverse_sample_rate(1, 1, 1, 1)
-        line["cpu_baseline"] = {"value": rate, "unit": "patches/s", "cores": threads, "kind": "port",
-                                "single_thread_value": rate1,
-                                "sample": f"2 patches x 2 of {T} reverse steps (oracle port of the reference's PyTorch "
-                                          f"CPU path, fp32, {per_call:.2f} s per call), extrapolated x50 to T={T}"}
+        line["cpu_baseline"] = cpu_line
     if not args.skip_extras and args.reverse_steps == T:
         # ---- BASELINE config 5: training step, B=64 patches per GPU, all ranks (DDP all-reduce over NCCL) ------
         train = measure_train_step(dev, dist, world, shapes)

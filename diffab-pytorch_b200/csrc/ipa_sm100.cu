@@ -20,6 +20,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -215,47 +217,60 @@ __global__ void __launch_bounds__(128) ipa_pack_kernel(const float* __restrict__
 }
 
 // ---- attention core ---------------------------------------------------------------------------------
+// One persistent CTA per SM holds TWO tile contexts (tile = (patch, 16 query rows); local tile k of a CTA runs in
+// context k & 1).  A context is a complete tile pipeline - its own softmax / epilogue warps, MMA issuer, probability
+// buffers and 256 TMEM columns - but the operand rings are SHARED and dedicated (nothing aliases them):
+//   * K ring (2 x 24 KB): K of the patch head by head, tiles in local order;
+//   * e/V ring (6 x 16 KB): per tile its 16 pair rows, then the 8 value tiles of its patch.
+// Ring order = tile order, so the two contexts run in anti-phase: while one context streams its pair rows (softmax,
+// pair aggregation), the other runs its O^T MMAs, its epilogue and the S^T MMAs of its next tile from operands that
+// were loaded in the background.  The pair-tensor stream therefore never pauses (two independent CTAs per SM, which
+// the kernel used to be, each stopped streaming for more than half of a tile: every operand shared one shared-memory
+// region and was loaded only when the stage needing it began).
 struct CoreSmem {
-  // Region X [0, 73,728) is reused by the stages of the kernel:
-  //   stage 1: three K buffers (one head each: three [128 x 64 B] blocks); Q sits in the (not yet used) P_h region
-  //   stage 2: ring of four 16 KB e rows + 4 KB of warp-private staging tiles
-  //   stage 3: four V buffers;   epilogue: global-frame points
-  static constexpr int kKBuf = 3 * L * 64;           // 24,576
-  static constexpr int kKBufs = 3;
-  static constexpr int kXBytes = kKBufs * kKBuf;     // 73,728
-  static constexpr int kQBuf = H * 3 * IB * 64;      // 24,576
-  static constexpr int kQOff = kXBytes;              // inside the P_h region, which is idle during stage 1
-  static constexpr int kEStage = L * C * 2;          // 16,384
-  static constexpr int kEStages = 4;
-  static constexpr int kStaging = kEStages * kEStage;  // 8 warps x 512 B
-  static constexpr int kPi2 = kStaging + 8 * 512;      // second P_i buffer of each group (4 KB of region-X slack)
-  static constexpr int kVBuf = L * V_W * 2;          // 16,384
-  static constexpr int kVBufs = 4;
-  // probabilities per head, B operand of the O^T MMA: [h][kb(2)][16 rows][128 B], fp16
-  static constexpr int kPh = kXBytes;
+  static constexpr int kSlot = L * C * 2;            // 16,384: one pair row [128 j x 64 c] or one value tile [128 j x 64]
+  static constexpr int kSlots = 6;
+  static constexpr int kRing = 0;
+  static constexpr int kKBuf = 3 * L * 64;           // 24,576: one head of K = three [128 x 64 B] blocks
+  static constexpr int kKBufs = 2;
+  static constexpr int kKRing = kRing + kSlots * kSlot;          // 98,304
+  static constexpr int kCtx0 = kKRing + kKBufs * kKBuf;          // 147,456
+  // ---- per context ----
+  // probabilities per head, B operand of the O^T MMA: [kb(2)][h][16 rows][128 B], fp16.  Its first 24 KB hold Q until
+  // the S^T MMAs have completed.  The epilogue works in the 16 KB behind them (tail of P_h + the P_i slots, all idle by
+  // then): 12 KB of global-frame points and a 512-byte staging tile per warp - so the next tile's Q may arrive as soon
+  // as the O^T MMAs are done, while the epilogue is still running.
+  static constexpr int kPh = 0;
   static constexpr int kPhBytes = H * 2 * IB * 128;  // 32,768
-  // probabilities of one row, B operand of the pair MMA, one buffer per group: [g][kb(2)][8 rows][128 B], bf16
+  static constexpr int kQBuf = H * 3 * IB * 64;      // 24,576
+  // probabilities of a row pair, B operand of the pair MMA, two slots: [slot][kb(2)][16 rows = 8 g + h][128 B], bf16.
   static constexpr int kPi = kPh + kPhBytes;
-  static constexpr int kPiBytes = 2 * 2048;
-  static constexpr int kMisc = kPi + kPiBytes;
-  static constexpr int kRedMax = kMisc;              // [2 groups][2 parity][4 warps][16] f32
-  static constexpr int kInvO = kRedMax + 1024;       // [16][8] f32: 1 / sum_j p (from the ones column of V)
-  static constexpr int kBars = kInvO + 512;          // 40 mbarriers
-  static constexpr int kTmemSlot = kBars + 40 * 8;
+  static constexpr int kPiSlot = 2 * 2048;
+  static constexpr int kCtxBytes = kPi + 2 * kPiSlot;            // 40,960
+  static constexpr int kMisc = kCtx0 + 2 * kCtxBytes;            // 229,376
+  static constexpr int kRedMax = kMisc;              // [ctx][2 groups][2 parity][4 warps][16] f32
+  static constexpr int kBars = kRedMax + 2 * 1024;
+  static constexpr int kNumBars = 48;
+  static constexpr int kTmemSlot = kBars + kNumBars * 8;
   static constexpr int kTotal = kTmemSlot + 16;
 };
-static_assert(CoreSmem::kPi2 + 2 * 2048 <= CoreSmem::kXBytes, "e ring + staging + spare P_i buffers must fit region X");
-static_assert(CoreSmem::kVBufs * CoreSmem::kVBuf <= CoreSmem::kXBytes, "V buffers must fit region X");
 static_assert(CoreSmem::kQBuf <= CoreSmem::kPhBytes, "Q must fit the idle P_h region");
-static_assert(CoreSmem::kTotal <= 113 * 1024, "two CTAs per SM");
+static_assert(CoreSmem::kTotal <= 227 * 1024, "one CTA per SM");
 
-enum Bar { K_FULL = 0, K_EMPTY = 3, Q_FULL = 6, S_DONE = 7, E_FULL = 8, E_EMPTY = 12, PAIR = 16 /* [group][slot] */,
-           V_FULL = 20, V_EMPTY = 24, O_DONE = 28, P_READY = 29 /* [group][slot], 128 arrivals */,
-           EPI_TMEM = 33 /* 256 arrivals: epilogue has read every accumulator */, EPI_DONE = 34 /* 256: region X free */,
-           EPI_SFREE = 35 /* 256: the O^T accumulators (columns of S^T) have been read */, N_BARS = 36 };
+// shared rings
+// K_TURN / R_TURN hand the shared rings from one context's issuer to the other's: completion k = the issuer of local
+// tile k has observed every K (every pair-row / value) entry of that tile, so the next tile's issuer may start waiting on
+// the ring's full barriers (whose parities would otherwise alias with the entries of the tile before).
+enum Bar { K_FULL = 0, K_EMPTY = 2, R_FULL = 4, R_EMPTY = 10, K_TURN = 16, R_TURN = 17, CTX_BARS = 18, N_BARS = 18 + 2 * 13 };
+// per context (index CTX_BARS + 13 * ctx + ...)
+enum CtxBar { Q_FULL = 0, S_DONE = 1, PAIR = 2 /* [slot] */, O_DONE = 4, P_READY = 5 /* [group][slot], 128 arrivals */,
+              EPI_TMEM = 9 /* 256 arrivals: epilogue has read every accumulator */,
+              EPI_DONE = 10 /* 256: the P_h region is free for the next Q */,
+              EPI_SFREE = 11 /* 256: the O^T accumulators (columns of S^T) have been read */, N_CTX_BARS = 13 };
+static_assert(N_BARS <= CoreSmem::kNumBars, "barrier storage");
 
-// TMEM columns
-constexpr uint32_t kColS = 0, kColPair = 128 /* 16 rows x 8 */, kTmemCols = 256;
+// TMEM columns (per context: + 256 * ctx)
+constexpr uint32_t kColS = 0, kColPair = 128 /* 16 rows x 8 */, kTmemCols = 512;
 
 // Reduce 8 per-lane values across the warp with 9 shuffles; lane ends up with the result for head
 // hsel = 4*bit4 + 2*bit3 + bit2 of its lane id (every group of 4 lanes holds the same head).
@@ -315,235 +330,269 @@ __device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, float (&v)[4]) {
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Warp roles (320 threads): warps 0-3 and 4-7 are two softmax/epilogue groups of 128 threads (thread t of a
-// group owns key j = t = TMEM lane t; group g handles query rows i = g, g+2, ...); warp 8 lane 0 issues every
-// tcgen05.mma; warp 9 lane 0 issues every TMA load.  The roles meet only at mbarriers.
+// Warp roles (640 threads).  Context c = 0, 1: warps 8c .. 8c+7 are its two softmax/epilogue groups of 128 threads
+// (thread t of a group owns key j = t = TMEM lane t; group g handles query rows i = g, g+2, ...); warp 16 + c lane 0
+// issues the context's tcgen05.mma; warp 18 lane 0 issues the K / Q loads of both contexts, warp 19 lane 0 the pair-row
+// and value loads.  The roles meet only at mbarriers.
 // `bias` is the layer's precomputed pair bias, fp16 [B*L rows i][128 j][8 h], already scaled by
 // scale_total * log2(e) (dab_ipa_pair_bias): e is constant over the six layers and the T steps, so the
 // e . Wpb contraction is hoisted out of the sampling loop entirely.
-__global__ void __launch_bounds__(320, 2)
+constexpr int kCoreThreads = 640;
+__global__ void __launch_bounds__(kCoreThreads, 1)
 ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_e,
                 const uint4* __restrict__ bias, const float* __restrict__ tc, const float* __restrict__ R,
                 __nv_bfloat16* __restrict__ cat, float* __restrict__ stats, uint4* __restrict__ pu,
                 int n_tiles, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  // Persistent CTAs: CTA c works on tiles c, c + gridDim.x, ...; tile = (patch, block of 16 query rows).  While the
-  // epilogue of a tile runs, the producer already loads Q and the first K tiles of the next one (the first-load
-  // latency of a fresh CTA was ~6k of its 45k cycles), and TMEM / barriers are set up once.
   // optional per-tile timeline: slot k of tile c at dbg[c * 64 + k]
-  long long* dbg_cta = dbg ? dbg + (size_t)blockIdx.x * 64 : nullptr;
-#define DAB_STAMP(k) do { if (dbg_cta && threadIdx.x == 0) dbg_cta[(k)] = clock64(); } while (0)
+  long long* dbg_cta = nullptr;
+#define DAB_STAMP(k) do { if (dbg_cta && (threadIdx.x & 255) == 0) dbg_cta[(k)] = clock64(); } while (0)
 #define DAB_STAMP_ISSUER(k) do { if (dbg_cta) dbg_cta[(k)] = clock64(); } while (0)
-  DAB_STAMP(0);
+  // wait on a barrier, adding the cycles spent to `acc` when the timeline is on
+#define DAB_TIMED_WAIT(bar, par, acc) do { if (dbg) { long long t0_ = clock64(); mbar_wait((bar), (par)); (acc) += clock64() - t0_; } else mbar_wait((bar), (par)); } while (0)
   using S = CoreSmem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
-  float* inv_o = reinterpret_cast<float*>(smem + S::kInvO);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t smem_base = smem_u32(smem);
   if ((smem_base & 1023u) != 0) asm volatile("trap;");
-  // completions per tile of the K ring barriers (8 heads over 3 buffers); every other ring completes an even
-  // number of times per tile, so only these and the once-per-tile barriers need the tile counter in their parity
-  auto kc = [](int s) { return s == 2 ? 2 : 3; };
+  // local tiles of this CTA: k = 0, 1, ... -> global tile blockIdx.x + k * gridDim.x, context k & 1
+  const int n_local = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
+  // Ring bookkeeping.  Per tile every K slot completes 4 times and every e/V slot 4 times (24 entries on 6 slots), an
+  // even number: slot and parity of an entry depend only on its index inside the tile.
+  //   K entry h (head):            slot h & 1,   completion (h >> 1) of the tile
+  //   e/V entry x (row r: x = r; value tile h: x = 16 + h): slot x % 6, completion x / 6 of the tile
 
-  // stage 1 operands: K of the patch head by head (ring of three), Q rows of this tile
-  auto load_k = [&](int h, int b) {
-    const int s = h % S::kKBufs;
-    uint8_t* kb = smem + s * S::kKBuf;
-    mbar_arrive_expect_tx(&bars[K_FULL + s], S::kKBuf);
-    for (int blk = 0; blk < 3; ++blk)
-      tma_load_2d(kb + blk * (L * 64), &map_k, &bars[K_FULL + s], (h * 3 + blk) * 32, b * L);
-  };
-  auto load_q = [&](int64_t row0) {
-    uint8_t* qbuf = smem + S::kQOff;
-    mbar_arrive_expect_tx(&bars[Q_FULL], S::kQBuf);
-    for (int blk = 0; blk < H * 3; ++blk)    // [blk][16 rows][64 B], 64B swizzle
-      tma_load_2d(qbuf + blk * (IB * 64), &map_q, &bars[Q_FULL], blk * 32, (int)row0);
-  };
-  // The shared-memory ring is only four pair rows deep, far less than the HBM latency-bandwidth product, so
-  // rows are pulled HBM -> L2 six rows ahead with TMA prefetches and the ring is fed from L2.
-  constexpr int kL2Ahead = 6;
-  if (warp == 9 && lane == 0) {
-    // The producer lane initialises the barriers itself and starts the first loads right away: they are in flight
-    // while the rest of the CTA allocates TMEM and synchronises (first-load latency is ~10 % of a CTA's life).
-    for (int i = 0; i < N_BARS; ++i)
-      mbar_init(&bars[i], (i >= P_READY && i < P_READY + 4) ? 128u : (i >= EPI_TMEM ? 256u : 1u));
+  if (tid == 0) {
+    for (int i = 0; i < CTX_BARS; ++i) mbar_init(&bars[i], 1u);   // rings and turn barriers
+    for (int c = 0; c < 2; ++c)
+      for (int i = 0; i < N_CTX_BARS; ++i)
+        mbar_init(&bars[CTX_BARS + N_CTX_BARS * c + i], (i >= P_READY && i < P_READY + 4) ? 128u : (i >= EPI_TMEM ? 256u : 1u));
     fence_barrier_init();
-    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
-    const int b = (int)blockIdx.x >> 3;
-    const int64_t row0 = (int64_t)b * L + ((int)blockIdx.x & 7) * IB;
-    load_k(0, b);
-    load_q(row0);
-    load_k(1, b);
-    load_k(2, b);
-    for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
   tcgen05_fence_before_sync();
   __syncthreads();
   tcgen05_fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
-  DAB_STAMP(1);
+  const uint32_t tmem_cta = *tmem_slot;
 
-  if (warp == 9) {
-    // ======================================= TMA producer =======================================
+  if (warp == 18) {
+    // ======================================= TMA producer: K ring and Q =======================================
     if (lane == 0) {
-     for (int n = 0, tile = blockIdx.x; tile < n_tiles; ++n, tile += gridDim.x) {
-      const int b = tile >> 3;
-      const int64_t row0 = (int64_t)b * L + (tile & 7) * IB;
-      for (int h = S::kKBufs; h < H; ++h) {
-        const int s = h % S::kKBufs;
-        mbar_wait(&bars[K_EMPTY + s], (n * kc(s) + (h / S::kKBufs) - 1) & 1);
-        load_k(h, b);
+      tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k);
+      for (int k = 0; k < n_local; ++k) {
+        const int c = k & 1, n = k >> 1, tile = tile_of(k);
+        const int b = tile >> 3;
+        const int64_t row0 = (int64_t)b * L + (tile & 7) * IB;
+        uint64_t* cb = bars + CTX_BARS + N_CTX_BARS * c;
+        uint8_t* cs = smem + S::kCtx0 + c * S::kCtxBytes;
+        auto load_k = [&](int h) {
+          const int s = h & 1;
+          if (k > 0 || h >= S::kKBufs) mbar_wait(&bars[K_EMPTY + s], ((h >> 1) + 1) & 1);
+          uint8_t* kb = smem + S::kKRing + s * S::kKBuf;
+          mbar_arrive_expect_tx(&bars[K_FULL + s], S::kKBuf);
+          for (int blk = 0; blk < 3; ++blk)
+            tma_load_2d(kb + blk * (L * 64), &map_k, &bars[K_FULL + s], (h * 3 + blk) * 32, b * L);
+        };
+        // the first two heads of K go out as soon as the ring has room (i.e. while the context is still busy with its
+        // previous tile); Q goes into the context's P_h region, free once the O^T MMAs of that tile have completed
+        load_k(0);
+        load_k(1);
+        if (n > 0) mbar_wait(&cb[O_DONE], (n - 1) & 1);
+        mbar_arrive_expect_tx(&cb[Q_FULL], S::kQBuf);
+        for (int blk = 0; blk < H * 3; ++blk)    // [blk][16 rows][64 B], 64B swizzle
+          tma_load_2d(cs + S::kPh + blk * (IB * 64), &map_q, &cb[Q_FULL], blk * 32, (int)row0);
+        for (int h = S::kKBufs; h < H; ++h) load_k(h);
       }
-      // ---- stage 2: the pair rows (ring of four); region X is free once every S^T MMA has completed
-      mbar_wait(&bars[S_DONE], n & 1);
-      for (int r = 0; r < IB; ++r) {
-        const int s = r % S::kEStages;
-        if (r >= S::kEStages) mbar_wait(&bars[E_EMPTY + s], ((r / S::kEStages) - 1) & 1);
-        mbar_arrive_expect_tx(&bars[E_FULL + s], S::kEStage);
-        tma_load_2d(smem + s * S::kEStage, &map_e, &bars[E_FULL + s], 0, (int)((row0 + r) * L));
-        if (r + kL2Ahead < IB) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r + kL2Ahead) * L));
-      }
-      // ---- stage 3: V of the patch head by head (ring of four) once the last pair MMAs have released region X
-      for (int s = 0; s < S::kEStages; ++s) mbar_wait(&bars[E_EMPTY + s], ((IB / S::kEStages) - 1) & 1);
-      for (int h = 0; h < H; ++h) {
-        const int s = h % S::kVBufs;
-        if (h >= S::kVBufs) mbar_wait(&bars[V_EMPTY + s], ((h / S::kVBufs) - 1) & 1);
-        mbar_arrive_expect_tx(&bars[V_FULL + s], S::kVBuf);
-        tma_load_2d(smem + s * S::kVBuf, &map_v, &bars[V_FULL + s], h * V_W, b * L);
-      }
-      // ---- next tile: Q and the first two K tiles as soon as the O^T MMAs have released the V ring and the P_h
-      //      region, its first pair rows towards L2, the third K tile once the epilogue has left region X
-      const int nt = tile + gridDim.x;
-      if (nt < n_tiles) {
-        const int nb = nt >> 3;
-        const int64_t nrow0 = (int64_t)nb * L + (nt & 7) * IB;
-        mbar_wait(&bars[O_DONE], n & 1);
-        load_k(0, nb);
-        load_q(nrow0);
-        load_k(1, nb);
-        for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((nrow0 + r) * L));
-        mbar_wait(&bars[EPI_DONE], n & 1);
-        load_k(2, nb);
-      }
-     }
     }
-  } else if (warp == 8) {
-    // ======================================= MMA issuer =======================================
+  } else if (warp == 19) {
+    // ======================================= TMA producer: pair rows and value tiles =======================================
+    // The ring is only six tiles deep, far less than the HBM latency-bandwidth product, so pair rows are pulled
+    // HBM -> L2 kL2Ahead rows ahead (across the tile boundary) with TMA prefetches and the ring is fed from L2.
     if (lane == 0) {
+      tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
+      constexpr int kL2Ahead = 8;
+      auto row0_of = [&](int k) { const int tile = tile_of(k); return (int64_t)(tile >> 3) * L + (tile & 7) * IB; };
+      if (n_local > 0)
+        for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0_of(0) + r) * L));
+      for (int k = 0; k < n_local; ++k) {
+        const int tile = tile_of(k), b = tile >> 3;
+        const int64_t row0 = row0_of(k);
+        const int64_t nrow0 = k + 1 < n_local ? row0_of(k + 1) : -1;
+        for (int x = 0; x < IB + H; ++x) {
+          const int s = x % S::kSlots;
+          if (k > 0 || x >= S::kSlots) mbar_wait(&bars[R_EMPTY + s], ((x / S::kSlots) + 1) & 1);
+          mbar_arrive_expect_tx(&bars[R_FULL + s], S::kSlot);
+          if (x < IB) {
+            tma_load_2d(smem + S::kRing + s * S::kSlot, &map_e, &bars[R_FULL + s], 0, (int)((row0 + x) * L));
+            const int a = x + kL2Ahead;
+            if (a < IB) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + a) * L));
+            else if (nrow0 >= 0) tma_prefetch_l2_2d(&map_e, 0, (int)((nrow0 + a - IB) * L));
+          } else {
+            tma_load_2d(smem + S::kRing + s * S::kSlot, &map_v, &bars[R_FULL + s], (x - IB) * V_W, b * L);
+          }
+        }
+      }
+    }
+  } else if (warp >= 16) {
+    // ======================================= MMA issuer of context c =======================================
+    // The whole warp runs the control flow (warp-uniform values stay in uniform registers: a single divergent lane
+    // spent ~20 instructions per MMA moving descriptors into them) and one elected lane issues.
+    const int c = __shfl_sync(0xffffffffu, warp, 0) - 16;
+    {
       constexpr uint32_t kIdescS = make_idesc_bf16(128, 16, 0, 0);     // S^T
       constexpr uint32_t kIdescPair = make_idesc_bf16(128, 16, 1, 0);  // A = two e tiles, MN-major
       constexpr uint32_t kIdescO = make_idesc_f16(128, 32, 1, 0);      // A = two V tiles, MN-major, fp16 operands
-     for (int n = 0, tile = blockIdx.x; tile < n_tiles; ++n, tile += gridDim.x) {
-      dbg_cta = dbg ? dbg + (size_t)tile * 64 : nullptr;
-      // ---- stage 1: S^T_h = K_h Q_h^T for the 8 heads
-      mbar_wait(&bars[Q_FULL], n & 1);
-      if (n > 0) {                                   // the previous tile's epilogue has read the O^T accumulators
-        mbar_wait(&bars[EPI_SFREE], (n - 1) & 1);    // (same columns as S^T; the pair accumulators are waited for below)
+      uint64_t* cb = bars + CTX_BARS + N_CTX_BARS * c;
+      const uint32_t cs = smem_base + S::kCtx0 + c * S::kCtxBytes;
+      const uint32_t tmem = tmem_cta + 256u * c;
+      // descriptors advance by adding (bytes >> 4) to their low word (addresses stay below 256 KB: no carry out of the field)
+      const uint64_t dK0 = make_smem_desc(smem_base + S::kKRing, 16, 512, kSwizzle64B);
+      const uint64_t dQ0 = make_smem_desc(cs + S::kPh, 16, 512, kSwizzle64B);
+      const uint64_t dR0 = make_smem_desc(smem_base + S::kRing, S::kSlot, 1024, kSwizzle128B);
+      const uint64_t dPi0 = make_smem_desc(cs + S::kPi, 16, 1024, kSwizzle128B);
+      const uint64_t dPh0 = make_smem_desc(cs + S::kPh, 16, 1024, kSwizzle128B);
+      for (int k = c, n = 0; k < n_local; k += 2, ++n) {
+        dbg_cta = (dbg && lane == 0) ? dbg + (size_t)tile_of(k) * 64 : nullptr;
+        long long w_q = 0, w_sfree = 0, w_kturn = 0, w_k = 0, w_epit = 0, w_rturn = 0, w_e = 0, w_p = 0, w_v = 0;
+        DAB_STAMP_ISSUER(16);
+        // ---- stage 1: S^T_h = K_h Q_h^T for the 8 heads
+        DAB_TIMED_WAIT(&cb[Q_FULL], n & 1, w_q);
+        if (n > 0) {                                   // the previous tile's epilogue has read the O^T accumulators
+          DAB_TIMED_WAIT(&cb[EPI_SFREE], (n - 1) & 1, w_sfree);      // (same columns as S^T; the pair accumulators are waited for below)
+        }
+        if (k > 0) DAB_TIMED_WAIT(&bars[K_TURN], (k - 1) & 1, w_kturn);
         tcgen05_fence_after_sync();
-      }
-      for (int h = 0; h < H; ++h) {
-        const int s = h % S::kKBufs;
-        mbar_wait(&bars[K_FULL + s], (n * kc(s) + h / S::kKBufs) & 1);
-        tcgen05_fence_after_sync();
-        DAB_STAMP_ISSUER(48 + h);
-        const uint32_t ka = smem_base + s * S::kKBuf;
-        const uint32_t qa = smem_base + S::kQOff + h * 3 * (IB * 64);
+        DAB_STAMP_ISSUER(1);
+        for (int h = 0; h < H; ++h) {
+          const int s = h & 1;
+          DAB_TIMED_WAIT(&bars[K_FULL + s], (h >> 1) & 1, w_k);
+          tcgen05_fence_after_sync();
+          DAB_STAMP_ISSUER(48 + h);
+          if (elect_one()) {
+            const uint64_t ka = dK0 + (uint32_t)((s * S::kKBuf) >> 4);
+            const uint64_t qa = dQ0 + (uint32_t)((h * 3 * (IB * 64)) >> 4);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          // (A block, B block): scalar.scalar, hi.hi (+ norm columns), hi.lo, lo.hi
-          const int ablk = (m == 0) ? 0 : (m == 3 ? 2 : 1), bblk = (m == 0) ? 0 : (m == 2 ? 2 : 1);
+            for (int m = 0; m < 4; ++m) {
+              // (A block, B block): scalar.scalar, hi.hi (+ norm columns), hi.lo, lo.hi
+              const int ablk = (m == 0) ? 0 : (m == 3 ? 2 : 1), bblk = (m == 0) ? 0 : (m == 2 ? 2 : 1);
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            uint64_t da = make_smem_desc(ka + ablk * (L * 64) + k * 32, 16, 512, kSwizzle64B);
-            uint64_t db = make_smem_desc(qa + bblk * (IB * 64) + k * 32, 16, 512, kSwizzle64B);
-            umma_bf16(tmem + kColS + h * 16, da, db, kIdescS, (m | k) != 0);
+              for (int kk = 0; kk < 2; ++kk)
+                umma_bf16(tmem + kColS + h * 16, ka + (uint32_t)((ablk * (L * 64) + kk * 32) >> 4),
+                          qa + (uint32_t)((bblk * (IB * 64) + kk * 32) >> 4), kIdescS, (m | kk) != 0);
+            }
+            umma_commit(&bars[K_EMPTY + s]);
           }
+          __syncwarp();
         }
-        umma_commit(&bars[K_EMPTY + s]);
-      }
-      umma_commit(&bars[S_DONE]);
-      DAB_STAMP_ISSUER(2);
-      // ---- stage 2: pair aggregation of TWO rows per MMA chain (rows 2n and 2n+1, one from each softmax group):
-      //      [pair_2n ; pair_2n+1]^T = [e[2n] | e[2n+1]]^T [P_2n ; P_2n+1]^T  (M = 128: 64 channels of each row,
-      //      N = 16: 8 heads of each row, K = 128 j).  The two off-diagonal blocks (row 2n channels x row 2n+1
-      //      probabilities and vice versa) are computed and ignored: a small tcgen05.mma costs the same ~90 cycles
-      //      whatever its shape, so halving the instruction count is what matters.
-      if (n > 0) mbar_wait(&bars[EPI_TMEM], (n - 1) & 1);    // previous tile's pair accumulators drained
-      for (int n = 0; n < IB / 2; ++n) {
-        const int st = (2 * n) % S::kEStages;     // rows 2n, 2n+1 sit in consecutive ring stages
-        const int slot = n & 1;
-        if (n == 4) DAB_STAMP_ISSUER(40);
-        mbar_wait(&bars[E_FULL + st], ((2 * n) / S::kEStages) & 1);
-        mbar_wait(&bars[E_FULL + st + 1], ((2 * n) / S::kEStages) & 1);
-        if (n == 4) DAB_STAMP_ISSUER(41);
-        mbar_wait(&bars[P_READY + slot], (n >> 1) & 1);          // group 0, row 2n
-        mbar_wait(&bars[P_READY + 2 + slot], (n >> 1) & 1);      // group 1, row 2n + 1
-        tcgen05_fence_after_sync();
-        if (n == 4) DAB_STAMP_ISSUER(42);
-        const uint32_t ea = smem_base + st * S::kEStage;
-        const uint32_t pa = smem_base + (slot ? S::kPi2 : S::kPi);
+        if (elect_one()) {
+          umma_commit(&cb[S_DONE]);
+          mbar_arrive(&bars[K_TURN]);
+        }
+        __syncwarp();
+        DAB_STAMP_ISSUER(2);
+        // ---- stage 2: pair aggregation of TWO rows per MMA chain (rows 2p and 2p+1, one from each softmax group):
+        //      [pair_2p ; pair_2p+1]^T = [e[2p] | e[2p+1]]^T [P_2p ; P_2p+1]^T  (M = 128: 64 channels of each row,
+        //      N = 16: 8 heads of each row, K = 128 j).  The two off-diagonal blocks (row 2p channels x row 2p+1
+        //      probabilities and vice versa) are computed and ignored: a small tcgen05.mma costs the same
+        //      whatever its shape, so halving the instruction count is what matters.
+        if (n > 0) DAB_TIMED_WAIT(&cb[EPI_TMEM], (n - 1) & 1, w_epit);    // previous tile's pair accumulators drained
+        if (k > 0) DAB_TIMED_WAIT(&bars[R_TURN], (k - 1) & 1, w_rturn);
+        DAB_STAMP_ISSUER(17);
+        for (int p = 0; p < IB / 2; ++p) {
+          const int x = 2 * p, st = x % S::kSlots;     // rows 2p, 2p+1 sit in consecutive ring slots
+          const int slot = p & 1;
+          DAB_TIMED_WAIT(&bars[R_FULL + st], (x / S::kSlots) & 1, w_e);
+          DAB_TIMED_WAIT(&bars[R_FULL + st + 1], (x / S::kSlots) & 1, w_e);
+          if (p == 4) DAB_STAMP_ISSUER(41);
+          DAB_TIMED_WAIT(&cb[P_READY + slot], (p >> 1) & 1, w_p);          // group 0, row 2p
+          DAB_TIMED_WAIT(&cb[P_READY + 2 + slot], (p >> 1) & 1, w_p);      // group 1, row 2p + 1
+          tcgen05_fence_after_sync();
+          if (p == 4) DAB_STAMP_ISSUER(42);
+          if (elect_one()) {
+            // A: two e tiles [j][c] read MN-major: M = 128 = two 64-wide atoms one ring slot apart (LBO);
+            //    K = j: 16 rows = 2048 B per step, 8-row groups 1024 B apart (SBO)
+            const uint64_t ea = dR0 + (uint32_t)((st * S::kSlot) >> 4);
+            const uint64_t pa = dPi0 + (uint32_t)((slot * S::kPiSlot) >> 4);
 #pragma unroll
-        for (int k = 0; k < L / 16; ++k) {
-          // A: two e tiles [j][c] read MN-major: M = 128 = two 64-wide atoms one ring stage apart (LBO);
-          //    K = j: 16 rows = 2048 B per step, 8-row groups 1024 B apart (SBO)
-          uint64_t da = make_smem_desc(ea + k * 2048, S::kEStage, 1024, kSwizzle128B);
-          uint64_t db = make_smem_desc(pa + (k >> 2) * 2048 + (k & 3) * 32, 16, 1024, kSwizzle128B);
-          umma_bf16(tmem + kColPair + n * 16, da, db, kIdescPair, k != 0);
+            for (int kk = 0; kk < L / 16; ++kk)
+              umma_bf16(tmem + kColPair + p * 16, ea + (uint32_t)((kk * 2048) >> 4),
+                        pa + (uint32_t)(((kk >> 2) * 2048 + (kk & 3) * 32) >> 4), kIdescPair, kk != 0);
+            umma_commit(&cb[PAIR + slot]);
+            umma_commit(&bars[R_EMPTY + st]);
+            umma_commit(&bars[R_EMPTY + st + 1]);
+          }
+          __syncwarp();
+          if (p == 4) DAB_STAMP_ISSUER(43);
         }
-        umma_commit(&bars[PAIR + slot]);
-        umma_commit(&bars[E_EMPTY + st]);
-        umma_commit(&bars[E_EMPTY + st + 1]);
-        if (n == 4) DAB_STAMP_ISSUER(43);
-      }
-      DAB_STAMP_ISSUER(3);
-      // ---- stage 3: O^T of TWO heads per MMA chain: [O_2m ; O_2m+1]^T = [V_2m | V_2m+1]^T [P_2m ; P_2m+1]^T
-      //      (M = 128: 64 value columns of each head, N = 32: 16 rows of each head, K = 128 j)
-      for (int m = 0; m < H / 2; ++m) {
-        const int s = (2 * m) % S::kVBufs;
-        mbar_wait(&bars[V_FULL + s], ((2 * m) / S::kVBufs) & 1);
-        mbar_wait(&bars[V_FULL + s + 1], ((2 * m) / S::kVBufs) & 1);
-        tcgen05_fence_after_sync();
-        DAB_STAMP_ISSUER(56 + m);
-        const uint32_t va = smem_base + s * S::kVBuf, pa = smem_base + S::kPh + (2 * m) * (IB * 128);
+        DAB_STAMP_ISSUER(3);
+        // ---- stage 3: O^T of TWO heads per MMA chain: [O_2m ; O_2m+1]^T = [V_2m | V_2m+1]^T [P_2m ; P_2m+1]^T
+        //      (M = 128: 64 value columns of each head, N = 32: 16 rows of each head, K = 128 j)
+        for (int m = 0; m < H / 2; ++m) {
+          const int x = IB + 2 * m, st = x % S::kSlots;
+          DAB_TIMED_WAIT(&bars[R_FULL + st], (x / S::kSlots) & 1, w_v);
+          DAB_TIMED_WAIT(&bars[R_FULL + st + 1], (x / S::kSlots) & 1, w_v);
+          tcgen05_fence_after_sync();
+          DAB_STAMP_ISSUER(56 + m);
+          if (elect_one()) {
+            const uint64_t va = dR0 + (uint32_t)((st * S::kSlot) >> 4);
+            const uint64_t pa = dPh0 + (uint32_t)(((2 * m) * (IB * 128)) >> 4);
 #pragma unroll
-        for (int k = 0; k < L / 16; ++k) {
-          uint64_t da = make_smem_desc(va + k * 2048, S::kVBuf, 1024, kSwizzle128B);
-          uint64_t db = make_smem_desc(pa + (k >> 2) * (H * IB * 128) + (k & 3) * 32, 16, 1024, kSwizzle128B);
-          umma_bf16(tmem + kColS + m * 32, da, db, kIdescO, k != 0);
+            for (int kk = 0; kk < L / 16; ++kk)
+              umma_bf16(tmem + kColS + m * 32, va + (uint32_t)((kk * 2048) >> 4),
+                        pa + (uint32_t)(((kk >> 2) * (H * IB * 128) + (kk & 3) * 32) >> 4), kIdescO, kk != 0);
+            umma_commit(&bars[R_EMPTY + st]);
+            umma_commit(&bars[R_EMPTY + st + 1]);
+          }
+          __syncwarp();
         }
-        umma_commit(&bars[V_EMPTY + s]);
-        umma_commit(&bars[V_EMPTY + s + 1]);
+        if (elect_one()) {
+          umma_commit(&cb[O_DONE]);
+          mbar_arrive(&bars[R_TURN]);
+        }
+        __syncwarp();
+        DAB_STAMP_ISSUER(7);
+        if (dbg_cta) {
+          dbg_cta[18] = w_q; dbg_cta[19] = w_sfree; dbg_cta[20] = w_kturn; dbg_cta[21] = w_k; dbg_cta[22] = w_epit;
+          dbg_cta[23] = w_rturn; dbg_cta[25] = w_e; dbg_cta[26] = w_p; dbg_cta[27] = w_v;
+        }
       }
-      umma_commit(&bars[O_DONE]);
-     }
     }
   } else {
-    // ======================================= softmax / epilogue groups =======================================
-    const int g = warp >> 2, gw = warp & 3, gt = tid & 127;
+    // ======================================= softmax / epilogue groups of context c =======================================
+    const int c = warp >> 3, cw = warp & 7;              // context, warp inside the context
+    const int g = cw >> 2, gw = cw & 3, gt = tid & 127, ct = tid & 255;
+    uint64_t* cb = bars + CTX_BARS + N_CTX_BARS * c;
+    uint8_t* cs = smem + S::kCtx0 + c * S::kCtxBytes;
+    const uint32_t tmem = tmem_cta + 256u * c;
     const uint32_t tmem_lane = tmem + ((uint32_t)(gw * 32) << 16);
     // value index this lane ends up with after warp_reduce16: 8*bit4 + 4*bit3 + 2*bit2 + bit1
     const int vsel = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-    uint8_t* stage_w = smem + S::kStaging + warp * 512;   // warp-private staging tile
-    float* red_max = reinterpret_cast<float*>(smem + S::kRedMax) + g * 128;    // [parity][4 warps][16]
-    auto bar_group = [&] { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
-    auto bar_all_compute = [] { asm volatile("bar.sync 3, 256;" ::: "memory"); };
+    float* red_max = reinterpret_cast<float*>(smem + S::kRedMax) + c * 256 + g * 128;    // [parity][4 warps][16]
+    float* red_ctx = reinterpret_cast<float*>(smem + S::kRedMax) + c * 256;
+    float* inv_o = red_ctx;                                    // [16][8] f32: 1 / sum_j p (epilogue only: the maxima buffer of group 0 / 1 is idle then)
+    auto bar_group = [&] { asm volatile("bar.sync %0, 128;" ::"r"(1 + 2 * c + g) : "memory"); };
+    auto bar_all_compute = [&] { asm volatile("bar.sync %0, 256;" ::"r"(5 + c) : "memory"); };
+    (void)ct;
 
-   for (int tn = 0, tile = blockIdx.x; tile < n_tiles; ++tn, tile += gridDim.x) {
+   for (int k = c, tn = 0; k < n_local; k += 2, ++tn) {
+    const int tile = tile_of(k);
     const int b = tile >> 3, i0 = (tile & 7) * IB;
     const int64_t row0 = (int64_t)b * L + i0;       // first query row (global residue index)
-    (void)i0;
     dbg_cta = dbg ? dbg + (size_t)tile * 64 : nullptr;
+    long long w_pair = 0;
+    DAB_STAMP(0);
     // pair bias of this thread's key for the group's rows, one quarter (two rows) ahead in registers
     const uint4* bias_t = bias + (row0 + g) * L + gt;      // local row n (i = 2n + g)  ->  + n * 2 * L
     uint4 b_cur[2] = {__ldg(bias_t), __ldg(bias_t + 2 * L)};
     uint4 b_nxt[2] = {__ldg(bias_t + 4 * L), __ldg(bias_t + 6 * L)};
-    mbar_wait(&bars[S_DONE], tn & 1);
+    mbar_wait(&cb[S_DONE], tn & 1);
     tcgen05_fence_after_sync();
+    DAB_STAMP(6);
     // Four quarters of the 16 query rows; this group owns rows 4q + g and 4q + 2 + g of each quarter and
     // treats them together: one butterfly and one group barrier give the 2 x 8 row maxima.
     for (int q = 0; q < IB / 4; ++q) {
@@ -564,9 +613,9 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       for (int r = 0; r < 2; ++r) {
         const __half2* hb = reinterpret_cast<const __half2*>(&b_use[r]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float2 f = __half22float2(hb[k]);
-          lg[r * 8 + 2 * k] = f.x; lg[r * 8 + 2 * k + 1] = f.y;
+        for (int kk = 0; kk < 4; ++kk) {
+          float2 f = __half22float2(hb[kk]);
+          lg[r * 8 + 2 * kk] = f.x; lg[r * 8 + 2 * kk + 1] = f.y;
         }
 #pragma unroll
         for (int h = 0; h < H; ++h) {
@@ -584,18 +633,18 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       {
         const float4* r4 = reinterpret_cast<const float4*>(rm);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float4 a = r4[k], bb = r4[4 + k], c = r4[8 + k], dd = r4[12 + k];
-          mx[4 * k] = fmaxf(fmaxf(a.x, bb.x), fmaxf(c.x, dd.x));
-          mx[4 * k + 1] = fmaxf(fmaxf(a.y, bb.y), fmaxf(c.y, dd.y));
-          mx[4 * k + 2] = fmaxf(fmaxf(a.z, bb.z), fmaxf(c.z, dd.z));
-          mx[4 * k + 3] = fmaxf(fmaxf(a.w, bb.w), fmaxf(c.w, dd.w));
+        for (int kk = 0; kk < 4; ++kk) {
+          float4 a = r4[kk], bb = r4[4 + kk], cc = r4[8 + kk], dd = r4[12 + kk];
+          mx[4 * kk] = fmaxf(fmaxf(a.x, bb.x), fmaxf(cc.x, dd.x));
+          mx[4 * kk + 1] = fmaxf(fmaxf(a.y, bb.y), fmaxf(cc.y, dd.y));
+          mx[4 * kk + 2] = fmaxf(fmaxf(a.z, bb.z), fmaxf(cc.z, dd.z));
+          mx[4 * kk + 3] = fmaxf(fmaxf(a.w, bb.w), fmaxf(cc.w, dd.w));
         }
       }
       if (stats && gt < 16) {   // row maxima (log2 units) of the group's two rows, kept for the backward
         float v = mx[0];
 #pragma unroll
-        for (int k = 1; k < 16; ++k) v = (k == gt) ? mx[k] : v;
+        for (int kk = 1; kk < 16; ++kk) v = (kk == gt) ? mx[kk] : v;
         stats[(row0 + 2 * (2 * q + (gt >> 3)) + g) * 16 + (gt & 7)] = v;
       }
 #pragma unroll
@@ -607,16 +656,16 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (pu)   // training: keep the un-normalised probabilities (bf16, [i][j][h]) for the backward
           pu[(row0 + i) * L + gt] = make_uint4(pack_bf162(p[0], p[1]), pack_bf162(p[2], p[3]), pack_bf162(p[4], p[5]),
                                                pack_bf162(p[6], p[7]));
-        // the pair MMA that last read this P_i buffer (row n-2 of this group) must have completed
-        if (n >= 2) mbar_wait(&bars[PAIR + (n & 1)], ((n >> 1) - 1) & 1);
+        // the pair MMA that last read this P_i slot (row n-2 of this group) must have completed
+        if (n >= 2) DAB_TIMED_WAIT(&cb[PAIR + (n & 1)], ((n >> 1) - 1) & 1, w_pair);
         // ---- probabilities -> shared memory in the two operand layouts (K-major, 128B swizzle); neighbouring
         //      lanes trade heads so that every store is a packed pair (j, j+1).  Un-normalised: the row sums come
         //      out of the O^T MMA itself (ones column of the V operand) and are applied in the epilogue.
         {
           const int je = gt & ~1;                                   // even key of the pair
           const uint32_t kb = je >> 6, chunk = (je & 63) >> 3, e2 = (je & 7) * 2;
-          uint8_t* pi = smem + ((n & 1) ? S::kPi2 : S::kPi) + kb * 2048 + g * 1024;   // [kb][row = 8 g + h][128 B]
-          uint8_t* ph = smem + S::kPh + kb * (H * IB * 128);                            // [kb][h][16 i][128 B]
+          uint8_t* pi = cs + S::kPi + (n & 1) * S::kPiSlot + kb * 2048 + g * 1024;   // [kb][row = 8 g + h][128 B]
+          uint8_t* ph = cs + S::kPh + kb * (H * IB * 128);                            // [kb][h][16 i][128 B]
           const bool odd = lane & 1;
 #pragma unroll
           for (int hh = 0; hh < 4; ++hh) {
@@ -630,11 +679,12 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         fence_proxy_async_smem();
         tcgen05_fence_before_sync();
-        mbar_arrive(&bars[P_READY + g * 2 + (n & 1)]);
+        mbar_arrive(&cb[P_READY + g * 2 + (n & 1)]);
         if (g == 0) DAB_STAMP(8 + n);
       }
     }
     DAB_STAMP(24);
+    if (dbg_cta && (tid & 255) == 0) dbg_cta[28] = w_pair;
 
     // ---- epilogue.  O^T of head pair m sits in columns 32 m .. 32 m + 31 (M = 128): TMEM lane d (warps 0, 1)
     //      = value column d of head 2m with the 16 rows in columns 0..15; lane 64 + d (warps 2, 3) = head 2m + 1
@@ -645,13 +695,13 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     {
       const int64_t row = row0 + (gt >> 3);
 #pragma unroll
-      for (int c = 0; c < 9; ++c) Rm[c] = __ldg(R + row * 9 + c);
+      for (int cc = 0; cc < 9; ++cc) Rm[cc] = __ldg(R + row * 9 + cc);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) tfr[c] = __ldg(tc + row * 3 + c);
+      for (int cc = 0; cc < 3; ++cc) tfr[cc] = __ldg(tc + row * 3 + cc);
     }
-    // 1 KB per warp in the tail of the P_h region (its first 24 KB receive the next tile's Q during the epilogue)
-    uint8_t* stage_e = smem + S::kPh + S::kQBuf + warp * 1024;
-    mbar_wait(&bars[O_DONE], tn & 1);
+    // 512 B per warp behind the global-frame points
+    uint8_t* stage_e = cs + S::kPh + S::kQBuf + 12288 + cw * 512;
+    mbar_wait(&cb[O_DONE], tn & 1);
     tcgen05_fence_after_sync();
     DAB_STAMP(4);
     const int hsel = gw >> 1;                    // which head of the pair this warp's lanes hold
@@ -671,8 +721,8 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
     bar_all_compute();
     if (stats && g == 0) stats[(row0 + (gt >> 3)) * 16 + 8 + (gt & 7)] = inv_o[gt];
-    // [16 i][8 h][24] global-frame points, in the third K buffer: the first two already take the next tile's K
-    float* s_og = reinterpret_cast<float*>(smem + 2 * S::kKBuf);
+    // [16 i][8 h][24] global-frame points, behind the Q area of the P_h region
+    float* s_og = reinterpret_cast<float*>(cs + S::kPh + S::kQBuf);
 #pragma unroll
     for (int mm = 0; mm < 2; ++mm) {
       const int m = 2 * g + mm, h = 2 * m + hsel;
@@ -682,21 +732,21 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       if ((gw & 1) == 0) {       // scalar values: d = lane
         __nv_bfloat16* st16 = reinterpret_cast<__nv_bfloat16*>(stage_e);
 #pragma unroll
-        for (int i = 0; i < IB; ++i) st16[i * 32 + lane] = __float2bfloat16_rn(o[i] * inv_o[i * H + h]);
-        __syncwarp();
+        for (int r = 0; r < 2; ++r) {   // two halves of 8 rows: [8 i][64 B] -> 32 chunks of 16 B, one per lane
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {   // [16 i][64 B] -> 64 chunks of 16 B, two per lane
-          const int q = lane + 32 * r, i = q >> 2, part = q & 3;
-          *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + h * DS + part * 8) = reinterpret_cast<const uint4*>(stage_e)[q];
+          for (int i = 0; i < 8; ++i) st16[i * 32 + lane] = __float2bfloat16_rn(o[8 * r + i] * inv_o[(8 * r + i) * H + h]);
+          __syncwarp();
+          const int i = 8 * r + (lane >> 2), part = lane & 3;
+          *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + h * DS + part * 8) = reinterpret_cast<const uint4*>(stage_e)[lane];
+          __syncwarp();
         }
-        __syncwarp();
       } else if (lane < 3 * P) { // point coordinates: d - 32 = lane
 #pragma unroll
         for (int i = 0; i < IB; ++i) s_og[(i * H + h) * 24 + lane] = o[i] * inv_o[i * H + h];
       }
     }
     tcgen05_fence_before_sync();
-    mbar_arrive(&bars[EPI_SFREE]);    // O^T read: the next tile's S^T MMAs may overwrite these columns
+    mbar_arrive(&cb[EPI_SFREE]);    // O^T read: the next tile's S^T MMAs may overwrite these columns
     bar_all_compute();
     // inverse frame + norms (diffab_pytorch.py:327-336,453-457): ol[c'] = sum_k (og[k] - t[k]) R[c'][k];
     // thread (i, h) handles the 8 points of one head -> 48 + 16 contiguous bytes
@@ -724,7 +774,6 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           make_uint4(pack_bf162(nrm[0], nrm[1]), pack_bf162(nrm[2], nrm[3]), pack_bf162(nrm[4], nrm[5]),
                      pack_bf162(nrm[6], nrm[7]));
     }
-    mbar_arrive(&bars[EPI_DONE]);     // s_og is no longer read: the whole of region X belongs to the next tile
     // pair aggregation: accumulator n (16 columns) holds rows 2n (lanes 0-63 = channel c, columns 0-7 = heads) and
     // 2n + 1 (lanes 64-127, columns 8-15).  The last pair MMA is older than the O^T MMAs, so O_DONE covers it.
     // Group g drains the accumulators n = g, g + 2, ...; warp gw holds channels 32 (gw & 1) .. + 31 of row 2n + hsel.
@@ -749,20 +798,17 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       __syncwarp();
     }
     tcgen05_fence_before_sync();
-    mbar_arrive(&bars[EPI_TMEM]);     // every accumulator of this tile has been read: the next tile's MMAs may start
+    mbar_arrive(&cb[EPI_TMEM]);     // every accumulator of this tile has been read: the next tile's MMAs may start
     DAB_STAMP(5);
+    bar_all_compute();              // inv_o / the staging tiles are read until here; the next tile's softmax rewrites them
    }
   }
   tcgen05_fence_before_sync();
   __syncthreads();
-  if (dbg_cta && tid == 0) {
-    uint32_t smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    dbg_cta[6] = smid;
-  }
 #undef DAB_STAMP
 #undef DAB_STAMP_ISSUER
-  if (warp == 0) tmem_free(tmem, kTmemCols);
+#undef DAB_TIMED_WAIT
+  if (warp == 0) tmem_free(tmem_cta, kTmemCols);
 }
 
 // Pair bias of up to six layers in ONE pass over the pair tensor, on the tensor cores:
@@ -1020,10 +1066,10 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
       cudaGetDevice(&dev_id);
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev_id);
     }
-    const int grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;     // persistent: two CTAs per SM
-    ipa_core_kernel<<<grid, 320, CoreSmem::kTotal, s>>>(mq, mk, mv, me, bias, ws.tc, R, ws.cat,
-                                                        save_for_bwd ? ws.stats : nullptr,
-                                                        save_for_bwd ? ws.pu : nullptr, n_tiles, g_core_dbg);
+    const int grid = n_tiles < n_sm ? n_tiles : n_sm;     // persistent: one CTA per SM, two tile contexts each
+    ipa_core_kernel<<<grid, kCoreThreads, CoreSmem::kTotal, s>>>(mq, mk, mv, me, bias, ws.tc, R, ws.cat,
+                                                                 save_for_bwd ? ws.stats : nullptr,
+                                                                 save_for_bwd ? ws.pu : nullptr, n_tiles, g_core_dbg);
     count_launch();
   }
   if (phases & 4) {

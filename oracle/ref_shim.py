@@ -9,15 +9,27 @@ no arithmetic to the hot path:
   ``Embedding(21, .)`` so UNK = 20 is assumed; unpinned by any reference test).
 
 ``load_reference()`` pre-seeds ``sys.modules`` with stand-ins for those names and then imports
-``diffab_pytorch`` from ``/root/reference`` untouched.  It returns ``None`` when the reference
-tree is not present (e.g. on the GPU box), where only the committed goldens are used.
+``diffab_pytorch`` untouched from the first of: ``$DIFFAB_REFERENCE_ROOT``, ``<repo>/baseline/_ref``
+(the offline ``pip install --no-deps --target`` of the reference; git-ignored, it travels
+to the GPU box with the snapshot) and ``/root/reference`` (build container only).  It returns ``None``
+when none of them exists; only the committed goldens are used then.
 """
 import enum
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("DIFFAB_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    for cand in (os.environ.get("DIFFAB_REFERENCE_ROOT"), os.path.join(_REPO, "baseline", "_ref"), "/root/reference"):
+        if cand and os.path.isfile(os.path.join(cand, "diffab_pytorch", "diffab_pytorch.py")):
+            return cand
+    return os.environ.get("DIFFAB_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def _install_standins():

@@ -29,11 +29,11 @@ with torch.no_grad():
     lib.dab_debug_set_timeline(None)
 n_tiles = B * 8
 tl = buf[: n_tiles * 64].view(n_tiles, 64).cpu().double()
-grid = min(n_tiles, 296)
+grid = min(n_tiles, 148)
 def stat(name, d):
     print(f"  {name:52s} mean {d.mean():8.0f}  p10 {d.quantile(0.1):8.0f}  p90 {d.quantile(0.9):8.0f}")
-later = torch.arange(n_tiles) >= grid          # tiles that are not the first of their CTA
-prev = torch.arange(n_tiles) - grid
+later = torch.arange(n_tiles) >= 2 * grid          # tiles that are not the first of their CTA
+prev = torch.arange(n_tiles) - 2 * grid
 print(f"{n_tiles} tiles on {grid} persistent CTAs; cycles (tiles after the first of each CTA):")
 stat("previous tile epilogue end -> K_0 of this tile in smem", (tl[later, 48] - tl[prev[later], 5]))
 stat("stage 1: K_0 in smem -> last S^T MMA issued", tl[later, 2] - tl[later, 48])
