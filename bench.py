@@ -345,6 +345,11 @@ def main():
         line["ipa_fwd_bwd"]["fp32_path"] = measure_ipa_fwd_bwd(dev)
 
         line["cpu_baseline"] = cpu_line
+    if not args.skip_extras and args.reverse_steps == T and dist is not None:
+        # ---- BASELINE config 4: 4096 patches sharded over the ranks, T = 100, results gathered with NCCL ----
+        c4 = measure_config4(model, dist, world, rank, dev, precision, not args.no_graph)
+        if rank == 0:
+            line["config4"] = c4
     if not args.skip_extras and args.reverse_steps == T:
         # ---- BASELINE config 5: training step, B=64 patches per GPU, all ranks (DDP all-reduce over NCCL) ------
         train = measure_train_step(dev, dist, world, shapes)
@@ -360,41 +365,85 @@ def main():
 
 
 def measure_roofline(model, layer, res_ctx, pair_ctx, x0, O0, precision, hbm_peak, peak_src, iters=20):
-    """Average device time of the attention-core launch alone (phase mask 2), CUDA events on the
-    launching stream, input (pair tensor of all patches) larger than L2."""
+    """Roofline of the dominant kernel (the IPA attention core) and of the whole IPA layer (its three launches), timed
+    live with CUDA events on the launching stream; the input (pair tensor of all patches) is larger than L2.
+    `achieved` uses SURVEY 8(d)'s ALGORITHMIC bytes of one IPA layer, B (L^2 C + 2 L D + 12 L) sz + params - what any
+    implementation of the layer must move - over the kernel's / the layer's duration; the bytes the kernel's own operand
+    list adds up to (which include this design's packed Q/K/V, bias planes and concat features) are reported beside it."""
+    import ctypes
     from diffab_pytorch_b200 import _lib
+    from diffab_pytorch_b200._lib import ptr
+    from diffab_pytorch_b200.diffab_pytorch import _ipa_structs
     lib = _lib.lib()
     B = res_ctx.shape[0]
     x = res_ctx.contiguous()
-    bias = layer.pair_bias(pair_ctx) if precision == "bf16" else None   # hoisted out of the loop, as in sample()
-    call = (lambda: layer(x, pair_ctx, O0, x0, bias)) if precision == "bf16" else (lambda: layer(x, pair_ctx, O0, x0))
-    with torch.no_grad():
-        call()                                # full call: fills the workspace the core kernel reads
-        torch.cuda.synchronize()
-        # inference calls reuse the layer's persistent workspace, which the phase-mask contract needs
-        lib.dab_debug_set_phase_mask(2)
-        try:
+    sz = pair_ctx.element_size()
+    alg = B * (L * L * 64 + 2 * L * 128 + 12 * L) * sz + 303752 * 4          # SURVEY 8(d), per layer
+    if precision != "bf16":
+        call = lambda: layer(x, pair_ctx, O0, x0)
+        with torch.no_grad():
             for _ in range(3):
                 call()
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
             for a, b_ in evs:
-                a.record()
-                call()
-                b_.record()
+                a.record(); call(); b_.record()
             torch.cuda.synchronize()
-        finally:
-            lib.dab_debug_set_phase_mask(7)
-    us = statistics.mean(a.elapsed_time(b_) for a, b_ in evs) * 1000.0
-    sz = pair_ctx.element_size()
-    if precision == "bf16":
-        # attention core (DESIGN.md "Algorithmic bytes"): e row (bf16) + precomputed bias row (fp16, 8 heads) per
-        # (i, j) pair; packed Q/K (2 x 768 bf16) + V (512 fp16) operands + centred t in, concat features (1024 bf16) out
-        alg = B * L * (L * 64 * 2 + L * 8 * 2 + (768 + 768 + 512 + 1024) * 2 + 12 + 36)
-    else:
-        # fp32 core: e (fp32) twice is NOT algorithmic (second read is a cache hit by design): e once, projections in,
-        # concat features out
-        alg = B * L * (L * 64 * 4 + (1344 + 1024) * 4 + 48)
-    achieved = alg / (us * 1e-6) / 1e9
+        us = statistics.mean(a.elapsed_time(b_) for a, b_ in evs) * 1000.0
+        return {"bound": "hbm", "kernel": "ipa layer (fp32 CUDA-core path, all launches)", "achieved": alg / us / 1e3,
+                "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": alg / us / 1e3 / hbm_peak, "traffic": None,
+                "us_per_launch": us, "algorithmic_bytes_per_launch": alg, "patches_per_launch": B}
+    with torch.no_grad():
+        bias = layer.pair_bias(pair_ctx)                                         # hoisted out of the loop, as in sample()
+        dims = _ipa_structs(layer, B, L)
+        packed = layer._packed_weights(dims)
+        ws = layer._workspace(lib.dab_ipa_sm100_workspace_bytes(ctypes.byref(dims)), x.device)
+        y = torch.empty(B, L, 128, device=x.device)
+
+        def run(stages):
+            _lib.check(lib.dab_ipa_fwd_sm100_stages(ctypes.byref(dims), ptr(packed), ptr(x), None, ptr(pair_ctx), ptr(bias),
+                                                    ptr(O0), ptr(x0), ptr(y), None, ptr(ws), ws.numel(), stages,
+                                                    _lib.stream_ptr()), "dab_ipa_fwd_sm100_stages")
+
+        def timed(stages):
+            for _ in range(3):
+                run(7)                                        # a full layer first: the stage then sees the cache state
+            evs = []                                          # it sees inside a stack of layers
+            reps = 4                                          # launches per event pair: the queue hides the launch latency
+            for _ in range(iters // reps + 1):
+                run(1)
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(reps):
+                    run(stages)
+                b_.record()
+                evs.append((a, b_))
+                run(4)
+            torch.cuda.synchronize()
+            return statistics.mean(a.elapsed_time(b_) for a, b_ in evs) * 1000.0 / reps
+
+        core_us = timed(2)
+        # the three launches of a layer back to back, replayed from a CUDA graph (no host gaps between them)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run(7)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(4):
+                run(7)
+        for _ in range(2):
+            g.replay()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            g.replay()
+        b_.record()
+        torch.cuda.synchronize()
+        layer_us = a.elapsed_time(b_) * 1000.0 / 20
+    # bytes on the core kernel's own operand list: e row (bf16) + precomputed bias row (fp16, 8 heads) per (i, j) pair;
+    # packed Q/K (2 x 768 bf16) + V (512 fp16) operands + centred t / R in, concat features (1024 bf16) out
+    operand = B * L * (L * 64 * 2 + L * 8 * 2 + (768 + 768 + 512 + 1024) * 2 + 12 + 36)
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of the same launch shape from the committed ncu capture
         prof = json.load(open(os.path.join(ROOT, "profiles", "core_ncu_summary.json")))
@@ -402,9 +451,67 @@ def measure_roofline(model, layer, res_ctx, pair_ctx, x0, O0, precision, hbm_pea
             traffic = prof["dram_bytes_per_launch"]
     except (OSError, ValueError, KeyError):
         pass
-    return {"bound": "hbm", "kernel": "ipa attention core (" + precision + ")", "achieved": achieved,
-            "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": traffic, "us_per_launch": us, "algorithmic_bytes_per_launch": alg, "patches_per_launch": B}
+    achieved = alg / core_us / 1e3
+    return {"bound": "hbm", "kernel": "ipa_core_kernel (attention core of one IPA layer, bf16 pair tensor)",
+            "achieved": achieved, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "traffic": traffic, "us_per_launch": core_us, "algorithmic_bytes_per_launch": alg,
+            "algorithmic_bytes_source": "SURVEY 8(d): B (L^2 C + 2 L D + 12 L) 2 + params, one IPA layer",
+            "patches_per_launch": B,
+            "operand_list": {"bytes_per_launch": operand, "achieved": operand / core_us / 1e3,
+                             "frac": operand / core_us / 1e3 / hbm_peak,
+                             "note": "this design's own operands (packed Q/K/V, fp16 bias planes, concat features)"},
+            "layer": {"launches": "ipa_proj_kernel + ipa_core_kernel + gemm_bf16_kernel (to_out), graph replay",
+                      "us": layer_us, "achieved": alg / layer_us / 1e3, "frac": alg / layer_us / 1e3 / hbm_peak}}
+
+
+def measure_config4(model, dist, world, rank, dev, precision, use_graph, total=4096, chunk=256):
+    """BASELINE config 4: batch-sharded sampling of 4096 synthetic patches (T = 100) over the ranks of one box with an
+    NCCL gather of the results.  Every rank samples its contiguous shard (4096 / N patches: 2048 / 1024 / 512 at
+    N = 2 / 4 / 8) through DiffAb.sample() from pinned host buffers in chunks of 256 patches (the captured graphs of
+    the main measurement are reused), then the sampled structures of all ranks are all-gathered; the time is the wall
+    clock from the first H2D copy to the end of the gather, max over ranks."""
+    from diffab_pytorch_b200 import synth
+    from diffab_pytorch_b200.distributed import shard_bounds
+    lo, hi = shard_bounds(total, world)[rank]
+    chunks = []
+    for c0 in range(lo, hi, chunk):
+        n = min(chunk, hi - c0)
+        batch = synth.make_patches(n, L, seed=500000 + c0, with_distmat=False)
+        chunks.append({k: v.pin_memory() for k, v in batch.items()})
+
+    def run():
+        outs = []
+        for h in chunks:
+            o = model.sample(h["seq_idx"], h["xyz"], h["orientations"], h["backbone_dihedrals"], None,
+                             h["pairwise_dihedrals"], h["atom_mask"], h["chain_idx"], h["residue_idx"],
+                             h["generation_mask"], h["residue_mask"], precision=precision, use_cuda_graph=use_graph)
+            outs.append(o)
+        local = {k: torch.cat([o[k] for o in outs]) for k in outs[0]}
+        gathered = {}
+        for k, v in local.items():
+            buf = torch.empty((world,) + v.shape, device=dev, dtype=v.dtype)
+            dist.all_gather_into_tensor(buf, v.contiguous())
+            gathered[k] = buf
+        torch.cuda.synchronize()
+        return gathered
+
+    h = chunks[0]                                                # warm-up: graphs for this shape are captured / reused
+    model.sample(h["seq_idx"], h["xyz"], h["orientations"], h["backbone_dihedrals"], None, h["pairwise_dihedrals"],
+                 h["atom_mask"], h["chain_idx"], h["residue_idx"], h["generation_mask"], h["residue_mask"],
+                 precision=precision, use_cuda_graph=use_graph)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = run()
+    dt = time.perf_counter() - t0
+    tmax = torch.tensor([dt], device=dev, dtype=torch.float64)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dt = float(tmax)
+    ok = bool(all(torch.isfinite(v.float()).all() for v in out.values()))
+    return {"what": "BASELINE config 4: batch-sharded sampling, T=100, NCCL all-gather of {seq, x, O} inside the timed region",
+            "patches_total": total, "patches_per_gpu": hi - lo, "n_gpus": world, "seconds": dt,
+            "patches_per_s": total / dt, "timing": "host wall clock from first H2D to end of gather, max over ranks",
+            "gathered_patches": int(out["seq_idx"].shape[0] * out["seq_idx"].shape[1]), "finite": ok}
 
 
 def measure_ipa_fwd_bwd(dev, B=32, iters=5):

@@ -11,7 +11,9 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_size
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdiffab_b200.so")
+# DAB_DEBUG_LIB=1 loads the debug build (make -C csrc debug: adds the process-global dab_debug_* hooks used by tools/)
+LIB_PATH = os.path.join(_HERE, "csrc", "libdiffab_b200_dbg.so" if os.environ.get("DAB_DEBUG_LIB") == "1"
+                        else "libdiffab_b200.so")
 _lib = None
 
 
@@ -50,7 +52,6 @@ EXPORTS = {
     "dab_version": (c_int, []),
     "dab_last_error": (c_char_p, []),
     "dab_launch_count": (ctypes.c_longlong, []),
-    "dab_debug_set_phase_mask": (c_int, [c_int]),
     "dab_so3_exp": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dab_so3_log": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dab_so3_log_skew": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
@@ -79,15 +80,13 @@ EXPORTS = {
     "dab_ipa_fwd_sm100": (c_int, [POINTER(DabIpaDims), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "dab_ipa_fwd_sm100_io": (c_int, [POINTER(DabIpaDims)] + [c_void_p] * 10 + [c_size_t, c_void_p]),
+    "dab_ipa_fwd_sm100_stages": (c_int, [POINTER(DabIpaDims)] + [c_void_p] * 10 + [c_size_t, c_int, c_void_p]),
     "dab_ipa_fwd_sm100_train": (c_int, [POINTER(DabIpaDims), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_size_t, c_void_p]),
     "dab_ipa_sm100_workspace_layout": (c_int, [POINTER(DabIpaDims), POINTER(c_size_t)]),
     "dab_ipa_bwd_sm100_workspace_bytes": (c_size_t, [POINTER(DabIpaDims)]),
     "dab_ipa_bwd_sm100": (c_int, [POINTER(DabIpaDims), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "dab_debug_set_bwd_timeline": (c_int, [c_void_p]),
-    "dab_debug_bwd_keep_qkv": (c_int, [c_int]),
-    "dab_debug_bwd_sm100_buffers": (c_int, [POINTER(DabIpaDims), c_void_p, c_void_p]),
     "dab_heads_packed_bytes": (c_size_t, []),
     "dab_heads_pack_weights": (c_int, [POINTER(DabHeadWeights), c_void_p, c_void_p]),
     "dab_heads_fwd_sm100": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -110,11 +109,30 @@ EXPORTS = {
     "dab_losses_fwd": (c_int, [c_void_p] * 7 + [c_int64, c_void_p, c_void_p, c_void_p]),
     "dab_losses_bwd": (c_int, [c_void_p] * 7 + [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dab_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
-    "dab_debug_set_timeline": (c_int, [c_void_p]),
-    "dab_debug_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "dab_debug_ipa_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                   c_void_p, c_void_p]),
+    "dab_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
+
+# present only in the debug build (libdiffab_b200_dbg.so)
+DEBUG_EXPORTS = {
+    "dab_debug_set_timeline": (c_int, [c_void_p]),
+    "dab_debug_set_bwd_timeline": (c_int, [c_void_p]),
+    "dab_debug_bwd_keep_qkv": (c_int, [c_int]),
+    "dab_debug_bwd_sm100_buffers": (c_int, [POINTER(DabIpaDims), c_void_p, c_void_p]),
+}
+
+
+_weight_generation = 0
+
+
+def weight_generation():
+    """Counter that is part of every weight-derived cache key (packed weights, captured sampling graphs)."""
+    return _weight_generation
+
+
+def bump_weight_generation():
+    """Declare that parameters may have changed behind PyTorch's back (updates replayed from a CUDA graph)."""
+    global _weight_generation
+    _weight_generation += 1
 
 
 def lib():
@@ -130,6 +148,11 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
+        for name, (res, args) in DEBUG_EXPORTS.items():
+            if hasattr(handle, name):
+                fn = getattr(handle, name)
+                fn.restype = res
+                fn.argtypes = args
         _lib = handle
     return _lib
 

@@ -10,10 +10,8 @@ namespace dab {
 
 static thread_local char g_error[512] = "";
 static std::atomic<long long> g_launches{0};
-static std::atomic<int> g_phase_mask{7};
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
-int phase_mask() { return g_phase_mask.load(std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -47,11 +45,6 @@ int dab_version(void) { return 100; /* 0.1.0 */ }
 const char* dab_last_error(void) { return dab::g_error; }
 
 long long dab_launch_count(void) { return dab::g_launches.load(); }
-
-int dab_debug_set_phase_mask(int mask) {
-  dab::g_phase_mask.store(mask & 7);
-  return DAB_OK;
-}
 
 int dab_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
   DAB_REQUIRE(n >= 0, DAB_EINVAL, "dab_cast_f32_to_bf16: negative n");

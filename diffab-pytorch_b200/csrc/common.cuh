@@ -12,7 +12,6 @@ namespace dab {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);   // bookkeeping behind dab_launch_count()
-int phase_mask();               // dab_debug_set_phase_mask(): bit0 projections, bit1 attention core, bit2 to_out
 
 inline int check_launch(const char* what) {
   cudaError_t err = cudaGetLastError();

@@ -63,35 +63,40 @@ __global__ void __launch_bounds__(128) gemm_bf16_kernel(const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   const int nk = K / kGemmBK;
-  if (threadIdx.x == 0) {
-    // ---- TMA producer: keeps the whole ring in flight, refilling a slot as soon as its MMAs have read it
+  if (warp == 0) {
+    // ---- TMA producer (whole warp walks the loop, one elected lane issues): keeps the whole ring in flight, refilling a
+    // slot as soon as its MMAs have read it
     for (int kc = 0; kc < nk; ++kc) {
       const int s = kc % kGemmStages;
       if (kc >= kGemmStages) mbar_wait(&empty[s], ((kc / kGemmStages) - 1) & 1);
-      uint8_t* a = smem + s * S::kStageBytes;
-      mbar_arrive_expect_tx(&full[s], S::kStageBytes);
-      tma_load_2d(a, &map_a, &full[s], kc * kGemmBK, m0);
-      tma_load_2d(a + S::kABytes, &map_b, &full[s], kc * kGemmBK, n0);
+      if (elect_one()) {
+        uint8_t* a = smem + s * S::kStageBytes;
+        mbar_arrive_expect_tx(&full[s], S::kStageBytes);
+        tma_load_2d(a, &map_a, &full[s], kc * kGemmBK, m0);
+        tma_load_2d(a + S::kABytes, &map_b, &full[s], kc * kGemmBK, n0);
+      }
+      __syncwarp();
     }
-  } else if (threadIdx.x == 32) {
+  } else if (warp == 1) {
     // ---- tcgen05.mma issuer (a different warp, so loads and MMAs never wait for each other's bookkeeping)
     constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, BN, 0, 0);
+    const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024, kSwizzle128B);
     for (int kc = 0; kc < nk; ++kc) {
       const int s = kc % kGemmStages;
       mbar_wait(&full[s], (kc / kGemmStages) & 1);
       tcgen05_fence_after_sync();
-      const uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
-      const uint32_t b_addr = a_addr + S::kABytes;
-#pragma unroll
-      for (int k = 0; k < kGemmBK / 16; ++k) {
+      if (elect_one()) {
         // K-major, 128B swizzle: 8-row groups are 1024 B apart (SBO); a K step of 16 bf16 is +32 B
-        uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024, kSwizzle128B);
-        uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024, kSwizzle128B);
-        umma_bf16(tmem_base, da, db, idesc, (kc | k) != 0);
+        const uint64_t da = d0 + (uint32_t)((s * S::kStageBytes) >> 4);
+        const uint64_t db = da + (uint32_t)(S::kABytes >> 4);
+#pragma unroll
+        for (int k = 0; k < kGemmBK / 16; ++k)
+          umma_bf16(tmem_base, da + (uint32_t)((k * 32) >> 4), db + (uint32_t)((k * 32) >> 4), idesc, (kc | k) != 0);
+        umma_commit(&empty[s]);  // slot reusable once these MMAs have read it
+        if (kc == nk - 1) umma_commit(done);
       }
-      umma_commit(&empty[s]);  // slot reusable once these MMAs have read it
+      __syncwarp();
     }
-    umma_commit(done);
   }
   __syncwarp();
   mbar_wait(done, 0);

@@ -40,8 +40,13 @@ namespace dab {
 namespace sm100 {
 
 constexpr float kLn2 = 0.6931471805599453f;
-static long long* g_bwd_dbg = nullptr;   // optional per-CTA clock64 timeline (dab_debug_set_bwd_timeline)
-static int g_bwd_keep_qkv = 0;           // test hook: also write the raw dQ / dK / dV accumulators
+#ifdef DAB_DEBUG_HOOKS
+static long long* g_bwd_dbg = nullptr;   // optional per-CTA clock64 timeline (dab_debug_set_bwd_timeline; debug build only)
+static int g_bwd_keep_qkv = 0;           // debug hook: also write the raw dQ / dK / dV accumulators
+#else
+static constexpr long long* g_bwd_dbg = nullptr;
+static constexpr int g_bwd_keep_qkv = 0;
+#endif
 
 // ---- backward workspace ---------------------------------------------------------------------------------
 struct BwdWs {
@@ -847,6 +852,7 @@ int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf1
   return check_launch("dab_ipa_bwd_sm100");
 }
 
+#ifdef DAB_DEBUG_HOOKS
 /* Test hook: keep the raw key-side accumulators (dQ, dK, dV of dab_debug_bwd_sm100_buffers) on later calls. */
 int dab_debug_bwd_keep_qkv(int on) {
   g_bwd_keep_qkv = on;
@@ -867,5 +873,7 @@ int dab_debug_bwd_sm100_buffers(const DabIpaDims* d, void* workspace, void** out
   out[5] = bw.Pn; out[6] = bw.dL; out[7] = bw.dQ; out[8] = bw.dK; out[9] = bw.dV;
   return DAB_OK;
 }
+
+#endif
 
 }  // extern "C"

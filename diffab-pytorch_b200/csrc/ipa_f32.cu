@@ -783,7 +783,7 @@ int dab_ipa_fwd_f32(const DabIpaDims* dims, const DabIpaWeights* w, const float*
   const float* Ws[6] = {w->w_q_scalar, w->w_k_scalar, w->w_v_scalar, w->w_q_point, w->w_k_point, w->w_v_point};
   int offs[6] = {d.o_qs, d.o_ks, d.o_vs, d.o_qp, d.o_kp, d.o_vp};
   int ns[6] = {d.NS, d.NS, d.NS, d.NQ, d.NQ, d.NV};
-  const int phases = phase_mask();
+  const int phases = 7;   // all three stages (projections, attention core, to_out)
   if (phases & 1) {
     for (int k = 0; k < 6; ++k) sgemm(s, x, d.D, 1, Ws[k], 1, d.D, ws.proj + offs[k], d.NPROJ, nullptr, M, ns[k], d.D, 0);
     int64_t npts = (int64_t)M * ((2 * d.NQ + d.NV) / 3);

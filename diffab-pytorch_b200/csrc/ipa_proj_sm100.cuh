@@ -113,44 +113,51 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
   PROJ_STAMP(1);
 
   if (warp == 8) {
-    if (lane == 0) {
+    // The whole warp walks the tile loop (warp-uniform values stay in uniform registers); one elected lane issues the TMA
+    // loads and the tcgen05.mma chains.
+    auto tile_rows = [](int tt) { return tt < 12 ? 64 : 48; };
+    auto tile_row0 = [](int tt) { return tt < 12 ? tt * 64 : 768 + (tt - 12) * 48; };
+    auto load_w = [&](int tt, int k) {      // called by ONE lane
+      const int s = k % S::kWStages;
+      uint8_t* dst = smem + S::kW + s * S::kWStage;
+      const int rows = tile_rows(tt);
+      mbar_arrive_expect_tx(&bars[W_FULL + s], 2 * rows * 128);
+      const CUtensorMap* m = tt < 12 ? &map_w64 : &map_w48;
+      tma_load_2d(dst, m, &bars[W_FULL + s], 0, tile_row0(tt));            // K 0..63
+      tma_load_2d(dst + rows * 128, m, &bars[W_FULL + s], 64, tile_row0(tt));  // K 64..127
+    };
+    if (elect_one()) {
       tma_prefetch_desc(&map_w64);
       tma_prefetch_desc(&map_w48);
-      auto tile_rows = [](int tt) { return tt < 12 ? 64 : 48; };
-      auto tile_row0 = [](int tt) { return tt < 12 ? tt * 64 : 768 + (tt - 12) * 48; };
-      auto load_w = [&](int tt, int k) {
-        const int s = k % S::kWStages;
-        uint8_t* dst = smem + S::kW + s * S::kWStage;
-        const int rows = tile_rows(tt);
-        mbar_arrive_expect_tx(&bars[W_FULL + s], 2 * rows * 128);
-        const CUtensorMap* m = tt < 12 ? &map_w64 : &map_w48;
-        tma_load_2d(dst, m, &bars[W_FULL + s], 0, tile_row0(tt));            // K 0..63
-        tma_load_2d(dst + rows * 128, m, &bars[W_FULL + s], 64, tile_row0(tt));  // K 64..127
-      };
       for (int k = 0; k < S::kWStages && k < n_local; ++k) load_w(split + k * n_split, k);
-      const uint32_t a_addr = smem_base + S::kA;
-      for (int k = 0; k < n_local; ++k) {       // k-th tile of this CTA = global tile tt
-        const int tt = split + k * n_split;
-        const int s = k % S::kWStages, acc = k & 1;
-        const int rows = tile_rows(tt);
-        mbar_wait(&bars[W_FULL + s], (k / S::kWStages) & 1);
-        if (k >= 2) mbar_wait(&bars[ACC_EMPTY + acc], ((k >> 1) - 1) & 1);   // epilogue drained this accumulator
-        tcgen05_fence_after_sync();
-        const uint32_t w_addr = smem_base + S::kW + s * S::kWStage;
+    }
+    __syncwarp();
+    const uint64_t dA0 = make_smem_desc(smem_base + S::kA, 16, 1024, kSwizzle128B);
+    const uint64_t dW0 = make_smem_desc(smem_base + S::kW, 16, 1024, kSwizzle128B);
+    for (int k = 0; k < n_local; ++k) {       // k-th tile of this CTA = global tile tt
+      const int tt = split + k * n_split;
+      const int s = k % S::kWStages, acc = k & 1;
+      const int rows = tile_rows(tt);
+      mbar_wait(&bars[W_FULL + s], (k / S::kWStages) & 1);
+      if (k >= 2) mbar_wait(&bars[ACC_EMPTY + acc], ((k >> 1) - 1) & 1);   // epilogue drained this accumulator
+      tcgen05_fence_after_sync();
+      if (elect_one()) {
+        const uint64_t dw = dW0 + (uint32_t)((s * S::kWStage) >> 4);
         const uint32_t idesc = make_idesc_bf16(128, rows, 0, 0);
+        const uint32_t kb1 = (uint32_t)((rows * 128) >> 4);
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          uint64_t da = make_smem_desc(a_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, kSwizzle128B);
-          uint64_t db = make_smem_desc(w_addr + (kk >> 2) * (rows * 128) + (kk & 3) * 32, 16, 1024, kSwizzle128B);
-          umma_bf16(tmem + acc * 64, da, db, idesc, kk != 0);
-        }
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_bf16(tmem + acc * 64, dA0 + (uint32_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
+                    dw + (kk >> 2) * kb1 + (uint32_t)(((kk & 3) * 32) >> 4), idesc, kk != 0);
         umma_commit(&bars[ACC_FULL + acc]);
         umma_commit(&bars[W_EMPTY + s]);
-        if (k >= 1 && k - 1 + S::kWStages < n_local) {
-          const int sp = (k - 1) % S::kWStages;
-          mbar_wait(&bars[W_EMPTY + sp], ((k - 1) / S::kWStages) & 1);
-          load_w(split + (k - 1 + S::kWStages) * n_split, k - 1 + S::kWStages);
-        }
+      }
+      __syncwarp();
+      if (k >= 1 && k - 1 + S::kWStages < n_local) {
+        const int sp = (k - 1) % S::kWStages;
+        mbar_wait(&bars[W_EMPTY + sp], ((k - 1) / S::kWStages) & 1);
+        if (elect_one()) load_w(split + (k - 1 + S::kWStages) * n_split, k - 1 + S::kWStages);
+        __syncwarp();
       }
     }
   } else {

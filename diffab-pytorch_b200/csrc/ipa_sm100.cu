@@ -1,21 +1,18 @@
-// sm_100a fast path of one InvariantPointAttentionLayer (inference, train.py configuration:
-// L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8).  Replaces diffab_pytorch.py:389-465 of the reference.
+// sm_100a fast path of one InvariantPointAttentionLayer (train.py configuration: L=128, D=128, C=64, H=8, ds=32,
+// Pq=Pv=8).  Replaces diffab_pytorch.py:389-465 of the reference.
 //
-// Launch sequence per layer (dab_ipa_fwd_sm100):
-//   1. cast x -> bf16
-//   2. projection GEMM on tcgen05 (gemm_sm100.cuh): proj[B*L,1344] = x Wcat^T
-//   3. pack: frame transform (x R + t, centred on the patch centroid), logit scales folded into q,
-//      split-bf16 (hi + lo) of the point coordinates, -0.5 c |k|^2 as extra K columns  -> Qp, Kp, Vp
-//   4. attention core (this file): per CTA = (patch, 16 query rows); TMA-staged tiles, tcgen05.mma with
-//      TMEM accumulators; j (keys) sits on the 128 TMEM lanes:
+// Three launches per layer (dab_ipa_fwd_sm100 / _io / _train / _stages):
+//   1. ipa_proj_kernel (ipa_proj_sm100.cuh): x -> bf16 -> the six projections on tcgen05 -> frame transform (x R + t,
+//      centred on the patch centroid), logit scales folded into q, split-bf16 (hi + lo) point coordinates,
+//      -0.5 c |k|^2 as extra K columns -> packed operands Qp, Kp, Vp (TMA stores)
+//   2. ipa_core_kernel (this file): one persistent CTA per SM with two tile contexts (tile = patch x 16 query rows);
+//      TMA-staged tiles, tcgen05.mma with TMEM accumulators; j (keys) sits on the 128 TMEM lanes:
 //        S^T_h = K_h Q_h^T          (M=128 j, N=16 i, K=32+3*32)   scalar + expanded point-distance logits
-//        bias^T_i = e[i] Wpb^T      (M=128 j, N=16,   K=64)        pair bias, e tile read by TMA once
-//        softmax over j in fp32 (warp butterflies + one shared-memory exchange per row)
-//        pair_i^T = e[i]^T P_i^T    (M=64 c,  N=8 h,  K=128 j)     same shared-memory e tile, MN-major
-//        O^T_h = [Vs|Vp]_h^T P_h^T  (M=64,    N=16 i, K=128 j)       fp16 operands: point coordinates (|v| ~ 40 A)
-//                                                                   keep 11 mantissa bits instead of 8
+//        + precomputed pair bias (dab_ipa_pair_bias*), softmax over j in fp32 (warp butterflies + one exchange per row pair)
+//        [pair_2p ; pair_2p+1]^T = [e[2p] | e[2p+1]]^T [P_2p ; P_2p+1]^T   (M=128, N=16, K=128 j)  same e tiles, MN-major
+//        [O_2m ; O_2m+1]^T = [V_2m | V_2m+1]^T [P_2m ; P_2m+1]^T          (M=128, N=32, K=128 j)  fp16 operands
 //      epilogue: normalise, inverse frame, norms -> concat features (bf16)
-//   5. to_out GEMM on tcgen05: y = concat Wout^T + b
+//   3. gemm_bf16_kernel (gemm_sm100.cuh): y = concat Wout^T + b
 // Logits never leave the SM; the pair tensor is read from HBM exactly once per layer.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -64,7 +61,11 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
 
 namespace sm100 {
 
-static long long* g_core_dbg = nullptr;   // optional timeline buffer (dab_debug_set_timeline)
+#ifdef DAB_DEBUG_HOOKS
+static long long* g_core_dbg = nullptr;   // optional timeline buffer (dab_debug_set_timeline; debug build only)
+#else
+static constexpr long long* g_core_dbg = nullptr;
+#endif
 
 // ---- weight packing (once per layer) --------------------------------------------------------------
 __global__ void pack_weights_kernel(DabIpaWeights w, uint8_t* packed) {
@@ -99,121 +100,6 @@ __global__ void pack_weights_kernel(DabIpaWeights w, uint8_t* packed) {
   float* gam = reinterpret_cast<float*>(packed + o.gamma);
   for (int i = tid; i < D; i += nth) bout[i] = w.b_out[i];
   for (int i = tid; i < H; i += nth) gam[i] = w.gamma[i];
-}
-
-// ---- operand packing (per call) --------------------------------------------------------------------
-// grid (L/16, B), 128 threads; warp w handles rows i0 + 4w .. 4w+3, lanes spread over features.
-__global__ void __launch_bounds__(128) ipa_pack_kernel(const float* __restrict__ proj, const float* __restrict__ R,
-                                                       const float* __restrict__ t, const float* __restrict__ gamma,
-                                                       __nv_bfloat16* __restrict__ Qp, __nv_bfloat16* __restrict__ Kp,
-                                                       __nv_bfloat16* __restrict__ Vp, float* __restrict__ tc) {
-  __shared__ float s_part[4][3];
-  __shared__ float s_cen[3];
-  const int b = blockIdx.y, i0 = blockIdx.x * 16;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // patch centroid of the translations (distances are translation invariant; centring keeps the
-  // expanded |q|^2 + |k|^2 - 2 q.k form well conditioned for patches far from the origin)
-  {
-    const float* tp = t + ((int64_t)b * L + threadIdx.x) * 3;
-    float x = tp[0], y = tp[1], z = tp[2];
-    x = warp_sum(x); y = warp_sum(y); z = warp_sum(z);
-    if (lane == 0) { s_part[warp][0] = x; s_part[warp][1] = y; s_part[warp][2] = z; }
-    __syncthreads();
-    if (threadIdx.x < 3)
-      s_cen[threadIdx.x] = (s_part[0][threadIdx.x] + s_part[1][threadIdx.x] + s_part[2][threadIdx.x] +
-                            s_part[3][threadIdx.x]) * (1.0f / L);
-    __syncthreads();
-  }
-  const float ss = rsqrtf((float)DS), sp = rsqrtf(4.5f * P), st = rsqrtf(3.0f);
-  const int h = lane >> 2, sub = lane & 3;
-  const float ch = st * sp * __ldg(gamma + h) * kLog2e;
-  for (int k = 0; k < 4; ++k) {
-    const int64_t row = (int64_t)b * L + i0 + warp * 4 + k;
-    const float* prow = proj + row * NPROJ;
-    const float* Rr = R + row * 9;
-    float Rm[9];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) Rm[c] = __ldg(Rr + c);
-    float tcx = __ldg(t + row * 3) - s_cen[0], tcy = __ldg(t + row * 3 + 1) - s_cen[1], tcz = __ldg(t + row * 3 + 2) - s_cen[2];
-    if (lane == 0) { tc[row * 3] = tcx; tc[row * 3 + 1] = tcy; tc[row * 3 + 2] = tcz; }
-    // scalars: lane covers features 8*lane .. 8*lane+7 -> head lane/4, offset (lane%4)*8
-#pragma unroll
-    for (int seg = 0; seg < 3; ++seg) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(prow + seg * NS + lane * 8));
-      const float4 c = __ldg(reinterpret_cast<const float4*>(prow + seg * NS + lane * 8 + 4));
-      const float sc = seg == 0 ? st * ss * kLog2e : 1.0f;   // scale_total * scale_scalar folded into q
-      uint4 o;
-      if (seg == 2) {   // values travel as fp16
-        o.x = pack_h2(a.x, a.y); o.y = pack_h2(a.z, a.w); o.z = pack_h2(c.x, c.y); o.w = pack_h2(c.z, c.w);
-      } else {
-        o.x = pack_bf162(a.x * sc, a.y * sc); o.y = pack_bf162(a.z * sc, a.w * sc);
-        o.z = pack_bf162(c.x * sc, c.y * sc); o.w = pack_bf162(c.z * sc, c.w * sc);
-      }
-      __nv_bfloat16* dst = seg == 0 ? Qp + row * (H * QK_W) + h * QK_W + sub * 8
-                         : seg == 1 ? Kp + row * (H * QK_W) + h * QK_W + sub * 8
-                                    : Vp + row * (H * V_W) + h * V_W + sub * 8;
-      *reinterpret_cast<uint4*>(dst) = o;
-    }
-    // points: lane covers points 2*lane, 2*lane+1 (6 consecutive floats) of head lane/4
-#pragma unroll
-    for (int seg = 0; seg < 3; ++seg) {
-      const float* pp = prow + 3 * NS + seg * NPT + lane * 6;
-      float loc[6];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float2 v = __ldg(reinterpret_cast<const float2*>(pp + 2 * c));
-        loc[2 * c] = v.x; loc[2 * c + 1] = v.y;
-      }
-      float g[6];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {   // euclidean_transform, diffab_pytorch.py:315-324 (row vector @ R + t)
-        float x = loc[3 * q], y = loc[3 * q + 1], z = loc[3 * q + 2];
-        g[3 * q] = x * Rm[0] + y * Rm[3] + z * Rm[6] + tcx;
-        g[3 * q + 1] = x * Rm[1] + y * Rm[4] + z * Rm[7] + tcy;
-        g[3 * q + 2] = x * Rm[2] + y * Rm[5] + z * Rm[8] + tcz;
-      }
-      if (seg == 2) {
-        __nv_bfloat16* dst = Vp + row * (H * V_W) + h * V_W + 32 + sub * 6;
-        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-        d32[0] = pack_h2(g[0], g[1]); d32[1] = pack_h2(g[2], g[3]); d32[2] = pack_h2(g[4], g[5]);
-        if (sub == 3)   // column 56 = 1: the O^T MMA then also returns the row sum of the probabilities
-          *reinterpret_cast<uint4*>(Vp + row * (H * V_W) + h * V_W + 56) = make_uint4(pack_h2(1.0f, 0.0f), 0, 0, 0);
-      } else {
-        const float sc = seg == 0 ? ch : 1.0f;
-        float hi[6], lo[6], n2 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          float v = g[c] * sc;
-          hi[c] = __bfloat162float(__float2bfloat16_rn(v));
-          lo[c] = v - hi[c];
-          n2 = fmaf(g[c], g[c], n2);
-        }
-        __nv_bfloat16* base = (seg == 0 ? Qp : Kp) + row * (H * QK_W) + h * QK_W;
-        uint32_t* dh = reinterpret_cast<uint32_t*>(base + 32 + sub * 6);
-        uint32_t* dl = reinterpret_cast<uint32_t*>(base + 64 + sub * 6);
-        dh[0] = pack_bf162(hi[0], hi[1]); dh[1] = pack_bf162(hi[2], hi[3]); dh[2] = pack_bf162(hi[4], hi[5]);
-        dl[0] = pack_bf162(lo[0], lo[1]); dl[1] = pack_bf162(lo[2], lo[3]); dl[2] = pack_bf162(lo[4], lo[5]);
-        // |k|^2 over the 8 points of the head: 4 lanes
-        n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
-        n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
-        if (sub == 3) {
-          uint4 tail = make_uint4(0, 0, 0, 0);
-          if (seg == 0) {                       // columns that pick up the key-side norm term: (1, 1, 1)
-            tail.x = pack_bf162(1.0f, 1.0f); tail.y = pack_bf162(1.0f, 0.0f);
-          } else {                              // -0.5 c_h |k|^2 split three ways (hi + mid + lo)
-            float nk = -0.5f * ch * n2;
-            float a = __bfloat162float(__float2bfloat16_rn(nk));
-            float m = __bfloat162float(__float2bfloat16_rn(nk - a));
-            float l = nk - a - m;
-            // column 59 = 1 (its Q counterpart is 0): the backward's dQ^T MMA then also returns sum_j dlogit
-            tail.x = pack_bf162(a, m); tail.y = pack_bf162(l, 1.0f);
-          }
-          *reinterpret_cast<uint4*>(base + 56) = tail;
-          *reinterpret_cast<uint4*>(base + 88) = make_uint4(0, 0, 0, 0);
-        }
-      }
-    }
-  }
 }
 
 // ---- attention core ---------------------------------------------------------------------------------
@@ -957,15 +843,17 @@ int dab_ipa_pack_weights(const DabIpaDims* d, const DabIpaWeights* w, void* pack
 
 size_t dab_ipa_sm100_workspace_bytes(const DabIpaDims* d) { return shape_ok(d) ? carve_ws(d->B, nullptr).bytes : 0; }
 
-/* Byte offsets of the workspace sections: Qp, Kp, Vp, tc, cat, bias, stats (the caller's library GEMMs of the
- * backward read `cat`; tests read the rest). */
-int dab_ipa_sm100_workspace_layout(const DabIpaDims* d, size_t* offsets /* 7 */) {
+/* Byte offsets of the workspace sections: Qp, Kp, Vp, tc, cat, bias, stats, pu (tests read them: `stats` = row maxima in
+ * log2 units [8 heads] | 1 / sum_j p [8 heads] per query row, `pu` = un-normalised probabilities 2^(l - max), bf16 [i][j][h],
+ * both written by the training forward). */
+int dab_ipa_sm100_workspace_layout(const DabIpaDims* d, size_t* offsets /* 8 */) {
   DAB_REQUIRE(shape_ok(d) && offsets, DAB_EINVAL, "dab_ipa_sm100_workspace_layout: bad argument");
   Ws w = carve_ws(d->B, nullptr);
   offsets[0] = reinterpret_cast<size_t>(w.Qp); offsets[1] = reinterpret_cast<size_t>(w.Kp);
   offsets[2] = reinterpret_cast<size_t>(w.Vp); offsets[3] = reinterpret_cast<size_t>(w.tc);
   offsets[4] = reinterpret_cast<size_t>(w.cat); offsets[5] = reinterpret_cast<size_t>(w.bias);
   offsets[6] = reinterpret_cast<size_t>(w.stats);
+  offsets[7] = reinterpret_cast<size_t>(w.pu);
   return DAB_OK;
 }
 
@@ -1001,7 +889,7 @@ int dab_ipa_pair_bias_multi(const DabIpaDims* d, const void* e_bf16, const float
 static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
                           const void* bias_f16, const float* R, const float* t, float* y, void* workspace,
                           size_t workspace_bytes, bool save_for_bwd, void* stream, const void* x_bf16 = nullptr,
-                          void* y_bf16 = nullptr) {
+                          void* y_bf16 = nullptr, int phases = 7) {
   DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
               "dab_ipa_fwd_sm100: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
   if (d->B == 0) return DAB_OK;
@@ -1017,7 +905,6 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
   const PackedOffsets po = packed_offsets();
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
   cudaStream_t s = (cudaStream_t)stream;
-  const int phases = phase_mask();
   if (phases & 1) {
     CUtensorMap mw64, mw48;
     uint64_t dw[2] = {(uint64_t)D, (uint64_t)NPROJ}, sw[1] = {(uint64_t)D * 2};
@@ -1119,26 +1006,32 @@ int dab_ipa_fwd_sm100_train(const DabIpaDims* d, const void* packed, const float
   return fwd_sm100_impl(d, packed, x, e_bf16, bias_f16, R, t, y, saved, saved_bytes, true, stream);
 }
 
-/* Profiling hook: per-CTA clock64 timeline of the attention core (64 slots per CTA), NULL to disable. */
+/* The same layer launch by launch: `stages` = bit0 projections + frame transform, bit1 attention core, bit2 to_out.  The
+ * workspace must hold the products of the earlier stages (a previous call with the lower bits).  Lets a caller bracket one
+ * stage with its own events (bench.py's roofline of the attention core) or interleave its own work between the stages. */
+int dab_ipa_fwd_sm100_stages(const DabIpaDims* d, const void* packed, const float* x, const void* x_bf16, const void* e_bf16,
+                             const void* bias_f16, const float* R, const float* t, float* y, void* y_bf16, void* workspace,
+                             size_t workspace_bytes, int stages, void* stream) {
+  DAB_REQUIRE((x == nullptr) != (x_bf16 == nullptr) && (y == nullptr) != (y_bf16 == nullptr), DAB_EINVAL,
+              "dab_ipa_fwd_sm100_stages: give exactly one of x / x_bf16 and one of y / y_bf16");
+  DAB_REQUIRE(stages > 0 && stages <= 7, DAB_EINVAL, "dab_ipa_fwd_sm100_stages: stages must be a non-empty subset of bits 0..2");
+  return fwd_sm100_impl(d, packed, x, e_bf16, bias_f16, R, t, y, workspace, workspace_bytes, false, stream, x_bf16, y_bf16,
+                        stages);
+}
+
+/* C[M,N] = A[M,K] B[N,K]^T + bias on the tcgen05 GEMM (bf16 operands, fp32 result; M % 128 == 0, N % 64 == 0, K % 64 == 0):
+ * the nn.Linear of diffab_pytorch.py:464 as a stand-alone entry point. */
+int dab_gemm_bf16(const void* A, const void* Bm, float* Cm, const float* bias, int M, int N, int K, void* stream) {
+  DAB_REQUIRE(A && Bm && Cm, DAB_EINVAL, "dab_gemm_bf16: null pointer");
+  return launch_gemm_bf16<64>(A, K, Bm, K, Cm, N, bias, M, N, K, (cudaStream_t)stream);
+}
+
+#ifdef DAB_DEBUG_HOOKS
+/* Profiling hook (debug build only): per-tile clock64 timeline of the attention core (64 slots per tile), NULL to disable. */
 int dab_debug_set_timeline(long long* buf) {
   g_core_dbg = buf;
   return DAB_OK;
 }
-
-/* Test hook: C[M,N] = A[M,K] B[N,K]^T + bias on the tcgen05 GEMM (bf16 in, fp32 out). */
-int dab_debug_gemm_bf16(const void* A, const void* Bm, float* Cm, const float* bias, int M, int N, int K, void* stream) {
-  DAB_REQUIRE(A && Bm && Cm, DAB_EINVAL, "dab_debug_gemm_bf16: null pointer");
-  return launch_gemm_bf16<64>(A, K, Bm, K, Cm, N, bias, M, N, K, (cudaStream_t)stream);
-}
-
-/* Test hook: run only the packing stage on a given fp32 projection tensor. */
-int dab_debug_ipa_pack(const float* proj, const float* R, const float* t, const float* gamma, int B, void* Qp, void* Kp,
-                       void* Vp, float* tc, void* stream) {
-  DAB_REQUIRE(proj && R && t && gamma && Qp && Kp && Vp && tc && B > 0, DAB_EINVAL, "dab_debug_ipa_pack: bad argument");
-  ipa_pack_kernel<<<dim3(L / 16, B), 128, 0, (cudaStream_t)stream>>>(proj, R, t, gamma, (__nv_bfloat16*)Qp,
-                                                                      (__nv_bfloat16*)Kp, (__nv_bfloat16*)Vp, tc);
-  count_launch();
-  return check_launch("dab_debug_ipa_pack");
-}
+#endif
 
 }  // extern "C"

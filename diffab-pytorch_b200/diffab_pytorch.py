@@ -321,7 +321,7 @@ class PairEmbedding(nn.Module):
               self.distance_embedding[0].weight, self.distance_embedding[0].bias, self.distance_embedding[2].weight,
               self.distance_embedding[2].bias, self.mlp[0].weight, self.mlp[0].bias, self.mlp[2].weight,
               self.mlp[2].bias, self.mlp[4].weight, self.mlp[4].bias)
-        key = tuple((w.data_ptr(), w._version) for w in ws)
+        key = tuple((w.data_ptr(), w._version) for w in ws) + (_lib.weight_generation(),)
         if getattr(self, "_packed", None) is None or self._packed[0] != key:
             buf = _lib.aligned_empty(lib.dab_pair_embed_packed_bytes(), xyz.device)
             wd = [_lib.dev(w.detach(), torch.float32, "pair embedding weight") for w in ws]
@@ -511,7 +511,7 @@ class _IpaFastFunction(torch.autograd.Function):
         M = B * L
         dims = _ipa_structs(layer, B, L)
         lib = _lib.lib()
-        offs = (ctypes.c_size_t * 7)()
+        offs = (ctypes.c_size_t * 8)()
         _lib.check(lib.dab_ipa_sm100_workspace_layout(ctypes.byref(dims), offs), "dab_ipa_sm100_workspace_layout")
         w_out = weights[8]
         ncat = w_out.shape[1]
@@ -607,11 +607,17 @@ class InvariantPointAttentionLayer(nn.Module):
 
     def _packed_weights(self, dims):
         ws = self._weights()
-        key = tuple((w.data_ptr(), w._version) for w in ws)
-        if self._packed is None or self._packed[0] != key:
+        key = tuple((w.data_ptr(), w._version) for w in ws) + (_lib.weight_generation(),)
+        # Training (gradients recorded): always repack - the call may be part of a CUDA-graph capture whose replays follow
+        # optimizer steps that no Python-side version counter sees, and the pack kernel costs a few microseconds.
+        training = torch.is_grad_enabled() and any(w.requires_grad for w in ws)
+        if training or self._packed is None or self._packed[0] != key:
             lib = _lib.lib()
             nbytes = lib.dab_ipa_packed_bytes(ctypes.byref(dims))
-            buf = _lib.aligned_empty(max(nbytes, 16), ws[0].device)
+            if self._packed is not None and self._packed[1].device == ws[0].device:
+                buf = self._packed[1]          # repack in place (stable address: graph captures keep pointing at it)
+            else:
+                buf = _lib.aligned_empty(max(nbytes, 16), ws[0].device)
             wstruct = _weights_struct([_lib.dev(w.detach(), torch.float32, "weight") for w in ws])
             _lib.check(lib.dab_ipa_pack_weights(ctypes.byref(dims), ctypes.byref(wstruct), ptr(buf), _lib.stream_ptr()),
                        "dab_ipa_pack_weights")
@@ -1144,7 +1150,8 @@ class DiffAb(nn.Module):
                             generation_mask, noises=None, generator=None, t_start=None, t_stop=1,
                             use_cuda_graph=False):
         """The reverse loop t_start..t_stop on resident tensors (this is what bench.py's ``value`` times).
-        ``pair_context_emb`` may be fp32 (exact path) or bf16 (tensor-core path)."""
+        ``pair_context_emb`` may be fp32 (exact path) or bf16 (tensor-core path).  ``noises`` = {t: draws of step t}
+        (``draw_step_noise``) injects every random draw (parity tests); it works with and without CUDA graphs."""
         T = self.T
         t_start = T if t_start is None else t_start
         s, x, O = seq_idx.clone(), translations.clone().contiguous(), orientations.clone().contiguous()
@@ -1152,9 +1159,9 @@ class DiffAb(nn.Module):
         dev = s.device
         _ = self.so3_reverse.histograms  # build the table outside any capture
         with _tf32_matmuls(pair_context_emb.dtype == torch.bfloat16):
-            if use_cuda_graph and noises is None:
+            if use_cuda_graph and generator is None:
                 return self._sample_graphed(s, x, O, res_context_emb, pair_context_emb, generation_mask, t_start,
-                                            t_stop)
+                                            t_stop, noises)
             pair_bias = self._pair_bias_planes(pair_context_emb)
             glue = self.denoiser.sampling_cache(res_context_emb) if pair_context_emb.dtype == torch.bfloat16 else None
             for step in range(t_start, t_stop - 1, -1):
@@ -1172,15 +1179,26 @@ class DiffAb(nn.Module):
             return None
         return self.denoiser.ipa.precompute_pair_bias(pair_ctx)
 
-    def _sample_graphed(self, s, x, O, res_ctx, pair_ctx, generation_mask, t_start, t_stop):
-        """One reverse step captured in a CUDA graph and replayed; the step index lives in a device tensor.
-        The graph works on static buffers (state, context, mask, pair-bias planes) and is cached per shape, so
-        repeated ``sample()`` calls only copy their context in (~1 GB device-to-device, well under a millisecond)."""
+    @staticmethod
+    def _fill_noise_(bufs):
+        """Redraw static noise buffers in place (same distributions as ``draw_step_noise``)."""
+        bufs["seq_exp"].exponential_(); bufs["z"].normal_(); bufs["axis"].normal_()
+        bufs["hist_exp"].exponential_(); bufs["jitter"].uniform_(); bufs["gauss"].normal_()
+
+    def _sample_graphed(self, s, x, O, res_ctx, pair_ctx, generation_mask, t_start, t_stop, noises=None):
+        """Reverse steps captured in CUDA graphs and replayed; the step index lives in a device tensor.
+        The graphs work on static buffers (state, context, mask, pair-bias planes, noise) and are cached per shape and
+        weight generation, so repeated ``sample()`` calls only copy their context in (~1 GB device-to-device, well
+        under a millisecond).  Two step graphs: one reverse step, and a block of ``graph_block_steps`` consecutive
+        steps; each reads its random draws from static buffers that a small companion graph redraws before every
+        replay - or that the caller's ``noises`` are copied into (injected draws, parity tests)."""
         B, L = s.shape
         dev = s.device
-        # the captured graph bakes in packed weights and per-run weight products: recapture when any parameter changed
+        # the captured graphs bake in packed weights and per-run weight products: recapture when any parameter changed
+        # (in-place updates bump _version; updates replayed from a CUDA graph bump the library-wide weight generation)
         wkey = tuple((p.data_ptr(), p._version) for p in self.denoiser.parameters())
-        key = (B, L, tuple(res_ctx.shape), tuple(pair_ctx.shape), pair_ctx.dtype, str(dev), wkey)
+        key = (B, L, tuple(res_ctx.shape), tuple(pair_ctx.shape), pair_ctx.dtype, str(dev), wkey,
+               _lib.weight_generation())
         cache = getattr(self, "_graph_cache", None)
         fresh = cache is None or cache["key"] != key
         if fresh:
@@ -1188,7 +1206,7 @@ class DiffAb(nn.Module):
                      "t": torch.full((B,), t_start, device=dev, dtype=torch.int64),
                      "res": torch.empty_like(res_ctx), "pair": torch.empty_like(pair_ctx),
                      "mask": torch.empty_like(generation_mask), "bias": None, "graph": None, "glue": None,
-                     "graph_block": None}
+                     "graph_block": None, "noise1": self.draw_step_noise(B, L, dev)}
         st = cache
         st["res"].copy_(res_ctx); st["pair"].copy_(pair_ctx); st["mask"].copy_(generation_mask)
         if pair_ctx.dtype == torch.bfloat16:   # per-layer pair-bias planes, written straight into the static buffers
@@ -1204,17 +1222,18 @@ class DiffAb(nn.Module):
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 for _ in range(2):  # warm-up outside capture (allocator, lazy init, weight packing)
+                    self._fill_noise_(st["noise1"])
                     self.reverse_step(st["s"].clone(), st["x"].clone(), st["O"].clone(), st["res"], st["pair"],
-                                      st["mask"], st["t"], self.draw_step_noise(B, L, dev), pair_bias=st["bias"],
-                                      glue_cache=st["glue"])
+                                      st["mask"], st["t"], st["noise1"], pair_bias=st["bias"], glue_cache=st["glue"])
             torch.cuda.current_stream(dev).wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                noise = self.draw_step_noise(B, L, dev)
-                self.reverse_step(st["s"], st["x"], st["O"], st["res"], st["pair"], st["mask"], st["t"], noise,
+            draw, graph = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(draw):
+                self._fill_noise_(st["noise1"])
+            with torch.cuda.graph(graph, pool=draw.pool()):
+                self.reverse_step(st["s"], st["x"], st["O"], st["res"], st["pair"], st["mask"], st["t"], st["noise1"],
                                   inplace=True, pair_bias=st["bias"], glue_cache=st["glue"])
                 st["t"].sub_(1)
-            st["graph"] = graph
+            st["graph"], st["draw"] = graph, draw
             self._graph_cache = st
         # Long runs replay a second graph that holds `graph_block_steps` consecutive steps: their random draws are six
         # launches per block instead of six per step (9 of the 32 launches of a step are PyTorch RNG / index kernels).
@@ -1222,28 +1241,57 @@ class DiffAb(nn.Module):
         n_steps = t_start - t_stop + 1
         n_blocks = n_steps // U if U > 1 else 0
         if n_blocks > 0 and (st["graph_block"] is None or st["graph_block"][0] != U):
-            block = torch.cuda.CUDAGraph()
             st["s"].copy_(s); st["x"].copy_(x); st["O"].copy_(O)
             st["t"].fill_(t_start)
-            # (a graph input: must live as long as the graph, so it is kept in the cache next to it)
+            # (graph inputs: must live as long as the graphs, so they are kept in the cache next to them)
             st["steps_back"] = steps_back = torch.arange(U, device=dev, dtype=torch.int64)[:, None]
-            with torch.cuda.graph(block):
-                noises = self.draw_block_noise(U, B, L, dev)
+            st["noiseU"] = noiseU = self.draw_block_noise(U, B, L, dev)
+            draw_block, block = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(draw_block, pool=st["draw"].pool()):
+                self._fill_noise_(noiseU)
+            with torch.cuda.graph(block, pool=st["draw"].pool()):
                 t_blk = st["t"][None, :] - steps_back                  # (U, B): the block's step indices ...
                 beta_blk = self.dsched.tensors["beta"][t_blk]          # ... and betas, one gather per block
                 for u in range(U):
                     self.reverse_step(st["s"], st["x"], st["O"], st["res"], st["pair"], st["mask"], t_blk[u],
-                                      {k: v[u] for k, v in noises.items()}, inplace=True, pair_bias=st["bias"],
+                                      {k: v[u] for k, v in noiseU.items()}, inplace=True, pair_bias=st["bias"],
                                       glue_cache=st["glue"], beta=beta_blk[u])
                 st["t"].sub_(U)
-            st["graph_block"] = (U, block)
+            st["graph_block"] = (U, block, draw_block)
         st["s"].copy_(s); st["x"].copy_(x); st["O"].copy_(O)
         st["t"].fill_(t_start)
+        step = t_start
         for _ in range(n_blocks):
+            if noises is None:
+                st["graph_block"][2].replay()
+            else:
+                for k, buf in st["noiseU"].items():
+                    for u in range(U):
+                        buf[u].copy_(noises[step - u][k].view_as(buf[u]))
             st["graph_block"][1].replay()
+            step -= U
         for _ in range(n_steps - n_blocks * U):
+            if noises is None:
+                st["draw"].replay()
+            else:
+                for k, buf in st["noise1"].items():
+                    buf.copy_(noises[step][k].view_as(buf))
             st["graph"].replay()
+            step -= 1
         return {"seq_idx": st["s"].clone(), "translations": st["x"].clone(), "orientations": st["O"].clone()}
+
+    def invalidate_weight_caches(self):
+        """Forget every weight-derived cache (packed bf16 weights, glue constants, captured sampling graphs).  Needed after
+        weight updates PyTorch cannot see - optimizer steps replayed from a CUDA graph, raw ``.data`` writes: in-place
+        updates made eagerly bump the parameters' version counters and are noticed without this call.
+        ``distributed.GraphedTrainStep`` calls the library-wide equivalent (``_lib.bump_weight_generation``)."""
+        _lib.bump_weight_generation()
+        self._graph_cache = None
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_weight_caches()
+        return out
 
     @torch.no_grad()
     def sample(self, seq_idx, xyz, orientations, backbone_dihedrals=None, distmat=None, pairwise_dihedrals=None,

@@ -195,6 +195,8 @@ class GraphedTrainStep:
     def __call__(self) -> torch.Tensor:
         """One optimisation step; returns this rank's share of the global loss (sum over ranks = global loss), as a
         1-element device tensor that the next call overwrites."""
+        from . import _lib
+        _lib.bump_weight_generation()      # the replayed optimizer step changes weights without touching their versions
         self.graph_a.replay()
         if self.world > 1:
             self._reduce_part()

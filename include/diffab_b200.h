@@ -41,10 +41,6 @@ int dab_version(void);
 const char* dab_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's "gpu_launches" claim). */
 long long dab_launch_count(void);
-/* Measurement aid: restrict dab_ipa_fwd_* to a subset of its launches (bit0 projections + frame
- * transform, bit1 attention core, bit2 to_out) so bench.py can bracket the dominant kernel alone with
- * CUDA events; the workspace must hold the products of an earlier full call.  Default 7 (all). */
-int dab_debug_set_phase_mask(int mask);
 
 /* ------------------------------------------------------------------ SO(3) maps, so3.py:142-259 */
 /* vector_to_rotation_matrix (so3.py:207-237): v[n,3] -> R[n,3,3], Rodrigues, no epsilon guard. */
@@ -181,6 +177,12 @@ int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, c
 int dab_ipa_fwd_sm100_io(const DabIpaDims* d, const void* packed, const float* x, const void* x_bf16, const void* e_bf16,
                          const void* bias_f16, const float* R, const float* t, float* y, void* y_bf16, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* The same layer launch by launch: `stages` = bit0 projections + frame transform, bit1 attention core, bit2 to_out; the
+ * workspace must hold the products of the lower stages (an earlier call).  For callers that bracket one stage with their
+ * own events (bench.py's roofline of the attention core) - there is no process-global measurement state in the library. */
+int dab_ipa_fwd_sm100_stages(const DabIpaDims* d, const void* packed, const float* x, const void* x_bf16, const void* e_bf16,
+                             const void* bias_f16, const float* R, const float* t, float* y, void* y_bf16, void* workspace,
+                             size_t workspace_bytes, int stages, void* stream);
 /* Training pair of the sm_100a path (bf16 pair tensor, fp32 x / y).  The forward is dab_ipa_fwd_sm100 (the pair
  * bias is rebuilt inside the call when bias_f16 is NULL); `saved` (dab_ipa_sm100_workspace_bytes) additionally keeps
  * the packed operands, the concat features, the un-normalised probabilities and the softmax statistics, and must
@@ -196,14 +198,16 @@ int dab_ipa_fwd_sm100_train(const DabIpaDims* d, const void* packed, const float
  *        dWcat = dproj^T . x are plain GEMMs of the caller), de_bf16[B,L,L,C] bf16 (overwritten),
  *        d_w_pair_bias[8,64] and d_gamma[8] (accumulated into).
  * R and t are treated as constants, as in dab_ipa_bwd_f32. */
-int dab_ipa_sm100_workspace_layout(const DabIpaDims* d, size_t* offsets /* 7: Qp, Kp, Vp, tc, cat, bias, stats */);
+int dab_ipa_sm100_workspace_layout(const DabIpaDims* d, size_t* offsets /* 8: Qp, Kp, Vp, tc, cat, bias, stats, pu */);
 size_t dab_ipa_bwd_sm100_workspace_bytes(const DabIpaDims* d);
 int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf16, const float* R, const float* dcat,
                       void* saved, size_t saved_bytes, void* dproj_bf16, void* de_bf16, float* d_w_pair_bias, float* d_gamma,
                       void* workspace, size_t workspace_bytes, void* stream);
+#ifdef DAB_DEBUG_HOOKS /* debug build only (make debug -> libdiffab_b200_dbg.so): process-global profiling / inspection hooks */
 int dab_debug_set_bwd_timeline(long long* device_buf /* 64 slots per CTA of the backward core, or NULL */);
 int dab_debug_bwd_keep_qkv(int on);
 int dab_debug_bwd_sm100_buffers(const DabIpaDims* d, void* workspace, void** out /* 10 device pointers */);
+#endif
 /* ------------------------------------------------------------------ epsilon-network tail
  * The three denoising heads of Denoiser.forward (diffab_pytorch.py:584-599) for d_residue_emb = 128, L = 128, fused
  * into one tcgen05 kernel: [x | beta, sin beta, cos beta] -> MLP(131 -> 128 -> 128 -> {3, 3, 21}) x 3, softmax on
@@ -288,12 +292,12 @@ int dab_losses_bwd(const float* post_pred, const float* post_tgt, const float* e
                    const float* O_true, const uint8_t* mask, int64_t n, const float* g, const float* fwd_out, float* d_post,
                    float* d_eps, float* d_O, void* stream);
 
-/* Test hooks of the sm_100a path (used by tests/ only): the tcgen05 GEMM C[M,N] = A[M,K] B[N,K]^T + bias
- * (bf16 in, fp32 out; M % 128 == 0, N % 64 == 0, K % 64 == 0) and the operand-packing stage alone. */
-int dab_debug_set_timeline(long long* device_buf /* 64 slots per CTA of the attention core, or NULL */);
-int dab_debug_gemm_bf16(const void* A, const void* Bm, float* C, const float* bias, int M, int N, int K, void* stream);
-int dab_debug_ipa_pack(const float* proj, const float* R, const float* t, const float* gamma, int B, void* Qp, void* Kp,
-                       void* Vp, float* tc, void* stream);
+/* The tcgen05 GEMM C[M,N] = A[M,K] B[N,K]^T + bias (bf16 in, fp32 out; M % 128 == 0, N % 64 == 0, K % 64 == 0): nn.Linear
+ * (diffab_pytorch.py:464) as a stand-alone entry point. */
+int dab_gemm_bf16(const void* A, const void* Bm, float* C, const float* bias, int M, int N, int K, void* stream);
+#ifdef DAB_DEBUG_HOOKS /* debug build only */
+int dab_debug_set_timeline(long long* device_buf /* 64 slots per tile of the attention core, or NULL */);
+#endif
 /* fp32 -> bf16 conversion of the pair tensor (once per patch; round-to-nearest-even). */
 int dab_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
 

@@ -16,6 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "diffab_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"#ifdef DAB_DEBUG_HOOKS.*?#endif", "", text, flags=re.S)     # debug build only (libdiffab_b200_dbg.so)
     return sorted(set(re.findall(r"\b(dab_[a-z0-9_]+)\s*\(", text)))
 
 
@@ -32,12 +33,19 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_integration_guide_names_every_entry_point():
-    """INTEGRATION.md is the binding surface a reference maintainer reads: every exported entry point (the debug hooks
-    as a family) must appear there next to the reference function it replaces."""
+    """INTEGRATION.md is the binding surface a reference maintainer reads: every exported entry point must appear there
+    next to the reference function it replaces."""
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
-    missing = [n for n in _declared_symbols() if not n.startswith("dab_debug") and n not in doc]
+    missing = [n for n in _declared_symbols() if n not in doc]
     assert not missing, missing
-    assert "dab_debug_" in doc
+
+
+def test_product_library_has_no_debug_hooks():
+    """The process-global profiling hooks live in the debug build only (make -C csrc debug)."""
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    assert not any(n.startswith("dab_debug") for n in _declared_symbols())
+    for name in _lib.DEBUG_EXPORTS:
+        assert not hasattr(handle, name), name
 
 
 def test_workspace_queries_run_without_a_gpu():

@@ -1,0 +1,205 @@
+"""GPU parity of the BENCHMARKED sampling path (bf16 tensor-core kernels, CUDA graphs) against the oracle sampler.
+
+The oracle (oracle/sampler.py + oracle/ipa.py, fp64, evaluated on the bf16-rounded pair tensor so that only the kernels'
+own error is measured) free-runs two windows of the reverse process, t = 100..96 and t = 10..6.  At every step the GPU
+takes the ORACLE's input state and the same injected draws and must reproduce the oracle's output state (teacher
+forcing: sampling is chaotic, a single legitimate near-tie flip would otherwise decorrelate everything after it):
+
+* eager and CUDA-graph replays of the step are bit-identical to each other;
+* C-alpha and rotation errors stay within the stated bounds;
+* sequences are EQUAL except where the oracle's own top-2 margin of p / Exp(1) is smaller than twice the measured
+  relative error of the bf16 posterior (the only residues whose argmax can legitimately move), and that error is
+  itself bounded.
+
+A free-running 25-step pass (one replay of the 20-step block graph + five single-step replays) must equal the eager loop
+bit for bit under the same injected draws.  The logits of the tensor-core layer are checked against the oracle's logits
+to north_star's 2e-2 bound, rebuilt from what the training forward saves (un-normalised probabilities + row maxima).
+"""
+import ctypes
+
+import pytest
+import torch
+
+from conftest import load_golden
+from diffab_pytorch_b200 import _lib, synth
+from diffab_pytorch_b200.diffab_pytorch import (DiffAb, InvariantPointAttentionLayer, _ipa_structs, cast_pair_to_bf16)
+from oracle import diffusion as odiff
+from oracle import ipa as oipa
+from oracle import sampler as osamp
+from oracle import so3 as oso3
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TRAIN = (128, 64, 6, 32, 8, 8, 8)
+
+# Bounds per window (measured on B200 in the comments; profiles/r02_parity_report.txt).  The t = 10 window is the
+# regime of north_star's 2e-2 bar: frames within the patch (tens of Angstrom).  In the t = 100 window the state is the
+# N(0, I) prior pushed through 1 / sqrt(alpha_100) = 31.6 by an UNTRAINED epsilon network: generated residues sit
+# 30-100 A from everything else, the point-distance logits are c |q - k|^2 / 2 ~ 10^2..10^3 with d logit / d coordinate
+# = c |q - k|, and the bf16 rounding of the residue stream / projection weights (2^-9 relative, inherent to a bf16 path)
+# is amplified accordingly from step to step - so that window gets the looser, stated bounds and still has to keep every
+# sequence flip margin-explained.
+BOUNDS = {
+    #        posterior rel   heads max-norm   CA / step length   rotation entries
+    10:  dict(post=2e-2,     head=2e-2,       ca=1e-2,           rot=2e-2),    # measured 5.1e-3, 1.1e-2, 1.1e-3, 2.8e-3
+    100: dict(post=5e-2,     head=1.5e-1,     ca=2e-2,           rot=1e-1),    # measured 3.3e-2, 1.0e-1, 2.3e-3, 3.6e-2
+}
+
+
+def _to(d):
+    return {k: v.to(DEV) for k, v in d.items()}
+
+
+def _setup(B=2, seed=9):
+    model = DiffAb(*TRAIN, device=DEV).eval()
+    model.load_state_dict(synth.synthetic_state(load_golden("state_shapes.pt"), seed=0))
+    batch = synth.make_patches(B, 128, seed=seed)
+    b = _to(batch)
+    with torch.no_grad():
+        res, pair = model.encode_context(b["seq_idx"], b["xyz"], b["orientations"], b["backbone_dihedrals"],
+                                         b["distmat"], b["pairwise_dihedrals"], b["atom_mask"], b["chain_idx"],
+                                         b["residue_idx"], b["generation_mask"], b["residue_mask"])
+        pair16 = cast_pair_to_bf16(pair)
+    return model, batch, b, res, pair16
+
+
+def _oracle_step(state64, sched, hist_rev, s, x, O, res64, pair64, mask, step, noise):
+    B = s.shape[0]
+    t = torch.full((B,), step, dtype=torch.long)
+    den = oipa.denoiser_forward(state64, s, x.double(), O.double(), res64, pair64, sched["beta"][t].double(), TRAIN[2],
+                                TRAIN[6])
+    nxt = osamp.reverse_step(sched, hist_rev, s, x.double(), O.double(), den["translations_eps"], den["orientations_t0"],
+                             den["seq_posterior"], mask, t, {k: v.double() if v.dtype.is_floating_point else v
+                                                             for k, v in noise.items()})
+    key = den["seq_posterior"].reshape(-1, 21) / noise["seq_exp"].double()
+    top2 = key.topk(2, dim=-1).values
+    margin = ((top2[:, 0] - top2[:, 1]) / top2[:, 0]).view(B, -1)
+    return nxt, den, margin
+
+
+@pytest.mark.parametrize("t_start", [100, 10])
+def test_bf16_graph_step_vs_oracle_teacher_forced(t_start):
+    model, batch, b, res, pair16 = _setup()
+    B, L = batch["seq_idx"].shape
+    m = batch["generation_mask"]
+    gen = torch.Generator().manual_seed(40 + t_start)
+    sched = odiff.cosine_schedule(100, s=0.01, beta_max=0.999)
+    hist_rev = model.so3_reverse.histograms.cpu()
+    state64 = {k: v.detach().cpu().double() for k, v in model.state_dict().items()}
+    res64, pair64 = res.cpu().double(), pair16.float().cpu().double()
+    if t_start == 100:
+        s, x, O = osamp.draw_initial_state(batch["seq_idx"], batch["xyz"][:, :, 1], batch["orientations"], m, generator=gen)
+    else:   # a state of the forward process at t_start (reference noising, oracle/diffusion.py)
+        torch.manual_seed(7)
+        noised = odiff.add_noise(sched, model.orientation_diffuser.so3.histograms.cpu(), batch["seq_idx"],
+                                 batch["xyz"][:, :, 1], batch["orientations"], m, torch.full((B,), t_start),
+                                 odiff.draw_add_noise_tensors(B, L))
+        s, x, O = noised["seq_idx_t"], noised["translations_t"], noised["orientations_t"]
+    glue = model.denoiser.sampling_cache(res)
+    planes = model._pair_bias_planes(pair16)
+    bound = BOUNDS[t_start]
+    worst = {"post_rel": 0.0, "ca_rel": 0.0, "rot_abs": 0.0, "flips": 0, "generated": 0}
+    for step in range(t_start, t_start - 5, -1):
+        noise = osamp.draw_step_noise(B, L, generator=gen)
+        ref, den, margin = _oracle_step(state64, sched, hist_rev, s, x, O, res64, pair64, m, step, noise)
+        args = (s.to(DEV), x.float().to(DEV), O.float().to(DEV), res, pair16, b["generation_mask"])
+        kw = dict(noises={step: _to(noise)}, t_start=step, t_stop=step)
+        eager = model.sample_from_context(*args, use_cuda_graph=False, **kw)
+        graph = model.sample_from_context(*args, use_cuda_graph=True, **kw)
+        for k in eager:
+            assert torch.equal(eager[k], graph[k]), (step, k)            # graph replay == eager launch sequence
+        # posterior of the bf16 path vs the oracle's (what decides which sequence flips are legitimate)
+        t_dev = torch.full((B,), step, device=DEV, dtype=torch.int64)
+        eps_g, v_g, post = model.denoiser.heads_fast(args[0], args[1], args[2], glue, pair16, model.dsched.tensors["beta"][t_dev],
+                                               planes)
+        p_ref = den["seq_posterior"]
+        big = p_ref > 1e-3
+        d_rel = float(((post.cpu().double() - p_ref).abs() / p_ref)[big].max())
+        worst["post_rel"] = max(worst["post_rel"], d_rel)
+        assert d_rel < bound["post"], (step, d_rel)
+        # sequences: equal except where the oracle's own top-2 margin is within the posterior error
+        diff = (eager["seq_idx"].cpu() != ref["seq_idx"])
+        assert not diff[~m].any()
+        allowed = margin <= 2 * d_rel / (1 - d_rel)
+        assert not (diff & ~allowed).any(), (step, int((diff & ~allowed).sum()), float(margin[diff].max()))
+        worst["flips"] += int(diff.sum()); worst["generated"] += int(m.sum())
+        # frames
+        step_len = (ref["translations"] - x.double()).norm(dim=-1)[m]
+        dx = (eager["translations"].cpu().double() - ref["translations"]).norm(dim=-1)[m]
+        ca_rel = float(dx.max() / step_len.mean())
+        # heads, max-normalised like every other bf16 bar of this repo (tests/test_gpu_ipa.py)
+        dv = float((v_g.cpu().double() - den["rotvec"]).abs().max() / den["rotvec"].abs().max())
+        de = float((eps_g.cpu().double() - den["translations_eps"]).abs().max() / den["translations_eps"].abs().max())
+        dO = float((eager["orientations"].cpu().double() - ref["orientations"]).abs().amax(dim=(-1, -2))[m].max())
+        worst["ca_rel"], worst["rot_abs"] = max(worst["ca_rel"], ca_rel), max(worst["rot_abs"], dO)
+        worst["dv"], worst["de"] = max(worst.get("dv", 0.0), dv), max(worst.get("de", 0.0), de)
+        print(f"  t={step}: post_rel {d_rel:.2e} ca_rel {ca_rel:.2e} dO {dO:.2e} dv {dv:.2e} de {de:.2e} |v|max {float(den['rotvec'].abs().max()):.2f}")
+        assert ca_rel < bound["ca"], (step, ca_rel)
+        assert dv < bound["head"] and de < bound["head"], (step, dv, de)
+        assert dO < bound["rot"], (step, dO)
+        assert torch.equal(eager["translations"].cpu()[~m], x.float()[~m])
+        s, x, O = ref["seq_idx"], ref["translations"].float(), ref["orientations"].float()   # teacher forcing
+    print(f"\n[parity t={t_start}..{t_start - 4}] bf16+graph vs fp64 oracle: posterior rel err {worst['post_rel']:.2e}, "
+          f"CA err / step length {worst['ca_rel']:.2e}, rotation entry err {worst['rot_abs']:.2e}, heads (max-normalised) rotvec {worst['dv']:.2e} eps {worst['de']:.2e}, "
+          f"margin-explained sequence flips {worst['flips']} of {worst['generated']}")
+
+
+def test_graphed_loop_equals_eager_loop_under_injected_noise():
+    """25 free-running steps: one replay of the 20-step block graph + five single-step replays vs the eager loop."""
+    model, batch, b, res, pair16 = _setup(seed=11)
+    B, L = batch["seq_idx"].shape
+    gen = torch.Generator().manual_seed(3)
+    s, x, O = osamp.draw_initial_state(batch["seq_idx"], batch["xyz"][:, :, 1], batch["orientations"],
+                                       batch["generation_mask"], generator=gen)
+    noises = {t: _to(osamp.draw_step_noise(B, L, generator=gen)) for t in range(100, 75, -1)}
+    args = (s.to(DEV), x.to(DEV), O.to(DEV), res, pair16, b["generation_mask"])
+    eager = model.sample_from_context(*args, noises=noises, t_start=100, t_stop=76, use_cuda_graph=False)
+    graph = model.sample_from_context(*args, noises=noises, t_start=100, t_stop=76, use_cuda_graph=True)
+    for k in eager:
+        assert torch.equal(eager[k], graph[k]), k
+    again = model.sample_from_context(*args, noises=noises, t_start=100, t_stop=76, use_cuda_graph=True)   # cached graphs
+    for k in eager:
+        assert torch.equal(eager[k], again[k]), k
+
+
+def test_tensor_core_logits_vs_oracle():
+    """north_star: bf16 tensor-core path <= 2e-2 on LOGITS.  The training forward keeps the un-normalised probabilities
+    2^(l - max_j l) (bf16) and the row maxima, so logits relative to their row maximum are recoverable and compared with
+    the oracle's (fp64, bf16-rounded pair tensor) - relative to the row maximum because the kernel drops the |q|^2 term,
+    which is constant over j (it cancels in the softmax)."""
+    c = load_golden("ipa_train.pt")["cfg"]
+    w = synth.synthetic_state(synth.ipa_layer_shapes(c["D"], c["C"], c["H"], c["ds"], c["Pq"], c["Pv"]), seed=c["seed"])
+    x, e, R, t = synth.make_ipa_inputs(c["B"], c["L"], c["D"], c["C"], seed=c["seed"] + 100)
+    layer = InvariantPointAttentionLayer(c["D"], c["C"], c["ds"], c["Pq"], c["Pv"], c["H"]).to(DEV)
+    layer.load_state_dict(w)
+    e16 = e.to(torch.bfloat16)
+    B, L, H = c["B"], c["L"], c["H"]
+    dims = _ipa_structs(layer, B, L)
+    lib = _lib.lib()
+    packed = layer._packed_weights(dims)
+    saved = _lib.aligned_empty(lib.dab_ipa_sm100_workspace_bytes(ctypes.byref(dims)), DEV)
+    y = torch.empty(B, L, c["D"], device=DEV)
+    xd, ed, Rd, td = x.to(DEV), e16.to(DEV), R.to(DEV), t.to(DEV)
+    _lib.check(lib.dab_ipa_fwd_sm100_train(ctypes.byref(dims), _lib.ptr(packed), _lib.ptr(xd), _lib.ptr(ed), None,
+                                           _lib.ptr(Rd), _lib.ptr(td), _lib.ptr(y), _lib.ptr(saved), saved.numel(),
+                                           _lib.stream_ptr()), "dab_ipa_fwd_sm100_train")
+    offs = (ctypes.c_size_t * 8)()
+    _lib.check(lib.dab_ipa_sm100_workspace_layout(ctypes.byref(dims), offs), "dab_ipa_sm100_workspace_layout")
+    rows = B * L
+    pu = saved[offs[7]: offs[7] + rows * L * H * 2].view(torch.bfloat16).view(B, L, L, H).float().cpu()     # [b][i][j][h]
+    stats = saved[offs[6]: offs[6] + rows * 16 * 4].view(torch.float32).view(B, L, 16).cpu()
+    wd = {k: v.double() for k, v in w.items()}
+    _, attn, logit = oipa.ipa_layer(wd, x.double(), e16.double(), R.double(), t.double(), H, return_attn=True)
+    rel_ref = (logit - logit.amax(dim=-1, keepdim=True)).permute(0, 2, 3, 1)        # (B, i, j, h), natural-log units
+    rel_gpu = torch.log(pu.double().clamp_min(1e-300))                               # ln(2^(l2 - max)) = l - max
+    live = rel_ref > -15.0                       # entries that carry probability (bf16 Pu keeps 8 bits down to 2^-126)
+    err = float((rel_gpu - rel_ref).abs()[live].max())
+    # 2e-2 (north_star) + 2^-9: the instrument's own error - the saved probability is rounded to bf16 (half an ulp = 2^-9
+    # relative = 2e-3 on its logarithm); the row maximum itself is stored exactly (p = 1)
+    assert err < 2e-2 + 2.0 ** -9, err
+    frac = float(((rel_gpu - rel_ref).abs()[live] > 1e-2).double().mean())
+    # normalisers: 1 / sum_j 2^(l - max) against the oracle's softmax denominator
+    inv = stats[..., 8:].double()
+    inv_ref = 1.0 / torch.exp(rel_ref).sum(dim=2)                                    # (B, i, h)
+    assert float(((inv - inv_ref).abs() / inv_ref).max()) < 2e-2
+    print(f"\n[logits] max |logit error| over {int(live.sum())} entries with l - max > -15: {err:.2e} ({frac:.1e} of them above 1e-2)")

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Per-tile clock64 timeline of the two-context tcgen05 attention core (GPU only): where each role waits."""
 import os, sys
+os.environ.setdefault("DAB_DEBUG_LIB", "1")   # needs the debug build: make -C diffab-pytorch_b200/csrc debug
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
