@@ -110,6 +110,8 @@ EXPORTS = {
     "dab_losses_bwd": (c_int, [c_void_p] * 7 + [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dab_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dab_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "dab_gemm_bf16_tn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    "dab_colsum_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 # present only in the debug build (libdiffab_b200_dbg.so)
@@ -122,6 +124,7 @@ DEBUG_EXPORTS = {
 
 
 _weight_generation = 0
+repack_when_capturing = False   # set by distributed.GraphedTrainStep around its captures (see _packed_weights)
 
 
 def weight_generation():
@@ -175,6 +178,11 @@ def dev(t, dtype, name):
         raise RuntimeError(f"{name}: expected a CUDA tensor - diffab_pytorch_b200 has no CPU path")
     if t.dtype != dtype:
         raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        # kernels are launched on the current device's stream (stream_ptr): a tensor that lives elsewhere would be
+        # dereferenced on the wrong GPU
+        raise RuntimeError(f"{name}: tensor is on cuda:{t.device.index} but the current device is "
+                           f"cuda:{torch.cuda.current_device()} - wrap the call in torch.cuda.device(...)")
     return t.contiguous()
 
 

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(128) forward_noise_kernel(
   if (tid < nv) {
     int b = (int)(r / L);
     int tt = (int)t[b];
+  if (tt < 0 || tt > sc.T) asm volatile("trap;");   // out-of-range timestep: the reference raises IndexError
     bool gen = mask[r] != 0;
     int s0 = (int)seq0[r];
 
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(128) seq_probs_kernel(Sched sc, int kind, cons
   if (r >= (int64_t)B * L) return;
   int b = (int)(r / L);
   int tt = (int)t[b];
+  if (tt < 0 || tt > sc.T) asm volatile("trap;");   // out-of-range timestep: the reference raises IndexError
   bool gen = mask[r] != 0;
   int s = (int)seq[r];
   if (kind == 0) {  // forward_prob_single_step
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(128) reverse_step_kernel(
   if (r >= (int64_t)B * L) return;
   int b = (int)(r / L);
   int tt = (int)t[b];
+  if (tt < 0 || tt > sc.T) asm volatile("trap;");   // out-of-range timestep: the reference raises IndexError
   bool gen = mask[r] != 0;
   bool noisy = tt > 1;
 

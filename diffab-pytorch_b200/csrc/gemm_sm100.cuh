@@ -18,17 +18,17 @@ namespace sm100 {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;   // bf16 elements per K chunk = one 128-byte swizzle atom row
-constexpr int kGemmStages = 3;
+constexpr int kGemmStages = 3;   // default ring depth (template parameter STAGES)
 
-template <int BN>
+template <int BN, int STAGES = kGemmStages>
 struct GemmSmem {
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;  // 16 KB
   static constexpr int kBBytes = BN * kGemmBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTotal = kGemmStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTotal = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, int STAGES = kGemmStages>
 __global__ void __launch_bounds__(128) gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
                                                         const __grid_constant__ CUtensorMap map_b,
                                                         float* __restrict__ C, int64_t ldc,
@@ -38,10 +38,11 @@ __global__ void __launch_bounds__(128) gemm_bf16_kernel(const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled operands need 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  using S = GemmSmem<BN>;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kGemmStages * S::kStageBytes);
-  uint64_t* empty = full + kGemmStages;
-  uint64_t* done = empty + kGemmStages;
+  using S = GemmSmem<BN, STAGES>;
+  constexpr int kStages = STAGES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint64_t* empty = full + kStages;
+  uint64_t* done = empty + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(128) gemm_bf16_kernel(const __grid_constant__ 
   constexpr uint32_t kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kGemmStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(done, 1);
     fence_barrier_init();
     tma_prefetch_desc(&map_a);
@@ -67,8 +68,8 @@ __global__ void __launch_bounds__(128) gemm_bf16_kernel(const __grid_constant__ 
     // ---- TMA producer (whole warp walks the loop, one elected lane issues): keeps the whole ring in flight, refilling a
     // slot as soon as its MMAs have read it
     for (int kc = 0; kc < nk; ++kc) {
-      const int s = kc % kGemmStages;
-      if (kc >= kGemmStages) mbar_wait(&empty[s], ((kc / kGemmStages) - 1) & 1);
+      const int s = kc % kStages;
+      if (kc >= kStages) mbar_wait(&empty[s], ((kc / kStages) - 1) & 1);
       if (elect_one()) {
         uint8_t* a = smem + s * S::kStageBytes;
         mbar_arrive_expect_tx(&full[s], S::kStageBytes);
@@ -82,8 +83,8 @@ __global__ void __launch_bounds__(128) gemm_bf16_kernel(const __grid_constant__ 
     constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, BN, 0, 0);
     const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024, kSwizzle128B);
     for (int kc = 0; kc < nk; ++kc) {
-      const int s = kc % kGemmStages;
-      mbar_wait(&full[s], (kc / kGemmStages) & 1);
+      const int s = kc % kStages;
+      mbar_wait(&full[s], (kc / kStages) & 1);
       tcgen05_fence_after_sync();
       if (elect_one()) {
         // K-major, 128B swizzle: 8-row groups are 1024 B apart (SBO); a K step of 16 bf16 is +32 B
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(128) gemm_bf16_kernel(const __grid_constant__ 
 // Host launcher.  A: [M, K] bf16 row-major (lda elements), B: [N, K] bf16 row-major (ldb), C fp32 - or, when C_bf16 is
 // given, bf16 with the same leading dimension -, M % 128 == 0,
 // N % BN == 0, K % 64 == 0.
-template <int BN>
+template <int BN, int STAGES = kGemmStages>
 int launch_gemm_bf16(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* C, int64_t ldc, const float* bias,
                      int M, int N, int K, cudaStream_t stream, void* C_bf16 = nullptr) {
   DAB_REQUIRE(M % kGemmBM == 0 && N % BN == 0 && K % kGemmBK == 0 && K > 0, DAB_EUNSUPPORTED,
@@ -154,9 +155,9 @@ int launch_gemm_bf16(const void* A, int64_t lda, const void* Bm, int64_t ldb, fl
   uint32_t box_a[2] = {kGemmBK, kGemmBM}, box_b[2] = {kGemmBK, (uint32_t)BN};
   if (int rc = make_tensor_map_bf16(&ma, A, 2, dims_a, str_a, box_a, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   if (int rc = make_tensor_map_bf16(&mb, Bm, 2, dims_b, str_b, box_b, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-  DAB_ENSURE_SMEM(gemm_bf16_kernel<BN>, GemmSmem<BN>::kTotal);
+  DAB_ENSURE_SMEM((gemm_bf16_kernel<BN, STAGES>), (GemmSmem<BN, STAGES>::kTotal));
   dim3 grid(N / BN, M / kGemmBM);
-  gemm_bf16_kernel<BN><<<grid, 128, GemmSmem<BN>::kTotal, stream>>>(ma, mb, C, ldc, bias, K,
+  gemm_bf16_kernel<BN, STAGES><<<grid, 128, GemmSmem<BN, STAGES>::kTotal, stream>>>(ma, mb, C, ldc, bias, K,
                                                                      reinterpret_cast<__nv_bfloat16*>(C_bf16));
   count_launch();
   return check_launch("gemm_bf16");

@@ -208,7 +208,7 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem[];
   long long* dbg_cta = dbg ? dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
 #define BWD_STAMP(k) do { if (dbg_cta && threadIdx.x == 0) dbg_cta[(k)] = clock64(); } while (0)
-#define BWD_STAMP_ISSUER(k) do { if (dbg_cta) dbg_cta[(k)] = clock64(); } while (0)
+#define BWD_STAMP_ISSUER(k) do { if (dbg_cta && (threadIdx.x & 31) == 0) dbg_cta[(k)] = clock64(); } while (0)
   BWD_STAMP(0);
   using S = BwdSmem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
@@ -230,7 +230,6 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
     mbar_arrive_expect_tx(&bars[BV_FULL + s], S::kVBuf);
     tma_load_2d(smem + s * S::kVBuf, &map_v, &bars[BV_FULL + s], h * V_W, b * L);
   };
-  constexpr int kL2Ahead = 6;
   if (warp == 9 && lane == 0) {
     // the producer lane initialises the barriers and starts the stage-1 loads before the CTA-wide synchronisation
     for (int i = 0; i < B_N_BARS; ++i) {
@@ -243,7 +242,8 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
     for (int h = 0; h < H; ++h)
       tma_load_2d(smem + S::kDoOff + h * 2048, &map_do, &bars[BQ_FULL], h * 64, (int)row0);
     for (int h = 0; h < S::kVBufs; ++h) load_v(h);
-    for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
+    // every pair row of the tile starts its way HBM -> L2 now: the stream runs during the dPv prologue
+    for (int r = 0; r < IB; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
   }
   // per-row constants of this CTA and the st * Wpb operand tile ([8 h][64 c] bf16, 128B-swizzled rows)
   if (tid < 128) {
@@ -286,12 +286,12 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
         mbar_arrive_expect_tx(&bars[BE_FULL + s], S::kEStage + 1024);
         tma_load_2d(smem + s * S::kEStage, &map_e, &bars[BE_FULL + s], 0, (int)((row0 + r) * L));
         tma_load_2d(smem + S::kDop + s * 1024, &map_dop, &bars[BE_FULL + s], 0, (int)((row0 + r) * H));
-        if (r + kL2Ahead < IB) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r + kL2Ahead) * L));
       }
     }
   } else if (warp == 8) {
     // ======================================= MMA issuer =======================================
-    if (lane == 0) {
+    // the whole warp walks the control flow (warp-uniform descriptors stay in uniform registers), one elected lane issues
+    {
       constexpr uint32_t kIdescDPV = make_idesc_f16(128, 16, 0, 0);
       constexpr uint32_t kIdescDPP = make_idesc_bf16(128, 16, 0, 0);
       constexpr uint32_t kIdescDE = make_idesc_bf16(128, 64, 0, 1);    // B = [dopair_i ; st Wpb], MN-major
@@ -302,17 +302,21 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
         const int s = h % S::kVBufs;
         mbar_wait(&bars[BV_FULL + s], (h / S::kVBufs) & 1);
         tcgen05_fence_after_sync();
-        const uint32_t va = smem_base + s * S::kVBuf;
-        const uint32_t oa = smem_base + S::kDoOff + h * 2048;
+        if (elect_one()) {
+          const uint32_t va = smem_base + s * S::kVBuf;
+          const uint32_t oa = smem_base + S::kDoOff + h * 2048;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint64_t da = make_smem_desc(va + k * 32, 16, 1024, kSwizzle128B);
-          uint64_t db = make_smem_desc(oa + k * 32, 16, 1024, kSwizzle128B);
-          umma_bf16(tmem + kBColDPV + h * 16, da, db, kIdescDPV, k != 0);
+          for (int k = 0; k < 4; ++k) {
+            uint64_t da = make_smem_desc(va + k * 32, 16, 1024, kSwizzle128B);
+            uint64_t db = make_smem_desc(oa + k * 32, 16, 1024, kSwizzle128B);
+            umma_bf16(tmem + kBColDPV + h * 16, da, db, kIdescDPV, k != 0);
+          }
+          umma_commit(&bars[BV_EMPTY + s]);
         }
-        umma_commit(&bars[BV_EMPTY + s]);
+        __syncwarp();
       }
-      umma_commit(&bars[BS_DONE]);
+      if (elect_one()) umma_commit(&bars[BS_DONE]);
+      __syncwarp();
       BWD_STAMP_ISSUER(2);
       // ---- stage 2
       auto issue_dpp = [&](int pos) {   // pair part of dP for the row at issue position pos
@@ -320,16 +324,19 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
         mbar_wait(&bars[BE_FULL + s], (r / S::kEStages) & 1);
         if (pos >= 3) mbar_wait(&bars[DPP_FREE + ds], ((pos / 3) - 1) & 1);
         tcgen05_fence_after_sync();
-        const uint32_t ea = smem_base + s * S::kEStage, da0 = smem_base + S::kDop + s * 1024;
+        if (elect_one()) {
+          const uint32_t ea = smem_base + s * S::kEStage, da0 = smem_base + S::kDop + s * 1024;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // N = 16: rows 8..15 of B are whatever follows the dopair tile (next ring slot or the Wpb tile) and
-          // land in accumulator columns 8..15, which nobody reads
-          uint64_t da = make_smem_desc(ea + k * 32, 16, 1024, kSwizzle128B);
-          uint64_t db = make_smem_desc(da0 + k * 32, 16, 1024, kSwizzle128B);
-          umma_bf16(tmem + kBColDPP + ds * 16, da, db, kIdescDPP, k != 0);
+          for (int k = 0; k < 4; ++k) {
+            // N = 16: rows 8..15 of B are whatever follows the dopair tile (next ring slot or the Wpb tile) and
+            // land in accumulator columns 8..15, which nobody reads
+            uint64_t da = make_smem_desc(ea + k * 32, 16, 1024, kSwizzle128B);
+            uint64_t db = make_smem_desc(da0 + k * 32, 16, 1024, kSwizzle128B);
+            umma_bf16(tmem + kBColDPP + ds * 16, da, db, kIdescDPP, k != 0);
+          }
+          umma_commit(&bars[DPP_DONE + ds]);
         }
-        umma_commit(&bars[DPP_DONE + ds]);
+        __syncwarp();
       };
       for (int k = 0; k < 3; ++k) issue_dpp(k);
       for (int k = 0; k < IB; ++k) {
@@ -339,6 +346,7 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
         mbar_wait(&bars[PCAT_READY + g * 2 + slot], (n >> 1) & 1);
         if (k >= 1) mbar_wait(&bars[DE_FREE], (k - 1) & 1);     // previous de drained out of the accumulator
         tcgen05_fence_after_sync();
+        if (elect_one()) {
         const uint32_t pc = smem_base + S::kPcat + (g * 2 + slot) * 4096;
         const uint32_t dop = smem_base + S::kDop + s * 1024;
         {
@@ -361,6 +369,8 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
         }
         umma_commit(&bars[BE_EMPTY + s]);
         umma_commit(&bars[PCAT_FREE + g * 2 + slot]);
+        }
+        __syncwarp();
         if (k + 3 < IB) issue_dpp(k + 3);
         BWD_STAMP_ISSUER(32 + k);
       }
@@ -561,7 +571,8 @@ ipa_bwd_keyside_kernel(const __grid_constant__ CUtensorMap map_pn, const __grid_
   tcgen05_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   if (warp == 4) {
-    if (lane == 0) {
+    // whole warp walks the control flow, one elected lane issues the loads and the MMAs
+    if (elect_one()) {
       const int prow = (b * H + h) * L;
       mbar_arrive_expect_tx(&bars[0], 32768 + 16384);
       tma_load_2d(smem + S::kPn, &map_pn, &bars[0], 0, prow);
@@ -572,10 +583,13 @@ ipa_bwd_keyside_kernel(const __grid_constant__ CUtensorMap map_pn, const __grid_
       tma_load_2d(smem + S::kDl + 16384, &map_dl, &bars[1], 64, prow);
       tma_load_2d(smem + S::kQ, &map_q64, &bars[1], h * QK_W, b * L);
       tma_load_2d(smem + S::kK, &map_k64, &bars[1], h * QK_W, b * L);
-      constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, 1, 1);
-      constexpr uint32_t idesc_q = make_idesc_bf16(128, 64, 0, 1);
-      mbar_wait(&bars[0], 0);
-      tcgen05_fence_after_sync();
+    }
+    __syncwarp();
+    constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, 1, 1);
+    constexpr uint32_t idesc_q = make_idesc_bf16(128, 64, 0, 1);
+    mbar_wait(&bars[0], 0);
+    tcgen05_fence_after_sync();
+    if (elect_one()) {
 #pragma unroll
       for (int k = 0; k < L / 16; ++k) {
         // A: [i][j] tile read MN-major (M = j): two 64-wide atoms 16 KB apart (LBO), 8-row (K = i) groups 1 KB apart
@@ -583,8 +597,11 @@ ipa_bwd_keyside_kernel(const __grid_constant__ CUtensorMap map_pn, const __grid_
         uint64_t db = make_smem_desc(smem_base + S::kDo + k * 2048, 1024, 1024, kSwizzle128B);
         umma_bf16(tmem, da, db, idesc_t, k != 0);
       }
-      mbar_wait(&bars[1], 0);
-      tcgen05_fence_after_sync();
+    }
+    __syncwarp();
+    mbar_wait(&bars[1], 0);
+    tcgen05_fence_after_sync();
+    if (elect_one()) {
 #pragma unroll
       for (int k = 0; k < L / 16; ++k) {
         uint64_t da = make_smem_desc(smem_base + S::kDl + k * 2048, 16384, 1024, kSwizzle128B);
@@ -600,6 +617,7 @@ ipa_bwd_keyside_kernel(const __grid_constant__ CUtensorMap map_pn, const __grid_
       }
       umma_commit(&bars[2]);
     }
+    __syncwarp();
   } else {
     // ---- epilogue: thread = residue (key row j for dV / dK, query row i for dQ), head h.  Scales, the
     //      -c q~ sum dl corrections, global -> local frame, and the result goes straight into the dproj row

@@ -67,40 +67,61 @@ static long long* g_core_dbg = nullptr;   // optional timeline buffer (dab_debug
 static constexpr long long* g_core_dbg = nullptr;
 #endif
 
-// ---- weight packing (once per layer) --------------------------------------------------------------
-__global__ void pack_weights_kernel(DabIpaWeights w, uint8_t* packed) {
+// ---- weight packing (once per weight update) -----------------------------------------------------------
+// One 32 x 32 tile of a weight matrix per block: fp32 rows in (coalesced), bf16 rows out twice - as they are
+// (Wcat [1344][128], Wout [128][1024]) and transposed through shared memory (Wcat^T [128][1344], Wout^T [1024][128],
+// the operands of the backward's data-gradient GEMMs).  Block 0 also copies the small fp32 tensors.
+__global__ void __launch_bounds__(256) pack_weights_kernel(DabIpaWeights w, uint8_t* packed) {
+  __shared__ float tile[32][33];
   const PackedOffsets o = packed_offsets();
-  __nv_bfloat16* wcat = reinterpret_cast<__nv_bfloat16*>(packed + o.wcat);
-  __nv_bfloat16* wout = reinterpret_cast<__nv_bfloat16*>(packed + o.wout);
-  const float* src[6] = {w.w_q_scalar, w.w_k_scalar, w.w_v_scalar, w.w_q_point, w.w_k_point, w.w_v_point};
-  const int rows[6] = {NS, NS, NS, NPT, NPT, NPT};
-  int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  int row0 = 0;
-  for (int s = 0; s < 6; ++s) {
-    for (int i = tid; i < rows[s] * D; i += nth) wcat[row0 * D + i] = __float2bfloat16_rn(src[s][i]);
-    row0 += rows[s];
+  constexpr int kCatTiles = (NPROJ / 32) * (D / 32);      // 42 x 4
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows per pass
+  const float* src;
+  __nv_bfloat16 *dst, *dst_t;
+  int r0, c0, ld_src, ld_dst, ld_t, row_off = 0;
+  int t = blockIdx.x;
+  if (t < kCatTiles) {
+    const int tr = t / (D / 32), tcn = t % (D / 32);
+    r0 = tr * 32; c0 = tcn * 32;
+    // source matrix of the row block: q/k/v scalars (256 rows each), q/k/v points (192 rows each); 32 divides both
+    const float* srcs[6] = {w.w_q_scalar, w.w_k_scalar, w.w_v_scalar, w.w_q_point, w.w_k_point, w.w_v_point};
+    const int seg = r0 < 3 * NS ? r0 / NS : 3 + (r0 - 3 * NS) / NPT;
+    row_off = seg < 3 ? seg * NS : 3 * NS + (seg - 3) * NPT;
+    src = srcs[seg]; ld_src = D;
+    dst = reinterpret_cast<__nv_bfloat16*>(packed + o.wcat); ld_dst = D;
+    dst_t = reinterpret_cast<__nv_bfloat16*>(packed + o.wcat_t); ld_t = NPROJ;
+  } else {
+    t -= kCatTiles;
+    const int tr = t / (NCAT / 32), tcn = t % (NCAT / 32);
+    r0 = tr * 32; c0 = tcn * 32;
+    src = w.w_out; ld_src = NCAT;
+    dst = reinterpret_cast<__nv_bfloat16*>(packed + o.wout); ld_dst = NCAT;
+    dst_t = reinterpret_cast<__nv_bfloat16*>(packed + o.wout_t); ld_t = D;
   }
-  for (int i = tid; i < D * NCAT; i += nth) wout[i] = __float2bfloat16_rn(w.w_out[i]);
-  // transposed copies (backward data-gradient GEMMs): wcat_t[d][f] = wcat[f][d], wout_t[f][d] = wout[d][f]
-  __nv_bfloat16* wcat_t = reinterpret_cast<__nv_bfloat16*>(packed + o.wcat_t);
-  __nv_bfloat16* wout_t = reinterpret_cast<__nv_bfloat16*>(packed + o.wout_t);
-  row0 = 0;
-  for (int s = 0; s < 6; ++s) {
-    for (int i = tid; i < rows[s] * D; i += nth) {
-      const int f = row0 + i / D, dd = i % D;
-      wcat_t[(size_t)dd * NPROJ + f] = __float2bfloat16_rn(src[s][i]);
-    }
-    row0 += rows[s];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = ty + 8 * k;
+    const float v = __ldg(src + (size_t)(r0 - row_off + r) * ld_src + c0 + tx);
+    tile[r][tx] = v;
+    dst[(size_t)(r0 + r) * ld_dst + c0 + tx] = __float2bfloat16_rn(v);
   }
-  for (int i = tid; i < D * NCAT; i += nth) wout_t[(size_t)(i % NCAT) * D + i / NCAT] = __float2bfloat16_rn(w.w_out[i]);
-  // raw fp32 pair-bias weights (H x C), used when a layer call arrives without a precomputed bias plane
-  float* wpb = reinterpret_cast<float*>(packed + o.wpb);
-  for (int i = tid; i < H * C; i += nth) wpb[i] = w.w_pair_bias[i];
-  float* bout = reinterpret_cast<float*>(packed + o.bout);
-  float* gam = reinterpret_cast<float*>(packed + o.gamma);
-  for (int i = tid; i < D; i += nth) bout[i] = w.b_out[i];
-  for (int i = tid; i < H; i += nth) gam[i] = w.gamma[i];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = ty + 8 * k;                              // column of the source tile = row of the transposed copy
+    dst_t[(size_t)(c0 + c) * ld_t + r0 + tx] = __float2bfloat16_rn(tile[tx][c]);
+  }
+  if (blockIdx.x == 0) {
+    // raw fp32 pair-bias weights (H x C), used when a layer call arrives without a precomputed bias plane
+    float* wpb = reinterpret_cast<float*>(packed + o.wpb);
+    for (int i = threadIdx.x; i < H * C; i += 256) wpb[i] = w.w_pair_bias[i];
+    float* bout = reinterpret_cast<float*>(packed + o.bout);
+    float* gam = reinterpret_cast<float*>(packed + o.gamma);
+    for (int i = threadIdx.x; i < D; i += 256) bout[i] = w.b_out[i];
+    for (int i = threadIdx.x; i < H; i += 256) gam[i] = w.gamma[i];
+  }
 }
+constexpr int kPackBlocks = (NPROJ / 32) * (D / 32) + (D / 32) * (NCAT / 32);   // 168 + 128
 
 // ---- attention core ---------------------------------------------------------------------------------
 // One persistent CTA per SM holds TWO tile contexts (tile = (patch, 16 query rows); local tile k of a CTA runs in
@@ -836,7 +857,7 @@ int dab_ipa_pack_weights(const DabIpaDims* d, const DabIpaWeights* w, void* pack
                   w->w_v_point && w->w_pair_bias && w->gamma && w->w_out && w->b_out,
               DAB_EINVAL, "dab_ipa_pack_weights: null pointer");
   DAB_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 1023) == 0, DAB_EINVAL, "dab_ipa_pack_weights: packed buffer must be 1024-byte aligned");
-  pack_weights_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(*w, reinterpret_cast<uint8_t*>(packed));
+  pack_weights_kernel<<<kPackBlocks, 256, 0, (cudaStream_t)stream>>>(*w, reinterpret_cast<uint8_t*>(packed));
   count_launch();
   return check_launch("dab_ipa_pack_weights");
 }
@@ -1023,6 +1044,12 @@ int dab_ipa_fwd_sm100_stages(const DabIpaDims* d, const void* packed, const floa
  * the nn.Linear of diffab_pytorch.py:464 as a stand-alone entry point. */
 int dab_gemm_bf16(const void* A, const void* Bm, float* Cm, const float* bias, int M, int N, int K, void* stream) {
   DAB_REQUIRE(A && Bm && Cm, DAB_EINVAL, "dab_gemm_bf16: null pointer");
+  // narrow N tiles and a deep ring when 64-wide tiles would leave most SMs idle (e.g. dx = dproj Wcat: N = 128, K = 1344);
+  // wide tiles when there are more than two waves of them (e.g. dcat = dy Wout: N = 1024, K = 128)
+  if (M > 0 && N % 64 == 0 && (M / kGemmBM) * (N / 64) < 148)
+    return launch_gemm_bf16<32, 6>(A, K, Bm, K, Cm, N, bias, M, N, K, (cudaStream_t)stream);
+  if (N % 128 == 0 && (M / kGemmBM) * (N / 128) >= 2 * 148)
+    return launch_gemm_bf16<128>(A, K, Bm, K, Cm, N, bias, M, N, K, (cudaStream_t)stream);
   return launch_gemm_bf16<64>(A, K, Bm, K, Cm, N, bias, M, N, K, (cudaStream_t)stream);
 }
 

@@ -291,15 +291,15 @@ __global__ void __launch_bounds__(256) pair_table_reduce_kernel(const float* __r
 
 // g_out = g_in where y > 0 else 0 (ReLU backward on bf16 rows of 64 channels), with the column sums of g_out - the bias
 // gradient of the layer - accumulated into colsum[64] in the same pass.
-__global__ void __launch_bounds__(256) relu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ g_in, const __nv_bfloat16* __restrict__ y,
-                                                              int64_t n_chunks, __nv_bfloat16* __restrict__ g_out,
+__global__ void __launch_bounds__(256) relu_bwd_colsum_kernel(const __nv_bfloat16* g_in /* may alias g_out (in-place) */, const __nv_bfloat16* __restrict__ y,
+                                                              int64_t n_chunks, __nv_bfloat16* g_out,
                                                               float* __restrict__ colsum) {
   __shared__ float s_part[256][9];
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;       // a multiple of 8: a thread keeps its 8 channels
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_chunks; idx += stride) {
     float g[8], a[8];
-    pt_unpack8(__ldg(reinterpret_cast<const uint4*>(g_in) + idx), g);
+    pt_unpack8(reinterpret_cast<const uint4*>(g_in)[idx], g);   // plain load: g_in may be g_out
     pt_unpack8(__ldg(reinterpret_cast<const uint4*>(y) + idx), a);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256) pair_zero_masked_kernel(__nv_bfloat16* __
 
 // out = sum of up to 8 bf16 tensors, accumulated in fp32, one pass (the pair-tensor gradients of the IPA layers)
 struct SumPtrs { const uint4* p[8]; };
-__global__ void __launch_bounds__(256) sum_bf16_kernel(SumPtrs src, int n_src, int64_t n_chunks, uint4* __restrict__ out) {
+__global__ void __launch_bounds__(256) sum_bf16_kernel(SumPtrs src, int n_src, int64_t n_chunks, uint4* out /* may be one of the sources */) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_chunks; idx += stride) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256) sum_bf16_kernel(SumPtrs src, int n_src, i
     for (int k = 0; k < 8; ++k) {
       if (k < n_src) {
         float v[8];
-        pt_unpack8(__ldg(src.p[k] + idx), v);
+        pt_unpack8(src.p[k][idx], v);   // plain load: `out` may be one of the sources
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] += v[e];
       }

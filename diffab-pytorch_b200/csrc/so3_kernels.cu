@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) igso3_table_kernel(const float* __restric
 constexpr int kSortThreads = 1024;
 
 __global__ void __launch_bounds__(kSortThreads) igso3_sample_kernel(
-    const float* __restrict__ hist, const float* __restrict__ sigmas, int n_bins, int n_pow2,
+    const float* __restrict__ hist, const float* __restrict__ sigmas, int n_bins, int n_sigma, int n_pow2,
     const int64_t* __restrict__ sigma_idx, int L, const float* __restrict__ axis_noise,
     const float* __restrict__ exp_noise, const float* __restrict__ jitter, const float* __restrict__ gauss,
     float thr, double binsize, float* __restrict__ rotvec, int64_t* __restrict__ bins) {
@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(kSortThreads) igso3_sample_kernel(
   int* s_idx = reinterpret_cast<int*>(smem_raw + sizeof(float) * n_pow2);
   int b = blockIdx.x;
   int64_t row = sigma_idx[b];
+  if (row < 0 || row >= n_sigma) asm volatile("trap;");   // the reference raises IndexError; here the launch fails loudly
   float sg = __ldg(sigmas + row);
   bool use_hist = sg < thr;
   bool need_sort = use_hist || bins != nullptr;
@@ -239,13 +240,9 @@ int dab_igso3_sample(const float* hist, const float* sigmas, int n_sigma, int n_
   while (n_pow2 < n_bins) n_pow2 <<= 1;
   DAB_REQUIRE(n_pow2 <= 16384, DAB_EUNSUPPORTED, "dab_igso3_sample: n_bins > 16384 does not fit shared memory");
   size_t smem = (size_t)n_pow2 * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(igso3_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
-    attr_set = true;
-  }
+  DAB_ENSURE_SMEM(igso3_sample_kernel, 16384 * 8);      // per device (the attribute is a per-device property)
   igso3_sample_kernel<<<B, kSortThreads, smem, (cudaStream_t)stream>>>(
-      hist, sigmas, n_bins, n_pow2, sigma_idx, L, axis_noise, exp_noise, jitter, gauss, sigma_threshold,
+      hist, sigmas, n_bins, n_sigma, n_pow2, sigma_idx, L, axis_noise, exp_noise, jitter, gauss, sigma_threshold,
       3.14159265358979323846 / (double)n_bins, rotvec, bins);
   count_launch();
   return check_launch("dab_igso3_sample");

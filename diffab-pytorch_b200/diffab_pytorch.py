@@ -473,8 +473,9 @@ class _PairFanOut(torch.autograd.Function):
 
 class _IpaFastFunction(torch.autograd.Function):
     """bf16 tensor-core IPA layer with gradients: ``dab_ipa_fwd_sm100_train`` / ``dab_ipa_bwd_sm100``.
-    The four plain GEMMs of the backward (through ``to_out`` and through the six projections) are library
-    GEMMs (TF32); everything between them runs in the library's tcgen05 kernels."""
+    Every GEMM of the backward runs in the library's tcgen05 kernels too: the data gradients through ``to_out`` and the
+    six projections on the K-major GEMM (``dab_gemm_bf16``), the weight gradients on the MN-major split-K GEMM
+    (``dab_gemm_bf16_tn``) - bf16 operands, fp32 accumulation."""
 
     @staticmethod
     def forward(ctx, layer, pair_bias, x, e, r, t, *weights):
@@ -515,33 +516,49 @@ class _IpaFastFunction(torch.autograd.Function):
         _lib.check(lib.dab_ipa_sm100_workspace_layout(ctypes.byref(dims), offs), "dab_ipa_sm100_workspace_layout")
         w_out = weights[8]
         ncat = w_out.shape[1]
-        cat = saved[offs[4]: offs[4] + M * ncat * 2].view(torch.bfloat16).view(M, ncat)
-        dy2 = _lib.dev(dy, torch.float32, "dy").view(M, D)
-        # the four plain GEMMs of the backward: library GEMMs on bf16 operands with fp32 accumulation and output
-        # (the forward ran the same products on bf16 operands)
-        bf = torch.bfloat16
-        # bf16 copies of the weights as the forward used them (rows of Wcat: q/k/v scalars, q/k/v points)
+        dev_ = x.device
+        bf, f32 = torch.bfloat16, torch.float32
+        st = _lib.stream_ptr()
+        cat = saved[offs[4]: offs[4] + M * ncat * 2].view(bf).view(M, ncat)
+        dy2 = _lib.dev(dy, f32, "dy").view(M, D)
+        # bf16 copies of the weights as the forward used them, and their transposes (rows of Wcat: q/k/v scalars, q/k/v points)
         poffs = (ctypes.c_size_t * 7)()
         _lib.check(lib.dab_ipa_packed_layout(ctypes.byref(dims), poffs), "dab_ipa_packed_layout")
         n_proj = sum(w.shape[0] for w in weights[:6])
-        w_cat_bf = packed[poffs[0]: poffs[0] + n_proj * D * 2].view(bf).view(n_proj, D)
-        w_out_bf = packed[poffs[1]: poffs[1] + D * ncat * 2].view(bf).view(D, ncat)
-        dy_bf = dy2.to(bf)
-        dcat = torch.mm(dy_bf, w_out_bf, out_dtype=torch.float32)              # (M, 1024)
-        d_w_out = torch.mm(dy_bf.t(), cat, out_dtype=torch.float32)            # (D, 1024)
-        d_b_out = torch.mv(dy2.t(), torch.ones(M, device=dy2.device))   # a 4 us gemv; a column reduction takes 13 us here
-        dproj = torch.empty(M, n_proj, device=x.device, dtype=bf)
+        w_cat_t = packed[poffs[5]: poffs[5] + D * n_proj * 2]        # Wcat^T [D][n_proj] bf16
+        w_out_t = packed[poffs[6]: poffs[6] + ncat * D * 2]          # Wout^T [ncat][D] bf16
+
+        def cast(t_):
+            out_ = torch.empty(t_.shape, device=dev_, dtype=bf)
+            _lib.check(lib.dab_cast_f32_to_bf16(ptr(t_), ptr(out_), t_.numel(), st), "dab_cast_f32_to_bf16")
+            return out_
+
+        # The plain GEMMs of the backward all run in the library on bf16 operands with fp32 accumulation and output (the
+        # forward ran the same products on bf16 operands): data gradients on the K-major tcgen05 GEMM against the
+        # transposed weight copies, weight gradients on the MN-major split-K GEMM straight from the activations.
+        dy_bf = torch.empty(M, D, device=dev_, dtype=bf)
+        d_b_out = torch.empty(D, device=dev_, dtype=f32)
+        _lib.check(lib.dab_colsum_f32(ptr(dy2), M, D, ptr(d_b_out), ptr(dy_bf), st), "dab_colsum_f32")   # + bf16 copy of dy
+        dcat = torch.empty(M, ncat, device=dev_, dtype=f32)
+        _lib.check(lib.dab_gemm_bf16(ptr(dy_bf), ptr(w_out_t), ptr(dcat), None, M, ncat, D, st), "dab_gemm_bf16 (dcat)")
+        d_w_out = torch.empty(D, ncat, device=dev_, dtype=f32)
+        _lib.check(lib.dab_gemm_bf16_tn(ptr(dy_bf), D, ptr(cat), ncat, ptr(d_w_out), ncat, D, ncat, M, st),
+                   "dab_gemm_bf16_tn (dWout)")
+        dproj = torch.empty(M, n_proj, device=dev_, dtype=bf)
         de = torch.empty_like(e)
-        zeros = torch.zeros(weights[6].numel() + weights[7].numel(), device=x.device, dtype=torch.float32)   # one fill
+        zeros = torch.zeros(weights[6].numel() + weights[7].numel(), device=dev_, dtype=f32)   # one fill
         d_wpb = zeros[: weights[6].numel()].view_as(weights[6])
         d_gamma = zeros[weights[6].numel():].view_as(weights[7])
-        bws = _lib.aligned_empty(max(lib.dab_ipa_bwd_sm100_workspace_bytes(ctypes.byref(dims)), 16), x.device)
+        bws = _lib.aligned_empty(max(lib.dab_ipa_bwd_sm100_workspace_bytes(ctypes.byref(dims)), 16), dev_)
         _lib.check(lib.dab_ipa_bwd_sm100(ctypes.byref(dims), ptr(packed), ptr(e), ptr(r), ptr(dcat), ptr(saved),
                                          saved.numel(), ptr(dproj), ptr(de), ptr(d_wpb), ptr(d_gamma), ptr(bws),
-                                         bws.numel(), _lib.stream_ptr()), "dab_ipa_bwd_sm100")
+                                         bws.numel(), st), "dab_ipa_bwd_sm100")
         layer._last_bwd_ws = bws   # kept for tools/debug_bwd.py (intermediate buffers of the last backward)
-        dx = torch.mm(dproj, w_cat_bf, out_dtype=torch.float32).view(B, L, D)
-        d_w_cat = torch.mm(dproj.t(), x.view(M, D).to(bf), out_dtype=torch.float32)
+        dx = torch.empty(B, L, D, device=dev_, dtype=f32)
+        _lib.check(lib.dab_gemm_bf16(ptr(dproj), ptr(w_cat_t), ptr(dx), None, M, D, n_proj, st), "dab_gemm_bf16 (dx)")
+        d_w_cat = torch.empty(n_proj, D, device=dev_, dtype=f32)
+        _lib.check(lib.dab_gemm_bf16_tn(ptr(dproj), n_proj, ptr(cast(x.view(M, D))), D, ptr(d_w_cat), D, n_proj, D, M, st),
+                   "dab_gemm_bf16_tn (dWcat)")
         d_proj_w = torch.split(d_w_cat, [w.shape[0] for w in weights[:6]], dim=0)
         return (None, None, dx, de, None, None, *d_proj_w, d_wpb, d_gamma, d_w_out, d_b_out)
 
@@ -608,10 +625,11 @@ class InvariantPointAttentionLayer(nn.Module):
     def _packed_weights(self, dims):
         ws = self._weights()
         key = tuple((w.data_ptr(), w._version) for w in ws) + (_lib.weight_generation(),)
-        # Training (gradients recorded): always repack - the call may be part of a CUDA-graph capture whose replays follow
-        # optimizer steps that no Python-side version counter sees, and the pack kernel costs a few microseconds.
-        training = torch.is_grad_enabled() and any(w.requires_grad for w in ws)
-        if training or self._packed is None or self._packed[0] != key:
+        # While a training step is being captured into a CUDA graph (distributed.GraphedTrainStep): always repack, so that
+        # the pack is part of the graph - its replays follow optimizer steps that no Python-side version counter sees.
+        capturing = (_lib.repack_when_capturing and torch.is_grad_enabled() and ws[0].is_cuda
+                     and torch.cuda.is_current_stream_capturing())
+        if capturing or self._packed is None or self._packed[0] != key:
             lib = _lib.lib()
             nbytes = lib.dab_ipa_packed_bytes(ctypes.byref(dims))
             if self._packed is not None and self._packed[1].device == ws[0].device:

@@ -166,13 +166,18 @@ class GraphedTrainStep:
                 optimizer.step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from . import _lib
         self.graph_a = torch.cuda.CUDAGraph()
         self.graph_b = None
-        with torch.cuda.graph(self.graph_a):
-            self._backward_part()
-            if self.world == 1:
-                self._reduce_part()
-                optimizer.step()
+        _lib.repack_when_capturing = True     # weight-derived buffers (packed bf16 weights) are rebuilt inside the graph
+        try:
+            with torch.cuda.graph(self.graph_a):
+                self._backward_part()
+                if self.world == 1:
+                    self._reduce_part()
+                    optimizer.step()
+        finally:
+            _lib.repack_when_capturing = False
         if self.world > 1:
             self.graph_b = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):

@@ -295,6 +295,15 @@ int dab_losses_bwd(const float* post_pred, const float* post_tgt, const float* e
 /* The tcgen05 GEMM C[M,N] = A[M,K] B[N,K]^T + bias (bf16 in, fp32 out; M % 128 == 0, N % 64 == 0, K % 64 == 0): nn.Linear
  * (diffab_pytorch.py:464) as a stand-alone entry point. */
 int dab_gemm_bf16(const void* A, const void* Bm, float* C, const float* bias, int M, int N, int K, void* stream);
+/* C[M,N] (fp32, overwritten) = A[K,M]^T B[K,N]: bf16 operands whose ROW index is the contraction index (activations as
+ * they lie in memory, one row per residue), read MN-major by tcgen05 - no transposed copies.  Split over K, partial tiles
+ * added with red.global (summation order not fixed).  K % 64 == 0, N % 64 == 0, lda / ldb % 8 == 0.  The autograd weight
+ * gradients of the nn.Linear layers of diffab_pytorch.py:391-408,464 (dWout = dy^T cat, dWcat = dproj^T x). */
+int dab_gemm_bf16_tn(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
+                     void* stream);
+/* out[cols] (fp32, overwritten) = column sums of x[rows, cols]: bias gradients (d b_out = sum over residues of dy);
+ * x_bf16 (may be NULL) receives x rounded to bf16 in the same pass (the operand of the gradient GEMMs). */
+int dab_colsum_f32(const float* x, int64_t rows, int cols, float* out, void* x_bf16, void* stream);
 #ifdef DAB_DEBUG_HOOKS /* debug build only */
 int dab_debug_set_timeline(long long* device_buf /* 64 slots per tile of the attention core, or NULL */);
 #endif
