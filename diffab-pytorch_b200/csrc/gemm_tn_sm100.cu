@@ -163,6 +163,7 @@ static int launch_gemm_tn(const void* A, int64_t lda, const void* Bm, int64_t ld
 // optionally also writes x rounded to bf16 (the operand of the gradient GEMMs) in the same pass
 __global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict__ x, int64_t rows, int cols,
                                                          float* __restrict__ out, __nv_bfloat16* __restrict__ x_bf16) {
+  __shared__ float4 part[256];
   const int c4 = cols / 4;                       // float4 columns
   const int lanes = c4 < 256 ? c4 : 256;         // threads that own a float4 column each (cols <= 1024)
   const int groups = 256 / lanes;                // row groups inside the block
@@ -177,6 +178,14 @@ __global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict
         reinterpret_cast<uint2*>(x_bf16 + r * cols)[tc] =
             make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
       }
+    }
+  }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  if (tg == 0) {                                  // one reduction per column quad and block (few blocks: little contention)
+    for (int k = 1; k < groups; ++k) {
+      const float4 o = part[k * lanes + tc];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
     }
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + 4 * tc), "f"(acc.x), "f"(acc.y), "f"(acc.z),
                  "f"(acc.w)
@@ -215,8 +224,8 @@ int dab_colsum_f32(const float* x, int64_t rows, int cols, float* out, void* x_b
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), s) != cudaSuccess) return check_launch("dab_colsum_f32 memset");
   if (rows == 0) return DAB_OK;
-  int64_t blocks = (rows + 15) / 16;
-  if (blocks > 592) blocks = 592;
+  int64_t blocks = (rows + 31) / 32;
+  if (blocks > 148) blocks = 148;
   colsum_f32_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, rows, cols, out, reinterpret_cast<__nv_bfloat16*>(x_bf16));
   count_launch();
   return check_launch("dab_colsum_f32");

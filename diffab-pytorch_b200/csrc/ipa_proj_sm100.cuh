@@ -180,24 +180,22 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
     // and round; a round = fill, fence, __syncwarp, issue - no block-level barrier anywhere in the epilogue.
     uint8_t* stg = smem + S::kStage + warp * 4096;            // 2 x 2 KB
     const int lrow = gt & 31, grow0 = b * L + (gt & ~31);     // row inside the warp's tile; first row of the tile
-    bool first_round = true;
-    auto begin_round = [&] {      // the previous round's stores must have finished reading the tiles
-      if (!first_round) {
-        if (lane == 0) tma_store_wait_read();
+    // The two staging tiles of a warp alternate: a tile is refilled as soon as every bulk group but the most recent one
+    // (the OTHER tile's store) has finished reading shared memory, so one store is always in flight behind the packing.
+    int n_put = 0;
+    auto put = [&](const uint4 (&seg)[4], const CUtensorMap* m, int col) {
+      const int slot = n_put & 1;
+      if (n_put >= 2) {
+        if (lane == 0) tma_store_wait_read_1();
         __syncwarp();
       }
-      first_round = false;
-    };
-    auto put = [&](int slot, const uint4 (&seg)[4]) {
+      ++n_put;
 #pragma unroll
       for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(stg + slot * 2048 + swz64_offset(lrow, q)) = seg[q];
-    };
-    auto end_round = [&](const CUtensorMap* m0, int col0, const CUtensorMap* m1, int col1) {
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(m0, stg, col0, grow0);
-        tma_store_2d(m1, stg + 2048, col1, grow0);
+        tma_store_2d(m, stg + slot * 2048, col, grow0);
         tma_store_commit();
       }
     };
@@ -238,13 +236,8 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
                                 pk_bf(s8[4] * sc, s8[5] * sc), pk_bf(s8[6] * sc, s8[7] * sc));
             }
           }
-          if (hh == 0) begin_round();
-          put(hh, o);
-        }
-        {
           const CUtensorMap* m = seg == 0 ? &map_sq : (seg == 1 ? &map_sk : &map_sv);
-          const int w = seg == 2 ? V_W : QK_W;
-          end_round(m, h0 * w, m, (h0 + 1) * w);
+          put(o, m, h * (seg == 2 ? V_W : QK_W));
         }
       } else {
         // ---------------- two heads of points: 8 points x 3 each; euclidean_transform (diffab_pytorch.py:315-324)
@@ -267,9 +260,7 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
               o[q] = make_uint4(pk_h(gl[8 * q], gl[8 * q + 1]), pk_h(gl[8 * q + 2], gl[8 * q + 3]),
                                 pk_h(gl[8 * q + 4], gl[8 * q + 5]), pk_h(gl[8 * q + 6], gl[8 * q + 7]));
             o[3] = make_uint4(pk_h(1.0f, 0.0f), 0, 0, 0);
-            if (hh == 0) begin_round();
-            put(hh, o);
-            if (hh == 1) end_round(&map_sv, h0 * V_W + 32, &map_sv, (h0 + 1) * V_W + 32);
+            put(o, &map_sv, h * V_W + 32);
           } else {
             const float ch = st * sp * __ldg(gamma + h) * kLog2e;
             const float sc = seg == 0 ? ch : 1.0f;
@@ -302,10 +293,8 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
             oh[3] = tail;
             ol[3] = make_uint4(0, 0, 0, 0);
             const CUtensorMap* m = seg == 0 ? &map_sq : &map_sk;
-            begin_round();
-            put(0, oh);
-            put(1, ol);
-            end_round(m, h * QK_W + 32, m, h * QK_W + 64);
+            put(oh, m, h * QK_W + 32);
+            put(ol, m, h * QK_W + 64);
           }
         }
       }

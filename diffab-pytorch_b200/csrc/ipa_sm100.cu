@@ -267,7 +267,11 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if ((smem_base & 1023u) != 0) asm volatile("trap;");
   // local tiles of this CTA: k = 0, 1, ... -> global tile blockIdx.x + k * gridDim.x, context k & 1
   const int n_local = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  auto tile_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
+  // Tiles are walked from the LAST patch down: the projection kernel has just written the packed operands in ascending
+  // patch order, so the highest patches are the ones still resident in L2 (and the to_out GEMM, which starts with patch
+  // 0, finds the concat features this kernel wrote last).  The pair rows are streamed with an evict-first policy so that
+  // they do not push those operands out of L2.
+  auto tile_of = [&](int k) { return n_tiles - 1 - ((int)blockIdx.x + k * (int)gridDim.x); };
   // Ring bookkeeping.  Per tile every K slot completes 4 times and every e/V slot 4 times (24 entries on 6 slots), an
   // even number: slot and parity of an entry depend only on its index inside the tile.
   //   K entry h (head):            slot h & 1,   completion (h >> 1) of the tile
@@ -322,10 +326,11 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // HBM -> L2 kL2Ahead rows ahead (across the tile boundary) with TMA prefetches and the ring is fed from L2.
     if (lane == 0) {
       tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
+      const uint64_t pol = policy_evict_first();
       constexpr int kL2Ahead = 8;
       auto row0_of = [&](int k) { const int tile = tile_of(k); return (int64_t)(tile >> 3) * L + (tile & 7) * IB; };
       if (n_local > 0)
-        for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0_of(0) + r) * L));
+        for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d_hint(&map_e, 0, (int)((row0_of(0) + r) * L), pol);
       for (int k = 0; k < n_local; ++k) {
         const int tile = tile_of(k), b = tile >> 3;
         const int64_t row0 = row0_of(k);
@@ -335,10 +340,10 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           if (k > 0 || x >= S::kSlots) mbar_wait(&bars[R_EMPTY + s], ((x / S::kSlots) + 1) & 1);
           mbar_arrive_expect_tx(&bars[R_FULL + s], S::kSlot);
           if (x < IB) {
-            tma_load_2d(smem + S::kRing + s * S::kSlot, &map_e, &bars[R_FULL + s], 0, (int)((row0 + x) * L));
+            tma_load_2d_hint(smem + S::kRing + s * S::kSlot, &map_e, &bars[R_FULL + s], 0, (int)((row0 + x) * L), pol);
             const int a = x + kL2Ahead;
-            if (a < IB) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + a) * L));
-            else if (nrow0 >= 0) tma_prefetch_l2_2d(&map_e, 0, (int)((nrow0 + a - IB) * L));
+            if (a < IB) tma_prefetch_l2_2d_hint(&map_e, 0, (int)((row0 + a) * L), pol);
+            else if (nrow0 >= 0) tma_prefetch_l2_2d_hint(&map_e, 0, (int)((nrow0 + a - IB) * L), pol);
           } else {
             tma_load_2d(smem + S::kRing + s * S::kSlot, &map_v, &bars[R_FULL + s], (x - IB) * V_W, b * L);
           }
@@ -1047,7 +1052,7 @@ int dab_gemm_bf16(const void* A, const void* Bm, float* Cm, const float* bias, i
   // narrow N tiles and a deep ring when 64-wide tiles would leave most SMs idle (e.g. dx = dproj Wcat: N = 128, K = 1344);
   // wide tiles when there are more than two waves of them (e.g. dcat = dy Wout: N = 1024, K = 128)
   if (M > 0 && N % 64 == 0 && (M / kGemmBM) * (N / 64) < 148)
-    return launch_gemm_bf16<32, 6>(A, K, Bm, K, Cm, N, bias, M, N, K, (cudaStream_t)stream);
+    return launch_gemm_bf16<32>(A, K, Bm, K, Cm, N, bias, M, N, K, (cudaStream_t)stream);
   if (N % 128 == 0 && (M / kGemmBM) * (N / 128) >= 2 * 148)
     return launch_gemm_bf16<128>(A, K, Bm, K, Cm, N, bias, M, N, K, (cudaStream_t)stream);
   return launch_gemm_bf16<64>(A, K, Bm, K, Cm, N, bias, M, N, K, (cudaStream_t)stream);
