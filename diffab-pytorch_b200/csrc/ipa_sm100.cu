@@ -275,7 +275,13 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   // Ring bookkeeping.  Per tile every K slot completes 4 times and every e/V slot 4 times (24 entries on 6 slots), an
   // even number: slot and parity of an entry depend only on its index inside the tile.
   //   K entry h (head):            slot h & 1,   completion (h >> 1) of the tile
-  //   e/V entry x (row r: x = r; value tile h: x = 16 + h): slot x % 6, completion x / 6 of the tile
+  //   e/V entry at ring position x: slot x % 6, completion x / 6 of the tile.  Positions inside a tile: pair rows 0..13
+  //   at 0..13, value tiles 0, 1 at 14, 15, pair rows 14, 15 at 16, 17, value tiles 2, 3 at 18, 19, value tiles 4..7 at
+  //   20..23 - the first value tiles are loaded BEFORE the last pair rows, so the O^T MMAs find them in shared memory
+  //   the moment the softmax is done (consumption order: row pairs 0..7, then value pairs 0..3; every producer wait is
+  //   for an entry consumed earlier in that order, so the interleaving cannot deadlock).
+  auto pos_e = [](int r) { return r < 14 ? r : r + 2; };
+  auto pos_v = [](int h) { return h < 2 ? 14 + h : (h < 4 ? 16 + h : 16 + h); };
 
   if (tid == 0) {
     for (int i = 0; i < CTX_BARS; ++i) mbar_init(&bars[i], 1u);   // rings and turn barriers
@@ -339,13 +345,17 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           const int s = x % S::kSlots;
           if (k > 0 || x >= S::kSlots) mbar_wait(&bars[R_EMPTY + s], ((x / S::kSlots) + 1) & 1);
           mbar_arrive_expect_tx(&bars[R_FULL + s], S::kSlot);
-          if (x < IB) {
-            tma_load_2d_hint(smem + S::kRing + s * S::kSlot, &map_e, &bars[R_FULL + s], 0, (int)((row0 + x) * L), pol);
-            const int a = x + kL2Ahead;
+          // what sits at position x: pair row r or value tile h
+          const bool is_v = (x == 14 || x == 15 || x >= 18);
+          if (!is_v) {
+            const int r = x < 14 ? x : x - 2;
+            tma_load_2d_hint(smem + S::kRing + s * S::kSlot, &map_e, &bars[R_FULL + s], 0, (int)((row0 + r) * L), pol);
+            const int a = r + kL2Ahead;
             if (a < IB) tma_prefetch_l2_2d_hint(&map_e, 0, (int)((row0 + a) * L), pol);
             else if (nrow0 >= 0) tma_prefetch_l2_2d_hint(&map_e, 0, (int)((nrow0 + a - IB) * L), pol);
           } else {
-            tma_load_2d(smem + S::kRing + s * S::kSlot, &map_v, &bars[R_FULL + s], (x - IB) * V_W, b * L);
+            const int h = x < 16 ? x - 14 : x - 16;
+            tma_load_2d(smem + S::kRing + s * S::kSlot, &map_v, &bars[R_FULL + s], h * V_W, b * L);
           }
         }
       }
@@ -416,7 +426,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (k > 0) DAB_TIMED_WAIT(&bars[R_TURN], (k - 1) & 1, w_rturn);
         DAB_STAMP_ISSUER(17);
         for (int p = 0; p < IB / 2; ++p) {
-          const int x = 2 * p, st = x % S::kSlots;     // rows 2p, 2p+1 sit in consecutive ring slots
+          const int x = pos_e(2 * p), st = x % S::kSlots;     // rows 2p, 2p+1 sit in consecutive ring slots
           const int slot = p & 1;
           DAB_TIMED_WAIT(&bars[R_FULL + st], (x / S::kSlots) & 1, w_e);
           DAB_TIMED_WAIT(&bars[R_FULL + st + 1], (x / S::kSlots) & 1, w_e);
@@ -445,7 +455,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // ---- stage 3: O^T of TWO heads per MMA chain: [O_2m ; O_2m+1]^T = [V_2m | V_2m+1]^T [P_2m ; P_2m+1]^T
         //      (M = 128: 64 value columns of each head, N = 32: 16 rows of each head, K = 128 j)
         for (int m = 0; m < H / 2; ++m) {
-          const int x = IB + 2 * m, st = x % S::kSlots;
+          const int x = pos_v(2 * m), st = x % S::kSlots;
           DAB_TIMED_WAIT(&bars[R_FULL + st], (x / S::kSlots) & 1, w_v);
           DAB_TIMED_WAIT(&bars[R_FULL + st + 1], (x / S::kSlots) & 1, w_v);
           tcgen05_fence_after_sync();
