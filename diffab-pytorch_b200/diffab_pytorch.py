@@ -18,6 +18,7 @@ Not a LightningModule: ``pytorch_lightning`` is not a dependency; ``training_ste
 """
 import contextlib
 import ctypes
+import types
 import math
 from typing import Dict, Optional
 
@@ -569,9 +570,6 @@ class InvariantPointAttentionLayer(nn.Module):
     def __init__(self, d_residue_emb, d_pair_emb, d_scalar_per_head=16, n_query_point_per_head=4,
                  n_value_point_per_head=4, n_head=8, use_pair_bias=True):
         super().__init__()
-        if not use_pair_bias:
-            raise NotImplementedError("use_pair_bias=False is never constructed by the reference model "
-                                      "(diffab_pytorch.py:482-489) and has no kernel here")
         self.d_residue_emb, self.d_pair_emb = d_residue_emb, d_pair_emb
         self.d_scalar_per_head = d_scalar_per_head
         self.n_query_point_per_head, self.n_value_point_per_head = n_query_point_per_head, n_value_point_per_head
@@ -582,7 +580,8 @@ class InvariantPointAttentionLayer(nn.Module):
         self.to_k_scalar = nn.Linear(d_residue_emb, d_scalar, bias=False)
         self.to_v_scalar = nn.Linear(d_residue_emb, d_scalar, bias=False)
         self.scale_scalar = d_scalar_per_head**-0.5
-        self.to_pair_bias = nn.Linear(d_pair_emb, n_head, bias=False)
+        if use_pair_bias:                                                   # :362-363
+            self.to_pair_bias = nn.Linear(d_pair_emb, n_head, bias=False)
         d_query_point = n_query_point_per_head * 3 * n_head
         d_value_point = n_value_point_per_head * 3 * n_head
         self.to_q_point = nn.Linear(d_residue_emb, d_query_point, bias=False)
@@ -590,9 +589,9 @@ class InvariantPointAttentionLayer(nn.Module):
         self.to_v_point = nn.Linear(d_residue_emb, d_value_point, bias=False)
         self.scale_point = (4.5 * n_query_point_per_head) ** -0.5
         self.gamma = nn.Parameter(torch.log(torch.exp(torch.ones(n_head)) - 1.0))  # used raw (:373,429)
-        self.to_out = nn.Linear(d_scalar + d_pair_emb * n_head + d_value_point + n_value_point_per_head * n_head,
-                                d_residue_emb)
-        self.num_independent_logits = 3
+        d_pair = d_pair_emb * n_head if use_pair_bias else 0                # :374-383
+        self.to_out = nn.Linear(d_scalar + d_pair + d_value_point + n_value_point_per_head * n_head, d_residue_emb)
+        self.num_independent_logits = 3 if use_pair_bias else 2            # :385
         self.scale_total = self.num_independent_logits**-0.5
         self._packed = None  # (version key, packed weights) for the sm_100a fast path
 
@@ -603,12 +602,37 @@ class InvariantPointAttentionLayer(nn.Module):
             self._ws = ws
         return ws[: (nbytes // 4) * 4]
 
+    # dummy pair width of the use_pair_bias=False re-expression (16-byte rows for the fp32 kernels)
+    _NOPB_C = 4
+
+    def _weights_no_pair_bias(self):
+        """``use_pair_bias=False`` (:374-387,438-462) expressed EXACTLY on the kernels of the pair-bias layer: a zero pair
+        tensor of width 4 and a zero ``to_pair_bias`` contribute nothing to the logits or the features; the kernels' fixed
+        scale_total = 3^-1/2 becomes the layer's 2^-1/2 by scaling ``to_q_scalar`` and ``gamma`` (both logit terms are
+        linear in them) by sqrt(3/2); ``to_out`` gets zero columns where the (all-zero) pair features sit.  Built from the
+        parameters with differentiable PyTorch ops, so autograd carries the kernels' gradients back to them."""
+        r = (3.0 / 2.0) ** 0.5
+        H, ns = self.n_head, self.d_scalar_per_head * self.n_head
+        w_out = self.to_out.weight
+        w_out = torch.cat([w_out[:, :ns], w_out.new_zeros(w_out.shape[0], H * self._NOPB_C), w_out[:, ns:]], dim=1)
+        return (self.to_q_scalar.weight * r, self.to_k_scalar.weight, self.to_v_scalar.weight, self.to_q_point.weight,
+                self.to_k_point.weight, self.to_v_point.weight, w_out.new_zeros(H, self._NOPB_C), self.gamma * r, w_out,
+                self.to_out.bias)
+
     def _weights(self):
         return (self.to_q_scalar.weight, self.to_k_scalar.weight, self.to_v_scalar.weight, self.to_q_point.weight,
                 self.to_k_point.weight, self.to_v_point.weight, self.to_pair_bias.weight, self.gamma,
                 self.to_out.weight, self.to_out.bias)
 
     def forward(self, x, e, r, t, pair_bias=None):
+        if not self.use_pair_bias:
+            # the pair tensor is accepted and unused, as in the reference (:389, :438-441); fp32 kernels
+            x = _lib.dev(x, torch.float32, "x")
+            B, L = x.shape[0], x.shape[1]
+            ws = self._weights_no_pair_bias()
+            e0 = x.new_zeros(B, L, L, self._NOPB_C)
+            need_bwd = torch.is_grad_enabled() and (x.requires_grad or any(w.requires_grad for w in ws))
+            return _IpaFunction.apply(self._nopb_view(), need_bwd, x, e0, r, t, *ws)
         if e.dtype == torch.bfloat16:
             return self.forward_fast(x, e, r, t, pair_bias)
         ws = self._weights()
@@ -616,9 +640,21 @@ class InvariantPointAttentionLayer(nn.Module):
                                                 t.requires_grad or any(w.requires_grad for w in ws))
         return _IpaFunction.apply(self, need_bwd, x, e, r, t, *ws)
 
+    def _nopb_view(self):
+        """What ``_ipa_structs`` / the workspace cache see for the use_pair_bias=False re-expression: this layer with the
+        dummy pair width."""
+        v = getattr(self, "_nopb", None)
+        if v is None:
+            v = types.SimpleNamespace(d_residue_emb=self.d_residue_emb, d_pair_emb=self._NOPB_C, n_head=self.n_head,
+                                      d_scalar_per_head=self.d_scalar_per_head,
+                                      n_query_point_per_head=self.n_query_point_per_head,
+                                      n_value_point_per_head=self.n_value_point_per_head, _workspace=self._workspace)
+            self._nopb = v
+        return v
+
     # ---- sm_100a fast path (inference; train.py configuration only) ----
     def fast_path_supported(self, L):
-        return (L == 128 and self.d_residue_emb == 128 and self.d_pair_emb == 64 and self.n_head == 8 and
+        return (self.use_pair_bias and L == 128 and self.d_residue_emb == 128 and self.d_pair_emb == 64 and self.n_head == 8 and
                 self.d_scalar_per_head == 32 and self.n_query_point_per_head == 8 and
                 self.n_value_point_per_head == 8)
 

@@ -17,8 +17,9 @@ IPA_KEYS = ("gamma", "to_q_scalar.weight", "to_k_scalar.weight", "to_v_scalar.we
             "to_out.weight", "to_out.bias")
 
 
-def ipa_layer(w, x, e, R, t, n_head, return_attn=False):
-    """``InvariantPointAttentionLayer.forward`` diffab_pytorch.py:389-465 (use_pair_bias=True).
+def ipa_layer(w, x, e, R, t, n_head, return_attn=False, use_pair_bias=True):
+    """``InvariantPointAttentionLayer.forward`` diffab_pytorch.py:389-465 (``use_pair_bias=False``: no bias term, no pair
+    features, two independent logits, ``:374-387,438-462``).
 
     x (B,L,D)  e (B,L,L,C)  R (B,L,3,3)  t (B,L,3)  ->  (B,L,D)
     Feature order of the projections is (h d) for scalars and (h p c) for points (``:395-408``);
@@ -42,9 +43,9 @@ def ipa_layer(w, x, e, R, t, n_head, return_attn=False):
 
     scale_scalar = ds ** -0.5                                     # :359
     scale_point = (4.5 * Pq) ** -0.5                              # :372
-    scale_total = 3 ** -0.5                                       # :385-387
+    scale_total = (3 if use_pair_bias else 2) ** -0.5             # :385-387
     logit_scalar = torch.einsum("bihd,bjhd->bhij", qs, ks) * scale_scalar          # :416-419
-    bias = torch.einsum("bijc,hc->bhij", e, w["to_pair_bias.weight"])              # :423
+    bias = torch.einsum("bijc,hc->bhij", e, w["to_pair_bias.weight"]) if use_pair_bias else 0.0   # :423
     diff = qp[:, :, None] - kp[:, None, :]                        # (B,i,j,H,P,3)   :426-428
     d2 = diff.pow(2).sum(-1).sum(-1).permute(0, 3, 1, 2)          # (B,H,i,j)       :435
     logit_point = -0.5 * scale_point * w["gamma"].view(1, H, 1, 1) * d2            # :431-436
@@ -56,7 +57,8 @@ def ipa_layer(w, x, e, R, t, n_head, return_attn=False):
     og = torch.einsum("bhij,bjhpc->bihpc", attn, vp)                               # :452
     ol = torch.einsum("bihpk,bick->bihpc", og - t[:, :, None, None, :], R)         # :327-336,453
     nrm = ol.norm(dim=-1)                                                           # :454
-    cat = torch.cat([o_scalar, o_pair, ol.reshape(B, L, -1), nrm.reshape(B, L, -1)], dim=-1)
+    parts = [o_scalar, o_pair, ol.reshape(B, L, -1), nrm.reshape(B, L, -1)]
+    cat = torch.cat(parts if use_pair_bias else parts[:1] + parts[2:], dim=-1)                  # :459-462
     y = cat @ w["to_out.weight"].transpose(0, 1) + w["to_out.bias"]                # :464
     return (y, attn, logit) if return_attn else y
 

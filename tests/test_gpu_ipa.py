@@ -297,3 +297,25 @@ def test_tensor_core_path_empty_batch_and_wrong_shape():
         with torch.no_grad():
             small(torch.rand(2, 16, 32, device=DEV), torch.rand(2, 16, 16, 16, device=DEV).bfloat16(),
                   torch.rand(2, 16, 3, 3, device=DEV), torch.rand(2, 16, 3, device=DEV))
+
+
+def test_layer_without_pair_bias_vs_reference():
+    """use_pair_bias=False (diffab_pytorch.py:374-387,438-462; never constructed by the reference model, but part of the
+    layer's interface): same state-dict keys as the reference, forward and every gradient vs its fp64 result."""
+    g = load_golden("ipa_nopb.pt")
+    c = g["cfg"]
+    layer = InvariantPointAttentionLayer(c["D"], c["C"], c["ds"], c["Pq"], c["Pv"], c["H"], use_pair_bias=False).to(DEV)
+    assert sorted(layer.state_dict()) == sorted(g["state"])
+    layer.load_state_dict({k: v.float() for k, v in g["state"].items()})
+    x, e, R, t = synth.make_ipa_inputs(c["B"], c["L"], c["D"], c["C"], seed=c["seed"] + 100)
+    gy = torch.randn(c["B"], c["L"], c["D"], generator=torch.Generator().manual_seed(c["seed"] + 200))
+    xg = x.to(DEV).requires_grad_(True)
+    y = layer(xg, e.to(DEV), R.to(DEV), t.to(DEV))
+    (y * gy.to(DEV)).sum().backward()
+    assert _rel(y, g["y"]) < REL
+    assert _rel(xg.grad, g["dx"]) < REL
+    params = dict(layer.named_parameters())
+    for n, gr in g["dw"].items():
+        assert _rel(params[n].grad, gr) < 5 * REL, n
+    with torch.no_grad():
+        assert torch.equal(layer(xg, e.to(DEV), R.to(DEV), t.to(DEV)), y)

@@ -135,3 +135,20 @@ def test_denoiser_and_losses():
     # context residues are untouched, generated ones moved
     m = batch["generation_mask"]
     assert torch.equal(out["translations"][~m], n["translations_t"][~m])
+
+
+def test_ipa_layer_without_pair_bias():
+    """use_pair_bias=False (diffab_pytorch.py:374-387,438-462): oracle variant vs the reference's fp64 forward + gradients."""
+    g = load_golden("ipa_nopb.pt")
+    c = g["cfg"]
+    x, e, R, t = synth.make_ipa_inputs(c["B"], c["L"], c["D"], c["C"], seed=c["seed"] + 100)
+    gy = torch.randn(c["B"], c["L"], c["D"], generator=torch.Generator().manual_seed(c["seed"] + 200))
+    w = {k: v.clone().requires_grad_(True) for k, v in g["state"].items()}
+    assert "to_pair_bias.weight" not in w
+    x64 = x.double().requires_grad_(True)
+    y = oipa.ipa_layer(w, x64, e.double(), R.double(), t.double(), c["H"], use_pair_bias=False)
+    (y * gy.double()).sum().backward()
+    assert (y - g["y"]).abs().max() < 1e-12
+    assert (x64.grad - g["dx"]).abs().max() < 1e-11
+    for n, gr in g["dw"].items():
+        assert (w[n].grad - gr).abs().max() < 1e-10, n
