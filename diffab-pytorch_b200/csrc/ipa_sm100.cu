@@ -127,8 +127,8 @@ constexpr int kPackBlocks = (NPROJ / 32) * (D / 32) + (D / 32) * (NCAT / 32);   
 // One persistent CTA per SM holds TWO tile contexts (tile = (patch, 16 query rows); local tile k of a CTA runs in
 // context k & 1).  A context is a complete tile pipeline - its own softmax / epilogue warps, MMA issuer, probability
 // buffers and 256 TMEM columns - but the operand rings are SHARED and dedicated (nothing aliases them):
-//   * K ring (2 x 24 KB): K of the patch head by head, tiles in local order;
-//   * e/V ring (6 x 16 KB): per tile its 16 pair rows, then the 8 value tiles of its patch.
+//   * K ring (3 x 24 KB): K of the patch head by head, tiles in local order;
+//   * e/V ring (4 x 16 KB): per tile its 16 pair rows, then the 8 value tiles of its patch.
 // Ring order = tile order, so the two contexts run in anti-phase: while one context streams its pair rows (softmax,
 // pair aggregation), the other runs its O^T MMAs, its epilogue and the S^T MMAs of its next tile from operands that
 // were loaded in the background.  The pair-tensor stream therefore never pauses (two independent CTAs per SM, which
@@ -136,10 +136,10 @@ constexpr int kPackBlocks = (NPROJ / 32) * (D / 32) + (D / 32) * (NCAT / 32);   
 // region and was loaded only when the stage needing it began).
 struct CoreSmem {
   static constexpr int kSlot = L * C * 2;            // 16,384: one pair row [128 j x 64 c] or one value tile [128 j x 64]
-  static constexpr int kSlots = 6;
+  static constexpr int kSlots = 4;
   static constexpr int kRing = 0;
   static constexpr int kKBuf = 3 * L * 64;           // 24,576: one head of K = three [128 x 64 B] blocks
-  static constexpr int kKBufs = 2;
+  static constexpr int kKBufs = 3;
   static constexpr int kKRing = kRing + kSlots * kSlot;          // 98,304
   static constexpr int kCtx0 = kKRing + kKBufs * kKBuf;          // 147,456
   // ---- per context ----
@@ -168,7 +168,7 @@ static_assert(CoreSmem::kTotal <= 227 * 1024, "one CTA per SM");
 // K_TURN / R_TURN hand the shared rings from one context's issuer to the other's: completion k = the issuer of local
 // tile k has observed every K (every pair-row / value) entry of that tile, so the next tile's issuer may start waiting on
 // the ring's full barriers (whose parities would otherwise alias with the entries of the tile before).
-enum Bar { K_FULL = 0, K_EMPTY = 2, R_FULL = 4, R_EMPTY = 10, K_TURN = 16, R_TURN = 17, CTX_BARS = 18, N_BARS = 18 + 2 * 13 };
+enum Bar { K_FULL = 0, K_EMPTY = 3, R_FULL = 6, R_EMPTY = 10, K_TURN = 14, R_TURN = 15, CTX_BARS = 16, N_BARS = 16 + 2 * 13 };
 // per context (index CTX_BARS + 13 * ctx + ...)
 enum CtxBar { Q_FULL = 0, S_DONE = 1, PAIR = 2 /* [slot] */, O_DONE = 4, P_READY = 5 /* [group][slot], 128 arrivals */,
               EPI_TMEM = 9 /* 256 arrivals: epilogue has read every accumulator */,
@@ -272,16 +272,14 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   // 0, finds the concat features this kernel wrote last).  The pair rows are streamed with an evict-first policy so that
   // they do not push those operands out of L2.
   auto tile_of = [&](int k) { return n_tiles - 1 - ((int)blockIdx.x + k * (int)gridDim.x); };
-  // Ring bookkeeping.  Per tile every K slot completes 4 times and every e/V slot 4 times (24 entries on 6 slots), an
-  // even number: slot and parity of an entry depend only on its index inside the tile.
-  //   K entry h (head):            slot h & 1,   completion (h >> 1) of the tile
-  //   e/V entry at ring position x: slot x % 6, completion x / 6 of the tile.  Positions inside a tile: pair rows 0..13
-  //   at 0..13, value tiles 0, 1 at 14, 15, pair rows 14, 15 at 16, 17, value tiles 2, 3 at 18, 19, value tiles 4..7 at
-  //   20..23 - the first value tiles are loaded BEFORE the last pair rows, so the O^T MMAs find them in shared memory
-  //   the moment the softmax is done (consumption order: row pairs 0..7, then value pairs 0..3; every producer wait is
-  //   for an entry consumed earlier in that order, so the interleaving cannot deadlock).
-  auto pos_e = [](int r) { return r < 14 ? r : r + 2; };
-  auto pos_v = [](int h) { return h < 2 ? 14 + h : (h < 4 ? 16 + h : 16 + h); };
+  // Ring bookkeeping.  e/V entry at ring position x of a tile (pair row r: x = r; value tile h: x = 16 + h): slot x % 4,
+  // completion x / 4 of the tile - 24 entries on 4 slots are 6 completions per slot and tile, an even number, so the
+  // parity of an entry depends only on its position inside the tile.  Rows 2p, 2p+1 and value tiles 2m, 2m+1 always sit
+  // in adjacent slots (the MMA descriptors address the pair with one leading-dimension stride).
+  auto pos_e = [](int r) { return r; };
+  auto pos_v = [](int h) { return IB + h; };
+  // K ring (3 slots): slots 0 and 1 complete three times per tile, slot 2 twice - the parity carries the local tile index
+  auto k_use = [](int k, int h) { return k * (h % 3 == 2 ? 2 : 3) + h / 3; };
 
   if (tid == 0) {
     for (int i = 0; i < CTX_BARS; ++i) mbar_init(&bars[i], 1u);   // rings and turn barriers
@@ -308,8 +306,8 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         uint64_t* cb = bars + CTX_BARS + N_CTX_BARS * c;
         uint8_t* cs = smem + S::kCtx0 + c * S::kCtxBytes;
         auto load_k = [&](int h) {
-          const int s = h & 1;
-          if (k > 0 || h >= S::kKBufs) mbar_wait(&bars[K_EMPTY + s], ((h >> 1) + 1) & 1);
+          const int s = h % S::kKBufs;
+          if (k > 0 || h >= S::kKBufs) mbar_wait(&bars[K_EMPTY + s], (k_use(k, h) - 1) & 1);
           uint8_t* kb = smem + S::kKRing + s * S::kKBuf;
           mbar_arrive_expect_tx(&bars[K_FULL + s], S::kKBuf);
           for (int blk = 0; blk < 3; ++blk)
@@ -319,6 +317,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // previous tile); Q goes into the context's P_h region, free once the O^T MMAs of that tile have completed
         load_k(0);
         load_k(1);
+        load_k(2);
         if (n > 0) mbar_wait(&cb[O_DONE], (n - 1) & 1);
         mbar_arrive_expect_tx(&cb[Q_FULL], S::kQBuf);
         for (int blk = 0; blk < H * 3; ++blk)    // [blk][16 rows][64 B], 64B swizzle
@@ -328,7 +327,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
   } else if (warp == 19) {
     // ======================================= TMA producer: pair rows and value tiles =======================================
-    // The ring is only six tiles deep, far less than the HBM latency-bandwidth product, so pair rows are pulled
+    // The ring is only four tiles deep, far less than the HBM latency-bandwidth product, so pair rows are pulled
     // HBM -> L2 kL2Ahead rows ahead (across the tile boundary) with TMA prefetches and the ring is fed from L2.
     if (lane == 0) {
       tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
@@ -345,17 +344,13 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           const int s = x % S::kSlots;
           if (k > 0 || x >= S::kSlots) mbar_wait(&bars[R_EMPTY + s], ((x / S::kSlots) + 1) & 1);
           mbar_arrive_expect_tx(&bars[R_FULL + s], S::kSlot);
-          // what sits at position x: pair row r or value tile h
-          const bool is_v = (x == 14 || x == 15 || x >= 18);
-          if (!is_v) {
-            const int r = x < 14 ? x : x - 2;
-            tma_load_2d_hint(smem + S::kRing + s * S::kSlot, &map_e, &bars[R_FULL + s], 0, (int)((row0 + r) * L), pol);
-            const int a = r + kL2Ahead;
+          if (x < IB) {
+            tma_load_2d_hint(smem + S::kRing + s * S::kSlot, &map_e, &bars[R_FULL + s], 0, (int)((row0 + x) * L), pol);
+            const int a = x + kL2Ahead;
             if (a < IB) tma_prefetch_l2_2d_hint(&map_e, 0, (int)((row0 + a) * L), pol);
             else if (nrow0 >= 0) tma_prefetch_l2_2d_hint(&map_e, 0, (int)((nrow0 + a - IB) * L), pol);
           } else {
-            const int h = x < 16 ? x - 14 : x - 16;
-            tma_load_2d(smem + S::kRing + s * S::kSlot, &map_v, &bars[R_FULL + s], h * V_W, b * L);
+            tma_load_2d(smem + S::kRing + s * S::kSlot, &map_v, &bars[R_FULL + s], (x - IB) * V_W, b * L);
           }
         }
       }
@@ -391,8 +386,8 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         tcgen05_fence_after_sync();
         DAB_STAMP_ISSUER(1);
         for (int h = 0; h < H; ++h) {
-          const int s = h & 1;
-          DAB_TIMED_WAIT(&bars[K_FULL + s], (h >> 1) & 1, w_k);
+          const int s = h % S::kKBufs;
+          DAB_TIMED_WAIT(&bars[K_FULL + s], k_use(k, h) & 1, w_k);
           tcgen05_fence_after_sync();
           DAB_STAMP_ISSUER(48 + h);
           if (elect_one()) {
