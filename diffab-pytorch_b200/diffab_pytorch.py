@@ -386,6 +386,28 @@ def inverse_euclidean_transform(x, r, t):
     return torch.einsum("bnlpk,blck->bnlpc", x - t[:, None, :, None, :], r)
 
 
+FAST_L = 128   # patch length of the tensor-core kernels (keys sit on the 128 TMEM lanes)
+
+
+def _pad_patch(x, e, r, t, L_to=FAST_L):
+    """Pad a patch batch of L < 128 residues to the tensor-core kernels' length: zero residues / pair rows, identity
+    frames.  Differentiable (F.pad / cat), so gradients reach the unpadded tensors."""
+    L = x.shape[1]
+    n = L_to - L
+    xp = F.pad(x, (0, 0, 0, n))
+    ep = F.pad(e, (0, 0, 0, n, 0, n))
+    eye = torch.eye(3, device=r.device, dtype=r.dtype).expand(r.shape[0], n, 3, 3)
+    return xp, ep, torch.cat([r, eye], dim=1), F.pad(t, (0, 0, 0, n))
+
+
+def _mask_padded_keys(planes, L):
+    """Pair-bias planes (.., L_pad(i), L_pad(j), H) of a padded batch: keys j >= L get -inf, so their probability is exactly
+    zero - the layer then computes what the reference computes on the L real residues (it has no masks of its own)."""
+    for p_ in planes:
+        p_[:, :, L:, :] = float("-inf")
+    return planes
+
+
 def _ipa_structs(layer, B, L):
     dims = _lib.DabIpaDims(B, L, layer.d_residue_emb, layer.d_pair_emb, layer.n_head, layer.d_scalar_per_head,
                            layer.n_query_point_per_head, layer.n_value_point_per_head)
@@ -634,6 +656,17 @@ class InvariantPointAttentionLayer(nn.Module):
             need_bwd = torch.is_grad_enabled() and (x.requires_grad or any(w.requires_grad for w in ws))
             return _IpaFunction.apply(self._nopb_view(), need_bwd, x, e0, r, t, *ws)
         if e.dtype == torch.bfloat16:
+            L = x.shape[1]
+            if L < FAST_L and self.fast_path_supported(FAST_L):
+                # shorter patch on the tensor-core kernels: padded to 128 residues, padded keys masked through the bias plane
+                xp, ep, rp, tp = _pad_patch(x, e, r, t)
+                with torch.no_grad():
+                    if pair_bias is None:
+                        bias = self.pair_bias(ep.detach())
+                    else:
+                        bias = F.pad(pair_bias, (0, 0, 0, FAST_L - L, 0, FAST_L - L))
+                    _mask_padded_keys([bias], L)
+                return self.forward_fast(xp, ep, rp, tp, bias)[:, :L]
             return self.forward_fast(x, e, r, t, pair_bias)
         ws = self._weights()
         need_bwd = torch.is_grad_enabled() and (x.requires_grad or e.requires_grad or r.requires_grad or
@@ -759,6 +792,18 @@ class InvariantPointAttentionModule(nn.Module):
                                          n_value_point_per_head, n_head) for _ in range(n_layers)])
 
     def forward(self, res_emb, pair_emb, orientations, translations, pair_bias=None):
+        L = res_emb.shape[1]
+        if pair_emb.dtype == torch.bfloat16 and L < FAST_L and self.layers[0].fast_path_supported(FAST_L):
+            # shorter patches on the tensor-core kernels: pad once for the whole stack, mask the padded keys in every
+            # layer's bias plane, slice the result
+            xp, ep, rp, tp = _pad_patch(res_emb, pair_emb, orientations, translations)
+            with torch.no_grad():
+                if pair_bias is None:
+                    planes = self.precompute_pair_bias(ep.detach())
+                else:
+                    planes = [F.pad(p_, (0, 0, 0, FAST_L - L, 0, FAST_L - L)) for p_ in pair_bias]
+                _mask_padded_keys(planes, L)
+            return self.forward(xp, ep, rp, tp, planes)[:, :L]
         if (pair_bias is None and pair_emb.dtype == torch.bfloat16 and
                 self.layers[0].fast_path_supported(pair_emb.shape[1])):
             # tensor-core path: the bias planes of all layers in one pass over the pair tensor (their gradient
@@ -839,19 +884,17 @@ class Denoiser(nn.Module):
         h = self.to_res_emb(h)
         h = self.ipa(h, pair_context_emb, orientations_t, translations_t, pair_bias)
         t_emb = torch.stack([beta, torch.sin(beta), torch.cos(beta)], dim=-1)
-        if h.is_cuda:
-            # [h | t_emb] @ W1^T = h @ W1[:, :D]^T + (t_emb @ W1[:, D:]^T): the three time columns are a per-patch bias,
-            # and the residue part is a K = 128 GEMM (K = 131 sends forward and both backward GEMMs to unaligned kernels)
-            D = h.shape[-1]
-            outs = []
-            for head in (self.coordinate_denoising, self.orientation_denoising, self.sequence_denoising):
-                w1, b1 = head[0].weight, head[0].bias
-                pb = torch.addmm(b1, t_emb, w1[:, D:].t())                                  # (B, D)
-                a = torch.relu(F.linear(h, w1[:, :D].contiguous()) + pb[:, None, :])
-                outs.append(head[2:](a))
-            return tuple(outs)
-        h = torch.cat([h, t_emb[:, None, :].expand(-1, n_residues, -1)], dim=-1)
-        return self.coordinate_denoising(h), self.orientation_denoising(h), self.sequence_denoising(h)
+        # (h is a CUDA tensor here: the IPA layers above raise on CPU tensors - there is no CPU path)
+        # [h | t_emb] @ W1^T = h @ W1[:, :D]^T + (t_emb @ W1[:, D:]^T): the three time columns are a per-patch bias,
+        # and the residue part is a K = 128 GEMM (K = 131 sends forward and both backward GEMMs to unaligned kernels)
+        D = h.shape[-1]
+        outs = []
+        for head in (self.coordinate_denoising, self.orientation_denoising, self.sequence_denoising):
+            w1, b1 = head[0].weight, head[0].bias
+            pb = torch.addmm(b1, t_emb, w1[:, D:].t())                                  # (B, D)
+            a = torch.relu(F.linear(h, w1[:, :D].contiguous()) + pb[:, None, :])
+            outs.append(head[2:](a))
+        return tuple(outs)
 
     # ---- sampling fast path of the dense glue (same arithmetic, regrouped; inference only) ----
     @torch.no_grad()

@@ -319,3 +319,45 @@ def test_layer_without_pair_bias_vs_reference():
         assert _rel(params[n].grad, gr) < 5 * REL, n
     with torch.no_grad():
         assert torch.equal(layer(xg, e.to(DEV), R.to(DEV), t.to(DEV)), y)
+
+
+@pytest.mark.parametrize("L", [100, 37])
+def test_tensor_core_path_for_shorter_patches(L):
+    """Patches of L < 128 residues (train.py head configuration) on the tensor-core kernels: padded to 128 residues, the
+    padded keys masked through the bias plane (-inf), so the layer computes exactly what the reference computes on the L
+    real residues.  Forward and every gradient vs the fp64 autograd of the oracle on the bf16-rounded pair tensor
+    (2e-2 max-normalised, the bf16 bar); a three-layer stack (inference hand-off and training) against the oracle chain."""
+    shp = synth.ipa_layer_shapes(128, 64, 8, 32, 8, 8)
+    layer = InvariantPointAttentionLayer(128, 64, 32, 8, 8, 8).to(DEV)
+    layer.load_state_dict(synth.synthetic_state(shp, seed=3))
+    x, e, R, t = synth.make_ipa_inputs(2, L, 128, 64, seed=300 + L)
+    gy = torch.randn(2, L, 128, generator=torch.Generator().manual_seed(L))
+    e16 = e.to(torch.bfloat16)
+    w = {k: v.detach().cpu().double().requires_grad_(True) for k, v in layer.state_dict().items()}
+    xd, ed = x.double().requires_grad_(True), e16.double().requires_grad_(True)
+    yd = oipa.ipa_layer(w, xd, ed, R.double(), t.double(), 8)
+    (yd * gy.double()).sum().backward()
+    xg, eg = x.to(DEV).requires_grad_(True), e16.to(DEV).requires_grad_(True)
+    y = layer(xg, eg, R.to(DEV), t.to(DEV))
+    assert y.shape == (2, L, 128)
+    (y * gy.to(DEV)).sum().backward()
+    assert _rel(y.detach(), yd.detach()) < 2e-2
+    assert _rel(xg.grad, xd.grad) < 2e-2
+    assert eg.grad.shape == e.shape and _rel(eg.grad, ed.grad) < 2e-2
+    for n, p in layer.named_parameters():
+        assert _rel(p.grad, w[n].grad) < 2e-2, n
+    with torch.no_grad():
+        assert _rel(layer(x.to(DEV), e16.to(DEV), R.to(DEV), t.to(DEV)), yd.detach()) < 2e-2
+    # layer stack: one padding for the whole chain
+    mod = InvariantPointAttentionModule(3, 128, 64, 32, 8, 8, 8).to(DEV)
+    state = {}
+    for k_, lay in enumerate(mod.layers):
+        sd = synth.synthetic_state(shp, seed=10 + k_)
+        lay.load_state_dict(sd)
+        state.update({f"l.{k_}.{n}": v.double() for n, v in sd.items()})
+    ref = oipa.ipa_module(state, x.double(), e16.double(), R.double(), t.double(), 3, 8, prefix="l.")
+    with torch.no_grad():
+        got = mod(x.to(DEV), e16.to(DEV), R.to(DEV), t.to(DEV))
+    assert got.shape == (2, L, 128) and _rel(got, ref) < 3e-2
+    got_t = mod(x.to(DEV).requires_grad_(True), e16.to(DEV), R.to(DEV), t.to(DEV))     # training path of the stack
+    assert _rel(got_t.detach(), ref) < 3e-2
