@@ -1245,12 +1245,34 @@ class DiffAb(nn.Module):
     @torch.no_grad()
     def sample_from_context(self, seq_idx, translations, orientations, res_context_emb, pair_context_emb,
                             generation_mask, noises=None, generator=None, t_start=None, t_stop=1,
-                            use_cuda_graph=False):
+                            use_cuda_graph=False, _valid_len=None):
         """The reverse loop t_start..t_stop on resident tensors (this is what bench.py's ``value`` times).
         ``pair_context_emb`` may be fp32 (exact path) or bf16 (tensor-core path).  ``noises`` = {t: draws of step t}
         (``draw_step_noise``) injects every random draw (parity tests); it works with and without CUDA graphs."""
         T = self.T
         t_start = T if t_start is None else t_start
+        L0 = seq_idx.shape[1]
+        if (pair_context_emb.dtype == torch.bfloat16 and L0 < FAST_L and _valid_len is None
+                and self.denoiser.ipa.layers[0].fast_path_supported(FAST_L)):
+            # Shorter patches on the tensor-core path: the state and the context are padded to 128 residues (never
+            # generated, never attended to: their keys are masked in every layer's bias plane), the loop runs on the
+            # padded batch and the result is cut back.
+            n = FAST_L - L0
+            eye = torch.eye(3, device=orientations.device, dtype=orientations.dtype).expand(orientations.shape[0], n, 3, 3)
+            pad_noise = None
+            if noises is not None:
+                B_ = seq_idx.shape[0]
+                def pn(d):
+                    return {"seq_exp": F.pad(d["seq_exp"].view(B_, L0, -1), (0, 0, 0, n), value=1.0).reshape(B_ * FAST_L, -1),
+                            "z": F.pad(d["z"], (0, 0, 0, n)), "axis": F.pad(d["axis"], (0, 0, 0, n), value=1.0),
+                            "hist_exp": d["hist_exp"], "jitter": F.pad(d["jitter"], (0, n)), "gauss": F.pad(d["gauss"], (0, n))}
+                pad_noise = {k: pn(v) for k, v in noises.items()}
+            out = self.sample_from_context(
+                F.pad(seq_idx, (0, n)), F.pad(translations, (0, 0, 0, n)), torch.cat([orientations, eye], dim=1),
+                F.pad(res_context_emb, (0, 0, 0, n)), F.pad(pair_context_emb, (0, 0, 0, n, 0, n)),
+                F.pad(generation_mask, (0, n)), noises=pad_noise, generator=generator, t_start=t_start, t_stop=t_stop,
+                use_cuda_graph=use_cuda_graph, _valid_len=L0)
+            return {k: v[:, :L0].contiguous() for k, v in out.items()}
         s, x, O = seq_idx.clone(), translations.clone().contiguous(), orientations.clone().contiguous()
         B, L = s.shape
         dev = s.device
@@ -1258,8 +1280,10 @@ class DiffAb(nn.Module):
         with _tf32_matmuls(pair_context_emb.dtype == torch.bfloat16):
             if use_cuda_graph and generator is None:
                 return self._sample_graphed(s, x, O, res_context_emb, pair_context_emb, generation_mask, t_start,
-                                            t_stop, noises)
+                                            t_stop, noises, _valid_len)
             pair_bias = self._pair_bias_planes(pair_context_emb)
+            if pair_bias is not None and _valid_len is not None:
+                _mask_padded_keys(pair_bias, _valid_len)
             glue = self.denoiser.sampling_cache(res_context_emb) if pair_context_emb.dtype == torch.bfloat16 else None
             for step in range(t_start, t_stop - 1, -1):
                 t = torch.full((B,), step, device=dev, dtype=torch.int64)
@@ -1282,7 +1306,7 @@ class DiffAb(nn.Module):
         bufs["seq_exp"].exponential_(); bufs["z"].normal_(); bufs["axis"].normal_()
         bufs["hist_exp"].exponential_(); bufs["jitter"].uniform_(); bufs["gauss"].normal_()
 
-    def _sample_graphed(self, s, x, O, res_ctx, pair_ctx, generation_mask, t_start, t_stop, noises=None):
+    def _sample_graphed(self, s, x, O, res_ctx, pair_ctx, generation_mask, t_start, t_stop, noises=None, valid_len=None):
         """Reverse steps captured in CUDA graphs and replayed; the step index lives in a device tensor.
         The graphs work on static buffers (state, context, mask, pair-bias planes, noise) and are cached per shape and
         weight generation, so repeated ``sample()`` calls only copy their context in (~1 GB device-to-device, well
@@ -1312,6 +1336,8 @@ class DiffAb(nn.Module):
                 st["bias_all"] = torch.empty(len(layers), B, L, L, layers[0].n_head, device=dev, dtype=torch.float16)
                 st["bias"] = list(st["bias_all"].unbind(0))
             self.denoiser.ipa.precompute_pair_bias(st["pair"], out=st["bias_all"])
+            if valid_len is not None:          # padded batch of shorter patches: the padded keys are never attended to
+                st["bias_all"][:, :, :, valid_len:, :] = float("-inf")
             st["glue"] = self.denoiser.sampling_cache(st["res"], cache=st["glue"])
         if fresh:
             st["s"].copy_(s); st["x"].copy_(x); st["O"].copy_(O)
@@ -1415,7 +1441,8 @@ class DiffAb(nn.Module):
         backbone_dihedrals = torch.zeros(B, L, 3, device=dev) if backbone_dihedrals is None else mv(backbone_dihedrals)
         pairwise_dihedrals = torch.zeros(B, L, L, 2, device=dev) if pairwise_dihedrals is None else mv(pairwise_dihedrals)
         distmat = mv(distmat)
-        use_bf16 = precision == "bf16" and self.denoiser.ipa.layers[0].fast_path_supported(L)
+        layer0 = self.denoiser.ipa.layers[0]
+        use_bf16 = precision == "bf16" and (layer0.fast_path_supported(L) or (L < FAST_L and layer0.fast_path_supported(FAST_L)))
         res_parts, pair_parts = [], []
         fused_pair = (use_bf16 and distmat is None and self.pair_context_embedding.fused_supported(L, A))
         from .synth import pairwise_atom_distances, pairwise_atom_sq_distances

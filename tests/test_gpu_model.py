@@ -484,3 +484,38 @@ def test_sample_on_ragged_patches_from_the_reader(tmp_path):
     step = (a32["translations"] - x.to(DEV)).norm(dim=-1)[b["generation_mask"]].mean()
     assert float((a32["translations"] - a16["translations"]).norm(dim=-1).max() / step) < 2e-2
     assert float((a32["orientations"] - a16["orientations"]).abs().max()) < 5e-2
+
+
+def test_shorter_patches_sample_on_the_tensor_core_path():
+    """L = 100 < 128: sample() runs the bf16 tensor-core path on a padded batch whose padded keys are masked, so one
+    reverse step agrees with the fp32 kernels on the unpadded batch (same injected draws), eagerly and from the graphs."""
+    from diffab_pytorch_b200.diffab_pytorch import cast_pair_to_bf16
+    model = _model(0)
+    L = 100
+    batch = synth.make_patches(2, L, seed=21, cdr=(40, 52))
+    b = _to(batch)
+    m = batch["generation_mask"]
+    with torch.no_grad():
+        res, pair = model.encode_context(b["seq_idx"], b["xyz"], b["orientations"], b["backbone_dihedrals"], b["distmat"],
+                                         b["pairwise_dihedrals"], b["atom_mask"], b["chain_idx"], b["residue_idx"],
+                                         b["generation_mask"], b["residue_mask"])
+    gen = torch.Generator().manual_seed(5)
+    s, x, O = osamp.draw_initial_state(batch["seq_idx"], batch["xyz"][:, :, 1], batch["orientations"], m, generator=gen)
+    noise = {50: _to(osamp.draw_step_noise(2, L, generator=gen))}
+    args = (s.to(DEV), x.to(DEV), O.to(DEV), res)
+    a32 = model.sample_from_context(*args, pair, b["generation_mask"], noises=noise, t_start=50, t_stop=50)
+    outs = [model.sample_from_context(*args, cast_pair_to_bf16(pair), b["generation_mask"], noises=noise, t_start=50,
+                                      t_stop=50, use_cuda_graph=g) for g in (False, True)]
+    for k in outs[0]:
+        assert outs[0][k].shape == a32[k].shape and torch.equal(outs[0][k], outs[1][k]), k
+    a16 = outs[0]
+    step = (a32["translations"] - x.to(DEV)).norm(dim=-1)[b["generation_mask"]].mean()
+    assert float((a32["translations"] - a16["translations"]).norm(dim=-1).max() / step) < 2e-2
+    assert float((a32["orientations"] - a16["orientations"]).abs().max()) < 5e-2
+    assert torch.equal(a16["seq_idx"].cpu()[~m], batch["seq_idx"][~m])
+    # end to end through sample(): host tensors in, the tensor-core path picked for L < 128
+    out = model.sample(batch["seq_idx"], batch["xyz"], batch["orientations"], batch["backbone_dihedrals"], None,
+                       batch["pairwise_dihedrals"], batch["atom_mask"], batch["chain_idx"], batch["residue_idx"],
+                       batch["generation_mask"], batch["residue_mask"], t_start=100, t_stop=97)
+    assert out["seq_idx"].shape == (2, L) and torch.isfinite(out["translations"]).all()
+    assert torch.equal(out["translations"].cpu()[~m], batch["xyz"][:, :, 1][~m])
