@@ -25,15 +25,21 @@ struct ProjSmem {
   static constexpr int kWStage = 2 * 64 * 128;        // 16,384: [kb(2)][64 rows][128 B]
   static constexpr int kWStages = 3;
   static constexpr int kW = kA + kABytes;
-  static constexpr int kMisc = kW + kWStages * kWStage;   // 81,920
-  static constexpr int kBars = kMisc;                 // 16 mbarriers
-  static constexpr int kTmemSlot = kBars + 16 * 8;
-  static constexpr int kCen = kTmemSlot + 16;         // centroid partials [4][3] + result [3]
-  static constexpr int kStage = kMisc + 512;          // per-warp staging: two [32 rows][64 B] tiles, 64B-swizzled
+  static constexpr int kStage = kW + kWStages * kWStage;   // 81,920: per-warp staging, two [32 rows][64 B] tiles, 64B-swizzled
   static constexpr int kStageGroup = 2 * 8192;        // (512-byte aligned), the source of the TMA stores; 4 warps per group
-  static constexpr int kTotal = kStage + 2 * kStageGroup;   // 115,200: two CTAs per SM, exactly
+  static constexpr int kMisc = kStage + 2 * kStageGroup;   // 114,688
+  static constexpr int kBars = kMisc;                 // 24 mbarriers
+  static constexpr int kTmemSlot = kBars + 24 * 8;
+  static constexpr int kCen = kTmemSlot + 16;         // centroid partials [4][3] + result [3]
+  static constexpr int kTotal = kMisc + 512;          // 115,200: two CTAs per SM, exactly
+  // fused to_out phase (the previous layer's y = cat Wout^T + b, computed straight into the A tile): ring of three 32 KB
+  // stages [128 rows of cat | 128 rows of Wout] x 64 K columns, in regions that are idle until the projections start
+  static constexpr int kGStage0 = kA, kGStage1 = kW, kGStage2 = kStage;
+  static constexpr int kGStageBytes = 32768;
 };
-enum ProjBar { W_FULL = 0, W_EMPTY = 3, ACC_FULL = 6, ACC_EMPTY = 8, PROJ_N_BARS = 10 };
+static_assert(ProjSmem::kW + ProjSmem::kGStageBytes <= ProjSmem::kStage && ProjSmem::kStage % 1024 == 0, "to_out ring layout");
+enum ProjBar { W_FULL = 0, W_EMPTY = 3, ACC_FULL = 6, ACC_EMPTY = 8, G_FULL = 10, G_EMPTY = 13, G_DONE = 16, A_READY = 17,
+               PROJ_N_BARS = 18 };
 
 constexpr int kProjTiles = 24;   // 12 scalar tiles (q,k,v x 4 head pairs) + 12 point tiles
 
@@ -53,7 +59,8 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
                 const __grid_constant__ CUtensorMap map_sv, const float* __restrict__ x, const float* __restrict__ R, const float* __restrict__ t,
                 const float* __restrict__ gamma, __nv_bfloat16* __restrict__ Qp, __nv_bfloat16* __restrict__ Kp,
                 __nv_bfloat16* __restrict__ Vp, float* __restrict__ tc, long long* __restrict__ dbg,
-                const __nv_bfloat16* __restrict__ x16) {
+                const __nv_bfloat16* __restrict__ x16, const __grid_constant__ CUtensorMap map_cat,
+                const __grid_constant__ CUtensorMap map_wout, const float* __restrict__ b_out, int fuse_out) {
   long long* dbg_cta = dbg ? dbg + (size_t)blockIdx.y * 64 : nullptr;   // (split 0 of) one patch per record
 #define PROJ_STAMP(k) do { if (dbg_cta && threadIdx.x == 0) dbg_cta[(k)] = clock64(); } while (0)
   PROJ_STAMP(0);
@@ -71,7 +78,8 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
   if ((smem_base & 1023u) != 0) asm volatile("trap;");
 
   if (tid == 0) {
-    for (int i = 0; i < PROJ_N_BARS; ++i) mbar_init(&bars[i], (i == ACC_EMPTY || i == ACC_EMPTY + 1) ? 128u : 1u);
+    for (int i = 0; i < PROJ_N_BARS; ++i)
+      mbar_init(&bars[i], (i == ACC_EMPTY || i == ACC_EMPTY + 1) ? 128u : (i == A_READY ? 256u : 1u));
     fence_barrier_init();
   }
   __syncwarp();
@@ -80,7 +88,9 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
   if (warp < 8) {
     // ---- x tile: fp32 global (coalesced float4) -> bf16, K-major 128B-swizzled A operand (16 rows per warp)
     const uint32_t kb = lane >> 4, chunk = (lane & 15) >> 1, half = (lane & 1) * 8;
-    if (x16 != nullptr) {   // the previous layer's to_out GEMM already rounded its output to bf16: straight copy
+    if (fuse_out) {
+      // the A tile is produced in place by the fused to_out phase below
+    } else if (x16 != nullptr) {   // the previous layer's to_out GEMM already rounded its output to bf16: straight copy
       const __nv_bfloat16* xb = x16 + (int64_t)b * L * D;
 #pragma unroll
       for (int rr = 0; rr < 16; ++rr) {
@@ -126,12 +136,56 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
       tma_load_2d(dst, m, &bars[W_FULL + s], 0, tile_row0(tt));            // K 0..63
       tma_load_2d(dst + rows * 128, m, &bars[W_FULL + s], 64, tile_row0(tt));  // K 64..127
     };
+    if (fuse_out) {
+      // ---- fused to_out of the previous layer: acc[128 residues x 128] = cat[128 x 1024] Wout^T, 16 K chunks of 64
+      constexpr uint32_t idesc_g = make_idesc_bf16(128, 128, 0, 0);
+      const int g_off[3] = {S::kGStage0, S::kGStage1, S::kGStage2};
+      auto load_g = [&](int kc) {     // ONE lane
+        const int st = kc % 3;
+        uint8_t* dst = smem + g_off[st];
+        mbar_arrive_expect_tx(&bars[G_FULL + st], S::kGStageBytes);
+        tma_load_2d(dst, &map_cat, &bars[G_FULL + st], kc * 64, b * L);
+        tma_load_2d(dst + 16384, &map_wout, &bars[G_FULL + st], kc * 64, 0);
+      };
+      if (elect_one()) {
+        tma_prefetch_desc(&map_cat); tma_prefetch_desc(&map_wout);
+        tma_prefetch_desc(&map_w64); tma_prefetch_desc(&map_w48);
+        for (int kc = 0; kc < 3; ++kc) load_g(kc);
+      }
+      __syncwarp();
+      constexpr int kChunks = 1024 / 64;
+      for (int kc = 0; kc < kChunks; ++kc) {
+        const int st = kc % 3;
+        mbar_wait(&bars[G_FULL + st], (kc / 3) & 1);
+        tcgen05_fence_after_sync();
+        if (elect_one()) {
+          const uint64_t da = make_smem_desc(smem_base + g_off[st], 16, 1024, kSwizzle128B);
+          const uint64_t db = make_smem_desc(smem_base + g_off[st] + 16384, 16, 1024, kSwizzle128B);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem, da + (uint32_t)((kk * 32) >> 4), db + (uint32_t)((kk * 32) >> 4), idesc_g, (kc | kk) != 0);
+          umma_commit(&bars[G_EMPTY + st]);
+          if (kc == kChunks - 1) umma_commit(&bars[G_DONE]);
+        }
+        __syncwarp();
+        if (kc + 3 < kChunks) {
+          mbar_wait(&bars[G_EMPTY + st], (kc / 3) & 1);
+          if (elect_one()) load_g(kc + 3);
+          __syncwarp();
+        }
+      }
+      // the projections' weight ring and the A tile share the to_out ring's memory: every to_out MMA must have completed
+      mbar_wait(&bars[G_DONE], 0);
+    }
     if (elect_one()) {
-      tma_prefetch_desc(&map_w64);
-      tma_prefetch_desc(&map_w48);
+      if (!fuse_out) { tma_prefetch_desc(&map_w64); tma_prefetch_desc(&map_w48); }
       for (int k = 0; k < S::kWStages && k < n_local; ++k) load_w(split + k * n_split, k);
     }
     __syncwarp();
+    if (fuse_out) {                  // the epilogue warps have written y (bf16) into the A tile and left the accumulator
+      mbar_wait(&bars[A_READY], 0);
+      tcgen05_fence_after_sync();
+    }
     const uint64_t dA0 = make_smem_desc(smem_base + S::kA, 16, 1024, kSwizzle128B);
     const uint64_t dW0 = make_smem_desc(smem_base + S::kW, 16, 1024, kSwizzle128B);
     for (int k = 0; k < n_local; ++k) {       // k-th tile of this CTA = global tile tt
@@ -174,6 +228,28 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
     const float tcx = __ldg(t + row * 3) - cenx, tcy = __ldg(t + row * 3 + 1) - ceny, tcz = __ldg(t + row * 3 + 2) - cenz;
     if (g == 0 && split == 0) { tc[row * 3] = tcx; tc[row * 3 + 1] = tcy; tc[row * 3 + 2] = tcz; }
     const float ss = rsqrtf((float)DS), sp = rsqrtf(4.5f * P), st = rsqrtf(3.0f);
+    if (fuse_out) {
+      // y = acc + b_out of the previous layer, rounded to bf16 exactly as its to_out GEMM would have written it, goes
+      // straight into the A tile (K-major, 128B swizzle): group g converts columns 64 g .. 64 g + 63 = K block g
+      mbar_wait(&bars[G_DONE], 0);
+      tcgen05_fence_after_sync();
+      float a[32], c[32];
+      tmem_ld_x32(tmem_lane + g * 64, a);
+      tmem_ld_x32(tmem_lane + g * 64 + 32, c);
+      tmem_wait_ld();
+      uint8_t* arow = smem + S::kA + g * 16384;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float* v8 = q < 4 ? a + 8 * q : c + 8 * (q - 4);
+        const float* b8 = b_out + g * 64 + 8 * q;
+        *reinterpret_cast<uint4*>(arow + swz128_offset(gt, q)) =
+            make_uint4(pk_bf(v8[0] + __ldg(b8), v8[1] + __ldg(b8 + 1)), pk_bf(v8[2] + __ldg(b8 + 2), v8[3] + __ldg(b8 + 3)),
+                       pk_bf(v8[4] + __ldg(b8 + 4), v8[5] + __ldg(b8 + 5)), pk_bf(v8[6] + __ldg(b8 + 6), v8[7] + __ldg(b8 + 7)));
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before_sync();
+      mbar_arrive(&bars[A_READY]);
+    }
     // Every output segment is 64 bytes per residue (a head's scalars, point-hi or point-lo columns).  A thread
     // drops its segment into a warp-private [32 rows][64 B] shared-memory tile (64B swizzle: conflict-free 16-byte
     // stores) and lane 0 hands the tile to the TMA as a 2-D store (row pitch = the packed row).  Two tiles per warp

@@ -916,6 +916,45 @@ int dab_ipa_pair_bias_multi(const DabIpaDims* d, const void* e_bf16, const float
   return check_launch("dab_ipa_pair_bias_multi");
 }
 
+// Projection launch of a layer (weights `pk`), packed operands into `ws`.  With `pk_prev` the kernel first computes the
+// PREVIOUS layer's to_out, y = cat Wout^T + b (cat = ws.cat, weights pk_prev), straight into its A tile: x is not read.
+static int launch_proj(int B, const uint8_t* pk, const float* x, const __nv_bfloat16* x16, const float* R, const float* t,
+                       const Ws& ws, const uint8_t* pk_prev, cudaStream_t s) {
+  const PackedOffsets po = packed_offsets();
+  const int M = B * L;
+  CUtensorMap mw64, mw48;
+  uint64_t dw[2] = {(uint64_t)D, (uint64_t)NPROJ}, sw[1] = {(uint64_t)D * 2};
+  uint32_t b64[2] = {64, 64}, b48[2] = {64, 48};
+  if (int rc = make_tensor_map_bf16(&mw64, pk + po.wcat, 2, dw, sw, b64, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  if (int rc = make_tensor_map_bf16(&mw48, pk + po.wcat, 2, dw, sw, b48, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  DAB_ENSURE_SMEM(ipa_proj_kernel, ProjSmem::kTotal);
+  CUtensorMap msq, msk, msv;   // TMA-store views of the packed operands: 64-byte segments of 32 rows
+  {
+    uint64_t dqk[2] = {(uint64_t)H * QK_W, (uint64_t)M}, sqk[1] = {(uint64_t)H * QK_W * 2};
+    uint64_t dv[2] = {(uint64_t)H * V_W, (uint64_t)M}, sv[1] = {(uint64_t)H * V_W * 2};
+    uint32_t bs[2] = {32, 32};     // one warp's rows
+    if (int rc = make_tensor_map_bf16(&msq, ws.Qp, 2, dqk, sqk, bs, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    if (int rc = make_tensor_map_bf16(&msk, ws.Kp, 2, dqk, sqk, bs, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    if (int rc = make_tensor_map_bf16(&msv, ws.Vp, 2, dv, sv, bs, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+  }
+  CUtensorMap mcat = mw64, mwout = mw64;     // (placeholders when the to_out phase is off)
+  const float* b_out = nullptr;
+  int n_split = B >= 128 ? 1 : (B >= 64 ? 2 : 4);   // small batches: several CTAs per patch
+  if (pk_prev) {
+    uint64_t dc[2] = {(uint64_t)NCAT, (uint64_t)M}, dwo[2] = {(uint64_t)NCAT, (uint64_t)D}, sc[1] = {(uint64_t)NCAT * 2};
+    uint32_t bc[2] = {64, 128};
+    if (int rc = make_tensor_map_bf16(&mcat, ws.cat, 2, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_tensor_map_bf16(&mwout, pk_prev + po.wout, 2, dwo, sc, bc, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    b_out = reinterpret_cast<const float*>(pk_prev + po.bout);
+    n_split = 1;                             // the to_out phase produces the whole A tile of the patch
+  }
+  ipa_proj_kernel<<<dim3(n_split, B), 288, ProjSmem::kTotal, s>>>(
+      mw64, mw48, msq, msk, msv, x, R, t, reinterpret_cast<const float*>(pk + po.gamma), ws.Qp, ws.Kp, ws.Vp, ws.tc,
+      g_core_dbg ? g_core_dbg + (1 << 20) : nullptr, x16, mcat, mwout, b_out, pk_prev ? 1 : 0);
+  count_launch();
+  return DAB_OK;
+}
+
 // x / y: fp32, or (x_bf16 / y_bf16 non-null) bf16 - the residue stream handed from layer to layer already rounded
 static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* x, const void* e_bf16,
                           const void* bias_f16, const float* R, const float* t, float* y, void* workspace,
@@ -937,26 +976,7 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
   cudaStream_t s = (cudaStream_t)stream;
   if (phases & 1) {
-    CUtensorMap mw64, mw48;
-    uint64_t dw[2] = {(uint64_t)D, (uint64_t)NPROJ}, sw[1] = {(uint64_t)D * 2};
-    uint32_t b64[2] = {64, 64}, b48[2] = {64, 48};
-    if (int rc = make_tensor_map_bf16(&mw64, pk + po.wcat, 2, dw, sw, b64, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    if (int rc = make_tensor_map_bf16(&mw48, pk + po.wcat, 2, dw, sw, b48, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    DAB_ENSURE_SMEM(ipa_proj_kernel, ProjSmem::kTotal);
-    CUtensorMap msq, msk, msv;   // TMA-store views of the packed operands: 64-byte segments of 32 rows
-    {
-      uint64_t dqk[2] = {(uint64_t)H * QK_W, (uint64_t)M}, sqk[1] = {(uint64_t)H * QK_W * 2};
-      uint64_t dv[2] = {(uint64_t)H * V_W, (uint64_t)M}, sv[1] = {(uint64_t)H * V_W * 2};
-      uint32_t bs[2] = {32, 32};     // one warp's rows
-      if (int rc = make_tensor_map_bf16(&msq, ws.Qp, 2, dqk, sqk, bs, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
-      if (int rc = make_tensor_map_bf16(&msk, ws.Kp, 2, dqk, sqk, bs, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
-      if (int rc = make_tensor_map_bf16(&msv, ws.Vp, 2, dv, sv, bs, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
-    }
-    const int n_split = B >= 128 ? 1 : (B >= 64 ? 2 : 4);   // small batches: several CTAs per patch
-    ipa_proj_kernel<<<dim3(n_split, B), 288, ProjSmem::kTotal, s>>>(mw64, mw48, msq, msk, msv, x, R, t, reinterpret_cast<const float*>(pk + po.gamma),
-                                                     ws.Qp, ws.Kp, ws.Vp, ws.tc, g_core_dbg ? g_core_dbg + (1 << 20) : nullptr,
-                                                     reinterpret_cast<const __nv_bfloat16*>(x_bf16));
-    count_launch();
+    if (int rc = launch_proj(B, pk, x, reinterpret_cast<const __nv_bfloat16*>(x_bf16), R, t, ws, nullptr, s)) return rc;
   }
   if (phases & 2) {
     const uint4* bias = reinterpret_cast<const uint4*>(bias_f16);
@@ -1048,6 +1068,28 @@ int dab_ipa_fwd_sm100_stages(const DabIpaDims* d, const void* packed, const floa
   DAB_REQUIRE(stages > 0 && stages <= 7, DAB_EINVAL, "dab_ipa_fwd_sm100_stages: stages must be a non-empty subset of bits 0..2");
   return fwd_sm100_impl(d, packed, x, e_bf16, bias_f16, R, t, y, workspace, workspace_bytes, false, stream, x_bf16, y_bf16,
                         stages);
+}
+
+/* Between two layers of a stack (inference): the previous layer's to_out (y = cat Wout^T + b, `packed_prev`; `cat` = the
+ * concat features its attention core left in `workspace`) fused with this layer's projections (`packed`): y is rounded to
+ * bf16 exactly as dab_ipa_fwd_sm100_io would hand it over, but goes straight into the projection kernel's operand tile
+ * and never exists in HBM; the packed Q / K / V of this layer replace those of the previous one in `workspace`.
+ * Sequence for a stack: stages(1) of layer 0, then per layer stages(2) followed by dab_ipa_mid_sm100 (or stages(4) after
+ * the last layer).  Bit-identical to the unfused sequence. */
+int dab_ipa_mid_sm100(const DabIpaDims* d, const void* packed_prev, const void* packed, const float* R, const float* t,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED, "dab_ipa_mid_sm100: the sm_100a fast path needs the train.py configuration");
+  if (d->B == 0) return DAB_OK;
+  DAB_REQUIRE(packed_prev && packed && R && t && workspace, DAB_EINVAL, "dab_ipa_mid_sm100: null pointer");
+  DAB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0 && (reinterpret_cast<uintptr_t>(packed) & 1023) == 0 &&
+                  (reinterpret_cast<uintptr_t>(packed_prev) & 1023) == 0,
+              DAB_EINVAL, "dab_ipa_mid_sm100: workspace / packed weights must be 1024-byte aligned");
+  Ws ws = carve_ws(d->B, workspace);
+  DAB_REQUIRE(workspace_bytes >= ws.bytes, DAB_EWORKSPACE, "dab_ipa_mid_sm100: workspace %zu < %zu", workspace_bytes, ws.bytes);
+  if (int rc = launch_proj(d->B, reinterpret_cast<const uint8_t*>(packed), nullptr, nullptr, R, t, ws,
+                           reinterpret_cast<const uint8_t*>(packed_prev), (cudaStream_t)stream))
+    return rc;
+  return check_launch("dab_ipa_mid_sm100");
 }
 
 /* C[M,N] = A[M,K] B[N,K]^T + bias on the tcgen05 GEMM (bf16 operands, fp32 result; M % 128 == 0, N % 64 == 0, K % 64 == 0):

@@ -815,6 +815,10 @@ class InvariantPointAttentionModule(nn.Module):
                 self.layers[0].fast_path_supported(pair_emb.shape[1])):
             # inference on the tensor-core path: the residue stream travels between the layers as bf16
             n = len(self.layers)
+            if res_emb.shape[0] >= 128:
+                # large batches (one projection CTA per patch): each layer's to_out is fused into the next layer's
+                # projection kernel, the stream between the layers never exists in HBM (bit-identical)
+                return self._forward_fused_stack(res_emb, pair_emb, orientations, translations, pair_bias)
             for k, layer in enumerate(self.layers):
                 res_emb = layer.forward_fast_io(res_emb, pair_emb, orientations, translations, pair_bias[k],
                                                 torch.float32 if k == n - 1 else torch.bfloat16)
@@ -829,6 +833,42 @@ class InvariantPointAttentionModule(nn.Module):
             else:
                 res_emb = layer(res_emb, pairs[k], orientations, translations)
         return res_emb
+
+    @torch.no_grad()
+    def _forward_fused_stack(self, res_emb, pair_emb, orientations, translations, pair_bias):
+        """The layer stack launch by launch on ONE shared workspace: projections of layer 0, then per layer the attention
+        core followed by ``dab_ipa_mid_sm100`` (its to_out + the next layer's projections in one kernel), to_out of the
+        last layer.  2 n launches instead of 3 n; results bit-identical to ``forward_fast_io`` layer by layer."""
+        layers = self.layers
+        n = len(layers)
+        B, L, D = res_emb.shape
+        x = _lib.dev(res_emb, res_emb.dtype if res_emb.dtype == torch.bfloat16 else torch.float32, "x")
+        e = _lib.dev(pair_emb, torch.bfloat16, "e")
+        r = _lib.dev(orientations, torch.float32, "r")
+        t = _lib.dev(translations, torch.float32, "t")
+        bias = [_lib.dev(p_, torch.float16, "pair_bias") for p_ in pair_bias]
+        dims = _ipa_structs(layers[0], B, L)
+        lib = _lib.lib()
+        st = _lib.stream_ptr()
+        packed = [layer._packed_weights(dims) for layer in layers]
+        ws = layers[0]._workspace(max(lib.dab_ipa_sm100_workspace_bytes(ctypes.byref(dims)), 16), x.device)
+        y = torch.empty(B, L, D, device=x.device, dtype=torch.float32)
+        x32, x16 = (None, x) if x.dtype == torch.bfloat16 else (x, None)
+
+        def stage(k, stages):     # (x is read by stage 1 only, y written by stage 4 only)
+            _lib.check(lib.dab_ipa_fwd_sm100_stages(
+                ctypes.byref(dims), ptr(packed[k]), ptr(x32), ptr(x16), ptr(e), ptr(bias[k]), ptr(r), ptr(t), ptr(y), None,
+                ptr(ws), ws.numel(), stages, st), "dab_ipa_fwd_sm100_stages")
+
+        stage(0, 1)
+        for k in range(n):
+            stage(k, 2)
+            if k + 1 < n:
+                _lib.check(lib.dab_ipa_mid_sm100(ctypes.byref(dims), ptr(packed[k]), ptr(packed[k + 1]), ptr(r), ptr(t), ptr(ws),
+                                                 ws.numel(), st), "dab_ipa_mid_sm100")
+            else:
+                stage(k, 4)
+        return y
 
     def precompute_pair_bias(self, pair_emb_bf16, out=None):
         """Per-layer pair-bias planes for the sm_100a path: one pass over the pair tensor for all layers

@@ -183,6 +183,13 @@ int dab_ipa_fwd_sm100_io(const DabIpaDims* d, const void* packed, const float* x
 int dab_ipa_fwd_sm100_stages(const DabIpaDims* d, const void* packed, const float* x, const void* x_bf16, const void* e_bf16,
                              const void* bias_f16, const float* R, const float* t, float* y, void* y_bf16, void* workspace,
                              size_t workspace_bytes, int stages, void* stream);
+/* Between two layers of a stack (inference): the previous layer's to_out (`packed_prev`; input = the concat features its
+ * attention core left in `workspace`) fused into this layer's projection kernel (`packed`): y is rounded to bf16 as
+ * dab_ipa_fwd_sm100_io would hand it over but never exists in HBM.  Stack = stages(1) of layer 0, then per layer stages(2)
+ * + dab_ipa_mid_sm100 (stages(4) after the last layer); bit-identical to the unfused sequence
+ * (InvariantPointAttentionModule.forward, diffab_pytorch.py:494-498). */
+int dab_ipa_mid_sm100(const DabIpaDims* d, const void* packed_prev, const void* packed, const float* R, const float* t,
+                      void* workspace, size_t workspace_bytes, void* stream);
 /* Training pair of the sm_100a path (bf16 pair tensor, fp32 x / y).  The forward is dab_ipa_fwd_sm100 (the pair
  * bias is rebuilt inside the call when bias_f16 is NULL); `saved` (dab_ipa_sm100_workspace_bytes) additionally keeps
  * the packed operands, the concat features, the un-normalised probabilities and the softmax statistics, and must

@@ -361,3 +361,29 @@ def test_tensor_core_path_for_shorter_patches(L):
     assert got.shape == (2, L, 128) and _rel(got, ref) < 3e-2
     got_t = mod(x.to(DEV).requires_grad_(True), e16.to(DEV), R.to(DEV), t.to(DEV))     # training path of the stack
     assert _rel(got_t.detach(), ref) < 3e-2
+
+
+def test_fused_stack_is_bit_identical_to_the_layerwise_stack():
+    """dab_ipa_mid_sm100 (a layer's to_out fused into the next layer's projection kernel, used for batches >= 128): the
+    six-layer stack gives the same bits as the layer-by-layer bf16 hand-off, for fp32 and for bf16 input."""
+    torch.manual_seed(0)
+    B = 128
+    mod = InvariantPointAttentionModule(6, 128, 64, 32, 8, 8, 8).to(DEV)
+    shp = synth.ipa_layer_shapes(128, 64, 8, 32, 8, 8)
+    for k_, lay in enumerate(mod.layers):
+        lay.load_state_dict(synth.synthetic_state(shp, seed=20 + k_))
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(B, 128, 128, device=DEV, generator=g)
+    e = torch.randn(B, 128, 128, 64, device=DEV, generator=g).bfloat16()
+    R = synth.uniform_rotations(B, 128, device=DEV)
+    t = 10 * torch.randn(B, 128, 3, device=DEV, generator=g)
+    with torch.no_grad():
+        planes = mod.precompute_pair_bias(e)
+        for xin in (x, x.bfloat16()):
+            fused = mod._forward_fused_stack(xin, e, R, t, planes)
+            h = xin
+            for k_, lay in enumerate(mod.layers):
+                h = lay.forward_fast_io(h, e, R, t, planes[k_], torch.float32 if k_ == 5 else torch.bfloat16)
+            assert torch.isfinite(fused).all()
+            assert torch.equal(fused, h)
+        assert torch.equal(mod(x, e, R, t, planes), fused)          # the module picks the fused stack at this batch size
