@@ -800,9 +800,9 @@ extern "C" {
 
 size_t dab_ipa_bwd_sm100_workspace_bytes(const DabIpaDims* d) { return shape_ok(d) ? carve_bwd(d->B, nullptr).bytes : 0; }
 
-int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf16, const float* R, const float* dcat,
-                      void* saved, size_t saved_bytes, void* dproj_bf16, void* de_bf16, float* d_w_pair_bias, float* d_gamma,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+static int bwd_sm100_impl(const DabIpaDims* d, const void* packed, const void* e_bf16, const float* R, const float* dcat,
+                          void* saved, size_t saved_bytes, void* dproj_bf16, void* de_bf16, float* d_w_pair_bias, float* d_gamma,
+                          void* workspace, size_t workspace_bytes, void* stream, int parts) {
   DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
               "dab_ipa_bwd_sm100: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
   if (d->B == 0) return DAB_OK;
@@ -823,6 +823,13 @@ int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf1
   const float* gamma = reinterpret_cast<const float*>(pk + po.gamma);
   cudaStream_t s = (cudaStream_t)stream;
 
+  if (!(parts & 1)) {   // only the final reductions: d_w_pair_bias / d_gamma from the partial sums of an earlier main pass
+    bwd_reduce_kernel<<<kRedBlocks, 512, 0, s>>>(bw.p_wpb, B * 8, bw.p_g1, bw.p_g2, B, bw.r_part);
+    count_launch();
+    bwd_finalize_kernel<<<1, 512, 0, s>>>(bw.r_part, wpb, gamma, d_w_pair_bias, d_gamma);
+    count_launch();
+    return check_launch("dab_ipa_bwd_sm100_finish");
+  }
   bwd_prep_kernel<<<M, 256, 0, s>>>(dcat, ws.cat, R, ws.tc, bw.dO16, bw.dObf, bw.dopair, bw.delta, bw.rscale);
   count_launch();
 
@@ -863,11 +870,37 @@ int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf1
                                                             reinterpret_cast<__nv_bfloat16*>(dproj_bf16), bw.p_g2,
                                                             g_bwd_keep_qkv ? bw.dQ : nullptr);
   count_launch();
-  bwd_reduce_kernel<<<kRedBlocks, 512, 0, s>>>(bw.p_wpb, B * 8, bw.p_g1, bw.p_g2, B, bw.r_part);
-  count_launch();
-  bwd_finalize_kernel<<<1, 512, 0, s>>>(bw.r_part, wpb, gamma, d_w_pair_bias, d_gamma);
-  count_launch();
+  if (parts & 2) {
+    bwd_reduce_kernel<<<kRedBlocks, 512, 0, s>>>(bw.p_wpb, B * 8, bw.p_g1, bw.p_g2, B, bw.r_part);
+    count_launch();
+    bwd_finalize_kernel<<<1, 512, 0, s>>>(bw.r_part, wpb, gamma, d_w_pair_bias, d_gamma);
+    count_launch();
+  }
   return check_launch("dab_ipa_bwd_sm100");
+}
+
+int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf16, const float* R, const float* dcat,
+                      void* saved, size_t saved_bytes, void* dproj_bf16, void* de_bf16, float* d_w_pair_bias, float* d_gamma,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_sm100_impl(d, packed, e_bf16, R, dcat, saved, saved_bytes, dproj_bf16, de_bf16, d_w_pair_bias, d_gamma, workspace,
+                        workspace_bytes, stream, 3);
+}
+
+/* The same backward in two calls, so that a caller can overlap what depends only on dproj (dx, dWcat) with the final
+ * reductions: `_main` = everything up to dproj / de and the per-CTA partial sums, `_finish` = d_w_pair_bias / d_gamma from
+ * those partial sums (same arguments; it reads only packed, d_w_pair_bias, d_gamma and the workspace).  May run on
+ * different streams if the caller orders _finish after _main. */
+int dab_ipa_bwd_sm100_main(const DabIpaDims* d, const void* packed, const void* e_bf16, const float* R, const float* dcat,
+                           void* saved, size_t saved_bytes, void* dproj_bf16, void* de_bf16, float* d_w_pair_bias,
+                           float* d_gamma, void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_sm100_impl(d, packed, e_bf16, R, dcat, saved, saved_bytes, dproj_bf16, de_bf16, d_w_pair_bias, d_gamma, workspace,
+                        workspace_bytes, stream, 1);
+}
+int dab_ipa_bwd_sm100_finish(const DabIpaDims* d, const void* packed, const void* e_bf16, const float* R, const float* dcat,
+                             void* saved, size_t saved_bytes, void* dproj_bf16, void* de_bf16, float* d_w_pair_bias,
+                             float* d_gamma, void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_sm100_impl(d, packed, e_bf16, R, dcat, saved, saved_bytes, dproj_bf16, de_bf16, d_w_pair_bias, d_gamma, workspace,
+                        workspace_bytes, stream, 2);
 }
 
 #ifdef DAB_DEBUG_HOOKS

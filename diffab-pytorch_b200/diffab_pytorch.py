@@ -408,6 +408,17 @@ def _mask_padded_keys(planes, L):
     return planes
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device, which=0):
+    """Auxiliary streams (per device) for the independent branches of the backward."""
+    key = (torch.device(device).index, which)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def _ipa_structs(layer, B, L):
     dims = _lib.DabIpaDims(B, L, layer.d_residue_emb, layer.d_pair_emb, layer.n_head, layer.d_scalar_per_head,
                            layer.n_query_point_per_head, layer.n_value_point_per_head)
@@ -559,29 +570,51 @@ class _IpaFastFunction(torch.autograd.Function):
         # The plain GEMMs of the backward all run in the library on bf16 operands with fp32 accumulation and output (the
         # forward ran the same products on bf16 operands): data gradients on the K-major tcgen05 GEMM against the
         # transposed weight copies, weight gradients on the MN-major split-K GEMM straight from the activations.
+        # The weight-gradient GEMMs depend only on dy / dproj and the saved activations, and at training batch sizes every
+        # kernel of the backward is a single under-filled wave: they run on a side stream beside the main chain
+        # (dcat -> prep -> backward core -> key side -> dx) and join before the gradients are returned (fork / join is
+        # captured as parallel branches when the step is recorded into a CUDA graph).
+        main = torch.cuda.current_stream(dev_)
+        side = _side_stream(dev_)
         dy_bf = torch.empty(M, D, device=dev_, dtype=bf)
         d_b_out = torch.empty(D, device=dev_, dtype=f32)
         _lib.check(lib.dab_colsum_f32(ptr(dy2), M, D, ptr(d_b_out), ptr(dy_bf), st), "dab_colsum_f32")   # + bf16 copy of dy
+        d_w_out = torch.empty(D, ncat, device=dev_, dtype=f32)
+        d_w_cat = torch.empty(n_proj, D, device=dev_, dtype=f32)
+        x2 = x.view(M, D)
+        x_bf = torch.empty(M, D, device=dev_, dtype=bf)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            sst = _lib.stream_ptr()
+            _lib.check(lib.dab_gemm_bf16_tn(ptr(dy_bf), D, ptr(cat), ncat, ptr(d_w_out), ncat, D, ncat, M, sst),
+                       "dab_gemm_bf16_tn (dWout)")
+            _lib.check(lib.dab_cast_f32_to_bf16(ptr(x2), ptr(x_bf), x2.numel(), sst), "dab_cast_f32_to_bf16")
         dcat = torch.empty(M, ncat, device=dev_, dtype=f32)
         _lib.check(lib.dab_gemm_bf16(ptr(dy_bf), ptr(w_out_t), ptr(dcat), None, M, ncat, D, st), "dab_gemm_bf16 (dcat)")
-        d_w_out = torch.empty(D, ncat, device=dev_, dtype=f32)
-        _lib.check(lib.dab_gemm_bf16_tn(ptr(dy_bf), D, ptr(cat), ncat, ptr(d_w_out), ncat, D, ncat, M, st),
-                   "dab_gemm_bf16_tn (dWout)")
         dproj = torch.empty(M, n_proj, device=dev_, dtype=bf)
         de = torch.empty_like(e)
         zeros = torch.zeros(weights[6].numel() + weights[7].numel(), device=dev_, dtype=f32)   # one fill
         d_wpb = zeros[: weights[6].numel()].view_as(weights[6])
         d_gamma = zeros[weights[6].numel():].view_as(weights[7])
         bws = _lib.aligned_empty(max(lib.dab_ipa_bwd_sm100_workspace_bytes(ctypes.byref(dims)), 16), dev_)
-        _lib.check(lib.dab_ipa_bwd_sm100(ctypes.byref(dims), ptr(packed), ptr(e), ptr(r), ptr(dcat), ptr(saved),
-                                         saved.numel(), ptr(dproj), ptr(de), ptr(d_wpb), ptr(d_gamma), ptr(bws),
-                                         bws.numel(), st), "dab_ipa_bwd_sm100")
+        bwd_args = (ctypes.byref(dims), ptr(packed), ptr(e), ptr(r), ptr(dcat), ptr(saved), saved.numel(), ptr(dproj), ptr(de),
+                    ptr(d_wpb), ptr(d_gamma), ptr(bws), bws.numel())
+        _lib.check(lib.dab_ipa_bwd_sm100_main(*bwd_args, st), "dab_ipa_bwd_sm100_main")
         layer._last_bwd_ws = bws   # kept for tools/debug_bwd.py (intermediate buffers of the last backward)
+        # dproj is complete: three independent branches - dWcat (side), the to_pair_bias / gamma reductions (second side
+        # stream), dx (main)
+        side2 = _side_stream(dev_, 1)
+        side.wait_stream(main)
+        side2.wait_stream(main)
+        with torch.cuda.stream(side):
+            _lib.check(lib.dab_gemm_bf16_tn(ptr(dproj), n_proj, ptr(x_bf), D, ptr(d_w_cat), D, n_proj, D, M, _lib.stream_ptr()),
+                       "dab_gemm_bf16_tn (dWcat)")
+        with torch.cuda.stream(side2):
+            _lib.check(lib.dab_ipa_bwd_sm100_finish(*bwd_args, _lib.stream_ptr()), "dab_ipa_bwd_sm100_finish")
         dx = torch.empty(B, L, D, device=dev_, dtype=f32)
         _lib.check(lib.dab_gemm_bf16(ptr(dproj), ptr(w_cat_t), ptr(dx), None, M, D, n_proj, st), "dab_gemm_bf16 (dx)")
-        d_w_cat = torch.empty(n_proj, D, device=dev_, dtype=f32)
-        _lib.check(lib.dab_gemm_bf16_tn(ptr(dproj), n_proj, ptr(cast(x.view(M, D))), D, ptr(d_w_cat), D, n_proj, D, M, st),
-                   "dab_gemm_bf16_tn (dWcat)")
+        main.wait_stream(side)
+        main.wait_stream(side2)
         d_proj_w = torch.split(d_w_cat, [w.shape[0] for w in weights[:6]], dim=0)
         return (None, None, dx, de, None, None, *d_proj_w, d_wpb, d_gamma, d_w_out, d_b_out)
 

@@ -210,6 +210,15 @@ size_t dab_ipa_bwd_sm100_workspace_bytes(const DabIpaDims* d);
 int dab_ipa_bwd_sm100(const DabIpaDims* d, const void* packed, const void* e_bf16, const float* R, const float* dcat,
                       void* saved, size_t saved_bytes, void* dproj_bf16, void* de_bf16, float* d_w_pair_bias, float* d_gamma,
                       void* workspace, size_t workspace_bytes, void* stream);
+/* The same backward in two calls (same arguments): `_main` = everything up to dproj / de and the per-CTA partial sums,
+ * `_finish` = d_w_pair_bias / d_gamma from those sums - lets the caller overlap the final reductions with the GEMMs that
+ * depend only on dproj (dx, dWcat). */
+int dab_ipa_bwd_sm100_main(const DabIpaDims* d, const void* packed, const void* e_bf16, const float* R, const float* dcat,
+                           void* saved, size_t saved_bytes, void* dproj_bf16, void* de_bf16, float* d_w_pair_bias,
+                           float* d_gamma, void* workspace, size_t workspace_bytes, void* stream);
+int dab_ipa_bwd_sm100_finish(const DabIpaDims* d, const void* packed, const void* e_bf16, const float* R, const float* dcat,
+                             void* saved, size_t saved_bytes, void* dproj_bf16, void* de_bf16, float* d_w_pair_bias,
+                             float* d_gamma, void* workspace, size_t workspace_bytes, void* stream);
 #ifdef DAB_DEBUG_HOOKS /* debug build only (make debug -> libdiffab_b200_dbg.so): process-global profiling / inspection hooks */
 int dab_debug_set_bwd_timeline(long long* device_buf /* 64 slots per CTA of the backward core, or NULL */);
 int dab_debug_bwd_keep_qkv(int on);
