@@ -962,11 +962,24 @@ class Denoiser(nn.Module):
         # and the residue part is a K = 128 GEMM (K = 131 sends forward and both backward GEMMs to unaligned kernels)
         D = h.shape[-1]
         outs = []
-        for head in (self.coordinate_denoising, self.orientation_denoising, self.sequence_denoising):
-            w1, b1 = head[0].weight, head[0].bias
-            pb = torch.addmm(b1, t_emb, w1[:, D:].t())                                  # (B, D)
-            a = torch.relu(F.linear(h, w1[:, :D].contiguous()) + pb[:, None, :])
-            outs.append(head[2:](a))
+        heads = (self.coordinate_denoising, self.orientation_denoising, self.sequence_denoising)
+        # the three heads are independent chains of small kernels: when gradients are recorded (a training step, replayed
+        # from a CUDA graph) each runs on its own stream, forward and - autograd replays a node on its forward stream - backward
+        fork = torch.is_grad_enabled() and h.requires_grad
+        main = torch.cuda.current_stream(h.device)
+        for k, head in enumerate(heads):
+            side = _side_stream(h.device, 3 + k) if fork else None
+            if fork:
+                side.wait_stream(main)
+            with torch.cuda.stream(side) if fork else contextlib.nullcontext():
+                w1, b1 = head[0].weight, head[0].bias
+                pb = torch.addmm(b1, t_emb, w1[:, D:].t())                                  # (B, D)
+                a = torch.relu(F.linear(h, w1[:, :D].contiguous()) + pb[:, None, :])
+                outs.append(head[2:](a))
+        if fork:
+            for k, o in enumerate(outs):
+                main.wait_stream(_side_stream(h.device, 3 + k))
+                o.record_stream(main)
         return tuple(outs)
 
     # ---- sampling fast path of the dense glue (same arithmetic, regrouped; inference only) ----
@@ -1178,11 +1191,25 @@ class DiffAb(nn.Module):
         context_mask = residue_mask & (~generation_mask)
         structure_context_mask = context_mask if generate_structure else None
         sequence_context_mask = context_mask if generate_sequence else None
-        res = self.residue_context_embedding(seq_idx_t0, xyz_t0, orientations_t0, backbone_dihedrals, chain_idx,
-                                             atom_mask, structure_context_mask, sequence_context_mask)
+        fork = seq_idx_t0.is_cuda and torch.is_grad_enabled() and getattr(self, "train_precision", "fp32") == "bf16"
+        if fork:
+            # Training: the two context encoders are independent - the small residue encoder (a few dozen small kernels,
+            # forward and, because autograd replays a node on the stream of its forward, backward) runs on a side stream
+            # beside the pair encoder (parallel branches of the captured graph).
+            main, side = torch.cuda.current_stream(seq_idx_t0.device), _side_stream(seq_idx_t0.device, 2)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                res = self.residue_context_embedding(seq_idx_t0, xyz_t0, orientations_t0, backbone_dihedrals, chain_idx,
+                                                     atom_mask, structure_context_mask, sequence_context_mask)
+        else:
+            res = self.residue_context_embedding(seq_idx_t0, xyz_t0, orientations_t0, backbone_dihedrals, chain_idx,
+                                                 atom_mask, structure_context_mask, sequence_context_mask)
         pair = self.pair_context_embedding(seq_idx_t0, distmat, pairwise_dihedrals, residue_idx, chain_idx, atom_mask,
                                            structure_context_mask, sequence_context_mask,
                                            distmat_is_squared=distmat_is_squared)
+        if fork:
+            main.wait_stream(side)
+            res.record_stream(main)
         return res, pair
 
     def denoise(self, seq_idx_t, translations_t, orientations_t, res_context_emb, pair_context_emb, beta,
@@ -1230,15 +1257,26 @@ class DiffAb(nn.Module):
         translations_t0 = xyz_t0[:, :, CA_IDX].contiguous()
         orientations_t0 = batch["orientations"]
         generation_mask = batch["generation_mask"]
-        noised = self._add_noise(seq_idx_t0, translations_t0, orientations_t0, generation_mask, t, noise=noise)
         bf16 = (getattr(self, "train_precision", "fp32") == "bf16" and
                 self.denoiser.ipa.layers[0].fast_path_supported(seq_idx_t0.shape[1]))
+        # forward noising is independent of the context encoders: in a (graph-captured) mixed-precision training step it runs
+        # on a side stream beside them
+        fork = bf16 and torch.is_grad_enabled() and seq_idx_t0.is_cuda
+        if fork:
+            main, nside = torch.cuda.current_stream(device), _side_stream(device, 6)
+            nside.wait_stream(main)
+        with torch.cuda.stream(nside) if fork else contextlib.nullcontext():
+            noised = self._add_noise(seq_idx_t0, translations_t0, orientations_t0, generation_mask, t, noise=noise)
         self.pair_context_embedding.fused_rbf = bf16
         with _tf32_matmuls(bf16):   # mixed-precision step: the context encoders' GEMMs on the tensor cores too (TF32)
             res_context_emb, pair_context_emb = self.encode_context(
                 seq_idx_t0, xyz_t0, orientations_t0, batch["backbone_dihedrals"], batch["distmat"],
                 batch["pairwise_dihedrals"], batch["atom_mask"], batch["chain_idx"], batch["residue_idx"],
                 batch["generation_mask"], batch["residue_mask"])
+        if fork:
+            main.wait_stream(nside)
+            for v in noised.values():
+                v.record_stream(main)
         if bf16:
             pair_context_emb = pair_context_emb.to(torch.bfloat16)   # autograd-aware cast (grad comes back as bf16)
         with _tf32_matmuls(bf16):
