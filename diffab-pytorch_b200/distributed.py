@@ -184,9 +184,26 @@ class GraphedTrainStep:
                 optimizer.step()
 
     def _backward_part(self):
-        self.bucket.zero()
+        # Gradients are produced into fresh tensors (``.grad = None``: autograd assigns instead of launching one small
+        # ``grad += new`` kernel per parameter into the bucket views) and gathered into the flat bucket by a multi-tensor
+        # copy; parameters that received no gradient contribute zeros.
+        bucket = self.bucket
+        for p in bucket.params:
+            p.grad = None
         num, cnt = self._loss_terms()
         num.backward()
+        views, grads, off = [], [], 0
+        for p in bucket.params:
+            view = bucket.flat[off: off + p.numel()].view_as(p)
+            off += p.numel()
+            if p.grad is None:
+                view.zero_()
+            else:
+                views.append(view)
+                grads.append(p.grad)
+            p.grad = view
+        if views:
+            torch._foreach_copy_(views, grads)
         self._num = num.detach().reshape(1)
         self._cnt = cnt.detach().to(num.dtype).reshape(1).clone()
 
