@@ -77,8 +77,9 @@ def cpu_sample_text(r):
     what = ("the UNMODIFIED reference (baseline/_ref: DiffAb.encode_context + DiffAb.denoise, stock fp32 CPU path) + the "
             "oracle's reverse update (the reference's sample() is a stub)" if r["kind"] == "reference" else
             "oracle port of the reference's PyTorch CPU path, fp32 (reference not installed); context encoders not run")
+    which = "every step" if r["n_steps"] >= T else "one Gaussian-branch step, one histogram-branch step"
     return (f"{r['n_patches']} patches: context encoding once ({r['t_context_s']:.2f} s) + {r['n_steps']} of {T} reverse steps "
-            f"({r['t_steps_s'] / max(r['n_steps'], 1):.2f} s each; one Gaussian-branch step, one histogram-branch step) on "
+            f"({r['t_steps_s'] / max(r['n_steps'], 1):.2f} s each; {which}) on "
             f"{r['threads']} threads; patches/s = patches / (t_context + {T} x t_step); {what}")
 
 
