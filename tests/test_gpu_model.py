@@ -109,6 +109,11 @@ def _oracle_sample(model, batch, s, x, O, res, pair, noises, t_start, t_stop=1):
 
 
 def test_reverse_steps_vs_oracle_sampler():
+    """Five FREE-RUNNING reverse steps of the fp32 kernels against the oracle sampler under injected draws.  Sequences must be
+    identical, except in a patch where the oracle's own top-2 margin of p / Exp(1) fell below 1e-4 at some step (a
+    near-tie that fp32 summation order may legitimately resolve the other way; everything downstream of it in that patch
+    may then differ).  Frames are compared on the patches whose sequences agree.  (The benchmarked bf16 + graph path has
+    its own, teacher-forced gate: tests/test_gpu_sampling_parity.py.)"""
     model = _model(0)
     batch = synth.make_patches(2, 128, seed=9)
     b = _to(batch)
@@ -121,18 +126,36 @@ def test_reverse_steps_vs_oracle_sampler():
                                        batch["generation_mask"], generator=gen)
     t_start, t_stop = 100, 96
     noises = {t: osamp.draw_step_noise(2, 128, generator=gen) for t in range(t_start, t_stop - 1, -1)}
-    ref = _oracle_sample(model, batch, s, x, O, res, pair, noises, t_start, t_stop)
+    m = batch["generation_mask"]
+    # oracle, step by step, keeping the smallest top-2 margin seen per patch
+    state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    sched = odiff.cosine_schedule(100, s=0.01, beta_max=0.999)
+    hist_rev = model.so3_reverse.histograms.cpu()
+    rs, rx, rO = s, x, O
+    near_tie = torch.zeros(2, dtype=torch.bool)
+    for step in range(t_start, t_stop - 1, -1):
+        tt = torch.full((2,), step, dtype=torch.long)
+        den = oipa.denoiser_forward(state, rs, rx, rO, res.cpu(), pair.cpu(), sched["beta"][tt], 6, 8)
+        key = den["seq_posterior"].reshape(-1, 21) / noises[step]["seq_exp"]
+        top2 = key.topk(2, dim=-1).values
+        margin = ((top2[:, 0] - top2[:, 1]) / top2[:, 0]).view(2, -1)
+        near_tie |= ((margin < 1e-4) & m).any(dim=1)
+        nxt = osamp.reverse_step(sched, hist_rev, rs, rx, rO, den["translations_eps"], den["orientations_t0"],
+                                 den["seq_posterior"], m, tt, noises[step])
+        rs, rx, rO = nxt["seq_idx"], nxt["translations"], nxt["orientations"]
     got = model.sample_from_context(s.to(DEV), x.to(DEV), O.to(DEV), res, pair, b["generation_mask"],
                                     noises={t: _to(n) for t, n in noises.items()}, t_start=t_start, t_stop=t_stop)
-    m = batch["generation_mask"]
-    mism = (got["seq_idx"].cpu() != ref["seq_idx"])[m].float().mean()
-    assert mism <= 0.02, float(mism)           # identical up to near-ties of p/q after fp32 reordering
     assert torch.equal(got["seq_idx"].cpu()[~m], batch["seq_idx"][~m])
-    same = (got["seq_idx"].cpu() == ref["seq_idx"]).all(dim=1)
-    dx = (got["translations"].cpu() - ref["translations"]).norm(dim=-1)[m]
-    assert dx.max() < 1e-2, float(dx.max())     # CA drift after 5 steps (Angstrom)
-    dO = (got["orientations"].cpu() - ref["orientations"]).abs().amax(dim=(-1, -2))[m]
-    assert dO.max() < 1e-2
+    same = (got["seq_idx"].cpu() == rs).all(dim=1)
+    assert bool((same | near_tie).all()), "sequence differs in a patch without any near-tie in the oracle"
+    assert bool(same.any())
+    for p_ in range(2):
+        if not bool(same[p_]):
+            continue
+        dx = (got["translations"].cpu()[p_] - rx[p_]).norm(dim=-1)[m[p_]]
+        assert dx.max() < 1e-2, float(dx.max())     # CA drift after 5 steps (Angstrom); the t = 100 step scales errors by 31.6
+        dO = (got["orientations"].cpu()[p_] - rO[p_]).abs().amax(dim=(-1, -2))[m[p_]]
+        assert dO.max() < 1e-2
 
 
 def test_sample_end_to_end_graph_and_eager():

@@ -40,9 +40,12 @@ TRAIN = (128, 64, 6, 32, 8, 8, 8)
 # is amplified accordingly from step to step - so that window gets the looser, stated bounds and still has to keep every
 # sequence flip margin-explained.
 BOUNDS = {
-    #        posterior rel   heads max-norm   CA / step length   rotation entries
-    10:  dict(post=2e-2,     head=2e-2,       ca=1e-2,           rot=2e-2),    # measured 5.1e-3, 1.1e-2, 1.1e-3, 2.8e-3
-    100: dict(post=5e-2,     head=1.5e-1,     ca=2e-2,           rot=1e-1),    # measured 3.3e-2, 1.0e-1, 2.3e-3, 3.6e-2
+    #                 posterior rel   heads max-norm   CA / step length   rotation entries
+    ("bf16", 10):  dict(post=2e-2,     head=2e-2,       ca=1e-2,           rot=2e-2),    # measured 5.1e-3, 1.1e-2, 1.1e-3, 2.8e-3
+    ("bf16", 100): dict(post=5e-2,     head=1.5e-1,     ca=2e-2,           rot=1e-1),    # measured 3.3e-2, 1.0e-1, 2.3e-3, 3.6e-2
+    # the exact (fp32 kernel) path against the same fp64 oracle: north_star's 1e-4 bar (heads max-normalised)
+    ("fp32", 10):  dict(post=1e-3,     head=1e-4,       ca=1e-4,           rot=1e-4),
+    ("fp32", 100): dict(post=1e-3,     head=1e-4,       ca=1e-4,           rot=1e-4),
 }
 
 
@@ -50,7 +53,7 @@ def _to(d):
     return {k: v.to(DEV) for k, v in d.items()}
 
 
-def _setup(B=2, seed=9):
+def _setup(B=2, seed=9, precision="bf16"):
     model = DiffAb(*TRAIN, device=DEV).eval()
     model.load_state_dict(synth.synthetic_state(load_golden("state_shapes.pt"), seed=0))
     batch = synth.make_patches(B, 128, seed=seed)
@@ -59,7 +62,7 @@ def _setup(B=2, seed=9):
         res, pair = model.encode_context(b["seq_idx"], b["xyz"], b["orientations"], b["backbone_dihedrals"],
                                          b["distmat"], b["pairwise_dihedrals"], b["atom_mask"], b["chain_idx"],
                                          b["residue_idx"], b["generation_mask"], b["residue_mask"])
-        pair16 = cast_pair_to_bf16(pair)
+        pair16 = cast_pair_to_bf16(pair) if precision == "bf16" else pair     # (fp32 path: the pair tensor as it is)
     return model, batch, b, res, pair16
 
 
@@ -77,9 +80,9 @@ def _oracle_step(state64, sched, hist_rev, s, x, O, res64, pair64, mask, step, n
     return nxt, den, margin
 
 
-@pytest.mark.parametrize("t_start", [100, 10])
-def test_bf16_graph_step_vs_oracle_teacher_forced(t_start):
-    model, batch, b, res, pair16 = _setup()
+@pytest.mark.parametrize("precision,t_start", [("bf16", 100), ("bf16", 10), ("fp32", 100), ("fp32", 10)])
+def test_graph_step_vs_oracle_teacher_forced(precision, t_start):
+    model, batch, b, res, pair16 = _setup(precision=precision)
     B, L = batch["seq_idx"].shape
     m = batch["generation_mask"]
     gen = torch.Generator().manual_seed(40 + t_start)
@@ -95,9 +98,10 @@ def test_bf16_graph_step_vs_oracle_teacher_forced(t_start):
                                  batch["xyz"][:, :, 1], batch["orientations"], m, torch.full((B,), t_start),
                                  odiff.draw_add_noise_tensors(B, L))
         s, x, O = noised["seq_idx_t"], noised["translations_t"], noised["orientations_t"]
-    glue = model.denoiser.sampling_cache(res)
+    bf16 = precision == "bf16"
+    glue = model.denoiser.sampling_cache(res) if bf16 else None
     planes = model._pair_bias_planes(pair16)
-    bound = BOUNDS[t_start]
+    bound = BOUNDS[(precision, t_start)]
     worst = {"post_rel": 0.0, "ca_rel": 0.0, "rot_abs": 0.0, "flips": 0, "generated": 0}
     for step in range(t_start, t_start - 5, -1):
         noise = osamp.draw_step_noise(B, L, generator=gen)
@@ -110,8 +114,13 @@ def test_bf16_graph_step_vs_oracle_teacher_forced(t_start):
             assert torch.equal(eager[k], graph[k]), (step, k)            # graph replay == eager launch sequence
         # posterior of the bf16 path vs the oracle's (what decides which sequence flips are legitimate)
         t_dev = torch.full((B,), step, device=DEV, dtype=torch.int64)
-        eps_g, v_g, post = model.denoiser.heads_fast(args[0], args[1], args[2], glue, pair16, model.dsched.tensors["beta"][t_dev],
-                                               planes)
+        with torch.no_grad():
+            if bf16:
+                eps_g, v_g, post = model.denoiser.heads_fast(args[0], args[1], args[2], glue, pair16,
+                                                             model.dsched.tensors["beta"][t_dev], planes)
+            else:
+                eps_g, v_g, post = model.denoiser.heads(args[0], args[1], args[2], res, pair16,
+                                                        model.dsched.tensors["beta"][t_dev])
         p_ref = den["seq_posterior"]
         big = p_ref > 1e-3
         d_rel = float(((post.cpu().double() - p_ref).abs() / p_ref)[big].max())
@@ -139,7 +148,7 @@ def test_bf16_graph_step_vs_oracle_teacher_forced(t_start):
         assert dO < bound["rot"], (step, dO)
         assert torch.equal(eager["translations"].cpu()[~m], x.float()[~m])
         s, x, O = ref["seq_idx"], ref["translations"].float(), ref["orientations"].float()   # teacher forcing
-    print(f"\n[parity t={t_start}..{t_start - 4}] bf16+graph vs fp64 oracle: posterior rel err {worst['post_rel']:.2e}, "
+    print(f"\n[parity t={t_start}..{t_start - 4}] {precision} + graph vs fp64 oracle: posterior rel err {worst['post_rel']:.2e}, "
           f"CA err / step length {worst['ca_rel']:.2e}, rotation entry err {worst['rot_abs']:.2e}, heads (max-normalised) rotvec {worst['dv']:.2e} eps {worst['de']:.2e}, "
           f"margin-explained sequence flips {worst['flips']} of {worst['generated']}")
 
