@@ -366,7 +366,7 @@ def main():
 
 
 def measure_roofline(model, layer, res_ctx, pair_ctx, x0, O0, precision, hbm_peak, peak_src, iters=20):
-    """Roofline of the dominant kernel (the IPA attention core) and of the whole IPA layer (its three launches), timed
+    """Roofline of the dominant kernel (the IPA attention core) and of the whole IPA layer (the stack / n_layers), timed
     live with CUDA events on the launching stream; the input (pair tensor of all patches) is larger than L2.
     `achieved` uses SURVEY 8(d)'s ALGORITHMIC bytes of one IPA layer, B (L^2 C + 2 L D + 12 L) sz + params - what any
     implementation of the layer must move - over the kernel's / the layer's duration; the bytes the kernel's own operand
@@ -423,16 +423,19 @@ def measure_roofline(model, layer, res_ctx, pair_ctx, x0, O0, precision, hbm_pea
             return statistics.mean(a.elapsed_time(b_) for a, b_ in evs) * 1000.0 / reps
 
         core_us = timed(2)
-        # the three launches of a layer back to back, replayed from a CUDA graph (no host gaps between them)
+        # the whole layer as sample() runs it: the six-layer stack (per layer the attention core and ONE projection
+        # kernel that carries the previous layer's to_out GEMM; 2 launches per layer + the first projection and the last
+        # to_out), replayed from a CUDA graph, divided by the number of layers
+        stack = model.denoiser.ipa
+        planes = stack.precompute_pair_bias(pair_ctx)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            run(7)
+            stack(x, pair_ctx, O0, x0, planes)
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            for _ in range(4):
-                run(7)
+            stack(x, pair_ctx, O0, x0, planes)
         for _ in range(2):
             g.replay()
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -441,7 +444,9 @@ def measure_roofline(model, layer, res_ctx, pair_ctx, x0, O0, precision, hbm_pea
             g.replay()
         b_.record()
         torch.cuda.synchronize()
-        layer_us = a.elapsed_time(b_) * 1000.0 / 20
+        n_layers = len(stack.layers)
+        layer_us = a.elapsed_time(b_) * 1000.0 / (5 * n_layers)
+        del g, planes
     # bytes on the core kernel's own operand list: e row (bf16) + precomputed bias row (fp16, 8 heads) per (i, j) pair;
     # packed Q/K (2 x 768 bf16) + V (512 fp16) operands + centred t / R in, concat features (1024 bf16) out
     operand = B * L * (L * 64 * 2 + L * 8 * 2 + (768 + 768 + 512 + 1024) * 2 + 12 + 36)
@@ -461,7 +466,8 @@ def measure_roofline(model, layer, res_ctx, pair_ctx, x0, O0, precision, hbm_pea
             "operand_list": {"bytes_per_launch": operand, "achieved": operand / core_us / 1e3,
                              "frac": operand / core_us / 1e3 / hbm_peak,
                              "note": "this design's own operands (packed Q/K/V, fp16 bias planes, concat features)"},
-            "layer": {"launches": "ipa_proj_kernel + ipa_core_kernel + gemm_bf16_kernel (to_out), graph replay",
+            "layer": {"launches": "%d-layer stack / %d: ipa_core_kernel + ipa_proj_kernel (with the previous layer's to_out "
+                                  "fused) per layer, graph replay" % (n_layers, n_layers),
                       "us": layer_us, "achieved": alg / layer_us / 1e3, "frac": alg / layer_us / 1e3 / hbm_peak}}
 
 
