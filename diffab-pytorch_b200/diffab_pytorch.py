@@ -246,25 +246,26 @@ class _PairMlpFunction(torch.autograd.Function):
         P, D = h2.shape
         lib, st = _lib.lib(), _lib.stream_ptr()
         mm32 = lambda a, b: torch.mm(a, b, out_dtype=f32)
-        bias_grads = torch.zeros(4, D, device=g.device, dtype=f32)
+        # The four 64-channel layers: weight, bias and data gradient of a layer (and the ReLU before it) in ONE pass over
+        # the pairs each (dab_pair_mlp_bwd_layer_sm100) - g and the layer input are read once, the next gradient written once.
+        acc = torch.zeros(4 * D * D + 5 * D, device=g.device, dtype=f32)      # one fill: dW of the four layers, five biases
+        dWs, dbs = acc[:4 * D * D].view(4, D, D), acc[4 * D * D:].view(5, D)
 
-        def relu_bwd(grad, act, slot):
-            """grad * (act > 0) in place, with the bias gradient (column sums) accumulated in the same pass."""
-            _lib.check(lib.dab_relu_bwd_colsum(ptr(grad), ptr(act), P, ptr(grad), ptr(bias_grads[slot]), st),
-                       "dab_relu_bwd_colsum")
-            return grad
+        def layer_bwd(k, grad, act_in, w, mask=None, db_prev=None):
+            g_prev = torch.empty_like(act_in)
+            _lib.check(lib.dab_pair_mlp_bwd_layer_sm100(ptr(grad), ptr(act_in), ptr(w.to(bf).contiguous()), ptr(mask), B, L,
+                                                        ptr(g_prev), ptr(dWs[k]), ptr(dbs[k]), ptr(db_prev), st),
+                       "dab_pair_mlp_bwd_layer_sm100")
+            return g_prev
 
-        rm = res_mask.to(bf)
-        pair_mask = (rm[:, :, None] * rm[:, None, :]).reshape(P, 1).expand(P, 8).contiguous()
-        g3 = _lib.dev(g.reshape(P, D), bf, "grad")         # masked pairs: h2 rows are zero, pair_mask handles the bias
-        d_w3, d_b3 = mm32(g3.t(), h2), mm32(g3.t(), pair_mask)[:, 0]
-        g2 = relu_bwd(torch.mm(g3, w3.to(bf)), h2, 0)
-        d_w2, d_b2 = mm32(g2.t(), h1), bias_grads[0]
-        g1 = relu_bwd(torch.mm(g2, w2.to(bf)), h1, 1)
+        g3 = _lib.dev(g.reshape(P, D), bf, "grad")         # masked pairs: rows of h2 are zero, the kernel leaves them out of d_b3
+        g2 = layer_bwd(0, g3, h2, w3, mask=res_mask)
+        g1 = layer_bwd(1, g2, h1, w2)
         del g2
-        d_b1 = bias_grads[1]
+        gd2 = layer_bwd(2, g1, fd, w1[:, 2 * D:3 * D])
+        d_w3, d_b3, d_w2, d_b2, d_b1 = dWs[0], dbs[0], dWs[1], dbs[1], dbs[2]
         d_w1 = torch.empty_like(w1)
-        d_w1[:, 2 * D:3 * D] = mm32(g1.t(), fd)
+        d_w1[:, 2 * D:3 * D] = dWs[2]
         d_w1[:, 3 * D:] = mm32(g1.t(), xh)[:, :w1.shape[1] - 3 * D]
         # embedding tables: S_type[s_i*21 + s_j] / S_rel[offset] = class sums of g1 over the pairs
         s_type = torch.zeros(e_type.shape[0], D, device=g.device, dtype=f32)
@@ -275,12 +276,11 @@ class _PairMlpFunction(torch.autograd.Function):
         d_w1[:, :D] = s_type.t() @ e_type
         d_w1[:, D:2 * D] = s_rel.t() @ e_rel
         d_type, d_rel = s_type @ w1[:, :D], s_rel @ w1[:, D:2 * D]
-        gd2 = relu_bwd(torch.mm(g1, w1[:, 2 * D:3 * D].to(bf)), fd, 2)
         del g1
-        d_wd2, d_bd2 = mm32(gd2.t(), a1), bias_grads[2]
-        gd1 = relu_bwd(torch.mm(gd2, wd2.to(bf)), a1, 3)
+        gd1 = layer_bwd(3, gd2, a1, wd2, db_prev=dbs[4])
         del gd2
-        d_wd1, d_bd1 = mm32(gd1.t(), x0)[:, :x0.shape[1] - ctx.kpad], bias_grads[3]
+        d_wd2, d_bd2, d_bd1 = dWs[3], dbs[3], dbs[4]
+        d_wd1 = mm32(gd1.t(), x0)[:, :x0.shape[1] - ctx.kpad]
         d_rbf = torch.mm(gd1, wd1p).view(B, L, L, -1) if ctx.needs_input_grad[0] else None
         return (d_rbf, None, None, None, None, None, None, d_type, d_rel, d_wd1, d_bd1, d_wd2, d_bd2, d_w1, d_b1, d_w2,
                 d_b2, d_w3, d_b3)

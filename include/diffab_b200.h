@@ -296,6 +296,15 @@ int dab_sum_bf16(const void* const* src, int n_src, int64_t n, void* out_bf16, v
 /* ReLU backward of a 64-channel bf16 layer fused with its bias gradient: g_out = g_in where y > 0 else 0 (may alias g_in),
  * colsum[64] += column sums of g_out. */
 int dab_relu_bwd_colsum(const void* g_in_bf16, const void* y_bf16, int64_t n, void* g_out_bf16, float* colsum, void* stream);
+/* One 64-channel layer y = a W^T + b of PairEmbedding's two MLPs (diffab_pytorch.py:214-223,303-311) backward in ONE pass over
+ * the B*L*L pairs (csrc/pair_mlp_bwd_sm100.cu): dW[64][64] += g^T a, db[64] += column sums of g over the valid pairs,
+ * g_prev = (g W) * (a > 0) - the gradient w.r.t. the pre-activation of the layer before, whose ReLU output a is - and
+ * db_prev[64] += column sums of g_prev.  g_bf16, a_bf16, g_prev_bf16: [B*L*L, 64] bf16;
+ * W_bf16: [64 out][64 in]; res_mask (optional, [B, L]): pairs with a masked residue are left out of db (their rows of a
+ * must be zero: dab_pair_zero_masked).  g_prev_bf16 and db_prev may be null.  dW, db, db_prev are fp32 and ACCUMULATED
+ * into with red.global (the caller zeroes them; summation order not fixed). */
+int dab_pair_mlp_bwd_layer_sm100(const void* g_bf16, const void* a_bf16, const void* W_bf16, const uint8_t* res_mask, int B,
+                                 int L, void* g_prev_bf16, float* dW, float* db, float* db_prev, void* stream);
 
 /* The three masked training losses in one pass each way (DiffAb._shared_step, diffab_pytorch.py:856-880 with KLDivLoss / MSELoss /
  * OrientationLoss :610-625, reduction "none", then masked mean; csrc/loss_kernels.cu).  n = B*L residues; post_*[n,21],

@@ -1,0 +1,68 @@
+"""dab_pair_mlp_bwd_layer_sm100 (one layer of PairEmbedding's MLPs backward in one pass) against the same gradients
+composed from PyTorch fp32 ops on the same bf16 inputs."""
+import pytest
+import torch
+
+from diffab_pytorch_b200 import _lib
+from diffab_pytorch_b200._lib import ptr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _case(B, L, seed, masked):
+    g_ = torch.Generator(device=DEV).manual_seed(seed)
+    P = B * L * L
+    g = torch.randn(P, 64, device=DEV, generator=g_).bfloat16()
+    a = torch.relu(torch.randn(P, 64, device=DEV, generator=g_)).bfloat16()
+    W = (0.2 * torch.randn(64, 64, device=DEV, generator=g_)).bfloat16()
+    m = torch.ones(B, L, device=DEV, dtype=torch.uint8)
+    if masked:
+        m[0, 1] = 0
+        m[B - 1, L - 3] = 0
+    return g, a, W, m
+
+
+@pytest.mark.parametrize("B,L,masked,with_prev", [(2, 128, True, True), (3, 128, False, False), (1, 20, True, True),
+                                                  (2, 100, True, True)])
+def test_layer_backward_matches_composed_gradients(B, L, masked, with_prev):
+    g, a, W, m = _case(B, L, 3 * B + L, masked)
+    P = B * L * L
+    pm = (m[:, :, None] & m[:, None, :]).reshape(P, 1).float()
+    a = (a.float() * pm).bfloat16()                       # rows of the layer input are zero for masked pairs
+    dW = torch.zeros(64, 64, device=DEV)
+    db = torch.zeros(64, device=DEV)
+    dbp = torch.zeros(64, device=DEV)
+    g_prev = torch.empty(P, 64, device=DEV, dtype=torch.bfloat16)
+    lib = _lib.lib()
+    for rep in range(2):                                    # the outputs are accumulated: the second call doubles them
+        _lib.check(lib.dab_pair_mlp_bwd_layer_sm100(ptr(g), ptr(a), ptr(W), ptr(m) if masked else None, B, L, ptr(g_prev),
+                                                    ptr(dW), ptr(db), ptr(dbp) if with_prev else None, _lib.stream_ptr()),
+                   "dab_pair_mlp_bwd_layer_sm100")
+    torch.cuda.synchronize()
+    gf, af, Wf = g.double(), a.double(), W.double()
+    ref_dW = 2 * gf.t() @ af
+    ref_db = 2 * (gf * pm.double()).sum(0)
+    ref_prev = ((gf @ Wf) * (af > 0)).float()
+    assert (dW.double() - ref_dW).abs().max() <= 1e-5 * ref_dW.abs().max()
+    assert (db.double() - ref_db).abs().max() <= 1e-5 * ref_db.abs().max() + 1e-3
+    # bf16 rounding of an fp32 accumulation against the rounding of the fp64 value: one bf16 ulp
+    err = (g_prev.float() - ref_prev).abs()
+    assert float((err / (ref_prev.abs() + 1e-2)).max()) < 1e-2
+    assert torch.equal(g_prev == 0, ref_prev.bfloat16() == 0) or float(((g_prev == 0) != (ref_prev.bfloat16() == 0)).float().mean()) < 1e-5
+    if with_prev:
+        ref_dbp = 2 * g_prev.double().sum(0)
+        assert (dbp.double() - ref_dbp).abs().max() <= 1e-5 * ref_dbp.abs().max() + 1e-3
+
+
+def test_layer_backward_without_data_gradient():
+    g, a, W, m = _case(1, 128, 5, False)
+    dW = torch.zeros(64, 64, device=DEV)
+    db = torch.zeros(64, device=DEV)
+    lib = _lib.lib()
+    _lib.check(lib.dab_pair_mlp_bwd_layer_sm100(ptr(g), ptr(a), ptr(W), None, 1, 128, None, ptr(dW), ptr(db), None,
+                                                _lib.stream_ptr()), "dab_pair_mlp_bwd_layer_sm100")
+    torch.cuda.synchronize()
+    ref = g.double().t() @ a.double()
+    assert (dW.double() - ref).abs().max() <= 1e-5 * ref.abs().max()
+    assert (db.double() - g.double().sum(0)).abs().max() <= 1e-3
