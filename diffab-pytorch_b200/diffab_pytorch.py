@@ -198,6 +198,8 @@ class _PairMlpFunction(torch.autograd.Function):
     ``dab_pair_table_grad`` (class sums in shared memory) instead of sorting 10^6 indices per table.  Only ``rbf``
     among the inputs carries a gradient (-> ``_RbfFunction`` -> pair2distcoef)."""
 
+    fused_forward = True     # False: the layer-by-layer form of the forward pass (any L; tests compare the two)
+
     @staticmethod
     def forward(ctx, rbf, dihedrals, seq_idx, residue_idx, chain_idx, res_mask, max_dist, e_type, e_rel, wd1, bd1, wd2,
                 bd2, w1, b1, w2, b2, w3, b3):
@@ -216,22 +218,33 @@ class _PairMlpFunction(torch.autograd.Function):
         kpad = x0.shape[1] - wd1.shape[1]
         wd1p = F.pad(wd1, (0, kpad)).to(bf)
         a1 = torch._addmm_activation(bd1.to(bf), x0, wd1p.t())                     # relu(rbf Wd1^T + bd1)
-        fd = torch._addmm_activation(bd2.to(bf), a1, wd2.to(bf).t())                # f_dist
         t_type = (e_type @ w1[:, :D].t() + b1).to(bf)                               # (441, D): W1 on the table, bias folded in
         t_rel = (e_rel @ w1[:, D:2 * D].t()).to(bf)                                 # (65, D)
-        base = torch.empty(P, D, device=rbf.device, dtype=bf)
+        dih = _lib.dev(dihedrals, torch.float32, "pairwise_dihedrals")
         xh = torch.empty(P, 32, device=rbf.device, dtype=bf)
-        _lib.check(lib.dab_pair_base_fwd(ptr(seq_idx), ptr(residue_idx), ptr(chain_idx),
-                                         ptr(_lib.dev(dihedrals, torch.float32, "pairwise_dihedrals")), ptr(t_type), ptr(t_rel),
-                                         B, L, max_dist, ptr(base), ptr(xh), st), "dab_pair_base_fwd")
-        w1h = F.pad(w1[:, 3 * D:], (0, xh.shape[1] - (w1.shape[1] - 3 * D))).to(bf)
-        h1 = base.addmm_(fd, w1[:, 2 * D:3 * D].to(bf).t()).addmm_(xh, w1h.t()).relu_()
-        h2 = torch._addmm_activation(b2.to(bf), h1, w2.to(bf).t())
-        out = torch.addmm(b3.to(bf), h2, w3.to(bf).t())
-        # `* pair_mask` (:309-311): masked rows of the output are zeroed, and so are those of h2 - its only other use is
-        # the backward pass, where zero rows switch the whole pair off (threshold_backward, weight-gradient GEMMs)
-        _lib.check(lib.dab_pair_zero_masked(ptr(out), ptr(res_mask), B, L, st), "dab_pair_zero_masked")
-        _lib.check(lib.dab_pair_zero_masked(ptr(h2), ptr(res_mask), B, L, st), "dab_pair_zero_masked")
+        if L == 128 and max_dist == 32 and _PairMlpFunction.fused_forward:
+            # everything behind the first distance layer in ONE kernel (csrc/pair_mlp_fwd_sm100.cu): reads a1 once and
+            # writes fd, h1, h2, out and the angular features once; the per-pair base row of h1 never exists in HBM
+            w5 = torch.stack([wd2, w1[:, 2 * D:3 * D], F.pad(w1[:, 3 * D:], (0, D - (w1.shape[1] - 3 * D))), w2, w3]).to(bf)
+            bias3 = torch.stack([bd2, b2, b3]).float()
+            fd, h1, h2, out = (torch.empty(P, D, device=rbf.device, dtype=bf) for _ in range(4))
+            _lib.check(lib.dab_pair_mlp_fwd_train_sm100(
+                ptr(a1), ptr(dih), ptr(seq_idx), ptr(residue_idx), ptr(chain_idx), ptr(res_mask), ptr(t_type), ptr(t_rel),
+                ptr(w5.contiguous()), ptr(bias3.contiguous()), B, L, max_dist, ptr(fd), ptr(h1), ptr(h2), ptr(out), ptr(xh),
+                st), "dab_pair_mlp_fwd_train_sm100")
+        else:
+            fd = torch._addmm_activation(bd2.to(bf), a1, wd2.to(bf).t())            # f_dist
+            base = torch.empty(P, D, device=rbf.device, dtype=bf)
+            _lib.check(lib.dab_pair_base_fwd(ptr(seq_idx), ptr(residue_idx), ptr(chain_idx), ptr(dih), ptr(t_type), ptr(t_rel),
+                                             B, L, max_dist, ptr(base), ptr(xh), st), "dab_pair_base_fwd")
+            w1h = F.pad(w1[:, 3 * D:], (0, xh.shape[1] - (w1.shape[1] - 3 * D))).to(bf)
+            h1 = base.addmm_(fd, w1[:, 2 * D:3 * D].to(bf).t()).addmm_(xh, w1h.t()).relu_()
+            h2 = torch._addmm_activation(b2.to(bf), h1, w2.to(bf).t())
+            out = torch.addmm(b3.to(bf), h2, w3.to(bf).t())
+            # `* pair_mask` (:309-311): masked rows of the output are zeroed, and so are those of h2 - its only other use is
+            # the backward pass, where zero rows switch the whole pair off (ReLU backward, weight-gradient contractions)
+            _lib.check(lib.dab_pair_zero_masked(ptr(out), ptr(res_mask), B, L, st), "dab_pair_zero_masked")
+            _lib.check(lib.dab_pair_zero_masked(ptr(h2), ptr(res_mask), B, L, st), "dab_pair_zero_masked")
         ctx.save_for_backward(x0, xh, a1, fd, h1, h2, seq_idx, residue_idx, chain_idx, res_mask, e_type, e_rel, wd1p, wd2,
                               w1, w2, w3)
         ctx.kpad, ctx.max_dist = kpad, max_dist

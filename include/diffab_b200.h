@@ -296,6 +296,18 @@ int dab_sum_bf16(const void* const* src, int n_src, int64_t n, void* out_bf16, v
 /* ReLU backward of a 64-channel bf16 layer fused with its bias gradient: g_out = g_in where y > 0 else 0 (may alias g_in),
  * colsum[64] += column sums of g_out. */
 int dab_relu_bwd_colsum(const void* g_in_bf16, const void* y_bf16, int64_t n, void* g_out_bf16, float* colsum, void* stream);
+/* PairEmbedding's MLPs behind the first distance layer, training forward, in ONE kernel (csrc/pair_mlp_fwd_sm100.cu;
+ * diffab_pytorch.py:214-223,262-285,303-311): fd = relu(a1 Wd2^T + bd2), h1 = relu(T_type[s_i*21+s_j] + c_i c_j T_rel[clamp(r_i-r_j)]
+ * + fd W1d^T + xh W1h^T), h2 = relu(h1 W2^T + b2) m_i m_j, out = (h2 W3^T + b3) m_i m_j; every activation the backward pass needs
+ * is written once.  a1_bf16 [B,L,L,64] = relu(Wd1 rbf + bd1); w5_bf16 [5][64 out][64 in] = Wd2, W1[:, 128:192], W1[:, 192:] zero-
+ * padded to 64 columns, W2, W3; bias3 [3][64] fp32 = bd2, b2, b3; t_type_bf16 [441,64] = E_type W1[:, :64]^T + b1;
+ * t_rel_bf16 [65,64] = E_rel W1[:, 64:128]^T.  Outputs (bf16): fd, h1, h2, out [B,L,L,64] and the angular features
+ * xh [B,L,L,32] (columns 18..31 zero).  L = 128 and max_dist = 32 only (DAB_EUNSUPPORTED otherwise). */
+int dab_pair_mlp_fwd_train_sm100(const void* a1_bf16, const float* pairwise_dihedrals, const int64_t* seq_masked,
+                                 const int64_t* residue_idx, const int64_t* chain_idx, const uint8_t* res_mask,
+                                 const void* t_type_bf16, const void* t_rel_bf16, const void* w5_bf16, const float* bias3, int B,
+                                 int L, int max_dist, void* fd_bf16, void* h1_bf16, void* h2_bf16, void* out_bf16,
+                                 void* xh_bf16, void* stream);
 /* One 64-channel layer y = a W^T + b of PairEmbedding's two MLPs (diffab_pytorch.py:214-223,303-311) backward in ONE pass over
  * the B*L*L pairs (csrc/pair_mlp_bwd_sm100.cu): dW[64][64] += g^T a, db[64] += column sums of g over the valid pairs,
  * g_prev = (g W) * (a > 0) - the gradient w.r.t. the pre-activation of the layer before, whose ReLU output a is - and
