@@ -615,7 +615,7 @@ def measure_train_step(dev, dist, world, shapes, B=64, steps=5, warmup=3):
     prev_prec = torch.get_float32_matmul_precision()
     torch.set_float32_matmul_precision("high")
     bucket = GradientBucket(model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True, fused=True)   # (PyTorch's single-kernel Adam)
     batch = {k: v.to(dev) for k, v in synth.make_patches(B, L, seed=2000 + rank, with_distmat=False).items()}
     batch["distmat"] = torch.cat([synth.pairwise_atom_distances(batch["xyz"][i:i + 8]) for i in range(0, B, 8)])
     group = dist.group.WORLD if dist is not None else None

@@ -1367,7 +1367,11 @@ class DiffAb(nn.Module):
         self.last_metrics = {k: v.detach() for k, v in metrics.items()}
 
     def configure_optimizers(self):
-        return torch.optim.Adam(self.parameters(), lr=self.lr, weight_decay=self.weight_decay, betas=self.betas)
+        """diffab_pytorch.py:925-931: Adam(lr, weight_decay, betas).  On CUDA parameters PyTorch's single-kernel (``fused``)
+        implementation of the same update: the default multi-tensor one is ~0.3 ms of small kernels per step here."""
+        on_gpu = all(p.is_cuda for p in self.parameters())
+        return torch.optim.Adam(self.parameters(), lr=self.lr, weight_decay=self.weight_decay, betas=self.betas,
+                                fused=True if on_gpu else None)
 
     # ---- sampling (a stub in the reference, diffab_pytorch.py:770-776) ----
     @staticmethod
