@@ -111,6 +111,7 @@ EXPORTS = {
     "dab_sum_bf16": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "dab_relu_bwd_colsum": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "dab_pair_zero_masked": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "dab_pair_table_grad_sm100": (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dab_pair_mlp_fwd_train_sm100": (c_int, [c_void_p] * 10 + [c_int, c_int, c_int] + [c_void_p] * 6),
     "dab_pair_mlp_bwd_layer_sm100": (c_int, [c_void_p] * 4 + [c_int, c_int] + [c_void_p] * 5),
     "dab_losses_fwd": (c_int, [c_void_p] * 7 + [c_int64, c_void_p, c_void_p, c_void_p]),

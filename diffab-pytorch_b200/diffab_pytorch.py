@@ -333,9 +333,13 @@ class _PairMlpFunction(torch.autograd.Function):
         # embedding tables: S_type[s_i*21 + s_j] / S_rel[offset] = class sums of g1 over the pairs
         s_type = torch.zeros(e_type.shape[0], D, device=g.device, dtype=f32)
         s_rel = torch.zeros(e_rel.shape[0], D, device=g.device, dtype=f32)
-        ws = torch.empty(lib.dab_pair_table_grad_workspace_bytes(B, L, ctx.max_dist) // 4, device=g.device, dtype=f32)
-        _lib.check(lib.dab_pair_table_grad(ptr(g1), ptr(seq_idx), ptr(residue_idx), ptr(chain_idx), B, L, ctx.max_dist,
-                                           ptr(s_type), ptr(s_rel), ptr(ws), ws.numel() * 4, st), "dab_pair_table_grad")
+        if L == 128 and ctx.max_dist <= 63:      # one-hot GEMMs on the tensor cores (csrc/pair_table_grad_sm100.cu)
+            _lib.check(lib.dab_pair_table_grad_sm100(ptr(g1), ptr(seq_idx), ptr(residue_idx), ptr(chain_idx), B, L,
+                                                     ctx.max_dist, ptr(s_type), ptr(s_rel), st), "dab_pair_table_grad_sm100")
+        else:
+            ws = torch.empty(lib.dab_pair_table_grad_workspace_bytes(B, L, ctx.max_dist) // 4, device=g.device, dtype=f32)
+            _lib.check(lib.dab_pair_table_grad(ptr(g1), ptr(seq_idx), ptr(residue_idx), ptr(chain_idx), B, L, ctx.max_dist,
+                                               ptr(s_type), ptr(s_rel), ptr(ws), ws.numel() * 4, st), "dab_pair_table_grad")
         d_w1[:, :D] = s_type.t() @ e_type
         d_w1[:, D:2 * D] = s_rel.t() @ e_rel
         d_type, d_rel = s_type @ w1[:, :D], s_rel @ w1[:, D:2 * D]

@@ -290,6 +290,12 @@ int dab_pair_table_grad(const void* g1_bf16, const int64_t* seq_masked, const in
                         int B, int L, int max_dist, float* s_type, float* s_rel, void* workspace, size_t workspace_bytes,
                         void* stream);
 int dab_pair_zero_masked(void* x_bf16, const uint8_t* res_mask, int B, int L, void* stream);
+/* dab_pair_table_grad on the tensor cores (csrc/pair_table_grad_sm100.cu; L = 128, max_dist <= 63): the class sums as GEMMs of
+ * one-hot matrices (residue type of the key: constant per patch; relative position: one entry per key moves per query row)
+ * against the g1 tile, read once.  s_type[441,64] and s_rel[2*max_dist+1,64] are ACCUMULATED into with red.global (fp32; the
+ * caller zeroes them; summation order not fixed). */
+int dab_pair_table_grad_sm100(const void* g1_bf16, const int64_t* seq_masked, const int64_t* residue_idx,
+                              const int64_t* chain_idx, int B, int L, int max_dist, float* s_type, float* s_rel, void* stream);
 /* out_bf16[n] = sum of n_src (1..8) bf16 tensors, fp32 accumulation, one pass: the pair-tensor gradients of the IPA layers
  * (autograd would add them pairwise, five passes and five bf16 roundings for six layers). */
 int dab_sum_bf16(const void* const* src, int n_src, int64_t n, void* out_bf16, void* stream);

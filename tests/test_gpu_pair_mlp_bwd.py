@@ -66,3 +66,35 @@ def test_layer_backward_without_data_gradient():
     ref = g.double().t() @ a.double()
     assert (dW.double() - ref).abs().max() <= 1e-5 * ref.abs().max()
     assert (db.double() - g.double().sum(0)).abs().max() <= 1e-3
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_table_gradients_on_tensor_cores_match_index_add(B):
+    """dab_pair_table_grad_sm100 (one-hot GEMMs) against torch.index_add_ on the same bf16 gradient, and against the
+    CUDA-core kernel dab_pair_table_grad; several chains, repeated residue indices, offsets beyond the clamp."""
+    L, D, md = 128, 64, 32
+    g_ = torch.Generator(device=DEV).manual_seed(B)
+    g1 = torch.randn(B * L * L, D, device=DEV, generator=g_).bfloat16()
+    seq = torch.randint(0, 21, (B, L), device=DEV, generator=g_)
+    ridx = torch.cumsum(torch.randint(0, 3, (B, L), device=DEV, generator=g_), 1)          # repeats and gaps
+    chain = torch.randint(0, 4, (B, L), device=DEV, generator=g_)                           # 0 = padding: weight zero
+    lib = _lib.lib()
+    s_type = torch.zeros(441, D, device=DEV)
+    s_rel = torch.zeros(2 * md + 1, D, device=DEV)
+    _lib.check(lib.dab_pair_table_grad_sm100(ptr(g1), ptr(seq), ptr(ridx), ptr(chain), B, L, md, ptr(s_type), ptr(s_rel),
+                                             _lib.stream_ptr()), "dab_pair_table_grad_sm100")
+    t_old = torch.zeros(441, D, device=DEV)
+    r_old = torch.zeros(2 * md + 1, D, device=DEV)
+    ws = torch.empty(lib.dab_pair_table_grad_workspace_bytes(B, L, md), device=DEV, dtype=torch.uint8)
+    _lib.check(lib.dab_pair_table_grad(ptr(g1), ptr(seq), ptr(ridx), ptr(chain), B, L, md, ptr(t_old), ptr(r_old), ptr(ws),
+                                       ws.numel(), _lib.stream_ptr()), "dab_pair_table_grad")
+    torch.cuda.synchronize()
+    pt = (seq[:, :, None] * 21 + seq[:, None, :]).reshape(-1)
+    rel = ((ridx[:, :, None] - ridx[:, None, :]).clamp(-md, md) + md).reshape(-1)
+    cp = (chain[:, :, None] * chain[:, None, :]).reshape(-1, 1).double()
+    ref_t = torch.zeros(441, D, device=DEV, dtype=torch.float64).index_add_(0, pt, g1.double())
+    ref_r = torch.zeros(2 * md + 1, D, device=DEV, dtype=torch.float64).index_add_(0, rel, g1.double() * cp)
+    assert (s_type.double() - ref_t).abs().max() <= 1e-5 * ref_t.abs().max() + 1e-4
+    assert (s_rel.double() - ref_r).abs().max() <= 1e-5 * ref_r.abs().max() + 1e-4
+    assert (s_type - t_old).abs().max() <= 1e-4 * t_old.abs().max() + 1e-4
+    assert (s_rel - r_old).abs().max() <= 1e-4 * r_old.abs().max() + 1e-4
