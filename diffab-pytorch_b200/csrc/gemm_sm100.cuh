@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap map_b,
                                                                  float* __restrict__ C, int64_t ldc,
                                                                  const float* __restrict__ bias, int K, int n_nt, int n_items,
-                                                                 __nv_bfloat16* __restrict__ C16 = nullptr) {
+                                                                 __nv_bfloat16* __restrict__ C16 = nullptr, int relu = 0) {
   static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "BN");
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled operands need 1024-byte aligned tiles
@@ -135,7 +135,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_kernel(const __grid_co
         if (crow16) {      // bf16 output (round-to-nearest-even, what the consumer's own fp32 -> bf16 conversion would give)
           float o[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = v[i] + (bias ? __ldg(bias + n0 + c0 + i) : 0.f);
+          for (int i = 0; i < 16; ++i) {
+            o[i] = v[i] + (bias ? __ldg(bias + n0 + c0 + i) : 0.f);
+            if (relu) o[i] = fmaxf(o[i], 0.f);
+          }
           uint4* dst = reinterpret_cast<uint4*>(crow16 + c0);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_kernel(const __grid_co
           o.y = v[4 * qq + 1] + (bias ? __ldg(bias + n0 + c0 + 4 * qq + 1) : 0.f);
           o.z = v[4 * qq + 2] + (bias ? __ldg(bias + n0 + c0 + 4 * qq + 2) : 0.f);
           o.w = v[4 * qq + 3] + (bias ? __ldg(bias + n0 + c0 + 4 * qq + 3) : 0.f);
+          if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
           *reinterpret_cast<float4*>(crow + c0 + 4 * qq) = o;
         }
       }
@@ -166,11 +170,11 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_kernel(const __grid_co
 }
 
 // Host launcher.  A: [M, K] bf16 row-major (lda elements), B: [N, K] bf16 row-major (ldb), C fp32 - or, when C_bf16 is
-// given, bf16 with the same leading dimension -, M % 128 == 0,
+// given, bf16 with the same leading dimension - (+ bias, ReLU when `relu`), M % 128 == 0,
 // N % BN == 0, K % 64 == 0.
 template <int BN, int STAGES = kGemmStages>
 int launch_gemm_bf16(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* C, int64_t ldc, const float* bias,
-                     int M, int N, int K, cudaStream_t stream, void* C_bf16 = nullptr) {
+                     int M, int N, int K, cudaStream_t stream, void* C_bf16 = nullptr, int relu = 0) {
   DAB_REQUIRE(M % kGemmBM == 0 && N % BN == 0 && K % kGemmBK == 0 && K > 0, DAB_EUNSUPPORTED,
               "gemm_bf16: M %% 128, N %% %d, K %% 64 required (M=%d N=%d K=%d)", BN, M, N, K);
   if (M == 0 || N == 0) return DAB_OK;
@@ -190,7 +194,7 @@ int launch_gemm_bf16(const void* A, int64_t lda, const void* Bm, int64_t ldb, fl
   }
   const int grid = n_items < n_sm ? n_items : n_sm;
   gemm_bf16_kernel<BN, STAGES><<<grid, kGemmThreads, GemmSmem<BN, STAGES>::kTotal, stream>>>(
-      ma, mb, C, ldc, bias, K, n_nt, n_items, reinterpret_cast<__nv_bfloat16*>(C_bf16));
+      ma, mb, C, ldc, bias, K, n_nt, n_items, reinterpret_cast<__nv_bfloat16*>(C_bf16), relu);
   count_launch();
   return check_launch("gemm_bf16");
 }

@@ -160,9 +160,11 @@ static int launch_gemm_tn(const void* A, int64_t lda, const void* Bm, int64_t ld
 }
 
 // out[c] = sum_r x[r, c]  (cols <= 1024, multiple of 4): blocks own row ranges, one red.global per column and block;
-// optionally also writes x rounded to bf16 (the operand of the gradient GEMMs) in the same pass
-__global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict__ x, int64_t rows, int cols,
-                                                         float* __restrict__ out, __nv_bfloat16* __restrict__ x_bf16) {
+// optionally x is first multiplied by the ReLU mask (y > 0) of a bf16 activation, and optionally the (masked) x is also
+// written rounded to bf16 (the operand of the gradient GEMMs) in the same pass.  TIn = float or __nv_bfloat16.
+template <typename TIn>
+__global__ void __launch_bounds__(256) colsum_kernel(const TIn* __restrict__ x, int64_t rows, int cols, float* __restrict__ out,
+                                                     __nv_bfloat16* __restrict__ x_bf16, const __nv_bfloat16* __restrict__ y_mask) {
   __shared__ float4 part[256];
   const int c4 = cols / 4;                       // float4 columns
   const int lanes = c4 < 256 ? c4 : 256;         // threads that own a float4 column each (cols <= 1024)
@@ -171,7 +173,21 @@ __global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tg < groups) {
     for (int64_t r = (int64_t)blockIdx.x * groups + tg; r < rows; r += (int64_t)gridDim.x * groups) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * cols) + tc);
+      float4 v;
+      if (sizeof(TIn) == 4) {
+        v = __ldg(reinterpret_cast<const float4*>(x + r * cols) + tc);
+      } else {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(x + r * cols) + tc);
+        v = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                        __uint_as_float(u.y & 0xFFFF0000u));
+      }
+      if (y_mask) {                              // bf16 > 0: sign clear and not zero
+        const uint2 m = __ldg(reinterpret_cast<const uint2*>(y_mask + r * cols) + tc);
+        if (!((m.x & 0xFFFFu) - 1u < 0x7FFFu)) v.x = 0.f;
+        if (!((m.x >> 16) - 1u < 0x7FFFu)) v.y = 0.f;
+        if (!((m.y & 0xFFFFu) - 1u < 0x7FFFu)) v.z = 0.f;
+        if (!((m.y >> 16) - 1u < 0x7FFFu)) v.w = 0.f;
+      }
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       if (x_bf16) {
         __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
@@ -226,9 +242,32 @@ int dab_colsum_f32(const float* x, int64_t rows, int cols, float* out, void* x_b
   if (rows == 0) return DAB_OK;
   int64_t blocks = (rows + 31) / 32;
   if (blocks > 148) blocks = 148;
-  colsum_f32_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, rows, cols, out, reinterpret_cast<__nv_bfloat16*>(x_bf16));
+  colsum_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(x, rows, cols, out, reinterpret_cast<__nv_bfloat16*>(x_bf16), nullptr);
   count_launch();
   return check_launch("dab_colsum_f32");
+}
+
+/* Bias gradient of an nn.Linear behind a ReLU, with the operand of its gradient GEMMs: g' = g * (y > 0) (y_bf16 = the ReLU
+ * output, NULL: no mask), db[cols] (fp32, overwritten) = column sums of g', g_out_bf16 (optional) = g' rounded to bf16.
+ * g: fp32 (g_is_bf16 = 0) or bf16, [rows, cols] contiguous; cols % 4 == 0, <= 1024. */
+int dab_bias_grad(const void* g, int g_is_bf16, const void* y_bf16, int64_t rows, int cols, float* db, void* g_out_bf16,
+                  void* stream) {
+  DAB_REQUIRE(g && db && rows >= 0 && cols > 0 && cols % 4 == 0 && cols <= 1024 && aligned16(g) && aligned16(db) &&
+                  aligned16(y_bf16) && aligned16(g_out_bf16) && (!g_is_bf16 || cols % 8 == 0),
+              DAB_EINVAL, "dab_bias_grad: bad argument (cols %% 4 == 0 (8 for bf16), <= 1024; 16-byte aligned pointers)");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(db, 0, (size_t)cols * sizeof(float), s) != cudaSuccess) return check_launch("dab_bias_grad memset");
+  if (rows == 0) return DAB_OK;
+  int64_t blocks = (rows + 31) / 32;
+  if (blocks > 148) blocks = 148;
+  const __nv_bfloat16* y = reinterpret_cast<const __nv_bfloat16*>(y_bf16);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g_out_bf16);
+  if (g_is_bf16)
+    colsum_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(g), rows, cols, db, o, y);
+  else
+    colsum_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float*>(g), rows, cols, db, o, y);
+  count_launch();
+  return check_launch("dab_bias_grad");
 }
 
 }  // extern "C"

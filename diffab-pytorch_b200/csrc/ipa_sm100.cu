@@ -1105,6 +1105,21 @@ int dab_gemm_bf16(const void* A, const void* Bm, float* Cm, const float* bias, i
   return launch_gemm_bf16<64>(A, K, Bm, K, Cm, N, bias, M, N, K, (cudaStream_t)stream);
 }
 
+/* nn.Linear (+ ReLU) of the dense glue on the same GEMM: C = act(A[M,K] W[N,K]^T + bias), bf16 operands, fp32 accumulation;
+ * the result as fp32 (C_f32) or rounded to bf16 (C_bf16) - exactly one of the two.  M % 128 == 0, N % 64 == 0, K % 64 == 0.
+ * Forward of the MLPs of diffab_pytorch.py:57-183,572-599 in mixed-precision training, and (W transposed) their data gradients. */
+int dab_linear_bf16(const void* A, const void* W, const float* bias, int relu, int M, int N, int K, float* C_f32, void* C_bf16,
+                    void* stream) {
+  DAB_REQUIRE(A && W && ((C_f32 == nullptr) != (C_bf16 == nullptr)), DAB_EINVAL,
+              "dab_linear_bf16: null pointer (exactly one of C_f32 / C_bf16 must be given)");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (M > 0 && N % 64 == 0 && (M / kGemmBM) * (N / 64) < 148)
+    return launch_gemm_bf16<32>(A, K, W, K, C_f32, N, bias, M, N, K, s, C_bf16, relu);
+  if (N % 128 == 0 && (M / kGemmBM) * (N / 128) >= 2 * 148)
+    return launch_gemm_bf16<128>(A, K, W, K, C_f32, N, bias, M, N, K, s, C_bf16, relu);
+  return launch_gemm_bf16<64>(A, K, W, K, C_f32, N, bias, M, N, K, s, C_bf16, relu);
+}
+
 #ifdef DAB_DEBUG_HOOKS
 /* Profiling hook (debug build only): per-tile clock64 timeline of the attention core (64 slots per tile), NULL to disable. */
 int dab_debug_set_timeline(long long* buf) {

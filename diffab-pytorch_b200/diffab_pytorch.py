@@ -112,16 +112,123 @@ class _LinearFunction(torch.autograd.Function):
         return dx, dw, db
 
 
+class _MixedMlpFunction(torch.autograd.Function):
+    """A run of nn.Linear (+ ReLU) layers on the library's kernels in mixed precision (bf16 operands and activations, fp32
+    accumulation and results): forward ``dab_linear_bf16`` per layer with the bias / ReLU / bf16 epilogue fused; backward per
+    layer ONE pass for ReLU backward + bias gradient + the bf16 operand (``dab_bias_grad``), the weight gradient on the
+    MN-major GEMM (``dab_gemm_bf16_tn``) and the data gradient on the K-major one against the transposed weight.
+    ``spec`` = tuple of booleans: ReLU behind layer k.  Every layer: in / out features multiples of 64, rows of 128."""
+
+    @staticmethod
+    def forward(ctx, x, spec, *params):
+        lib, st = _lib.lib(), _lib.stream_ptr()
+        bf, f32 = torch.bfloat16, torch.float32
+        n = len(spec)
+        lead, M = x.shape[:-1], x.numel() // x.shape[-1]
+        a = torch.empty(M, x.shape[-1], device=x.device, dtype=bf)
+        xc = _lib.dev(x.reshape(M, -1), f32, "x")
+        _lib.check(lib.dab_cast_f32_to_bf16(ptr(xc), ptr(a), xc.numel(), st), "dab_cast_f32_to_bf16")
+        acts, w16 = [a], []
+        out = None
+        for k in range(n):
+            w, b = params[2 * k], params[2 * k + 1]
+            wk = w.detach().to(bf).contiguous()
+            w16.append(wk)
+            N, K = w.shape
+            last = k == n - 1
+            y = torch.empty(M, N, device=x.device, dtype=f32 if last else bf)
+            _lib.check(lib.dab_linear_bf16(ptr(acts[-1]), ptr(wk), ptr(_lib.dev(b.detach(), f32, "bias")), int(spec[k]), M, N, K,
+                                           ptr(y) if last else None, None if last else ptr(y), st), "dab_linear_bf16")
+            if last:
+                out = y
+                if spec[k]:                       # the ReLU mask of the last layer (its output leaves as fp32)
+                    acts.append(y)
+            else:
+                acts.append(y)
+        ctx.save_for_backward(*acts, *w16)
+        ctx.spec, ctx.n = spec, n
+        return out.view(*lead, out.shape[-1])
+
+    @staticmethod
+    def backward(ctx, g):
+        lib, st = _lib.lib(), _lib.stream_ptr()
+        bf, f32 = torch.bfloat16, torch.float32
+        n, spec = ctx.n, ctx.spec
+        saved = ctx.saved_tensors
+        n_act = len(saved) - n
+        acts, w16 = saved[:n_act], saved[n_act:]
+        M = acts[0].shape[0]
+        grads = [None] * (2 * n)
+        gk = _lib.dev(g.reshape(M, -1), f32, "grad")
+        g_is_bf16 = 0
+        dx = None
+        for k in range(n - 1, -1, -1):
+            N, K = w16[k].shape
+            mask = None
+            if spec[k]:
+                y = acts[k + 1]                 # ReLU output of layer k (bf16; fp32 for the last layer)
+                mask = y if y.dtype == bf else y.to(bf)
+            db = torch.empty(N, device=g.device, dtype=f32)
+            g16 = torch.empty(M, N, device=g.device, dtype=bf)
+            _lib.check(lib.dab_bias_grad(ptr(gk), g_is_bf16, ptr(mask), M, N, ptr(db), ptr(g16), st), "dab_bias_grad")
+            dw = torch.empty(N, K, device=g.device, dtype=f32)
+            _lib.check(lib.dab_gemm_bf16_tn(ptr(g16), N, ptr(acts[k]), K, ptr(dw), K, N, K, M, st), "dab_gemm_bf16_tn")
+            grads[2 * k], grads[2 * k + 1] = dw, db
+            if k > 0 or ctx.needs_input_grad[0]:
+                wt = w16[k].t().contiguous()    # [K, N]: dx = g W as a K-major GEMM against W^T
+                first = k == 0
+                gx = torch.empty(M, K, device=g.device, dtype=f32 if first else bf)
+                _lib.check(lib.dab_linear_bf16(ptr(g16), ptr(wt), None, 0, M, K, N, ptr(gx) if first else None,
+                                               None if first else ptr(gx), st), "dab_linear_bf16 (dx)")
+                if first:
+                    dx = gx
+                else:
+                    gk, g_is_bf16 = gx, 1
+        if dx is not None:
+            dx = dx.view(*g.shape[:-1], dx.shape[-1])
+        return (dx, None, *grads)
+
+
+_MIXED_GLUE = [False]     # set for the duration of a mixed-precision training forward (DiffAb._shared_step)
+
+
+@contextlib.contextmanager
+def _mixed_glue(enabled):
+    prev = _MIXED_GLUE[0]
+    _MIXED_GLUE[0] = bool(enabled)
+    try:
+        yield
+    finally:
+        _MIXED_GLUE[0] = prev
+
+
 def _run_mlp(mlp, x):
-    """``mlp(x)`` for an ``_mlp`` Sequential; on CUDA tensors that record gradients its Linear layers go through
-    ``_LinearFunction`` (same forward call, cheaper bias gradient)."""
+    """``mlp(x)`` for an ``_mlp`` Sequential.  On CUDA tensors that record gradients: in a mixed-precision training step,
+    runs of layers whose shapes the tcgen05 GEMM takes (features multiples of 64, rows of 128) go through
+    ``_MixedMlpFunction``; other Linear layers through ``_LinearFunction`` (same forward call, cheaper bias gradient)."""
     if not (x.is_cuda and torch.is_grad_enabled()):
         return mlp(x)
-    for m in mlp:
-        if isinstance(m, nn.Linear) and m.bias is not None:
+    mods = list(mlp)
+    rows = x.numel() // x.shape[-1]
+    ok = lambda m: (_MIXED_GLUE[0] and isinstance(m, nn.Linear) and m.bias is not None and m.in_features % 64 == 0 and
+                    m.out_features % 64 == 0 and rows % 128 == 0 and x.dtype == torch.float32)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if ok(m):
+            spec, params = [], []
+            while i < len(mods) and ok(mods[i]):
+                relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                spec.append(relu)
+                params += [mods[i].weight, mods[i].bias]
+                i += 2 if relu else 1
+            x = _MixedMlpFunction.apply(x, tuple(spec), *params)
+        elif isinstance(m, nn.Linear) and m.bias is not None:
             x = _LinearFunction.apply(x, m.weight, m.bias)
+            i += 1
         else:
             x = m(x)
+            i += 1
     return x
 
 
@@ -1335,7 +1442,7 @@ class DiffAb(nn.Module):
         with torch.cuda.stream(nside) if fork else contextlib.nullcontext():
             noised = self._add_noise(seq_idx_t0, translations_t0, orientations_t0, generation_mask, t, noise=noise)
         self.pair_context_embedding.fused_rbf = bf16
-        with _tf32_matmuls(bf16):   # mixed-precision step: the context encoders' GEMMs on the tensor cores too (TF32)
+        with _tf32_matmuls(bf16), _mixed_glue(bf16):   # mixed-precision step: the context encoders' GEMMs on the tensor cores too
             res_context_emb, pair_context_emb = self.encode_context(
                 seq_idx_t0, xyz_t0, orientations_t0, batch["backbone_dihedrals"], batch["distmat"],
                 batch["pairwise_dihedrals"], batch["atom_mask"], batch["chain_idx"], batch["residue_idx"],
@@ -1346,7 +1453,7 @@ class DiffAb(nn.Module):
                 v.record_stream(main)
         if bf16:
             pair_context_emb = pair_context_emb.to(torch.bfloat16)   # autograd-aware cast (grad comes back as bf16)
-        with _tf32_matmuls(bf16):
+        with _tf32_matmuls(bf16), _mixed_glue(bf16):
             denoised = self.denoise(noised["seq_idx_t"], noised["translations_t"], noised["orientations_t"],
                                     res_context_emb, pair_context_emb, beta, batch["generation_mask"],
                                     batch["residue_mask"])

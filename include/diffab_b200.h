@@ -347,6 +347,18 @@ int dab_gemm_bf16_tn(const void* A, int64_t lda, const void* Bm, int64_t ldb, fl
 /* out[cols] (fp32, overwritten) = column sums of x[rows, cols]: bias gradients (d b_out = sum over residues of dy);
  * x_bf16 (may be NULL) receives x rounded to bf16 in the same pass (the operand of the gradient GEMMs). */
 int dab_colsum_f32(const float* x, int64_t rows, int cols, float* out, void* x_bf16, void* stream);
+/* Mixed-precision nn.Linear layers of the dense glue (ResidueEmbedding.mlp, Denoiser.to_res_emb, the heads:
+ * diffab_pytorch.py:57-183,572-599) on the library's tcgen05 GEMM.
+ * dab_linear_bf16: C = act(A[M,K] W[N,K]^T + bias), bf16 operands, fp32 accumulation; act = ReLU when relu != 0; the result as
+ *   fp32 (C_f32) or rounded to bf16 (C_bf16), exactly one of the two non-NULL.  M % 128 == 0, N % 64 == 0, K % 64 == 0.
+ *   Forward y = x W^T + b, and with W transposed the data gradient dx = g W.
+ * dab_bias_grad: g' = g * (y > 0) (y_bf16 = the layer's ReLU output, NULL: no mask), db[cols] (fp32, overwritten) = column
+ *   sums of g', g_out_bf16 (optional) = g' rounded to bf16 (the operand of dx = g' W and dW = g'^T x, dab_gemm_bf16_tn).
+ *   g: fp32 (g_is_bf16 = 0) or bf16, [rows, cols] contiguous; cols % 4 == 0 (8 for bf16 input), <= 1024. */
+int dab_linear_bf16(const void* A, const void* W, const float* bias, int relu, int M, int N, int K, float* C_f32, void* C_bf16,
+                    void* stream);
+int dab_bias_grad(const void* g, int g_is_bf16, const void* y_bf16, int64_t rows, int cols, float* db, void* g_out_bf16,
+                  void* stream);
 #ifdef DAB_DEBUG_HOOKS /* debug build only */
 int dab_debug_set_timeline(long long* device_buf /* 64 slots per tile of the attention core, or NULL */);
 #endif
