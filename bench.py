@@ -648,8 +648,9 @@ def measure_train_step(dev, dist, world, shapes, B=64, steps=5, warmup=3):
             "patches_per_s": B * world * 1000.0 / ms, "ms_per_step": ms, "patches_per_gpu": B, "n_gpus": world,
             "cuda_graph": "whole step (zero, forward, backward, Adam) replayed from CUDA graphs; gradient all-reduce "
                           "between the backward and the optimizer graph when n_gpus > 1",
-            "matmul_precision": "bf16 tensor-core IPA kernels; TF32 for the PyTorch glue and context encoders "
-                                "(as the reference's train.py:47)", "loss_finite": finite}
+            "matmul_precision": "bf16 operands / fp32 accumulation in the library's kernels (IPA layers, pair context encoder, "
+                                "aligned Linear layers of the dense glue); TF32 for the remaining PyTorch GEMMs (as the "
+                                "reference's train.py:47); PyTorch's fused Adam", "loss_finite": finite}
 
 
 def measure_ipa_fwd_bwd_bf16(dev, B=32, iters=20):
