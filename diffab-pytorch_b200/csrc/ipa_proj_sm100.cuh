@@ -60,7 +60,8 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
                 const float* __restrict__ gamma, __nv_bfloat16* __restrict__ Qp, __nv_bfloat16* __restrict__ Kp,
                 __nv_bfloat16* __restrict__ Vp, float* __restrict__ tc, long long* __restrict__ dbg,
                 const __nv_bfloat16* __restrict__ x16, const __grid_constant__ CUtensorMap map_cat,
-                const __grid_constant__ CUtensorMap map_wout, const float* __restrict__ b_out, int fuse_out) {
+                const __grid_constant__ CUtensorMap map_wout, const float* __restrict__ b_out, int fuse_out,
+                const float* __restrict__ cen_ext) {
   long long* dbg_cta = dbg ? dbg + (size_t)blockIdx.y * 64 : nullptr;   // (split 0 of) one patch per record
 #define PROJ_STAMP(k) do { if (dbg_cta && threadIdx.x == 0) dbg_cta[(k)] = clock64(); } while (0)
   PROJ_STAMP(0);
@@ -108,8 +109,11 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
         *reinterpret_cast<uint2*>(smem + S::kA + kb * 16384 + swz128_offset(r, chunk) + half) = o;
       }
     }
-    // ---- patch centroid of the translations (see ipa_sm100.cu: keeps the expanded distance well conditioned)
-    if (warp < 4) {
+    // ---- patch centroid of the translations (see ipa_sm100.cu: keeps the expanded distance well conditioned).  A patch
+    //      of 256 residues is two blocks of this kernel: both must centre on the SAME point, handed in as cen_ext
+    if (cen_ext != nullptr) {
+      if (tid < 12) s_cen[tid] = tid < 3 ? __ldg(cen_ext + (int64_t)b * 3 + tid) * (float)L : 0.f;
+    } else if (warp < 4) {
       const float* tp = t + ((int64_t)b * L + tid) * 3;
       float cx = warp_sum(tp[0]), cy = warp_sum(tp[1]), cz = warp_sum(tp[2]);
       if (lane == 0) { s_cen[warp * 3] = cx; s_cen[warp * 3 + 1] = cy; s_cen[warp * 3 + 2] = cz; }

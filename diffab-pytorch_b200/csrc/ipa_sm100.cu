@@ -245,12 +245,13 @@ __device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, float (&v)[4]) {
 // scale_total * log2(e) (dab_ipa_pair_bias): e is constant over the six layers and the T steps, so the
 // e . Wpb contraction is hoisted out of the sampling loop entirely.
 constexpr int kCoreThreads = 640;
+template <bool KB2>     // KB2: key-block mode for patches of 256 residues (see `decode` below); false: the L = 128 kernel
 __global__ void __launch_bounds__(kCoreThreads, 1)
 ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_e,
                 const uint4* __restrict__ bias, const float* __restrict__ tc, const float* __restrict__ R,
                 __nv_bfloat16* __restrict__ cat, float* __restrict__ stats, uint4* __restrict__ pu,
-                int n_tiles, long long* __restrict__ dbg) {
+                int n_tiles, long long* __restrict__ dbg, int64_t out_stride) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // optional per-tile timeline: slot k of tile c at dbg[c * 64 + k]
   long long* dbg_cta = nullptr;
@@ -272,6 +273,25 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   // 0, finds the concat features this kernel wrote last).  The pair rows are streamed with an evict-first policy so that
   // they do not push those operands out of L2.
   auto tile_of = [&](int k) { return n_tiles - 1 - ((int)blockIdx.x + k * (int)gridDim.x); };
+  // A tile = 16 query rows against one block of 128 keys.  Plain mode (KB2 = false): tile >> 3 = patch, keys = the patch.
+  // Key-block mode (KB2, patches of 256 residues = two blocks): tile >> 3 = (query block, key block) pair; the pair
+  // tensor / bias rows are 256 pairs long and the key block starts at pair 128 kb of the row; the (normalised) result and
+  // its softmax statistics go to slice kb of the outputs (out_stride rows apart) and are merged afterwards.
+  struct TileIdx { int64_t q0, kv0, o0; int lrow, joff; };
+  auto decode = [&](int tile) {
+    TileIdx ti;
+    const int v = tile >> 3, it = tile & 7;
+    if (KB2) {
+      const int qblk = v >> 1, kb = v & 1;
+      ti.q0 = (int64_t)qblk * L + it * IB;
+      ti.kv0 = (int64_t)((qblk & ~1) + kb) * L;
+      ti.o0 = (int64_t)kb * out_stride + ti.q0;
+      ti.lrow = 2 * L; ti.joff = kb * L;
+    } else {
+      ti.q0 = (int64_t)v * L + it * IB; ti.kv0 = (int64_t)v * L; ti.o0 = ti.q0; ti.lrow = L; ti.joff = 0;
+    }
+    return ti;
+  };
   // Ring bookkeeping.  e/V entry at ring position x of a tile (pair row r: x = r; value tile h: x = 16 + h): slot x % 4,
   // completion x / 4 of the tile - 24 entries on 4 slots are 6 completions per slot and tile, an even number, so the
   // parity of an entry depends only on its position inside the tile.  Rows 2p, 2p+1 and value tiles 2m, 2m+1 always sit
@@ -301,8 +321,9 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k);
       for (int k = 0; k < n_local; ++k) {
         const int c = k & 1, n = k >> 1, tile = tile_of(k);
-        const int b = tile >> 3;
-        const int64_t row0 = (int64_t)b * L + (tile & 7) * IB;
+        const TileIdx ti = decode(tile);
+        const int64_t row0 = ti.q0;
+        const int kvrow = (int)ti.kv0;
         uint64_t* cb = bars + CTX_BARS + N_CTX_BARS * c;
         uint8_t* cs = smem + S::kCtx0 + c * S::kCtxBytes;
         auto load_k = [&](int h) {
@@ -311,7 +332,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           uint8_t* kb = smem + S::kKRing + s * S::kKBuf;
           mbar_arrive_expect_tx(&bars[K_FULL + s], S::kKBuf);
           for (int blk = 0; blk < 3; ++blk)
-            tma_load_2d(kb + blk * (L * 64), &map_k, &bars[K_FULL + s], (h * 3 + blk) * 32, b * L);
+            tma_load_2d(kb + blk * (L * 64), &map_k, &bars[K_FULL + s], (h * 3 + blk) * 32, kvrow);
         };
         // the first two heads of K go out as soon as the ring has room (i.e. while the context is still busy with its
         // previous tile); Q goes into the context's P_h region, free once the O^T MMAs of that tile have completed
@@ -333,24 +354,24 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
       const uint64_t pol = policy_evict_first();
       constexpr int kL2Ahead = 8;
-      auto row0_of = [&](int k) { const int tile = tile_of(k); return (int64_t)(tile >> 3) * L + (tile & 7) * IB; };
+      // pair index of (query row r of tile k, first key of the tile's key block)
+      auto pair0_of = [&](int k, int r) { const TileIdx ti = decode(tile_of(k)); return (int)((ti.q0 + r) * ti.lrow + ti.joff); };
       if (n_local > 0)
-        for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d_hint(&map_e, 0, (int)((row0_of(0) + r) * L), pol);
+        for (int r = 0; r < kL2Ahead; ++r) tma_prefetch_l2_2d_hint(&map_e, 0, pair0_of(0, r), pol);
       for (int k = 0; k < n_local; ++k) {
-        const int tile = tile_of(k), b = tile >> 3;
-        const int64_t row0 = row0_of(k);
-        const int64_t nrow0 = k + 1 < n_local ? row0_of(k + 1) : -1;
+        const int kvrow = (int)decode(tile_of(k)).kv0;
+        const bool has_next = k + 1 < n_local;
         for (int x = 0; x < IB + H; ++x) {
           const int s = x % S::kSlots;
           if (k > 0 || x >= S::kSlots) mbar_wait(&bars[R_EMPTY + s], ((x / S::kSlots) + 1) & 1);
           mbar_arrive_expect_tx(&bars[R_FULL + s], S::kSlot);
           if (x < IB) {
-            tma_load_2d_hint(smem + S::kRing + s * S::kSlot, &map_e, &bars[R_FULL + s], 0, (int)((row0 + x) * L), pol);
+            tma_load_2d_hint(smem + S::kRing + s * S::kSlot, &map_e, &bars[R_FULL + s], 0, pair0_of(k, x), pol);
             const int a = x + kL2Ahead;
-            if (a < IB) tma_prefetch_l2_2d_hint(&map_e, 0, (int)((row0 + a) * L), pol);
-            else if (nrow0 >= 0) tma_prefetch_l2_2d_hint(&map_e, 0, (int)((nrow0 + a - IB) * L), pol);
+            if (a < IB) tma_prefetch_l2_2d_hint(&map_e, 0, pair0_of(k, a), pol);
+            else if (has_next) tma_prefetch_l2_2d_hint(&map_e, 0, pair0_of(k + 1, a - IB), pol);
           } else {
-            tma_load_2d(smem + S::kRing + s * S::kSlot, &map_v, &bars[R_FULL + s], (x - IB) * V_W, b * L);
+            tma_load_2d(smem + S::kRing + s * S::kSlot, &map_v, &bars[R_FULL + s], (x - IB) * V_W, kvrow);
           }
         }
       }
@@ -498,15 +519,17 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
    for (int k = c, tn = 0; k < n_local; k += 2, ++tn) {
     const int tile = tile_of(k);
-    const int b = tile >> 3, i0 = (tile & 7) * IB;
-    const int64_t row0 = (int64_t)b * L + i0;       // first query row (global residue index)
+    const TileIdx ti = decode(tile);
+    const int64_t row0 = ti.q0;          // first query row (global residue index): frames, centred translations
+    const int64_t orow0 = KB2 ? ti.o0 : row0;       // first row of the outputs (concat features, statistics)
+    constexpr int64_t LR = KB2 ? 2 * L : L;         // pairs per row of the pair tensor / the bias planes
     dbg_cta = dbg ? dbg + (size_t)tile * 64 : nullptr;
     long long w_pair = 0;
     DAB_STAMP(0);
     // pair bias of this thread's key for the group's rows, one quarter (two rows) ahead in registers
-    const uint4* bias_t = bias + (row0 + g) * L + gt;      // local row n (i = 2n + g)  ->  + n * 2 * L
-    uint4 b_cur[2] = {__ldg(bias_t), __ldg(bias_t + 2 * L)};
-    uint4 b_nxt[2] = {__ldg(bias_t + 4 * L), __ldg(bias_t + 6 * L)};
+    const uint4* bias_t = bias + (row0 + g) * LR + (KB2 ? ti.joff : 0) + gt;      // local row n (i = 2n + g)  ->  + n * 2 * LR
+    uint4 b_cur[2] = {__ldg(bias_t), __ldg(bias_t + 2 * LR)};
+    uint4 b_nxt[2] = {__ldg(bias_t + 4 * LR), __ldg(bias_t + 6 * LR)};
     mbar_wait(&cb[S_DONE], tn & 1);
     tcgen05_fence_after_sync();
     DAB_STAMP(6);
@@ -516,8 +539,8 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const uint4 b_use[2] = {b_cur[0], b_cur[1]};
       b_cur[0] = b_nxt[0]; b_cur[1] = b_nxt[1];
       if (q + 2 < IB / 4) {
-        b_nxt[0] = __ldg(bias_t + (size_t)(2 * q + 4) * 2 * L);
-        b_nxt[1] = __ldg(bias_t + (size_t)(2 * q + 5) * 2 * L);
+        b_nxt[0] = __ldg(bias_t + (size_t)(2 * q + 4) * 2 * LR);
+        b_nxt[1] = __ldg(bias_t + (size_t)(2 * q + 5) * 2 * LR);
       }
       float sreg[H][4];
 #pragma unroll
@@ -562,7 +585,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         float v = mx[0];
 #pragma unroll
         for (int kk = 1; kk < 16; ++kk) v = (kk == gt) ? mx[kk] : v;
-        stats[(row0 + 2 * (2 * q + (gt >> 3)) + g) * 16 + (gt & 7)] = v;
+        stats[(orow0 + 2 * (2 * q + (gt >> 3)) + g) * 16 + (gt & 7)] = v;
       }
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
@@ -637,7 +660,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
     }
     bar_all_compute();
-    if (stats && g == 0) stats[(row0 + (gt >> 3)) * 16 + 8 + (gt & 7)] = inv_o[gt];
+    if (stats && g == 0) stats[(orow0 + (gt >> 3)) * 16 + 8 + (gt & 7)] = inv_o[gt];
     // [16 i][8 h][24] global-frame points, behind the Q area of the P_h region
     float* s_og = reinterpret_cast<float*>(cs + S::kPh + S::kQBuf);
 #pragma unroll
@@ -654,7 +677,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           for (int i = 0; i < 8; ++i) st16[i * 32 + lane] = __float2bfloat16_rn(o[8 * r + i] * inv_o[(8 * r + i) * H + h]);
           __syncwarp();
           const int i = 8 * r + (lane >> 2), part = lane & 3;
-          *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + h * DS + part * 8) = reinterpret_cast<const uint4*>(stage_e)[lane];
+          *reinterpret_cast<uint4*>(cat + (orow0 + i) * NCAT + h * DS + part * 8) = reinterpret_cast<const uint4*>(stage_e)[lane];
           __syncwarp();
         }
       } else if (lane < 3 * P) { // point coordinates: d - 32 = lane
@@ -682,12 +705,13 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         out[3 * p] = lx; out[3 * p + 1] = ly; out[3 * p + 2] = lz;
         nrm[p] = sqrtf(lx * lx + ly * ly + lz * lz);
       }
-      uint4* dpt = reinterpret_cast<uint4*>(cat + row * NCAT + NS + H * C + h * 24);
+      const int64_t orow = orow0 + i;
+      uint4* dpt = reinterpret_cast<uint4*>(cat + orow * NCAT + NS + H * C + h * 24);
 #pragma unroll
       for (int q = 0; q < 3; ++q)
         dpt[q] = make_uint4(pack_bf162(out[8 * q], out[8 * q + 1]), pack_bf162(out[8 * q + 2], out[8 * q + 3]),
                             pack_bf162(out[8 * q + 4], out[8 * q + 5]), pack_bf162(out[8 * q + 6], out[8 * q + 7]));
-      *reinterpret_cast<uint4*>(cat + row * NCAT + NS + H * C + NPT + h * 8) =
+      *reinterpret_cast<uint4*>(cat + orow * NCAT + NS + H * C + NPT + h * 8) =
           make_uint4(pack_bf162(nrm[0], nrm[1]), pack_bf162(nrm[2], nrm[3]), pack_bf162(nrm[4], nrm[5]),
                      pack_bf162(nrm[6], nrm[7]));
     }
@@ -709,7 +733,7 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       __syncwarp();
       {   // [8 h][64 B] -> 32 chunks of 16 B, one per lane
         const int h = lane >> 2, part = lane & 3;
-        *reinterpret_cast<uint4*>(cat + (row0 + i) * NCAT + NS + h * C + (gw & 1) * 32 + part * 8) =
+        *reinterpret_cast<uint4*>(cat + (orow0 + i) * NCAT + NS + h * C + (gw & 1) * 32 + part * 8) =
             reinterpret_cast<const uint4*>(stage_e)[lane];
       }
       __syncwarp();
@@ -836,6 +860,76 @@ ipa_pair_bias_mma_kernel(const __grid_constant__ CUtensorMap map_e, const float*
   if (warp == 0) tmem_free(tmem, 256);
 }
 
+// ---- patches of 256 residues: common centroid of the two blocks, merge of the two key blocks ----------------------------
+// cen[2 b], cen[2 b + 1] = mean translation of patch b (256 residues)
+__global__ void __launch_bounds__(256) centroid256_kernel(const float* __restrict__ t, float* __restrict__ cen) {
+  __shared__ float part[8][3];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* tp = t + ((int64_t)b * 2 * L + tid) * 3;
+  float cx = tp[0], cy = tp[1], cz = tp[2];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cx += __shfl_xor_sync(0xffffffffu, cx, o); cy += __shfl_xor_sync(0xffffffffu, cy, o); cz += __shfl_xor_sync(0xffffffffu, cz, o);
+  }
+  if (lane == 0) { part[warp][0] = cx; part[warp][1] = cy; part[warp][2] = cz; }
+  __syncthreads();
+  if (tid < 3) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += part[w][tid];
+    v *= 1.0f / (2 * L);
+    cen[(int64_t)b * 6 + tid] = v;
+    cen[(int64_t)b * 6 + 3 + tid] = v;
+  }
+}
+
+// One thread per (query row, head): the two key blocks' features are convex-combined with the weights
+//   w_k = S_k 2^(m_k - m) / sum_k' S_k' 2^(m_k' - m),   m_k = row maximum (log2 units), S_k = sum_j p of block k
+// - exact for the scalar, pair and (affine inverse-frame) point features; the point norms are recomputed from the merged points.
+__global__ void __launch_bounds__(256) merge_kb2_kernel(const __nv_bfloat16* __restrict__ cat2, const float* __restrict__ stats2,
+                                                        int64_t rows, __nv_bfloat16* __restrict__ cat) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * H) return;
+  const int64_t row = idx >> 3;
+  const int h = (int)(idx & 7);
+  const float m0 = stats2[row * 16 + h], m1 = stats2[(rows + row) * 16 + h];
+  const float s0 = 1.0f / stats2[row * 16 + 8 + h], s1 = 1.0f / stats2[(rows + row) * 16 + 8 + h];
+  const float m = fmaxf(m0, m1);
+  const float a0 = s0 * ex2(m0 - m), a1 = s1 * ex2(m1 - m);
+  const float w0 = a0 / (a0 + a1), w1 = a1 / (a0 + a1);
+  const __nv_bfloat16* c0 = cat2 + row * NCAT;
+  const __nv_bfloat16* c1 = cat2 + (rows + row) * NCAT;
+  __nv_bfloat16* out = cat + row * NCAT;
+  auto mix8 = [&](int off, float* keep) {      // eight consecutive features
+    const uint4 u0 = *reinterpret_cast<const uint4*>(c0 + off), u1 = *reinterpret_cast<const uint4*>(c1 + off);
+    const __nv_bfloat162* p0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
+    const __nv_bfloat162* p1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f0 = __bfloat1622float2(p0[e]), f1 = __bfloat1622float2(p1[e]);
+      v[2 * e] = w0 * f0.x + w1 * f1.x; v[2 * e + 1] = w0 * f0.y + w1 * f1.y;
+    }
+    if (keep) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) keep[e] = v[e];
+    }
+    *reinterpret_cast<uint4*>(out + off) = make_uint4(pack_bf162(v[0], v[1]), pack_bf162(v[2], v[3]), pack_bf162(v[4], v[5]),
+                                                      pack_bf162(v[6], v[7]));
+  };
+#pragma unroll
+  for (int q = 0; q < DS / 8; ++q) mix8(h * DS + 8 * q, nullptr);                 // scalar values
+#pragma unroll
+  for (int q = 0; q < C / 8; ++q) mix8(NS + h * C + 8 * q, nullptr);             // pair aggregation
+  float pt[24];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) mix8(NS + H * C + h * 24 + 8 * q, pt + 8 * q);     // local-frame points
+  float nrm[8];
+#pragma unroll
+  for (int p = 0; p < P; ++p) nrm[p] = sqrtf(pt[3 * p] * pt[3 * p] + pt[3 * p + 1] * pt[3 * p + 1] + pt[3 * p + 2] * pt[3 * p + 2]);
+  *reinterpret_cast<uint4*>(out + NS + H * C + NPT + h * 8) =
+      make_uint4(pack_bf162(nrm[0], nrm[1]), pack_bf162(nrm[2], nrm[3]), pack_bf162(nrm[4], nrm[5]), pack_bf162(nrm[6], nrm[7]));
+}
+
 static int launch_pair_bias(const void* e_bf16, const float* wpb, int nl, void* planes, int64_t n_pairs, cudaStream_t s) {
   CUtensorMap me;
   uint64_t de[2] = {(uint64_t)C, (uint64_t)n_pairs}, se[1] = {(uint64_t)C * 2};
@@ -858,11 +952,11 @@ using namespace dab::sm100;
 
 extern "C" {
 
-size_t dab_ipa_packed_bytes(const DabIpaDims* d) { return shape_ok(d) ? packed_offsets().total : 0; }
+size_t dab_ipa_packed_bytes(const DabIpaDims* d) { return shape_ok_fwd(d) ? packed_offsets().total : 0; }
 
 int dab_ipa_pack_weights(const DabIpaDims* d, const DabIpaWeights* w, void* packed, void* stream) {
-  DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
-              "dab_ipa_pack_weights: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
+  DAB_REQUIRE(shape_ok_fwd(d), DAB_EUNSUPPORTED,
+              "dab_ipa_pack_weights: the sm_100a fast path needs L=128 (or 256), D=128, C=64, H=8, ds=32, Pq=Pv=8");
   DAB_REQUIRE(w && packed && w->w_q_scalar && w->w_k_scalar && w->w_v_scalar && w->w_q_point && w->w_k_point &&
                   w->w_v_point && w->w_pair_bias && w->gamma && w->w_out && w->b_out,
               DAB_EINVAL, "dab_ipa_pack_weights: null pointer");
@@ -872,7 +966,10 @@ int dab_ipa_pack_weights(const DabIpaDims* d, const DabIpaWeights* w, void* pack
   return check_launch("dab_ipa_pack_weights");
 }
 
-size_t dab_ipa_sm100_workspace_bytes(const DabIpaDims* d) { return shape_ok(d) ? carve_ws(d->B, nullptr).bytes : 0; }
+size_t dab_ipa_sm100_workspace_bytes(const DabIpaDims* d) {
+  if (!shape_ok_fwd(d)) return 0;
+  return d->L == 2 * L ? carve_ws2(d->B, nullptr).bytes : carve_ws(d->B, nullptr).bytes;
+}
 
 /* Byte offsets of the workspace sections: Qp, Kp, Vp, tc, cat, bias, stats, pu (tests read them: `stats` = row maxima in
  * log2 units [8 heads] | 1 / sum_j p [8 heads] per query row, `pu` = un-normalised probabilities 2^(l - max), bf16 [i][j][h],
@@ -889,13 +986,13 @@ int dab_ipa_sm100_workspace_layout(const DabIpaDims* d, size_t* offsets /* 8 */)
 }
 
 int dab_ipa_pair_bias(const DabIpaDims* d, const void* e_bf16, const float* w_pair_bias, void* bias_f16, void* stream) {
-  DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
-              "dab_ipa_pair_bias: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
+  DAB_REQUIRE(shape_ok_fwd(d), DAB_EUNSUPPORTED,
+              "dab_ipa_pair_bias: the sm_100a fast path needs L=128 (or 256), D=128, C=64, H=8, ds=32, Pq=Pv=8");
   if (d->B == 0) return DAB_OK;
   DAB_REQUIRE(e_bf16 && w_pair_bias && bias_f16 && (reinterpret_cast<uintptr_t>(e_bf16) & 127) == 0 &&
                   aligned16(bias_f16),
               DAB_EINVAL, "dab_ipa_pair_bias: null or misaligned pointer (e 128 B, bias 16 B)");
-  const int64_t n_pairs = (int64_t)d->B * L * L;
+  const int64_t n_pairs = (int64_t)d->B * d->L * d->L;
   if (int rc = launch_pair_bias(e_bf16, w_pair_bias, 1, bias_f16, n_pairs, (cudaStream_t)stream)) return rc;
   return check_launch("dab_ipa_pair_bias");
 }
@@ -904,14 +1001,14 @@ int dab_ipa_pair_bias(const DabIpaDims* d, const void* e_bf16, const float* w_pa
  * planes_f16[n_layers][B*L*L][8] fp16 (contiguous). */
 int dab_ipa_pair_bias_multi(const DabIpaDims* d, const void* e_bf16, const float* w_pair_bias, int n_layers,
                             void* planes_f16, void* stream) {
-  DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
-              "dab_ipa_pair_bias_multi: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
+  DAB_REQUIRE(shape_ok_fwd(d), DAB_EUNSUPPORTED,
+              "dab_ipa_pair_bias_multi: the sm_100a fast path needs L=128 (or 256), D=128, C=64, H=8, ds=32, Pq=Pv=8");
   DAB_REQUIRE(n_layers >= 1 && n_layers <= 6, DAB_EUNSUPPORTED, "dab_ipa_pair_bias_multi: 1 <= n_layers <= 6");
   if (d->B == 0) return DAB_OK;
   DAB_REQUIRE(e_bf16 && w_pair_bias && planes_f16 && (reinterpret_cast<uintptr_t>(e_bf16) & 127) == 0 &&
                   aligned16(planes_f16),
               DAB_EINVAL, "dab_ipa_pair_bias_multi: null or misaligned pointer");
-  const int64_t n_pairs = (int64_t)d->B * L * L;
+  const int64_t n_pairs = (int64_t)d->B * d->L * d->L;
   if (int rc = launch_pair_bias(e_bf16, w_pair_bias, n_layers, planes_f16, n_pairs, (cudaStream_t)stream)) return rc;
   return check_launch("dab_ipa_pair_bias_multi");
 }
@@ -919,7 +1016,7 @@ int dab_ipa_pair_bias_multi(const DabIpaDims* d, const void* e_bf16, const float
 // Projection launch of a layer (weights `pk`), packed operands into `ws`.  With `pk_prev` the kernel first computes the
 // PREVIOUS layer's to_out, y = cat Wout^T + b (cat = ws.cat, weights pk_prev), straight into its A tile: x is not read.
 static int launch_proj(int B, const uint8_t* pk, const float* x, const __nv_bfloat16* x16, const float* R, const float* t,
-                       const Ws& ws, const uint8_t* pk_prev, cudaStream_t s) {
+                       const Ws& ws, const uint8_t* pk_prev, cudaStream_t s, const float* cen_ext = nullptr) {
   const PackedOffsets po = packed_offsets();
   const int M = B * L;
   CUtensorMap mw64, mw48;
@@ -950,7 +1047,7 @@ static int launch_proj(int B, const uint8_t* pk, const float* x, const __nv_bflo
   }
   ipa_proj_kernel<<<dim3(n_split, B), 288, ProjSmem::kTotal, s>>>(
       mw64, mw48, msq, msk, msv, x, R, t, reinterpret_cast<const float*>(pk + po.gamma), ws.Qp, ws.Kp, ws.Vp, ws.tc,
-      g_core_dbg ? g_core_dbg + (1 << 20) : nullptr, x16, mcat, mwout, b_out, pk_prev ? 1 : 0);
+      g_core_dbg ? g_core_dbg + (1 << 20) : nullptr, x16, mcat, mwout, b_out, pk_prev ? 1 : 0, cen_ext);
   count_launch();
   return DAB_OK;
 }
@@ -960,8 +1057,8 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
                           const void* bias_f16, const float* R, const float* t, float* y, void* workspace,
                           size_t workspace_bytes, bool save_for_bwd, void* stream, const void* x_bf16 = nullptr,
                           void* y_bf16 = nullptr, int phases = 7) {
-  DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED,
-              "dab_ipa_fwd_sm100: the sm_100a fast path needs L=128, D=128, C=64, H=8, ds=32, Pq=Pv=8");
+  DAB_REQUIRE(save_for_bwd ? shape_ok(d) : shape_ok_fwd(d), DAB_EUNSUPPORTED,
+              "dab_ipa_fwd_sm100: the sm_100a fast path needs D=128, C=64, H=8, ds=32, Pq=Pv=8 and L=128 (inference: 128 or 256)");
   if (d->B == 0) return DAB_OK;
   DAB_REQUIRE(packed && (x || x_bf16) && e_bf16 && R && t && (y || y_bf16) && workspace, DAB_EINVAL,
               "dab_ipa_fwd_sm100: null pointer");
@@ -969,21 +1066,29 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
                   (reinterpret_cast<uintptr_t>(e_bf16) & 127) == 0 && aligned16(x) && aligned16(y) && aligned16(x_bf16) &&
                   aligned16(y_bf16),
               DAB_EINVAL, "dab_ipa_fwd_sm100: misaligned pointer (workspace/packed 1024 B, e 128 B, x/y 16 B)");
-  const int B = d->B, M = B * L;
+  // A patch of 256 residues = two blocks of 128: everything row-wise (projections, to_out) runs on 2 B blocks, the attention
+  // core once per (query block, key block) pair, and the two key blocks' results are merged by their softmax statistics.
+  const bool two = d->L == 2 * L;
+  const int Lp = d->L, B = two ? 2 * d->B : d->B, M = B * L;
   Ws ws = carve_ws(B, workspace);
-  DAB_REQUIRE(workspace_bytes >= ws.bytes, DAB_EWORKSPACE, "dab_ipa_fwd_sm100: workspace %zu < %zu", workspace_bytes, ws.bytes);
+  Ws2 w2 = {};
+  size_t need = ws.bytes;
+  if (two) { w2 = carve_ws2(d->B, workspace); need = w2.bytes; }
+  DAB_REQUIRE(workspace_bytes >= need, DAB_EWORKSPACE, "dab_ipa_fwd_sm100: workspace %zu < %zu", workspace_bytes, need);
   const PackedOffsets po = packed_offsets();
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
   cudaStream_t s = (cudaStream_t)stream;
   if (phases & 1) {
-    if (int rc = launch_proj(B, pk, x, reinterpret_cast<const __nv_bfloat16*>(x_bf16), R, t, ws, nullptr, s)) return rc;
+    if (two) { centroid256_kernel<<<d->B, 256, 0, s>>>(t, w2.cen); count_launch(); }
+    if (int rc = launch_proj(B, pk, x, reinterpret_cast<const __nv_bfloat16*>(x_bf16), R, t, ws, nullptr, s, two ? w2.cen : nullptr))
+      return rc;
   }
   if (phases & 2) {
     const uint4* bias = reinterpret_cast<const uint4*>(bias_f16);
     if (bias == nullptr) {   // one-off call without a precomputed bias: build this layer's plane now
-      if (int rc = launch_pair_bias(e_bf16, reinterpret_cast<const float*>(pk + po.wpb), 1, ws.bias, (int64_t)M * L, s))
-        return rc;
-      bias = ws.bias;
+      uint4* plane = two ? w2.bias2 : ws.bias;
+      if (int rc = launch_pair_bias(e_bf16, reinterpret_cast<const float*>(pk + po.wpb), 1, plane, (int64_t)M * Lp, s)) return rc;
+      bias = plane;
     }
     CUtensorMap mq, mk, mv, me;
     uint64_t dqk[2] = {(uint64_t)H * QK_W, (uint64_t)M}, sqk[1] = {(uint64_t)H * QK_W * 2};
@@ -993,11 +1098,10 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
     uint64_t dv[2] = {(uint64_t)H * V_W, (uint64_t)M}, sv[1] = {(uint64_t)H * V_W * 2};
     uint32_t bv[2] = {V_W, L};
     if (int rc = make_tensor_map_bf16(&mv, ws.Vp, 2, dv, sv, bv, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    uint64_t de[2] = {(uint64_t)C, (uint64_t)M * L}, se[1] = {(uint64_t)C * 2};
+    uint64_t de[2] = {(uint64_t)C, (uint64_t)M * Lp}, se[1] = {(uint64_t)C * 2};
     uint32_t be[2] = {C, L};
     if (int rc = make_tensor_map_bf16(&me, e_bf16, 2, de, se, be, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    DAB_ENSURE_SMEM(ipa_core_kernel, CoreSmem::kTotal);
-    const int n_tiles = B * (L / IB);
+    const int n_tiles = (two ? 2 * B : B) * (L / IB);      // 256: one tile set per (query block, key block) pair
     int n_sm = 148;
     {
       int dev_id = 0;
@@ -1005,10 +1109,21 @@ static int fwd_sm100_impl(const DabIpaDims* d, const void* packed, const float* 
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev_id);
     }
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;     // persistent: one CTA per SM, two tile contexts each
-    ipa_core_kernel<<<grid, kCoreThreads, CoreSmem::kTotal, s>>>(mq, mk, mv, me, bias, ws.tc, R, ws.cat,
-                                                                 save_for_bwd ? ws.stats : nullptr,
-                                                                 save_for_bwd ? ws.pu : nullptr, n_tiles, g_core_dbg);
+    if (two) {
+      DAB_ENSURE_SMEM(ipa_core_kernel<true>, CoreSmem::kTotal);
+      ipa_core_kernel<true><<<grid, kCoreThreads, CoreSmem::kTotal, s>>>(mq, mk, mv, me, bias, ws.tc, R, w2.cat2, w2.stats2, nullptr,
+                                                                         n_tiles, g_core_dbg, (int64_t)M);
+    } else {
+      DAB_ENSURE_SMEM(ipa_core_kernel<false>, CoreSmem::kTotal);
+      ipa_core_kernel<false><<<grid, kCoreThreads, CoreSmem::kTotal, s>>>(mq, mk, mv, me, bias, ws.tc, R, ws.cat,
+                                                                          save_for_bwd ? ws.stats : nullptr,
+                                                                          save_for_bwd ? ws.pu : nullptr, n_tiles, g_core_dbg, 0);
+    }
     count_launch();
+    if (two) {
+      merge_kb2_kernel<<<(unsigned)(((int64_t)M * H + 255) / 256), 256, 0, s>>>(w2.cat2, w2.stats2, (int64_t)M, ws.cat);
+      count_launch();
+    }
   }
   if (phases & 4) {
     // y = cat Wout^T + b: one 128-wide N tile per CTA when the batch fills the GPU, four 32-wide ones otherwise
@@ -1031,7 +1146,7 @@ int dab_ipa_fwd_sm100(const DabIpaDims* d, const void* packed, const float* x, c
  * Wcat^T bf16 [128][1344], Wout^T bf16 [1024][128] - so that a caller's own GEMMs can reuse the bf16 copies. */
 int dab_ipa_packed_layout(const DabIpaDims* d, size_t* offs) {
   DAB_REQUIRE(d && offs, DAB_EINVAL, "dab_ipa_packed_layout: null pointer");
-  DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED, "dab_ipa_packed_layout: the sm_100a fast path needs the train.py configuration");
+  DAB_REQUIRE(shape_ok_fwd(d), DAB_EUNSUPPORTED, "dab_ipa_packed_layout: the sm_100a fast path needs the train.py configuration");
   const PackedOffsets po = packed_offsets();
   offs[0] = po.wcat; offs[1] = po.wout; offs[2] = po.wpb; offs[3] = po.bout; offs[4] = po.gamma; offs[5] = po.wcat_t;
   offs[6] = po.wout_t;
@@ -1078,16 +1193,22 @@ int dab_ipa_fwd_sm100_stages(const DabIpaDims* d, const void* packed, const floa
  * the last layer).  Bit-identical to the unfused sequence. */
 int dab_ipa_mid_sm100(const DabIpaDims* d, const void* packed_prev, const void* packed, const float* R, const float* t,
                       void* workspace, size_t workspace_bytes, void* stream) {
-  DAB_REQUIRE(shape_ok(d), DAB_EUNSUPPORTED, "dab_ipa_mid_sm100: the sm_100a fast path needs the train.py configuration");
+  DAB_REQUIRE(shape_ok_fwd(d), DAB_EUNSUPPORTED, "dab_ipa_mid_sm100: the sm_100a fast path needs the train.py configuration");
   if (d->B == 0) return DAB_OK;
   DAB_REQUIRE(packed_prev && packed && R && t && workspace, DAB_EINVAL, "dab_ipa_mid_sm100: null pointer");
   DAB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0 && (reinterpret_cast<uintptr_t>(packed) & 1023) == 0 &&
                   (reinterpret_cast<uintptr_t>(packed_prev) & 1023) == 0,
               DAB_EINVAL, "dab_ipa_mid_sm100: workspace / packed weights must be 1024-byte aligned");
-  Ws ws = carve_ws(d->B, workspace);
-  DAB_REQUIRE(workspace_bytes >= ws.bytes, DAB_EWORKSPACE, "dab_ipa_mid_sm100: workspace %zu < %zu", workspace_bytes, ws.bytes);
-  if (int rc = launch_proj(d->B, reinterpret_cast<const uint8_t*>(packed), nullptr, nullptr, R, t, ws,
-                           reinterpret_cast<const uint8_t*>(packed_prev), (cudaStream_t)stream))
+  const bool two = d->L == 2 * L;
+  const int nblk = two ? 2 * d->B : d->B;
+  Ws ws = carve_ws(nblk, workspace);
+  Ws2 w2 = {};
+  size_t need = ws.bytes;
+  if (two) { w2 = carve_ws2(d->B, workspace); need = w2.bytes; }
+  DAB_REQUIRE(workspace_bytes >= need, DAB_EWORKSPACE, "dab_ipa_mid_sm100: workspace %zu < %zu", workspace_bytes, need);
+  if (two) { centroid256_kernel<<<d->B, 256, 0, (cudaStream_t)stream>>>(t, w2.cen); count_launch(); }
+  if (int rc = launch_proj(nblk, reinterpret_cast<const uint8_t*>(packed), nullptr, nullptr, R, t, ws,
+                           reinterpret_cast<const uint8_t*>(packed_prev), (cudaStream_t)stream, two ? w2.cen : nullptr))
     return rc;
   return check_launch("dab_ipa_mid_sm100");
 }

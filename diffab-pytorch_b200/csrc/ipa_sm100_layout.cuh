@@ -82,6 +82,32 @@ inline Ws carve_ws(int B, void* base) {
 inline bool shape_ok(const DabIpaDims* d) {
   return d && d->L == L && d->D == D && d->C == C && d->H == H && d->ds == DS && d->Pq == P && d->Pv == P && d->B >= 0;
 }
+// inference forward: patches of 256 residues too (two blocks of 128: block-wise projections on a common centroid, the
+// attention core once per (query block, key block) pair, the two key blocks' results merged by their softmax statistics)
+inline bool shape_ok_fwd(const DabIpaDims* d) {
+  return d && (d->L == L || d->L == 2 * L) && d->D == D && d->C == C && d->H == H && d->ds == DS && d->Pq == P && d->Pv == P &&
+         d->B >= 0;
+}
+// extra workspace sections of a 256-residue forward, behind the sections of carve_ws(2 B blocks)
+struct Ws2 {
+  __nv_bfloat16* cat2;   // [2 key blocks][rows][NCAT] bf16: per-key-block concat features (normalised inside the block)
+  float* stats2;         // [2][rows][16]: their softmax statistics
+  float* cen;            // [blocks][3]: the patch centroid, repeated for the patch's two blocks
+  uint4* bias2;          // fallback bias plane [rows][256] (caller without precomputed planes)
+  size_t bytes;          // total, including the base sections
+};
+inline Ws2 carve_ws2(int B, void* base) {
+  auto al = [](size_t n) { return (n + 1023) / 1024 * 1024; };
+  const size_t rows = (size_t)B * 2 * L;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base) + carve_ws(2 * B, base).bytes;
+  Ws2 w;
+  w.cat2 = reinterpret_cast<__nv_bfloat16*>(p); p += al(2 * rows * NCAT * 2);
+  w.stats2 = reinterpret_cast<float*>(p); p += al(2 * rows * 16 * 4);
+  w.cen = reinterpret_cast<float*>(p); p += al((size_t)2 * B * 3 * 4);
+  w.bias2 = reinterpret_cast<uint4*>(p); p += al(rows * 2 * L * 16);
+  w.bytes = (size_t)(p - reinterpret_cast<uint8_t*>(base));
+  return w;
+}
 
 
 }  // namespace sm100

@@ -561,6 +561,14 @@ def inverse_euclidean_transform(x, r, t):
 
 
 FAST_L = 128   # patch length of the tensor-core kernels (keys sit on the 128 TMEM lanes)
+FAST_L2 = 256  # inference only: two blocks of 128 (block-wise projections, the core per (query block, key block), merged)
+
+
+def _fast_len(L, inference):
+    """Length a patch of L residues is padded to for the tensor-core kernels (None: not covered)."""
+    if L <= FAST_L:
+        return FAST_L
+    return FAST_L2 if inference and L <= FAST_L2 else None
 
 
 def _pad_patch(x, e, r, t, L_to=FAST_L):
@@ -864,16 +872,25 @@ class InvariantPointAttentionLayer(nn.Module):
             return _IpaFunction.apply(self._nopb_view(), need_bwd, x, e0, r, t, *ws)
         if e.dtype == torch.bfloat16:
             L = x.shape[1]
-            if L < FAST_L and self.fast_path_supported(FAST_L):
-                # shorter patch on the tensor-core kernels: padded to 128 residues, padded keys masked through the bias plane
-                xp, ep, rp, tp = _pad_patch(x, e, r, t)
+            no_grad = not (torch.is_grad_enabled() and (x.requires_grad or e.requires_grad or
+                                                        any(w.requires_grad for w in self._weights())))
+            Lp = _fast_len(L, no_grad)
+            if Lp is not None and L < Lp and self.fast_path_supported(Lp, no_grad):
+                # shorter patch on the tensor-core kernels: padded to 128 (without gradients: 256) residues, padded keys
+                # masked through the bias plane
+                xp, ep, rp, tp = _pad_patch(x, e, r, t, Lp)
                 with torch.no_grad():
                     if pair_bias is None:
                         bias = self.pair_bias(ep.detach())
                     else:
-                        bias = F.pad(pair_bias, (0, 0, 0, FAST_L - L, 0, FAST_L - L))
+                        bias = F.pad(pair_bias, (0, 0, 0, Lp - L, 0, Lp - L))
                     _mask_padded_keys([bias], L)
+                if Lp == FAST_L2:
+                    return self.forward_fast_io(xp, ep, rp, tp, bias, torch.float32)[:, :L]
                 return self.forward_fast(xp, ep, rp, tp, bias)[:, :L]
+            if L == FAST_L2 and no_grad and self.fast_path_supported(L, True):
+                return self.forward_fast_io(x, e, r, t, pair_bias if pair_bias is not None else self.pair_bias(e),
+                                            torch.float32)
             return self.forward_fast(x, e, r, t, pair_bias)
         ws = self._weights()
         need_bwd = torch.is_grad_enabled() and (x.requires_grad or e.requires_grad or r.requires_grad or
@@ -893,10 +910,11 @@ class InvariantPointAttentionLayer(nn.Module):
         return v
 
     # ---- sm_100a fast path (inference; train.py configuration only) ----
-    def fast_path_supported(self, L):
-        return (self.use_pair_bias and L == 128 and self.d_residue_emb == 128 and self.d_pair_emb == 64 and self.n_head == 8 and
-                self.d_scalar_per_head == 32 and self.n_query_point_per_head == 8 and
-                self.n_value_point_per_head == 8)
+    def fast_path_supported(self, L, inference=False):
+        """Shapes of the tensor-core kernels: the train.py configuration at L = 128; without gradients also L = 256."""
+        return (self.use_pair_bias and (L == FAST_L or (inference and L == FAST_L2)) and self.d_residue_emb == 128 and
+                self.d_pair_emb == 64 and self.n_head == 8 and self.d_scalar_per_head == 32 and
+                self.n_query_point_per_head == 8 and self.n_value_point_per_head == 8)
 
     def _packed_weights(self, dims):
         ws = self._weights()
@@ -968,7 +986,7 @@ class InvariantPointAttentionLayer(nn.Module):
         ``out_dtype``): the layers of a stack hand it over already rounded to bf16 - what the next layer's projections
         consume anyway, so no bit of the result changes - via ``dab_ipa_fwd_sm100_io``."""
         B, L, D = x.shape
-        if not self.fast_path_supported(L):
+        if not self.fast_path_supported(L, True):
             raise RuntimeError("the sm_100a fast path only supports the train.py configuration")
         x = _lib.dev(x, x.dtype if x.dtype == torch.bfloat16 else torch.float32, "x")
         e = _lib.dev(e_bf16, torch.bfloat16, "e")
@@ -1000,29 +1018,31 @@ class InvariantPointAttentionModule(nn.Module):
 
     def forward(self, res_emb, pair_emb, orientations, translations, pair_bias=None):
         L = res_emb.shape[1]
-        if pair_emb.dtype == torch.bfloat16 and L < FAST_L and self.layers[0].fast_path_supported(FAST_L):
-            # shorter patches on the tensor-core kernels: pad once for the whole stack, mask the padded keys in every
-            # layer's bias plane, slice the result
-            xp, ep, rp, tp = _pad_patch(res_emb, pair_emb, orientations, translations)
+        needs_grad = torch.is_grad_enabled() and (res_emb.requires_grad or pair_emb.requires_grad or
+                                                  any(p.requires_grad for p in self.parameters()))
+        Lp = _fast_len(L, not needs_grad)
+        if (pair_emb.dtype == torch.bfloat16 and Lp is not None and L < Lp and
+                self.layers[0].fast_path_supported(Lp, not needs_grad)):
+            # shorter patches on the tensor-core kernels: pad once for the whole stack (to 128, without gradients to 256
+            # residues), mask the padded keys in every layer's bias plane, slice the result
+            xp, ep, rp, tp = _pad_patch(res_emb, pair_emb, orientations, translations, Lp)
             with torch.no_grad():
                 if pair_bias is None:
                     planes = self.precompute_pair_bias(ep.detach())
                 else:
-                    planes = [F.pad(p_, (0, 0, 0, FAST_L - L, 0, FAST_L - L)) for p_ in pair_bias]
+                    planes = [F.pad(p_, (0, 0, 0, Lp - L, 0, Lp - L)) for p_ in pair_bias]
                 _mask_padded_keys(planes, L)
             return self.forward(xp, ep, rp, tp, planes)[:, :L]
         if (pair_bias is None and pair_emb.dtype == torch.bfloat16 and
-                self.layers[0].fast_path_supported(pair_emb.shape[1])):
+                self.layers[0].fast_path_supported(pair_emb.shape[1], not needs_grad)):
             # tensor-core path: the bias planes of all layers in one pass over the pair tensor (their gradient
             # w.r.t. to_pair_bias and the pair tensor is produced by the layers' own backward kernels)
             pair_bias = self.precompute_pair_bias(pair_emb.detach())
-        needs_grad = torch.is_grad_enabled() and (res_emb.requires_grad or pair_emb.requires_grad or
-                                                  any(p.requires_grad for p in self.parameters()))
         if (not needs_grad and pair_bias is not None and pair_emb.dtype == torch.bfloat16 and len(self.layers) > 1 and
-                self.layers[0].fast_path_supported(pair_emb.shape[1])):
+                self.layers[0].fast_path_supported(pair_emb.shape[1], True)):
             # inference on the tensor-core path: the residue stream travels between the layers as bf16
             n = len(self.layers)
-            if res_emb.shape[0] >= 128:
+            if res_emb.shape[0] * (L // FAST_L) >= 128:
                 # large batches (one projection CTA per patch): each layer's to_out is fused into the next layer's
                 # projection kernel, the stream between the layers never exists in HBM (bit-identical)
                 return self._forward_fused_stack(res_emb, pair_emb, orientations, translations, pair_bias)
@@ -1210,7 +1230,7 @@ class Denoiser(nn.Module):
         D = cache["c"].shape[-1]
         if cache.get("w2_bf16") is not None and pair_context_emb.dtype == torch.bfloat16 and (B * L) % 128 == 0:
             # bf16 out when the layer stack takes it (its first projection kernel rounds an fp32 input the same way)
-            h16 = pair_bias is not None and len(self.ipa.layers) > 1 and self.ipa.layers[0].fast_path_supported(L)
+            h16 = pair_bias is not None and len(self.ipa.layers) > 1 and self.ipa.layers[0].fast_path_supported(L, True)
             h = torch.empty(B, L, D, device=seq_idx_t.device, dtype=torch.bfloat16 if h16 else torch.float32)
             _lib.check(_lib.lib().dab_front_fwd_sm100(ptr(cache["c"]), ptr(cache["t1"]), ptr(seq_idx_t.contiguous()),
                                                       B * L, ptr(cache["w2_bf16"]), ptr(cache["b2"]),
@@ -1225,9 +1245,11 @@ class Denoiser(nn.Module):
             eps = torch.empty(B, L, 3, device=h.device)
             rot = torch.empty(B, L, 3, device=h.device)
             post = torch.empty(B, L, 21, device=h.device)
-            _lib.check(_lib.lib().dab_heads_fwd_sm100(ptr(cache["heads_packed"]), ptr(h.contiguous()),
-                                                      ptr(beta.contiguous()), B, L, ptr(eps), ptr(rot), ptr(post),
-                                                      _lib.stream_ptr()), "dab_heads_fwd_sm100")
+            nb = L // FAST_L if L % FAST_L == 0 else 1     # the kernel works on blocks of 128 residues (CTA = block)
+            beta_blk = beta.contiguous() if nb == 1 else beta.repeat_interleave(nb)
+            _lib.check(_lib.lib().dab_heads_fwd_sm100(ptr(cache["heads_packed"]), ptr(h.contiguous()), ptr(beta_blk),
+                                                      B * nb, L // nb, ptr(eps), ptr(rot), ptr(post), _lib.stream_ptr()),
+                       "dab_heads_fwd_sm100")
             return eps, rot, post
         t_emb = torch.stack([beta, torch.sin(beta), torch.cos(beta)], dim=-1)                   # (B, 3)
         pb = torch.addmm(cache["bh1"], t_emb, cache["wt1"])                                      # (B, 3D)
@@ -1541,18 +1563,19 @@ class DiffAb(nn.Module):
         T = self.T
         t_start = T if t_start is None else t_start
         L0 = seq_idx.shape[1]
-        if (pair_context_emb.dtype == torch.bfloat16 and L0 < FAST_L and _valid_len is None
-                and self.denoiser.ipa.layers[0].fast_path_supported(FAST_L)):
-            # Shorter patches on the tensor-core path: the state and the context are padded to 128 residues (never
+        Lp = _fast_len(L0, True)
+        if (pair_context_emb.dtype == torch.bfloat16 and Lp is not None and L0 < Lp and _valid_len is None
+                and self.denoiser.ipa.layers[0].fast_path_supported(Lp, True)):
+            # Shorter patches on the tensor-core path: the state and the context are padded to 128 (or 256) residues (never
             # generated, never attended to: their keys are masked in every layer's bias plane), the loop runs on the
             # padded batch and the result is cut back.
-            n = FAST_L - L0
+            n = Lp - L0
             eye = torch.eye(3, device=orientations.device, dtype=orientations.dtype).expand(orientations.shape[0], n, 3, 3)
             pad_noise = None
             if noises is not None:
                 B_ = seq_idx.shape[0]
                 def pn(d):
-                    return {"seq_exp": F.pad(d["seq_exp"].view(B_, L0, -1), (0, 0, 0, n), value=1.0).reshape(B_ * FAST_L, -1),
+                    return {"seq_exp": F.pad(d["seq_exp"].view(B_, L0, -1), (0, 0, 0, n), value=1.0).reshape(B_ * Lp, -1),
                             "z": F.pad(d["z"], (0, 0, 0, n)), "axis": F.pad(d["axis"], (0, 0, 0, n), value=1.0),
                             "hist_exp": d["hist_exp"], "jitter": F.pad(d["jitter"], (0, n)), "gauss": F.pad(d["gauss"], (0, n))}
                 pad_noise = {k: pn(v) for k, v in noises.items()}
@@ -1731,7 +1754,8 @@ class DiffAb(nn.Module):
         pairwise_dihedrals = torch.zeros(B, L, L, 2, device=dev) if pairwise_dihedrals is None else mv(pairwise_dihedrals)
         distmat = mv(distmat)
         layer0 = self.denoiser.ipa.layers[0]
-        use_bf16 = precision == "bf16" and (layer0.fast_path_supported(L) or (L < FAST_L and layer0.fast_path_supported(FAST_L)))
+        Lp = _fast_len(L, True)                       # tensor-core path: L <= 256 (padded to 128 or 256 residues)
+        use_bf16 = precision == "bf16" and Lp is not None and layer0.fast_path_supported(Lp, True)
         res_parts, pair_parts = [], []
         fused_pair = (use_bf16 and distmat is None and self.pair_context_embedding.fused_supported(L, A))
         from .synth import pairwise_atom_distances, pairwise_atom_sq_distances

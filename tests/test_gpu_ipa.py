@@ -387,3 +387,58 @@ def test_fused_stack_is_bit_identical_to_the_layerwise_stack():
             assert torch.isfinite(fused).all()
             assert torch.equal(fused, h)
         assert torch.equal(mod(x, e, R, t, planes), fused)          # the module picks the fused stack at this batch size
+
+
+@pytest.mark.parametrize("L", [256, 200, 129])
+def test_tensor_core_inference_for_patches_up_to_256_residues(L):
+    """Inference on patches of 128 < L <= 256 residues - what the reference's preprocessing produces (the union of two
+    128-nearest-residue sets, preprocess_pdb.py:48-58) - on the tensor-core kernels: two blocks of 128 (block-wise
+    projections on the patch centroid, the attention core per (query block, key block), the key blocks merged by their
+    softmax statistics), ragged lengths padded to 256 with the padded keys masked.  One layer and a three-layer stack
+    against the fp64 oracle on the bf16-rounded pair tensor (2e-2 / 3e-2 max-normalised, the bf16 bars of L = 128)."""
+    shp = synth.ipa_layer_shapes(128, 64, 8, 32, 8, 8)
+    layer = InvariantPointAttentionLayer(128, 64, 32, 8, 8, 8).to(DEV)
+    layer.load_state_dict(synth.synthetic_state(shp, seed=5))
+    x, e, R, t = synth.make_ipa_inputs(2, L, 128, 64, seed=500 + L)
+    e16 = e.to(torch.bfloat16)
+    w = {k: v.detach().cpu().double() for k, v in layer.state_dict().items()}
+    ref = oipa.ipa_layer(w, x.double(), e16.double(), R.double(), t.double(), 8)
+    with torch.no_grad():
+        got = layer(x.to(DEV), e16.to(DEV), R.to(DEV), t.to(DEV))
+        assert got.shape == (2, L, 128) and torch.isfinite(got).all()
+        assert _rel(got, ref) < 2e-2
+        if L == 256:   # with the bias plane given (as the sampling loop does)
+            assert torch.equal(layer(x.to(DEV), e16.to(DEV), R.to(DEV), t.to(DEV), layer.pair_bias(e16.to(DEV))), got)
+    mod = InvariantPointAttentionModule(3, 128, 64, 32, 8, 8, 8).to(DEV)
+    state = {}
+    for k_, lay in enumerate(mod.layers):
+        sd = synth.synthetic_state(shp, seed=30 + k_)
+        lay.load_state_dict(sd)
+        state.update({f"l.{k_}.{n}": v.double() for n, v in sd.items()})
+    refm = oipa.ipa_module(state, x.double(), e16.double(), R.double(), t.double(), 3, 8, prefix="l.")
+    with torch.no_grad():
+        gotm = mod(x.to(DEV), e16.to(DEV), R.to(DEV), t.to(DEV))
+    assert gotm.shape == (2, L, 128) and _rel(gotm, refm) < 3e-2
+
+
+def test_fused_stack_at_256_residues_matches_the_layerwise_stack():
+    """Batches of >= 64 patches of 256 residues take the fused stack (to_out of a layer inside the next layer's projection
+    kernel, 128 blocks of 128 residues): same bits as the layer-by-layer bf16 hand-off."""
+    B, L = 64, 256
+    mod = InvariantPointAttentionModule(3, 128, 64, 32, 8, 8, 8).to(DEV)
+    shp = synth.ipa_layer_shapes(128, 64, 8, 32, 8, 8)
+    for k_, lay in enumerate(mod.layers):
+        lay.load_state_dict(synth.synthetic_state(shp, seed=40 + k_))
+    g = torch.Generator(device=DEV).manual_seed(2)
+    x = torch.randn(B, L, 128, device=DEV, generator=g)
+    e = torch.randn(B, L, L, 64, device=DEV, generator=g).bfloat16()
+    R = synth.uniform_rotations(B, L, device=DEV)
+    t = 10 * torch.randn(B, L, 3, device=DEV, generator=g)
+    with torch.no_grad():
+        planes = mod.precompute_pair_bias(e)
+        fused = mod._forward_fused_stack(x, e, R, t, planes)
+        h = x
+        for k_, lay in enumerate(mod.layers):
+            h = lay.forward_fast_io(h, e, R, t, planes[k_], torch.float32 if k_ == 2 else torch.bfloat16)
+        assert torch.isfinite(fused).all() and torch.equal(fused, h)
+        assert torch.equal(mod(x, e, R, t, planes), fused)
