@@ -151,7 +151,13 @@ int dab_ipa_bwd_f32(const DabIpaDims* d, const DabIpaWeights* w, const float* x,
  * bf16 pair tensor streamed by TMA, tcgen05 tensor-core contractions with TMEM accumulators,
  * split-bf16 point-distance logits, fp32 softmax.  `packed` is produced once per layer by
  * dab_ipa_pack_weights (weights are constant during sampling).  x[B,L,D] fp32 in, y[B,L,D] fp32
- * out, e_bf16[B,L,L,C] bf16. */
+ * out, e_bf16[B,L,L,C] bf16.
+ * The inference entry points (dab_ipa_fwd_sm100, _io, _stages, dab_ipa_mid_sm100, dab_ipa_pair_bias*, the packing and
+ * workspace functions) also take L = 256 - the reference's preprocessed patches have 128..256 residues
+ * (preprocess_pdb.py:48-58; shorter ones are padded by the caller with -inf in the padded keys' bias columns): a patch is
+ * then two blocks of 128 residues - block-wise projections centred on the patch centroid, the attention core once per
+ * (query block, key block) pair, the two key blocks' results merged by their softmax statistics (exact for the scalar,
+ * pair and local-frame point features; point norms recomputed).  The training pair (_train / dab_ipa_bwd_sm100) is L = 128. */
 size_t dab_ipa_packed_bytes(const DabIpaDims* d);
 int dab_ipa_pack_weights(const DabIpaDims* d, const DabIpaWeights* w, void* packed, void* stream);
 /* offs[0..6]: byte offsets of Wcat bf16 [1344][128] (rows in the order to_q_scalar, to_k_scalar, to_v_scalar, to_q_point,

@@ -544,12 +544,13 @@ def test_sample_on_ragged_patches_from_the_reader(tmp_path):
     assert float((a32["orientations"] - a16["orientations"]).abs().max()) < 5e-2
 
 
-def test_shorter_patches_sample_on_the_tensor_core_path():
-    """L = 100 < 128: sample() runs the bf16 tensor-core path on a padded batch whose padded keys are masked, so one
-    reverse step agrees with the fp32 kernels on the unpadded batch (same injected draws), eagerly and from the graphs."""
+@pytest.mark.parametrize("L", [100, 176, 256])
+def test_other_patch_lengths_sample_on_the_tensor_core_path(L):
+    """L = 100 < 128 and 128 < L <= 256 (the lengths of the reference's preprocessed patches): sample() runs the bf16
+    tensor-core path on a batch padded to 128 / 256 residues whose padded keys are masked, so one reverse step agrees with
+    the fp32 kernels on the unpadded batch (same injected draws), eagerly and from the graphs."""
     from diffab_pytorch_b200.diffab_pytorch import cast_pair_to_bf16
     model = _model(0)
-    L = 100
     batch = synth.make_patches(2, L, seed=21, cdr=(40, 52))
     b = _to(batch)
     m = batch["generation_mask"]
@@ -571,7 +572,7 @@ def test_shorter_patches_sample_on_the_tensor_core_path():
     assert float((a32["translations"] - a16["translations"]).norm(dim=-1).max() / step) < 2e-2
     assert float((a32["orientations"] - a16["orientations"]).abs().max()) < 5e-2
     assert torch.equal(a16["seq_idx"].cpu()[~m], batch["seq_idx"][~m])
-    # end to end through sample(): host tensors in, the tensor-core path picked for L < 128
+    # end to end through sample(): host tensors in, the tensor-core path picked for this length
     out = model.sample(batch["seq_idx"], batch["xyz"], batch["orientations"], batch["backbone_dihedrals"], None,
                        batch["pairwise_dihedrals"], batch["atom_mask"], batch["chain_idx"], batch["residue_idx"],
                        batch["generation_mask"], batch["residue_mask"], t_start=100, t_stop=97)
