@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(288, 1)
 pair_embed_kernel(const __grid_constant__ CUtensorMap map_w, const uint8_t* __restrict__ packed,
                   const int64_t* __restrict__ seq, const float* __restrict__ xyz, const float* __restrict__ dihedrals,
                   const int64_t* __restrict__ residue_idx, const int64_t* __restrict__ chain_idx,
-                  const uint8_t* __restrict__ atom_mask, int n_rows, __nv_bfloat16* __restrict__ e_out) {
+                  const uint8_t* __restrict__ atom_mask, int n_rows, __nv_bfloat16* __restrict__ e_out, int Lp) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using S = PeSmem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
@@ -117,8 +117,13 @@ pair_embed_kernel(const __grid_constant__ CUtensorMap map_w, const uint8_t* __re
   const uint32_t smem_base = smem_u32(smem);
   if ((smem_base & 1023u) != 0) asm volatile("trap;");
 
+  // Work item = (query row, block of 128 keys): `n_rows` items.  Patches of Lp = 256 residues have two key blocks per
+  // query row; the items of a patch are ordered key block first, so consecutive items share the per-key registers.
   const int rows_per_cta = (n_rows + gridDim.x - 1) / gridDim.x;
   const int row_lo = blockIdx.x * rows_per_cta, row_hi = min(n_rows, row_lo + rows_per_cta);
+  const int nkb = Lp / PE_L, per_patch = Lp * nkb;
+  auto qrow_of = [&](int item) { const int b = item / per_patch; return b * Lp + (item - b * per_patch) % Lp; };
+  auto kblk_of = [&](int item) { const int b = item / per_patch; return b * nkb + (item - b * per_patch) / Lp; };   // (patch, key block)
 
   if (tid == 0) {
     for (int i = 0; i < PE_N_BARS; ++i) mbar_init(&bars[i], (i == PE_A_READY || i >= PE_ACT) ? 256u : 1u);
@@ -148,8 +153,8 @@ pair_embed_kernel(const __grid_constant__ CUtensorMap map_w, const uint8_t* __re
           for (int kb = 0; kb < kblocks[m]; ++kb, ++slot)
             tma_load_2d(smem + S::kW + slot * 8192, &map_w, &bars[PE_W_FULL], kb * 64, m * 64);
       }
-      auto load_row_tables = [&](int row) {     // the 21 coefficient rows and 21 pair-type rows this query row can hit
-        const int si = (int)__ldg(seq + row);
+      auto load_row_tables = [&](int item) {    // the 21 coefficient rows and 21 pair-type rows this query row can hit
+        const int si = (int)__ldg(seq + qrow_of(item));
         mbar_arrive_expect_tx(&bars[PE_ROW_FULL], S::kCoefBytes + PE_V * 64 * 2);
         bulk_load_1d(smem + S::kCoef, packed + PePacked::kCoef + (size_t)si * PE_V * PE_COEF_STRIDE * 4, S::kCoefBytes,
                      &bars[PE_ROW_FULL]);
@@ -215,12 +220,14 @@ pair_embed_kernel(const __grid_constant__ CUtensorMap map_w, const uint8_t* __re
     int sj = 0;
     float chain_j = 0.f, resmask_j = 0.f;
     int ridx_j = 0;
-    for (int row = row_lo, it = 0; row < row_hi; ++row, ++it) {
+    for (int item = row_lo, it = 0; item < row_hi; ++item, ++it) {
       const uint32_t ph = it & 1;
-      const int b = row / PE_L, i = row % PE_L;
-      if (b != cur_b) {       // per-patch data of key j (registers)
+      const int row = qrow_of(item);                  // query row (b, i)
+      const int b = kblk_of(item);                    // (patch, key block): the keys are residues 128 kb + j of the patch
+      const int64_t joff = (int64_t)(b % nkb) * PE_L + j;      // key index inside the patch
+      if (b != cur_b) {       // per-(patch, key block) data of key j (registers)
         cur_b = b;
-        const int64_t rj = (int64_t)b * PE_L + j;
+        const int64_t rj = (int64_t)(b / nkb) * Lp + joff;
 #pragma unroll
         for (int c = 0; c < PE_A * 3; ++c) xj[c] = __ldg(xyz + rj * (PE_A * 3) + c);
         mj = 0;
@@ -245,7 +252,7 @@ pair_embed_kernel(const __grid_constant__ CUtensorMap map_w, const uint8_t* __re
       }
       bar_compute();
       const uint32_t mi = __float_as_uint(s_row[48]);
-      const float2 dih = __ldg(reinterpret_cast<const float2*>(dihedrals) + (int64_t)row * PE_L + j);
+      const float2 dih = __ldg(reinterpret_cast<const float2*>(dihedrals) + (int64_t)row * Lp + joff);
       // ---- RBF tile: thread (j, half) fills atoms a = 8 half .. 8 half + 7 of its row (a = 15 is zero padding)
       mbar_wait(&bars[PE_ROW_FULL], ph);
       if (it > 0) {                                   // the previous row's last chain has finished reading tile A
@@ -377,7 +384,7 @@ pair_embed_kernel(const __grid_constant__ CUtensorMap map_w, const uint8_t* __re
         tmem_ld_x32(tmem_lane + half * 32, v);
         tmem_wait_ld();
         const float rm = s_row[52] * resmask_j;
-        uint4* dst = reinterpret_cast<uint4*>(e_out + ((int64_t)row * PE_L + j) * PE_C + half * 32);
+        uint4* dst = reinterpret_cast<uint4*>(e_out + ((int64_t)row * Lp + joff) * PE_C + half * 32);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float o[8];
@@ -417,7 +424,8 @@ int dab_pair_embed_pack_weights(const DabPairEmbedWeights* w, void* packed, void
 int dab_pair_embed_fwd_sm100(const void* packed, const int64_t* seq_masked, const float* xyz, const float* pairwise_dihedrals,
                              const int64_t* residue_idx, const int64_t* chain_idx, const uint8_t* atom_mask, int B, int L_,
                              int A, void* e_bf16, void* stream) {
-  DAB_REQUIRE(L_ == PE_L && A == PE_A, DAB_EUNSUPPORTED, "dab_pair_embed_fwd_sm100: needs L = 128 residues and 15 atoms per residue");
+  DAB_REQUIRE((L_ == PE_L || L_ == 2 * PE_L) && A == PE_A, DAB_EUNSUPPORTED,
+              "dab_pair_embed_fwd_sm100: needs L = 128 or 256 residues and 15 atoms per residue");
   DAB_REQUIRE(B >= 0, DAB_EINVAL, "dab_pair_embed_fwd_sm100: negative batch");
   if (B == 0) return DAB_OK;
   DAB_REQUIRE(packed && seq_masked && xyz && pairwise_dihedrals && residue_idx && chain_idx && atom_mask && e_bf16, DAB_EINVAL,
@@ -432,11 +440,11 @@ int dab_pair_embed_fwd_sm100(const void* packed, const int64_t* seq_masked, cons
                                     CU_TENSOR_MAP_SWIZZLE_128B))
     return rc;
   DAB_ENSURE_SMEM(pair_embed_kernel, PeSmem::kTotal);
-  const int n_rows = B * PE_L;
+  const int n_rows = B * L_ * (L_ / PE_L);      // work items: (query row, block of 128 keys)
   const int grid = n_rows < 148 ? n_rows : 148;
   pair_embed_kernel<<<grid, 288, PeSmem::kTotal, (cudaStream_t)stream>>>(
       mw, reinterpret_cast<const uint8_t*>(packed), seq_masked, xyz, pairwise_dihedrals, residue_idx, chain_idx, atom_mask,
-      n_rows, reinterpret_cast<__nv_bfloat16*>(e_bf16));
+      n_rows, reinterpret_cast<__nv_bfloat16*>(e_bf16), L_);
   count_launch();
   return check_launch("dab_pair_embed_fwd_sm100");
 }

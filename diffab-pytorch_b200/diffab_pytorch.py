@@ -481,7 +481,7 @@ class PairEmbedding(nn.Module):
 
     def fused_supported(self, L, A):
         """Shapes the fused tcgen05 kernel (csrc/pair_embed_sm100.cu) covers."""
-        return (L == 128 and A == 15 and self.d_feat == 64 and self.max_dist_to_consider == 32 and
+        return (L in (128, 256) and A == 15 and self.d_feat == 64 and self.max_dist_to_consider == 32 and
                 self.pair2distcoef.weight.shape[1] == 225)
 
     @torch.no_grad()
@@ -1757,7 +1757,7 @@ class DiffAb(nn.Module):
         Lp = _fast_len(L, True)                       # tensor-core path: L <= 256 (padded to 128 or 256 residues)
         use_bf16 = precision == "bf16" and Lp is not None and layer0.fast_path_supported(Lp, True)
         res_parts, pair_parts = [], []
-        fused_pair = (use_bf16 and distmat is None and self.pair_context_embedding.fused_supported(L, A))
+        fused_pair = (use_bf16 and distmat is None and self.pair_context_embedding.fused_supported(Lp, A))
         from .synth import pairwise_atom_distances, pairwise_atom_sq_distances
         # distances derived on the device: exact differences on the fp32 path, the cheaper Gram-matrix form
         # (|a|^2 + |b|^2 - 2 a.b, ~1e-3 A^2 absolute error) on the bf16 path
@@ -1769,8 +1769,16 @@ class DiffAb(nn.Module):
                 ctx_mask = residue_mask & (~generation_mask)
                 res_ctx = self.residue_context_embedding(seq_idx, xyz, orientations, backbone_dihedrals, chain_idx,
                                                          atom_mask, ctx_mask, ctx_mask)
-                pair_ctx = self.pair_context_embedding.forward_fused_bf16(seq_idx, xyz, pairwise_dihedrals, residue_idx,
-                                                                          chain_idx, atom_mask, ctx_mask)
+                if L < Lp:    # ragged length: the fused kernel works on 128 / 256 residues - pad with absent residues, cut back
+                    n = Lp - L
+                    pad1 = lambda v: F.pad(v, (0, n))
+                    pair_ctx = self.pair_context_embedding.forward_fused_bf16(
+                        pad1(seq_idx), F.pad(xyz, (0, 0, 0, 0, 0, n)), F.pad(pairwise_dihedrals, (0, 0, 0, n, 0, n)),
+                        pad1(residue_idx), pad1(chain_idx), F.pad(atom_mask, (0, 0, 0, n)), pad1(ctx_mask))
+                    pair_ctx = pair_ctx[:, :L, :L].contiguous()
+                else:
+                    pair_ctx = self.pair_context_embedding.forward_fused_bf16(seq_idx, xyz, pairwise_dihedrals, residue_idx,
+                                                                              chain_idx, atom_mask, ctx_mask)
             else:
                 for lo in range(0, B, context_chunk):
                     sl = slice(lo, min(B, lo + context_chunk))

@@ -256,7 +256,7 @@ int dab_front_fwd_sm100(const float* c, const float* t1, const int64_t* seq, int
 
 /* ------------------------------------------------------------------ pair context encoder
  * PairEmbedding.forward (diffab_pytorch.py:186-312) fused into one tcgen05 kernel that writes the pair tensor in bf16
- * (inference / sampling; L = 128 residues, 15 atoms, d_pair_emb = 64, max_dist_to_consider = 32).  Distances are
+ * (inference / sampling; L = 128 or 256 residues, 15 atoms, d_pair_emb = 64, max_dist_to_consider = 32).  Distances are
  * computed from xyz inside the kernel.  Weights: the module's state-dict tensors, nn.Linear layout (out, in). */
 typedef struct DabPairEmbedWeights {
   const float* type_emb;      /* aa_pair_type_embedding.weight (441, 64) */

@@ -370,18 +370,20 @@ def test_regrouped_sampling_glue_matches_module_path():
     assert (outs[0][1] - outs[1][1]).norm(dim=-1)[m].max() < 1e-2
 
 
-def test_fused_pair_embedding_matches_module():
+@pytest.mark.parametrize("L", [128, 256])
+def test_fused_pair_embedding_matches_module(L):
     """csrc/pair_embed_sm100.cu (PairEmbedding.forward in one tcgen05 kernel, bf16 out, distances from xyz) against the
-    PyTorch module on exact distances: bf16 operands -> 3e-2 max-normalised; masked residues give exact zeros."""
+    PyTorch module on exact distances: bf16 operands -> 3e-2 max-normalised; masked residues give exact zeros.  L = 256:
+    two key blocks per query row."""
     model = _model(0)
-    batch = synth.make_patches(3, 128, seed=21)
+    batch = synth.make_patches(3, L, seed=21)
     batch["atom_mask"][1, 5] = False           # a residue without atoms and one without CA
     batch["atom_mask"][2, 17, 1] = False
     batch["atom_mask"][0, 40, 7:] = False
     b = _to(batch)
     ctx = b["residue_mask"] & ~b["generation_mask"]
     pe = model.pair_context_embedding
-    assert pe.fused_supported(128, 15)
+    assert pe.fused_supported(L, 15)
     with torch.no_grad():
         ref = pe(b["seq_idx"], b["distmat"], b["pairwise_dihedrals"], b["residue_idx"], b["chain_idx"], b["atom_mask"],
                  ctx, ctx)
