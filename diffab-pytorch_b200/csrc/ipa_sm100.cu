@@ -1015,8 +1015,11 @@ int dab_ipa_pair_bias_multi(const DabIpaDims* d, const void* e_bf16, const float
 
 // Projection launch of a layer (weights `pk`), packed operands into `ws`.  With `pk_prev` the kernel first computes the
 // PREVIOUS layer's to_out, y = cat Wout^T + b (cat = ws.cat, weights pk_prev), straight into its A tile: x is not read.
+// the epsilon network's front MLP as the input of layer 0 (mode 2 of the projection kernel): y = relu(c[row] + t1[seq[row]]) W2^T + b2
+struct FrontIn { const float* c; const float* t1; const int64_t* seq; const void* w2_bf16; const float* b2; };
 static int launch_proj(int B, const uint8_t* pk, const float* x, const __nv_bfloat16* x16, const float* R, const float* t,
-                       const Ws& ws, const uint8_t* pk_prev, cudaStream_t s, const float* cen_ext = nullptr) {
+                       const Ws& ws, const uint8_t* pk_prev, cudaStream_t s, const float* cen_ext = nullptr,
+                       const FrontIn* front = nullptr) {
   const PackedOffsets po = packed_offsets();
   const int M = B * L;
   CUtensorMap mw64, mw48;
@@ -1044,10 +1047,18 @@ static int launch_proj(int B, const uint8_t* pk, const float* x, const __nv_bflo
     if (int rc = make_tensor_map_bf16(&mwout, pk_prev + po.wout, 2, dwo, sc, bc, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     b_out = reinterpret_cast<const float*>(pk_prev + po.bout);
     n_split = 1;                             // the to_out phase produces the whole A tile of the patch
+  } else if (front) {
+    uint64_t dw2[2] = {(uint64_t)D, (uint64_t)D}, sw2[1] = {(uint64_t)D * 2};
+    uint32_t bw2[2] = {64, 128};
+    if (int rc = make_tensor_map_bf16(&mwout, front->w2_bf16, 2, dw2, sw2, bw2, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    b_out = front->b2;
+    n_split = 1;
   }
   ipa_proj_kernel<<<dim3(n_split, B), 288, ProjSmem::kTotal, s>>>(
       mw64, mw48, msq, msk, msv, x, R, t, reinterpret_cast<const float*>(pk + po.gamma), ws.Qp, ws.Kp, ws.Vp, ws.tc,
-      g_core_dbg ? g_core_dbg + (1 << 20) : nullptr, x16, mcat, mwout, b_out, pk_prev ? 1 : 0, cen_ext);
+      g_core_dbg ? g_core_dbg + (1 << 20) : nullptr, x16, mcat, mwout, b_out, pk_prev ? 1 : (front ? 2 : 0), cen_ext,
+      front ? reinterpret_cast<const float4*>(front->c) : nullptr, front ? reinterpret_cast<const float4*>(front->t1) : nullptr,
+      front ? front->seq : nullptr);
   count_launch();
   return DAB_OK;
 }
@@ -1211,6 +1222,35 @@ int dab_ipa_mid_sm100(const DabIpaDims* d, const void* packed_prev, const void* 
                            reinterpret_cast<const uint8_t*>(packed_prev), (cudaStream_t)stream, two ? w2.cen : nullptr))
     return rc;
   return check_launch("dab_ipa_mid_sm100");
+}
+
+/* The projections of the FIRST layer of the epsilon network's stack with the front MLP (Denoiser.to_res_emb during sampling,
+ * diffab_pytorch.py:572-574) fused in: the layer input y = relu(c[row] + t1[seq[row]]) W2^T + b2 (first layer regrouped into
+ * the per-run constant c[B*L,128] and the 25-row table t1[25,128], as dab_front_fwd_sm100 computes it; w2_bf16 [128][128],
+ * b2 [128]) is formed in the projection kernel's operand tile and never exists in HBM.  Replaces dab_front_fwd_sm100 +
+ * stages(1); the same bits. */
+int dab_ipa_front_proj_sm100(const DabIpaDims* d, const void* packed, const float* c, const float* t1, const int64_t* seq,
+                             const void* w2_bf16, const float* b2, const float* R, const float* t, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  DAB_REQUIRE(shape_ok_fwd(d), DAB_EUNSUPPORTED, "dab_ipa_front_proj_sm100: the sm_100a fast path needs the train.py configuration");
+  if (d->B == 0) return DAB_OK;
+  DAB_REQUIRE(packed && c && t1 && seq && w2_bf16 && b2 && R && t && workspace, DAB_EINVAL, "dab_ipa_front_proj_sm100: null pointer");
+  DAB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0 && (reinterpret_cast<uintptr_t>(packed) & 1023) == 0 &&
+                  aligned16(c) && aligned16(t1) && aligned16(w2_bf16),
+              DAB_EINVAL, "dab_ipa_front_proj_sm100: misaligned pointer (workspace / packed 1024 B, c / t1 / w2 16 B)");
+  const bool two = d->L == 2 * L;
+  const int nblk = two ? 2 * d->B : d->B;
+  Ws ws = carve_ws(nblk, workspace);
+  Ws2 w2s = {};
+  size_t need = ws.bytes;
+  if (two) { w2s = carve_ws2(d->B, workspace); need = w2s.bytes; }
+  DAB_REQUIRE(workspace_bytes >= need, DAB_EWORKSPACE, "dab_ipa_front_proj_sm100: workspace %zu < %zu", workspace_bytes, need);
+  if (two) { centroid256_kernel<<<d->B, 256, 0, (cudaStream_t)stream>>>(t, w2s.cen); count_launch(); }
+  const FrontIn fr = {c, t1, seq, w2_bf16, b2};
+  if (int rc = launch_proj(nblk, reinterpret_cast<const uint8_t*>(packed), nullptr, nullptr, R, t, ws, nullptr,
+                           (cudaStream_t)stream, two ? w2s.cen : nullptr, &fr))
+    return rc;
+  return check_launch("dab_ipa_front_proj_sm100");
 }
 
 /* C[M,N] = A[M,K] B[N,K]^T + bias on the tcgen05 GEMM (bf16 operands, fp32 result; M % 128 == 0, N % 64 == 0, K % 64 == 0):

@@ -1042,7 +1042,7 @@ class InvariantPointAttentionModule(nn.Module):
                 self.layers[0].fast_path_supported(pair_emb.shape[1], True)):
             # inference on the tensor-core path: the residue stream travels between the layers as bf16
             n = len(self.layers)
-            if res_emb.shape[0] * (L // FAST_L) >= 128:
+            if self.fused_stack_applicable(res_emb.shape[0], L, pair_emb, pair_bias):
                 # large batches (one projection CTA per patch): each layer's to_out is fused into the next layer's
                 # projection kernel, the stream between the layers never exists in HBM (bit-identical)
                 return self._forward_fused_stack(res_emb, pair_emb, orientations, translations, pair_bias)
@@ -1061,16 +1061,23 @@ class InvariantPointAttentionModule(nn.Module):
                 res_emb = layer(res_emb, pairs[k], orientations, translations)
         return res_emb
 
+    def fused_stack_applicable(self, B, L, pair_emb, pair_bias):
+        """Inference on the tensor-core path with enough 128-residue blocks for one projection CTA per block."""
+        return (pair_bias is not None and pair_emb.dtype == torch.bfloat16 and len(self.layers) > 1 and
+                self.layers[0].fast_path_supported(L, True) and B * (L // FAST_L) >= 128)
+
     @torch.no_grad()
-    def _forward_fused_stack(self, res_emb, pair_emb, orientations, translations, pair_bias):
+    def _forward_fused_stack(self, res_emb, pair_emb, orientations, translations, pair_bias, front=None):
         """The layer stack launch by launch on ONE shared workspace: projections of layer 0, then per layer the attention
         core followed by ``dab_ipa_mid_sm100`` (its to_out + the next layer's projections in one kernel), to_out of the
-        last layer.  2 n launches instead of 3 n; results bit-identical to ``forward_fast_io`` layer by layer."""
+        last layer.  2 n launches instead of 3 n; results bit-identical to ``forward_fast_io`` layer by layer.
+        ``front`` = (sampling cache of the Denoiser, seq_idx_t) instead of ``res_emb``: the epsilon network's front MLP
+        runs inside the first projection kernel (``dab_ipa_front_proj_sm100``)."""
         layers = self.layers
         n = len(layers)
-        B, L, D = res_emb.shape
-        x = _lib.dev(res_emb, res_emb.dtype if res_emb.dtype == torch.bfloat16 else torch.float32, "x")
         e = _lib.dev(pair_emb, torch.bfloat16, "e")
+        B, L = e.shape[0], e.shape[1]
+        D = layers[0].d_residue_emb
         r = _lib.dev(orientations, torch.float32, "r")
         t = _lib.dev(translations, torch.float32, "t")
         bias = [_lib.dev(p_, torch.float16, "pair_bias") for p_ in pair_bias]
@@ -1078,16 +1085,26 @@ class InvariantPointAttentionModule(nn.Module):
         lib = _lib.lib()
         st = _lib.stream_ptr()
         packed = [layer._packed_weights(dims) for layer in layers]
-        ws = layers[0]._workspace(max(lib.dab_ipa_sm100_workspace_bytes(ctypes.byref(dims)), 16), x.device)
-        y = torch.empty(B, L, D, device=x.device, dtype=torch.float32)
-        x32, x16 = (None, x) if x.dtype == torch.bfloat16 else (x, None)
+        ws = layers[0]._workspace(max(lib.dab_ipa_sm100_workspace_bytes(ctypes.byref(dims)), 16), e.device)
+        y = torch.empty(B, L, D, device=e.device, dtype=torch.float32)
+        x32 = x16 = None
+        if front is None:
+            x = _lib.dev(res_emb, res_emb.dtype if res_emb.dtype == torch.bfloat16 else torch.float32, "x")
+            x32, x16 = (None, x) if x.dtype == torch.bfloat16 else (x, None)
 
         def stage(k, stages):     # (x is read by stage 1 only, y written by stage 4 only)
             _lib.check(lib.dab_ipa_fwd_sm100_stages(
                 ctypes.byref(dims), ptr(packed[k]), ptr(x32), ptr(x16), ptr(e), ptr(bias[k]), ptr(r), ptr(t), ptr(y), None,
                 ptr(ws), ws.numel(), stages, st), "dab_ipa_fwd_sm100_stages")
 
-        stage(0, 1)
+        if front is None:
+            stage(0, 1)
+        else:
+            cache, seq = front
+            _lib.check(lib.dab_ipa_front_proj_sm100(
+                ctypes.byref(dims), ptr(packed[0]), ptr(cache["c"]), ptr(cache["t1"]), ptr(_lib.dev(seq, torch.int64, "seq_idx")),
+                ptr(cache["w2_bf16"]), ptr(cache["b2"]), ptr(r), ptr(t), ptr(ws), ws.numel(), st), "dab_ipa_front_proj_sm100")
+            x16 = ws                # (stages 2 / 4 do not read x: any non-null pointer satisfies the argument check)
         for k in range(n):
             stage(k, 2)
             if k + 1 < n:
@@ -1228,6 +1245,12 @@ class Denoiser(nn.Module):
         """``heads`` with the per-run constants of ``sampling_cache``; returns (eps, rotvec, seq_posterior)."""
         B, L = seq_idx_t.shape
         D = cache["c"].shape[-1]
+        if (cache.get("w2_bf16") is not None and cache["c"].dtype == torch.float32 and cache["c"].is_contiguous() and
+                self.ipa.fused_stack_applicable(B, L, pair_context_emb, pair_bias)):
+            # large batches: the front MLP runs inside the first layer's projection kernel (same bits as the branch below)
+            h = self.ipa._forward_fused_stack(None, pair_context_emb, orientations_t, translations_t, pair_bias,
+                                              front=(cache, seq_idx_t.contiguous()))
+            return self._heads_from(h, cache, pair_context_emb, beta)
         if cache.get("w2_bf16") is not None and pair_context_emb.dtype == torch.bfloat16 and (B * L) % 128 == 0:
             # bf16 out when the layer stack takes it (its first projection kernel rounds an fp32 input the same way)
             h16 = pair_bias is not None and len(self.ipa.layers) > 1 and self.ipa.layers[0].fast_path_supported(L, True)
@@ -1241,6 +1264,11 @@ class Denoiser(nn.Module):
             h = torch.relu_(cache["c"] + F.embedding(seq_idx_t, cache["t1"]))
             h = torch.addmm(cache["b2"], h.view(-1, D), cache["w2t"]).view(B, L, D)
         h = self.ipa(h, pair_context_emb, orientations_t, translations_t, pair_bias)
+        return self._heads_from(h, cache, pair_context_emb, beta)
+
+    def _heads_from(self, h, cache, pair_context_emb, beta):
+        """The three heads on the stack's output (sampling)."""
+        B, L, D = h.shape
         if cache.get("heads_packed") is not None and pair_context_emb.dtype == torch.bfloat16:
             eps = torch.empty(B, L, 3, device=h.device)
             rot = torch.empty(B, L, 3, device=h.device)

@@ -196,6 +196,13 @@ int dab_ipa_fwd_sm100_stages(const DabIpaDims* d, const void* packed, const floa
  * (InvariantPointAttentionModule.forward, diffab_pytorch.py:494-498). */
 int dab_ipa_mid_sm100(const DabIpaDims* d, const void* packed_prev, const void* packed, const float* R, const float* t,
                       void* workspace, size_t workspace_bytes, void* stream);
+/* Projections of the FIRST layer of the stack with the epsilon network's front MLP (Denoiser.to_res_emb during sampling,
+ * diffab_pytorch.py:572-574) fused in: the layer input relu(c[row] + t1[seq[row]]) W2^T + b2 - c[B*L,128] / t1[25,128] the
+ * regrouped first layer as in dab_front_fwd_sm100, w2_bf16 [128][128], b2 [128] - is formed in the projection kernel's operand
+ * tile and never exists in HBM.  Replaces dab_front_fwd_sm100 followed by dab_ipa_fwd_sm100_stages(.., 1); the same bits. */
+int dab_ipa_front_proj_sm100(const DabIpaDims* d, const void* packed, const float* c, const float* t1, const int64_t* seq,
+                             const void* w2_bf16, const float* b2, const float* R, const float* t, void* workspace,
+                             size_t workspace_bytes, void* stream);
 /* Training pair of the sm_100a path (bf16 pair tensor, fp32 x / y).  The forward is dab_ipa_fwd_sm100 (the pair
  * bias is rebuilt inside the call when bias_f16 is NULL); `saved` (dab_ipa_sm100_workspace_bytes) additionally keeps
  * the packed operands, the concat features, the un-normalised probabilities and the softmax statistics, and must

@@ -580,3 +580,30 @@ def test_other_patch_lengths_sample_on_the_tensor_core_path(L):
                        batch["generation_mask"], batch["residue_mask"], t_start=100, t_stop=97)
     assert out["seq_idx"].shape == (2, L) and torch.isfinite(out["translations"]).all()
     assert torch.equal(out["translations"].cpu()[~m], batch["xyz"][:, :, 1][~m])
+
+
+def test_front_mlp_fused_into_the_first_projection_kernel_changes_no_bit():
+    """dab_ipa_front_proj_sm100 (batches of >= 128 blocks: the epsilon network's front MLP inside the first layer's
+    projection kernel) against front kernel + GEMM + layer-by-layer stack: identical head outputs."""
+    from diffab_pytorch_b200.diffab_pytorch import cast_pair_to_bf16
+    model = _model(0)
+    B = 128
+    g = torch.Generator(device=DEV).manual_seed(3)
+    res = torch.randn(B, 128, 128, device=DEV, generator=g)
+    pair = torch.randn(B, 128, 128, 64, device=DEV, generator=g).bfloat16()
+    batch = _to(synth.make_patches(B, 128, seed=4, with_distmat=False))
+    s, x, O = batch["seq_idx"], batch["xyz"][:, :, 1].contiguous(), batch["orientations"]
+    with torch.no_grad():
+        planes = model._pair_bias_planes(pair)
+        cache = model.denoiser.sampling_cache(res)
+        beta = model.dsched.tensors["beta"][torch.full((B,), 42, device=DEV)]
+        ipa = model.denoiser.ipa
+        assert ipa.fused_stack_applicable(B, 128, pair, planes)
+        fused = model.denoiser.heads_fast(s, x, O, cache, pair, beta, planes)
+        try:
+            ipa.fused_stack_applicable = lambda *a, **k: False
+            plain = model.denoiser.heads_fast(s, x, O, cache, pair, beta, planes)
+        finally:
+            del ipa.fused_stack_applicable
+    for a, b in zip(fused, plain):
+        assert torch.isfinite(a).all() and torch.equal(a, b)
