@@ -46,7 +46,10 @@ struct HeadsSmem {
   static constexpr int kTotal = kTmemSlot + 16;
 };
 enum HBar { HW_FULL = 0 /* 2 */, HW_EMPTY = 2 /* 2 */, HW3_FULL = 4, HL1_DONE = 5, HA1_READY = 6 /* 256 arrivals */,
-            HL2_DONE = 7, HA2_READY = 8 /* 256 arrivals */, HL3_DONE = 9, H_N_BARS = 10 };
+            HL2_DONE = 7, HA2_READY = 8 /* 256 arrivals */, HL3_DONE = 9,
+            // fused to_out of the last IPA layer (y = cat Wout^T + b straight into the A tile): ring of three 32 KB stages
+            // [128 rows of cat | 128 rows of Wout] x 64 K columns in kA2 and the (still idle) weight ring
+            HG_FULL = 10 /* 3 */, HG_EMPTY = 13 /* 3 */, HG_DONE = 16, HX_READY = 17 /* 256 arrivals */, H_N_BARS = 18 };
 
 __device__ __forceinline__ uint32_t hpk(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
@@ -91,7 +94,9 @@ __global__ void pack_heads_kernel(DabHeadWeights w, uint8_t* packed) {
 __global__ void __launch_bounds__(288, 1)
 denoiser_heads_kernel(const __grid_constant__ CUtensorMap map_w128, const __grid_constant__ CUtensorMap map_w32,
                       const float* __restrict__ x, const float* __restrict__ beta, const uint8_t* __restrict__ packed,
-                      float* __restrict__ eps, float* __restrict__ rotvec, float* __restrict__ post) {
+                      float* __restrict__ eps, float* __restrict__ rotvec, float* __restrict__ post,
+                      const __grid_constant__ CUtensorMap map_cat, const __grid_constant__ CUtensorMap map_wout,
+                      const float* __restrict__ b_out, int fuse_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using S = HeadsSmem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
@@ -105,21 +110,23 @@ denoiser_heads_kernel(const __grid_constant__ CUtensorMap map_w128, const __grid
   const float* b3 = reinterpret_cast<const float*>(packed + HeadsPacked::kB3);
 
   if (tid == 0) {
-    for (int i = 0; i < H_N_BARS; ++i) mbar_init(&bars[i], (i == HA1_READY || i == HA2_READY) ? 256u : 1u);
+    for (int i = 0; i < H_N_BARS; ++i) mbar_init(&bars[i], (i == HA1_READY || i == HA2_READY || i == HX_READY) ? 256u : 1u);
     fence_barrier_init();
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   if (warp < 8) {
     // x tile: fp32 global (coalesced float4) -> bf16, K-major 128B-swizzled A operand (16 rows per warp)
-    const float* xb = x + (int64_t)b * 128 * HD;
-    const uint32_t kb = lane >> 4, chunk = (lane & 15) >> 1, half = (lane & 1) * 8;
+    if (!fuse_out) {
+      const float* xb = x + (int64_t)b * 128 * HD;
+      const uint32_t kb = lane >> 4, chunk = (lane & 15) >> 1, half = (lane & 1) * 8;
 #pragma unroll
-    for (int rr = 0; rr < 16; ++rr) {   // all 16 loads of the warp in flight before the first conversion
-      const int r = warp * 16 + rr;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(xb + r * HD) + lane);
-      *reinterpret_cast<uint2*>(smem + S::kA + kb * 16384 + swz128_offset(r, chunk) + half) =
-          make_uint2(hpk(v.x, v.y), hpk(v.z, v.w));
+      for (int rr = 0; rr < 16; ++rr) {   // all 16 loads of the warp in flight before the first conversion
+        const int r = warp * 16 + rr;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(xb + r * HD) + lane);
+        *reinterpret_cast<uint2*>(smem + S::kA + kb * 16384 + swz128_offset(r, chunk) + half) =
+            make_uint2(hpk(v.x, v.y), hpk(v.z, v.w));
+      }
     }
     // per-patch bias of the first layers: the three time columns of [x | beta, sin beta, cos beta]
     const float* wt1 = reinterpret_cast<const float*>(packed + HeadsPacked::kWt1);
@@ -138,6 +145,38 @@ denoiser_heads_kernel(const __grid_constant__ CUtensorMap map_w128, const __grid
     if (lane == 0) {
       tma_prefetch_desc(&map_w128);
       tma_prefetch_desc(&map_w32);
+      if (fuse_out) {
+        // ---- to_out of the last IPA layer: acc[128 residues x 128] = cat[128 x 1024] Wout^T, 16 K chunks of 64
+        tma_prefetch_desc(&map_cat); tma_prefetch_desc(&map_wout);
+        constexpr uint32_t idesc_g = make_idesc_bf16(128, 128, 0, 0);
+        const int g_off[3] = {S::kA2, S::kW, S::kW + 32768};
+        auto load_g = [&](int kc) {
+          const int st = kc % 3;
+          mbar_arrive_expect_tx(&bars[HG_FULL + st], 32768);
+          tma_load_2d(smem + g_off[st], &map_cat, &bars[HG_FULL + st], kc * 64, b * 128);
+          tma_load_2d(smem + g_off[st] + 16384, &map_wout, &bars[HG_FULL + st], kc * 64, 0);
+        };
+        for (int kc = 0; kc < 3; ++kc) load_g(kc);
+        constexpr int kChunks = 1024 / 64;
+        for (int kc = 0; kc < kChunks; ++kc) {
+          const int st = kc % 3;
+          mbar_wait(&bars[HG_FULL + st], (kc / 3) & 1);
+          tcgen05_fence_after_sync();
+          const uint64_t da = make_smem_desc(smem_base + g_off[st], 16, 1024, kSwizzle128B);
+          const uint64_t db = make_smem_desc(smem_base + g_off[st] + 16384, 16, 1024, kSwizzle128B);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem, da + (uint32_t)((kk * 32) >> 4), db + (uint32_t)((kk * 32) >> 4), idesc_g, (kc | kk) != 0);
+          umma_commit(&bars[HG_EMPTY + st]);
+          if (kc == kChunks - 1) umma_commit(&bars[HG_DONE]);
+          if (kc + 3 < kChunks) {
+            mbar_wait(&bars[HG_EMPTY + st], (kc / 3) & 1);
+            load_g(kc + 3);
+          }
+        }
+        // the heads' weight ring shares the to_out ring's memory: every to_out MMA must have completed
+        mbar_wait(&bars[HG_DONE], 0);
+      }
       // weight tiles through the ring of two: t = 0..2 first layers, 3..5 second layers (rows 128 t of the blob)
       auto load_w = [&](int tt) {
         const int s = tt & 1;
@@ -163,6 +202,10 @@ denoiser_heads_kernel(const __grid_constant__ CUtensorMap map_w128, const __grid
           umma_bf16(tmem + dcol, da, db, idesc, k != 0);
         }
       };
+      if (fuse_out) {                // the epilogue warps have written y (bf16) into the A tile and left the accumulator
+        mbar_wait(&bars[HX_READY], 0);
+        tcgen05_fence_after_sync();
+      }
       // ---- layer 1 of the three heads
       for (int tt = 0; tt < 3; ++tt) {
         const int s = tt & 1;
@@ -220,6 +263,28 @@ denoiser_heads_kernel(const __grid_constant__ CUtensorMap map_w128, const __grid
         }
       }
     };
+    if (fuse_out) {
+      // y = acc + b_out of the last IPA layer, rounded to bf16 exactly as the heads would round its fp32 output, goes
+      // straight into the A tile: this thread converts its row of K block `chalf`
+      mbar_wait(&bars[HG_DONE], 0);
+      tcgen05_fence_after_sync();
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        float v[32];
+        tmem_ld_x32(tmem_lane + chalf * 64 + part * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float* b8 = b_out + chalf * 64 + part * 32 + q * 8;
+          *reinterpret_cast<uint4*>(smem + S::kA + chalf * 16384 + swz128_offset(row, part * 4 + q)) =
+              make_uint4(hpk(v[q * 8] + __ldg(b8), v[q * 8 + 1] + __ldg(b8 + 1)), hpk(v[q * 8 + 2] + __ldg(b8 + 2), v[q * 8 + 3] + __ldg(b8 + 3)),
+                         hpk(v[q * 8 + 4] + __ldg(b8 + 4), v[q * 8 + 5] + __ldg(b8 + 5)), hpk(v[q * 8 + 6] + __ldg(b8 + 6), v[q * 8 + 7] + __ldg(b8 + 7)));
+        }
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before_sync();
+      mbar_arrive(&bars[HX_READY]);
+    }
     mbar_wait(&bars[HL1_DONE], 0);
     tcgen05_fence_after_sync();
     for (int k = 0; k < 3; ++k) {
@@ -314,9 +379,39 @@ int dab_heads_fwd_sm100(const void* packed, const float* x, const float* beta, i
   if (int rc = make_tensor_map_bf16(&m128, pk + HeadsPacked::kW, 2, dims, strides, b128, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   if (int rc = make_tensor_map_bf16(&m32, pk + HeadsPacked::kW, 2, dims, strides, b32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   DAB_ENSURE_SMEM(denoiser_heads_kernel, HeadsSmem::kTotal);
-  denoiser_heads_kernel<<<n_patches, 288, HeadsSmem::kTotal, (cudaStream_t)stream>>>(m128, m32, x, beta, pk, eps, rotvec, post);
+  denoiser_heads_kernel<<<n_patches, 288, HeadsSmem::kTotal, (cudaStream_t)stream>>>(m128, m32, x, beta, pk, eps, rotvec, post,
+                                                                                      m128, m128, nullptr, 0);
   count_launch();
   return check_launch("dab_heads_fwd_sm100");
+}
+
+/* The same heads with the LAST IPA layer's to_out (diffab_pytorch.py:464: y = cat Wout^T + b) fused in front: cat_bf16
+ * [n_patches*128, 1024] = the concat features the layer's attention core left in its workspace, wout_bf16 [128][1024] and
+ * b_out [128] from the layer's packed weights (dab_ipa_packed_layout).  The stack's output never exists in HBM; the same bits
+ * as dab_ipa_fwd_sm100_stages(.., 4) followed by dab_heads_fwd_sm100. */
+int dab_out_heads_fwd_sm100(const void* packed, const void* cat_bf16, const void* wout_bf16, const float* b_out, const float* beta,
+                            int n_patches, int L_, float* eps, float* rotvec, float* post, void* stream) {
+  DAB_REQUIRE(L_ == 128, DAB_EUNSUPPORTED, "dab_out_heads_fwd_sm100: the fused heads kernel needs L = 128 (one block per CTA)");
+  DAB_REQUIRE(n_patches >= 0, DAB_EINVAL, "dab_out_heads_fwd_sm100: negative batch");
+  if (n_patches == 0) return DAB_OK;
+  DAB_REQUIRE(packed && cat_bf16 && wout_bf16 && b_out && beta && eps && rotvec && post, DAB_EINVAL,
+              "dab_out_heads_fwd_sm100: null pointer");
+  DAB_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 1023) == 0 && aligned16(cat_bf16) && aligned16(wout_bf16), DAB_EINVAL,
+              "dab_out_heads_fwd_sm100: misaligned pointer (packed 1024 B, cat / Wout 16 B)");
+  CUtensorMap m128, m32, mcat, mwout;
+  uint64_t dims[2] = {(uint64_t)HD, 864}, strides[1] = {(uint64_t)HD * 2};
+  uint32_t b128[2] = {64, 128}, b32[2] = {64, HN3};
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
+  if (int rc = make_tensor_map_bf16(&m128, pk + HeadsPacked::kW, 2, dims, strides, b128, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  if (int rc = make_tensor_map_bf16(&m32, pk + HeadsPacked::kW, 2, dims, strides, b32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  uint64_t dc[2] = {1024, (uint64_t)n_patches * 128}, dwo[2] = {1024, (uint64_t)HD}, sc[1] = {1024 * 2};
+  if (int rc = make_tensor_map_bf16(&mcat, cat_bf16, 2, dc, sc, b128, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  if (int rc = make_tensor_map_bf16(&mwout, wout_bf16, 2, dwo, sc, b128, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  DAB_ENSURE_SMEM(denoiser_heads_kernel, HeadsSmem::kTotal);
+  denoiser_heads_kernel<<<n_patches, 288, HeadsSmem::kTotal, (cudaStream_t)stream>>>(m128, m32, nullptr, beta, pk, eps, rotvec, post,
+                                                                                      mcat, mwout, b_out, 1);
+  count_launch();
+  return check_launch("dab_out_heads_fwd_sm100");
 }
 
 /* x0[n_rows,128] = relu(c[row] + t1[seq[row]]) . w2^T + b2  (to_res_emb during sampling; n_rows % 128 == 0).

@@ -1067,12 +1067,14 @@ class InvariantPointAttentionModule(nn.Module):
                 self.layers[0].fast_path_supported(L, True) and B * (L // FAST_L) >= 128)
 
     @torch.no_grad()
-    def _forward_fused_stack(self, res_emb, pair_emb, orientations, translations, pair_bias, front=None):
+    def _forward_fused_stack(self, res_emb, pair_emb, orientations, translations, pair_bias, front=None, heads=None):
         """The layer stack launch by launch on ONE shared workspace: projections of layer 0, then per layer the attention
         core followed by ``dab_ipa_mid_sm100`` (its to_out + the next layer's projections in one kernel), to_out of the
         last layer.  2 n launches instead of 3 n; results bit-identical to ``forward_fast_io`` layer by layer.
         ``front`` = (sampling cache of the Denoiser, seq_idx_t) instead of ``res_emb``: the epsilon network's front MLP
-        runs inside the first projection kernel (``dab_ipa_front_proj_sm100``)."""
+        runs inside the first projection kernel (``dab_ipa_front_proj_sm100``).  ``heads`` = (packed head weights, beta per
+        block): the last layer's to_out runs inside the heads kernel (``dab_out_heads_fwd_sm100``) and the call returns
+        (eps, rotvec, posterior) instead of the stack's output."""
         layers = self.layers
         n = len(layers)
         e = _lib.dev(pair_emb, torch.bfloat16, "e")
@@ -1110,9 +1112,25 @@ class InvariantPointAttentionModule(nn.Module):
             if k + 1 < n:
                 _lib.check(lib.dab_ipa_mid_sm100(ctypes.byref(dims), ptr(packed[k]), ptr(packed[k + 1]), ptr(r), ptr(t), ptr(ws),
                                                  ws.numel(), st), "dab_ipa_mid_sm100")
-            else:
+            elif heads is None:
                 stage(k, 4)
-        return y
+        if heads is None:
+            return y
+        heads_packed, beta_blk = heads
+        nblk = B * (L // FAST_L)
+        bdims = _ipa_structs(layers[0], nblk, FAST_L)          # the workspace sections are laid out per 128-residue block
+        offs = (ctypes.c_size_t * 8)()
+        _lib.check(lib.dab_ipa_sm100_workspace_layout(ctypes.byref(bdims), offs), "dab_ipa_sm100_workspace_layout")
+        poffs = (ctypes.c_size_t * 7)()
+        _lib.check(lib.dab_ipa_packed_layout(ctypes.byref(dims), poffs), "dab_ipa_packed_layout")
+        eps = torch.empty(B, L, 3, device=e.device)
+        rot = torch.empty(B, L, 3, device=e.device)
+        post = torch.empty(B, L, 21, device=e.device)
+        pk_last = packed[n - 1]
+        _lib.check(lib.dab_out_heads_fwd_sm100(ptr(heads_packed), ws.data_ptr() + offs[4], pk_last.data_ptr() + poffs[1],
+                                               pk_last.data_ptr() + poffs[3], ptr(beta_blk), nblk, FAST_L, ptr(eps), ptr(rot),
+                                               ptr(post), st), "dab_out_heads_fwd_sm100")
+        return eps, rot, post
 
     def precompute_pair_bias(self, pair_emb_bf16, out=None):
         """Per-layer pair-bias planes for the sm_100a path: one pass over the pair tensor for all layers
@@ -1193,6 +1211,8 @@ class Denoiser(nn.Module):
                 o.record_stream(main)
         return tuple(outs)
 
+    fuse_out_into_heads = True     # False: to_out of the last layer as its own GEMM in front of the heads kernel (timing A/B)
+
     # ---- sampling fast path of the dense glue (same arithmetic, regrouped; inference only) ----
     @torch.no_grad()
     def sampling_cache(self, res_context_emb, cache=None):
@@ -1248,8 +1268,14 @@ class Denoiser(nn.Module):
         if (cache.get("w2_bf16") is not None and cache["c"].dtype == torch.float32 and cache["c"].is_contiguous() and
                 self.ipa.fused_stack_applicable(B, L, pair_context_emb, pair_bias)):
             # large batches: the front MLP runs inside the first layer's projection kernel (same bits as the branch below)
-            h = self.ipa._forward_fused_stack(None, pair_context_emb, orientations_t, translations_t, pair_bias,
-                                              front=(cache, seq_idx_t.contiguous()))
+            front = (cache, seq_idx_t.contiguous())
+            if cache.get("heads_packed") is not None and self.fuse_out_into_heads:
+                # ... and the last layer's to_out inside the heads kernel: the stack's output never exists in HBM either
+                nb = L // FAST_L
+                beta_blk = beta.contiguous() if nb == 1 else beta.repeat_interleave(nb)
+                return self.ipa._forward_fused_stack(None, pair_context_emb, orientations_t, translations_t, pair_bias,
+                                                     front=front, heads=(cache["heads_packed"], beta_blk))
+            h = self.ipa._forward_fused_stack(None, pair_context_emb, orientations_t, translations_t, pair_bias, front=front)
             return self._heads_from(h, cache, pair_context_emb, beta)
         if cache.get("w2_bf16") is not None and pair_context_emb.dtype == torch.bfloat16 and (B * L) % 128 == 0:
             # bf16 out when the layer stack takes it (its first projection kernel rounds an fp32 input the same way)

@@ -252,6 +252,12 @@ int dab_heads_pack_weights(const DabHeadWeights* w, void* packed, void* stream);
 /* x[n_patches*L,128] fp32, beta[n_patches] fp32 -> eps[.,3], rotvec[.,3], seq_posterior[.,21] fp32. */
 int dab_heads_fwd_sm100(const void* packed, const float* x, const float* beta, int n_patches, int L, float* eps,
                         float* rotvec, float* seq_posterior, void* stream);
+/* The same heads with the LAST IPA layer's to_out (diffab_pytorch.py:464: y = cat Wout^T + b) fused in front: cat_bf16
+ * [n_patches*128, 1024] = the concat features the layer's attention core left in its workspace (dab_ipa_sm100_workspace_layout),
+ * wout_bf16 [128][1024] and b_out [128] from the layer's packed weights (dab_ipa_packed_layout).  The stack's output never
+ * exists in HBM; the same bits as dab_ipa_fwd_sm100_stages(.., 4) followed by dab_heads_fwd_sm100. */
+int dab_out_heads_fwd_sm100(const void* packed, const void* cat_bf16, const void* wout_bf16, const float* b_out, const float* beta,
+                            int n_patches, int L, float* eps, float* rotvec, float* post, void* stream);
 
 /* Front of the epsilon network during sampling (diffab_pytorch.py:572-574, to_res_emb on [res_ctx | emb(s_t)]):
  * x0[n_rows,128] = relu(c[row] + t1[seq[row]]) . w2^T + b2, where c = res_ctx . W1[:, :128]^T + b1 (per-run constant,

@@ -582,23 +582,23 @@ def test_other_patch_lengths_sample_on_the_tensor_core_path(L):
     assert torch.equal(out["translations"].cpu()[~m], batch["xyz"][:, :, 1][~m])
 
 
-def test_front_mlp_fused_into_the_first_projection_kernel_changes_no_bit():
-    """dab_ipa_front_proj_sm100 (batches of >= 128 blocks: the epsilon network's front MLP inside the first layer's
-    projection kernel) against front kernel + GEMM + layer-by-layer stack: identical head outputs."""
-    from diffab_pytorch_b200.diffab_pytorch import cast_pair_to_bf16
+@pytest.mark.parametrize("B,L", [(128, 128), (64, 256)])
+def test_front_mlp_and_last_to_out_fused_into_their_neighbours_change_no_bit(B, L):
+    """Batches of >= 128 blocks of 128 residues: the epsilon network's front MLP runs inside the first layer's projection
+    kernel (dab_ipa_front_proj_sm100) and the last layer's to_out inside the heads kernel (dab_out_heads_fwd_sm100) -
+    identical head outputs to front kernel + GEMM + layer-by-layer stack + heads kernel."""
     model = _model(0)
-    B = 128
     g = torch.Generator(device=DEV).manual_seed(3)
-    res = torch.randn(B, 128, 128, device=DEV, generator=g)
-    pair = torch.randn(B, 128, 128, 64, device=DEV, generator=g).bfloat16()
-    batch = _to(synth.make_patches(B, 128, seed=4, with_distmat=False))
+    res = torch.randn(B, L, 128, device=DEV, generator=g)
+    pair = torch.randn(B, L, L, 64, device=DEV, generator=g).bfloat16()
+    batch = _to(synth.make_patches(B, L, seed=4, with_distmat=False))
     s, x, O = batch["seq_idx"], batch["xyz"][:, :, 1].contiguous(), batch["orientations"]
     with torch.no_grad():
         planes = model._pair_bias_planes(pair)
         cache = model.denoiser.sampling_cache(res)
         beta = model.dsched.tensors["beta"][torch.full((B,), 42, device=DEV)]
         ipa = model.denoiser.ipa
-        assert ipa.fused_stack_applicable(B, 128, pair, planes)
+        assert ipa.fused_stack_applicable(B, L, pair, planes)
         fused = model.denoiser.heads_fast(s, x, O, cache, pair, beta, planes)
         try:
             ipa.fused_stack_applicable = lambda *a, **k: False
@@ -606,4 +606,4 @@ def test_front_mlp_fused_into_the_first_projection_kernel_changes_no_bit():
         finally:
             del ipa.fused_stack_applicable
     for a, b in zip(fused, plain):
-        assert torch.isfinite(a).all() and torch.equal(a, b)
+        assert a.shape == b.shape and torch.isfinite(a).all() and torch.equal(a, b)
