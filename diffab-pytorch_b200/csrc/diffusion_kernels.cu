@@ -6,13 +6,9 @@
 // are bit-exact against the reference given the same injected noise: the probability expressions
 // use explicit round-to-nearest intrinsics so nvcc cannot contract them into FMAs.
 #include "common.cuh"
+#include "step_device.cuh"
 
 namespace dab {
-
-struct Sched {
-  int T;
-  const float *alpha, *alpha_bar, *alpha_bar_sqrt, *one_minus_alpha_bar_sqrt, *beta;
-};
 
 __device__ __forceinline__ float kUniform() { return __fdiv_rn(1.0f, 21.0f); }  // fl32(1/21), diffusion.py:71
 
@@ -21,19 +17,6 @@ __device__ __forceinline__ float mix_prob(bool hot, float w_keep, float w_noise,
   float oh = hot ? 1.0f : 0.0f;
   if (!generated) return oh;
   return __fadd_rn(__fmul_rn(w_keep, oh), __fmul_rn(w_noise, kUniform()));
-}
-
-// argmax_k p_k / q_k with first-index tie-break == torch.multinomial(p, 1) given its Exp(1) draw q
-template <typename F>
-__device__ __forceinline__ int argmax_ratio(F prob, const float* __restrict__ q) {
-  int best = 0;
-  float best_key = -1.0f;
-#pragma unroll
-  for (int k = 0; k < DAB_VOCAB; ++k) {
-    float key = __fdiv_rn(prob(k), q[k]);   // q may live in shared memory: plain (generic) load
-    if (key > best_key) { best_key = key; best = k; }
-  }
-  return best;
 }
 
 // One thread per residue, 128 residues per block.  Every per-residue record (21 exponential draws, 21 posterior
@@ -155,7 +138,7 @@ __global__ void __launch_bounds__(128) seq_probs_kernel(Sched sc, int kind, cons
   }
 }
 
-// Reverse step; composition fixed by oracle/sampler.py (the reference has none).
+// Reverse step (stand-alone form; the sampling loop runs it fused with the IGSO(3) draw, so3_kernels.cu).
 __global__ void __launch_bounds__(128) reverse_step_kernel(
     Sched sc, const int64_t* seq_t, const float* x_t, const float* O_t,  // may alias the outputs (in-place)
     const float* __restrict__ eps_theta, const float* __restrict__ v_theta, const float* __restrict__ seq_post,
@@ -164,57 +147,8 @@ __global__ void __launch_bounds__(128) reverse_step_kernel(
     int64_t* seq_out, float* x_out, float* O_out, float* O0_out) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= (int64_t)B * L) return;
-  int b = (int)(r / L);
-  int tt = (int)t[b];
-  if (tt < 0 || tt > sc.T) asm volatile("trap;");   // out-of-range timestep: the reference raises IndexError
-  bool gen = mask[r] != 0;
-  bool noisy = tt > 1;
-
-  // sequence
-  int64_t s_old = seq_t[r];
-  if (gen) {
-    const float* p = seq_post + r * DAB_VOCAB;
-    seq_out[r] = argmax_ratio([&](int k) { return __ldg(p + k); }, seq_exp + r * DAB_VOCAB);
-  } else {
-    seq_out[r] = s_old;
-  }
-  // positions: (x_t - beta/sqrt(1-abar) eps_theta) * (1/sqrt(alpha)) + sqrt(beta) z
-  float beta = __ldg(sc.beta + tt);
-  float c_eps = __fdiv_rn(beta, __ldg(sc.one_minus_alpha_bar_sqrt + tt));
-  float inv_sa = __fdiv_rn(1.0f, __fsqrt_rn(__ldg(sc.alpha + tt)));
-  float sig = noisy ? __fsqrt_rn(beta) : 0.f;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float xo = x_t[r * 3 + c];
-    float v = __fadd_rn(__fmul_rn(__fsub_rn(xo, __fmul_rn(c_eps, __ldg(eps_theta + r * 3 + c))), inv_sa),
-                        __fmul_rn(sig, __ldg(z + r * 3 + c)));
-    x_out[r * 3 + c] = gen ? v : xo;
-  }
-  // orientations: O0 = O_t @ exp(v_theta)  (Denoiser tail, diffab_pytorch.py:594-596); O' = O0 @ exp(rotvec)
-  float Rt[9], Re[9], R0[9];
-#pragma unroll
-  for (int c = 0; c < 9; ++c) Rt[c] = O_t[r * 9 + c];
-  so3_exp(__ldg(v_theta + r * 3), __ldg(v_theta + r * 3 + 1), __ldg(v_theta + r * 3 + 2), Re);
-  mat3_mul(Rt, Re, R0);
-  if (O0_out) {
-#pragma unroll
-    for (int c = 0; c < 9; ++c) O0_out[r * 9 + c] = R0[c];
-  }
-  if (gen) {
-    if (noisy) {
-      float Rn[9], Ro[9];
-      so3_exp(__ldg(rotvec + r * 3), __ldg(rotvec + r * 3 + 1), __ldg(rotvec + r * 3 + 2), Rn);
-      mat3_mul(R0, Rn, Ro);
-#pragma unroll
-      for (int c = 0; c < 9; ++c) O_out[r * 9 + c] = Ro[c];
-    } else {
-#pragma unroll
-      for (int c = 0; c < 9; ++c) O_out[r * 9 + c] = R0[c];
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < 9; ++c) O_out[r * 9 + c] = Rt[c];
-  }
+  reverse_update_residue(sc, r, (int)t[r / L], seq_t, x_t, O_t, eps_theta, v_theta, seq_post, mask, seq_exp, z, rotvec + r * 3,
+                         seq_out, x_out, O_out, O0_out);
 }
 
 static int check_sched(const DabSchedule* s, Sched& out, const char* name) {
