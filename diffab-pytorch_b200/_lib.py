@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # DAB_DEBUG_LIB=1 loads the debug build (make -C csrc debug: adds the process-global dab_debug_* hooks used by tools/)
 LIB_PATH = os.path.join(_HERE, "csrc", "libdiffab_b200_dbg.so" if os.environ.get("DAB_DEBUG_LIB") == "1"
-                        else "libdiffab_b200.so")
+                        else os.environ.get("DAB_LIB_VARIANT", "libdiffab_b200.so"))   # DAB_LIB_VARIANT: an experiment build in csrc/ (tools only)
 _lib = None
 
 
@@ -123,6 +123,7 @@ EXPORTS = {
     "dab_ipa_front_proj_sm100": (c_int, [c_void_p] * 10 + [c_size_t, c_void_p]),
     "dab_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "dab_gemm_bf16_tn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    "dab_gemm_bf16_tn_acc": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "dab_linear_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dab_bias_grad": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "dab_colsum_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),

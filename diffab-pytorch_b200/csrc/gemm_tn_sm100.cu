@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(128) gemm_tn_bf16_kernel(const __grid_constant
 
 template <int BN>
 static int launch_gemm_tn(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, bool accumulate = false) {
   CUtensorMap ma, mb;
   uint64_t dims_a[2] = {(uint64_t)M, (uint64_t)K}, str_a[1] = {(uint64_t)lda * 2};
   uint64_t dims_b[2] = {(uint64_t)N, (uint64_t)K}, str_b[1] = {(uint64_t)ldb * 2};
@@ -152,7 +152,8 @@ static int launch_gemm_tn(const void* A, int64_t lda, const void* Bm, int64_t ld
   if (splits > n_chunks / 4) splits = n_chunks / 4 > 0 ? n_chunks / 4 : 1;
   const int per = (n_chunks + splits - 1) / splits;
   splits = (n_chunks + per - 1) / per;
-  if (cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), stream) != cudaSuccess) return check_launch("gemm_tn memset");
+  if (!accumulate && cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), stream) != cudaSuccess)
+    return check_launch("gemm_tn memset");
   dim3 grid(N / BN, (M + kTnBM - 1) / kTnBM, splits);
   gemm_tn_bf16_kernel<BN><<<grid, 128, TnSmem<BN>::kTotal, stream>>>(ma, mb, C, ldc, M, per, n_chunks);
   count_launch();
@@ -232,6 +233,19 @@ int dab_gemm_bf16_tn(const void* A, int64_t lda, const void* Bm, int64_t ldb, fl
   return launch_gemm_tn<64>(A, lda, Bm, ldb, C, ldc, M, N, K, (cudaStream_t)stream);
 }
 
+/* C[M,N] += A[K,M]^T B[K,N]: dab_gemm_bf16_tn without the fill of C - the caller zeroes (or pre-loads) C, e.g. on a side
+ * stream long before the operands exist, so that no fill sits between the producer of the operands and this GEMM. */
+int dab_gemm_bf16_tn_acc(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
+                         void* stream) {
+  DAB_REQUIRE(A && Bm && C, DAB_EINVAL, "dab_gemm_bf16_tn_acc: null pointer");
+  DAB_REQUIRE(M > 0 && N > 0 && K > 0 && K % kTnKC == 0 && N % 64 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 &&
+                  lda >= M && ldb >= N && ldc >= N,
+              DAB_EUNSUPPORTED, "dab_gemm_bf16_tn_acc: K %% 64, N %% 64, lda/ldb %% 8, ldc %% 4 required (M=%d N=%d K=%d)", M, N, K);
+  DAB_REQUIRE(aligned16(A) && aligned16(Bm) && aligned16(C), DAB_EINVAL, "dab_gemm_bf16_tn_acc: misaligned pointer");
+  if (N % 128 == 0) return launch_gemm_tn<128>(A, lda, Bm, ldb, C, ldc, M, N, K, (cudaStream_t)stream, true);
+  return launch_gemm_tn<64>(A, lda, Bm, ldb, C, ldc, M, N, K, (cudaStream_t)stream, true);
+}
+
 /* out[cols] (fp32, overwritten) = column sums of x[rows, cols] (fp32, contiguous): bias gradients (sum over residues).
  * x_bf16 (optional, may be NULL): x rounded to bf16, written in the same pass (the operand of the gradient GEMMs). */
 int dab_colsum_f32(const float* x, int64_t rows, int cols, float* out, void* x_bf16, void* stream) {
@@ -240,8 +254,11 @@ int dab_colsum_f32(const float* x, int64_t rows, int cols, float* out, void* x_b
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), s) != cudaSuccess) return check_launch("dab_colsum_f32 memset");
   if (rows == 0) return DAB_OK;
-  int64_t blocks = (rows + 31) / 32;
-  if (blocks > 148) blocks = 148;
+  // small inputs are latency-bound: one row per thread (more blocks, one red.global per column and block); large ones
+  // walk the rows with 148 x 4 blocks
+  const int c4 = cols / 4, groups = 256 / (c4 < 256 ? c4 : 256);
+  int64_t blocks = (rows + groups - 1) / groups;
+  if (blocks > 148 * 4) blocks = 148 * 4;
   colsum_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(x, rows, cols, out, reinterpret_cast<__nv_bfloat16*>(x_bf16), nullptr);
   count_launch();
   return check_launch("dab_colsum_f32");

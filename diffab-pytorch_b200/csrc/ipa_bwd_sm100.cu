@@ -15,19 +15,18 @@
 //              sum dl l from the logits in registers, sum dl ls = <qs, dqs>, sum dl lb = <st Wpb, sum dl e>.
 //
 // Launch sequence (dab_ipa_bwd_sm100):
-//   1. bwd_prep_kernel      : dcat, cat -> dO (fp16, per-row power-of-two scaling; bf16 copy), dopair (bf16), Delta
-//   2. ipa_bwd_core_kernel  : per CTA = (patch, 16 query rows), thread = key j = TMEM lane (as the forward core):
-//        S^T_h  = K_h Q_h^T                (recompute logits)             M=128 j, N=16 i, K=32+3*32   bf16
+//   1. ipa_bwd_core_kernel  : per CTA = (patch, 16 query rows), thread = key j = TMEM lane (as the forward core):
+//        prologue: dcat, cat rows of the tile -> dO (fp16 with a per-row power-of-two scale, in shared memory; bf16 copy to
+//                  HBM for the key side), dopair (bf16, shared memory), Delta   (a separate launch until round 2)
 //        dPv^T_h = V_h dO_h^T              (value part of dP)             M=128 j, N=16 i, K=64        fp16
-//        per query row i, on the TMA-staged pair row e[i] (read from HBM once):
+//        per query row i, on the TMA-staged pair row e[i] (read from HBM once; P comes from the forward's saved Pu):
 //          dPp_i = e[i] dopair_i^T         (pair part of dP)              M=128 j, N=16(8 h), K=64 c
 //          de_i  = [P_i | dl_i] [dopair_i ; st Wpb]                       M=128 j, N=64 c, K=16        -> HBM (bf16)
 //          Z    += e[i]^T dl_i             (to_pair_bias gradient)        M=64 c,  N=8 h,  K=128 j
-//        dQ^T_h = K_h[:, :64]^T dl_h       (scalar + point-hi columns)    M=64,    N=16 i, K=128 j
 //      P and dl also go to HBM as bf16 [b][h][i][j] for the key side.
-//   3. ipa_bwd_keyside_kernel: per (patch, head): dV_h = P_h^T dO_h, dK_h = dl_h^T Q_h[:, :64], dQ_h = dl_h K_h[:, :64]
+//   2. ipa_bwd_keyside_kernel: per (patch, head): dV_h = P_h^T dO_h, dK_h = dl_h^T Q_h[:, :64], dQ_h = dl_h K_h[:, :64]
 //      and, in its epilogue: scales, the -c q~ sum dl corrections, global -> local frame -> dproj rows (bf16)
-//   4. bwd_reduce_kernel / bwd_finalize_kernel: reduce the per-CTA partials into dWpb and dgamma
+//   3. bwd_reduce_kernel / bwd_finalize_kernel: reduce the per-CTA partials into dWpb and dgamma
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <math.h>
@@ -50,11 +49,8 @@ static constexpr int g_bwd_keep_qkv = 0;
 
 // ---- backward workspace ---------------------------------------------------------------------------------
 struct BwdWs {
-  __half* dO16;             // [rows][8][64] fp16, scaled by 2^k(row): [dos 32 | dog 24 | 0 x 8]
-  __nv_bfloat16* dObf;      // same, unscaled bf16 (key side)
-  __nv_bfloat16* dopair;    // [rows][8][64] bf16
-  float* delta;             // [rows][8]
-  float* rscale;            // [rows] 1 / 2^k(row)
+  __nv_bfloat16* dObf;      // [rows][8][64] bf16: [dos 32 | dog 24 | 0 x 8], unscaled (key side; the query side keeps its
+                            // scaled fp16 copy, dopair, Delta and the row scales in shared memory)
   __nv_bfloat16 *Pn, *dL;   // [B][8][128 i][128 j] bf16
   float *dQ, *dK, *dV;      // [rows][8][64] fp32: raw key-side accumulators, written only for tests (contiguous)
   float *p_wpb, *p_g1, *p_g2;   // partials: [B*8][512], [B*8][8], [B][8]
@@ -66,11 +62,7 @@ inline BwdWs carve_bwd(int B, void* base) {
   const size_t rows = (size_t)B * L;
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   BwdWs w;
-  w.dO16 = reinterpret_cast<__half*>(p); p += al(rows * H * 64 * 2);
   w.dObf = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * H * 64 * 2);
-  w.dopair = reinterpret_cast<__nv_bfloat16*>(p); p += al(rows * H * 64 * 2);
-  w.delta = reinterpret_cast<float*>(p); p += al(rows * H * 4);
-  w.rscale = reinterpret_cast<float*>(p); p += al(rows * 4);
   w.Pn = reinterpret_cast<__nv_bfloat16*>(p); p += al((size_t)B * H * L * L * 2);
   w.dL = reinterpret_cast<__nv_bfloat16*>(p); p += al((size_t)B * H * L * L * 2);
   w.dQ = reinterpret_cast<float*>(p); p += al(rows * H * 64 * 4);
@@ -84,79 +76,13 @@ inline BwdWs carve_bwd(int B, void* base) {
   return w;
 }
 
-// ---- 1. prep ----------------------------------------------------------------------------------------------
-// One block per residue row, warp = head.  cat row layout (diffab_pytorch.py:456-462):
-// [scalar (h d) 256 | pair (h c) 512 | local points (h p c) 192 | norms (h p) 64].
-__global__ void __launch_bounds__(256) bwd_prep_kernel(const float* __restrict__ dcat, const __nv_bfloat16* __restrict__ cat,
-                                                       const float* __restrict__ R, const float* __restrict__ tc,
-                                                       __half* __restrict__ dO16, __nv_bfloat16* __restrict__ dObf,
-                                                       __nv_bfloat16* __restrict__ dopair, float* __restrict__ delta,
-                                                       float* __restrict__ rscale) {
-  __shared__ float s_max[8];
-  const int64_t row = blockIdx.x;
-  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* dc = dcat + row * NCAT;
-  const __nv_bfloat16* ct = cat + row * NCAT;
-  const float dos = dc[h * DS + lane];
-  const float os = __bfloat162float(ct[h * DS + lane]);
-  const float dp0 = dc[NS + h * C + lane], dp1 = dc[NS + h * C + 32 + lane];
-  const float op0 = __bfloat162float(ct[NS + h * C + lane]), op1 = __bfloat162float(ct[NS + h * C + 32 + lane]);
-  float acc = dos * os + dp0 * op0 + dp1 * op1;
-  float dog[3] = {0.f, 0.f, 0.f};
-  if (lane < P) {
-    // ol = (og - t) R^T, nrm = |ol| (diffab_pytorch.py:327-336,453-457)  ->  d_ol += dnrm ol / nrm; dog = d_ol R
-    const int o = NS + H * C + h * (P * 3) + lane * 3;
-    float ol[3], dl[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { ol[c] = __bfloat162float(ct[o + c]); dl[c] = dc[o + c]; }
-    const float dn = dc[NS + H * C + NPT + h * P + lane];
-    const float nrm = sqrtf(ol[0] * ol[0] + ol[1] * ol[1] + ol[2] * ol[2]);
-    if (nrm > 0.f) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) dl[c] += dn * ol[c] / nrm;
-    }
-    const float* Rr = R + row * 9;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) dog[k] = dl[0] * Rr[k] + dl[1] * Rr[3 + k] + dl[2] * Rr[6 + k];
-    // <dog, og> with og = ol R + t:  (d_ol R).(ol R) = d_ol . ol  (R orthogonal)
-    acc += dl[0] * ol[0] + dl[1] * ol[1] + dl[2] * ol[2] + dog[0] * tc[row * 3] + dog[1] * tc[row * 3 + 1] +
-           dog[2] * tc[row * 3 + 2];
-  }
-  acc = warp_sum(acc);
-  float mx = fmaxf(fabsf(dos), fmaxf(fabsf(dog[0]), fmaxf(fabsf(dog[1]), fabsf(dog[2]))));
-  mx = warp_max(mx);
-  if (lane == 0) { s_max[h] = mx; delta[row * H + h] = acc; }
-  __syncthreads();
-  float m = s_max[0];
-#pragma unroll
-  for (int k = 1; k < 8; ++k) m = fmaxf(m, s_max[k]);
-  // power-of-two scale that puts the largest entry of the row in [2^11, 2^12): fp16 keeps >= 11 bits for
-  // everything within 2^-25 of it, whatever the magnitude of the upstream gradient
-  float s = 1.0f;
-  if (m > 0.f && m < 3.0e38f) {
-    int ex;
-    frexpf(m, &ex);
-    s = ldexpf(1.0f, max(-100, min(100, 12 - ex)));
-  }
-  if (threadIdx.x == 0) rscale[row] = 1.0f / s;
-  const int64_t base = (row * H + h) * 64;
-  dO16[base + lane] = __float2half_rn(dos * s);
-  dObf[base + lane] = __float2bfloat16_rn(dos);
-  if (lane < P) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      dO16[base + 32 + lane * 3 + k] = __float2half_rn(dog[k] * s);
-      dObf[base + 32 + lane * 3 + k] = __float2bfloat16_rn(dog[k]);
-    }
-  } else if (lane < 16) {
-    dO16[base + 48 + lane] = __float2half_rn(0.f);
-    dObf[base + 48 + lane] = __float2bfloat16_rn(0.f);
-  }
-  dopair[base + lane] = __float2bfloat16_rn(dp0);
-  dopair[base + 32 + lane] = __float2bfloat16_rn(dp1);
-}
-
-// ---- 2. query-side core ---------------------------------------------------------------------------------------
+// ---- 1 + 2. query-side core (with the preparation of its own rows) -------------------------------------------------
+// Prologue (what a separate "prep" launch did before: 22 us at B = 32 on the critical path): everything the tile needs
+// from dcat is a function of ITS OWN 16 query rows, so the eight compute warps (warp = head) turn the rows' dcat / cat
+// (cat row layout, diffab_pytorch.py:456-462: [scalar (h d) 256 | pair (h c) 512 | local points (h p c) 192 | norms (h p) 64])
+// into dO (fp16 with a per-row power-of-two scale, straight into the swizzled MMA operand tile; unscaled bf16 copy to HBM
+// for the key side), dopair (bf16, the sixteen operand tiles stay resident) and Delta = <dO, O> - while the V tiles and
+// the first pair rows are already on their way.
 // The forward saved the un-normalised probabilities Pu[b][i][j][8 h] (bf16) and 1 / sum_j p, so the logits are not
 // recomputed: no Q / K operands here (dQ moved to the key-side kernel, where dl_h is a resident tile anyway).
 struct BwdSmem {
@@ -169,13 +95,16 @@ struct BwdSmem {
   // region P: stage 1 = dO rows of this CTA ([h][16 i][128 B] fp16); stage 2 = four [P | dl] operand buffers
   static constexpr int kDoOff = kXBytes;             // 16,384
   static constexpr int kPcat = kXBytes;              // 4 x { [128 j][16 B] P | [128 j][16 B] dl } bf16
-  static constexpr int kDop = kPcat + 16384;         // ring of four [8 h][128 B] bf16 dopair rows ...
-  static constexpr int kWpb = kDop + kEStages * 1024;   // ... directly followed by [8 h][128 B] bf16: st * Wpb
+  static constexpr int kDop = kPcat + 16384;         // the CTA's sixteen [8 h][128 B] bf16 dopair rows ...
+  static constexpr int kWpb = kDop + IB * 1024;      // ... directly followed by [8 h][128 B] bf16: st * Wpb
   static constexpr int kInv = kWpb + 1024;           // [16 i][8] f32: 1 / sum_j p
   static constexpr int kDelta = kInv + 512;          // [16 i][8] f32
   static constexpr int kRs = kDelta + 512;           // [16] f32
   static constexpr int kRed = kRs + 64;              // [8 warps][8] f32
-  static constexpr int kBars = kRed + 256;           // 48 mbarriers
+  static constexpr int kMax = kRed + 256;            // [16 i][8 h] f32: largest |dO| entry per (row, head)  (prologue)
+  static constexpr int kFrame = kMax + 512;          // [16 i][12] f32: R (9) | centred t (3) of the CTA's rows
+  static constexpr int kScr = kFrame + 768;          // [8 h][16 i] f32: pair part of Delta (prologue)
+  static constexpr int kBars = kScr + 512;           // 48 mbarriers
   static constexpr int kTmemSlot = kBars + 384;
   static constexpr int kTotal = kTmemSlot + 16;
 };
@@ -200,9 +129,10 @@ __device__ __forceinline__ float lg2(float x) {
 
 __global__ void __launch_bounds__(320, 2)
 ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_e,
-                    const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_dop,
-                    const uint4* __restrict__ Pu, const float* __restrict__ stats, const float* __restrict__ delta,
-                    const float* __restrict__ rscale, const float* __restrict__ wpb, __nv_bfloat16* __restrict__ de,
+                    const float* __restrict__ dcat, const __nv_bfloat16* __restrict__ cat, const float* __restrict__ R,
+                    const float* __restrict__ tc, __nv_bfloat16* __restrict__ dObf,
+                    const uint4* __restrict__ Pu, const float* __restrict__ stats,
+                    const float* __restrict__ wpb, __nv_bfloat16* __restrict__ de,
                     __nv_bfloat16* __restrict__ Pn, __nv_bfloat16* __restrict__ dL, float* __restrict__ p_wpb,
                     float* __restrict__ p_g1, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -234,23 +164,28 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
     // the producer lane initialises the barriers and starts the stage-1 loads before the CTA-wide synchronisation
     for (int i = 0; i < B_N_BARS; ++i) {
       const bool many = (i >= DPP_FREE && i < DPP_FREE + 3) || (i >= PCAT_READY && i < PCAT_READY + 4) || i == DE_FREE;
-      mbar_init(&bars[i], many ? 128u : 1u);
+      mbar_init(&bars[i], i == BQ_FULL ? 256u : (many ? 128u : 1u));   // BQ_FULL: the compute threads publish dO / dopair
     }
     fence_barrier_init();
-    tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e); tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_dop);
-    mbar_arrive_expect_tx(&bars[BQ_FULL], 16384);
-    for (int h = 0; h < H; ++h)
-      tma_load_2d(smem + S::kDoOff + h * 2048, &map_do, &bars[BQ_FULL], h * 64, (int)row0);
+    tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
     for (int h = 0; h < S::kVBufs; ++h) load_v(h);
-    // every pair row of the tile starts its way HBM -> L2 now: the stream runs during the dPv prologue
-    for (int r = 0; r < IB; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
+#ifndef DAB_BWD_PF_ROWS
+#define DAB_BWD_PF_ROWS 16
+#endif
+#ifdef DAB_BWD_PF_DCAT
+    // the tile's own dcat / cat rows first (the prologue's loads then find them in L2)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(dcat + row0 * NCAT), "r"(IB * NCAT * 4) : "memory");
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(cat + row0 * NCAT), "r"(IB * NCAT * 2) : "memory");
+#endif
+    // the first pair rows of the tile start their way HBM -> L2 now: the stream runs during the prologue
+    for (int r = 0; r < DAB_BWD_PF_ROWS; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
   }
   // per-row constants of this CTA and the st * Wpb operand tile ([8 h][64 c] bf16, 128B-swizzled rows)
-  if (tid < 128) {
-    s_inv[tid] = stats[(row0 + (tid >> 3)) * 16 + 8 + (tid & 7)];
-    s_delta[tid] = delta[row0 * 8 + tid];
+  if (tid < 128) s_inv[tid] = stats[(row0 + (tid >> 3)) * 16 + 8 + (tid & 7)];
+  if (tid < IB * 12) {           // frames of the CTA's rows for the prologue
+    const int i = tid / 12, k = tid % 12;
+    reinterpret_cast<float*>(smem + S::kFrame)[tid] = k < 9 ? R[(row0 + i) * 9 + k] : tc[(row0 + i) * 3 + (k - 9)];
   }
-  if (tid < 16) s_rs[tid] = rscale[row0 + tid];
   if (tid < 256) {
     const float st = rsqrtf(3.0f);
     const int hh = tid >> 5, c2 = (tid & 31) * 2;   // two consecutive channels
@@ -274,6 +209,10 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
   if (warp == 9) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
+      if (DAB_BWD_PF_ROWS < IB) {      // the rest once the prologue's loads are through
+        mbar_wait(&bars[BQ_FULL], 0);
+        for (int r = DAB_BWD_PF_ROWS; r < IB; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
+      }
       for (int h = S::kVBufs; h < H; ++h) {
         mbar_wait(&bars[BV_EMPTY + h % S::kVBufs], ((h / S::kVBufs) - 1) & 1);
         load_v(h);
@@ -283,9 +222,8 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
       for (int r = 0; r < IB; ++r) {
         const int s = r % S::kEStages;
         if (r >= S::kEStages) mbar_wait(&bars[BE_EMPTY + s], ((r / S::kEStages) - 1) & 1);
-        mbar_arrive_expect_tx(&bars[BE_FULL + s], S::kEStage + 1024);
+        mbar_arrive_expect_tx(&bars[BE_FULL + s], S::kEStage);
         tma_load_2d(smem + s * S::kEStage, &map_e, &bars[BE_FULL + s], 0, (int)((row0 + r) * L));
-        tma_load_2d(smem + S::kDop + s * 1024, &map_dop, &bars[BE_FULL + s], 0, (int)((row0 + r) * H));
       }
     }
   } else if (warp == 8) {
@@ -325,10 +263,10 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
         if (pos >= 3) mbar_wait(&bars[DPP_FREE + ds], ((pos / 3) - 1) & 1);
         tcgen05_fence_after_sync();
         if (elect_one()) {
-          const uint32_t ea = smem_base + s * S::kEStage, da0 = smem_base + S::kDop + s * 1024;
+          const uint32_t ea = smem_base + s * S::kEStage, da0 = smem_base + S::kDop + r * 1024;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            // N = 16: rows 8..15 of B are whatever follows the dopair tile (next ring slot or the Wpb tile) and
+            // N = 16: rows 8..15 of B are whatever follows the dopair tile (the next row's tile or the Wpb tile) and
             // land in accumulator columns 8..15, which nobody reads
             uint64_t da = make_smem_desc(ea + k * 32, 16, 1024, kSwizzle128B);
             uint64_t db = make_smem_desc(da0 + k * 32, 16, 1024, kSwizzle128B);
@@ -348,7 +286,7 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
         tcgen05_fence_after_sync();
         if (elect_one()) {
         const uint32_t pc = smem_base + S::kPcat + (g * 2 + slot) * 4096;
-        const uint32_t dop = smem_base + S::kDop + s * 1024;
+        const uint32_t dop = smem_base + S::kDop + r * 1024;
         {
           // A: [128 j][16] K-major, no swizzle: core matrices of 8 rows x 16 B; K chunks 2048 B apart (LBO),
           //    8-row groups 128 B apart (SBO).  B: [16 k][64 c] MN-major 128B-swizzled, two 8-row atoms:
@@ -387,6 +325,123 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
 
     const uint4* pu_t = Pu + (row0 + 2 * g) * L + gt;     // row 4q + 2g + rr  ->  + (4q + rr) * L
     uint4 u_nxt[2] = {__ldg(pu_t), __ldg(pu_t + L)};
+
+    // ---- prologue: dO / dopair / Delta of the CTA's 16 rows from dcat and cat.  Thread = (head ph, row pi), twice: warps
+    //      0-3 take the scalar + point parts of their (row, head), warps 4-7 its pair part - every thread walks its own
+    //      contiguous segments of the two rows with 16-byte loads (no shuffles, no per-warp serial work; the version with
+    //      warp = head and lanes = columns spent 5k instructions per warp and was issue-bound at 45k cycles).
+    {
+      const int ph = (tid & 127) >> 4, pi = tid & 15;
+      const float* dc = dcat + (row0 + pi) * NCAT;
+      const __nv_bfloat16* ct = cat + (row0 + pi) * NCAT;
+      float* s_max = reinterpret_cast<float*>(smem + S::kMax);            // [16 i][8 h]
+      float* s_dp = reinterpret_cast<float*>(smem + S::kScr);             // [8 h][16 i]: pair part of Delta
+      const float* fr = reinterpret_cast<const float*>(smem + S::kFrame) + pi * 12;
+      auto bf_lo = [](uint32_t u) { return __uint_as_float(u << 16); };
+      auto bf_hi = [](uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); };
+      float dos[32], dog[24], acc = 0.f;
+      BWD_STAMP(16);
+      if (warp >= 4) {
+        // pair part: the dopair operand tile of row pi ([8 h][128 B] bf16, 128B-swizzled) and its share of Delta
+        uint8_t* tile = smem + S::kDop + pi * 1024 + ph * 128;
+        const float* dp = dc + NS + ph * C;
+        const __nv_bfloat16* op = ct + NS + ph * C;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const int c = (c8 + pi) & 7;     // the 8 lanes of a quarter-warp (rows pi .. pi+7, same head) hit 8 different banks
+          const float4 a = __ldg(reinterpret_cast<const float4*>(dp + c * 8));
+          const float4 b2 = __ldg(reinterpret_cast<const float4*>(dp + c * 8 + 4));
+          const uint4 o = __ldg(reinterpret_cast<const uint4*>(op + c * 8));
+          acc += a.x * bf_lo(o.x) + a.y * bf_hi(o.x) + a.z * bf_lo(o.y) + a.w * bf_hi(o.y) + b2.x * bf_lo(o.z) +
+                 b2.y * bf_hi(o.z) + b2.z * bf_lo(o.w) + b2.w * bf_hi(o.w);
+          *reinterpret_cast<uint4*>(tile + ((c ^ ph) << 4)) =
+              make_uint4(pack_bf162(a.x, a.y), pack_bf162(a.z, a.w), pack_bf162(b2.x, b2.y), pack_bf162(b2.z, b2.w));
+        }
+        s_dp[tid & 127] = acc;
+      } else {
+        // point part: ol = (og - t) R^T, nrm = |ol| (diffab_pytorch.py:327-336,453-457) -> d_ol += dnrm ol / nrm; dog = d_ol R
+        float dl[24], ol[24], dn[8];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(dc + NS + H * C + ph * (P * 3) + c * 4));
+          dl[4 * c] = a.x; dl[4 * c + 1] = a.y; dl[4 * c + 2] = a.z; dl[4 * c + 3] = a.w;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const uint4 o = __ldg(reinterpret_cast<const uint4*>(ct + NS + H * C + ph * (P * 3) + c * 8));
+          ol[8 * c] = bf_lo(o.x); ol[8 * c + 1] = bf_hi(o.x); ol[8 * c + 2] = bf_lo(o.y); ol[8 * c + 3] = bf_hi(o.y);
+          ol[8 * c + 4] = bf_lo(o.z); ol[8 * c + 5] = bf_hi(o.z); ol[8 * c + 6] = bf_lo(o.w); ol[8 * c + 7] = bf_hi(o.w);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(dc + NS + H * C + NPT + ph * P + c * 4));
+          dn[4 * c] = a.x; dn[4 * c + 1] = a.y; dn[4 * c + 2] = a.z; dn[4 * c + 3] = a.w;
+        }
+        float mx = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          const float x0 = ol[3 * p], x1 = ol[3 * p + 1], x2 = ol[3 * p + 2];
+          float d0 = dl[3 * p], d1 = dl[3 * p + 1], d2 = dl[3 * p + 2];
+          const float nrm = sqrtf(x0 * x0 + x1 * x1 + x2 * x2);
+          if (nrm > 0.f) { d0 += dn[p] * x0 / nrm; d1 += dn[p] * x1 / nrm; d2 += dn[p] * x2 / nrm; }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            dog[3 * p + k] = d0 * fr[k] + d1 * fr[3 + k] + d2 * fr[6 + k];
+            mx = fmaxf(mx, fabsf(dog[3 * p + k]));
+          }
+          // <dog, og> with og = ol R + t:  (d_ol R).(ol R) = d_ol . ol  (R orthogonal)
+          acc += d0 * x0 + d1 * x1 + d2 * x2 + dog[3 * p] * fr[9] + dog[3 * p + 1] * fr[10] + dog[3 * p + 2] * fr[11];
+        }
+        // scalar part
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(dc + ph * DS + c * 8));
+          const float4 b2 = __ldg(reinterpret_cast<const float4*>(dc + ph * DS + c * 8 + 4));
+          const uint4 o = __ldg(reinterpret_cast<const uint4*>(ct + ph * DS + c * 8));
+          dos[8 * c] = a.x; dos[8 * c + 1] = a.y; dos[8 * c + 2] = a.z; dos[8 * c + 3] = a.w;
+          dos[8 * c + 4] = b2.x; dos[8 * c + 5] = b2.y; dos[8 * c + 6] = b2.z; dos[8 * c + 7] = b2.w;
+          acc += a.x * bf_lo(o.x) + a.y * bf_hi(o.x) + a.z * bf_lo(o.y) + a.w * bf_hi(o.y) + b2.x * bf_lo(o.z) +
+                 b2.y * bf_hi(o.z) + b2.z * bf_lo(o.w) + b2.w * bf_hi(o.w);
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) mx = fmaxf(mx, fabsf(dos[k]));
+        s_max[pi * 8 + ph] = mx;
+      }
+      BWD_STAMP(18);
+      bar_all_compute();
+      if (warp < 4) {
+        s_delta[pi * 8 + ph] = acc + s_dp[tid];
+        // power-of-two scale that puts the largest entry of the row in [2^11, 2^12): fp16 keeps >= 11 bits for
+        // everything within 2^-25 of it, whatever the magnitude of the upstream gradient
+        const float4 m0 = *reinterpret_cast<const float4*>(s_max + pi * 8), m1 = *reinterpret_cast<const float4*>(s_max + pi * 8 + 4);
+        const float m = fmaxf(fmaxf(fmaxf(m0.x, m0.y), fmaxf(m0.z, m0.w)), fmaxf(fmaxf(m1.x, m1.y), fmaxf(m1.z, m1.w)));
+        float sc = 1.0f;
+        if (m > 0.f && m < 3.0e38f) {
+          int ex;
+          frexpf(m, &ex);
+          sc = ldexpf(1.0f, max(-100, min(100, 12 - ex)));
+        }
+        if (ph == 0) s_rs[pi] = 1.0f / sc;
+        // dO row of (head, row): [dos 32 | dog 24 | 0 x 8] -> fp16 scaled into the B operand tile of dPv ([16 i][128 B],
+        // 128B-swizzled), bf16 unscaled to HBM for the key side
+        uint8_t* ot = smem + S::kDoOff + ph * 2048 + pi * 128;
+        uint4* ob = reinterpret_cast<uint4*>(dObf + ((row0 + pi) * H + ph) * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = c < 4 ? dos[8 * c + k] : (c < 7 ? dog[8 * (c - 4) + k] : 0.f);
+          *reinterpret_cast<uint4*>(ot + ((c ^ (pi & 7)) << 4)) =
+              make_uint4(pack_h2(v[0] * sc, v[1] * sc), pack_h2(v[2] * sc, v[3] * sc), pack_h2(v[4] * sc, v[5] * sc),
+                         pack_h2(v[6] * sc, v[7] * sc));
+          ob[c] = make_uint4(pack_bf162(v[0], v[1]), pack_bf162(v[2], v[3]), pack_bf162(v[4], v[5]), pack_bf162(v[6], v[7]));
+        }
+      }
+      BWD_STAMP(20);
+      fence_proxy_async_smem();
+      mbar_arrive(&bars[BQ_FULL]);
+      bar_all_compute();        // s_delta / s_rs of every row are visible to every compute thread
+    }
     mbar_wait(&bars[BS_DONE], 0);
     tcgen05_fence_after_sync();
     BWD_STAMP(4);
@@ -481,10 +536,15 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
               tcgen05_fence_before_sync();
               mbar_arrive(&bars[DE_FREE]);
             }
+            // 256-bit stores: every request is one whole 32-byte sector of the key's 128-byte line (16-byte stores at a
+            // 128-byte lane stride are half-sector writes, twice as many requests)
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq)
-              dst[half * 4 + qq] = make_uint4(pack_bf162(v[8 * qq], v[8 * qq + 1]), pack_bf162(v[8 * qq + 2], v[8 * qq + 3]),
-                                              pack_bf162(v[8 * qq + 4], v[8 * qq + 5]), pack_bf162(v[8 * qq + 6], v[8 * qq + 7]));
+            for (int qq = 0; qq < 2; ++qq)
+              st_global_v8(dst + half * 4 + qq * 2,
+                           pack_bf162(v[16 * qq], v[16 * qq + 1]), pack_bf162(v[16 * qq + 2], v[16 * qq + 3]),
+                           pack_bf162(v[16 * qq + 4], v[16 * qq + 5]), pack_bf162(v[16 * qq + 6], v[16 * qq + 7]),
+                           pack_bf162(v[16 * qq + 8], v[16 * qq + 9]), pack_bf162(v[16 * qq + 10], v[16 * qq + 11]),
+                           pack_bf162(v[16 * qq + 12], v[16 * qq + 13]), pack_bf162(v[16 * qq + 14], v[16 * qq + 15]));
           }
         }
         BWD_STAMP(8 + n);
@@ -830,26 +890,19 @@ static int bwd_sm100_impl(const DabIpaDims* d, const void* packed, const void* e
     count_launch();
     return check_launch("dab_ipa_bwd_sm100_finish");
   }
-  bwd_prep_kernel<<<M, 256, 0, s>>>(dcat, ws.cat, R, ws.tc, bw.dO16, bw.dObf, bw.dopair, bw.delta, bw.rscale);
-  count_launch();
-
-  CUtensorMap mv, me, mdo, mdop;
+  CUtensorMap mv, me;
   {
     uint64_t dv[2] = {(uint64_t)H * V_W, (uint64_t)M}, sv[1] = {(uint64_t)H * V_W * 2};
-    uint32_t bv[2] = {V_W, L}, bdo[2] = {64, IB};
+    uint32_t bv[2] = {V_W, L};
     if (int rc = make_tensor_map_bf16(&mv, ws.Vp, 2, dv, sv, bv, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    if (int rc = make_tensor_map_bf16(&mdo, bw.dO16, 2, dv, sv, bdo, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     uint64_t de_[2] = {(uint64_t)C, (uint64_t)M * L}, se[1] = {(uint64_t)C * 2};
     uint32_t be[2] = {C, L};
     if (int rc = make_tensor_map_bf16(&me, e_bf16, 2, de_, se, be, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    uint64_t ddp[2] = {64, (uint64_t)M * H}, sdp[1] = {128};
-    uint32_t bdp[2] = {64, H};
-    if (int rc = make_tensor_map_bf16(&mdop, bw.dopair, 2, ddp, sdp, bdp, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
   DAB_ENSURE_SMEM(ipa_bwd_core_kernel, BwdSmem::kTotal);
   DAB_ENSURE_SMEM(ipa_bwd_keyside_kernel, KsSmem::kTotal);
   ipa_bwd_core_kernel<<<dim3(L / IB, B), 320, BwdSmem::kTotal, s>>>(
-      mv, me, mdo, mdop, ws.pu, ws.stats, bw.delta, bw.rscale, wpb, reinterpret_cast<__nv_bfloat16*>(de_bf16), bw.Pn,
+      mv, me, dcat, ws.cat, R, ws.tc, bw.dObf, ws.pu, ws.stats, wpb, reinterpret_cast<__nv_bfloat16*>(de_bf16), bw.Pn,
       bw.dL, bw.p_wpb, bw.p_g1, g_bwd_dbg);
   count_launch();
 
@@ -920,7 +973,7 @@ int dab_debug_set_bwd_timeline(long long* buf) {
 int dab_debug_bwd_sm100_buffers(const DabIpaDims* d, void* workspace, void** out /* 10 pointers */) {
   DAB_REQUIRE(shape_ok(d) && workspace && out, DAB_EINVAL, "dab_debug_bwd_sm100_buffers: bad argument");
   BwdWs bw = carve_bwd(d->B, workspace);
-  out[0] = bw.dO16; out[1] = bw.dObf; out[2] = bw.dopair; out[3] = bw.delta; out[4] = bw.rscale;
+  out[0] = nullptr; out[1] = bw.dObf; out[2] = nullptr; out[3] = nullptr; out[4] = nullptr;   // 0, 2-4: no longer in HBM
   out[5] = bw.Pn; out[6] = bw.dL; out[7] = bw.dQ; out[8] = bw.dK; out[9] = bw.dV;
   return DAB_OK;
 }

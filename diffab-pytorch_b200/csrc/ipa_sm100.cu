@@ -353,7 +353,10 @@ ipa_core_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (lane == 0) {
       tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
       const uint64_t pol = policy_evict_first();
-      constexpr int kL2Ahead = 8;
+#ifndef DAB_L2_AHEAD
+#define DAB_L2_AHEAD 8
+#endif
+      constexpr int kL2Ahead = DAB_L2_AHEAD;   // <= IB
       // pair index of (query row r of tile k, first key of the tile's key block)
       auto pair0_of = [&](int k, int r) { const TileIdx ti = decode(tile_of(k)); return (int)((ti.q0 + r) * ti.lrow + ti.joff); };
       if (n_local > 0)

@@ -237,6 +237,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ uint32_t swz128_offset(uint32_t row, uint32_t chunk16) {
   return row * 128u + ((chunk16 ^ (row & 7u)) << 4);
 }
+// One 256-bit global store (sm_100: STG.256): a whole 32-byte sector per request; `p` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                             uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4),
+               "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
 // Same for 64-byte rows (CU_TENSOR_MAP_SWIZZLE_64B): 8-row atoms of 512 B, chunk XOR ((row >> 1) & 3).
 __device__ __forceinline__ uint32_t swz64_offset(uint32_t row, uint32_t chunk16) {
   return row * 64u + ((chunk16 ^ ((row >> 1) & 3u)) << 4);

@@ -758,43 +758,59 @@ class _IpaFastFunction(torch.autograd.Function):
         # captured as parallel branches when the step is recorded into a CUDA graph).
         main = torch.cuda.current_stream(dev_)
         side = _side_stream(dev_)
+        side2 = _side_stream(dev_, 1)
         dy_bf = torch.empty(M, D, device=dev_, dtype=bf)
         d_b_out = torch.empty(D, device=dev_, dtype=f32)
-        _lib.check(lib.dab_colsum_f32(ptr(dy2), M, D, ptr(d_b_out), ptr(dy_bf), st), "dab_colsum_f32")   # + bf16 copy of dy
         d_w_out = torch.empty(D, ncat, device=dev_, dtype=f32)
         d_w_cat = torch.empty(n_proj, D, device=dev_, dtype=f32)
+        zeros = torch.empty(weights[6].numel() + weights[7].numel(), device=dev_, dtype=f32)
+        d_wpb = zeros[: weights[6].numel()].view_as(weights[6])
+        d_gamma = zeros[weights[6].numel():].view_as(weights[7])
         x2 = x.view(M, D)
         x_bf = torch.empty(M, D, device=dev_, dtype=bf)
+        # Everything that does not feed the main chain starts on the side streams right away: the fills of the split-K
+        # accumulators (a fill node between two kernels of a graph costs several microseconds of hand-over), the bias
+        # gradient, the bf16 copy of x.  The main chain begins with the one thing dcat needs: the bf16 copy of dy.
         side.wait_stream(main)
+        side2.wait_stream(main)
+        with torch.cuda.stream(side2):
+            zeros.zero_()
+            d_w_cat.zero_()
+            ev_fill = side2.record_event()
+            _lib.check(lib.dab_colsum_f32(ptr(dy2), M, D, ptr(d_b_out), None, _lib.stream_ptr()), "dab_colsum_f32")
+        _lib.check(lib.dab_cast_f32_to_bf16(ptr(dy2), ptr(dy_bf), dy2.numel(), st), "dab_cast_f32_to_bf16")
         with torch.cuda.stream(side):
             sst = _lib.stream_ptr()
-            _lib.check(lib.dab_gemm_bf16_tn(ptr(dy_bf), D, ptr(cat), ncat, ptr(d_w_out), ncat, D, ncat, M, sst),
-                       "dab_gemm_bf16_tn (dWout)")
+            d_w_out.zero_()
             _lib.check(lib.dab_cast_f32_to_bf16(ptr(x2), ptr(x_bf), x2.numel(), sst), "dab_cast_f32_to_bf16")
+            ev_xbf = side.record_event()
+            side.wait_stream(main)      # dy_bf
+            _lib.check(lib.dab_gemm_bf16_tn_acc(ptr(dy_bf), D, ptr(cat), ncat, ptr(d_w_out), ncat, D, ncat, M, sst),
+                       "dab_gemm_bf16_tn_acc (dWout)")
         dcat = torch.empty(M, ncat, device=dev_, dtype=f32)
         _lib.check(lib.dab_gemm_bf16(ptr(dy_bf), ptr(w_out_t), ptr(dcat), None, M, ncat, D, st), "dab_gemm_bf16 (dcat)")
         dproj = torch.empty(M, n_proj, device=dev_, dtype=bf)
         de = torch.empty_like(e)
-        zeros = torch.zeros(weights[6].numel() + weights[7].numel(), device=dev_, dtype=f32)   # one fill
-        d_wpb = zeros[: weights[6].numel()].view_as(weights[6])
-        d_gamma = zeros[weights[6].numel():].view_as(weights[7])
         bws = _lib.aligned_empty(max(lib.dab_ipa_bwd_sm100_workspace_bytes(ctypes.byref(dims)), 16), dev_)
         bwd_args = (ctypes.byref(dims), ptr(packed), ptr(e), ptr(r), ptr(dcat), ptr(saved), saved.numel(), ptr(dproj), ptr(de),
                     ptr(d_wpb), ptr(d_gamma), ptr(bws), bws.numel())
         _lib.check(lib.dab_ipa_bwd_sm100_main(*bwd_args, st), "dab_ipa_bwd_sm100_main")
         layer._last_bwd_ws = bws   # kept for tools/debug_bwd.py (intermediate buffers of the last backward)
-        # dproj is complete: three independent branches - dWcat (side), the to_pair_bias / gamma reductions (second side
-        # stream), dx (main)
-        side2 = _side_stream(dev_, 1)
+        # dproj is complete: three independent branches - dx (side), the to_pair_bias / gamma reductions (second side
+        # stream), dWcat (main)
         side.wait_stream(main)
         side2.wait_stream(main)
+        # the longer of the two GEMMs (dWcat, split over K) continues on the main stream without a stream hand-over
+        dx = torch.empty(B, L, D, device=dev_, dtype=f32)
         with torch.cuda.stream(side):
-            _lib.check(lib.dab_gemm_bf16_tn(ptr(dproj), n_proj, ptr(x_bf), D, ptr(d_w_cat), D, n_proj, D, M, _lib.stream_ptr()),
-                       "dab_gemm_bf16_tn (dWcat)")
+            _lib.check(lib.dab_gemm_bf16(ptr(dproj), ptr(w_cat_t), ptr(dx), None, M, D, n_proj, _lib.stream_ptr()),
+                       "dab_gemm_bf16 (dx)")
         with torch.cuda.stream(side2):
             _lib.check(lib.dab_ipa_bwd_sm100_finish(*bwd_args, _lib.stream_ptr()), "dab_ipa_bwd_sm100_finish")
-        dx = torch.empty(B, L, D, device=dev_, dtype=f32)
-        _lib.check(lib.dab_gemm_bf16(ptr(dproj), ptr(w_cat_t), ptr(dx), None, M, D, n_proj, st), "dab_gemm_bf16 (dx)")
+        main.wait_event(ev_fill)        # the fill of d_w_cat and the bf16 copy of x: long done
+        main.wait_event(ev_xbf)
+        _lib.check(lib.dab_gemm_bf16_tn_acc(ptr(dproj), n_proj, ptr(x_bf), D, ptr(d_w_cat), D, n_proj, D, M, st),
+                   "dab_gemm_bf16_tn_acc (dWcat)")
         main.wait_stream(side)
         main.wait_stream(side2)
         d_proj_w = torch.split(d_w_cat, [w.shape[0] for w in weights[:6]], dim=0)

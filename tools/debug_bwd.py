@@ -56,7 +56,7 @@ dims = _ipa_structs(layer, B, 128)
 bws = layer._last_bwd_ws
 ptrs = (ctypes.c_void_p * 10)()
 _lib.check(lib.dab_debug_bwd_sm100_buffers(ctypes.byref(dims), ctypes.c_void_p(bws.data_ptr()), ptrs), "buffers")
-offs = [p - bws.data_ptr() for p in ptrs]
+offs = [(p or 0) - bws.data_ptr() for p in ptrs]
 rows = B * 128
 
 
@@ -64,17 +64,13 @@ def view(k, nbytes, dtype, shape):
     return bws[offs[k]: offs[k] + nbytes].view(dtype).view(*shape)
 
 
-dO16 = view(0, rows * 8 * 64 * 2, torch.float16, (rows, 8, 64))
-dObf = view(1, rows * 8 * 64 * 2, torch.bfloat16, (rows, 8, 64))
-delta = view(3, rows * 8 * 4, torch.float32, (rows, 8))
-rscale = view(4, rows * 4, torch.float32, (rows,))
+dObf = view(1, rows * 8 * 64 * 2, torch.bfloat16, (rows, 8, 64))    # (the scaled fp16 copy, dopair, Delta stay in shared memory)
 Pn = view(5, B * 8 * 128 * 128 * 2, torch.bfloat16, (B, 8, 128, 128))
 dL = view(6, B * 8 * 128 * 128 * 2, torch.bfloat16, (B, 8, 128, 128))
 dQ = view(7, rows * 8 * 64 * 4, torch.float32, (rows, 8, 64))
 dK = view(8, rows * 8 * 64 * 4, torch.float32, (rows, 8, 64))
 dV = view(9, rows * 8 * 64 * 4, torch.float32, (rows, 8, 64))
 
-rel(dO16.float() * rscale[:, None, None], dObf.float(), "dO16*rscale vs dObf")
 # Delta_i,h = sum_j P dP = sum_j attn * dattn
 rel(Pn, attn, "P (normalised)")
 rel(dL, logit.grad, "dl")

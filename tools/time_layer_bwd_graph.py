@@ -21,6 +21,9 @@ gy = torch.randn(B, 128, 128, device=dev, generator=g)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 def step():
+    x.grad = None; e.grad = None
+    for p_ in layer.parameters():      # as after zero_grad(set_to_none=True): no accumulation kernels
+        p_.grad = None
     y = layer(x, e, R, t)
     y.backward(gy)
 

@@ -36,7 +36,9 @@ def show(k, prev, label):
     d = tl[:, k] - tl[:, prev]
     print(f"  {label:40s} mean {d.mean():9.0f}  p10 {d.quantile(0.1):9.0f}  p90 {d.quantile(0.9):9.0f}")
 print(f"{B*8} CTAs; cycles per phase:")
-show(1, 0, names[1]); show(2, 1, names[2]); show(4, 1, names[4])
+show(1, 0, names[1]); show(16, 1, "prologue: start"); show(18, 16, "prologue: loads + math (thread 0)")
+show(20, 18, "prologue: barrier, scale, stores")
+show(2, 1, names[2]); show(4, 1, names[4])
 prev = 4
 for n in range(8):
     show(8 + n, prev, f"group 0 row n={n} published"); prev = 8 + n
