@@ -708,11 +708,14 @@ ipa_bwd_keyside_kernel(const __grid_constant__ CUtensorMap map_pn, const __grid_
       }
     };
     auto store_scalars = [&](int seg, float scale) {
-      uint4* dst = reinterpret_cast<uint4*>(out + seg * NS + h * DS);
+      uint4* dst = reinterpret_cast<uint4*>(out + seg * NS + h * DS);      // 64 B, 32-byte aligned: two 256-bit stores
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        dst[q] = make_uint4(pack_bf162(U[8 * q] * scale, U[8 * q + 1] * scale), pack_bf162(U[8 * q + 2] * scale, U[8 * q + 3] * scale),
-                            pack_bf162(U[8 * q + 4] * scale, U[8 * q + 5] * scale), pack_bf162(U[8 * q + 6] * scale, U[8 * q + 7] * scale));
+      for (int q = 0; q < 2; ++q) {
+        uint32_t w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w[e] = pack_bf162(U[16 * q + 2 * e] * scale, U[16 * q + 2 * e + 1] * scale);
+        st_global_v8(dst + 2 * q, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+      }
     };
     // global-frame gradient gp[24] -> local frame (p_glob = p_loc R + t  =>  dp_loc = dp_glob R^T)
     auto store_points = [&](int seg, const float (&gp)[24]) {
@@ -724,11 +727,18 @@ ipa_bwd_keyside_kernel(const __grid_constant__ CUtensorMap map_pn, const __grid_
         loc[3 * p + 1] = x * Rm[3] + y * Rm[4] + z * Rm[5];
         loc[3 * p + 2] = x * Rm[6] + y * Rm[7] + z * Rm[8];
       }
+      // 48 B at a 16-byte aligned offset (48 h): one 256-bit store on the 32-byte aligned part, one 16-byte store
       uint4* dst = reinterpret_cast<uint4*>(out + 3 * NS + seg * NPT + h * 24);
+      uint32_t w[12];
 #pragma unroll
-      for (int q = 0; q < 3; ++q)
-        dst[q] = make_uint4(pack_bf162(loc[8 * q], loc[8 * q + 1]), pack_bf162(loc[8 * q + 2], loc[8 * q + 3]),
-                            pack_bf162(loc[8 * q + 4], loc[8 * q + 5]), pack_bf162(loc[8 * q + 6], loc[8 * q + 7]));
+      for (int e = 0; e < 12; ++e) w[e] = pack_bf162(loc[2 * e], loc[2 * e + 1]);
+      if (h & 1) {
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        st_global_v8(dst + 1, w[4], w[5], w[6], w[7], w[8], w[9], w[10], w[11]);
+      } else {
+        st_global_v8(dst, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+        dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+      }
     };
     auto load_points = [&](const __nv_bfloat16* src, float (&pt)[24]) {   // hi + lo of the packed row
       const uint4* r = reinterpret_cast<const uint4*>(src + row * (H * QK_W) + h * QK_W);

@@ -386,11 +386,12 @@ pair_embed_kernel(const __grid_constant__ CUtensorMap map_w, const uint8_t* __re
         const float rm = s_row[52] * resmask_j;
         uint4* dst = reinterpret_cast<uint4*>(e_out + ((int64_t)row * Lp + joff) * PE_C + half * 32);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float o[8];
+        for (int q = 0; q < 2; ++q) {     // 256-bit stores: one whole 32-byte sector per request
+          float o[16];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = (v[q * 8 + e] + s_bias[256 + half * 32 + q * 8 + e]) * rm;
-          dst[q] = make_uint4(pe_pk(o[0], o[1]), pe_pk(o[2], o[3]), pe_pk(o[4], o[5]), pe_pk(o[6], o[7]));
+          for (int e = 0; e < 16; ++e) o[e] = (v[q * 16 + e] + s_bias[256 + half * 32 + q * 16 + e]) * rm;
+          st_global_v8(dst + 2 * q, pe_pk(o[0], o[1]), pe_pk(o[2], o[3]), pe_pk(o[4], o[5]), pe_pk(o[6], o[7]),
+                       pe_pk(o[8], o[9]), pe_pk(o[10], o[11]), pe_pk(o[12], o[13]), pe_pk(o[14], o[15]));
         }
       }
       tcgen05_fence_before_sync();

@@ -224,14 +224,18 @@ pair_mlp_fwd_train_kernel(const __grid_constant__ CUtensorMap map_a1, const __gr
 #pragma unroll
         for (int k = 18; k < 24; ++k) f[k] = 0.f;
         uint4* dst = reinterpret_cast<uint4*>(xh_out + ((int64_t)row * MF_L + j) * MF_XW);
+        uint4 u[4];
 #pragma unroll
         for (int k8 = 0; k8 < 3; ++k8) {
-          const uint4 u = make_uint4(mf_pk(f[8 * k8], f[8 * k8 + 1]), mf_pk(f[8 * k8 + 2], f[8 * k8 + 3]),
-                                     mf_pk(f[8 * k8 + 4], f[8 * k8 + 5]), mf_pk(f[8 * k8 + 6], f[8 * k8 + 7]));
-          dst[k8] = u;                               // (the previous row's h1 chain has finished reading the tile: its
-          *reinterpret_cast<uint4*>(cs + S::kXh + swz128_offset(j, k8)) = u;   //  accumulator was waited for below)
+          u[k8] = make_uint4(mf_pk(f[8 * k8], f[8 * k8 + 1]), mf_pk(f[8 * k8 + 2], f[8 * k8 + 3]),
+                             mf_pk(f[8 * k8 + 4], f[8 * k8 + 5]), mf_pk(f[8 * k8 + 6], f[8 * k8 + 7]));
+          // (the previous row's h1 chain has finished reading the tile: its accumulator was waited for below)
+          *reinterpret_cast<uint4*>(cs + S::kXh + swz128_offset(j, k8)) = u[k8];
         }
-        dst[3] = make_uint4(0, 0, 0, 0);
+        u[3] = make_uint4(0, 0, 0, 0);
+        // the pair's 64-byte row as two 256-bit stores (whole sectors; 16-byte stores at a 64-byte lane stride are half sectors)
+        st_global_v8(dst, u[0].x, u[0].y, u[0].z, u[0].w, u[1].x, u[1].y, u[1].z, u[1].w);
+        st_global_v8(dst + 2, u[2].x, u[2].y, u[2].z, u[2].w, u[3].x, u[3].y, u[3].z, u[3].w);
         fence_proxy_async_smem();
         mbar_arrive(&cb[MF_XH_READY]);
       }
