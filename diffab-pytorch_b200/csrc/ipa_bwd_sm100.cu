@@ -116,7 +116,7 @@ enum BBar { BV_FULL = 0, BV_EMPTY = 4, BQ_FULL = 8, BS_DONE = 9, BE_FULL = 10, B
             PCAT_FREE = 28, DE_DONE = 32 /* [g] */, DE_FREE = 34 /* 128 arrivals */, B_N_BARS = 35 };
 
 // TMEM columns (256 per CTA): value part of dP for the 16 rows, ring of three pair parts, de, to_pair_bias gradient
-constexpr uint32_t kBColDPV = 0, kBColDPP = 128 /* 3 x 16 */, kBColDE = 176 /* 64 */, kBColWPB = 240 /* 8 */;
+constexpr uint32_t kBColDPV = 0, kBColDPP = 128 /* 3 x 16 */, kBColDE = 176 /* 64 */, kBColWPB = 240 /* 16 */;
 
 __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
   return make_uint4(pack_bf162(v[0], v[1]), pack_bf162(v[2], v[3]), pack_bf162(v[4], v[5]), pack_bf162(v[6], v[7]));
@@ -139,6 +139,7 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
   long long* dbg_cta = dbg ? dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
 #define BWD_STAMP(k) do { if (dbg_cta && threadIdx.x == 0) dbg_cta[(k)] = clock64(); } while (0)
 #define BWD_STAMP_ISSUER(k) do { if (dbg_cta && (threadIdx.x & 31) == 0) dbg_cta[(k)] = clock64(); } while (0)
+#define BWD_TIMED_WAIT(bar, par, acc) do { if (dbg_cta) { long long t0_ = clock64(); mbar_wait((bar), (par)); (acc) += clock64() - t0_; } else mbar_wait((bar), (par)); } while (0)
   BWD_STAMP(0);
   using S = BwdSmem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
@@ -169,16 +170,9 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
     fence_barrier_init();
     tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_e);
     for (int h = 0; h < S::kVBufs; ++h) load_v(h);
-#ifndef DAB_BWD_PF_ROWS
-#define DAB_BWD_PF_ROWS 16
-#endif
-#ifdef DAB_BWD_PF_DCAT
-    // the tile's own dcat / cat rows first (the prologue's loads then find them in L2)
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(dcat + row0 * NCAT), "r"(IB * NCAT * 4) : "memory");
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(cat + row0 * NCAT), "r"(IB * NCAT * 2) : "memory");
-#endif
-    // the first pair rows of the tile start their way HBM -> L2 now: the stream runs during the prologue
-    for (int r = 0; r < DAB_BWD_PF_ROWS; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
+    // every pair row of the tile starts its way HBM -> L2 now: the stream runs during the prologue (prefetching only the
+    // first 4 / 8 rows here, or the tile's dcat / cat rows first, changed nothing)
+    for (int r = 0; r < IB; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
   }
   // per-row constants of this CTA and the st * Wpb operand tile ([8 h][64 c] bf16, 128B-swizzled rows)
   if (tid < 128) s_inv[tid] = stats[(row0 + (tid >> 3)) * 16 + 8 + (tid & 7)];
@@ -209,18 +203,14 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
   if (warp == 9) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
-      if (DAB_BWD_PF_ROWS < IB) {      // the rest once the prologue's loads are through
-        mbar_wait(&bars[BQ_FULL], 0);
-        for (int r = DAB_BWD_PF_ROWS; r < IB; ++r) tma_prefetch_l2_2d(&map_e, 0, (int)((row0 + r) * L));
-      }
       for (int h = S::kVBufs; h < H; ++h) {
         mbar_wait(&bars[BV_EMPTY + h % S::kVBufs], ((h / S::kVBufs) - 1) & 1);
         load_v(h);
       }
       // ---- stage 2: pair rows + their dopair tiles (region X / P are free once every dPv MMA has completed)
       mbar_wait(&bars[BS_DONE], 0);
-      for (int r = 0; r < IB; ++r) {
-        const int s = r % S::kEStages;
+      for (int k2 = 0; k2 < IB; ++k2) {     // in issue order: the slots of a row pair are released together (Z MMAs below)
+        const int r = ord(k2), s = r % S::kEStages;
         if (r >= S::kEStages) mbar_wait(&bars[BE_EMPTY + s], ((r / S::kEStages) - 1) & 1);
         mbar_arrive_expect_tx(&bars[BE_FULL + s], S::kEStage);
         tma_load_2d(smem + s * S::kEStage, &map_e, &bars[BE_FULL + s], 0, (int)((row0 + r) * L));
@@ -233,7 +223,7 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
       constexpr uint32_t kIdescDPV = make_idesc_f16(128, 16, 0, 0);
       constexpr uint32_t kIdescDPP = make_idesc_bf16(128, 16, 0, 0);
       constexpr uint32_t kIdescDE = make_idesc_bf16(128, 64, 0, 1);    // B = [dopair_i ; st Wpb], MN-major
-      constexpr uint32_t kIdescZ = make_idesc_bf16(64, 8, 1, 1);       // A = e tile MN-major, B = dl chunk MN-major
+      constexpr uint32_t kIdescZ = make_idesc_bf16(128, 16, 1, 1);     // A = two e tiles MN-major, B = two dl chunks MN-major
       // ---- stage 1: dPv^T_h = V_h dO_h^T
       mbar_wait(&bars[BQ_FULL], 0);
       for (int h = 0; h < H; ++h) {
@@ -296,17 +286,26 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
           umma_bf16(tmem + kBColDE, da, db, kIdescDE, false);
         }
         umma_commit(&bars[DE_DONE + g]);
-        const uint32_t ea = smem_base + s * S::kEStage;
+        if (k & 1) {
+          // Z of the row PAIR at issue positions (k - 1, k) = rows (r - 2, r) = (group 0, group 1), same buffer slot:
+          // [Z_a ; Z_b] = [e_a | e_b]^T [dl_a | dl_b]  (M = 128: 64 channels of each row, N = 16: 8 heads of each row,
+          // K = 128 j) - a small tcgen05.mma costs ~60-80 issue cycles whatever its shape and this kernel's row loop is
+          // bound by them (13 per row before, 9 now); the off-diagonal blocks are computed and ignored.
+          // A: two e tiles read MN-major, two ring slots apart (LBO); B: two dl chunks [128 j][8 h] MN-major, no
+          //    swizzle: 8-row (K) groups 128 B apart (LBO), the second group's buffer 8192 B behind the first (SBO).
+          const uint32_t ea = smem_base + (s - 2) * S::kEStage;
+          const uint32_t pc0 = smem_base + S::kPcat + slot * 4096;      // group 0's [P | dl] buffer of this slot
 #pragma unroll
-        for (int kk = 0; kk < L / 16; ++kk) {
-          // A: e[i] tile read MN-major (M = c).  B: dl chunk [128 j][8 h] MN-major, no swizzle: 8-row (K) groups
-          //    128 B apart (LBO)
-          uint64_t da = make_smem_desc(ea + kk * 2048, 1024, 1024, kSwizzle128B);
-          uint64_t db = make_smem_desc(pc + 2048 + kk * 256, 128, 2048, kSwizzleNone);
-          umma_bf16(tmem + kBColWPB, da, db, kIdescZ, (k | kk) != 0);
+          for (int kk = 0; kk < L / 16; ++kk) {
+            uint64_t da = make_smem_desc(ea + kk * 2048, 2 * S::kEStage, 1024, kSwizzle128B);
+            uint64_t db = make_smem_desc(pc0 + 2048 + kk * 256, 128, 8192, kSwizzleNone);
+            umma_bf16(tmem + kBColWPB, da, db, kIdescZ, (k > 1) || (kk != 0));
+          }
+          umma_commit(&bars[BE_EMPTY + s - 2]);
+          umma_commit(&bars[BE_EMPTY + s]);
+          umma_commit(&bars[PCAT_FREE + slot]);
+          umma_commit(&bars[PCAT_FREE + 2 + slot]);
         }
-        umma_commit(&bars[BE_EMPTY + s]);
-        umma_commit(&bars[PCAT_FREE + g * 2 + slot]);
         }
         __syncwarp();
         if (k + 3 < IB) issue_dpp(k + 3);
@@ -445,6 +444,7 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
     mbar_wait(&bars[BS_DONE], 0);
     tcgen05_fence_after_sync();
     BWD_STAMP(4);
+    long long w_dpp = 0, w_pcat = 0, w_de = 0;
     for (int q = 0; q < IB / 4; ++q) {
       const uint4 u_use[2] = {u_nxt[0], u_nxt[1]};
       if (q + 1 < IB / 4) {
@@ -475,7 +475,7 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
           }
         }
         // pair part of dP for this row
-        mbar_wait(&bars[DPP_DONE + pos % 3], (pos / 3) & 1);
+        BWD_TIMED_WAIT(&bars[DPP_DONE + pos % 3], (pos / 3) & 1, w_dpp);
         tcgen05_fence_after_sync();
         float dpp[8];
         tmem_ld_x8(tmem_lane + kBColDPP + (pos % 3) * 16, dpp);
@@ -493,7 +493,7 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
             accg[h] = fmaf(dl[h], lm[h], accg[h]);
           }
         }
-        if (n >= 2) mbar_wait(&bars[PCAT_FREE + g * 2 + (n & 1)], ((n >> 1) - 1) & 1);
+        if (n >= 2) BWD_TIMED_WAIT(&bars[PCAT_FREE + g * 2 + (n & 1)], ((n >> 1) - 1) & 1, w_pcat);
         // ---- [P | dl] of this key: A operand of the de MMA, and (dl half) B operand of the Z MMA
         {
           uint8_t* pc = smem + S::kPcat + (g * 2 + (n & 1)) * 4096;
@@ -524,7 +524,7 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
         }
         // ---- de_i: TMEM -> bf16 -> 128 contiguous bytes per key; then hand the accumulator back
         {
-          mbar_wait(&bars[DE_DONE + g], n & 1);
+          BWD_TIMED_WAIT(&bars[DE_DONE + g], n & 1, w_de);
           tcgen05_fence_after_sync();
           uint4* dst = reinterpret_cast<uint4*>(de + ((row0 + i) * L + gt) * C);
 #pragma unroll
@@ -551,6 +551,7 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
       }
     }
     BWD_STAMP(5);
+    if (dbg_cta && tid == 0) { dbg_cta[21] = w_dpp; dbg_cta[22] = w_pcat; dbg_cta[23] = w_de; }
 
     // ---- sum_ij dl (l - m) per head (natural-log units) for dgamma
 #pragma unroll
@@ -565,16 +566,23 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
       for (int w = 0; w < 8; ++w) s += s_red[w * 8 + tid];
       p_g1[(size_t)cta * 8 + tid] = s * kLn2;
     }
-    // ---- to_pair_bias partial (M = 64: channel c = 16 gw + lane in lanes 0-15)
+    // ---- to_pair_bias partial: TMEM lane = channel c of the pair's first row (lanes 0-63, columns 0-7) / second row
+    //      (lanes 64-127, columns 8-15); the two halves meet in shared memory (the [P | dl] buffers are idle by now)
     if (g == 1) {
-      mbar_wait(&bars[PCAT_FREE + 3], 1);   // 4th completion of [g=1][slot=1]: commit behind the Z MMAs of the last row
+      mbar_wait(&bars[PCAT_FREE + 3], 1);   // 4th completion of [g=1][slot=1]: commit behind the Z MMAs of the last row pair
       tcgen05_fence_after_sync();
       float z[8];
-      tmem_ld_x8(tmem_lane + kBColWPB, z);
+      tmem_ld_x8(tmem_lane + kBColWPB + (gt >> 6) * 8, z);
       tmem_wait_ld();
-      if (lane < 16) {
+      float* s_z = reinterpret_cast<float*>(smem + S::kPcat);      // [64 c][8 h]
+      if (gt >= 64) {
 #pragma unroll
-        for (int h = 0; h < H; ++h) p_wpb[(size_t)cta * 512 + h * C + gw * 16 + lane] = z[h];
+        for (int h = 0; h < H; ++h) s_z[(gt - 64) * 8 + h] = z[h];
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (gt < 64) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) p_wpb[(size_t)cta * 512 + h * C + gt] = z[h] + s_z[gt * 8 + h];
       }
     }
     BWD_STAMP(6);
@@ -584,6 +592,7 @@ ipa_bwd_core_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_cons
   BWD_STAMP(7);
 #undef BWD_STAMP
 #undef BWD_STAMP_ISSUER
+#undef BWD_TIMED_WAIT
   if (warp == 0) tmem_free(tmem, 256);
 }
 

@@ -43,6 +43,7 @@ prev = 4
 for n in range(8):
     show(8 + n, prev, f"group 0 row n={n} published"); prev = 8 + n
 show(5, 15, names[5]); show(6, 5, names[6]); show(7, 6, names[7])
+print(f"group 0 thread 0 waits over the 8 rows (cycles): dPp done {tl[:,21].float().mean():.0f}, [P|dl] slot free {tl[:,22].float().mean():.0f}, de done {tl[:,23].float().mean():.0f}")
 print(f"total per CTA: mean {(tl[:,7]-tl[:,0]).mean():.0f}")
 print("issuer stage 2 steps (k = issue order):")
 prev = 2
