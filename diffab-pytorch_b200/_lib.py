@@ -66,8 +66,6 @@ EXPORTS = {
     "dab_seq_probs": (c_int, [POINTER(DabSchedule), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                               c_void_p, c_void_p]),
     "dab_reverse_step": (c_int, [POINTER(DabSchedule)] + [c_void_p] * 8 + [c_int, c_int] + [c_void_p] * 8),
-    "dab_igso3_reverse_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float] + [c_void_p] * 4 + [POINTER(DabSchedule)] +
-                               [c_void_p] * 8 + [c_int, c_int] + [c_void_p] * 6),
     "dab_ipa_f32_workspace_bytes": (c_size_t, [POINTER(DabIpaDims), c_int]),
     "dab_ipa_fwd_f32": (c_int, [POINTER(DabIpaDims), POINTER(DabIpaWeights), c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_size_t, c_int, c_void_p]),

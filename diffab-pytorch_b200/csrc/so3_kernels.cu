@@ -7,7 +7,6 @@
 #include <math_constants.h>
 
 #include "common.cuh"
-#include "step_device.cuh"
 
 namespace dab {
 
@@ -205,28 +204,6 @@ __global__ void __launch_bounds__(kSortThreads) igso3_sample_kernel(
               rotvec + (int64_t)b * L * 3, bins, smem_raw);
 }
 
-// IGSO(3) draw + reverse step of a patch in ONE launch (the tail of a sampling step): the block draws the patch's L
-// rotation vectors into shared memory, then thread j applies the reverse update of residue (b, j) (step_device.cuh).
-constexpr int kStepMaxL = 512;
-__global__ void __launch_bounds__(kSortThreads) igso3_reverse_step_kernel(
-    const float* __restrict__ hist, const float* __restrict__ sigmas, int n_bins, int n_sigma, int n_pow2, int L,
-    const float* __restrict__ axis_noise, const float* __restrict__ exp_noise, const float* __restrict__ jitter,
-    const float* __restrict__ gauss, float thr, double binsize, Sched sc, const int64_t* seq_t, const float* x_t,
-    const float* O_t, const float* __restrict__ eps_theta, const float* __restrict__ v_theta,
-    const float* __restrict__ seq_post, const uint8_t* __restrict__ mask, const int64_t* __restrict__ t,
-    const float* __restrict__ seq_exp, const float* __restrict__ z, int64_t* seq_out, float* x_out, float* O_out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float s_rv[kStepMaxL * 3];
-  const int b = blockIdx.x;
-  igso3_block(hist, sigmas, n_bins, n_sigma, n_pow2, t, b, L, axis_noise, exp_noise, jitter, gauss, thr, binsize, s_rv, nullptr,
-              smem_raw);
-  __syncthreads();
-  const int tt = (int)t[b];
-  for (int j = threadIdx.x; j < L; j += blockDim.x)
-    reverse_update_residue(sc, (int64_t)b * L + j, tt, seq_t, x_t, O_t, eps_theta, v_theta, seq_post, mask, seq_exp, z,
-                           s_rv + j * 3, seq_out, x_out, O_out, nullptr);
-}
-
 }  // namespace dab
 
 using namespace dab;
@@ -281,36 +258,5 @@ int dab_igso3_sample(const float* hist, const float* sigmas, int n_sigma, int n_
   return check_launch("dab_igso3_sample");
 }
 
-
-/* The tail of a sampling step in one launch: IGSO(3) draw (dab_igso3_sample with sigma_idx = t) followed by the reverse update
- * (dab_reverse_step) of every residue - the rotation-vector draws stay in shared memory.  Same arguments, same results. */
-int dab_igso3_reverse_step(const float* hist, const float* sigmas, int n_sigma, int n_bins, float sigma_threshold,
-                           const float* axis_noise, const float* exp_noise, const float* jitter, const float* gauss,
-                           const DabSchedule* sched, const int64_t* seq_t, const float* x_t, const float* O_t,
-                           const float* eps_theta, const float* v_theta, const float* seq_post, const uint8_t* mask,
-                           const int64_t* t, int B, int L, const float* seq_exp, const float* z, int64_t* seq_out,
-                           float* x_out, float* O_out, void* stream) {
-  DAB_REQUIRE(sched && sched->alpha && sched->alpha_bar && sched->alpha_bar_sqrt && sched->one_minus_alpha_bar_sqrt &&
-                  sched->beta && sched->T > 0,
-              DAB_EINVAL, "dab_igso3_reverse_step: incomplete schedule");
-  DAB_REQUIRE(hist && sigmas && axis_noise && exp_noise && jitter && gauss && seq_t && x_t && O_t && eps_theta && v_theta &&
-                  seq_post && mask && t && seq_exp && z && seq_out && x_out && O_out,
-              DAB_EINVAL, "dab_igso3_reverse_step: null pointer");
-  DAB_REQUIRE(B >= 0 && L >= 0 && n_bins > 0 && n_sigma > 0, DAB_EINVAL, "dab_igso3_reverse_step: bad sizes");
-  if (B == 0 || L == 0) return DAB_OK;
-  DAB_REQUIRE(L <= n_bins && L <= kStepMaxL, DAB_EUNSUPPORTED, "dab_igso3_reverse_step: L = %d must not exceed %d (and n_bins)", L,
-              kStepMaxL);
-  int n_pow2 = 1;
-  while (n_pow2 < n_bins) n_pow2 <<= 1;
-  DAB_REQUIRE(n_pow2 <= 16384, DAB_EUNSUPPORTED, "dab_igso3_reverse_step: n_bins > 16384 does not fit shared memory");
-  const Sched sc{sched->T, sched->alpha, sched->alpha_bar, sched->alpha_bar_sqrt, sched->one_minus_alpha_bar_sqrt, sched->beta};
-  DAB_ENSURE_SMEM(igso3_reverse_step_kernel, 16384 * 8);
-  igso3_reverse_step_kernel<<<B, kSortThreads, (size_t)n_pow2 * 8, (cudaStream_t)stream>>>(
-      hist, sigmas, n_bins, n_sigma, n_pow2, L, axis_noise, exp_noise, jitter, gauss, sigma_threshold,
-      3.14159265358979323846 / (double)n_bins, sc, seq_t, x_t, O_t, eps_theta, v_theta, seq_post, mask, t, seq_exp, z, seq_out,
-      x_out, O_out);
-  count_launch();
-  return check_launch("dab_igso3_reverse_step");
-}
 
 }  // extern "C"

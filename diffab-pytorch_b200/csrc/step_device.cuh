@@ -1,5 +1,5 @@
-// Device-side pieces shared by the diffusion kernels (diffusion_kernels.cu) and the fused IGSO(3) draw + reverse step
-// (so3_kernels.cu): the schedule view, the categorical draw and the per-residue reverse update.
+// Device-side pieces of the diffusion kernels (diffusion_kernels.cu): the schedule view, the categorical draw and the
+// per-residue reverse update.
 #pragma once
 #include "common.cuh"
 

@@ -192,15 +192,6 @@ def fused_reverse_step(dsched, so3_rev, seq_t, x_t, O_t, eps_theta, v_theta, seq
         s_out, x_out, O_out = seq_t, x_t, O_t
     else:
         s_out, x_out, O_out = torch.empty_like(seq_t), torch.empty_like(x_t), torch.empty_like(O_t)
-    if not return_O0 and L <= 512 and all(k in noise for k in ("axis", "hist_exp", "jitter", "gauss")):
-        # IGSO(3) draw + update of every residue in one launch (block = patch; the draws stay in shared memory)
-        f = lambda k: _lib.dev(noise[k], torch.float32, k)
-        _lib.check(_lib.lib().dab_igso3_reverse_step(
-            ptr(so3_rev.histograms), ptr(so3_rev.sigmas_to_consider), so3_rev.sigmas_to_consider.numel(), so3_rev.n_bins,
-            float(so3_rev.sigma_threshold), ptr(f("axis")), ptr(f("hist_exp")), ptr(f("jitter")), ptr(f("gauss")), dsched.ref(),
-            ptr(seq_t), ptr(x_t), ptr(O_t), ptr(eps_theta), ptr(v_theta), ptr(seq_post), ptr(m), ptr(t), B, L, ptr(seq_exp),
-            ptr(z), ptr(s_out), ptr(x_out), ptr(O_out), _lib.stream_ptr()), "dab_igso3_reverse_step")
-        return {"seq_idx": s_out, "translations": x_out, "orientations": O_out}
     rotvec = so3_rev.sample_isotropic_gaussian(t, L, noise=noise)
     O0 = torch.empty_like(O_t) if return_O0 else None
     _lib.check(_lib.lib().dab_reverse_step(dsched.ref(), ptr(seq_t), ptr(x_t), ptr(O_t), ptr(eps_theta), ptr(v_theta),

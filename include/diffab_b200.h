@@ -105,15 +105,6 @@ int dab_reverse_step(const DabSchedule* sched, const int64_t* seq_t, const float
                      const uint8_t* mask, const int64_t* t, int B, int L, const float* seq_exp,
                      const float* z, const float* rotvec, int64_t* seq_out, float* x_out, float* O_out,
                      float* O0_out, void* stream);
-/* The tail of a sampling step in ONE launch: the IGSO(3) draw (dab_igso3_sample with sigma_idx = t, so3.py:98-126) followed by
- * the reverse update of every residue (dab_reverse_step) - block = patch, the rotation-vector draws stay in shared memory.
- * Same arguments, same results as the two calls (no orientations_t0 output).  L <= 512. */
-int dab_igso3_reverse_step(const float* hist, const float* sigmas, int n_sigma, int n_bins, float sigma_threshold,
-                           const float* axis_noise, const float* exp_noise, const float* jitter, const float* gauss,
-                           const DabSchedule* sched, const int64_t* seq_t, const float* x_t, const float* O_t,
-                           const float* eps_theta, const float* v_theta, const float* seq_post, const uint8_t* mask,
-                           const int64_t* t, int B, int L, const float* seq_exp, const float* z, int64_t* seq_out,
-                           float* x_out, float* O_out, void* stream);
 
 /* ------------------------------------------------------------------ invariant point attention */
 /* One InvariantPointAttentionLayer (diffab_pytorch.py:339-465, use_pair_bias=True).
