@@ -23,6 +23,7 @@ inline int check_launch(const char* what) {
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }   // 256-bit stores
 
 // Opt a kernel in to `bytes` of dynamic shared memory once per (kernel, device): the attribute is per device, and the
 // library may be called from several host threads (an atomic bit mask per call site; a repeated set is harmless).

@@ -889,8 +889,8 @@ static int bwd_sm100_impl(const DabIpaDims* d, const void* packed, const void* e
               DAB_EINVAL, "dab_ipa_bwd_sm100: null pointer");
   DAB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0 && (reinterpret_cast<uintptr_t>(saved) & 1023) == 0 &&
                   (reinterpret_cast<uintptr_t>(e_bf16) & 127) == 0 && (reinterpret_cast<uintptr_t>(de_bf16) & 127) == 0 &&
-                  aligned16(dcat) && aligned16(dproj_bf16),
-              DAB_EINVAL, "dab_ipa_bwd_sm100: misaligned pointer (workspaces 1024 B, e/de 128 B, dcat/dproj 16 B)");
+                  aligned16(dcat) && aligned32(dproj_bf16),
+              DAB_EINVAL, "dab_ipa_bwd_sm100: misaligned pointer (workspaces 1024 B, e/de 128 B, dcat 16 B, dproj 32 B)");
   const int B = d->B, M = B * L;
   Ws ws = carve_ws(B, saved);
   BwdWs bw = carve_bwd(B, workspace);

@@ -431,9 +431,9 @@ int dab_pair_embed_fwd_sm100(const void* packed, const int64_t* seq_masked, cons
   if (B == 0) return DAB_OK;
   DAB_REQUIRE(packed && seq_masked && xyz && pairwise_dihedrals && residue_idx && chain_idx && atom_mask && e_bf16, DAB_EINVAL,
               "dab_pair_embed_fwd_sm100: null pointer");
-  DAB_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 1023) == 0 && aligned16(e_bf16) &&
+  DAB_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 1023) == 0 && aligned32(e_bf16) &&
                   (reinterpret_cast<uintptr_t>(pairwise_dihedrals) & 7) == 0,
-              DAB_EINVAL, "dab_pair_embed_fwd_sm100: misaligned pointer (packed 1024 B, e 16 B, dihedrals 8 B)");
+              DAB_EINVAL, "dab_pair_embed_fwd_sm100: misaligned pointer (packed 1024 B, e 32 B, dihedrals 8 B)");
   CUtensorMap mw;
   uint64_t dims[2] = {256, 320}, strides[1] = {512};
   uint32_t box[2] = {64, 64};

@@ -318,9 +318,9 @@ int dab_pair_mlp_fwd_train_sm100(const void* a1_bf16, const float* pairwise_dihe
                   w5_bf16 && bias3 && fd_bf16 && h1_bf16 && h2_bf16 && out_bf16 && xh_bf16,
               DAB_EINVAL, "dab_pair_mlp_fwd_train_sm100: null pointer");
   DAB_REQUIRE(aligned16(a1_bf16) && aligned16(t_type_bf16) && aligned16(t_rel_bf16) && aligned16(w5_bf16) && aligned16(fd_bf16) &&
-                  aligned16(h1_bf16) && aligned16(h2_bf16) && aligned16(out_bf16) && aligned16(xh_bf16) &&
+                  aligned16(h1_bf16) && aligned16(h2_bf16) && aligned16(out_bf16) && aligned32(xh_bf16) &&
                   (reinterpret_cast<uintptr_t>(pairwise_dihedrals) & 7) == 0,
-              DAB_EINVAL, "dab_pair_mlp_fwd_train_sm100: pointers must be 16-byte aligned");
+              DAB_EINVAL, "dab_pair_mlp_fwd_train_sm100: pointers must be 16-byte aligned (xh: 32)");
   const int n_rows = B * L;
   const uint64_t P = (uint64_t)n_rows * L;
   CUtensorMap maps[5];

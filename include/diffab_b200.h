@@ -10,7 +10,8 @@
  * Conventions
  *  - Every pointer is a DEVICE pointer owned by the caller; the library never allocates, frees or
  *    retains memory.  Tensors are contiguous in the layouts given; float pointers must be 16-byte
- *    aligned (bf16 pair tensors handed to the TMA path: 128-byte aligned).
+ *    aligned (bf16 pair tensors handed to the TMA path: 128-byte aligned; bf16 outputs written with 256-bit stores -
+ *    dproj_bf16 of the backward, the pair tensor of dab_pair_embed_fwd_sm100, xh_bf16 of the pair-MLP forward: 32-byte).
  *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), does no host
  *    synchronisation and no allocation, and is CUDA-graph capturable.
  *  - Return value: 0 on success, negative DAB_E* code otherwise; dab_last_error() gives a
