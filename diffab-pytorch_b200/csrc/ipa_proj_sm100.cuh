@@ -278,6 +278,8 @@ ipa_proj_kernel(const __grid_constant__ CUtensorMap map_w64, const __grid_consta
     // drops its segment into a warp-private [32 rows][64 B] shared-memory tile (64B swizzle: conflict-free 16-byte
     // stores) and lane 0 hands the tile to the TMA as a 2-D store (row pitch = the packed row).  Two tiles per warp
     // and round; a round = fill, fence, __syncwarp, issue - no block-level barrier anywhere in the epilogue.
+    // (Measured at B = 256 with the fused to_out phase: 48.1 us this way, 52.5 us with two 256-bit stores per thread and
+    // segment instead, 33.9 us without any output store: the packed operands' write-back costs ~14 us of the kernel.)
     uint8_t* stg = smem + S::kStage + warp * 4096;            // 2 x 2 KB
     const int lrow = gt & 31, grow0 = b * L + (gt & ~31);     // row inside the warp's tile; first row of the tile
     // The two staging tiles of a warp alternate: a tile is refilled as soon as every bulk group but the most recent one

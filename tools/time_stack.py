@@ -59,3 +59,11 @@ alg = B * (128 * 128 * 64 + 2 * 128 * 128 + 12 * 128) * 2 + 303752 * 4
 us = ts[len(ts) // 2]
 print(f"B={B}: {us:.1f} us per layer (median of 20 replays of {NL} layers; min {ts[0]:.1f}); 8(d) bytes {alg / 1e6:.1f} MB -> "
       f"{alg / us / 1e3:.0f} GB/s = {alg / us / 1e3 / peak:.3f} of {peak:.0f} GB/s; finite={bool(torch.isfinite(y).all())}")
+if os.environ.get("KERNELS") == "1":     # per-kernel device times inside the replays (CUPTI through torch.profiler)
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+    for ev in sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:6]:
+        print(f"    {ev.device_time_total / ev.count:8.1f} us x{ev.count:<3d} {ev.key[:90]}")
