@@ -1613,15 +1613,25 @@ class DiffAb(nn.Module):
         schedule's beta at ``t`` when the caller has already gathered it."""
         if beta is None:
             beta = self.dsched.tensors["beta"][t]
+        rotvec = None
         if glue_cache is not None:
+            # the step's IGSO(3) draw depends on t and the noise only: it runs on a side stream beside the epsilon network
+            # (a parallel branch of the step graph) instead of between the heads and the update
+            B, L = seq_idx_t.shape
+            rotvec = torch.empty(B, L, 3, device=seq_idx_t.device, dtype=torch.float32)
+            main, side = torch.cuda.current_stream(seq_idx_t.device), _side_stream(seq_idx_t.device, 2)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.so3_reverse.sample_isotropic_gaussian(t, L, noise=noise, out=rotvec)
             eps, v_eps, post = self.denoiser.heads_fast(seq_idx_t, translations_t, orientations_t, glue_cache,
                                                         pair_context_emb, beta, pair_bias)
+            main.wait_stream(side)
         else:
             eps, v_eps, post = self.denoiser.heads(seq_idx_t, translations_t, orientations_t, res_context_emb,
                                                    pair_context_emb, beta, pair_bias)
         return _diffusion.fused_reverse_step(self.dsched, self.so3_reverse, seq_idx_t, translations_t,
                                              orientations_t, eps, v_eps, post, generation_mask, t, noise,
-                                             inplace=inplace)
+                                             inplace=inplace, rotvec=rotvec)
 
     @torch.no_grad()
     def sample_from_context(self, seq_idx, translations, orientations, res_context_emb, pair_context_emb,

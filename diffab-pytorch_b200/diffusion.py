@@ -175,8 +175,9 @@ def fused_add_noise(dsched, so3_table, seq0, x0, O0, generation_mask, t, noise):
 
 
 def fused_reverse_step(dsched, so3_rev, seq_t, x_t, O_t, eps_theta, v_theta, seq_post, generation_mask, t, noise,
-                       inplace=False, return_O0=False):
-    """Reverse step (oracle/sampler.py; not in the reference): IGSO(3) sampler + one fused kernel."""
+                       inplace=False, return_O0=False, rotvec=None):
+    """Reverse step (oracle/sampler.py; not in the reference): IGSO(3) sampler + one fused kernel.  ``rotvec``: the step's
+    IGSO(3) draw when the caller has already made it (it depends on t and the noise only, not on the network)."""
     seq_t = _lib.dev(seq_t, torch.int64, "seq_idx_t")
     x_t = _lib.dev(x_t, torch.float32, "translations_t")
     O_t = _lib.dev(O_t, torch.float32, "orientations_t")
@@ -192,7 +193,9 @@ def fused_reverse_step(dsched, so3_rev, seq_t, x_t, O_t, eps_theta, v_theta, seq
         s_out, x_out, O_out = seq_t, x_t, O_t
     else:
         s_out, x_out, O_out = torch.empty_like(seq_t), torch.empty_like(x_t), torch.empty_like(O_t)
-    rotvec = so3_rev.sample_isotropic_gaussian(t, L, noise=noise)
+    if rotvec is None:
+        rotvec = so3_rev.sample_isotropic_gaussian(t, L, noise=noise)
+    rotvec = _lib.dev(rotvec, torch.float32, "rotvec")
     O0 = torch.empty_like(O_t) if return_O0 else None
     _lib.check(_lib.lib().dab_reverse_step(dsched.ref(), ptr(seq_t), ptr(x_t), ptr(O_t), ptr(eps_theta), ptr(v_theta),
                                            ptr(seq_post), ptr(m), ptr(t), B, L, ptr(seq_exp), ptr(z), ptr(rotvec),

@@ -189,14 +189,19 @@ class SO3:
         }
 
     def sample_isotropic_gaussian(self, sigma_idx: torch.LongTensor, num_samples: int, noise=None,
-                                  return_bins=False) -> torch.FloatTensor:
-        """so3.py:98-126: (n,) indices -> (n, num_samples, 3) rotation vectors."""
+                                  return_bins=False, out=None) -> torch.FloatTensor:
+        """so3.py:98-126: (n,) indices -> (n, num_samples, 3) rotation vectors (written into ``out`` when given)."""
         idx = _lib.dev(sigma_idx, torch.int64, "sigma_idx")
         n = idx.numel()
         if noise is None:
             noise = self.draw_noise(n, num_samples)
         f = lambda k: _lib.dev(noise[k], torch.float32, k)
-        out = torch.empty(n, num_samples, 3, device=self.device, dtype=torch.float32)
+        if out is None:
+            out = torch.empty(n, num_samples, 3, device=self.device, dtype=torch.float32)
+        else:
+            out = _lib.dev(out, torch.float32, "out")
+            if out.numel() != n * num_samples * 3:
+                raise ValueError("sample_isotropic_gaussian: out must hold (n, num_samples, 3) floats")
         bins = torch.empty(n, num_samples, device=self.device, dtype=torch.int64) if return_bins else None
         _lib.check(_lib.lib().dab_igso3_sample(
             ptr(self.histograms), ptr(self.sigmas_to_consider), self.sigmas_to_consider.numel(), self.n_bins,
