@@ -113,6 +113,13 @@ def test_igso3_sampler_bins_bit_exact_and_angles():
                                                   return_bins=True)
     assert torch.equal(bins.cpu(), ref_bins)                  # integer work: bit-exact, both sigma branches
     assert (got.cpu() - ref).abs().max() < 1e-5
+    # the sampling loop's form: the draw written into a caller's buffer (made on a side stream beside the epsilon network)
+    buf = torch.empty(4, 128, 3, device=DEV)
+    ret = sampler.sample_isotropic_gaussian(t.to(DEV), 128, noise={k: v.to(DEV) for k, v in noise.items()}, out=buf)
+    assert ret.data_ptr() == buf.data_ptr() and torch.equal(buf, got)
+    with pytest.raises(ValueError):
+        sampler.sample_isotropic_gaussian(t.to(DEV), 128, noise={k: v.to(DEV) for k, v in noise.items()},
+                                          out=torch.empty(4, 64, 3, device=DEV))
     # ragged / edge sizes: L = 1, L = 37, B = 1
     for B, L in ((1, 1), (3, 37)):
         tt = torch.tensor([1, 5, 100][:B])

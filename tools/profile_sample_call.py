@@ -49,3 +49,11 @@ rest = sorted(((t, k, c) for k, t, c in rows if not any(s in k for s in step_ker
 print(f"device time in the reverse steps' kernels: {steps / 1e3:.2f} ms; everything else: {sum(t for t, _, _ in rest) / 1e3:.2f} ms")
 for t, k, c in rest[:25]:
     print(f"  {t / 1e3:8.3f} ms  x{c:<4d} {k[:110]}")
+if os.environ.get("SHAPES") == "1":      # which copies / conversions make up aten::copy_
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof2:
+        call()
+        torch.cuda.synchronize()
+    big = [(e.self_device_time_total, e.key, str(e.input_shapes)[:90], e.count)
+           for e in prof2.key_averages(group_by_input_shape=True) if e.key in ("aten::copy_", "aten::mul", "aten::cat")]
+    for t, k, shp, c in sorted(big, reverse=True)[:14]:
+        print(f"  {t / 1e3:8.3f} ms  x{c:<3d} {k} {shp}")
