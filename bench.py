@@ -605,7 +605,7 @@ def measure_train_step(dev, dist, world, shapes, B=64, steps=5, warmup=3):
     Device time over `steps` steps (CUDA events), max over ranks; weak scaling (every rank has its own 64 patches)."""
     from diffab_pytorch_b200 import synth
     from diffab_pytorch_b200.diffab_pytorch import DiffAb
-    from diffab_pytorch_b200.distributed import GradientBucket, GraphedTrainStep, diffab_loss_terms
+    from diffab_pytorch_b200.distributed import FlatAdam, GradientBucket, GraphedTrainStep, diffab_loss_terms
     rank = dist.get_rank() if dist is not None else 0
     model = DiffAb(*TRAIN_CFG, device=dev).train()
     model.load_state_dict(synth.synthetic_state(shapes, seed=0))
@@ -615,7 +615,9 @@ def measure_train_step(dev, dist, world, shapes, B=64, steps=5, warmup=3):
     prev_prec = torch.get_float32_matmul_precision()
     torch.set_float32_matmul_precision("high")
     bucket = GradientBucket(model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True, fused=True)   # (PyTorch's single-kernel Adam)
+    # Adam over ONE flat parameter that aliases all 106 weight tensors (its gradient is the bucket): one elementwise pass
+    # of the library's kernel (distributed.FlatAdam = torch.optim.Adam's update, step count on the device)
+    opt = FlatAdam(bucket, lr=1e-4)
     batch = {k: v.to(dev) for k, v in synth.make_patches(B, L, seed=2000 + rank, with_distmat=False).items()}
     batch["distmat"] = torch.cat([synth.pairwise_atom_distances(batch["xyz"][i:i + 8]) for i in range(0, B, 8)])
     group = dist.group.WORLD if dist is not None else None

@@ -104,11 +104,53 @@ __global__ void __launch_bounds__(128) losses_bwd_kernel(const float* __restrict
       d_O[r * 9 + i * 3 + j] = m ? 2.f * gr * (D[j * 3] * T[i * 3] + D[j * 3 + 1] * T[i * 3 + 1] + D[j * 3 + 2] * T[i * 3 + 2]) : 0.f;
 }
 
+// Adam on one flat fp32 parameter vector (torch.optim.Adam with capturable=True, diffab_pytorch.py:925-931 of the
+// reference's configure_optimizers): step count on the device (already incremented by the caller), L2 weight decay added
+// to the gradient, bias-corrected first / second moments.  HBM-bound: 16 B read + 12 B written per element, float4 per thread.
+__global__ void __launch_bounds__(256) adam_flat_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                                                        float4* __restrict__ v, const float* __restrict__ step, float lr, float b1,
+                                                        float b2, float eps, float wd, int64_t n4) {
+  const float t = __ldg(step);
+  const float bc1 = 1.0f - powf(b1, t), bc2 = 1.0f - powf(b2, t);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+    float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = ga[k] + wd * pa[k];
+      ma[k] = b1 * ma[k] + (1.0f - b1) * gk;
+      va[k] = b2 * va[k] + (1.0f - b2) * gk * gk;
+      pa[k] -= step_size * ma[k] / (sqrtf(va[k]) * inv_sqrt_bc2 + eps);
+    }
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+}
+
 }  // namespace dab
 
 using namespace dab;
 
 extern "C" {
+
+/* One Adam step on a flat parameter vector: p, m, v updated in place from the gradient g (n fp32 elements each, n % 4 == 0,
+ * 16-byte aligned); `step` = device scalar (float) holding the step count INCLUDING this step (the caller increments it:
+ * the call is graph-capturable and has no host state).  torch.optim.Adam semantics (L2 weight decay, bias corrections). */
+int dab_adam_flat(float* p, const float* g, float* m, float* v, const float* step, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int64_t n, void* stream) {
+  DAB_REQUIRE(p && g && m && v && step, DAB_EINVAL, "dab_adam_flat: null pointer");
+  DAB_REQUIRE(n >= 0 && n % 4 == 0 && aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), DAB_EINVAL,
+              "dab_adam_flat: n %% 4 == 0 and 16-byte aligned vectors required");
+  if (n == 0) return DAB_OK;
+  const int64_t n4 = n / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_flat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+      reinterpret_cast<float4*>(v), step, lr, beta1, beta2, eps, weight_decay, n4);
+  count_launch();
+  return check_launch("dab_adam_flat");
+}
 
 /* out[0..2] = (sequence KL, translation MSE, orientation) losses of DiffAb._shared_step (diffab_pytorch.py:856-880), each the
  * masked sum over the n = B*L residues divided by out[3] = the number of masked residues.  post_*[n,21], eps_*[n,3],

@@ -88,6 +88,25 @@ class GradientBucket:
             p.grad = self.flat[off: off + p.numel()].view_as(p)
             off += p.numel()
 
+    def flatten_parameters(self) -> torch.nn.Parameter:
+        """Move the parameters into ONE flat buffer - every parameter becomes a view of it; names, shapes and the
+        state_dict are unchanged - and return the buffer as a single ``Parameter`` whose gradient is the bucket.  An
+        optimizer built over ``[that parameter]`` updates all weights in one elementwise pass (PyTorch's fused Adam walks
+        the 106 small tensors chunk by chunk: ~165 us per step against ~10 us).  Call it BEFORE constructing the optimizer,
+        and only with elementwise optimizers (Adam / AdamW / SGD: the update of an element depends on that element alone,
+        so the result is the per-tensor one, bit for bit)."""
+        flat_p = torch.empty_like(self.flat)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                n = p.numel()
+                flat_p[off: off + n].copy_(p.detach().reshape(-1))
+                p.data = flat_p[off: off + n].view_as(p)
+                off += n
+        self.flat_param = torch.nn.Parameter(flat_p, requires_grad=True)
+        self.flat_param.grad = self.flat
+        return self.flat_param
+
     def zero(self):
         self.flat.zero_()
 
@@ -106,6 +125,47 @@ class GradientBucket:
         _, world = world_info(group)
         if world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+
+
+class FlatAdam:
+    """Adam (``torch.optim.Adam`` semantics: L2 weight decay, bias corrections) on ``GradientBucket.flatten_parameters()``:
+    ONE launch of the library's elementwise kernel (``dab_adam_flat``) per step - the step count lives on the device, so
+    the step is CUDA-graph capturable.  PyTorch's fused Adam on the same flat tensor walks it in 64K-element chunks,
+    one block each (39 blocks for DiffAb's 2.5 M weights: ~73 us); on the 106 separate tensors ~165 us."""
+
+    def __init__(self, bucket: "GradientBucket", lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        if getattr(bucket, "flat_param", None) is None:
+            bucket.flatten_parameters()
+        self.bucket = bucket
+        p = bucket.flat_param
+        if not p.is_cuda or p.dtype != torch.float32 or p.numel() % 4 != 0:
+            raise ValueError("FlatAdam: needs a CUDA fp32 flat parameter with a multiple of 4 elements")
+        self.exp_avg, self.exp_avg_sq = torch.zeros_like(p.data), torch.zeros_like(p.data)
+        self.step_count = torch.zeros((), device=p.device, dtype=torch.float32)
+        self.param_groups = [{"params": [p], "lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay,
+                              "capturable": True}]
+
+    def zero_grad(self, set_to_none=False):
+        self.bucket.zero()
+
+    @torch.no_grad()
+    def step(self):
+        from . import _lib
+        g = self.param_groups[0]
+        p = self.bucket.flat_param
+        self.step_count.add_(1.0)
+        _lib.check(_lib.lib().dab_adam_flat(_lib.ptr(p.data), _lib.ptr(self.bucket.flat), _lib.ptr(self.exp_avg),
+                                            _lib.ptr(self.exp_avg_sq), _lib.ptr(self.step_count), float(g["lr"]),
+                                            float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                                            float(g["weight_decay"]), p.numel(), _lib.stream_ptr()), "dab_adam_flat")
+
+    def state_dict(self):
+        return {"step": self.step_count.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}]}
+
+    def load_state_dict(self, state):
+        self.step_count.copy_(state["step"]); self.exp_avg.copy_(state["exp_avg"]); self.exp_avg_sq.copy_(state["exp_avg_sq"])
+        self.param_groups[0].update(state["param_groups"][0])
 
 
 def ddp_step(loss_terms: Callable[[], "tuple[torch.Tensor, torch.Tensor]"], bucket: GradientBucket,

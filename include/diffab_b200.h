@@ -354,6 +354,11 @@ int dab_losses_fwd(const float* post_pred, const float* post_tgt, const float* e
 int dab_losses_bwd(const float* post_pred, const float* post_tgt, const float* eps_pred, const float* eps_tgt, const float* O_pred,
                    const float* O_true, const uint8_t* mask, int64_t n, const float* g, const float* fwd_out, float* d_post,
                    float* d_eps, float* d_O, void* stream);
+/* One Adam step (torch.optim.Adam semantics, the reference's configure_optimizers diffab_pytorch.py:925-931) on a FLAT fp32
+ * parameter vector: p, m, v [n] updated in place from the gradient g [n] (n % 4 == 0, 16-byte aligned); `step` = device
+ * scalar (float) with the step count including this step, incremented by the caller - no host state, graph-capturable. */
+int dab_adam_flat(float* p, const float* g, float* m, float* v, const float* step, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int64_t n, void* stream);
 
 /* The tcgen05 GEMM C[M,N] = A[M,K] B[N,K]^T + bias (bf16 in, fp32 out; M % 128 == 0, N % 64 == 0, K % 64 == 0): nn.Linear
  * (diffab_pytorch.py:464) as a stand-alone entry point. */

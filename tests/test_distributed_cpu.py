@@ -102,3 +102,31 @@ def test_graphed_step_rejects_a_non_capturable_optimizer():
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     with pytest.raises(ValueError, match="capturable"):
         dd.GraphedTrainStep(lambda: (model(torch.randn(4, 3)).pow(2).sum(), torch.tensor(4.0)), bucket, opt)
+
+
+def test_flat_parameter_optimizer_equals_the_per_tensor_one():
+    """GradientBucket.flatten_parameters: every parameter becomes a view of one flat buffer and an optimizer over that one
+    tensor (its gradient = the bucket) makes the per-tensor update, bit for bit; names and the state_dict are unchanged."""
+    torch.manual_seed(0)
+    ref = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+    flat = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+    flat.load_state_dict(ref.state_dict())
+    keys = list(flat.state_dict().keys())
+    bucket = dd.GradientBucket(flat.parameters())
+    fp = bucket.flatten_parameters()
+    assert list(flat.state_dict().keys()) == keys and fp.numel() == sum(p.numel() for p in ref.parameters())
+    assert all(torch.equal(a, b) for a, b in zip(flat.state_dict().values(), ref.state_dict().values()))
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-2, weight_decay=1e-3)
+    opt_flat = torch.optim.Adam([fp], lr=1e-2, weight_decay=1e-3)
+    for step in range(3):
+        x = torch.randn(6, 5)
+        opt_ref.zero_grad()
+        ref(x).pow(2).sum().backward()
+        opt_ref.step()
+        loss = dd.ddp_step(lambda: (flat(x).pow(2).sum(), torch.tensor(1.0)), bucket, opt_flat)
+        assert torch.isfinite(loss)
+    for (n, a), b in zip(flat.named_parameters(), ref.parameters()):
+        assert torch.equal(a, b), n
+    # a checkpoint loads in place: the views stay views of the flat buffer
+    flat.load_state_dict(ref.state_dict())
+    assert flat[0].weight.data_ptr() == fp.data_ptr()

@@ -607,3 +607,49 @@ def test_front_mlp_and_last_to_out_fused_into_their_neighbours_change_no_bit(B, 
             del ipa.fused_stack_applicable
     for a, b in zip(fused, plain):
         assert a.shape == b.shape and torch.isfinite(a).all() and torch.equal(a, b)
+
+
+def test_flat_adam_matches_torch_adam():
+    """distributed.FlatAdam (dab_adam_flat on GradientBucket.flatten_parameters()) against torch.optim.Adam on the separate
+    tensors: five steps with weight decay, eager and replayed from a CUDA graph (the step count lives on the device)."""
+    from diffab_pytorch_b200 import distributed as dd
+    torch.manual_seed(0)
+    ref = torch.nn.Sequential(torch.nn.Linear(64, 96), torch.nn.ReLU(), torch.nn.Linear(96, 32)).to(DEV)
+    flat = torch.nn.Sequential(torch.nn.Linear(64, 96), torch.nn.ReLU(), torch.nn.Linear(96, 32)).to(DEV)
+    flat.load_state_dict(ref.state_dict())
+    bucket = dd.GradientBucket(flat.parameters())
+    opt_flat = dd.FlatAdam(bucket, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2)
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2)
+    xs = [torch.randn(16, 64, device=DEV) for _ in range(5)]
+    for x in xs[:3]:
+        opt_ref.zero_grad()
+        ref(x).pow(2).sum().backward()
+        opt_ref.step()
+        bucket.rebind(); bucket.zero()
+        flat(x).pow(2).sum().backward()
+        opt_flat.step()
+    # two more steps with the optimizer step replayed from a graph
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    snap = (bucket.flat_param.data.clone(), opt_flat.exp_avg.clone(), opt_flat.exp_avg_sq.clone(), opt_flat.step_count.clone())
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        opt_flat.step()                      # warm-up outside the capture, undone below
+    torch.cuda.current_stream().wait_stream(side)
+    bucket.flat_param.data.copy_(snap[0]); opt_flat.exp_avg.copy_(snap[1]); opt_flat.exp_avg_sq.copy_(snap[2])
+    opt_flat.step_count.copy_(snap[3])
+    with torch.cuda.graph(graph):
+        opt_flat.step()
+    bucket.flat_param.data.copy_(snap[0]); opt_flat.exp_avg.copy_(snap[1]); opt_flat.exp_avg_sq.copy_(snap[2])
+    opt_flat.step_count.copy_(snap[3])
+    for x in xs[3:]:
+        opt_ref.zero_grad()
+        ref(x).pow(2).sum().backward()
+        opt_ref.step()
+        bucket.rebind(); bucket.zero()
+        flat(x).pow(2).sum().backward()
+        graph.replay()
+    assert float(opt_flat.step_count) == 5.0
+    for (n, a), b in zip(flat.named_parameters(), ref.parameters()):
+        err = float((a - b).abs().max() / b.abs().max())
+        assert err < 2e-6, (n, err)

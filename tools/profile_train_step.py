@@ -9,7 +9,7 @@ import torch
 import diffab_pytorch_b200  # noqa
 from diffab_pytorch_b200 import synth
 from diffab_pytorch_b200.diffab_pytorch import DiffAb
-from diffab_pytorch_b200.distributed import GradientBucket, GraphedTrainStep, diffab_loss_terms
+from diffab_pytorch_b200.distributed import FlatAdam, GradientBucket, GraphedTrainStep, diffab_loss_terms
 from torch.profiler import profile, ProfilerActivity
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
@@ -20,7 +20,7 @@ model.load_state_dict(synth.synthetic_state(shapes, seed=0))
 model.train_precision = "bf16"
 torch.set_float32_matmul_precision("high")   # as the reference's train.py:47
 bucket = GradientBucket(model.parameters())
-opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True, fused=True)
+opt = FlatAdam(bucket, lr=1e-4)
 batch = {k: v.to(dev) for k, v in synth.make_patches(B, 128, seed=2000, with_distmat=False).items()}
 batch["distmat"] = torch.cat([synth.pairwise_atom_distances(batch["xyz"][i:i + 8]) for i in range(0, B, 8)])
 graphed = GraphedTrainStep(lambda: diffab_loss_terms(model, batch), bucket, opt)
