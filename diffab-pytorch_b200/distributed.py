@@ -13,6 +13,8 @@ collective.  NCCL is used for exactly two things:
 Everything here takes a ``torch.distributed`` process group, so the same code runs on ``gloo``
 (CPU, used by the world_size-2 tests) and ``nccl``.
 """
+import os
+import warnings
 from typing import Callable, Dict, Iterable, Optional
 
 import torch
@@ -202,14 +204,17 @@ class GraphedTrainStep:
     Graph A: zero the gradient bucket, forward, backward of the local loss NUMERATOR.  Between the graphs, eagerly:
     all-reduce of the mask count and of the flat bucket (``world > 1``), division by the global count - the gradient of
     numerator / global_count, exactly what ``ddp_step`` back-propagates.  Graph B: ``optimizer.step()`` (the optimizer
-    must be constructed with ``capturable=True``).  With one rank everything is ONE graph.
+    must be constructed with ``capturable=True``).  With one rank everything is ONE graph; with
+    ``capture_collectives=True`` (or ``DAB_GRAPH_COLLECTIVES=1``) also with several ranks - the NCCL collectives are then
+    captured with the rest (measured on 2 GPUs: 4.416 ms against 4.422 ms: what the step pays for at N > 1 is the
+    all-reduce itself, not the hand-over between the graphs, so the two-graph form stays the default).
 
     The tensors of ``batch`` (and of ``t`` / ``noise`` when given) are the graphs' static inputs: refill them in
     place (``tensor.copy_``) for the next batch.  Random draws made inside the step (timesteps, noise) advance with
     every replay, as in eager mode.  Shapes are fixed by the capture."""
 
     def __init__(self, loss_terms: Callable[[], "tuple[torch.Tensor, torch.Tensor]"], bucket: GradientBucket,
-                 optimizer: torch.optim.Optimizer, group=None, warmup: int = 3):
+                 optimizer: torch.optim.Optimizer, group=None, warmup: int = 3, capture_collectives: Optional[bool] = None):
         self.bucket, self.optimizer, self.group = bucket, optimizer, group
         _, self.world = world_info(group)
         for pg in optimizer.param_groups:
@@ -227,18 +232,36 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         from . import _lib
-        self.graph_a = torch.cuda.CUDAGraph()
+        self.graph_a = None
         self.graph_b = None
+        if capture_collectives is None:
+            capture_collectives = os.environ.get("DAB_GRAPH_COLLECTIVES", "0") == "1"
         _lib.repack_when_capturing = True     # weight-derived buffers (packed bf16 weights) are rebuilt inside the graph
         try:
-            with torch.cuda.graph(self.graph_a):
-                self._backward_part()
-                if self.world == 1:
-                    self._reduce_part()
-                    optimizer.step()
+            if self.world > 1 and capture_collectives:
+                # The two NCCL all-reduces captured with the rest: the whole step is ONE graph on every rank.
+                # NCCL's watchdog thread may touch CUDA during the capture: thread-local capture mode keeps it legal.
+                try:
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                        self._backward_part()
+                        self._reduce_part()
+                        optimizer.step()
+                    self.graph_a, self.one_graph = graph, True
+                except Exception as exc:   # noqa: BLE001 - any capture failure: fall back to the two-graph form below
+                    warnings.warn(f"GraphedTrainStep: collectives not capturable here ({exc}); using two graphs")
+                    torch.cuda.synchronize()
+            if self.graph_a is None:
+                self.one_graph = self.world == 1
+                self.graph_a = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_a):
+                    self._backward_part()
+                    if self.world == 1:
+                        self._reduce_part()
+                        optimizer.step()
         finally:
             _lib.repack_when_capturing = False
-        if self.world > 1:
+        if not self.one_graph:
             self.graph_b = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
                 optimizer.step()
@@ -280,7 +303,7 @@ class GraphedTrainStep:
         from . import _lib
         _lib.bump_weight_generation()      # the replayed optimizer step changes weights without touching their versions
         self.graph_a.replay()
-        if self.world > 1:
+        if not self.one_graph:
             self._reduce_part()
             self.graph_b.replay()
         return self._loss
